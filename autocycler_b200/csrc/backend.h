@@ -1,0 +1,97 @@
+// Thin device abstraction for the k-mer pipeline.
+//
+// Product build (nvcc, sm_100a): kernels are functor bodies launched as grid-stride CUDA kernels, memory
+// is cudaMalloc'd HBM, atomics are the hardware atomics.
+//
+// AC_EMULATE build (g++, tests/emu only): the same functor bodies run serially on the host so that the
+// per-thread device logic can be exercised by the CPU test-suite in a container that has no GPU.  The
+// emulation library is test infrastructure; the product library never falls back to it.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#ifdef AC_EMULATE
+// ------------------------------------------------------------------------------------------------
+#define AC_HD inline
+#define AC_D inline
+
+template <class T> inline T ac_atomic_cas(T* p, T cmp, T val) { T old = *p; if (old == cmp) *p = val; return old; }
+template <class T> inline T ac_atomic_add(T* p, T v) { T old = *p; *p = (T)(old + v); return old; }
+template <class T> inline T ac_atomic_or(T* p, T v) { T old = *p; *p = (T)(old | v); return old; }
+template <class T> inline T ac_atomic_min(T* p, T v) { T old = *p; if (v < old) *p = v; return old; }
+template <class T> inline T ac_ld_volatile(const T* p) { return *p; }
+inline uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+
+struct AcStream { int dummy; };
+
+inline void* ac_dev_alloc(size_t bytes) { void* p = malloc(bytes ? bytes : 1); if (!p) throw std::runtime_error("emu alloc failed"); return p; }
+inline void ac_dev_free(void* p) { free(p); }
+inline void ac_memset(void* p, int v, size_t bytes, AcStream*) { memset(p, v, bytes); }
+inline void ac_h2d(void* d, const void* h, size_t bytes, AcStream*) { memcpy(d, h, bytes); }
+inline void ac_d2h(void* h, const void* d, size_t bytes, AcStream*) { memcpy(h, d, bytes); }
+inline void ac_sync(AcStream*) {}
+inline void* ac_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+inline void ac_host_free(void* p) { free(p); }
+
+template <class Body> inline void ac_launch(const char*, AcStream*, const Body& body, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i) body(i);
+}
+
+#else
+// ------------------------------------------------------------------------------------------------
+#include <cuda_runtime.h>
+
+#define AC_HD __host__ __device__ __forceinline__
+#define AC_D __device__ __forceinline__
+
+#define AC_CUDA_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) \
+    throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+
+AC_D uint64_t ac_atomic_cas(uint64_t* p, uint64_t cmp, uint64_t val) {
+    return (uint64_t)atomicCAS((unsigned long long*)p, (unsigned long long)cmp, (unsigned long long)val);
+}
+AC_D uint32_t ac_atomic_cas(uint32_t* p, uint32_t cmp, uint32_t val) { return atomicCAS(p, cmp, val); }
+AC_D uint32_t ac_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+AC_D uint64_t ac_atomic_add(uint64_t* p, uint64_t v) { return (uint64_t)atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+AC_D unsigned long long ac_atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+AC_D uint32_t ac_atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+AC_D uint32_t ac_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
+template <class T> AC_D T ac_ld_volatile(const T* p) { return *(const volatile T*)p; }
+AC_D uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
+
+struct AcStream { cudaStream_t s; };
+
+inline void* ac_dev_alloc(size_t bytes) { void* p = nullptr; AC_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1)); return p; }
+inline void ac_dev_free(void* p) { if (p) cudaFree(p); }
+inline void ac_memset(void* p, int v, size_t bytes, AcStream* st) { AC_CUDA_CHECK(cudaMemsetAsync(p, v, bytes, st->s)); }
+inline void ac_h2d(void* d, const void* h, size_t bytes, AcStream* st) { AC_CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st->s)); }
+inline void ac_d2h(void* h, const void* d, size_t bytes, AcStream* st) { AC_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st->s)); }
+inline void ac_sync(AcStream* st) { AC_CUDA_CHECK(cudaStreamSynchronize(st->s)); }
+inline void* ac_host_alloc(size_t bytes) { void* p = nullptr; AC_CUDA_CHECK(cudaMallocHost(&p, bytes ? bytes : 1)); return p; }
+inline void ac_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// Every functor-body kernel is launched through this one grid-stride template; the launch counter
+// feeds bench.py's "gpu_launches".
+extern unsigned long long g_ac_kernel_launches;
+
+template <class Body> __global__ void __launch_bounds__(256) ac_body_kernel(const Body body, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) body(i);
+}
+
+template <class Body> inline void ac_launch(const char* name, AcStream* st, const Body& body, uint64_t n) {
+    if (n == 0) return;
+    const int threads = 256;
+    uint64_t want = (n + threads - 1) / threads;
+    const uint64_t max_blocks = 148ull * 16;   // 148 SMs x up to 16 resident 256-thread CTAs, grid-stride beyond that
+    unsigned blocks = (unsigned)(want < max_blocks ? want : max_blocks);
+    ac_body_kernel<Body><<<blocks, threads, 0, st->s>>>(body, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("launch ") + name + ": " + cudaGetErrorString(e));
+    ++g_ac_kernel_launches;
+}
+#endif

@@ -1,0 +1,358 @@
+// extern "C" boundary of libautocycler_gpu.so (include/autocycler_gpu.h).  No exception leaves this file.
+#include "../../include/autocycler_gpu.h"
+
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "backend.h"
+#include "host_graph.h"
+#include "host_io.h"
+#include "pipeline.h"
+
+namespace {
+thread_local std::string g_error;
+
+struct NoDevice { std::string msg; };
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct PinnedBytes {     // host staging buffer for the concatenated padded strands (pinned, so the H2D copy is a DMA)
+    uint8_t* p = nullptr; size_t size = 0, cap = 0;
+    void append(const uint8_t* src, size_t n) {
+        if (size + n > cap) {
+            size_t ncap = std::max<size_t>(cap * 2, size + n + (1 << 20));
+            uint8_t* q = (uint8_t*)ac_host_alloc(ncap);
+            if (size) memcpy(q, p, size);
+            ac_host_free(p); p = q; cap = ncap;
+        }
+        memcpy(p + size, src, n); size += n;
+    }
+    void clear() { size = 0; }
+    ~PinnedBytes() { ac_host_free(p); }
+};
+}  // namespace
+
+struct ac_handle {
+    ac_config cfg{};
+    mutable std::string err;
+    std::vector<HostSeq> seqs;
+    std::vector<SeqInfo> infos;
+    PinnedBytes ascii;
+    LoadedInput loaded;                    // only when filled by ac_load_sequences (keeps the YAML details)
+    std::unique_ptr<DevicePipeline> pipe;
+    PipelineResult res;
+    HostGraph graph;
+    std::string gfa;
+    bool uploaded = false, built = false, gfa_ready = false;
+    ac_timings t{};
+    uint64_t links_now = 0;
+};
+
+static int set_error(const ac_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    g_error = msg;
+    return code;
+}
+
+#define AC_GUARD_BEGIN try {
+#define AC_GUARD_END(h) } catch (const InputError& e) { return set_error(h, AC_EINPUT, e.msg); } \
+    catch (const NoDevice& e) { return set_error(h, AC_ENODEVICE, e.msg); } \
+    catch (const std::bad_alloc&) { return set_error(h, AC_ERANGE, "out of host memory"); } \
+    catch (const std::exception& e) { std::string m = e.what(); \
+        int code = m.find("no CUDA device") != std::string::npos ? AC_ENODEVICE : (m.find("cuda") != std::string::npos ? AC_ECUDA : AC_EINVAL); \
+        return set_error(h, code, m); } \
+    catch (...) { return set_error(h, AC_EINVAL, "unknown error"); }
+
+extern "C" {
+
+const char* ac_last_error(const ac_handle* h) { return h ? h->err.c_str() : g_error.c_str(); }
+
+const char* ac_version(void) {
+#ifdef AC_EMULATE
+    return "autocycler_gpu 0.1 (host emulation build: tests only)";
+#else
+    return "autocycler_gpu 0.1 (sm_100a)";
+#endif
+}
+
+int ac_create(ac_handle** out, const ac_config* cfg) {
+    ac_handle* h = nullptr;
+    AC_GUARD_BEGIN
+    if (!out || !cfg) return set_error(nullptr, AC_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->k < 3 || (cfg->k & 1) == 0) return set_error(nullptr, AC_EINVAL, "--kmer must be odd");          // compress.rs:58
+    if (cfg->k > 64 * AC_MAX_W / 2 - 1)
+        return set_error(nullptr, AC_EINVAL, "k-mer sizes above 127 are not supported by the GPU path (there is no CPU fallback)");
+    h = new ac_handle;
+    h->cfg = *cfg;
+    h->pipe.reset(new DevicePipeline(cfg->device, cfg->stream));
+    *out = h;
+    return AC_OK;
+    AC_GUARD_END(((delete h), (ac_handle*)nullptr))
+}
+
+void ac_destroy(ac_handle* h) { delete h; }
+
+int ac_clear_sequences(ac_handle* h) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    h->seqs.clear(); h->infos.clear(); h->ascii.clear(); h->loaded = LoadedInput();
+    h->uploaded = h->built = h->gfa_ready = false;
+    return AC_OK;
+}
+
+int ac_add_sequence(ac_handle* h, uint16_t seq_id, const uint8_t* fwd, uint64_t n, const char* filename, const char* header) {
+    if (!h || !fwd) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    const uint32_t k = h->cfg.k, half = k / 2;
+    if (n < 2ull * k - 1) return set_error(h, AC_EINVAL, "padded sequence shorter than 2k-1 (contigs shorter than k are skipped by the caller, compress.rs:109)");
+    if (seq_id == 0 || seq_id > 32767) return set_error(h, AC_EINVAL, "sequence id must be in 1..32767 (position.rs:21)");
+    uint64_t lead = 0, trail = 0;
+    while (lead < n && fwd[lead] == '.') ++lead;
+    while (trail < n && fwd[n - 1 - trail] == '.') ++trail;
+    if (lead > half || trail > half) return set_error(h, AC_EINVAL, "more than k/2 padding dots at a sequence end");
+    for (uint64_t i = lead; i < n - trail; ++i) {
+        const uint8_t c = fwd[i];
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return set_error(h, AC_EINVAL, "sequence bytes must be ACGT with dots only at the ends");
+    }
+    if (n - (k - 1) > 0xFFFFFFFFull) return set_error(h, AC_ERANGE, "contig longer than Position.pos allows (position.rs:20)");
+    HostSeq s; s.id = seq_id; s.filename = filename ? filename : ""; s.contig_header = header ? header : "";
+    s.length = n - (k - 1); s.start = h->ascii.size;
+    SeqInfo info{}; info.start = s.start; info.len = (uint32_t)s.length; info.lead = (uint16_t)lead; info.trail = (uint16_t)trail; info.id = seq_id;
+    h->ascii.append(fwd, n);
+    h->seqs.push_back(std::move(s)); h->infos.push_back(info);
+    h->uploaded = h->built = h->gfa_ready = false;
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
+int ac_upload(ac_handle* h) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    AC_GUARD_BEGIN
+    if (h->seqs.empty()) return set_error(h, AC_EINPUT, "no sequences found in input assemblies");
+    h->pipe->upload(h->ascii.p, h->ascii.size, h->infos.data(), (uint32_t)h->infos.size(), h->cfg.k);
+    h->uploaded = true; h->built = h->gfa_ready = false;
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
+int ac_build(ac_handle* h) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    AC_GUARD_BEGIN
+    if (!h->uploaded) return set_error(h, AC_EINVAL, "ac_upload must precede ac_build");
+    h->pipe->build(h->res);
+    const double t0 = now_ms();
+    h->graph.build(h->res, h->seqs, h->ascii.p, h->cfg.k, h->cfg.keep_positions != 0);
+    h->graph.check_links();
+    const double t1 = now_ms();
+    const PipelineTimings& pt = h->res.t;
+    ac_timings& t = h->t;
+    t.h2d = pt.h2d; t.pack = pt.pack; t.insert = pt.insert; t.adjacency = pt.adjacency; t.boundaries = pt.boundaries; t.runs = pt.runs;
+    t.unitigs = pt.unitigs; t.links = pt.links; t.d2h = pt.d2h; t.device_total = pt.total;
+    t.host_graph = (float)(t1 - t0); t.host_simplify = 0; t.host_gfa = 0;
+    uint64_t windows = 0; for (auto& s : h->seqs) windows += s.length;
+    t.insert_occurrences = windows; t.table_capacity = h->res.capacity; t.table_used = h->res.n_slots_used;
+    t.kernel_launches = h->pipe->kernel_launches();
+    h->built = true; h->gfa_ready = false;
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
+int ac_simplify(ac_handle* h) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    AC_GUARD_BEGIN
+    if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_simplify");
+    const double t0 = now_ms();
+    h->graph.simplify_structure();
+    h->t.host_simplify = (float)(now_ms() - t0);
+    h->gfa_ready = false;
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
+int ac_counts_get(const ac_handle* h, ac_counts* out) {
+    if (!h || !out) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_counts_get");
+    memset(out, 0, sizeof *out);
+    out->n_kmers = 2 * h->res.n_slots_used;
+    out->n_unitigs = h->graph.units.size();
+    out->n_links = h->graph.link_count_single();
+    out->total_length = h->graph.total_length();
+    out->seq_bytes = out->total_length;
+    for (auto& u : h->graph.units) { out->n_fwd_pos += u.fpos.size(); out->n_rev_pos += u.rpos.size(); out->n_next += u.next[0].size() + u.next[1].size(); }
+    out->n_sequences = h->seqs.size();
+    for (auto& p : h->graph.paths) out->n_path_steps += p.size();
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
+int ac_unitigs_copy(const ac_handle* h, ac_unitigs* o) {
+    if (!h || !o) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_unitigs_copy");
+    const HostGraph& g = h->graph;
+    uint64_t so = 0, fo = 0, ro = 0, no = 0;
+    for (size_t n = 0; n < g.order.size(); ++n) {
+        const HostUnitig& u = g.units[g.order[n]];
+        if (o->number) o->number[n] = u.number;
+        if (o->depth) o->depth[n] = (double)u.depth;
+        if (o->seq_off) o->seq_off[n] = so;
+        if (o->seq) memcpy(o->seq + so, u.seq.data(), u.seq.size());
+        so += u.seq.size();
+        if (o->fpos_off) o->fpos_off[n] = fo;
+        if (o->rpos_off) o->rpos_off[n] = ro;
+        for (uint64_t v : u.fpos) { if (o->fpos) o->fpos[fo] = (uint32_t)(v >> 16); if (o->fpos_id_strand) o->fpos_id_strand[fo] = (uint16_t)(v & 0xFFFF); ++fo; }
+        for (uint64_t v : u.rpos) { if (o->rpos) o->rpos[ro] = (uint32_t)(v >> 16); if (o->rpos_id_strand) o->rpos_id_strand[ro] = (uint16_t)(v & 0xFFFF); ++ro; }
+        for (int s = 0; s < 2; ++s) {
+            if (o->next_off) o->next_off[2 * n + s] = no;
+            for (UStrand t : u.next[s]) { if (o->next) { int32_t num = (int32_t)g.units[us_index(t)].number; o->next[no] = us_reverse(t) ? -num : num; } ++no; }
+        }
+    }
+    const size_t U = g.order.size();
+    if (o->seq_off) o->seq_off[U] = so;
+    if (o->fpos_off) o->fpos_off[U] = fo;
+    if (o->rpos_off) o->rpos_off[U] = ro;
+    if (o->next_off) o->next_off[2 * U] = no;
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
+int ac_path_copy(const ac_handle* h, uint64_t seq_index, int32_t* out, uint64_t cap, uint64_t* n) {
+    if (!h || !n) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    if (!h->built || seq_index >= h->graph.paths.size()) return set_error(h, AC_EINVAL, "no such sequence");
+    const auto& p = h->graph.paths[seq_index];
+    *n = p.size();
+    if (!out) return AC_OK;
+    if (cap < p.size()) return set_error(h, AC_ERANGE, "path buffer too small");
+    for (size_t i = 0; i < p.size(); ++i) { int32_t num = (int32_t)h->graph.units[us_index(p[i])].number; out[i] = us_reverse(p[i]) ? -num : num; }
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
+int ac_gfa_size(ac_handle* h, uint64_t* n_bytes) {
+    if (!h || !n_bytes) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_gfa_size");
+    if (!h->gfa_ready) {
+        const double t0 = now_ms();
+        h->gfa = h->graph.gfa_text(h->seqs);
+        h->t.host_gfa = (float)(now_ms() - t0);
+        h->gfa_ready = true;
+    }
+    *n_bytes = h->gfa.size();
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
+int ac_gfa_copy(ac_handle* h, char* buf, uint64_t cap) {
+    uint64_t n = 0;
+    int rc = ac_gfa_size(h, &n);
+    if (rc != AC_OK) return rc;
+    if (!buf || cap < n) return set_error(h, AC_ERANGE, "GFA buffer too small");
+    memcpy(buf, h->gfa.data(), n);
+    return AC_OK;
+}
+
+int ac_timings_get(const ac_handle* h, ac_timings* out) {
+    if (!h || !out) return set_error(h, AC_EINVAL, "null argument");
+    *out = h->t;
+    out->kernel_launches = h->pipe->kernel_launches();
+    return AC_OK;
+}
+
+int ac_load_sequences(ac_handle* h, const char* dir, uint32_t max_contigs, uint32_t threads, uint64_t* assembly_count) {
+    if (!h || !dir) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    ac_clear_sequences(h);
+    LoadedInput in = load_sequences(dir, h->cfg.k, max_contigs, threads ? threads : 1, false);
+    for (size_t i = 0; i < in.seqs.size(); ++i) {
+        int rc = ac_add_sequence(h, in.seqs[i].id, (const uint8_t*)in.padded[i].data(), in.padded[i].size(),
+                                 in.seqs[i].filename.c_str(), in.seqs[i].contig_header.c_str());
+        if (rc != AC_OK) return rc;
+    }
+    if (assembly_count) *assembly_count = in.assembly_count;
+    in.padded.clear(); in.padded.shrink_to_fit();
+    h->loaded = std::move(in);
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
+int ac_sequence_get(const ac_handle* h, uint64_t index, uint16_t* seq_id, uint64_t* length, char* fwd, uint64_t cap_fwd,
+                    char* filename, uint64_t cap_fn, char* header, uint64_t cap_hd) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    if (index >= h->seqs.size()) return set_error(h, AC_EINVAL, "no such sequence");
+    const HostSeq& s = h->seqs[index];
+    const uint64_t padded = s.length + h->cfg.k - 1;
+    if (seq_id) *seq_id = s.id;
+    if (length) *length = s.length;
+    if (fwd) { if (cap_fwd < padded + 1) return set_error(h, AC_ERANGE, "buffer too small"); memcpy(fwd, h->ascii.p + s.start, padded); fwd[padded] = 0; }
+    if (filename) { if (cap_fn < s.filename.size() + 1) return set_error(h, AC_ERANGE, "buffer too small"); memcpy(filename, s.filename.c_str(), s.filename.size() + 1); }
+    if (header) { if (cap_hd < s.contig_header.size() + 1) return set_error(h, AC_ERANGE, "buffer too small"); memcpy(header, s.contig_header.c_str(), s.contig_header.size() + 1); }
+    return AC_OK;
+}
+
+int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint32_t k, uint32_t max_contigs, uint32_t threads,
+                    int32_t device, int32_t verbose) {
+    if (!assemblies_dir || !autocycler_dir) return set_error(nullptr, AC_EINVAL, "null argument");
+    ac_handle* h = nullptr;
+    AC_GUARD_BEGIN
+    // check_settings, compress.rs:53-62
+    struct stat st;
+    if (stat(assemblies_dir, &st) != 0) return set_error(nullptr, AC_EINPUT, std::string("directory does not exist: ") + assemblies_dir);
+    if (!S_ISDIR(st.st_mode)) return set_error(nullptr, AC_EINPUT, std::string(assemblies_dir) + " is not a directory");
+    if (stat(autocycler_dir, &st) == 0 && !S_ISDIR(st.st_mode)) return set_error(nullptr, AC_EINPUT, std::string(autocycler_dir) + " exists but is not a directory");
+    if (k < 11) return set_error(nullptr, AC_EINPUT, "--kmer cannot be less than 11");
+    if (k > 501) return set_error(nullptr, AC_EINPUT, "--kmer cannot be greater than 501");
+    if (k % 2 == 0) return set_error(nullptr, AC_EINPUT, "--kmer must be odd");
+    if (threads < 1) return set_error(nullptr, AC_EINPUT, "--threads cannot be less than 1");
+    if (threads > 100) return set_error(nullptr, AC_EINPUT, "--threads cannot be greater than 100");
+    ac_config cfg{}; cfg.k = k; cfg.device = device; cfg.stream = nullptr; cfg.keep_positions = 0;
+    int rc = ac_create(&h, &cfg);
+    if (rc != AC_OK) return rc;
+    std::unique_ptr<ac_handle, void (*)(ac_handle*)> guard(h, ac_destroy);
+    { std::string d = autocycler_dir; for (size_t i = 1; i <= d.size(); ++i) if (i == d.size() || d[i] == '/') mkdir(d.substr(0, i).c_str(), 0777); }   // create_dir_all
+    uint64_t assemblies = 0;
+    const double t0 = now_ms();
+    if ((rc = ac_load_sequences(h, assemblies_dir, max_contigs, threads, &assemblies)) != AC_OK) { g_error = h->err; return rc; }
+    const double t1 = now_ms();
+    if (verbose) fprintf(stderr, "%zu sequence%s loaded from %llu assembl%s\n\n", h->seqs.size(), h->seqs.size() == 1 ? "" : "s",
+                         (unsigned long long)assemblies, assemblies == 1 ? "y" : "ies");
+    if ((rc = ac_upload(h)) != AC_OK || (rc = ac_build(h)) != AC_OK) { g_error = h->err; return rc; }
+    ac_counts c{};
+    ac_counts_get(h, &c);
+    if (verbose) fprintf(stderr, "Graph contains %llu k-mers\n\n%llu unitig%s, %llu link%s\ntotal length: %llu bp\n\n", (unsigned long long)c.n_kmers,
+                         (unsigned long long)c.n_unitigs, c.n_unitigs == 1 ? "" : "s", (unsigned long long)c.n_links, c.n_links == 1 ? "" : "s",
+                         (unsigned long long)c.total_length);
+    if ((rc = ac_simplify(h)) != AC_OK) { g_error = h->err; return rc; }
+    ac_counts_get(h, &c);
+    if (verbose) fprintf(stderr, "%llu unitig%s, %llu link%s\ntotal length: %llu bp\n\n", (unsigned long long)c.n_unitigs, c.n_unitigs == 1 ? "" : "s",
+                         (unsigned long long)c.n_links, c.n_links == 1 ? "" : "s", (unsigned long long)c.total_length);
+    uint64_t n = 0;
+    if ((rc = ac_gfa_size(h, &n)) != AC_OK) { g_error = h->err; return rc; }
+    const std::string out_gfa = std::string(autocycler_dir) + "/input_assemblies.gfa", out_yaml = std::string(autocycler_dir) + "/input_assemblies.yaml";
+    FILE* f = fopen(out_gfa.c_str(), "wb");
+    if (!f || fwrite(h->gfa.data(), 1, h->gfa.size(), f) != h->gfa.size()) { if (f) fclose(f); return set_error(nullptr, AC_EIO, "cannot write " + out_gfa); }
+    fclose(f);
+    const std::string yaml = metrics_yaml(h->loaded, c.n_unitigs, c.total_length);
+    f = fopen(out_yaml.c_str(), "wb");
+    if (!f || fwrite(yaml.data(), 1, yaml.size(), f) != yaml.size()) { if (f) fclose(f); return set_error(nullptr, AC_EIO, "cannot write " + out_yaml); }
+    fclose(f);
+    if (verbose) {
+        const ac_timings& t = h->t;
+        fprintf(stderr, "Compressed unitig graph: %s\nInput assembly stats:    %s\n", out_gfa.c_str(), out_yaml.c_str());
+        fprintf(stderr, "load+repair %.1f ms | h2d %.2f pack %.2f insert %.2f adjacency %.2f boundaries %.2f runs %.2f unitigs %.2f links %.2f d2h %.2f ms"
+                        " | host graph %.1f simplify %.1f gfa %.1f ms | total %.1f ms\n\n",
+                t1 - t0, t.h2d, t.pack, t.insert, t.adjacency, t.boundaries, t.runs, t.unitigs, t.links, t.d2h, t.host_graph, t.host_simplify, t.host_gfa, now_ms() - t0);
+    }
+    return AC_OK;
+    AC_GUARD_END(nullptr)
+}
+
+}  // extern "C"

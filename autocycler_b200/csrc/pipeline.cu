@@ -1,0 +1,653 @@
+// Device pipeline: k-mer table build, adjacency, unitig occurrences ("runs"), unitig identity,
+// seed k-mers and links.  Every kernel is a functor body (backend.h); this file compiles with nvcc
+// for sm_100a (product) and with g++ -DAC_EMULATE (tests/emu, serial host execution of the same bodies).
+//
+// Order-free restatement of the reference's serial walk (unitig_graph.rs:176-226), see DESIGN.md §3:
+//   * per canonical k-mer: depth, first/last flags, node-centric in/out degree over ". A C G T"
+//   * an edge K->K' is merged iff outdeg(K)==1, !last(K), indeg(K')==1, !first(K'), K' != K, K' != rc(K)
+//   * unitigs are the maximal chains of merged edges; because every occurrence of a chain member is
+//     preceded/followed by its chain neighbours, the chains are exactly the maximal runs of merged
+//     edges ALONG THE INPUT SEQUENCES, so chain construction is a flag + scan over positions instead
+//     of list ranking over a hash table.
+#include "pipeline.h"
+
+#include <algorithm>
+#include <vector>
+
+#ifndef AC_EMULATE
+unsigned long long g_ac_kernel_launches = 0;
+#else
+static unsigned long long g_ac_kernel_launches = 0;
+#endif
+
+#define AC_NONE32 0xFFFFFFFFu
+#define AC_CHUNK 32            // windows per thread in the insert kernel
+#define AC_MINCHUNK 128        // windows per thread in the seed-k-mer kernel
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+struct TableView {
+    Slot* slots;
+    uint64_t cap;
+    const uint64_t* packed;
+    const SeqInfo* seqs;
+    uint32_t n_seqs;
+};
+
+template <int W> AC_D Key<W> window_key(const TableView& t, uint64_t g, bool dotted, const KParams& p) {
+    Key<W> key = fetch_codes<W>(t.packed, g, p);
+    if (dotted) {
+        const SeqInfo s = t.seqs[find_seq(t.seqs, t.n_seqs, g)];
+        key.d = window_dots(s, g - s.start, p.k);
+    }
+    return key;
+}
+
+// Find the slot holding k-mer `a` (whose reverse complement is `arc`), or AC_NONE32.
+template <int W> AC_D uint32_t table_find(const TableView& t, const Key<W>& a, const Key<W>& arc, const KParams& p) {
+    const Key<W>& canon = key_is_canonical(a, p) ? a : arc;
+    const uint64_t h = key_hash(canon);
+    const uint64_t tag = entry_tag(make_entry(0, a.d != 0, h));
+    uint64_t slot = ac_umul64hi(h, t.cap);
+    for (;;) {
+        const uint64_t e = t.slots[slot].entry;
+        if (e == AC_EMPTY_ENTRY) return AC_NONE32;
+        if (entry_tag(e) == tag) {
+            Key<W> rep = window_key<W>(t, entry_gpos(e), a.d != 0, p);
+            if (key_eq(rep, a) || key_eq(rep, arc)) return (uint32_t)slot;
+        }
+        if (++slot == t.cap) slot = 0;
+    }
+}
+
+// Calls f(succ, succ_rc) for every k-mer that could follow `a` (kmer_graph.rs:136-150): drop the first
+// symbol, append one of ". A C G T".  Combinations that would put a base after a dot, or dots on both
+// ends, cannot exist in the graph and are skipped.
+template <int W, class F> AC_D void for_each_successor(const Key<W>& a, const Key<W>& arc, bool any_dotted, const KParams& p, F&& f) {
+    if (a.d == 0) {
+        for (uint64_t x = 0; x < 4; ++x) {
+            Key<W> s = a, src = arc;
+            key_push_right(s, x, p); key_push_left(src, 3 - x, p);
+            f(s, src);
+        }
+        if (any_dotted) { Key<W> s = a; key_push_right(s, 0, p); s.d = -1; f(s, key_rc(s, p)); }
+    } else if (a.d > 0) {               // p leading dots -> p-1 leading dots, any base appended
+        for (uint64_t x = 0; x < 4; ++x) { Key<W> s = a; key_push_right(s, x, p); s.d = a.d - 1; f(s, key_rc(s, p)); }
+    } else {                            // trailing dots: only another dot can follow
+        Key<W> s = a; key_push_right(s, 0, p); s.d = a.d - 1; f(s, key_rc(s, p));
+    }
+}
+
+// Predecessors (kmer_graph.rs:152-166): drop the last symbol, prepend one of ". A C G T".
+template <int W, class F> AC_D void for_each_predecessor(const Key<W>& a, const Key<W>& arc, bool any_dotted, const KParams& p, F&& f) {
+    if (a.d == 0) {
+        for (uint64_t x = 0; x < 4; ++x) {
+            Key<W> s = a, src = arc;
+            key_push_left(s, x, p); key_push_right(src, 3 - x, p);
+            f(s, src);
+        }
+        if (any_dotted) { Key<W> s = a; key_push_left(s, 0, p); s.d = 1; f(s, key_rc(s, p)); }
+    } else if (a.d < 0) {               // s trailing dots -> s-1 trailing dots, any base prepended
+        for (uint64_t x = 0; x < 4; ++x) { Key<W> s = a; key_push_left(s, x, p); s.d = a.d + 1; f(s, key_rc(s, p)); }
+    } else {                            // leading dots: only another dot can precede
+        Key<W> s = a; key_push_left(s, 0, p); s.d = a.d + 1; f(s, key_rc(s, p));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel bodies
+// ------------------------------------------------------------------------------------------------
+// ASCII -> 2-bit packed, 32 bases per thread ('.' -> 0; the dot runs are described by SeqInfo).
+struct PackBody {
+    const uint8_t* ascii; uint64_t total; uint64_t* packed;
+    AC_D void operator()(uint64_t i) const {
+        uint64_t word = 0;
+        const uint64_t base = i * 32;
+        for (uint32_t j = 0; j < 32; ++j) {
+            const uint64_t g = base + j;
+            const uint64_t code = g < total ? base_code(ascii[g]) : 0;
+            word |= code << (62 - 2 * j);
+        }
+        packed[i] = word;
+    }
+};
+
+struct InitSlotsBody {
+    Slot* slots;
+    AC_D void operator()(uint64_t i) const { Slot s; s.entry = AC_EMPTY_ENTRY; s.count = 0; s.aux = 0; slots[i] = s; }
+};
+
+// kmer_graph.rs:92-134 add_sequence, both strands at once: one canonical entry per k-mer, count = depth.
+template <int W> struct InsertBody {
+    TableView t; KParams p; uint64_t total;
+    uint32_t* pos_slot;                 // [total] slot of the window starting at each global coordinate
+    unsigned long long* counters;       // [0] slots claimed, [1] dotted k-mers claimed
+    AC_D void insert(const Key<W>& fwd, const Key<W>& rc, uint64_t g, uint64_t fs, uint32_t len) const {
+        const bool canon_fwd = key_is_canonical(fwd, p);
+        const Key<W>& canon = canon_fwd ? fwd : rc;
+        const uint64_t h = key_hash(canon);
+        const bool dotted = fwd.d != 0;
+        const uint64_t mine = make_entry(g, dotted, h);
+        uint64_t slot = ac_umul64hi(h, t.cap);
+        for (;;) {
+            uint64_t e = ac_ld_volatile(&t.slots[slot].entry);
+            if (e == AC_EMPTY_ENTRY) {
+                e = ac_atomic_cas(&t.slots[slot].entry, (uint64_t)AC_EMPTY_ENTRY, mine);
+                if (e == AC_EMPTY_ENTRY) {
+                    ac_atomic_add(&counters[0], 1ull);
+                    if (dotted) ac_atomic_add(&counters[1], 1ull);
+                    break;
+                }
+            }
+            if (entry_tag(e) == entry_tag(mine)) {
+                Key<W> rep = window_key<W>(t, entry_gpos(e), dotted, p);
+                if (key_eq(rep, fwd) || key_eq(rep, rc)) break;
+            }
+            if (++slot == t.cap) slot = 0;
+        }
+        ac_atomic_add(&t.slots[slot].count, 1u);
+        // Kmer::first_position (kmer_graph.rs:57-60): position 0 of the forward strand is window 0; position 0
+        // of the reverse strand is the reverse complement of the last window (kmer_graph.rs:103-108).
+        uint32_t bits = 0;
+        if (fs == 0) bits |= canon_fwd ? AC_AUX_FIRST_CANON : AC_AUX_FIRST_RC;
+        if (fs + 1 == len) bits |= canon_fwd ? AC_AUX_FIRST_RC : AC_AUX_FIRST_CANON;
+        if (bits) ac_atomic_or(&t.slots[slot].aux, bits);
+        pos_slot[g] = (uint32_t)slot;
+    }
+    AC_D void operator()(uint64_t i) const {
+        uint64_t g = i * AC_CHUNK;
+        const uint64_t g1 = (g + AC_CHUNK < total) ? g + AC_CHUNK : total;
+        uint32_t si = find_seq(t.seqs, t.n_seqs, g);
+        while (g < g1) {
+            const SeqInfo s = t.seqs[si];
+            uint64_t fs = g - s.start;
+            if (fs >= s.len) {                       // inside the k-1 padded bytes that start no window
+                if (si + 1 >= t.n_seqs) return;
+                ++si;
+                if (t.seqs[si].start > g) g = t.seqs[si].start;
+                continue;
+            }
+            const uint64_t stop = (s.start + s.len < g1) ? s.start + s.len : g1;
+            Key<W> fwd, rc;
+            bool rolling = false;
+            for (; g < stop; ++g, ++fs) {
+                const int32_t d = window_dots(s, fs, p.k);
+                if (d != 0) {
+                    fwd = fetch_codes<W>(t.packed, g, p); fwd.d = d; rc = key_rc(fwd, p);
+                    rolling = false;
+                } else if (!rolling) {
+                    fwd = fetch_codes<W>(t.packed, g, p); rc = key_rc(fwd, p);
+                    rolling = true;
+                } else {
+                    const uint64_t code = packed_base(t.packed, g + p.k - 1);
+                    key_push_right(fwd, code, p); key_push_left(rc, 3 - code, p);
+                }
+                insert(fwd, rc, g, fs, s.len);
+            }
+        }
+    }
+};
+
+// Node-centric degrees (kmer_graph.rs:136-166) and the per-k-mer halves of the merge rule
+// (unitig_graph.rs:192-223): outOK(K) = outdeg(K)==1 && !first(rc K); inOK(K) = indeg(K)==1 && !first(K).
+template <int W> struct AdjacencyBody {
+    TableView t; KParams p; bool any_dotted; uint8_t* flags8;
+    AC_D void operator()(uint64_t i) const {
+        const uint64_t e = t.slots[i].entry;
+        if (e == AC_EMPTY_ENTRY) { flags8[i] = 0; return; }
+        const Key<W> f = window_key<W>(t, entry_gpos(e), entry_dotted(e), p);
+        const Key<W> r = key_rc(f, p);
+        uint32_t outdeg = 0, indeg = 0;
+        for_each_successor<W>(f, r, any_dotted, p, [&](const Key<W>& a, const Key<W>& arc) { if (table_find<W>(t, a, arc, p) != AC_NONE32) ++outdeg; });
+        for_each_predecessor<W>(f, r, any_dotted, p, [&](const Key<W>& a, const Key<W>& arc) { if (table_find<W>(t, a, arc, p) != AC_NONE32) ++indeg; });
+        const bool canon_fwd = key_is_canonical(f, p);
+        const uint32_t out_c = canon_fwd ? outdeg : indeg, in_c = canon_fwd ? indeg : outdeg;
+        const uint32_t aux = t.slots[i].aux;
+        uint32_t bits = 0;
+        if (out_c == 1 && !(aux & AC_AUX_FIRST_RC)) bits |= AC_AUX_OUT_OK;
+        if (in_c == 1 && !(aux & AC_AUX_FIRST_CANON)) bits |= AC_AUX_IN_OK;
+        t.slots[i].aux = aux | bits;
+        flags8[i] = (uint8_t)(bits >> 2);            // bit0 outOK, bit1 inOK (canonical orientation)
+    }
+};
+
+// One thread per 64 global coordinates: bit j set <=> a unitig occurrence starts at coordinate 64i+j,
+// i.e. it is window 0 of a sequence or the edge from the previous window is not merged.
+struct BoundaryBody {
+    const uint64_t* packed; const SeqInfo* seqs; uint32_t n_seqs; uint32_t h; uint64_t total;
+    const uint32_t* pos_slot; const uint8_t* flags8;
+    uint64_t* bmask; uint32_t* bcount;
+    AC_D void operator()(uint64_t i) const {
+        uint64_t g = i * 64;
+        const uint64_t g1 = (g + 64 < total) ? g + 64 : total;
+        uint64_t bits = 0;
+        uint32_t si = find_seq(seqs, n_seqs, g);
+        while (g < g1) {
+            const SeqInfo s = seqs[si];
+            uint64_t fs = g - s.start;
+            if (fs >= s.len) {
+                if (si + 1 >= n_seqs) break;
+                ++si;
+                if (seqs[si].start > g) g = seqs[si].start;
+                continue;
+            }
+            const uint64_t stop = (s.start + s.len < g1) ? s.start + s.len : g1;
+            uint32_t prev_slot = 0; bool prev_out = false;
+            if (fs > 0) {
+                prev_slot = pos_slot[g - 1];
+                const uint8_t fl = flags8[prev_slot];
+                const bool o = packed_base(packed, g - 1 + h) < 2;
+                prev_out = o ? (fl & 1) : (fl & 2);
+            }
+            for (; g < stop; ++g, ++fs) {
+                const uint32_t slot = pos_slot[g];
+                const uint8_t fl = flags8[slot];
+                const bool o = packed_base(packed, g + h) < 2;     // forward window is the stored orientation
+                const bool in_ok = o ? (fl & 2) : (fl & 1);
+                const bool merged = fs > 0 && prev_out && in_ok && slot != prev_slot;   // slot equality covers K'==K and K'==rc(K)
+                if (!merged) bits |= 1ull << (g & 63);
+                prev_slot = slot; prev_out = o ? (fl & 1) : (fl & 2);
+            }
+        }
+        bmask[i] = bits;
+#ifdef AC_EMULATE
+        bcount[i] = (uint32_t)__builtin_popcountll(bits);
+#else
+        bcount[i] = (uint32_t)__popcll(bits);
+#endif
+    }
+};
+
+struct RunScatterBody {
+    const uint64_t* bmask; const uint32_t* boff; uint64_t* run_start;
+    AC_D void operator()(uint64_t i) const {
+        uint64_t bits = bmask[i];
+        uint32_t off = boff[i];
+        while (bits) {
+#ifdef AC_EMULATE
+            const int b = __builtin_ctzll(bits);
+#else
+            const int b = __ffsll((long long)bits) - 1;
+#endif
+            run_start[off++] = i * 64 + (uint64_t)b;
+            bits &= bits - 1;
+        }
+    }
+};
+
+// Per occurrence: its extent and the identity of its unitig.  A unitig is named by the smaller of the
+// table slots of its two end k-mers (each canonical k-mer belongs to exactly one unitig); `dir` tells
+// from which end this occurrence reads it.  The smallest occurrence index becomes the representative.
+struct RunInfoBody {
+    const uint64_t* packed; const SeqInfo* seqs; uint32_t n_seqs; uint32_t h;
+    const uint64_t* run_start; uint64_t n_runs; const uint32_t* pos_slot;
+    uint32_t* run_len; uint32_t* run_uk; uint8_t* run_dir; uint32_t* uid_rep;
+    AC_D void operator()(uint64_t r) const {
+        const uint64_t g0 = run_start[r];
+        const SeqInfo s = seqs[find_seq(seqs, n_seqs, g0)];
+        const uint64_t seq_last = s.start + s.len - 1;
+        uint64_t g1 = seq_last;
+        if (r + 1 < n_runs && run_start[r + 1] <= seq_last) g1 = run_start[r + 1] - 1;
+        const uint32_t hs = pos_slot[g0], ts = pos_slot[g1];
+        const uint32_t uk = hs < ts ? hs : ts;
+        uint8_t dir;
+        if (hs != ts) dir = hs < ts ? 0 : 1;
+        else dir = packed_base(packed, g0 + h) < 2 ? 0 : 1;     // single k-mer: orientation of the window itself
+        run_len[r] = (uint32_t)(g1 - g0 + 1);
+        run_uk[r] = uk; run_dir[r] = dir;
+        ac_atomic_min(&uid_rep[uk], (uint32_t)r);
+    }
+};
+
+struct RepFlagBody {
+    const uint32_t* run_uk; const uint32_t* uid_rep; uint32_t* is_rep;
+    AC_D void operator()(uint64_t r) const { is_rep[r] = uid_rep[run_uk[r]] == (uint32_t)r ? 1u : 0u; }
+};
+
+struct RunAssignBody {
+    const uint64_t* run_start; const uint32_t* run_len; const uint32_t* run_uk; const uint8_t* run_dir;
+    const uint32_t* uid_rep; const uint32_t* rep_idx; const uint32_t* pos_slot; const Slot* slots;
+    uint32_t* run_unitig; DeviceUnitig* unitigs; uint32_t* slot_unitig;
+    AC_D void operator()(uint64_t r) const {
+        const uint32_t rep = uid_rep[run_uk[r]];
+        const uint32_t j = rep_idx[rep];
+        run_unitig[r] = (j << 1) | (run_dir[r] == run_dir[rep] ? 1u : 0u);
+        if (rep == (uint32_t)r) {
+            const uint64_t g0 = run_start[r]; const uint32_t len = run_len[r];
+            const uint32_t hs = pos_slot[g0], ts = pos_slot[g0 + len - 1];
+            DeviceUnitig u;
+            u.start = g0; u.len = len; u.depth = slots[hs].count; u.flip = 0; u.min_d = 0;
+            for (int w = 0; w < AC_MAX_W; ++w) u.min_w[w] = 0;
+            unitigs[j] = u;
+            slot_unitig[hs] = j; slot_unitig[ts] = j;
+        }
+    }
+};
+
+struct ChunkCountBody {
+    const DeviceUnitig* unitigs; uint32_t* nchunks;
+    AC_D void operator()(uint64_t j) const { nchunks[j] = (unitigs[j].len + AC_MINCHUNK - 1) / AC_MINCHUNK; }
+};
+
+template <int W> struct MinPartial { Key<W> key; uint32_t from_rc; };
+
+// Smallest k-mer (5-letter byte order) over both strands of AC_MINCHUNK consecutive windows of a unitig.
+template <int W> struct ChunkMinBody {
+    const uint64_t* packed; const SeqInfo* seqs; uint32_t n_seqs; KParams p;
+    const DeviceUnitig* unitigs; uint32_t n_unitigs; const uint32_t* chunk_off; MinPartial<W>* partial;
+    AC_D void operator()(uint64_t c) const {
+        uint32_t lo = 0, hi = n_unitigs;       // largest j with chunk_off[j] <= c
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (chunk_off[mid] <= c) lo = mid; else hi = mid; }
+        const DeviceUnitig u = unitigs[lo];
+        const uint64_t first = (c - chunk_off[lo]) * AC_MINCHUNK;
+        const uint64_t n = (u.len - first < AC_MINCHUNK) ? u.len - first : AC_MINCHUNK;
+        uint64_t g = u.start + first;
+        const SeqInfo s = seqs[find_seq(seqs, n_seqs, g)];
+        uint64_t fs = g - s.start;
+        Key<W> fwd, rc, best; bool rolling = false, have = false; uint32_t best_rc = 0;
+        for (uint64_t t = 0; t < n; ++t, ++g, ++fs) {
+            const int32_t d = window_dots(s, fs, p.k);
+            if (d != 0) { fwd = fetch_codes<W>(packed, g, p); fwd.d = d; rc = key_rc(fwd, p); rolling = false; }
+            else if (!rolling) { fwd = fetch_codes<W>(packed, g, p); rc = key_rc(fwd, p); rolling = true; }
+            else { const uint64_t code = packed_base(packed, g + p.k - 1); key_push_right(fwd, code, p); key_push_left(rc, 3 - code, p); }
+            if (!have || key_less5(fwd, best)) { best = fwd; best_rc = 0; have = true; }
+            if (key_less5(rc, best)) { best = rc; best_rc = 1; }
+        }
+        MinPartial<W> out; out.key = best; out.from_rc = best_rc;
+        partial[c] = out;
+    }
+};
+
+// The walk's seed is the smallest k-mer of both strands; the strand that holds it is the unitig's
+// forward strand (unitig_graph.rs:179-185: seeds are visited in sorted order, forward = the seed).
+template <int W> struct UnitigMinBody {
+    const uint32_t* chunk_off; const MinPartial<W>* partial; DeviceUnitig* unitigs;
+    AC_D void operator()(uint64_t j) const {
+        const uint32_t c0 = chunk_off[j], c1 = chunk_off[j + 1];
+        MinPartial<W> best = partial[c0];
+        for (uint32_t c = c0 + 1; c < c1; ++c) { const MinPartial<W> q = partial[c]; if (key_less5(q.key, best.key)) best = q; }
+        DeviceUnitig u = unitigs[j];
+        u.flip = best.from_rc; u.min_d = best.key.d;
+        for (int w = 0; w < W; ++w) u.min_w[w] = best.key.w[w];
+        unitigs[j] = u;
+    }
+};
+
+// unitig_graph.rs:234-287 create_links, as k-mer adjacency: the successors of a unitig strand's last k-mer
+// are the first k-mers of the linked unitig strands (overlap k-1 on the untrimmed sequences).
+template <int W> struct LinkBody {
+    TableView t; KParams p; bool any_dotted;
+    const DeviceUnitig* unitigs; const uint32_t* pos_slot; const uint32_t* slot_unitig;
+    uint32_t* link_count; uint32_t* links;
+    AC_D void operator()(uint64_t i) const {
+        const uint32_t j = (uint32_t)(i >> 1), e = (uint32_t)(i & 1);
+        const DeviceUnitig u = unitigs[j];
+        Key<W> tail, tail_rc;
+        if (e == 0) {
+            const uint64_t g = u.start + u.len - 1;
+            tail = fetch_codes<W>(t.packed, g, p);
+            const SeqInfo s = t.seqs[find_seq(t.seqs, t.n_seqs, g)];
+            tail.d = window_dots(s, g - s.start, p.k);
+            tail_rc = key_rc(tail, p);
+        } else {
+            const uint64_t g = u.start;
+            tail_rc = fetch_codes<W>(t.packed, g, p);
+            const SeqInfo s = t.seqs[find_seq(t.seqs, t.n_seqs, g)];
+            tail_rc.d = window_dots(s, g - s.start, p.k);
+            tail = key_rc(tail_rc, p);
+        }
+        uint32_t n = 0;
+        for_each_successor<W>(tail, tail_rc, any_dotted, p, [&](const Key<W>& a, const Key<W>& arc) {
+            const uint32_t s2 = table_find<W>(t, a, arc, p);
+            if (s2 == AC_NONE32) return;
+            const uint32_t j2 = slot_unitig[s2];
+            const DeviceUnitig v = unitigs[j2];
+            // `a` heads unitig j2 read in its representative direction iff it is the forward k-mer of v's first window
+            const bool a_canon = key_is_canonical(a, p);
+            const bool head_fwd = pos_slot[v.start] == s2 && ((packed_base(t.packed, v.start + p.h) < 2) == a_canon);
+            if (n < AC_MAX_LINKS) links[i * AC_MAX_LINKS + n] = (j2 << 1) | (head_fwd ? 0u : 1u);
+            ++n;
+        });
+        link_count[i] = n;
+    }
+};
+
+// 256-ary blocked exclusive scan built from serial per-thread pieces (volumes here are tiny: one
+// value per 64 coordinates or per unitig).  levels: sums[l+1][i] = sum of sums[l][256i .. 256i+255].
+struct ScanReduceBody {
+    const uint32_t* in; uint64_t n; uint32_t* sums;
+    AC_D void operator()(uint64_t i) const {
+        const uint64_t a = i * 256, b = (a + 256 < n) ? a + 256 : n;
+        uint32_t s = 0; for (uint64_t x = a; x < b; ++x) s += in[x];
+        sums[i] = s;
+    }
+};
+struct ScanApplyBody {
+    const uint32_t* in; uint64_t n; const uint32_t* block_off; uint32_t* out;
+    AC_D void operator()(uint64_t i) const {
+        const uint64_t a = i * 256, b = (a + 256 < n) ? a + 256 : n;
+        uint32_t s = block_off ? block_off[i] : 0;
+        for (uint64_t x = a; x < b; ++x) { const uint32_t v = in[x]; out[x] = s; s += v; }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    void ensure(size_t bytes) { if (bytes > cap) { ac_dev_free(p); p = nullptr; cap = 0; p = ac_dev_alloc(bytes); cap = bytes; } }
+    template <class T> T* as() { return (T*)p; }
+    ~DevBuf() { ac_dev_free(p); }
+};
+
+struct DevicePipeline::Impl {
+    int device = 0;
+    AcStream stream;
+    bool own_stream = false;
+    uint64_t total = 0; uint32_t n_seqs = 0, k = 0; int W = 0;
+    DevBuf ascii, packed, seqs, slots, pos_slot, flags8, bmask, bcount, boff, counters, uid_rep, slot_unitig;
+    DevBuf run_start, run_len, run_uk, run_dir, is_rep, rep_idx, run_unitig, unitigs, nchunks, chunk_off, partial, link_count, links;
+    DevBuf scan_tmp[4];
+#ifndef AC_EMULATE
+    cudaEvent_t ev[12];
+#endif
+
+    void mark(int i) {
+#ifndef AC_EMULATE
+        AC_CUDA_CHECK(cudaEventRecord(ev[i], stream.s));
+#else
+        (void)i;
+#endif
+    }
+    float between(int a, int b) {
+#ifndef AC_EMULATE
+        float ms = 0; AC_CUDA_CHECK(cudaEventElapsedTime(&ms, ev[a], ev[b])); return ms;
+#else
+        (void)a; (void)b; return 0.f;
+#endif
+    }
+
+    // exclusive scan of n uint32 values; returns the total.  out may alias in.
+    uint32_t exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, int level = 0) {
+        if (n == 0) return 0;
+        if (level >= 4) throw std::runtime_error("scan too deep");
+        const uint64_t nb = (n + 255) / 256;
+        scan_tmp[level].ensure((nb + 1) * sizeof(uint32_t));
+        uint32_t* sums = scan_tmp[level].as<uint32_t>();
+        ac_launch("scan_reduce", &stream, ScanReduceBody{in, n, sums}, nb);
+        uint32_t total_sum;
+        if (nb == 1) {
+            ac_d2h(&total_sum, sums, sizeof(uint32_t), &stream); ac_sync(&stream);
+            ac_launch("scan_apply", &stream, ScanApplyBody{in, n, nullptr, out}, nb);
+        } else {
+            total_sum = exclusive_scan(sums, sums, nb, level + 1);
+            ac_launch("scan_apply", &stream, ScanApplyBody{in, n, sums, out}, nb);
+        }
+        return total_sum;
+    }
+
+    template <int W> void build_w(PipelineResult& out);
+};
+
+DevicePipeline::DevicePipeline(int device, void* stream) : impl(new Impl) {
+    impl->device = device;
+#ifndef AC_EMULATE
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        throw std::runtime_error(std::string("autocycler_gpu: no CUDA device available (") + cudaGetErrorString(e) +
+                                 "); this library has no CPU path");
+    AC_CUDA_CHECK(cudaSetDevice(device));
+    if (stream) { impl->stream.s = (cudaStream_t)stream; }
+    else { AC_CUDA_CHECK(cudaStreamCreateWithFlags(&impl->stream.s, cudaStreamNonBlocking)); impl->own_stream = true; }
+    for (auto& ev : impl->ev) AC_CUDA_CHECK(cudaEventCreate(&ev));
+#else
+    (void)stream;
+#endif
+}
+
+DevicePipeline::~DevicePipeline() {
+#ifndef AC_EMULATE
+    cudaSetDevice(impl->device);
+    for (auto& ev : impl->ev) cudaEventDestroy(ev);
+#endif
+    Impl* p = impl; impl = nullptr;
+#ifndef AC_EMULATE
+    cudaStream_t s = p->stream.s; bool own = p->own_stream;
+    delete p;
+    if (own) cudaStreamDestroy(s);
+#else
+    delete p;
+#endif
+}
+
+unsigned long long DevicePipeline::kernel_launches() const { return g_ac_kernel_launches; }
+
+void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t k) {
+    Impl& m = *impl;
+#ifndef AC_EMULATE
+    AC_CUDA_CHECK(cudaSetDevice(m.device));
+#endif
+    if (k < 3 || (k & 1) == 0) throw std::runtime_error("k must be odd and >= 3");
+    const int W = (int)((2 * k + 63) / 64);
+    if (W > AC_MAX_W) throw std::runtime_error("k-mer sizes above 127 are not supported by the GPU path (no CPU fallback exists)");
+    if (total >= (1ull << 36)) throw std::runtime_error("more than 2^36 padded input bytes are not supported");
+    if (n_seqs == 0 || total == 0) throw std::runtime_error("no sequences");
+    m.total = total; m.n_seqs = n_seqs; m.k = k; m.W = W;
+    m.mark(0);
+    m.ascii.ensure(total);
+    ac_h2d(m.ascii.p, ascii, total, &m.stream);
+    m.seqs.ensure(n_seqs * sizeof(SeqInfo));
+    ac_h2d(m.seqs.p, seqs, n_seqs * sizeof(SeqInfo), &m.stream);
+    m.mark(1);
+}
+
+template <int W> void DevicePipeline::Impl::build_w(PipelineResult& out) {
+    const KParams p = make_kparams(k, W);
+    out = PipelineResult();
+    out.W = W;
+
+    // windows = total - n_seqs*(k-1); a canonical table can hold at most that many entries
+    const uint64_t n_windows = total - (uint64_t)n_seqs * (k - 1);
+    uint64_t cap = n_windows + n_windows / 2 + 64;
+    if (cap >= 0xFFFFFFF0ull) throw std::runtime_error("input too large for 32-bit slot indices");
+    out.capacity = cap;
+
+    // ---- pack ----
+    mark(2);
+    const uint64_t n_words = (total + 31) / 32;
+    packed.ensure((n_words + W + 2) * sizeof(uint64_t));
+    ac_memset(packed.as<uint64_t>() + n_words, 0, (W + 2) * sizeof(uint64_t), &stream);
+    ac_launch("pack", &stream, PackBody{ascii.as<uint8_t>(), total, packed.as<uint64_t>()}, n_words);
+    mark(3);
+
+    // ---- insert ----
+    slots.ensure(cap * sizeof(Slot));
+    ac_launch("init_slots", &stream, InitSlotsBody{slots.as<Slot>()}, cap);
+    pos_slot.ensure(total * sizeof(uint32_t));
+    counters.ensure(2 * sizeof(unsigned long long));
+    ac_memset(counters.p, 0, 2 * sizeof(unsigned long long), &stream);
+    TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
+    ac_launch("insert", &stream, InsertBody<W>{tv, p, total, pos_slot.as<uint32_t>(), counters.as<unsigned long long>()},
+              (total + AC_CHUNK - 1) / AC_CHUNK);
+    mark(4);
+    unsigned long long hc[2];
+    ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
+    out.n_slots_used = hc[0]; out.n_dotted = hc[1];
+    const bool any_dotted = hc[1] != 0;
+
+    // ---- adjacency ----
+    flags8.ensure(cap);
+    ac_launch("adjacency", &stream, AdjacencyBody<W>{tv, p, any_dotted, flags8.as<uint8_t>()}, cap);
+    mark(5);
+
+    // ---- unitig occurrences along the sequences ----
+    const uint64_t n_bwords = (total + 63) / 64;
+    bmask.ensure(n_bwords * sizeof(uint64_t)); bcount.ensure(n_bwords * sizeof(uint32_t)); boff.ensure(n_bwords * sizeof(uint32_t));
+    ac_launch("boundaries", &stream, BoundaryBody{packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, p.h, total, pos_slot.as<uint32_t>(),
+                                                  flags8.as<uint8_t>(), bmask.as<uint64_t>(), bcount.as<uint32_t>()}, n_bwords);
+    const uint64_t n_runs = exclusive_scan(bcount.as<uint32_t>(), boff.as<uint32_t>(), n_bwords);
+    mark(6);
+    run_start.ensure(n_runs * sizeof(uint64_t)); run_len.ensure(n_runs * 4); run_uk.ensure(n_runs * 4); run_dir.ensure(n_runs);
+    is_rep.ensure(n_runs * 4); rep_idx.ensure(n_runs * 4); run_unitig.ensure(n_runs * 4);
+    uid_rep.ensure(cap * 4); slot_unitig.ensure(cap * 4);
+    ac_memset(uid_rep.p, 0xFF, cap * 4, &stream);
+    ac_launch("run_scatter", &stream, RunScatterBody{bmask.as<uint64_t>(), boff.as<uint32_t>(), run_start.as<uint64_t>()}, n_bwords);
+    ac_launch("run_info", &stream, RunInfoBody{packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, p.h, run_start.as<uint64_t>(), n_runs, pos_slot.as<uint32_t>(),
+                                               run_len.as<uint32_t>(), run_uk.as<uint32_t>(), run_dir.as<uint8_t>(), uid_rep.as<uint32_t>()}, n_runs);
+    ac_launch("rep_flag", &stream, RepFlagBody{run_uk.as<uint32_t>(), uid_rep.as<uint32_t>(), is_rep.as<uint32_t>()}, n_runs);
+    const uint32_t n_unitigs = exclusive_scan(is_rep.as<uint32_t>(), rep_idx.as<uint32_t>(), n_runs);
+    unitigs.ensure((size_t)n_unitigs * sizeof(DeviceUnitig));
+    ac_launch("run_assign", &stream, RunAssignBody{run_start.as<uint64_t>(), run_len.as<uint32_t>(), run_uk.as<uint32_t>(), run_dir.as<uint8_t>(),
+                                                   uid_rep.as<uint32_t>(), rep_idx.as<uint32_t>(), pos_slot.as<uint32_t>(), slots.as<Slot>(),
+                                                   run_unitig.as<uint32_t>(), unitigs.as<DeviceUnitig>(), slot_unitig.as<uint32_t>()}, n_runs);
+    mark(7);
+
+    // ---- seed k-mer / orientation per unitig ----
+    nchunks.ensure(((size_t)n_unitigs + 1) * 4); chunk_off.ensure(((size_t)n_unitigs + 1) * 4);
+    ac_launch("chunk_count", &stream, ChunkCountBody{unitigs.as<DeviceUnitig>(), nchunks.as<uint32_t>()}, n_unitigs);
+    ac_memset(nchunks.as<uint32_t>() + n_unitigs, 0, 4, &stream);
+    const uint32_t n_chunks = exclusive_scan(nchunks.as<uint32_t>(), chunk_off.as<uint32_t>(), (uint64_t)n_unitigs + 1);
+    partial.ensure((size_t)n_chunks * sizeof(MinPartial<W>));
+    ac_launch("chunk_min", &stream, ChunkMinBody<W>{packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, p, unitigs.as<DeviceUnitig>(), n_unitigs,
+                                                    chunk_off.as<uint32_t>(), partial.as<MinPartial<W>>()}, n_chunks);
+    ac_launch("unitig_min", &stream, UnitigMinBody<W>{chunk_off.as<uint32_t>(), partial.as<MinPartial<W>>(), unitigs.as<DeviceUnitig>()}, n_unitigs);
+    mark(8);
+
+    // ---- links ----
+    link_count.ensure((size_t)n_unitigs * 2 * 4); links.ensure((size_t)n_unitigs * 2 * AC_MAX_LINKS * 4);
+    ac_launch("links", &stream, LinkBody<W>{tv, p, any_dotted, unitigs.as<DeviceUnitig>(), pos_slot.as<uint32_t>(), slot_unitig.as<uint32_t>(),
+                                            link_count.as<uint32_t>(), links.as<uint32_t>()}, (uint64_t)n_unitigs * 2);
+    mark(9);
+
+    // ---- results to the host ----
+    out.unitigs.resize(n_unitigs); out.link_count.resize((size_t)n_unitigs * 2); out.links.resize((size_t)n_unitigs * 2 * AC_MAX_LINKS);
+    out.run_start.resize(n_runs); out.run_len.resize(n_runs); out.run_unitig.resize(n_runs);
+    ac_d2h(out.unitigs.data(), unitigs.p, (size_t)n_unitigs * sizeof(DeviceUnitig), &stream);
+    ac_d2h(out.link_count.data(), link_count.p, out.link_count.size() * 4, &stream);
+    ac_d2h(out.links.data(), links.p, out.links.size() * 4, &stream);
+    ac_d2h(out.run_start.data(), run_start.p, n_runs * sizeof(uint64_t), &stream);
+    ac_d2h(out.run_len.data(), run_len.p, n_runs * 4, &stream);
+    ac_d2h(out.run_unitig.data(), run_unitig.p, n_runs * 4, &stream);
+    mark(10);
+    ac_sync(&stream);
+    out.t.h2d = between(0, 1); out.t.pack = between(2, 3); out.t.insert = between(3, 4); out.t.adjacency = between(4, 5);
+    out.t.boundaries = between(5, 6); out.t.runs = between(6, 7); out.t.unitigs = between(7, 8); out.t.links = between(8, 9);
+    out.t.d2h = between(9, 10); out.t.total = between(2, 10);
+}
+
+void DevicePipeline::build(PipelineResult& out) {
+    Impl& m = *impl;
+#ifndef AC_EMULATE
+    AC_CUDA_CHECK(cudaSetDevice(m.device));
+#endif
+    switch (m.W) {
+        case 1: m.build_w<1>(out); break;
+        case 2: m.build_w<2>(out); break;
+        case 3: m.build_w<3>(out); break;
+        case 4: m.build_w<4>(out); break;
+        default: throw std::runtime_error("upload() must precede build()");
+    }
+}

@@ -1,0 +1,121 @@
+/* autocycler_gpu.h — C ABI of libautocycler_gpu.so, the B200 implementation of Autocycler's
+ * `compress` hot path.
+ *
+ * The reference (rrwick/Autocycler v0.6.1, Rust) has no FFI for this path; the path sits behind
+ * in-crate calls.  Each entry point below names the reference interface it replaces (file:line
+ * under the reference's src/), so that a Rust `extern "C"` shim can bind them in
+ * place of those calls:
+ *
+ *   KmerGraph::new + add_sequences          kmer_graph.rs:79-90      -> ac_create, ac_add_sequence, ac_upload
+ *   UnitigGraph::from_kmer_graph            unitig_graph.rs:36-48    -> ac_build
+ *   (the UnitigGraph / Unitig fields)       unitig_graph.rs:28-33, unitig.rs:30-45 -> ac_counts_get, ac_unitigs_copy
+ *   simplify_structure                      graph_simplification.rs:26-40 -> ac_simplify
+ *   UnitigGraph::save_gfa                   unitig_graph.rs:317-331  -> ac_gfa_size, ac_gfa_copy
+ *   compress (the whole subcommand)         compress.rs:32-50        -> ac_compress_dir
+ *
+ * Conventions: every function returns 0 on success and a negative AC_E* code on failure; the message
+ * is available from ac_last_error(handle) (or ac_last_error(NULL) when no handle exists).  No C++
+ * exception crosses the boundary.  The caller owns every buffer it passes; inputs are copied during
+ * the call; outputs are written into caller-allocated buffers sized from ac_counts_get / ac_gfa_size.
+ * A handle must be used from one host thread at a time (the reference path is single-threaded and
+ * !Send).  There is no CPU fallback: without a CUDA device ac_create fails with AC_ENODEVICE.
+ */
+#ifndef AUTOCYCLER_GPU_H
+#define AUTOCYCLER_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AC_OK 0
+#define AC_EINVAL (-1)      /* bad argument (even k, k out of range, non-ACGT. byte, call order) */
+#define AC_ENODEVICE (-2)   /* no usable CUDA device */
+#define AC_ECUDA (-3)       /* CUDA runtime error */
+#define AC_ERANGE (-4)      /* buffer too small / input too large */
+#define AC_EIO (-5)         /* file system error (ac_compress_dir) */
+#define AC_EINPUT (-6)      /* the reference's own input errors (misc.rs:130-136 quit_with_error) */
+
+typedef struct ac_handle ac_handle;
+
+typedef struct {
+    uint32_t k;             /* odd; 3..127 on the GPU path (compress.rs:56-58 restricts the CLI to 11..501) */
+    int32_t device;         /* CUDA device ordinal */
+    void* stream;           /* cudaStream_t to run on, or NULL for a private stream */
+    uint32_t keep_positions;/* non-zero: ac_unitigs_copy can return full forward/reverse position lists */
+} ac_config;
+
+typedef struct {
+    uint64_t n_kmers;       /* both strands == KmerGraph.kmers.len() printed at compress.rs:152 */
+    uint64_t n_unitigs;
+    uint64_t n_links;       /* UnitigGraph::link_count().1 (unitig_graph.rs:478-507) */
+    uint64_t total_length;  /* UnitigGraph::total_length (unitig_graph.rs:474-476) */
+    uint64_t seq_bytes;     /* sum of unitig sequence lengths for ac_unitigs_copy (trimmed) */
+    uint64_t n_fwd_pos, n_rev_pos;   /* total entries of forward_positions / reverse_positions */
+    uint64_t n_next;        /* total entries of forward_next + reverse_next */
+    uint64_t n_sequences;
+    uint64_t n_path_steps;  /* sum of path lengths over all sequences */
+} ac_counts;
+
+/* Unitigs in the graph's current order (after ac_build: the order renumber_unitigs gives, numbers 1..U).
+ * All arrays are caller-allocated from ac_counts; offsets arrays have n_unitigs+1 entries. */
+typedef struct {
+    uint32_t* number;       /* [U] Unitig.number */
+    uint64_t* seq_off;      /* [U+1] */
+    uint8_t* seq;           /* [seq_bytes] forward_seq, ASCII */
+    double* depth;          /* [U] Unitig.depth */
+    uint64_t* fpos_off;     /* [U+1]; positions need ac_config.keep_positions, else pass NULL */
+    uint32_t* fpos;         /* [n_fwd_pos] Position.pos (position.rs:20) */
+    uint16_t* fpos_id_strand; /* [n_fwd_pos] Position.seq_id_and_strand (position.rs:21; bit 15 = forward strand) */
+    uint64_t* rpos_off; uint32_t* rpos; uint16_t* rpos_id_strand;
+    uint64_t* next_off;     /* [2U+1] forward_next of unitig i at 2i, reverse_next at 2i+1 */
+    int32_t* next;          /* [n_next] signed unitig numbers, negative = reverse strand (UnitigStrand::signed_number) */
+} ac_unitigs;
+
+typedef struct {            /* milliseconds */
+    float h2d, pack, insert, adjacency, boundaries, runs, unitigs, links, d2h, device_total;
+    float host_graph, host_simplify, host_gfa;
+    uint64_t insert_occurrences;   /* k-mer occurrences hashed by the insert kernel (forward windows; each feeds both strands) */
+    uint64_t table_capacity, table_used;
+    uint64_t kernel_launches;      /* cumulative launches of this library's kernels in the process */
+} ac_timings;
+
+const char* ac_last_error(const ac_handle* h);
+const char* ac_version(void);
+
+int ac_create(ac_handle** out, const ac_config* cfg);
+void ac_destroy(ac_handle* h);
+
+/* One padded, end-repaired forward strand (Sequence.forward_seq after compress.rs:125, bytes in "ACGT.",
+ * k/2 dots or repaired bases at both ends) with the fields save_gfa prints (unitig_graph.rs:352-360). */
+int ac_add_sequence(ac_handle* h, uint16_t seq_id, const uint8_t* fwd_padded, uint64_t padded_len,
+                    const char* filename, const char* contig_header);
+int ac_clear_sequences(ac_handle* h);
+int ac_upload(ac_handle* h);            /* host -> HBM copy of the added sequences */
+int ac_build(ac_handle* h);             /* k-mer table, unitigs, links, renumber: the graph after from_kmer_graph */
+int ac_simplify(ac_handle* h);          /* simplify_structure */
+int ac_counts_get(const ac_handle* h, ac_counts* out);
+int ac_unitigs_copy(const ac_handle* h, ac_unitigs* out);
+int ac_path_copy(const ac_handle* h, uint64_t seq_index, int32_t* out, uint64_t cap, uint64_t* n);  /* get_unitig_path_for_sequence_i32 */
+int ac_gfa_size(ac_handle* h, uint64_t* n_bytes);
+int ac_gfa_copy(ac_handle* h, char* buf, uint64_t cap);
+int ac_timings_get(const ac_handle* h, ac_timings* out);
+
+/* `autocycler compress -i assemblies_dir -a autocycler_dir --kmer k --max_contigs m -t threads`
+ * (main.rs:126-147, compress.rs:32-50): writes input_assemblies.gfa and input_assemblies.yaml. */
+int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint32_t k, uint32_t max_contigs,
+                    uint32_t threads, int32_t device, int32_t verbose);
+
+/* Host-side stage A of compress (compress.rs:98-133): directory scan, FASTA load, padding, end repair.
+ * Fills a handle created with the same k, ready for ac_upload.  Returns the number of assemblies. */
+int ac_load_sequences(ac_handle* h, const char* assemblies_dir, uint32_t max_contigs, uint32_t threads,
+                      uint64_t* assembly_count);
+/* Read back one loaded sequence (for tests of stage A): padded forward strand and header fields. */
+int ac_sequence_get(const ac_handle* h, uint64_t index, uint16_t* seq_id, uint64_t* length,
+                    char* fwd_padded, uint64_t cap_fwd, char* filename, uint64_t cap_fn, char* header, uint64_t cap_hd);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
