@@ -46,12 +46,18 @@ template <class Body> inline void ac_launch(const char*, AcStream*, const Body& 
 // ------------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
 
+#ifdef __CUDACC__
 #define AC_HD __host__ __device__ __forceinline__
 #define AC_D __device__ __forceinline__
+#else   // host translation units of the product build only see the host-callable part
+#define AC_HD inline
+#define AC_D inline
+#endif
 
 #define AC_CUDA_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) \
     throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
 
+#ifdef __CUDACC__
 AC_D uint64_t ac_atomic_cas(uint64_t* p, uint64_t cmp, uint64_t val) {
     return (uint64_t)atomicCAS((unsigned long long*)p, (unsigned long long)cmp, (unsigned long long)val);
 }
@@ -63,6 +69,7 @@ AC_D uint32_t ac_atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
 AC_D uint32_t ac_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 template <class T> AC_D T ac_ld_volatile(const T* p) { return *(const volatile T*)p; }
 AC_D uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
+#endif
 
 struct AcStream { cudaStream_t s; };
 
@@ -75,6 +82,7 @@ inline void ac_sync(AcStream* st) { AC_CUDA_CHECK(cudaStreamSynchronize(st->s));
 inline void* ac_host_alloc(size_t bytes) { void* p = nullptr; AC_CUDA_CHECK(cudaMallocHost(&p, bytes ? bytes : 1)); return p; }
 inline void ac_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+#ifdef __CUDACC__
 // Every functor-body kernel is launched through this one grid-stride template; the launch counter
 // feeds bench.py's "gpu_launches".
 extern unsigned long long g_ac_kernel_launches;
@@ -94,4 +102,5 @@ template <class Body> inline void ac_launch(const char* name, AcStream* st, cons
     if (e != cudaSuccess) throw std::runtime_error(std::string("launch ") + name + ": " + cudaGetErrorString(e));
     ++g_ac_kernel_launches;
 }
+#endif   // __CUDACC__
 #endif

@@ -158,6 +158,7 @@ int ac_build(ac_handle* h) {
     uint64_t windows = 0; for (auto& s : h->seqs) windows += s.length;
     t.insert_occurrences = windows; t.table_capacity = h->res.capacity; t.table_used = h->res.n_slots_used;
     t.kernel_launches = h->pipe->kernel_launches();
+    t.h2d_bytes = h->res.h2d_bytes; t.d2h_bytes = h->res.d2h_bytes;
     h->built = true; h->gfa_ready = false;
     return AC_OK;
     AC_GUARD_END(h)

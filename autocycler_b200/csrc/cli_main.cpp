@@ -1,0 +1,43 @@
+// `autocycler compress` with the reference's flags (main.rs:126-147), messages and exit codes
+// (misc.rs:130-136: "Error: <text>" on stderr, exit 1), running the B200 path through the C ABI.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/autocycler_gpu.h"
+
+static void usage() {
+    fprintf(stderr,
+            "Usage: autocycler compress --assemblies_dir <ASSEMBLIES_DIR> --autocycler_dir <AUTOCYCLER_DIR> [OPTIONS]\n\n"
+            "Options:\n"
+            "  -i, --assemblies_dir <DIR>   Directory containing input assemblies (required)\n"
+            "  -a, --autocycler_dir <DIR>   Autocycler directory to be created (required)\n"
+            "      --kmer <KMER>            K-mer size for De Bruijn graph [default: 51]\n"
+            "      --max_contigs <N>        refuse to run if mean contigs per assembly exceeds this value [default: 25]\n"
+            "  -t, --threads <THREADS>      Number of CPU threads (end repair) [default: 8]\n"
+            "      --device <ORDINAL>       CUDA device [default: 0]\n");
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2 || strcmp(argv[1], "compress") != 0) { usage(); return 2; }
+    std::string in, out; unsigned k = 51, max_contigs = 25, threads = 8; int device = 0;
+    for (int i = 2; i < argc; ++i) {
+        std::string a = argv[i];
+        auto value = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "error: a value is required for '%s'\n", a.c_str()); exit(2); } return argv[++i]; };
+        if (a == "-i" || a == "--assemblies_dir") in = value();
+        else if (a == "-a" || a == "--autocycler_dir") out = value();
+        else if (a == "--kmer") k = (unsigned)strtoul(value(), nullptr, 10);
+        else if (a == "--max_contigs") max_contigs = (unsigned)strtoul(value(), nullptr, 10);
+        else if (a == "-t" || a == "--threads") threads = (unsigned)strtoul(value(), nullptr, 10);
+        else if (a == "--device") device = atoi(value());
+        else if (a == "-h" || a == "--help") { usage(); return 0; }
+        else { fprintf(stderr, "error: unexpected argument '%s'\n", a.c_str()); usage(); return 2; }
+    }
+    if (in.empty() || out.empty()) { usage(); return 2; }
+    fprintf(stderr, "\nStarting autocycler compress (%s)\n\nSettings:\n  --assemblies_dir %s\n  --autocycler_dir %s\n  --kmer %u\n  --threads %u\n\n",
+            ac_version(), in.c_str(), out.c_str(), k, threads);
+    int rc = ac_compress_dir(in.c_str(), out.c_str(), k, max_contigs, threads, device, 1);
+    if (rc != AC_OK) { fprintf(stderr, "\nError: %s\n", ac_last_error(nullptr)); return 1; }
+    return 0;
+}

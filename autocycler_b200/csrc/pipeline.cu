@@ -63,7 +63,7 @@ template <int W> AC_D uint32_t table_find(const TableView& t, const Key<W>& a, c
 
 // Calls f(succ, succ_rc) for every k-mer that could follow `a` (kmer_graph.rs:136-150): drop the first
 // symbol, append one of ". A C G T".  Combinations that would put a base after a dot, or dots on both
-// ends, cannot exist in the graph and are skipped.
+// ends (impossible because every contig has L >= k), cannot exist in the graph and are skipped.
 template <int W, class F> AC_D void for_each_successor(const Key<W>& a, const Key<W>& arc, bool any_dotted, const KParams& p, F&& f) {
     if (a.d == 0) {
         for (uint64_t x = 0; x < 4; ++x) {
@@ -74,6 +74,7 @@ template <int W, class F> AC_D void for_each_successor(const Key<W>& a, const Ke
         if (any_dotted) { Key<W> s = a; key_push_right(s, 0, p); s.d = -1; f(s, key_rc(s, p)); }
     } else if (a.d > 0) {               // p leading dots -> p-1 leading dots, any base appended
         for (uint64_t x = 0; x < 4; ++x) { Key<W> s = a; key_push_right(s, x, p); s.d = a.d - 1; f(s, key_rc(s, p)); }
+        if (a.d == 1) { Key<W> s = a; key_push_right(s, 0, p); s.d = -1; f(s, key_rc(s, p)); }   // ".X" -> "X." (k-1 bases then a dot)
     } else {                            // trailing dots: only another dot can follow
         Key<W> s = a; key_push_right(s, 0, p); s.d = a.d - 1; f(s, key_rc(s, p));
     }
@@ -90,6 +91,7 @@ template <int W, class F> AC_D void for_each_predecessor(const Key<W>& a, const 
         if (any_dotted) { Key<W> s = a; key_push_left(s, 0, p); s.d = 1; f(s, key_rc(s, p)); }
     } else if (a.d < 0) {               // s trailing dots -> s-1 trailing dots, any base prepended
         for (uint64_t x = 0; x < 4; ++x) { Key<W> s = a; key_push_left(s, x, p); s.d = a.d + 1; f(s, key_rc(s, p)); }
+        if (a.d == -1) { Key<W> s = a; key_push_left(s, 0, p); s.d = 1; f(s, key_rc(s, p)); }    // "X." <- ".X"
     } else {                            // leading dots: only another dot can precede
         Key<W> s = a; key_push_left(s, 0, p); s.d = a.d + 1; f(s, key_rc(s, p));
     }
@@ -345,7 +347,7 @@ template <int W> struct ChunkMinBody {
         uint64_t g = u.start + first;
         const SeqInfo s = seqs[find_seq(seqs, n_seqs, g)];
         uint64_t fs = g - s.start;
-        Key<W> fwd, rc, best; bool rolling = false, have = false; uint32_t best_rc = 0;
+        Key<W> fwd, rc, best = Key<W>(); bool rolling = false, have = false; uint32_t best_rc = 0;
         for (uint64_t t = 0; t < n; ++t, ++g, ++fs) {
             const int32_t d = window_dots(s, fs, p.k);
             if (d != 0) { fwd = fetch_codes<W>(packed, g, p); fwd.d = d; rc = key_rc(fwd, p); rolling = false; }
@@ -631,6 +633,8 @@ template <int W> void DevicePipeline::Impl::build_w(PipelineResult& out) {
     ac_d2h(out.run_start.data(), run_start.p, n_runs * sizeof(uint64_t), &stream);
     ac_d2h(out.run_len.data(), run_len.p, n_runs * 4, &stream);
     ac_d2h(out.run_unitig.data(), run_unitig.p, n_runs * 4, &stream);
+    out.d2h_bytes = (uint64_t)n_unitigs * sizeof(DeviceUnitig) + out.link_count.size() * 4 + out.links.size() * 4 + n_runs * 16 + 2 * sizeof(unsigned long long) + 3 * sizeof(uint32_t);
+    out.h2d_bytes = total + (uint64_t)n_seqs * sizeof(SeqInfo);
     mark(10);
     ac_sync(&stream);
     out.t.h2d = between(0, 1); out.t.pack = between(2, 3); out.t.insert = between(3, 4); out.t.adjacency = between(4, 5);

@@ -29,6 +29,7 @@ struct PipelineResult {
     uint64_t n_slots_used = 0;                 // distinct canonical k-mers; KmerGraph.kmers.len() == 2x this
     uint64_t capacity = 0;
     uint64_t n_dotted = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;     // bytes copied host->device by upload() and device->host by build()
     std::vector<DeviceUnitig> unitigs;         // in representative-occurrence order (not yet seed order)
     std::vector<uint32_t> link_count;          // [2*U]   index 2j+e, e=0: strand of the representative occurrence, e=1: its reverse
     std::vector<uint32_t> links;               // [2*U*AC_MAX_LINKS] targets as 2j'+e'

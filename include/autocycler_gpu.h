@@ -79,6 +79,7 @@ typedef struct {            /* milliseconds */
     uint64_t insert_occurrences;   /* k-mer occurrences hashed by the insert kernel (forward windows; each feeds both strands) */
     uint64_t table_capacity, table_used;
     uint64_t kernel_launches;      /* cumulative launches of this library's kernels in the process */
+    uint64_t h2d_bytes, d2h_bytes; /* bytes moved by ac_upload / ac_build */
 } ac_timings;
 
 const char* ac_last_error(const ac_handle* h);

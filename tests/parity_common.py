@@ -1,0 +1,50 @@
+"""Shared body of the parity tests: run one case through a C-ABI library (the CUDA build on the GPU box, or
+the host-emulation build of the same device bodies on CPU) and compare with the oracle."""
+import os
+import tempfile
+
+import cases
+import oracle_lib as o
+from autocycler_b200 import api
+
+
+def run_library(lib, directory, k, positions=False):
+    kg, seqs, count = api.load_sequences(directory, k, lib=lib)
+    if positions:
+        kg2 = api.KmerGraph(k, lib=lib, keep_positions=True)
+        kg2.add_sequences(seqs, count)
+        kg = kg2
+    else:
+        kg.upload()
+    graph = api.UnitigGraph.from_kmer_graph(kg)
+    before = graph.counts()
+    seed_state = graph.unitigs(positions=True) if positions else None
+    api.simplify_structure(graph)
+    after = graph.counts()
+    return dict(gfa=graph.gfa_bytes().decode(), before=before, after=after, seqs=seqs, count=count, graph=graph,
+                seed_state=seed_state)
+
+
+def check_case(lib, files, k, tmpdir=None):
+    with tempfile.TemporaryDirectory(dir=tmpdir) as d:
+        cases.write_case(files, d)
+        try:
+            expected, yaml, st = o.compress_dir(d, k)
+        except o.OracleError as e:
+            # the reference rejects this input (quit_with_error); the library must reject it too
+            try:
+                run_library(lib, d, k)
+            except api.AutocyclerGpuError:
+                return None
+            raise AssertionError(f"oracle rejected the input ({e}) but the library accepted it")
+        count, oseqs = o.load_sequences(d, k)
+        got = run_library(lib, d, k)
+        assert [(s.id, s.filename, s.contig_header, s.length, s.forward_seq) for s in got["seqs"]] == oseqs, "load/end-repair differs"
+        assert got["count"] == count
+        assert got["before"].n_kmers == st.n_kmers
+        assert (got["before"].n_unitigs, got["before"].n_links, got["before"].total_length) == \
+               (st.unitigs_before, st.links_before, st.length_before)
+        assert (got["after"].n_unitigs, got["after"].n_links, got["after"].total_length) == \
+               (st.unitigs_after, st.links_after, st.length_after)
+        assert got["gfa"] == expected, "GFA differs from the oracle"
+        return got

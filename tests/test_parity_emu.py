@@ -1,0 +1,113 @@
+"""CPU tests of the product's host logic and of the device function bodies, the latter through the
+host-emulation build (tests/emu/libautocycler_emu.so: the same kernel bodies run serially).  The CUDA
+build itself is exercised by test_parity_gpu.py on the B200."""
+import os
+import subprocess
+
+import pytest
+
+import cases
+import oracle_lib as o
+from autocycler_b200 import api, synth
+from parity_common import check_case, run_library
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def emu():
+    path = os.path.join(ROOT, "tests", "emu", "libautocycler_emu.so")
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "autocycler_b200", "csrc"), "emu"], check=True)
+    return api.load_library(path)
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 31, 33, 51, 63, 65, 91, 127])
+def test_random_adversarial_cases(emu, k):
+    for seed in range(12):
+        check_case(emu, cases.random_case(1000 * k + seed, k), k)
+
+
+def test_reference_fixed_seqs(emu):   # tests.rs:131-148 inputs
+    from test_oracle_kats import FIXED
+    files = [(f"{n}.fasta", [(n, s.split("\n")[1])]) for n, s in zip("abcde", FIXED)]
+    for k in (5, 9, 13, 51):
+        check_case(emu, files, k)
+
+
+def test_config1(emu, tmp_path):   # BASELINE.json configs[0]: 3 synthetic 100 kbp assemblies, k=51
+    d = str(tmp_path / "cfg1")
+    synth.write_assemblies(synth.make_assemblies("cfg1"), d)
+    expected, yaml, st = o.compress_dir(d, 51)
+    got = run_library(emu, d, 51)
+    assert got["gfa"] == expected
+    assert got["before"].n_kmers == st.n_kmers
+
+
+def test_positions_match_oracle_seed_state(emu, tmp_path):
+    """forward_positions / reverse_positions (unitig.rs:135-146) as multisets, on the graph after from_kmer_graph."""
+    files = cases.random_case(4242, 9)
+    d = str(tmp_path / "c"); cases.write_case(files, d)
+    count, oseqs = o.load_sequences(d, 9)
+    gfa, st, seed_dump = o.compress_seqs(oseqs, count, 9, want_seed_dump=True)
+    got = run_library(emu, d, 9, positions=True)
+    h = 9 // 2
+    want = {}
+    for line in seed_dump.splitlines():
+        seq, depth, fpos, rpos = line.split("\t")
+        want[seq[h:len(seq) - h]] = (float(depth), sorted(fpos.split(",")), sorted(rpos.split(",")))
+    have = {u["seq"]: (u["depth"], sorted(u["forward_positions"]), sorted(u["reverse_positions"])) for u in got["seed_state"]}
+    # distinct unitigs can share a trimmed sequence; compare only unambiguous ones, but require full coverage by count
+    assert len(got["seed_state"]) == len(seed_dump.splitlines())
+    for seq, val in have.items():
+        if sum(1 for u in got["seed_state"] if u["seq"] == seq) == 1 and seq in want:
+            assert want[seq] == val
+
+
+def test_error_behaviour(emu, tmp_path):
+    # even k / tiny k are refused like compress.rs:56-58 (the C ABI accepts 3..127 odd)
+    with pytest.raises(api.AutocyclerGpuError):
+        api.KmerGraph(10, lib=emu)
+    with pytest.raises(api.AutocyclerGpuError):
+        api.KmerGraph(129, lib=emu)
+    # non-ACGT input (sequence.rs:40-42)
+    d = tmp_path / "bad"; d.mkdir(); (d / "a.fasta").write_text(">a\nACGTNNACGTACGTACGT\n")
+    with pytest.raises(api.AutocyclerGpuError, match="non-ACGT"):
+        api.load_sequences(str(d), 5, lib=emu)
+    # duplicate names (misc.rs:189-193)
+    d2 = tmp_path / "dup"; d2.mkdir(); (d2 / "a.fasta").write_text(">a\nACGTACGT\n>a\nACGTACGA\n")
+    with pytest.raises(api.AutocyclerGpuError, match="duplicate name"):
+        api.load_sequences(str(d2), 5, lib=emu)
+    # no assemblies (misc.rs:79-81)
+    d3 = tmp_path / "empty"; d3.mkdir()
+    with pytest.raises(api.AutocyclerGpuError, match="no assemblies found"):
+        api.load_sequences(str(d3), 5, lib=emu)
+    # too many contigs (compress.rs:84-95)
+    d4 = tmp_path / "many"; d4.mkdir()
+    (d4 / "a.fasta").write_text("".join(f">c{i}\nACGTACGTAC\n" for i in range(5)))
+    with pytest.raises(api.AutocyclerGpuError, match="exceeds the allowed"):
+        api.load_sequences(str(d4), 5, max_contigs=2, lib=emu)
+
+
+def test_file_discovery_and_gz(emu, tmp_path):   # misc.rs:64-95 incl. the precedence quirk, misc.rs:233-245 gzip sniffing
+    import gzip
+    d = tmp_path / "in"; d.mkdir()
+    seq = "CTTATGAGCAGTCCTTAACGTAGCGGTGTGTGGCTTTGAGAAGTTAGCGG"
+    (d / "a.fasta").write_text(f">a\n{seq}\n")
+    (d / "b.fna.gz").write_bytes(gzip.compress(f">b desc\n{seq[:25]}\n{seq[25:]}\n".encode()))
+    (d / "c.fa.bak").write_text(f">c\n{seq}\n")          # qualifies through the reference's && / || precedence
+    (d / "d.txt").write_text(f">d\n{seq}\n")             # ignored
+    (d / "e.fasta").write_text(f">e\r\n{seq.lower()}\r\n\r\n")   # CRLF, lower case, blank line
+    count, oseqs = o.load_sequences(str(d), 11)
+    kg, seqs, n = api.load_sequences(str(d), 11, lib=emu)
+    assert n == count == 4
+    assert [(s.id, s.filename, s.contig_header, s.length, s.forward_seq) for s in seqs] == oseqs
+
+
+def test_cli_yaml_and_gfa_files(emu, tmp_path):
+    """ac_compress_dir writes both files; the YAML sidecar matches the oracle's rendering (metrics.rs:65-107)."""
+    d = str(tmp_path / "cfg"); out = str(tmp_path / "out")
+    synth.write_assemblies(synth.make_assemblies("x", n_assemblies=3, replicon_lengths=[5000], seed=7), d)
+    api.compress(d, out, 51, lib=emu)
+    expected, yaml, st = o.compress_dir(d, 51)
+    assert open(os.path.join(out, "input_assemblies.gfa")).read() == expected
+    assert open(os.path.join(out, "input_assemblies.yaml")).read() == yaml
