@@ -181,14 +181,16 @@ int ac_counts_get(const ac_handle* h, ac_counts* out) {
     AC_GUARD_BEGIN
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_counts_get");
     memset(out, 0, sizeof *out);
+    const HostGraph& g = h->graph;
     out->n_kmers = 2 * h->res.n_slots_used;
-    out->n_unitigs = h->graph.units.size();
-    out->n_links = h->graph.link_count_single();
-    out->total_length = h->graph.total_length();
+    out->n_unitigs = g.U;
+    out->n_links = g.link_count_single();
+    out->total_length = g.total_length();
     out->seq_bytes = out->total_length;
-    for (auto& u : h->graph.units) { out->n_fwd_pos += u.fpos.size(); out->n_rev_pos += u.rpos.size(); out->n_next += u.next[0].size() + u.next[1].size(); }
+    out->n_fwd_pos = g.fpos.size(); out->n_rev_pos = g.rpos.size();
+    out->n_next = g.next.size();
     out->n_sequences = h->seqs.size();
-    for (auto& p : h->graph.paths) out->n_path_steps += p.size();
+    out->n_path_steps = g.path.size();
     return AC_OK;
     AC_GUARD_END(h)
 }
@@ -198,28 +200,35 @@ int ac_unitigs_copy(const ac_handle* h, ac_unitigs* o) {
     AC_GUARD_BEGIN
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_unitigs_copy");
     const HostGraph& g = h->graph;
+    const bool have_pos = !g.fpos_off.empty();
+    if ((o->fpos_off || o->fpos || o->rpos_off || o->rpos) && !have_pos) return set_error(h, AC_EINVAL, "positions need ac_config.keep_positions");
     uint64_t so = 0, fo = 0, ro = 0, no = 0;
-    for (size_t n = 0; n < g.order.size(); ++n) {
-        const HostUnitig& u = g.units[g.order[n]];
-        if (o->number) o->number[n] = u.number;
-        if (o->depth) o->depth[n] = (double)u.depth;
+    for (uint32_t n = 0; n < g.U; ++n) {
+        const uint32_t u = g.order[n];
+        if (o->number) o->number[n] = g.number[u];
+        if (o->depth) o->depth[n] = (double)g.depth[u];
         if (o->seq_off) o->seq_off[n] = so;
-        if (o->seq) memcpy(o->seq + so, u.seq.data(), u.seq.size());
-        so += u.seq.size();
+        if (o->seq) memcpy(o->seq + so, g.seq_ptr(u), g.len[u]);
+        so += g.len[u];
         if (o->fpos_off) o->fpos_off[n] = fo;
         if (o->rpos_off) o->rpos_off[n] = ro;
-        for (uint64_t v : u.fpos) { if (o->fpos) o->fpos[fo] = (uint32_t)(v >> 16); if (o->fpos_id_strand) o->fpos_id_strand[fo] = (uint16_t)(v & 0xFFFF); ++fo; }
-        for (uint64_t v : u.rpos) { if (o->rpos) o->rpos[ro] = (uint32_t)(v >> 16); if (o->rpos_id_strand) o->rpos_id_strand[ro] = (uint16_t)(v & 0xFFFF); ++ro; }
-        for (int s = 0; s < 2; ++s) {
-            if (o->next_off) o->next_off[2 * n + s] = no;
-            for (UStrand t : u.next[s]) { if (o->next) { int32_t num = (int32_t)g.units[us_index(t)].number; o->next[no] = us_reverse(t) ? -num : num; } ++no; }
+        if (have_pos) {
+            for (uint64_t x = g.fpos_off[u]; x < g.fpos_off[u + 1]; ++x) { if (o->fpos) o->fpos[fo] = (uint32_t)(g.fpos[x] >> 16); if (o->fpos_id_strand) o->fpos_id_strand[fo] = (uint16_t)(g.fpos[x] & 0xFFFF); ++fo; }
+            for (uint64_t x = g.rpos_off[u]; x < g.rpos_off[u + 1]; ++x) { if (o->rpos) o->rpos[ro] = (uint32_t)(g.rpos[x] >> 16); if (o->rpos_id_strand) o->rpos_id_strand[ro] = (uint16_t)(g.rpos[x] & 0xFFFF); ++ro; }
+        }
+        for (uint32_t rev = 0; rev < 2; ++rev) {
+            if (o->next_off) o->next_off[2 * (size_t)n + rev] = no;
+            const UStrand from = us_make(u, rev != 0);
+            for (uint32_t x = g.next_off[from]; x < g.next_off[from + 1]; ++x) {
+                if (o->next) { const int32_t num = (int32_t)g.number[us_index(g.next[x])]; o->next[no] = us_reverse(g.next[x]) ? -num : num; }
+                ++no;
+            }
         }
     }
-    const size_t U = g.order.size();
-    if (o->seq_off) o->seq_off[U] = so;
-    if (o->fpos_off) o->fpos_off[U] = fo;
-    if (o->rpos_off) o->rpos_off[U] = ro;
-    if (o->next_off) o->next_off[2 * U] = no;
+    if (o->seq_off) o->seq_off[g.U] = so;
+    if (o->fpos_off) o->fpos_off[g.U] = fo;
+    if (o->rpos_off) o->rpos_off[g.U] = ro;
+    if (o->next_off) o->next_off[2 * (size_t)g.U] = no;
     return AC_OK;
     AC_GUARD_END(h)
 }
@@ -227,12 +236,13 @@ int ac_unitigs_copy(const ac_handle* h, ac_unitigs* o) {
 int ac_path_copy(const ac_handle* h, uint64_t seq_index, int32_t* out, uint64_t cap, uint64_t* n) {
     if (!h || !n) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
-    if (!h->built || seq_index >= h->graph.paths.size()) return set_error(h, AC_EINVAL, "no such sequence");
-    const auto& p = h->graph.paths[seq_index];
-    *n = p.size();
+    const HostGraph& g = h->graph;
+    if (!h->built || seq_index + 1 >= g.path_off.size()) return set_error(h, AC_EINVAL, "no such sequence");
+    const uint64_t a = g.path_off[seq_index], b = g.path_off[seq_index + 1];
+    *n = b - a;
     if (!out) return AC_OK;
-    if (cap < p.size()) return set_error(h, AC_ERANGE, "path buffer too small");
-    for (size_t i = 0; i < p.size(); ++i) { int32_t num = (int32_t)h->graph.units[us_index(p[i])].number; out[i] = us_reverse(p[i]) ? -num : num; }
+    if (cap < b - a) return set_error(h, AC_ERANGE, "path buffer too small");
+    for (uint64_t x = a; x < b; ++x) { const int32_t num = (int32_t)g.number[us_index(g.path[x])]; out[x - a] = us_reverse(g.path[x]) ? -num : num; }
     return AC_OK;
     AC_GUARD_END(h)
 }
@@ -243,9 +253,14 @@ int ac_gfa_size(ac_handle* h, uint64_t* n_bytes) {
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_gfa_size");
     if (!h->gfa_ready) {
         const double t0 = now_ms();
-        h->gfa = h->graph.gfa_text(h->seqs);
+        h->graph.gfa_text(h->seqs, h->gfa);
         h->t.host_gfa = (float)(now_ms() - t0);
         h->gfa_ready = true;
+        if (getenv("AC_HOST_PROFILE")) {
+            const HostProfile& p = h->graph.prof;
+            fprintf(stderr, "[host] seed_sort %.1f seqs %.1f links %.1f paths %.1f renumber(total) %.1f expand %.1f (%d passes) gfa %.1f ms; U=%u\n",
+                    p.seed_sort, p.seqs, p.links, p.paths, p.renumber, p.expand, p.passes, (double)h->t.host_gfa, h->graph.U);
+        }
     }
     *n_bytes = h->gfa.size();
     return AC_OK;

@@ -1,6 +1,11 @@
 // Host side of the compress path: everything that operates on unitigs (10^2..10^6 objects, order
 // dependent) — link ordering, renumbering, repeat expansion and GFA text.  Input is the device
 // pipeline's result; output is byte-identical to the reference's UnitigGraph::save_gfa.
+//
+// Data layout: structure-of-arrays indexed by the unitig's SEED index (the order in which the
+// reference's walk would have created the unitigs, unitig_graph.rs:179-225; it never changes), link
+// lists in CSR form per unitig strand, all sequences in one arena with slack on both sides of every
+// unitig so that repeat expansion moves bytes without reallocating.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -15,49 +20,57 @@ struct HostSeq {              // sequence.rs:19-28 minus the bytes (they live in
     uint64_t start;           // global coordinate of padded byte 0
 };
 
-// A unitig strand: (index << 1) | reverse.  Indices are seed order (the order in which the
-// reference's walk would have created the unitigs, unitig_graph.rs:179-225) and never change.
+// A unitig strand: (seed index << 1) | reverse.
 typedef uint32_t UStrand;
 static inline uint32_t us_index(UStrand s) { return s >> 1; }
 static inline bool us_reverse(UStrand s) { return s & 1; }
 static inline UStrand us_make(uint32_t idx, bool reverse) { return (idx << 1) | (reverse ? 1u : 0u); }
 static inline UStrand us_flip(UStrand s) { return s ^ 1u; }
 
-struct HostUnitig {           // unitig.rs:30-45
-    uint32_t number = 0;
-    std::string seq;          // forward_seq (trimmed)
-    uint32_t depth = 0;       // integral on this path: every k-mer of a chain has the same depth
-    uint32_t min_fpos = 0xFFFFFFFFu, min_rpos = 0xFFFFFFFFu;   // min over forward_positions / reverse_positions
-    std::vector<UStrand> next[2], prev[2];                     // [0] forward strand, [1] reverse strand
-    std::vector<uint64_t> fpos, rpos;                          // optional full position lists (pos << 16 | id_and_strand)
-};
-
-struct GraphStats {
-    uint64_t n_kmers = 0;                     // both strands, == KmerGraph.kmers.len() (compress.rs:152)
-    uint64_t unitigs_before = 0, links_before = 0, length_before = 0;
-    uint64_t unitigs_after = 0, links_after = 0, length_after = 0;
-    double ms_build = 0, ms_simplify = 0, ms_gfa = 0;
-};
+struct HostProfile { double seed_sort = 0, seqs = 0, links = 0, paths = 0, renumber = 0, check = 0, expand = 0, gfa = 0; int passes = 0; };
 
 class HostGraph {
 public:
     uint32_t k = 0;
-    std::vector<HostUnitig> units;            // seed order
-    std::vector<uint32_t> order;              // current numbering order: order[n-1] = index of unitig number n
-    std::vector<std::vector<UStrand>> paths;  // per sequence, its unitig path (unitig_graph.rs:447-465)
+    uint32_t U = 0;
+    // --- per unitig, seed order (unitig.rs:30-45) ---
+    std::vector<uint32_t> number;             // Unitig.number (1-based position in `order`)
+    std::vector<uint32_t> depth;              // integral on this path: every k-mer of a chain has the same depth
+    std::vector<uint32_t> len;                // forward_seq.len()
+    std::vector<uint64_t> seq_off;            // forward_seq = arena[seq_off, seq_off+len)
+    std::vector<uint32_t> room_before, room_after;
+    std::vector<uint32_t> min_fpos, min_rpos; // min over forward_positions / reverse_positions (all entries shift together)
+    std::vector<char> arena;
+    // --- links, CSR over strands (index 2*idx + reverse): forward_next/reverse_next and forward_prev/reverse_prev ---
+    std::vector<uint32_t> next_off, prev_off; // [2U+1]
+    std::vector<UStrand> next, prev;
+    // --- numbering order and paths ---
+    std::vector<uint32_t> order;              // order[n-1] = seed index of unitig number n
+    std::vector<uint64_t> path_off;           // [S+1]
+    std::vector<UStrand> path;                // get_unitig_path_for_sequence for every sequence (unitig_graph.rs:447-465)
+    // optional full position lists (ac_config.keep_positions): CSR per unitig, value = pos << 16 | seq_id_and_strand
+    std::vector<uint64_t> fpos_off, rpos_off, fpos, rpos;
+    HostProfile prof;
 
     // unitig_graph.rs:36-48 from the device result (build, simplify_seqs, create_links, trim_overlaps, renumber, check)
-    void build(const PipelineResult& r, const std::vector<HostSeq>& seqs, const uint8_t* ascii, uint32_t k,
-               bool keep_positions);
+    void build(const PipelineResult& r, const std::vector<HostSeq>& seqs, const uint8_t* ascii, uint32_t k, bool keep_positions);
     void renumber();                          // unitig_graph.rs:295-315
     void check_links() const;                 // unitig_graph.rs:752-793
     void simplify_structure();                // graph_simplification.rs:26-40
     size_t expand_repeats();                  // graph_simplification.rs:43-86
-    std::string gfa_text(const std::vector<HostSeq>& seqs) const;   // unitig_graph.rs:317-360
+    void gfa_text(const std::vector<HostSeq>& seqs, std::string& out) const;   // unitig_graph.rs:317-360
     uint64_t total_length() const;
     uint64_t link_count_single() const;       // unitig_graph.rs:478-507 (.1)
+    const char* seq_ptr(uint32_t idx) const { return arena.data() + seq_off[idx]; }
+    const UStrand* next_begin(UStrand s) const { return next.data() + next_off[s]; }
+    uint32_t next_size(UStrand s) const { return next_off[s + 1] - next_off[s]; }
+    const UStrand* prev_begin(UStrand s) const { return prev.data() + prev_off[s]; }
+    uint32_t prev_size(UStrand s) const { return prev_off[s + 1] - prev_off[s]; }
 private:
     std::vector<uint8_t> fixed_start, fixed_end;
     bool fixed_ready = false;
     void compute_fixed();
+    void grow_front(uint32_t idx, uint32_t need);
+    void grow_back(uint32_t idx, uint32_t need);
+    void relocate(uint32_t idx, uint32_t before, uint32_t after);
 };
