@@ -46,7 +46,7 @@ class AcUnitigs(C.Structure):
 
 
 class AcTimings(C.Structure):
-    _fields_ = [(n, C.c_float) for n in ("h2d", "pack", "insert", "adjacency", "boundaries", "runs", "unitigs", "links", "d2h",
+    _fields_ = [(n, C.c_float) for n in ("h2d", "pack", "insert", "adjacency", "boundaries", "runs", "unitigs", "links", "seed_sort", "emit", "d2h",
                                         "device_total", "host_graph", "host_simplify", "host_gfa")] + \
                [(n, C.c_uint64) for n in ("insert_occurrences", "table_capacity", "table_used", "kernel_launches", "h2d_bytes", "d2h_bytes")]
 
@@ -84,7 +84,7 @@ def load_library(path=None):
     lib.ac_unitigs_copy.argtypes = [C.c_void_p, C.POINTER(AcUnitigs)]
     lib.ac_path_copy.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), C.c_uint64, C.POINTER(C.c_uint64)]
     lib.ac_gfa_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-    lib.ac_gfa_copy.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+    lib.ac_gfa_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.ac_timings_get.argtypes = [C.c_void_p, C.POINTER(AcTimings)]
     lib.ac_compress_dir.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32]
     lib.ac_load_sequences.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
@@ -228,9 +228,12 @@ class UnitigGraph:
     def gfa_bytes(self):            # the bytes save_gfa writes
         n = C.c_uint64()
         self._h.check(self._h.lib.ac_gfa_size(self._h.ptr, C.byref(n)))
-        buf = C.create_string_buffer(n.value + 1)
-        self._h.check(self._h.lib.ac_gfa_copy(self._h.ptr, buf, n.value))
-        return buf.raw[:n.value]
+        out = bytearray(n.value)
+        if n.value:
+            buf = (C.c_char * n.value).from_buffer(out)     # the library writes straight into the result, no second copy
+            self._h.check(self._h.lib.ac_gfa_copy(self._h.ptr, buf, n.value))
+            del buf
+        return out
 
     def save_gfa(self, gfa_filename, sequences=None, use_other_colour=False):   # unitig_graph.rs:317-331
         with open(gfa_filename, "wb") as f:

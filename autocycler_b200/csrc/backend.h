@@ -24,6 +24,7 @@ template <class T> inline T ac_atomic_cas(T* p, T cmp, T val) { T old = *p; if (
 template <class T> inline T ac_atomic_add(T* p, T v) { T old = *p; *p = (T)(old + v); return old; }
 template <class T> inline T ac_atomic_or(T* p, T v) { T old = *p; *p = (T)(old | v); return old; }
 template <class T> inline T ac_atomic_min(T* p, T v) { T old = *p; if (v < old) *p = v; return old; }
+template <class T> inline T ac_atomic_max(T* p, T v) { T old = *p; if (v > old) *p = v; return old; }
 template <class T> inline T ac_ld_volatile(const T* p) { return *p; }
 inline uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 
@@ -67,6 +68,7 @@ AC_D uint64_t ac_atomic_add(uint64_t* p, uint64_t v) { return (uint64_t)atomicAd
 AC_D unsigned long long ac_atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 AC_D uint32_t ac_atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
 AC_D uint32_t ac_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
+AC_D uint32_t ac_atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
 template <class T> AC_D T ac_ld_volatile(const T* p) { return *(const volatile T*)p; }
 AC_D uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 #endif

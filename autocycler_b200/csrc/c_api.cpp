@@ -145,15 +145,15 @@ int ac_build(ac_handle* h) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     AC_GUARD_BEGIN
     if (!h->uploaded) return set_error(h, AC_EINVAL, "ac_upload must precede ac_build");
-    h->pipe->build(h->res);
+    h->pipe->build(h->res, h->cfg.keep_positions != 0);
     const double t0 = now_ms();
-    h->graph.build(h->res, h->seqs, h->ascii.p, h->cfg.k, h->cfg.keep_positions != 0);
+    h->graph.build(h->res, h->seqs, h->cfg.k, h->cfg.keep_positions != 0);
     h->graph.check_links();
     const double t1 = now_ms();
     const PipelineTimings& pt = h->res.t;
     ac_timings& t = h->t;
     t.h2d = pt.h2d; t.pack = pt.pack; t.insert = pt.insert; t.adjacency = pt.adjacency; t.boundaries = pt.boundaries; t.runs = pt.runs;
-    t.unitigs = pt.unitigs; t.links = pt.links; t.d2h = pt.d2h; t.device_total = pt.total;
+    t.unitigs = pt.unitigs; t.links = pt.links; t.seed_sort = pt.seed_sort; t.emit = pt.emit; t.d2h = pt.d2h; t.device_total = pt.total;
     t.host_graph = (float)(t1 - t0); t.host_simplify = 0; t.host_gfa = 0;
     uint64_t windows = 0; for (auto& s : h->seqs) windows += s.length;
     t.insert_occurrences = windows; t.table_capacity = h->res.capacity; t.table_used = h->res.n_slots_used;
@@ -188,9 +188,9 @@ int ac_counts_get(const ac_handle* h, ac_counts* out) {
     out->total_length = g.total_length();
     out->seq_bytes = out->total_length;
     out->n_fwd_pos = g.fpos.size(); out->n_rev_pos = g.rpos.size();
-    out->n_next = g.next.size();
+    out->n_next = g.n_links;
     out->n_sequences = h->seqs.size();
-    out->n_path_steps = g.path.size();
+    out->n_path_steps = g.n_path;
     return AC_OK;
     AC_GUARD_END(h)
 }
@@ -208,8 +208,8 @@ int ac_unitigs_copy(const ac_handle* h, ac_unitigs* o) {
         if (o->number) o->number[n] = g.number[u];
         if (o->depth) o->depth[n] = (double)g.depth[u];
         if (o->seq_off) o->seq_off[n] = so;
-        if (o->seq) memcpy(o->seq + so, g.seq_ptr(u), g.len[u]);
-        so += g.len[u];
+        if (o->seq) memcpy(o->seq + so, g.seq_ptr(u), g.rec[u].len);
+        so += g.rec[u].len;
         if (o->fpos_off) o->fpos_off[n] = fo;
         if (o->rpos_off) o->rpos_off[n] = ro;
         if (have_pos) {
@@ -237,7 +237,7 @@ int ac_path_copy(const ac_handle* h, uint64_t seq_index, int32_t* out, uint64_t 
     if (!h || !n) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     const HostGraph& g = h->graph;
-    if (!h->built || seq_index + 1 >= g.path_off.size()) return set_error(h, AC_EINVAL, "no such sequence");
+    if (!h->built || seq_index >= g.n_seqs) return set_error(h, AC_EINVAL, "no such sequence");
     const uint64_t a = g.path_off[seq_index], b = g.path_off[seq_index + 1];
     *n = b - a;
     if (!out) return AC_OK;
@@ -258,8 +258,8 @@ int ac_gfa_size(ac_handle* h, uint64_t* n_bytes) {
         h->gfa_ready = true;
         if (getenv("AC_HOST_PROFILE")) {
             const HostProfile& p = h->graph.prof;
-            fprintf(stderr, "[host] seed_sort %.1f seqs %.1f links %.1f paths %.1f renumber(total) %.1f expand %.1f (%d passes) gfa %.1f ms; U=%u\n",
-                    p.seed_sort, p.seqs, p.links, p.paths, p.renumber, p.expand, p.passes, (double)h->t.host_gfa, h->graph.U);
+            fprintf(stderr, "[host] adopt %.1f renumber(total) %.1f expand %.1f (%d passes; candidates %.1f, +compare %.1f, pass1 %.1f) gfa %.1f ms; U=%u\n",
+                    p.paths, p.renumber, p.expand, p.passes, p.seqs, p.check, p.links, (double)h->t.host_gfa, h->graph.U);
         }
     }
     *n_bytes = h->gfa.size();

@@ -2,10 +2,12 @@
 #include "host_graph.h"
 
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <chrono>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 
 namespace {
 inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -14,142 +16,60 @@ inline char comp(char c) {   // misc.rs:324-333 (unitig sequences hold only ACGT
     switch (c) { case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C'; default: return c == '.' ? '.' : 'N'; }
 }
 
-struct SeedKey { uint64_t w[AC_MAX_W]; int32_t d; uint32_t dev; };
-inline bool seed_less(const SeedKey& a, const SeedKey& b) {   // byte order of the k-mer text, '.' < A < C < G < T (kmer_key.h key_less5)
-    const int la = a.d > 0 ? a.d : 0, lb = b.d > 0 ? b.d : 0;
-    if (la != lb) return la > lb;
-    for (int j = 0; j < AC_MAX_W; ++j) if (a.w[j] != b.w[j]) return a.w[j] < b.w[j];
-    const int ta = a.d < 0 ? -a.d : 0, tb = b.d < 0 ? -b.d : 0;
-    return ta > tb;
+unsigned host_threads() {
+    static const unsigned n = [] {
+        unsigned hw = std::thread::hardware_concurrency();
+        if (const char* e = getenv("AC_HOST_THREADS")) { int v = atoi(e); if (v > 0) return (unsigned)v; }
+        return hw == 0 ? 4u : (hw > 16 ? 16u : hw);
+    }();
+    return n;
 }
 
-const uint32_t SLACK = 32;   // spare bytes on each side of every unitig in the arena
+// Runs fn(task) for task in [0, n_tasks) on up to host_threads() threads (dynamic scheduling).
+template <class F> void parallel_tasks(size_t n_tasks, F&& fn) {
+    const unsigned nt = (unsigned)std::min<size_t>(host_threads(), n_tasks);
+    if (nt <= 1) { for (size_t t = 0; t < n_tasks; ++t) fn(t); return; }
+    std::atomic<size_t> next{0};
+    std::exception_ptr err = nullptr; std::atomic<bool> failed{false};
+    auto work = [&]() {
+        try { for (size_t t; (t = next.fetch_add(1)) < n_tasks;) fn(t); }
+        catch (...) { if (!failed.exchange(true)) err = std::current_exception(); }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    if (err) std::rethrow_exception(err);
+}
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// build
+// build: adopt the device result (already in seed order, links already in the reference's push order)
 // ------------------------------------------------------------------------------------------------
-void HostGraph::build(const PipelineResult& r, const std::vector<HostSeq>& seqs, const uint8_t* ascii, uint32_t k_size,
-                      bool keep_positions) {
+void HostGraph::build(const PipelineResult& r, const std::vector<HostSeq>& seqs, uint32_t k_size, bool keep_positions) {
     prof = HostProfile();
-    double t0 = now_ms();
+    const double t0 = now_ms();
     k = k_size;
-    const uint32_t h = k / 2;
-    U = (uint32_t)r.unitigs.size();
-    fixed_ready = false;
+    U = r.n_unitigs;
+    fixed_ready = false; cands_ready = false;
+    rec = r.rec; depth = r.depth;
+    arena = r.arena; arena_used = r.arena_used; arena_cap = r.arena_cap; arena_overflow.clear();
+    next_off = r.next_off; next = r.next; prev_off = r.prev_off; prev = r.prev; n_links = r.n_links;
+    path_off = r.path_off; path = r.path; n_path = r.n_runs; n_seqs = r.n_seqs;
+    number.assign(U, 0);
 
-    // Seed order (kmer_graph.rs:168-173 + unitig_graph.rs:179-185): ascending smallest k-mer of both strands.
-    // min_w holds W significant words; the unused slots are zero for every unitig, so comparing all is safe.
-    std::vector<SeedKey> keys(U);
-    for (uint32_t j = 0; j < U; ++j) {
-        SeedKey& sk = keys[j];
-        for (int w = 0; w < AC_MAX_W; ++w) sk.w[w] = r.unitigs[j].min_w[w];
-        sk.d = r.unitigs[j].min_d; sk.dev = j;
-    }
-    std::sort(keys.begin(), keys.end(), seed_less);
-    std::vector<uint32_t> rank(U);
-    for (uint32_t s = 0; s < U; ++s) rank[keys[s].dev] = s;
-    double t1 = now_ms(); prof.seed_sort = t1 - t0;
-
-    // Sequences (unitig.rs:120-133 + 157-165): the trimmed unitig is the centre base of each of its k-mers, i.e. a
-    // slice of the padded input shifted by k/2 (reverse-complemented when the seed k-mer lies on the other strand).
-    number.assign(U, 0); depth.resize(U); len.resize(U); seq_off.resize(U);
-    room_before.assign(U, SLACK); room_after.assign(U, SLACK);
-    min_fpos.assign(U, 0xFFFFFFFFu); min_rpos.assign(U, 0xFFFFFFFFu);
-    uint64_t arena_bytes = 0;
-    for (uint32_t s = 0; s < U; ++s) {
-        const DeviceUnitig& d = r.unitigs[keys[s].dev];
-        seq_off[s] = arena_bytes + SLACK; len[s] = d.len; depth[s] = d.depth;
-        arena_bytes += (uint64_t)d.len + 2 * SLACK;
-    }
-    arena.resize(arena_bytes);
-    for (uint32_t s = 0; s < U; ++s) {
-        const DeviceUnitig& d = r.unitigs[keys[s].dev];
-        const char* src = (const char*)ascii + d.start + h;
-        char* dst = arena.data() + seq_off[s];
-        if (!d.flip) memcpy(dst, src, d.len);
-        else for (uint32_t i = 0; i < d.len; ++i) dst[i] = comp(src[d.len - 1 - i]);
-    }
-    double t2 = now_ms(); prof.seqs = t2 - t1;
-
-    // Links.  Device strand e (0 = direction of the representative occurrence) -> unitig strand.
-    std::vector<uint8_t> flip(U);
-    for (uint32_t j = 0; j < U; ++j) flip[j] = (uint8_t)r.unitigs[j].flip;
-    auto to_strand = [&](uint32_t dev_strand) -> UStrand {
-        const uint32_t j = dev_strand >> 1, e = dev_strand & 1;
-        return us_make(rank[j], (e ^ flip[j]) != 0);
-    };
-    next_off.assign(2 * (size_t)U + 1, 0); prev_off.assign(2 * (size_t)U + 1, 0);
-    for (uint32_t i = 0; i < 2 * U; ++i) {
-        if (r.link_count[i] > AC_MAX_LINKS) throw std::runtime_error("link overflow");
-        next_off[to_strand(i) + 1] = r.link_count[i];
-    }
-    for (size_t s = 0; s < 2 * (size_t)U; ++s) next_off[s + 1] += next_off[s];
-    next.resize(next_off[2 * (size_t)U]);
-    for (uint32_t i = 0; i < 2 * U; ++i) {
-        const UStrand from = to_strand(i);
-        const uint32_t n = r.link_count[i], a = us_index(from);
-        UStrand* out = next.data() + next_off[from];
-        for (uint32_t x = 0; x < n; ++x) out[x] = to_strand(r.links[(size_t)i * AC_MAX_LINKS + x]);
-        if (n < 2) continue;
-        if (!us_reverse(from)) {
-            // forward_next: all b+ ascending, then all b- ascending (unitig_graph.rs:255-275, blocks 1 and 2 of iteration a)
-            std::sort(out, out + n, [](UStrand x, UStrand y) {
-                if (us_reverse(x) != us_reverse(y)) return !us_reverse(x);
-                return us_index(x) < us_index(y); });
-        } else {
-            // reverse_next: x- pushed by block 1 of iteration x (x < a); iteration a pushes a- (self loop) then all b+
-            // ascending (block 3); then x- for x > a (unitig_graph.rs:262-264, 277-285)
-            auto phase = [a](UStrand t) { if (us_reverse(t)) return us_index(t) < a ? 0 : (us_index(t) == a ? 1 : 3); return 2; };
-            std::sort(out, out + n, [&](UStrand x, UStrand y) {
-                const int px = phase(x), py = phase(y);
-                if (px != py) return px < py;
-                return us_index(x) < us_index(y); });
-        }
-    }
-    // prev lists mirror next lists: (a,s)->(b,t) puts (a,s) into prev(b,t).  Only membership matters downstream.
-    for (UStrand t : next) prev_off[t + 1] += 1;
-    for (size_t s = 0; s < 2 * (size_t)U; ++s) prev_off[s + 1] += prev_off[s];
-    prev.resize(next.size());
-    {
-        std::vector<uint32_t> cursor(prev_off.begin(), prev_off.end() - 1);
-        for (UStrand from = 0; from < 2 * U; ++from)
-            for (uint32_t x = next_off[from]; x < next_off[from + 1]; ++x) prev[cursor[next[x]]++] = from;
-    }
-    double t3 = now_ms(); prof.links = t3 - t2;
-
-    // Paths and positions from the occurrences.  An occurrence [fs, fs+n) on the forward strand of sequence i is also
-    // an occurrence of the opposite unitig strand at L-fs-n on its reverse strand (kmer_graph.rs:103-108);
-    // forward_positions / reverse_positions are those of the first k-mer of each unitig strand (unitig.rs:135-146).
-    const size_t R = r.run_start.size(), S = seqs.size();
-    path_off.assign(S + 1, 0); path.resize(R);
-    std::vector<uint32_t> pos_count;
-    if (keep_positions) pos_count.assign(U, 0);
-    size_t si = 0;
-    for (size_t x = 0; x < R; ++x) {
-        const uint64_t g = r.run_start[x];
-        while (si + 1 < S && seqs[si + 1].start <= g) ++si;
-        const HostSeq& s = seqs[si];
-        const uint32_t dev = r.run_unitig[x] >> 1, same = r.run_unitig[x] & 1;
-        const uint32_t idx = rank[dev];
-        const bool plus = (same ^ flip[dev]) != 0;
-        path[x] = us_make(idx, !plus);
-        path_off[si + 1] = x + 1;
-        const uint32_t fs = (uint32_t)(g - s.start), n = r.run_len[x];
-        const uint32_t mirrored = (uint32_t)(s.length - fs - n);
-        const uint32_t f = plus ? fs : mirrored, rv = plus ? mirrored : fs;
-        if (f < min_fpos[idx]) min_fpos[idx] = f;
-        if (rv < min_rpos[idx]) min_rpos[idx] = rv;
-        if (keep_positions) pos_count[idx] += 1;
-    }
-    for (size_t i = 1; i <= S; ++i) if (path_off[i] < path_off[i - 1]) path_off[i] = path_off[i - 1];
+    // Full position lists (unitig.rs:135-146), only on request: an occurrence [fs, fs+n) on the forward strand of
+    // sequence i is also an occurrence of the opposite unitig strand at L-fs-n on its reverse strand (kmer_graph.rs:103-108).
     fpos_off.clear(); rpos_off.clear(); fpos.clear(); rpos.clear();
     if (keep_positions) {
+        const size_t R = r.n_runs, S = seqs.size();
+        std::vector<uint32_t> pos_count(U, 0);
+        for (size_t x = 0; x < R; ++x) pos_count[us_index(path[x])] += 1;
         fpos_off.assign((size_t)U + 1, 0);
         for (uint32_t u = 0; u < U; ++u) fpos_off[u + 1] = fpos_off[u] + pos_count[u];
         rpos_off = fpos_off; fpos.resize(R); rpos.resize(R);
         std::vector<uint64_t> cursor(fpos_off.begin(), fpos_off.end() - 1);
-        si = 0;
+        size_t si = 0;
         for (size_t x = 0; x < R; ++x) {
             const uint64_t g = r.run_start[x];
             while (si + 1 < S && seqs[si + 1].start <= g) ++si;
@@ -161,7 +81,7 @@ void HostGraph::build(const PipelineResult& r, const std::vector<HostSeq>& seqs,
             rpos[at] = ((uint64_t)(plus ? mirrored : fs) << 16) | (uint64_t)(s.id | (plus ? 0u : 0x8000u));
         }
     }
-    double t4 = now_ms(); prof.paths = t4 - t3;
+    prof.paths = now_ms() - t0;
 
     order.resize(U);
     for (uint32_t s = 0; s < U; ++s) order[s] = s;
@@ -175,44 +95,59 @@ void HostGraph::renumber() {   // unitig_graph.rs:295-315: stable sort by length
     const double t0 = now_ms();
     struct Key { uint32_t len; uint32_t pos; uint64_t prefix; uint32_t idx; uint32_t depth; };
     std::vector<Key> keys(U);
-    for (uint32_t n = 0; n < U; ++n) {
-        const uint32_t idx = order[n];
-        Key& key = keys[n];
-        key.len = len[idx]; key.pos = n; key.idx = idx; key.depth = depth[idx];
-        const unsigned char* p = (const unsigned char*)seq_ptr(idx);
-        uint64_t v = 0;
-        const uint32_t m = key.len < 8 ? key.len : 8;
-        for (uint32_t i = 0; i < m; ++i) v |= (uint64_t)p[i] << (56 - 8 * i);
-        key.prefix = v;
-    }
-    std::sort(keys.begin(), keys.end(), [&](const Key& a, const Key& b) {
+    const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads(), U / 4096));
+    auto bounds = [&](size_t t) { return (size_t)((uint64_t)U * t / T); };
+    auto less = [&](const Key& a, const Key& b) {
         if (a.len != b.len) return a.len > b.len;
         if (a.prefix != b.prefix) return a.prefix < b.prefix;
         if (a.len > 8) { const int c = memcmp(seq_ptr(a.idx) + 8, seq_ptr(b.idx) + 8, a.len - 8); if (c != 0) return c < 0; }
         if (a.depth != b.depth) return a.depth > b.depth;
         return a.pos < b.pos;   // ties keep their previous order: slice::sort_by is stable
+    };
+    parallel_tasks(T, [&](size_t t) {
+        for (size_t n = bounds(t); n < bounds(t + 1); ++n) {
+            const uint32_t idx = order[n];
+            Key& key = keys[n];
+            key.len = rec[idx].len; key.pos = (uint32_t)n; key.idx = idx; key.depth = depth[idx];
+            const unsigned char* p = (const unsigned char*)seq_ptr(idx);
+            uint64_t v = 0;
+            const uint32_t m = key.len < 8 ? key.len : 8;
+            for (uint32_t i = 0; i < m; ++i) v |= (uint64_t)p[i] << (56 - 8 * i);
+            key.prefix = v;
+        }
+        std::sort(keys.begin() + bounds(t), keys.begin() + bounds(t + 1), less);
     });
+    for (size_t width = 1; width < T; width *= 2) {   // pairwise merges of the sorted pieces, each level in parallel
+        const size_t pairs = (T + 2 * width - 1) / (2 * width);
+        parallel_tasks(pairs, [&](size_t q) {
+            const size_t a = q * 2 * width, m = std::min(T, a + width), b = std::min(T, a + 2 * width);
+            if (m < b) std::inplace_merge(keys.begin() + bounds(a), keys.begin() + bounds(m), keys.begin() + bounds(b), less);
+        });
+    }
     for (uint32_t n = 0; n < U; ++n) { order[n] = keys[n].idx; number[keys[n].idx] = n + 1; }
     prof.renumber += now_ms() - t0;
 }
 
 void HostGraph::check_links() const {   // unitig_graph.rs:752-793: every link has its mirror and its prev entry
     auto has = [](const UStrand* b, uint32_t n, UStrand x) { for (uint32_t i = 0; i < n; ++i) if (b[i] == x) return true; return false; };
-    for (UStrand from = 0; from < 2 * U; ++from) {
-        for (uint32_t x = next_off[from]; x < next_off[from + 1]; ++x) {
-            const UStrand to = next[x];
-            if (!has(prev_begin(to), prev_size(to), from)) throw std::runtime_error("missing prev link");
-            if (!has(next_begin(us_flip(to)), next_size(us_flip(to)), us_flip(from))) throw std::runtime_error("missing next link");
+    const size_t n_strands = 2 * (size_t)U, T = std::max<size_t>(1, std::min<size_t>(host_threads(), n_strands / 8192));
+    parallel_tasks(T, [&](size_t t) {
+        for (UStrand from = (UStrand)(n_strands * t / T); from < (UStrand)(n_strands * (t + 1) / T); ++from) {
+            for (uint32_t x = next_off[from]; x < next_off[from + 1]; ++x) {
+                const UStrand to = next[x];
+                if (!has(prev_begin(to), prev_size(to), from)) throw std::runtime_error("missing prev link");
+                if (!has(next_begin(us_flip(to)), next_size(us_flip(to)), us_flip(from))) throw std::runtime_error("missing next link");
+            }
+            for (uint32_t x = prev_off[from]; x < prev_off[from + 1]; ++x)
+                if (!has(next_begin(prev[x]), next_size(prev[x]), from)) throw std::runtime_error("missing next link");
         }
-        for (uint32_t x = prev_off[from]; x < prev_off[from + 1]; ++x)
-            if (!has(next_begin(prev[x]), next_size(prev[x]), from)) throw std::runtime_error("missing next link");
-    }
+    });
 }
 
-uint64_t HostGraph::total_length() const { uint64_t t = 0; for (uint32_t u = 0; u < U; ++u) t += len[u]; return t; }
+uint64_t HostGraph::total_length() const { uint64_t t = 0; for (uint32_t u = 0; u < U; ++u) t += rec[u].len; return t; }
 
 uint64_t HostGraph::link_count_single() const {   // unitig_graph.rs:478-507: a link and its mirror count once; hairpins are their own mirror
-    uint64_t all = next.size(), hairpins = 0;
+    uint64_t all = n_links, hairpins = 0;
     for (UStrand from = 0; from < 2 * U; ++from)
         for (uint32_t x = next_off[from]; x < next_off[from + 1]; ++x) if (next[x] == us_flip(from)) ++hairpins;
     return (all - hairpins) / 2 + hairpins;
@@ -222,20 +157,27 @@ uint64_t HostGraph::link_count_single() const {   // unitig_graph.rs:478-507: a 
 // arena growth
 // ------------------------------------------------------------------------------------------------
 void HostGraph::relocate(uint32_t idx, uint32_t before, uint32_t after) {
-    const uint64_t old_off = seq_off[idx], at = arena.size();
-    arena.resize(at + before + len[idx] + after);
-    memcpy(arena.data() + at + before, arena.data() + old_off, len[idx]);
-    seq_off[idx] = at + before; room_before[idx] = before; room_after[idx] = after;
+    const uint64_t need = (uint64_t)before + rec[idx].len + after;
+    if (arena_used + need > arena_cap) {   // outgrew the pinned arena: continue in ordinary host memory
+        std::vector<char> bigger((arena_used + need) * 2);
+        memcpy(bigger.data(), arena, arena_used);
+        arena_overflow.swap(bigger);
+        arena = arena_overflow.data(); arena_cap = arena_overflow.size();
+    }
+    const uint64_t at = arena_used;
+    arena_used += need;
+    memmove(arena + at + before, arena + rec[idx].seq_off, rec[idx].len);
+    rec[idx].seq_off = at + before; rec[idx].room_before = before; rec[idx].room_after = after;
 }
-void HostGraph::grow_front(uint32_t idx, uint32_t need) { if (room_before[idx] < need) relocate(idx, need + 4 * SLACK, room_after[idx] < SLACK ? SLACK : room_after[idx]); }
-void HostGraph::grow_back(uint32_t idx, uint32_t need) { if (room_after[idx] < need) relocate(idx, room_before[idx] < SLACK ? SLACK : room_before[idx], need + 4 * SLACK); }
+void HostGraph::grow_front(uint32_t idx, uint32_t need) { if (rec[idx].room_before < need) relocate(idx, need + 4 * AC_SEQ_SLACK, rec[idx].room_after < AC_SEQ_SLACK ? AC_SEQ_SLACK : rec[idx].room_after); }
+void HostGraph::grow_back(uint32_t idx, uint32_t need) { if (rec[idx].room_after < need) relocate(idx, rec[idx].room_before < AC_SEQ_SLACK ? AC_SEQ_SLACK : rec[idx].room_before, need + 4 * AC_SEQ_SLACK); }
 
 // ------------------------------------------------------------------------------------------------
 // graph_simplification.rs:26-312
 // ------------------------------------------------------------------------------------------------
 void HostGraph::compute_fixed() {   // graph_simplification.rs:190-230; paths and links never change during simplification
     fixed_start.assign(U, 0); fixed_end.assign(U, 0);
-    for (size_t i = 0; i + 1 < path_off.size(); ++i) {
+    for (size_t i = 0; i < n_seqs; ++i) {
         if (path_off[i + 1] == path_off[i]) continue;
         const UStrand first = path[path_off[i]], last = path[path_off[i + 1] - 1];
         if (!us_reverse(first)) fixed_start[us_index(first)] = 1; else fixed_end[us_index(first)] = 1;
@@ -255,96 +197,188 @@ void HostGraph::compute_fixed() {   // graph_simplification.rs:190-230; paths an
     fixed_ready = true;
 }
 
+// Which (unitig, side) pairs can ever shift is decided by links, paths and fixed sets alone, and none of those change
+// while `while expand_repeats() > 0 {}` runs (graph_simplification.rs:26-27; the renumbering comes after), so the
+// candidates are listed once, in the iteration order of the reference's loop (graph.unitigs order; inputs side first).
+void HostGraph::compute_candidates() {
+    if (!fixed_ready) compute_fixed();
+    const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads(), U / 8192));
+    std::vector<std::vector<Candidate>> part(T);
+    parallel_tasks(T, [&](size_t t) {
+        std::vector<Candidate>& out = part[t];
+        for (uint32_t n = (uint32_t)((uint64_t)U * t / T); n < (uint32_t)((uint64_t)U * (t + 1) / T); ++n) {
+            const uint32_t idx = order[n];
+            const UStrand self_fwd = us_make(idx, false);
+            {   // get_exclusive_inputs (:233-255) and the guards of expand_repeats (:66-72)
+                const UStrand* grp = prev_begin(self_fwd); const uint32_t gn = prev_size(self_fwd);
+                bool ok = gn >= 2 && !fixed_start[idx];
+                for (uint32_t a = 0; ok && a < gn; ++a) {
+                    const UStrand p = grp[a];
+                    if (!(next_size(p) == 1 && next_begin(p)[0] == self_fwd) || us_index(p) == idx) ok = false;
+                    else if ((!us_reverse(p) && fixed_end[us_index(p)]) || (us_reverse(p) && fixed_start[us_index(p)])) ok = false;
+                }
+                if (ok) out.push_back({idx, 0});
+            }
+            {   // get_exclusive_outputs (:258-280) and the guards (:75-82)
+                const UStrand* grp = next_begin(self_fwd); const uint32_t gn = next_size(self_fwd);
+                bool ok = gn >= 2 && !fixed_end[idx];
+                for (uint32_t a = 0; ok && a < gn; ++a) {
+                    const UStrand q = grp[a];
+                    if (!(prev_size(q) == 1 && prev_begin(q)[0] == self_fwd) || us_index(q) == idx) ok = false;
+                    else if ((!us_reverse(q) && fixed_start[us_index(q)]) || (us_reverse(q) && fixed_end[us_index(q)])) ok = false;
+                }
+                if (ok) out.push_back({idx, 1});
+            }
+        }
+    });
+    cands.clear();
+    for (auto& v : part) cands.insert(cands.end(), v.begin(), v.end());
+    cand_at.assign(2 * (size_t)U, -1);
+    for (size_t i = 0; i < cands.size(); ++i) cand_at[2 * (size_t)cands[i].idx + cands[i].side] = (int32_t)i;
+    compute_dependents();
+    dirty.assign((cands.size() + 63) / 64, ~0ull);
+    if (cands.size() % 64) dirty.back() = (1ull << (cands.size() % 64)) - 1;
+    for (uint32_t u = 0; u < U; ++u) rec[u].flags = 0;
+    first_pass = true;
+    cands_ready = true;
+}
+
+namespace {
+const struct CompLut { unsigned char same[256], comp[256]; CompLut() { for (int i = 0; i < 256; ++i) { same[i] = (unsigned char)i; comp[i] = (unsigned char)::comp((char)i); } } } g_lut;
+// A unitig strand read from its start or from its end without materialising the reverse complement
+// (UnitigStrand::get_seq): character i is map[base[i * step]].
+struct Cursor { const unsigned char* base; ptrdiff_t step; const unsigned char* map;
+                unsigned char at(size_t i) const { return map[base[(ptrdiff_t)i * step]]; } };
+}  // namespace
+
+// get_common_end_seq (:298-312) for side 0 / get_common_start_seq (:283-295) for side 1: length of the common piece
+uint32_t HostGraph::common_length(const Candidate& cand) const {
+    const UStrand self_fwd = us_make(cand.idx, false);
+    const UStrand* grp = cand.side == 0 ? prev_begin(self_fwd) : next_begin(self_fwd);
+    const uint32_t gn = cand.side == 0 ? prev_size(self_fwd) : next_size(self_fwd);
+    auto cursor = [&](UStrand s) {
+        const uint32_t u = us_index(s); const unsigned char* p = (const unsigned char*)seq_ptr(u);
+        const bool at_back = (cand.side == 0) != us_reverse(s);    // forward strand read from its end, or reverse strand read from its start
+        return Cursor{at_back ? p + rec[u].len - 1 : p, at_back ? -1 : 1, us_reverse(s) ? g_lut.comp : g_lut.same};
+    };
+    const Cursor first = cursor(grp[0]);
+    size_t c = rec[us_index(grp[0])].len;
+    for (uint32_t a = 1; a < gn; ++a) {
+        const uint32_t la = rec[us_index(grp[a])].len;
+        if (la < c) c = la;
+        const Cursor cur = cursor(grp[a]);
+        size_t m = 0;
+        while (m < c && cur.at(m) == first.at(m)) ++m;
+        c = m;
+    }
+    return (uint32_t)c;
+}
+
+// A change to unitig u can only matter to the candidates that read it: those of u itself (its minimum position) and
+// those of the unitigs it exclusively feeds (as an input) or is exclusively fed by (as an output).
+void HostGraph::compute_dependents() {
+    deps.resize(U);
+    const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads(), U / 8192));
+    parallel_tasks(T, [&](size_t t) {
+        for (uint32_t u = (uint32_t)((uint64_t)U * t / T); u < (uint32_t)((uint64_t)U * (t + 1) / T); ++u) {
+            Deps& d = deps[u];
+            d.c[0] = cand_at[2 * (size_t)u]; d.c[1] = cand_at[2 * (size_t)u + 1];
+            for (uint32_t rev = 0; rev < 2; ++rev) {
+                const UStrand s = us_make(u, rev != 0);
+                d.c[2 + 2 * rev] = (next_size(s) == 1 && !us_reverse(next_begin(s)[0])) ? cand_at[2 * (size_t)us_index(next_begin(s)[0])] : -1;
+                d.c[3 + 2 * rev] = (prev_size(s) == 1 && !us_reverse(prev_begin(s)[0])) ? cand_at[2 * (size_t)us_index(prev_begin(s)[0]) + 1] : -1;
+            }
+        }
+    });
+}
+
+void HostGraph::mark_dependents(uint32_t u) {
+    const Deps& d = deps[u];
+    for (int i = 0; i < 6; ++i) if (d.c[i] >= 0) dirty[(size_t)d.c[i] >> 6] |= 1ull << (d.c[i] & 63);
+}
+
 size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
     const double t0 = now_ms();
-    if (!fixed_ready) compute_fixed();
+    if (!cands_ready) { compute_candidates(); prof.seqs = now_ms() - t0; }
+    if (first_pass) {   // every candidate is evaluated in the first pass; do the byte comparisons for all of them in parallel
+        spec_len.resize(cands.size());
+        const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads() * 4, cands.size() / 1024));
+        parallel_tasks(T, [&](size_t t) {
+            for (size_t i = cands.size() * t / T; i < cands.size() * (t + 1) / T; ++i) spec_len[i] = common_length(cands[i]);
+        });
+        prof.check = now_ms() - t0;
+    }
     size_t total_shifted = 0;
     std::string common;
-    // character i counted from the start / from the end of a unitig strand (UnitigStrand::get_seq without the copy)
-    auto from_start = [&](UStrand s, size_t i) { const uint32_t u = us_index(s); const char* p = seq_ptr(u); return us_reverse(s) ? comp(p[len[u] - 1 - i]) : p[i]; };
-    auto from_end = [&](UStrand s, size_t i) { const uint32_t u = us_index(s); const char* p = seq_ptr(u); return us_reverse(s) ? comp(p[i]) : p[len[u] - 1 - i]; };
+    for (size_t w = 0; w < dirty.size(); ++w) {
+        uint64_t passed = 0;                       // candidates of this word already visited in this pass
+        for (;;) {
+            // a candidate marked again at or behind the current position waits for the next pass, exactly as the
+            // reference's loop would only reach it again in its next call
+            const uint64_t avail = dirty[w] & ~passed;
+            if (!avail) break;
+            const int bit = __builtin_ctzll(avail);
+            passed = bit == 63 ? ~0ull : ((2ull << bit) - 1);
+            dirty[w] &= ~(1ull << bit);
+            const size_t ci = w * 64 + (size_t)bit;
+            const Candidate cand = cands[ci];
+            const uint32_t idx = cand.idx;
+            const UStrand self_fwd = us_make(idx, false);
+            const UStrand* grp = cand.side == 0 ? prev_begin(self_fwd) : next_begin(self_fwd);
+            const uint32_t gn = cand.side == 0 ? prev_size(self_fwd) : next_size(self_fwd);
 
-    for (uint32_t n = 0; n < U; ++n) {
-        const uint32_t idx = order[n];
-        const UStrand self_fwd = us_make(idx, false);
-
-        // ---- get_exclusive_inputs (:233-255) + shift_sequence_1 (:89-116) ----
-        {
-            const UStrand* grp = prev_begin(self_fwd); const uint32_t gn = prev_size(self_fwd);
-            bool ok = gn >= 2 && !fixed_start[idx];
-            for (uint32_t a = 0; ok && a < gn; ++a) {
-                const UStrand p = grp[a];
-                if (!(next_size(p) == 1 && next_begin(p)[0] == self_fwd) || us_index(p) == idx) ok = false;
-                else if ((!us_reverse(p) && fixed_end[us_index(p)]) || (us_reverse(p) && fixed_start[us_index(p)])) ok = false;
+            bool dup = false, pristine = first_pass; uint32_t min_len = 0xFFFFFFFFu;
+            for (uint32_t a = 0; a < gn; ++a) {
+                const uint32_t s = us_index(grp[a]);
+                if (rec[s].len < min_len) min_len = rec[s].len;
+                if (rec[s].flags) pristine = false;
+                for (uint32_t b = 0; b < a; ++b) if (s == us_index(grp[b])) dup = true;
             }
-            if (ok) {
-                size_t c = len[us_index(grp[0])];               // get_common_end_seq, :298-312
-                bool dup = false; uint32_t min_len = 0xFFFFFFFFu;
+            const size_t common_len = pristine ? spec_len[ci] : common_length(cand);
+            size_t c = common_len;
+            // avoid_zero_len_unitigs (:141-158) and avoid_start_of_path (:161-181) trim the common piece on the far side
+            if (c > 0) c = std::min<size_t>(c, (min_len - 1) / (dup ? 2 : 1));
+            const uint32_t min_pos = cand.side == 0 ? rec[idx].min_fpos : rec[idx].min_rpos;
+            if (c > 0) c = min_pos == 0 ? 0 : std::min<size_t>(c, min_pos - 1);
+            if (c == 0) continue;
+
+            common.resize(c);
+            {
+                const uint32_t u0 = us_index(grp[0]); const unsigned char* p0 = (const unsigned char*)seq_ptr(u0);
+                const bool at_back = (cand.side == 0) != us_reverse(grp[0]);
+                const Cursor first{at_back ? p0 + rec[u0].len - 1 : p0, at_back ? -1 : 1, us_reverse(grp[0]) ? g_lut.comp : g_lut.same};
+                if (cand.side == 0) for (size_t i = 0; i < c; ++i) common[c - 1 - i] = (char)first.at(i);
+                else for (size_t i = 0; i < c; ++i) common[i] = (char)first.at(i);
+            }
+            if (cand.side == 0) {   // shift_sequence_1 (:89-116): common end of the inputs moves to the start of this unitig
                 for (uint32_t a = 0; a < gn; ++a) {
-                    const uint32_t la = len[us_index(grp[a])];
-                    if (la < c) c = la;
-                    size_t m = 0; while (m < c && from_end(grp[a], m) == from_end(grp[0], m)) ++m;
-                    c = m;
-                    if (la < min_len) min_len = la;
-                    for (uint32_t b = 0; b < a; ++b) if (us_index(grp[a]) == us_index(grp[b])) dup = true;
+                    const uint32_t s = us_index(grp[a]);
+                    if (!us_reverse(grp[a])) { rec[s].min_rpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].room_after += (uint32_t)c; }                 // remove_seq_from_end, unitig.rs:225-232
+                    else { rec[s].min_fpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].seq_off += c; rec[s].room_before += (uint32_t)c; }                // remove_seq_from_start, unitig.rs:216-223
                 }
-                // avoid_zero_len_unitigs (:141-158) and avoid_start_of_path (:161-181): both trim from the start
-                if (c > 0) c = std::min<size_t>(c, (min_len - 1) / (dup ? 2 : 1));
-                if (c > 0) c = min_fpos[idx] == 0 ? 0 : std::min<size_t>(c, min_fpos[idx] - 1);
-                if (c > 0) {
-                    common.resize(c);
-                    for (size_t i = 0; i < c; ++i) common[c - 1 - i] = from_end(grp[0], i);
-                    for (uint32_t a = 0; a < gn; ++a) {
-                        const uint32_t s = us_index(grp[a]);
-                        if (!us_reverse(grp[a])) { min_rpos[s] += (uint32_t)c; len[s] -= (uint32_t)c; room_after[s] += (uint32_t)c; }                       // remove_seq_from_end, unitig.rs:225-232
-                        else { min_fpos[s] += (uint32_t)c; len[s] -= (uint32_t)c; seq_off[s] += c; room_before[s] += (uint32_t)c; }                      // remove_seq_from_start, unitig.rs:216-223
-                    }
-                    grow_front(idx, (uint32_t)c);                                                                                                          // add_seq_to_start, unitig.rs:234-240
-                    seq_off[idx] -= c; room_before[idx] -= (uint32_t)c; len[idx] += (uint32_t)c; min_fpos[idx] -= (uint32_t)c;
-                    memcpy(arena.data() + seq_off[idx], common.data(), c);
-                    total_shifted += c;
-                }
-            }
-        }
-
-        // ---- get_exclusive_outputs (:258-280) + shift_sequence_2 (:119-138) ----
-        {
-            const UStrand* grp = next_begin(self_fwd); const uint32_t gn = next_size(self_fwd);
-            bool ok = gn >= 2 && !fixed_end[idx];
-            for (uint32_t a = 0; ok && a < gn; ++a) {
-                const UStrand q = grp[a];
-                if (!(prev_size(q) == 1 && prev_begin(q)[0] == self_fwd) || us_index(q) == idx) ok = false;
-                else if ((!us_reverse(q) && fixed_start[us_index(q)]) || (us_reverse(q) && fixed_end[us_index(q)])) ok = false;
-            }
-            if (ok) {
-                size_t c = len[us_index(grp[0])];               // get_common_start_seq, :283-295
-                bool dup = false; uint32_t min_len = 0xFFFFFFFFu;
+                grow_front(idx, (uint32_t)c);                                                                                                    // add_seq_to_start, unitig.rs:234-240
+                rec[idx].seq_off -= c; rec[idx].room_before -= (uint32_t)c; rec[idx].len += (uint32_t)c; rec[idx].min_fpos -= (uint32_t)c;
+                memcpy(arena + rec[idx].seq_off, common.data(), c);
+            } else {                // shift_sequence_2 (:119-138): common start of the outputs moves to the end of this unitig
                 for (uint32_t a = 0; a < gn; ++a) {
-                    const uint32_t la = len[us_index(grp[a])];
-                    if (la < c) c = la;
-                    size_t m = 0; while (m < c && from_start(grp[a], m) == from_start(grp[0], m)) ++m;
-                    c = m;
-                    if (la < min_len) min_len = la;
-                    for (uint32_t b = 0; b < a; ++b) if (us_index(grp[a]) == us_index(grp[b])) dup = true;
+                    const uint32_t s = us_index(grp[a]);
+                    if (!us_reverse(grp[a])) { rec[s].min_fpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].seq_off += c; rec[s].room_before += (uint32_t)c; }
+                    else { rec[s].min_rpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].room_after += (uint32_t)c; }
                 }
-                if (c > 0) c = std::min<size_t>(c, (min_len - 1) / (dup ? 2 : 1));
-                if (c > 0) c = min_rpos[idx] == 0 ? 0 : std::min<size_t>(c, min_rpos[idx] - 1);
-                if (c > 0) {
-                    common.resize(c);
-                    for (size_t i = 0; i < c; ++i) common[i] = from_start(grp[0], i);
-                    for (uint32_t a = 0; a < gn; ++a) {
-                        const uint32_t s = us_index(grp[a]);
-                        if (!us_reverse(grp[a])) { min_fpos[s] += (uint32_t)c; len[s] -= (uint32_t)c; seq_off[s] += c; room_before[s] += (uint32_t)c; }
-                        else { min_rpos[s] += (uint32_t)c; len[s] -= (uint32_t)c; room_after[s] += (uint32_t)c; }
-                    }
-                    grow_back(idx, (uint32_t)c);                                                                                                           // add_seq_to_end, unitig.rs:242-248
-                    memcpy(arena.data() + seq_off[idx] + len[idx], common.data(), c);
-                    room_after[idx] -= (uint32_t)c; len[idx] += (uint32_t)c; min_rpos[idx] -= (uint32_t)c;
-                    total_shifted += c;
-                }
+                grow_back(idx, (uint32_t)c);                                                                                                     // add_seq_to_end, unitig.rs:242-248
+                memcpy(arena + rec[idx].seq_off + rec[idx].len, common.data(), c);
+                rec[idx].room_after -= (uint32_t)c; rec[idx].len += (uint32_t)c; rec[idx].min_rpos -= (uint32_t)c;
             }
+            total_shifted += c;
+            rec[idx].flags = 1; mark_dependents(idx);
+            for (uint32_t a = 0; a < gn; ++a) { rec[us_index(grp[a])].flags = 1; mark_dependents(us_index(grp[a])); }
+            // The whole common piece moved: what is left of the sources has no common end/start any more, so this candidate
+            // can only find something again after another shift touches one of its unitigs (which marks it again).
+            if (c == common_len) dirty[w] &= ~(1ull << bit);
         }
     }
+    first_pass = false;
+    if (prof.passes == 0) prof.links = now_ms() - t0;      // first pass (incl. candidate listing)
     prof.expand += now_ms() - t0; prof.passes += 1;
     return total_shifted;
 }
@@ -352,6 +386,7 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
 void HostGraph::simplify_structure() {   // graph_simplification.rs:26-40
     while (expand_repeats() > 0) {}
     renumber();
+    cands_ready = false;      // the numbering order changed: a later call starts from the new order
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -360,43 +395,113 @@ void HostGraph::simplify_structure() {   // graph_simplification.rs:26-40
 namespace {
 inline char* put_uint(char* p, uint64_t v) { auto r = std::to_chars(p, p + 24, v); return r.ptr; }
 inline char* put_str(char* p, const char* s, size_t n) { memcpy(p, s, n); return p + n; }
+inline uint32_t digits10(uint64_t v) { uint32_t d = 1; while (v >= 10) { v /= 10; ++d; } return d; }
 }  // namespace
 
 void HostGraph::gfa_text(const std::vector<HostSeq>& seqs, std::string& out) const {
-    size_t est = 64 + total_length() + (size_t)U * 40 + next.size() * 40 + path.size() * 12;
-    for (auto& s : seqs) est += 96 + s.filename.size() + s.contig_header.size();
-    out.resize(est);
-    char* const base = &out[0];
-    char* p = base;
-    p = put_str(p, "H\tVN:Z:1.0\tKM:i:", 16); p = put_uint(p, k); *p++ = '\n';
-    for (uint32_t n = 0; n < U; ++n) {   // unitig.rs:167-171; depth is integral here so {:.2} renders as N.00
-        const uint32_t idx = order[n];
-        *p++ = 'S'; *p++ = '\t'; p = put_uint(p, n + 1); *p++ = '\t';
-        p = put_str(p, seq_ptr(idx), len[idx]);
-        p = put_str(p, "\tDP:f:", 6); p = put_uint(p, depth[idx]); p = put_str(p, ".00\n", 4);
+    // Decimal text of every unitig number, by seed index, so that the hot loops copy bytes instead of dividing.
+    std::vector<uint64_t> num_txt(U); std::vector<uint8_t> num_len(U);
+    const size_t TU = std::max<size_t>(1, std::min<size_t>(host_threads() * 4, (size_t)U / 2048));
+    auto ub = [&](size_t t) { return (uint32_t)((uint64_t)U * t / TU); };
+    // task list: S-line blocks, L-line blocks (both by position in `order`), and P-line pieces (by path range)
+    struct Piece { size_t seq; uint64_t a, b; };
+    std::vector<Piece> pieces;
+    const uint64_t P_CHUNK = 65536;
+    for (size_t i = 0; i < seqs.size(); ++i) {
+        uint64_t a = path_off[i];
+        do { const uint64_t b = std::min(path_off[i + 1], a + P_CHUNK); pieces.push_back({i, a, b}); a = b; } while (a < path_off[i + 1]);
     }
-    for (uint32_t n = 0; n < U; ++n) {   // get_links_for_gfa, :333-350: forward_next then reverse_next of each unitig
-        const uint32_t idx = order[n];
-        for (uint32_t rev = 0; rev < 2; ++rev) {
-            const UStrand from = us_make(idx, rev != 0);
-            for (uint32_t x = next_off[from]; x < next_off[from + 1]; ++x) {
-                const UStrand to = next[x];
-                *p++ = 'L'; *p++ = '\t'; p = put_uint(p, n + 1); *p++ = '\t'; *p++ = rev ? '-' : '+'; *p++ = '\t';
-                p = put_uint(p, number[us_index(to)]); *p++ = '\t'; *p++ = us_reverse(to) ? '-' : '+'; p = put_str(p, "\t0M\n", 4);
+    std::vector<uint64_t> s_size(TU), l_size(TU), p_size(pieces.size());
+    parallel_tasks(TU, [&](size_t t) {
+        for (uint32_t n = ub(t); n < ub(t + 1); ++n) {
+            const uint32_t idx = order[n];
+            char buf[24]; const uint32_t d = (uint32_t)(put_uint(buf, (uint64_t)n + 1) - buf);
+            uint64_t v = 0; memcpy(&v, buf, d < 8 ? d : 8); num_txt[idx] = v; num_len[idx] = (uint8_t)d;
+        }
+    });
+    if (U >= 100000000u) throw std::runtime_error("more than 99,999,999 unitigs are not supported by the GFA writer");
+    parallel_tasks(TU, [&](size_t t) {
+        uint64_t ss = 0, ls = 0;
+        for (uint32_t n = ub(t); n < ub(t + 1); ++n) {
+            const uint32_t idx = order[n];
+            ss += 2 + num_len[idx] + 1 + rec[idx].len + 6 + digits10(depth[idx]) + 4;            // "S\t" num "\t" seq "\tDP:f:" depth ".00\n"
+            for (uint32_t rev = 0; rev < 2; ++rev) {
+                const UStrand from = us_make(idx, rev != 0);
+                for (uint32_t x = next_off[from]; x < next_off[from + 1]; ++x)
+                    ls += 2 + num_len[idx] + 3 + num_len[us_index(next[x])] + 2 + 4;           // "L\t" a "\t+\t" b "\t+" "\t0M\n"
             }
         }
-    }
-    for (size_t i = 0; i < seqs.size(); ++i) {   // get_gfa_path_line, :352-360
-        const HostSeq& s = seqs[i];
-        *p++ = 'P'; *p++ = '\t'; p = put_uint(p, s.id); *p++ = '\t';
-        for (uint64_t x = path_off[i]; x < path_off[i + 1]; ++x) {
-            if (x != path_off[i]) *p++ = ',';
-            p = put_uint(p, number[us_index(path[x])]); *p++ = us_reverse(path[x]) ? '-' : '+';
+        s_size[t] = ss; l_size[t] = ls;
+    });
+    parallel_tasks(pieces.size(), [&](size_t q) {
+        const Piece& pc = pieces[q]; const HostSeq& s = seqs[pc.seq];
+        uint64_t sz = 0;
+        if (pc.a == path_off[pc.seq]) sz += 2 + digits10(s.id) + 1;                                                      // "P\t" id "\t"
+        for (uint64_t x = pc.a; x < pc.b; ++x) sz += num_len[us_index(path[x])] + 2;                                  // num sign ","
+        if (pc.b == path_off[pc.seq + 1]) {
+            if (pc.b > pc.a) sz -= 1;                                                                                  // no comma after the last step
+            sz += 8 + digits10(s.length) + 6 + s.filename.size() + 6 + s.contig_header.size() + 1;
         }
-        p = put_str(p, "\t*\tLN:i:", 8); p = put_uint(p, s.length);
-        p = put_str(p, "\tFN:Z:", 6); p = put_str(p, s.filename.data(), s.filename.size());
-        p = put_str(p, "\tHD:Z:", 6); p = put_str(p, s.contig_header.data(), s.contig_header.size()); *p++ = '\n';
-    }
-    if ((size_t)(p - base) > est) throw std::runtime_error("GFA size estimate too small");
-    out.resize((size_t)(p - base));
+        p_size[q] = sz;
+    });
+    char head[64]; char* hp = put_str(head, "H\tVN:Z:1.0\tKM:i:", 16); hp = put_uint(hp, k); *hp++ = '\n';
+    const uint64_t head_size = (uint64_t)(hp - head);
+    std::vector<uint64_t> s_at(TU), l_at(TU), p_at(pieces.size());
+    uint64_t at = head_size;
+    for (size_t t = 0; t < TU; ++t) { s_at[t] = at; at += s_size[t]; }
+    for (size_t t = 0; t < TU; ++t) { l_at[t] = at; at += l_size[t]; }
+    for (size_t q = 0; q < pieces.size(); ++q) { p_at[q] = at; at += p_size[q]; }
+    out.resize(at + 8);                 // 8 spare bytes: the number copies below write whole words
+    char* const base = &out[0];
+    memcpy(base, head, head_size);
+    auto put_num = [&](char* p, uint32_t idx) { memcpy(p, &num_txt[idx], 8); return p + num_len[idx]; };
+
+    parallel_tasks(2 * TU + pieces.size(), [&](size_t task) {
+        if (task < TU) {                                        // S lines, unitig.rs:167-171; depth is integral so {:.2} renders as N.00
+            char* p = base + s_at[task];
+            for (uint32_t n = ub(task); n < ub(task + 1); ++n) {
+                const uint32_t idx = order[n];
+                *p++ = 'S'; *p++ = '\t'; p = put_uint(p, (uint64_t)n + 1); *p++ = '\t';
+                p = put_str(p, seq_ptr(idx), rec[idx].len);
+                p = put_str(p, "\tDP:f:", 6); p = put_uint(p, depth[idx]); p = put_str(p, ".00\n", 4);
+            }
+            if ((uint64_t)(p - base) != s_at[task] + s_size[task]) throw std::runtime_error("GFA S-line size mismatch");
+        } else if (task < 2 * TU) {                             // L lines, get_links_for_gfa :333-350: forward_next then reverse_next
+            const size_t t = task - TU;
+            char* p = base + l_at[t];
+            for (uint32_t n = ub(t); n < ub(t + 1); ++n) {
+                const uint32_t idx = order[n];
+                for (uint32_t rev = 0; rev < 2; ++rev) {
+                    const UStrand from = us_make(idx, rev != 0);
+                    for (uint32_t x = next_off[from]; x < next_off[from + 1]; ++x) {
+                        const UStrand to = next[x];
+                        *p++ = 'L'; *p++ = '\t'; p = put_uint(p, (uint64_t)n + 1); *p++ = '\t'; *p++ = rev ? '-' : '+'; *p++ = '\t';
+                        p = put_uint(p, number[us_index(to)]); *p++ = '\t'; *p++ = us_reverse(to) ? '-' : '+'; p = put_str(p, "\t0M\n", 4);
+                    }
+                }
+            }
+            if ((uint64_t)(p - base) != l_at[t] + l_size[t]) throw std::runtime_error("GFA L-line size mismatch");
+        } else {                                                // P lines, get_gfa_path_line :352-360
+            const size_t q = task - 2 * TU;
+            const Piece& pc = pieces[q]; const HostSeq& s = seqs[pc.seq];
+            char* p = base + p_at[q];
+            if (pc.a == path_off[pc.seq]) { *p++ = 'P'; *p++ = '\t'; p = put_uint(p, s.id); *p++ = '\t'; }
+            const bool last_piece = pc.b == path_off[pc.seq + 1];
+            for (uint64_t x = pc.a; x < pc.b; ++x) {
+                // whole-word copies spill up to 7 bytes past the number; the spill is overwritten by this thread's next writes,
+                // except near the end of the piece where the neighbouring piece may already be in place
+                const uint32_t u = us_index(path[x]);
+                if (x + 8 < pc.b) p = put_num(p, u); else { memcpy(p, &num_txt[u], num_len[u]); p += num_len[u]; }
+                *p++ = us_reverse(path[x]) ? '-' : '+';
+                if (!(last_piece && x + 1 == pc.b)) *p++ = ',';
+            }
+            if (last_piece) {
+                p = put_str(p, "\t*\tLN:i:", 8); p = put_uint(p, s.length);
+                p = put_str(p, "\tFN:Z:", 6); p = put_str(p, s.filename.data(), s.filename.size());
+                p = put_str(p, "\tHD:Z:", 6); p = put_str(p, s.contig_header.data(), s.contig_header.size()); *p++ = '\n';
+            }
+            if ((uint64_t)(p - base) != p_at[q] + p_size[q]) throw std::runtime_error("GFA P-line size mismatch");
+        }
+    });
+    out.resize(at);
 }

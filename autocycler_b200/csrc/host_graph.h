@@ -20,8 +20,7 @@ struct HostSeq {              // sequence.rs:19-28 minus the bytes (they live in
     uint64_t start;           // global coordinate of padded byte 0
 };
 
-// A unitig strand: (seed index << 1) | reverse.
-typedef uint32_t UStrand;
+// A unitig strand: (seed index << 1) | reverse (UStrand, pipeline.h).
 static inline uint32_t us_index(UStrand s) { return s >> 1; }
 static inline bool us_reverse(UStrand s) { return s & 1; }
 static inline UStrand us_make(uint32_t idx, bool reverse) { return (idx << 1) | (reverse ? 1u : 0u); }
@@ -34,26 +33,25 @@ public:
     uint32_t k = 0;
     uint32_t U = 0;
     // --- per unitig, seed order (unitig.rs:30-45) ---
+    // The arrays below are the pipeline's pinned result buffers, adopted and edited in place.
     std::vector<uint32_t> number;             // Unitig.number (1-based position in `order`)
-    std::vector<uint32_t> depth;              // integral on this path: every k-mer of a chain has the same depth
-    std::vector<uint32_t> len;                // forward_seq.len()
-    std::vector<uint64_t> seq_off;            // forward_seq = arena[seq_off, seq_off+len)
-    std::vector<uint32_t> room_before, room_after;
-    std::vector<uint32_t> min_fpos, min_rpos; // min over forward_positions / reverse_positions (all entries shift together)
-    std::vector<char> arena;
+    const uint32_t* depth = nullptr;          // integral on this path: every k-mer of a chain has the same depth
+    UnitigRec* rec = nullptr;                 // sequence location, length, minimum positions, arena slack (pipeline.h)
+    char* arena = nullptr; uint64_t arena_used = 0, arena_cap = 0;
+    std::vector<char> arena_overflow;         // only if repeat expansion outgrows the pinned arena
     // --- links, CSR over strands (index 2*idx + reverse): forward_next/reverse_next and forward_prev/reverse_prev ---
-    std::vector<uint32_t> next_off, prev_off; // [2U+1]
-    std::vector<UStrand> next, prev;
+    const uint32_t* next_off = nullptr; const uint32_t* prev_off = nullptr;   // [2U+1]
+    const UStrand* next = nullptr; const UStrand* prev = nullptr; uint64_t n_links = 0;
     // --- numbering order and paths ---
     std::vector<uint32_t> order;              // order[n-1] = seed index of unitig number n
-    std::vector<uint64_t> path_off;           // [S+1]
-    std::vector<UStrand> path;                // get_unitig_path_for_sequence for every sequence (unitig_graph.rs:447-465)
+    const uint64_t* path_off = nullptr;       // [S+1]
+    const UStrand* path = nullptr; uint64_t n_path = 0; uint32_t n_seqs = 0;   // get_unitig_path_for_sequence for every sequence (unitig_graph.rs:447-465)
     // optional full position lists (ac_config.keep_positions): CSR per unitig, value = pos << 16 | seq_id_and_strand
     std::vector<uint64_t> fpos_off, rpos_off, fpos, rpos;
     HostProfile prof;
 
     // unitig_graph.rs:36-48 from the device result (build, simplify_seqs, create_links, trim_overlaps, renumber, check)
-    void build(const PipelineResult& r, const std::vector<HostSeq>& seqs, const uint8_t* ascii, uint32_t k, bool keep_positions);
+    void build(const PipelineResult& r, const std::vector<HostSeq>& seqs, uint32_t k, bool keep_positions);
     void renumber();                          // unitig_graph.rs:295-315
     void check_links() const;                 // unitig_graph.rs:752-793
     void simplify_structure();                // graph_simplification.rs:26-40
@@ -61,15 +59,28 @@ public:
     void gfa_text(const std::vector<HostSeq>& seqs, std::string& out) const;   // unitig_graph.rs:317-360
     uint64_t total_length() const;
     uint64_t link_count_single() const;       // unitig_graph.rs:478-507 (.1)
-    const char* seq_ptr(uint32_t idx) const { return arena.data() + seq_off[idx]; }
-    const UStrand* next_begin(UStrand s) const { return next.data() + next_off[s]; }
+    const char* seq_ptr(uint32_t idx) const { return arena + rec[idx].seq_off; }
+    const UStrand* next_begin(UStrand s) const { return next + next_off[s]; }
     uint32_t next_size(UStrand s) const { return next_off[s + 1] - next_off[s]; }
-    const UStrand* prev_begin(UStrand s) const { return prev.data() + prev_off[s]; }
+    const UStrand* prev_begin(UStrand s) const { return prev + prev_off[s]; }
     uint32_t prev_size(UStrand s) const { return prev_off[s + 1] - prev_off[s]; }
 private:
     std::vector<uint8_t> fixed_start, fixed_end;
     bool fixed_ready = false;
     void compute_fixed();
+    // repeat expansion work list: (unitig, side) pairs that satisfy the structural conditions of expand_repeats
+    struct Candidate { uint32_t idx; uint32_t side; };
+    std::vector<Candidate> cands;
+    std::vector<int32_t> cand_at;             // [2U] candidate index of (unitig, side), -1 if none
+    std::vector<uint64_t> dirty;              // bitmap over cands: must be (re-)evaluated
+    std::vector<uint32_t> spec_len;           // common-piece lengths computed in parallel from the untouched graph
+    bool cands_ready = false, first_pass = true;
+    void compute_candidates();
+    uint32_t common_length(const Candidate& cand) const;
+    struct Deps { int32_t c[6]; };            // candidates that read unitig u: its own two, and those it exclusively feeds / is fed by
+    std::vector<Deps> deps;
+    void compute_dependents();
+    void mark_dependents(uint32_t u);
     void grow_front(uint32_t idx, uint32_t need);
     void grow_back(uint32_t idx, uint32_t need);
     void relocate(uint32_t idx, uint32_t before, uint32_t after);

@@ -415,6 +415,181 @@ template <int W> struct LinkBody {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Seed order and the host-ready arrays
+// ------------------------------------------------------------------------------------------------
+// Seed order = ascending byte order of the seed k-mer text (kmer_graph.rs:168-173), i.e. key_less5 on the stored
+// seed k-mers.  The seeds are minima, so their leading bits are heavily skewed and bucketing on them does not work;
+// a bottom-up merge sort does: in every pass each element finds its place in the merged pair of runs with one binary
+// search in the sibling run (thread per element, U <= ~10^6 keys, all of them L2 resident).
+struct SeedLess {
+    const DeviceUnitig* unitigs; int W;
+    AC_D bool operator()(uint32_t a, uint32_t b) const {
+        const DeviceUnitig& x = unitigs[a]; const DeviceUnitig& y = unitigs[b];
+        const int lx = x.min_d > 0 ? x.min_d : 0, ly = y.min_d > 0 ? y.min_d : 0;
+        if (lx != ly) return lx > ly;
+        for (int w = 0; w < W; ++w) if (x.min_w[w] != y.min_w[w]) return x.min_w[w] < y.min_w[w];
+        const int tx = x.min_d < 0 ? -x.min_d : 0, ty = y.min_d < 0 ? -y.min_d : 0;
+        return tx > ty;
+    }
+};
+#define AC_SORT_LEAF 8
+struct SortLeafBody {   // insertion sort of AC_SORT_LEAF consecutive unitigs: the first three merge levels in one launch
+    SeedLess less; uint32_t n; uint32_t* idx;
+    AC_D void operator()(uint64_t c) const {
+        const uint32_t a = (uint32_t)c * AC_SORT_LEAF, b = a + AC_SORT_LEAF < n ? a + AC_SORT_LEAF : n;
+        uint32_t v[AC_SORT_LEAF];
+        for (uint32_t x = a; x < b; ++x) {
+            uint32_t y = x - a;
+            while (y > 0 && less(x, v[y - 1])) { v[y] = v[y - 1]; --y; }
+            v[y] = x;
+        }
+        for (uint32_t x = a; x < b; ++x) idx[x] = v[x - a];
+    }
+};
+struct MergePassBody {
+    SeedLess less; uint32_t n, width; const uint32_t* in; uint32_t* out;
+    AC_D void operator()(uint64_t i) const {
+        const uint32_t me = in[i];
+        const uint32_t run = (uint32_t)i / width, pair_start = (run & ~1u) * width, run_start = run * width;
+        uint32_t lo, hi;                                   // the sibling run
+        const bool left = !(run & 1u);
+        if (left) { lo = run_start + width; hi = lo + width; } else { lo = pair_start; hi = run_start; }
+        if (lo > n) lo = n;
+        if (hi > n) hi = n;
+        const uint32_t base = lo;
+        while (lo < hi) {                                  // left run: elements of the sibling strictly below me; right run: not above me
+            const uint32_t mid = (lo + hi) >> 1;
+            const bool before = left ? less(in[mid], me) : !less(me, in[mid]);
+            if (before) lo = mid + 1; else hi = mid;
+        }
+        out[pair_start + ((uint32_t)i - run_start) + (lo - base)] = me;
+    }
+};
+
+struct IotaBody { uint32_t* out; AC_D void operator()(uint64_t i) const { out[i] = (uint32_t)i; } };
+
+// perm[s] = device unitig at seed position s.  Fills rank, the seed-ordered scalars and the arena space request.
+struct SeedGatherBody {
+    const uint32_t* perm; const DeviceUnitig* unitigs; uint32_t n;
+    uint32_t* rank; uint32_t* len; uint32_t* depth; uint32_t* need; uint32_t* min_fpos; uint32_t* min_rpos;
+    AC_D void operator()(uint64_t s) const {
+        if (s == n) { need[s] = 0; return; }
+        const uint32_t j = perm[s];
+        const DeviceUnitig& u = unitigs[j];
+        rank[j] = (uint32_t)s; len[s] = u.len; depth[s] = u.depth; need[s] = u.len + 2 * AC_SEQ_SLACK;
+        min_fpos[s] = 0xFFFFFFFFu; min_rpos[s] = 0xFFFFFFFFu;
+    }
+};
+struct SeqOffBody { const uint32_t* need_off; uint64_t* seq_off; AC_D void operator()(uint64_t s) const { seq_off[s] = (uint64_t)need_off[s] + AC_SEQ_SLACK; } };
+
+// Trimmed forward sequence of every unitig (unitig.rs:120-133, 157-165): the centre base of each of its k-mers,
+// reverse-complemented when the seed k-mer lies on the other strand of the representative occurrence.
+struct EmitSeqBody {
+    const uint64_t* packed; uint32_t h; const DeviceUnitig* unitigs; uint32_t n_unitigs; const uint32_t* chunk_off;
+    const uint32_t* rank; const uint64_t* seq_off; char* arena;
+    AC_D void operator()(uint64_t c) const {
+        uint32_t lo = 0, hi = n_unitigs;
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (chunk_off[mid] <= c) lo = mid; else hi = mid; }
+        const DeviceUnitig u = unitigs[lo];
+        const uint64_t first = (c - chunk_off[lo]) * AC_MINCHUNK;
+        const uint64_t n = (u.len - first < AC_MINCHUNK) ? u.len - first : AC_MINCHUNK;
+        char* dst = arena + seq_off[rank[lo]];
+        const uint64_t g0 = u.start + h + first;
+        if (!u.flip) for (uint64_t t = 0; t < n; ++t) dst[first + t] = "ACGT"[packed_base(packed, g0 + t)];
+        else for (uint64_t t = 0; t < n; ++t) dst[u.len - 1 - (first + t)] = "TGCA"[packed_base(packed, g0 + t)];
+    }
+};
+
+AC_D UStrand seed_strand(uint32_t dev_strand, const uint32_t* rank, const DeviceUnitig* unitigs) {
+    const uint32_t j = dev_strand >> 1;
+    return (rank[j] << 1) | ((dev_strand & 1u) ^ (unitigs[j].flip & 1u));
+}
+
+struct LinkCountBody {
+    const uint32_t* link_count; const uint32_t* rank; const DeviceUnitig* unitigs; uint32_t n_strands; uint32_t* cnt;
+    AC_D void operator()(uint64_t i) const {
+        if (i == n_strands) { cnt[i] = 0; return; }
+        cnt[seed_strand((uint32_t)i, rank, unitigs)] = link_count[i];
+    }
+};
+
+// forward_next / reverse_next in the push order of create_links (unitig_graph.rs:248-286), which iterates the unitigs
+// in seed order: forward_next(a) = all b+ ascending then all b- ascending; reverse_next(a) = x- for x < a (pushed while
+// iteration x handled x+ -> a+), then a- (self loop), then all b+ ascending, then x- for x > a.
+struct LinkOrderBody {
+    const uint32_t* link_count; const uint32_t* links; const uint32_t* rank; const DeviceUnitig* unitigs;
+    const uint32_t* next_off; UStrand* next; uint32_t* prev_cnt;
+    AC_D static uint64_t order_key(UStrand from, UStrand t) {
+        const uint32_t a = from >> 1, b = t >> 1; const bool trev = t & 1;
+        uint32_t phase;
+        if (!(from & 1)) phase = trev ? 1 : 0;
+        else phase = trev ? (b < a ? 0 : (b == a ? 1 : 3)) : 2;
+        return ((uint64_t)phase << 32) | b;
+    }
+    AC_D void operator()(uint64_t i) const {
+        const UStrand from = seed_strand((uint32_t)i, rank, unitigs);
+        const uint32_t n = link_count[i];
+        UStrand t[AC_MAX_LINKS];
+        for (uint32_t x = 0; x < n && x < AC_MAX_LINKS; ++x) t[x] = seed_strand(links[i * AC_MAX_LINKS + x], rank, unitigs);
+        for (uint32_t x = 1; x < n; ++x) {           // insertion sort, n <= 5
+            const UStrand v = t[x]; const uint64_t kv = order_key(from, v); uint32_t y = x;
+            while (y > 0 && order_key(from, t[y - 1]) > kv) { t[y] = t[y - 1]; --y; }
+            t[y] = v;
+        }
+        UStrand* out = next + next_off[from];
+        for (uint32_t x = 0; x < n; ++x) { out[x] = t[x]; ac_atomic_add(&prev_cnt[t[x]], 1u); }
+    }
+};
+struct PrevFillBody {   // (a,s) -> (b,t) puts (a,s) into prev(b,t)
+    const uint32_t* next_off; const UStrand* next; const uint32_t* prev_off; uint32_t* cursor; UStrand* prev;
+    AC_D void operator()(uint64_t from) const {
+        for (uint32_t x = next_off[from]; x < next_off[from + 1]; ++x) { const UStrand t = next[x]; prev[prev_off[t] + ac_atomic_add(&cursor[t], 1u)] = (UStrand)from; }
+    }
+};
+struct PrevSortBody {   // ascending, so that the result does not depend on the order the atomics landed in
+    const uint32_t* prev_off; UStrand* prev;
+    AC_D void operator()(uint64_t s) const {
+        UStrand* p = prev + prev_off[s]; const uint32_t n = prev_off[s + 1] - prev_off[s];
+        for (uint32_t x = 1; x < n; ++x) { const UStrand v = p[x]; uint32_t y = x; while (y > 0 && p[y - 1] > v) { p[y] = p[y - 1]; --y; } p[y] = v; }
+    }
+};
+
+// The path of every sequence is the list of its occurrences (unitig_graph.rs:447-465 walks the same list through
+// links and positions); forward_positions / reverse_positions only enter the output through their minimum.
+struct PathBody {
+    const SeqInfo* seqs; uint32_t n_seqs; const uint64_t* run_start; const uint32_t* run_len; const uint32_t* run_unitig;
+    const uint32_t* rank; const DeviceUnitig* unitigs; UStrand* path; uint32_t* min_fpos; uint32_t* min_rpos;
+    AC_D void operator()(uint64_t x) const {
+        const uint32_t dev = run_unitig[x] >> 1, same = run_unitig[x] & 1;
+        const uint32_t s = rank[dev];
+        const bool plus = (same ^ (unitigs[dev].flip & 1u)) != 0;
+        path[x] = (s << 1) | (plus ? 0u : 1u);
+        const uint64_t g = run_start[x];
+        const SeqInfo q = seqs[find_seq(seqs, n_seqs, g)];
+        const uint32_t fs = (uint32_t)(g - q.start), mirrored = q.len - fs - run_len[x];   // kmer_graph.rs:103-108
+        ac_atomic_min(&min_fpos[s], plus ? fs : mirrored);
+        ac_atomic_min(&min_rpos[s], plus ? mirrored : fs);
+    }
+};
+struct PackRecBody {   // structure-of-arrays -> the host's 32-byte records
+    const uint64_t* seq_off; const uint32_t* len; const uint32_t* min_fpos; const uint32_t* min_rpos; UnitigRec* rec;
+    AC_D void operator()(uint64_t s) const {
+        UnitigRec r; r.seq_off = seq_off[s]; r.len = len[s]; r.min_fpos = min_fpos[s]; r.min_rpos = min_rpos[s];
+        r.room_before = AC_SEQ_SLACK; r.room_after = AC_SEQ_SLACK; r.flags = 0;
+        rec[s] = r;
+    }
+};
+struct PathOffBody {
+    const SeqInfo* seqs; uint32_t n_seqs; const uint64_t* run_start; uint64_t n_runs; uint64_t* path_off;
+    AC_D void operator()(uint64_t i) const {
+        if (i == n_seqs) { path_off[i] = n_runs; return; }
+        uint64_t lo = 0, hi = n_runs;               // first run with start >= seqs[i].start
+        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (run_start[mid] < seqs[i].start) lo = mid + 1; else hi = mid; }
+        path_off[i] = lo;
+    }
+};
+
 // 256-ary blocked exclusive scan built from serial per-thread pieces (volumes here are tiny: one
 // value per 64 coordinates or per unitig).  levels: sums[l+1][i] = sum of sums[l][256i .. 256i+255].
 struct ScanReduceBody {
@@ -444,6 +619,13 @@ struct DevBuf {
     ~DevBuf() { ac_dev_free(p); }
 };
 
+struct PinBuf {   // pinned host memory: D2H lands at DMA speed and the host graph works on it in place
+    void* p = nullptr; size_t cap = 0;
+    void ensure(size_t bytes) { if (bytes > cap) { ac_host_free(p); p = nullptr; cap = 0; p = ac_host_alloc(bytes); cap = bytes; } }
+    template <class T> T* as() { return (T*)p; }
+    ~PinBuf() { ac_host_free(p); }
+};
+
 struct DevicePipeline::Impl {
     int device = 0;
     AcStream stream;
@@ -452,8 +634,12 @@ struct DevicePipeline::Impl {
     DevBuf ascii, packed, seqs, slots, pos_slot, flags8, bmask, bcount, boff, counters, uid_rep, slot_unitig;
     DevBuf run_start, run_len, run_uk, run_dir, is_rep, rep_idx, run_unitig, unitigs, nchunks, chunk_off, partial, link_count, links;
     DevBuf scan_tmp[4];
+    DevBuf sort_a, sort_b, rank, d_len, d_depth, need, d_seq_off, d_arena, d_min_fpos, d_min_rpos;
+    DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
+    DevBuf d_rec;
+    PinBuf h_rec, h_depth, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
-    cudaEvent_t ev[12];
+    cudaEvent_t ev[16];
 #endif
 
     void mark(int i) {
@@ -472,25 +658,25 @@ struct DevicePipeline::Impl {
     }
 
     // exclusive scan of n uint32 values; returns the total.  out may alias in.
-    uint32_t exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, int level = 0) {
+    uint32_t exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, int level = 0, bool want_total = true) {
         if (n == 0) return 0;
         if (level >= 4) throw std::runtime_error("scan too deep");
         const uint64_t nb = (n + 255) / 256;
         scan_tmp[level].ensure((nb + 1) * sizeof(uint32_t));
         uint32_t* sums = scan_tmp[level].as<uint32_t>();
         ac_launch("scan_reduce", &stream, ScanReduceBody{in, n, sums}, nb);
-        uint32_t total_sum;
+        uint32_t total_sum = 0;
         if (nb == 1) {
-            ac_d2h(&total_sum, sums, sizeof(uint32_t), &stream); ac_sync(&stream);
+            if (want_total) { ac_d2h(&total_sum, sums, sizeof(uint32_t), &stream); ac_sync(&stream); }   // the only host round trip
             ac_launch("scan_apply", &stream, ScanApplyBody{in, n, nullptr, out}, nb);
         } else {
-            total_sum = exclusive_scan(sums, sums, nb, level + 1);
+            total_sum = exclusive_scan(sums, sums, nb, level + 1, want_total);
             ac_launch("scan_apply", &stream, ScanApplyBody{in, n, sums, out}, nb);
         }
         return total_sum;
     }
 
-    template <int W> void build_w(PipelineResult& out);
+    template <int W> void build_w(PipelineResult& out, bool keep_positions);
 };
 
 DevicePipeline::DevicePipeline(int device, void* stream) : impl(new Impl) {
@@ -546,7 +732,7 @@ void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo*
     m.mark(1);
 }
 
-template <int W> void DevicePipeline::Impl::build_w(PipelineResult& out) {
+template <int W> void DevicePipeline::Impl::build_w(PipelineResult& out, bool keep_positions) {
     const KParams p = make_kparams(k, W);
     out = PipelineResult();
     out.W = W;
@@ -624,34 +810,95 @@ template <int W> void DevicePipeline::Impl::build_w(PipelineResult& out) {
                                             link_count.as<uint32_t>(), links.as<uint32_t>()}, (uint64_t)n_unitigs * 2);
     mark(9);
 
-    // ---- results to the host ----
-    out.unitigs.resize(n_unitigs); out.link_count.resize((size_t)n_unitigs * 2); out.links.resize((size_t)n_unitigs * 2 * AC_MAX_LINKS);
-    out.run_start.resize(n_runs); out.run_len.resize(n_runs); out.run_unitig.resize(n_runs);
-    ac_d2h(out.unitigs.data(), unitigs.p, (size_t)n_unitigs * sizeof(DeviceUnitig), &stream);
-    ac_d2h(out.link_count.data(), link_count.p, out.link_count.size() * 4, &stream);
-    ac_d2h(out.links.data(), links.p, out.links.size() * 4, &stream);
-    ac_d2h(out.run_start.data(), run_start.p, n_runs * sizeof(uint64_t), &stream);
-    ac_d2h(out.run_len.data(), run_len.p, n_runs * 4, &stream);
-    ac_d2h(out.run_unitig.data(), run_unitig.p, n_runs * 4, &stream);
-    out.d2h_bytes = (uint64_t)n_unitigs * sizeof(DeviceUnitig) + out.link_count.size() * 4 + out.links.size() * 4 + n_runs * 16 + 2 * sizeof(unsigned long long) + 3 * sizeof(uint32_t);
-    out.h2d_bytes = total + (uint64_t)n_seqs * sizeof(SeqInfo);
+    // ---- seed order: stable LSD radix sort of the unitigs by their seed k-mer ----
+    const uint32_t U = n_unitigs;
+    sort_a.ensure((size_t)U * 4); sort_b.ensure((size_t)U * 4);
+    uint32_t* idx_in = sort_a.as<uint32_t>(); uint32_t* idx_out = sort_b.as<uint32_t>();
+    const SeedLess seed_less{unitigs.as<DeviceUnitig>(), W};
+    ac_launch("sort_leaf", &stream, SortLeafBody{seed_less, U, idx_in}, ((uint64_t)U + AC_SORT_LEAF - 1) / AC_SORT_LEAF);
+    for (uint64_t width = AC_SORT_LEAF; width < U; width *= 2) {
+        ac_launch("merge_pass", &stream, MergePassBody{seed_less, U, (uint32_t)width, idx_in, idx_out}, U);
+        std::swap(idx_in, idx_out);
+    }
+    const uint32_t* perm = idx_in;
     mark(10);
+
+    // ---- host-ready arrays in seed order ----
+    rank.ensure((size_t)U * 4); d_len.ensure((size_t)U * 4); d_depth.ensure((size_t)U * 4); need.ensure(((size_t)U + 1) * 4);
+    d_seq_off.ensure((size_t)U * 8); d_min_fpos.ensure((size_t)U * 4); d_min_rpos.ensure((size_t)U * 4);
+    ac_launch("seed_gather", &stream, SeedGatherBody{perm, unitigs.as<DeviceUnitig>(), U, rank.as<uint32_t>(), d_len.as<uint32_t>(), d_depth.as<uint32_t>(),
+                                                     need.as<uint32_t>(), d_min_fpos.as<uint32_t>(), d_min_rpos.as<uint32_t>()}, (uint64_t)U + 1);
+    {   // the arena must stay below 4 GB for the 32-bit scan; sum(len) <= windows
+        if (n_windows + (uint64_t)U * 2 * AC_SEQ_SLACK >= 0xFFFFFFF0ull) throw std::runtime_error("unitig sequence arena would exceed 4 GB");
+    }
+    const uint64_t arena_bytes = exclusive_scan(need.as<uint32_t>(), need.as<uint32_t>(), (uint64_t)U + 1);
+    ac_launch("seq_off", &stream, SeqOffBody{need.as<uint32_t>(), d_seq_off.as<uint64_t>()}, U);
+    d_arena.ensure(arena_bytes);
+    ac_launch("emit_seq", &stream, EmitSeqBody{packed.as<uint64_t>(), p.h, unitigs.as<DeviceUnitig>(), U, chunk_off.as<uint32_t>(), rank.as<uint32_t>(),
+                                               d_seq_off.as<uint64_t>(), d_arena.as<char>()}, n_chunks);
+    // links -> CSR in seed-strand order
+    const uint32_t n_strands = 2 * U;
+    strand_cnt.ensure(((size_t)n_strands + 1) * 4); d_next_off.ensure(((size_t)n_strands + 1) * 4);
+    prev_cnt.ensure(((size_t)n_strands + 1) * 4); d_prev_off.ensure(((size_t)n_strands + 1) * 4);
+    ac_launch("link_count", &stream, LinkCountBody{link_count.as<uint32_t>(), rank.as<uint32_t>(), unitigs.as<DeviceUnitig>(), n_strands, strand_cnt.as<uint32_t>()},
+              (uint64_t)n_strands + 1);
+    const uint64_t n_links = exclusive_scan(strand_cnt.as<uint32_t>(), d_next_off.as<uint32_t>(), (uint64_t)n_strands + 1);
+    d_next.ensure(n_links * 4); d_prev.ensure(n_links * 4);
+    ac_memset(prev_cnt.p, 0, ((size_t)n_strands + 1) * 4, &stream);
+    ac_launch("link_order", &stream, LinkOrderBody{link_count.as<uint32_t>(), links.as<uint32_t>(), rank.as<uint32_t>(), unitigs.as<DeviceUnitig>(),
+                                                   d_next_off.as<uint32_t>(), d_next.as<UStrand>(), prev_cnt.as<uint32_t>()}, n_strands);
+    exclusive_scan(prev_cnt.as<uint32_t>(), d_prev_off.as<uint32_t>(), (uint64_t)n_strands + 1);
+    ac_memset(prev_cnt.p, 0, ((size_t)n_strands + 1) * 4, &stream);    // reused as the fill cursor
+    ac_launch("prev_fill", &stream, PrevFillBody{d_next_off.as<uint32_t>(), d_next.as<UStrand>(), d_prev_off.as<uint32_t>(), prev_cnt.as<uint32_t>(), d_prev.as<UStrand>()}, n_strands);
+    ac_launch("prev_sort", &stream, PrevSortBody{d_prev_off.as<uint32_t>(), d_prev.as<UStrand>()}, n_strands);
+    // paths
+    d_path.ensure(n_runs * 4); d_path_off.ensure(((size_t)n_seqs + 1) * 8);
+    ac_launch("path", &stream, PathBody{seqs.as<SeqInfo>(), n_seqs, run_start.as<uint64_t>(), run_len.as<uint32_t>(), run_unitig.as<uint32_t>(), rank.as<uint32_t>(),
+                                        unitigs.as<DeviceUnitig>(), d_path.as<UStrand>(), d_min_fpos.as<uint32_t>(), d_min_rpos.as<uint32_t>()}, n_runs);
+    d_rec.ensure((size_t)U * sizeof(UnitigRec));
+    ac_launch("pack_rec", &stream, PackRecBody{d_seq_off.as<uint64_t>(), d_len.as<uint32_t>(), d_min_fpos.as<uint32_t>(), d_min_rpos.as<uint32_t>(), d_rec.as<UnitigRec>()}, U);
+    ac_launch("path_off", &stream, PathOffBody{seqs.as<SeqInfo>(), n_seqs, run_start.as<uint64_t>(), n_runs, d_path_off.as<uint64_t>()}, (uint64_t)n_seqs + 1);
+    mark(11);
+
+    // ---- results to the host (pinned) ----
+    const uint64_t arena_cap = arena_bytes + arena_bytes / 4 + (1u << 20);     // head room for relocations during repeat expansion
+    h_rec.ensure((size_t)U * sizeof(UnitigRec)); h_depth.ensure((size_t)U * 4);
+    h_arena.ensure(arena_cap); h_next_off.ensure(((size_t)n_strands + 1) * 4); h_prev_off.ensure(((size_t)n_strands + 1) * 4);
+    h_next.ensure(n_links * 4 + 4); h_prev.ensure(n_links * 4 + 4); h_path.ensure(n_runs * 4 + 4); h_path_off.ensure(((size_t)n_seqs + 1) * 8);
+    uint64_t d2h = 0;
+    auto pull = [&](PinBuf& dst, DevBuf& src, size_t bytes) { if (bytes) ac_d2h(dst.p, src.p, bytes, &stream); d2h += bytes; };
+    pull(h_rec, d_rec, (size_t)U * sizeof(UnitigRec)); pull(h_depth, d_depth, (size_t)U * 4); pull(h_arena, d_arena, arena_bytes);
+    pull(h_next_off, d_next_off, ((size_t)n_strands + 1) * 4); pull(h_prev_off, d_prev_off, ((size_t)n_strands + 1) * 4);
+    pull(h_next, d_next, n_links * 4); pull(h_prev, d_prev, n_links * 4); pull(h_path, d_path, n_runs * 4); pull(h_path_off, d_path_off, ((size_t)n_seqs + 1) * 8);
+    if (keep_positions) {
+        h_run_start.ensure(n_runs * 8 + 8); h_run_len.ensure(n_runs * 4 + 4);
+        pull(h_run_start, run_start, n_runs * 8); pull(h_run_len, run_len, n_runs * 4);
+    }
+    out.d2h_bytes = d2h + 2 * sizeof(unsigned long long) + 8 * sizeof(uint32_t);
+    out.h2d_bytes = total + (uint64_t)n_seqs * sizeof(SeqInfo);
+    mark(12);
     ac_sync(&stream);
+    out.n_unitigs = U; out.n_runs = n_runs; out.n_seqs = n_seqs; out.n_links = n_links;
+    out.rec = h_rec.as<UnitigRec>(); out.depth = h_depth.as<uint32_t>();
+    out.arena = h_arena.as<char>(); out.arena_used = arena_bytes; out.arena_cap = arena_cap;
+    out.next_off = h_next_off.as<uint32_t>(); out.next = h_next.as<UStrand>(); out.prev_off = h_prev_off.as<uint32_t>(); out.prev = h_prev.as<UStrand>();
+    out.path_off = h_path_off.as<uint64_t>(); out.path = h_path.as<UStrand>();
+    out.run_start = keep_positions ? h_run_start.as<uint64_t>() : nullptr; out.run_len = keep_positions ? h_run_len.as<uint32_t>() : nullptr;
     out.t.h2d = between(0, 1); out.t.pack = between(2, 3); out.t.insert = between(3, 4); out.t.adjacency = between(4, 5);
     out.t.boundaries = between(5, 6); out.t.runs = between(6, 7); out.t.unitigs = between(7, 8); out.t.links = between(8, 9);
-    out.t.d2h = between(9, 10); out.t.total = between(2, 10);
+    out.t.seed_sort = between(9, 10); out.t.emit = between(10, 11); out.t.d2h = between(11, 12); out.t.total = between(2, 12);
 }
 
-void DevicePipeline::build(PipelineResult& out) {
+void DevicePipeline::build(PipelineResult& out, bool keep_positions) {
     Impl& m = *impl;
 #ifndef AC_EMULATE
     AC_CUDA_CHECK(cudaSetDevice(m.device));
 #endif
     switch (m.W) {
-        case 1: m.build_w<1>(out); break;
-        case 2: m.build_w<2>(out); break;
-        case 3: m.build_w<3>(out); break;
-        case 4: m.build_w<4>(out); break;
+        case 1: m.build_w<1>(out, keep_positions); break;
+        case 2: m.build_w<2>(out, keep_positions); break;
+        case 3: m.build_w<3>(out, keep_positions); break;
+        case 4: m.build_w<4>(out, keep_positions); break;
         default: throw std::runtime_error("upload() must precede build()");
     }
 }

@@ -1,5 +1,5 @@
-// Device pipeline interface (host side).  Replaces the reference's KmerGraph build + unitig walk
-// (compress.rs:42-43 -> kmer_graph.rs:86-134, unitig_graph.rs:176-226, unitig.rs:112-155) with an
+// Device pipeline interface (host side).  Replaces the reference's KmerGraph build + unitig walk + link
+// creation (compress.rs:42-43 -> kmer_graph.rs:86-134, unitig_graph.rs:176-293, unitig.rs:112-165) with an
 // order-free formulation that runs as data-parallel kernels; see DESIGN.md.
 #pragma once
 #include <cstdint>
@@ -10,9 +10,10 @@
 
 #define AC_MAX_W 4            // k <= 127
 #define AC_MAX_LINKS 5        // successors over the 5-letter alphabet (kmer_graph.rs:142)
+#define AC_SEQ_SLACK 32       // spare bytes on both sides of every unitig in the sequence arena
 
 struct PipelineTimings {      // milliseconds, CUDA events on the pipeline's stream (0 under emulation)
-    float h2d = 0, pack = 0, insert = 0, adjacency = 0, boundaries = 0, runs = 0, unitigs = 0, links = 0, d2h = 0, total = 0;
+    float h2d = 0, pack = 0, insert = 0, adjacency = 0, boundaries = 0, runs = 0, unitigs = 0, links = 0, seed_sort = 0, emit = 0, d2h = 0, total = 0;
 };
 
 struct DeviceUnitig {
@@ -24,18 +25,42 @@ struct DeviceUnitig {
     uint64_t min_w[AC_MAX_W];
 };
 
+// The mutable per-unitig state in one 32-byte record (one cache line touch per unitig during repeat expansion).
+struct UnitigRec {
+    uint64_t seq_off;                          // forward_seq = arena[seq_off, seq_off+len)
+    uint32_t len;                              // forward_seq.len()
+    uint32_t min_fpos, min_rpos;               // min over forward_positions / reverse_positions (unitig.rs:135-146); all entries shift together
+    uint32_t room_before, room_after;          // free arena bytes on both sides (AC_SEQ_SLACK initially)
+    uint32_t flags;                            // host scratch
+};
+
+// A unitig strand: (seed index << 1) | reverse.  The seed index is the position the unitig would have had in the
+// reference's `unitigs` vector straight after build_unitigs_from_kmer_graph (unitig_graph.rs:179-225).
+typedef uint32_t UStrand;
+
+// Everything the host needs, in seed order, living in pinned host memory owned by the pipeline (valid until the
+// next build()).  The host edits len / seq_off / min_*pos / arena in place during repeat expansion.
 struct PipelineResult {
     uint32_t W = 0;
     uint64_t n_slots_used = 0;                 // distinct canonical k-mers; KmerGraph.kmers.len() == 2x this
     uint64_t capacity = 0;
     uint64_t n_dotted = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;     // bytes copied host->device by upload() and device->host by build()
-    std::vector<DeviceUnitig> unitigs;         // in representative-occurrence order (not yet seed order)
-    std::vector<uint32_t> link_count;          // [2*U]   index 2j+e, e=0: strand of the representative occurrence, e=1: its reverse
-    std::vector<uint32_t> links;               // [2*U*AC_MAX_LINKS] targets as 2j'+e'
-    std::vector<uint64_t> run_start;           // [R] global coordinate of each unitig occurrence along the input sequences
-    std::vector<uint32_t> run_len;             // [R]
-    std::vector<uint32_t> run_unitig;          // [R] (unitig << 1) | same_direction_as_representative
+    uint32_t n_unitigs = 0;
+    uint64_t n_runs = 0;
+    uint32_t n_seqs = 0;
+    UnitigRec* rec = nullptr;                  // [U]
+    uint32_t* depth = nullptr;                 // [U]
+    char* arena = nullptr; uint64_t arena_used = 0, arena_cap = 0;
+    uint32_t* next_off = nullptr;              // [2U+1] CSR over strands: forward_next / reverse_next in the reference's push order
+    UStrand* next = nullptr;
+    uint32_t* prev_off = nullptr;              // [2U+1] forward_prev / reverse_prev (ascending; only membership matters downstream)
+    UStrand* prev = nullptr;
+    uint64_t n_links = 0;
+    uint64_t* path_off = nullptr;              // [S+1]
+    UStrand* path = nullptr;                   // [R] unitig path of every sequence (unitig_graph.rs:447-465)
+    uint64_t* run_start = nullptr;             // [R] only when keep_positions: global coordinate / length of every occurrence
+    uint32_t* run_len = nullptr;
     PipelineTimings t;
 };
 
@@ -44,9 +69,8 @@ public:
     DevicePipeline(int device, void* stream);
     ~DevicePipeline();
     // ascii: all padded, end-repaired forward strands concatenated (bytes in "ACGT."); seqs: their layout.
-    // host_pinned: ascii lives in pinned host memory (H2D copy can be async).
     void upload(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t k);
-    void build(PipelineResult& out);           // kernels + D2H of the (small) results
+    void build(PipelineResult& out, bool keep_positions);   // kernels + D2H of the results
     unsigned long long kernel_launches() const;
     struct Impl;
 private:

@@ -166,7 +166,7 @@ def run_gpu(args):
         "roofline": {"kernel": "InsertBody<%d> (k-mer hash insert)" % W, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "peak_kind": peak_kind, "traffic": None,
                      "algorithmic_bytes_per_window": bytes_per_window, "windows_per_launch": int(t.insert_occurrences), "kernel_ms": round(insert_ms, 3)},
-        "stage_ms": {k2: round(mean(k2), 3) for k2 in ("pack", "insert", "adjacency", "boundaries", "runs", "unitigs", "links", "d2h", "device_total",
+        "stage_ms": {k2: round(mean(k2), 3) for k2 in ("pack", "insert", "adjacency", "boundaries", "runs", "unitigs", "links", "seed_sort", "emit", "d2h", "device_total",
                                                         "host_graph", "host_simplify", "host_gfa")},
     }
     if rank == 0:

@@ -74,7 +74,7 @@ typedef struct {
 } ac_unitigs;
 
 typedef struct {            /* milliseconds */
-    float h2d, pack, insert, adjacency, boundaries, runs, unitigs, links, d2h, device_total;
+    float h2d, pack, insert, adjacency, boundaries, runs, unitigs, links, seed_sort, emit, d2h, device_total;
     float host_graph, host_simplify, host_gfa;
     uint64_t insert_occurrences;   /* k-mer occurrences hashed by the insert kernel (forward windows; each feeds both strands) */
     uint64_t table_capacity, table_used;

@@ -23,8 +23,15 @@ def emu():
 
 @pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 31, 33, 51, 63, 65, 91, 127])
 def test_random_adversarial_cases(emu, k):
-    for seed in range(12):
+    for seed in range(40):
         check_case(emu, cases.random_case(1000 * k + seed, k), k)
+
+
+@pytest.mark.parametrize("seed,k", [(339, 3), (717, 9), (755, 7), (760, 11), (773, 7), (780, 33), (802, 65), (816, 9), (858, 33),
+                                    (865, 91), (871, 51), (876, 7), (903, 51), (927, 51), (928, 31), (944, 31), (950, 65), (991, 31)])
+def test_regressions_found_by_the_stress_harness(emu, seed, k):
+    """Inputs on which an earlier revision differed from the oracle (dotted successor rule; repeat-expansion work list)."""
+    check_case(emu, cases.random_case(seed * 100 + k, k), k)
 
 
 def test_reference_fixed_seqs(emu):   # tests.rs:131-148 inputs

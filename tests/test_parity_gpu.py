@@ -28,6 +28,11 @@ def test_random_adversarial_cases(lib, k):
         check_case(lib, cases.random_case(1000 * k + seed, k), k)
 
 
+@pytest.mark.parametrize("seed,k", [(339, 3), (717, 9), (780, 33), (802, 65), (865, 91), (871, 51), (944, 31)])
+def test_regressions_found_by_the_stress_harness(lib, seed, k):
+    check_case(lib, cases.random_case(seed * 100 + k, k), k)
+
+
 def test_reference_fixed_seqs(lib):   # tests.rs:131-148 inputs
     from test_oracle_kats import FIXED
     files = [(f"{n}.fasta", [(n, s.split("\n")[1])]) for n, s in zip("abcde", FIXED)]
