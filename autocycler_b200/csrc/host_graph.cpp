@@ -217,7 +217,7 @@ void HostGraph::compute_candidates() {
                     if (!(next_size(p) == 1 && next_begin(p)[0] == self_fwd) || us_index(p) == idx) ok = false;
                     else if ((!us_reverse(p) && fixed_end[us_index(p)]) || (us_reverse(p) && fixed_start[us_index(p)])) ok = false;
                 }
-                if (ok) out.push_back({idx, 0});
+                if (ok) { Candidate c{idx, 0, (uint16_t)gn, {0, 0, 0, 0, 0, 0}}; for (uint32_t a = 0; a < gn && a < 6; ++a) c.src[a] = grp[a]; out.push_back(c); }
             }
             {   // get_exclusive_outputs (:258-280) and the guards (:75-82)
                 const UStrand* grp = next_begin(self_fwd); const uint32_t gn = next_size(self_fwd);
@@ -227,7 +227,7 @@ void HostGraph::compute_candidates() {
                     if (!(prev_size(q) == 1 && prev_begin(q)[0] == self_fwd) || us_index(q) == idx) ok = false;
                     else if ((!us_reverse(q) && fixed_start[us_index(q)]) || (us_reverse(q) && fixed_end[us_index(q)])) ok = false;
                 }
-                if (ok) out.push_back({idx, 1});
+                if (ok) { Candidate c{idx, 1, (uint16_t)gn, {0, 0, 0, 0, 0, 0}}; for (uint32_t a = 0; a < gn && a < 6; ++a) c.src[a] = grp[a]; out.push_back(c); }
             }
         }
     });
@@ -253,9 +253,7 @@ struct Cursor { const unsigned char* base; ptrdiff_t step; const unsigned char* 
 
 // get_common_end_seq (:298-312) for side 0 / get_common_start_seq (:283-295) for side 1: length of the common piece
 uint32_t HostGraph::common_length(const Candidate& cand) const {
-    const UStrand self_fwd = us_make(cand.idx, false);
-    const UStrand* grp = cand.side == 0 ? prev_begin(self_fwd) : next_begin(self_fwd);
-    const uint32_t gn = cand.side == 0 ? prev_size(self_fwd) : next_size(self_fwd);
+    const UStrand* grp = cand.src; const uint32_t gn = cand.gn;
     auto cursor = [&](UStrand s) {
         const uint32_t u = us_index(s); const unsigned char* p = (const unsigned char*)seq_ptr(u);
         const bool at_back = (cand.side == 0) != us_reverse(s);    // forward strand read from its end, or reverse strand read from its start
@@ -323,9 +321,23 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
             const size_t ci = w * 64 + (size_t)bit;
             const Candidate cand = cands[ci];
             const uint32_t idx = cand.idx;
-            const UStrand self_fwd = us_make(idx, false);
-            const UStrand* grp = cand.side == 0 ? prev_begin(self_fwd) : next_begin(self_fwd);
-            const uint32_t gn = cand.side == 0 ? prev_size(self_fwd) : next_size(self_fwd);
+            const UStrand* grp = cand.src; const uint32_t gn = cand.gn;
+            if (first_pass) {   // the first pass walks the list in order: pull the next candidates' records and sequence ends into cache
+                if (ci + 16 < cands.size()) {
+                    const Candidate& f = cands[ci + 16];
+                    __builtin_prefetch(&rec[f.idx]); __builtin_prefetch(&deps[f.idx]);
+                    for (uint32_t a = 0; a < f.gn; ++a) { __builtin_prefetch(&rec[us_index(f.src[a])]); __builtin_prefetch(&deps[us_index(f.src[a])]); }
+                }
+                if (ci + 6 < cands.size()) {
+                    const Candidate& f = cands[ci + 6];
+                    __builtin_prefetch(arena + rec[f.idx].seq_off - (f.side == 0 ? 32 : 0) + (f.side == 0 ? 0 : rec[f.idx].len));
+                    for (uint32_t a = 0; a < f.gn; ++a) {
+                        const UnitigRec& r = rec[us_index(f.src[a])];
+                        const bool at_back = (f.side == 0) != us_reverse(f.src[a]);
+                        __builtin_prefetch(arena + r.seq_off + (at_back ? (r.len > 32 ? r.len - 32 : 0) : 0));
+                    }
+                }
+            }
 
             bool dup = false, pristine = first_pass; uint32_t min_len = 0xFFFFFFFFu;
             for (uint32_t a = 0; a < gn; ++a) {

@@ -69,7 +69,7 @@ private:
     bool fixed_ready = false;
     void compute_fixed();
     // repeat expansion work list: (unitig, side) pairs that satisfy the structural conditions of expand_repeats
-    struct Candidate { uint32_t idx; uint32_t side; };
+    struct Candidate { uint32_t idx; uint16_t side, gn; UStrand src[6]; };   // 32 B: destination, side (0 inputs / 1 outputs) and its sources inline
     std::vector<Candidate> cands;
     std::vector<int32_t> cand_at;             // [2U] candidate index of (unitig, side), -1 if none
     std::vector<uint64_t> dirty;              // bitmap over cands: must be (re-)evaluated
