@@ -56,7 +56,9 @@ class AcTimings(C.Structure):
 
 EXPORTS = ["ac_last_error", "ac_version", "ac_create", "ac_destroy", "ac_add_sequence", "ac_clear_sequences", "ac_upload",
            "ac_build", "ac_simplify", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
-           "ac_timings_get", "ac_compress_dir", "ac_load_sequences", "ac_sequence_get"]
+           "ac_timings_get", "ac_compress_dir", "ac_load_sequences", "ac_sequence_get",
+           "ac_build_local", "ac_entries_count", "ac_entries_export", "ac_entries_merge", "ac_runs_local", "ac_runs_export",
+           "ac_runs_import", "ac_build_finish"]
 
 _libs = {}
 
@@ -90,6 +92,14 @@ def load_library(path=None):
     lib.ac_load_sequences.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
     lib.ac_sequence_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint16), C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64,
                                     C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    lib.ac_build_local.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.ac_entries_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.ac_entries_export.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.ac_entries_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.ac_runs_local.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.ac_runs_export.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.ac_runs_import.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.ac_build_finish.argtypes = [C.c_void_p]
     _libs[path] = lib
     return lib
 

@@ -27,6 +27,7 @@ template <class T> inline T ac_atomic_min(T* p, T v) { T old = *p; if (v < old) 
 template <class T> inline T ac_atomic_max(T* p, T v) { T old = *p; if (v > old) *p = v; return old; }
 template <class T> inline T ac_ld_volatile(const T* p) { return *p; }
 inline uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+inline uint32_t ac_popc(uint32_t v) { return (uint32_t)__builtin_popcount(v); }
 
 struct AcStream { int dummy; };
 
@@ -69,8 +70,11 @@ AC_D unsigned long long ac_atomic_add(unsigned long long* p, unsigned long long 
 AC_D uint32_t ac_atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
 AC_D uint32_t ac_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 AC_D uint32_t ac_atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
+AC_D uint64_t ac_atomic_min(uint64_t* p, uint64_t v) { return (uint64_t)atomicMin((unsigned long long*)p, (unsigned long long)v); }
 template <class T> AC_D T ac_ld_volatile(const T* p) { return *(const volatile T*)p; }
 AC_D uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
+AC_D uint32_t ac_popc(uint32_t v) { return (uint32_t)__popc(v); }
+AC_D uint64_t ac_atomic_or(uint64_t* p, uint64_t v) { return (uint64_t)atomicOr((unsigned long long*)p, (unsigned long long)v); }
 #endif
 
 struct AcStream { cudaStream_t s; };

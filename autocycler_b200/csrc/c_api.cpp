@@ -141,11 +141,7 @@ int ac_upload(ac_handle* h) {
     AC_GUARD_END(h)
 }
 
-int ac_build(ac_handle* h) {
-    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
-    AC_GUARD_BEGIN
-    if (!h->uploaded) return set_error(h, AC_EINVAL, "ac_upload must precede ac_build");
-    h->pipe->build(h->res, h->cfg.keep_positions != 0);
+static void adopt_result(ac_handle* h) {   // host graph over the device result + bookkeeping shared by ac_build / ac_build_finish
     const double t0 = now_ms();
     h->graph.build(h->res, h->seqs, h->cfg.k, h->cfg.keep_positions != 0);
     h->graph.check_links();
@@ -160,6 +156,76 @@ int ac_build(ac_handle* h) {
     t.kernel_launches = h->pipe->kernel_launches();
     t.h2d_bytes = h->res.h2d_bytes; t.d2h_bytes = h->res.d2h_bytes;
     h->built = true; h->gfa_ready = false;
+}
+
+int ac_build(ac_handle* h) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    AC_GUARD_BEGIN
+    if (!h->uploaded) return set_error(h, AC_EINVAL, "ac_upload must precede ac_build");
+    h->pipe->build(h->res, h->cfg.keep_positions != 0);
+    adopt_result(h);
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
+// ---- multi-GPU stages: one process per GPU, the caller runs the collectives between them on device buffers ----
+int ac_build_local(ac_handle* h, uint32_t seq_lo, uint32_t seq_hi, uint32_t multi) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    AC_GUARD_BEGIN
+    if (!h->uploaded) return set_error(h, AC_EINVAL, "ac_upload must precede ac_build_local");
+    h->built = false;
+    h->pipe->build_local(seq_lo, seq_hi, multi != 0);
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+int ac_entries_count(ac_handle* h, uint64_t* n) {
+    if (!h || !n) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    *n = h->pipe->count_entries();
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+int ac_entries_export(ac_handle* h, void* dst, uint64_t cap_records) {
+    if (!h || !dst) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    h->pipe->export_entries(dst, cap_records);
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+int ac_entries_merge(ac_handle* h, const void* src, uint64_t n) {
+    if (!h || (!src && n)) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    h->pipe->merge_entries(src, n);
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+int ac_runs_local(ac_handle* h, uint64_t* n_runs) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    AC_GUARD_BEGIN
+    h->pipe->runs_local();
+    if (n_runs) *n_runs = h->pipe->local_runs();
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+int ac_runs_export(ac_handle* h, void* dst, uint64_t cap_records) {
+    if (!h || !dst) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    h->pipe->export_runs(dst, cap_records);
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+int ac_runs_import(ac_handle* h, const void* src, uint64_t n) {
+    if (!h || !src) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    h->pipe->import_runs(src, n);
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+int ac_build_finish(ac_handle* h) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    AC_GUARD_BEGIN
+    h->pipe->finish(h->res, h->cfg.keep_positions != 0);
+    adopt_result(h);
     return AC_OK;
     AC_GUARD_END(h)
 }

@@ -192,3 +192,6 @@ struct Slot {               // 16 B: two slots per 32-B sector
 #define AC_AUX_FIRST_RC 2u
 #define AC_AUX_OUT_OK 4u
 #define AC_AUX_IN_OK 8u
+#define AC_AUX_OBS_OUT_SHIFT 4      // bits 4..7 : base b follows this k-mer somewhere in the input (canonical orientation)
+#define AC_AUX_OBS_IN_SHIFT 8       // bits 8..11: base b precedes it
+#define AC_AUX_MERGE_MASK 0xFF3u    // what the multi-GPU exchange ORs together: first flags + observed neighbours

@@ -23,6 +23,7 @@ static unsigned long long g_ac_kernel_launches = 0;
 #define AC_NONE32 0xFFFFFFFFu
 #define AC_CHUNK 32            // windows per thread in the insert kernel
 #define AC_MINCHUNK 128        // windows per thread in the seed-k-mer kernel
+#define AC_STRIPES 1024        // the claim counters are striped: a single hot address would serialise in one L2 slice
 
 // ------------------------------------------------------------------------------------------------
 // small device helpers
@@ -122,10 +123,11 @@ struct InitSlotsBody {
 
 // kmer_graph.rs:92-134 add_sequence, both strands at once: one canonical entry per k-mer, count = depth.
 template <int W> struct InsertBody {
-    TableView t; KParams p; uint64_t total;
+    TableView t; KParams p; uint64_t g_begin, g_end;   // coordinates of the sequences this rank owns
+    bool track_min;                     // multi-GPU: the entry must end up pointing at the SMALLEST occurrence (a rank-independent name for the k-mer)
     uint32_t* pos_slot;                 // [total] slot of the window starting at each global coordinate
-    unsigned long long* counters;       // [0] slots claimed, [1] dotted k-mers claimed
-    AC_D void insert(const Key<W>& fwd, const Key<W>& rc, uint64_t g, uint64_t fs, uint32_t len) const {
+    unsigned long long* counters;       // [2*stripe] slots claimed, [2*stripe+1] dotted k-mers claimed
+    AC_D void insert(const Key<W>& fwd, const Key<W>& rc, uint64_t g, uint64_t fs, uint32_t len, uint32_t obs, uint32_t& claimed, uint32_t& claimed_dotted) const {
         const bool canon_fwd = key_is_canonical(fwd, p);
         const Key<W>& canon = canon_fwd ? fwd : rc;
         const uint64_t h = key_hash(canon);
@@ -136,36 +138,36 @@ template <int W> struct InsertBody {
             uint64_t e = ac_ld_volatile(&t.slots[slot].entry);
             if (e == AC_EMPTY_ENTRY) {
                 e = ac_atomic_cas(&t.slots[slot].entry, (uint64_t)AC_EMPTY_ENTRY, mine);
-                if (e == AC_EMPTY_ENTRY) {
-                    ac_atomic_add(&counters[0], 1ull);
-                    if (dotted) ac_atomic_add(&counters[1], 1ull);
-                    break;
-                }
+                if (e == AC_EMPTY_ENTRY) { ++claimed; if (dotted) ++claimed_dotted; break; }
             }
             if (entry_tag(e) == entry_tag(mine)) {
                 Key<W> rep = window_key<W>(t, entry_gpos(e), dotted, p);
-                if (key_eq(rep, fwd) || key_eq(rep, rc)) break;
+                if (key_eq(rep, fwd) || key_eq(rep, rc)) {
+                    if (track_min && mine < e) ac_atomic_min(&t.slots[slot].entry, mine);   // same tag => ordered by gpos
+                    break;
+                }
             }
             if (++slot == t.cap) slot = 0;
         }
         ac_atomic_add(&t.slots[slot].count, 1u);
         // Kmer::first_position (kmer_graph.rs:57-60): position 0 of the forward strand is window 0; position 0
         // of the reverse strand is the reverse complement of the last window (kmer_graph.rs:103-108).
-        uint32_t bits = 0;
+        uint32_t bits = obs;
         if (fs == 0) bits |= canon_fwd ? AC_AUX_FIRST_CANON : AC_AUX_FIRST_RC;
         if (fs + 1 == len) bits |= canon_fwd ? AC_AUX_FIRST_RC : AC_AUX_FIRST_CANON;
-        if (bits) ac_atomic_or(&t.slots[slot].aux, bits);
+        if (bits && (ac_ld_volatile(&t.slots[slot].aux) & bits) != bits) ac_atomic_or(&t.slots[slot].aux, bits);   // usually already there
         pos_slot[g] = (uint32_t)slot;
     }
     AC_D void operator()(uint64_t i) const {
-        uint64_t g = i * AC_CHUNK;
-        const uint64_t g1 = (g + AC_CHUNK < total) ? g + AC_CHUNK : total;
+        uint64_t g = g_begin + i * AC_CHUNK;
+        const uint64_t g1 = (g + AC_CHUNK < g_end) ? g + AC_CHUNK : g_end;
         uint32_t si = find_seq(t.seqs, t.n_seqs, g);
+        uint32_t claimed = 0, claimed_dotted = 0;
         while (g < g1) {
             const SeqInfo s = t.seqs[si];
             uint64_t fs = g - s.start;
             if (fs >= s.len) {                       // inside the k-1 padded bytes that start no window
-                if (si + 1 >= t.n_seqs) return;
+                if (si + 1 >= t.n_seqs) break;
                 ++si;
                 if (t.seqs[si].start > g) g = t.seqs[si].start;
                 continue;
@@ -185,27 +187,81 @@ template <int W> struct InsertBody {
                     const uint64_t code = packed_base(t.packed, g + p.k - 1);
                     key_push_right(fwd, code, p); key_push_left(rc, 3 - code, p);
                 }
-                insert(fwd, rc, g, fs, s.len);
+                // Neighbouring bases seen next to this k-mer, in the canonical strand's terms: a lower bound on the node-centric
+                // degrees that spares the adjacency kernel the probes for neighbours it already knows to exist.
+                uint32_t obs = 0;
+                if (d == 0) {
+                    const bool cf = key_is_canonical(fwd, p);
+                    if (fs + 1 < s.len && window_dots(s, fs + 1, p.k) == 0) {
+                        const uint32_t b = packed_base(t.packed, g + p.k);
+                        obs |= cf ? (1u << (AC_AUX_OBS_OUT_SHIFT + b)) : (1u << (AC_AUX_OBS_IN_SHIFT + 3 - b));
+                    }
+                    if (fs > 0 && window_dots(s, fs - 1, p.k) == 0) {
+                        const uint32_t b = packed_base(t.packed, g - 1);
+                        obs |= cf ? (1u << (AC_AUX_OBS_IN_SHIFT + b)) : (1u << (AC_AUX_OBS_OUT_SHIFT + 3 - b));
+                    }
+                }
+                insert(fwd, rc, g, fs, s.len, obs, claimed, claimed_dotted);
             }
         }
+        if (claimed) ac_atomic_add(&counters[2 * (i % AC_STRIPES)], (unsigned long long)claimed);
+        if (claimed_dotted) ac_atomic_add(&counters[2 * (i % AC_STRIPES) + 1], (unsigned long long)claimed_dotted);
     }
 };
 
 // Node-centric degrees (kmer_graph.rs:136-166) and the per-k-mer halves of the merge rule
 // (unitig_graph.rs:192-223): outOK(K) = outdeg(K)==1 && !first(rc K); inOK(K) = indeg(K)==1 && !first(K).
+AC_D void bloom_slot(uint64_t h, uint64_t n_words, uint64_t& word, uint64_t& mask) {   // 2 bits in one 64-bit word: one L2 access per test
+    word = ac_umul64hi(h * 0x9E3779B97F4A7C15ull, n_words);
+    mask = (1ull << (h & 63)) | (1ull << ((h >> 6) & 63));
+}
+template <int W> struct BloomBuildBody {   // 16 filter bits per distinct k-mer, built once the table is complete
+    TableView t; KParams p; const uint32_t* occupied; uint64_t* bloom; uint64_t n_words;
+    AC_D void operator()(uint64_t x) const {
+        const uint64_t e = t.slots[occupied[x]].entry;
+        const Key<W> f = window_key<W>(t, entry_gpos(e), entry_dotted(e), p);
+        uint64_t word, mask;
+        bloom_slot(key_hash(key_is_canonical(f, p) ? f : key_rc(f, p)), n_words, word, mask);
+        if ((ac_ld_volatile(&bloom[word]) & mask) != mask) ac_atomic_or(&bloom[word], mask);
+    }
+};
 template <int W> struct AdjacencyBody {
-    TableView t; KParams p; bool any_dotted; uint8_t* flags8;
-    AC_D void operator()(uint64_t i) const {
+    TableView t; KParams p; bool any_dotted; const uint32_t* occupied; uint8_t* flags8;   // one thread per OCCUPIED slot (full warps)
+    const uint64_t* bloom; uint64_t n_words;
+    // Is k-mer `a` in the table?  Almost every candidate neighbour is absent; the L2-resident Bloom filter answers that
+    // without touching the table in HBM.
+    AC_D bool present(const Key<W>& a, const Key<W>& arc) const {
+        uint64_t word, mask;
+        bloom_slot(key_hash(key_is_canonical(a, p) ? a : arc), n_words, word, mask);
+        if ((bloom[word] & mask) != mask) return false;
+        return table_find<W>(t, a, arc, p) != AC_NONE32;
+    }
+    AC_D void operator()(uint64_t x) const {
+        const uint64_t i = occupied[x];
         const uint64_t e = t.slots[i].entry;
-        if (e == AC_EMPTY_ENTRY) { flags8[i] = 0; return; }
+        const uint32_t aux = t.slots[i].aux;
         const Key<W> f = window_key<W>(t, entry_gpos(e), entry_dotted(e), p);
         const Key<W> r = key_rc(f, p);
-        uint32_t outdeg = 0, indeg = 0;
-        for_each_successor<W>(f, r, any_dotted, p, [&](const Key<W>& a, const Key<W>& arc) { if (table_find<W>(t, a, arc, p) != AC_NONE32) ++outdeg; });
-        for_each_predecessor<W>(f, r, any_dotted, p, [&](const Key<W>& a, const Key<W>& arc) { if (table_find<W>(t, a, arc, p) != AC_NONE32) ++indeg; });
         const bool canon_fwd = key_is_canonical(f, p);
-        const uint32_t out_c = canon_fwd ? outdeg : indeg, in_c = canon_fwd ? indeg : outdeg;
-        const uint32_t aux = t.slots[i].aux;
+        uint32_t out_c, in_c;
+        if (f.d != 0) {     // dotted k-mers (a handful per unrepaired sequence end): plain probing of every candidate
+            uint32_t outdeg = 0, indeg = 0;
+            for_each_successor<W>(f, r, any_dotted, p, [&](const Key<W>& a, const Key<W>& arc) { if (table_find<W>(t, a, arc, p) != AC_NONE32) ++outdeg; });
+            for_each_predecessor<W>(f, r, any_dotted, p, [&](const Key<W>& a, const Key<W>& arc) { if (table_find<W>(t, a, arc, p) != AC_NONE32) ++indeg; });
+            out_c = canon_fwd ? outdeg : indeg; in_c = canon_fwd ? indeg : outdeg;
+        } else {            // canonical strand c: neighbours seen during the insert are known; the others go through the filter
+            const Key<W>& c = canon_fwd ? f : r; const Key<W>& crc = canon_fwd ? r : f;
+            const uint32_t obs_out = (aux >> AC_AUX_OBS_OUT_SHIFT) & 15u, obs_in = (aux >> AC_AUX_OBS_IN_SHIFT) & 15u;
+            out_c = ac_popc(obs_out); in_c = ac_popc(obs_in);
+            for (uint64_t b = 0; b < 4; ++b) {
+                if (!((obs_out >> b) & 1u)) { Key<W> s = c, src = crc; key_push_right(s, b, p); key_push_left(src, 3 - b, p); if (present(s, src)) ++out_c; }
+                if (!((obs_in >> b) & 1u)) { Key<W> s = c, src = crc; key_push_left(s, b, p); key_push_right(src, 3 - b, p); if (present(s, src)) ++in_c; }
+            }
+            if (any_dotted) {   // "X." after c and ".X" before it (kmer_graph.rs:142,158 try '.' too)
+                { Key<W> s = c; key_push_right(s, 0, p); s.d = -1; if (table_find<W>(t, s, key_rc(s, p), p) != AC_NONE32) ++out_c; }
+                { Key<W> s = c; key_push_left(s, 0, p); s.d = 1; if (table_find<W>(t, s, key_rc(s, p), p) != AC_NONE32) ++in_c; }
+            }
+        }
         uint32_t bits = 0;
         if (out_c == 1 && !(aux & AC_AUX_FIRST_RC)) bits |= AC_AUX_OUT_OK;
         if (in_c == 1 && !(aux & AC_AUX_FIRST_CANON)) bits |= AC_AUX_IN_OK;
@@ -217,12 +273,13 @@ template <int W> struct AdjacencyBody {
 // One thread per 64 global coordinates: bit j set <=> a unitig occurrence starts at coordinate 64i+j,
 // i.e. it is window 0 of a sequence or the edge from the previous window is not merged.
 struct BoundaryBody {
-    const uint64_t* packed; const SeqInfo* seqs; uint32_t n_seqs; uint32_t h; uint64_t total;
+    const uint64_t* packed; const SeqInfo* seqs; uint32_t n_seqs; uint32_t h; uint64_t g_begin, g_end;   // this rank's coordinates
     const uint32_t* pos_slot; const uint8_t* flags8;
     uint64_t* bmask; uint32_t* bcount;
     AC_D void operator()(uint64_t i) const {
-        uint64_t g = i * 64;
-        const uint64_t g1 = (g + 64 < total) ? g + 64 : total;
+        uint64_t g = i * 64 > g_begin ? i * 64 : g_begin;
+        const uint64_t g1 = (i * 64 + 64 < g_end) ? i * 64 + 64 : g_end;
+        if (g >= g1) { bmask[i] = 0; bcount[i] = 0; return; }
         uint64_t bits = 0;
         uint32_t si = find_seq(seqs, n_seqs, g);
         while (g < g1) {
@@ -278,25 +335,48 @@ struct RunScatterBody {
     }
 };
 
-// Per occurrence: its extent and the identity of its unitig.  A unitig is named by the smaller of the
-// table slots of its two end k-mers (each canonical k-mer belongs to exactly one unitig); `dir` tells
-// from which end this occurrence reads it.  The smallest occurrence index becomes the representative.
-struct RunInfoBody {
-    const uint64_t* packed; const SeqInfo* seqs; uint32_t n_seqs; uint32_t h;
-    const uint64_t* run_start; uint64_t n_runs; const uint32_t* pos_slot;
-    uint32_t* run_len; uint32_t* run_uk; uint8_t* run_dir; uint32_t* uid_rep;
+// Per occurrence: its extent and the table slots of its first and last k-mer.
+struct RunEndsLocalBody {
+    const SeqInfo* seqs; uint32_t n_seqs; const uint64_t* run_start; uint64_t n_runs; const uint32_t* pos_slot;
+    uint32_t* run_len; uint32_t* run_hs; uint32_t* run_ts;
     AC_D void operator()(uint64_t r) const {
         const uint64_t g0 = run_start[r];
         const SeqInfo s = seqs[find_seq(seqs, n_seqs, g0)];
         const uint64_t seq_last = s.start + s.len - 1;
         uint64_t g1 = seq_last;
         if (r + 1 < n_runs && run_start[r + 1] <= seq_last) g1 = run_start[r + 1] - 1;
-        const uint32_t hs = pos_slot[g0], ts = pos_slot[g1];
+        run_len[r] = (uint32_t)(g1 - g0 + 1); run_hs[r] = pos_slot[g0]; run_ts[r] = pos_slot[g1];
+    }
+};
+// Multi-GPU: an occurrence in rank-independent terms (its end k-mers are named by their smallest occurrence, which is
+// what every rank's table entry points at after the exchange), and back into this rank's slots.
+struct RunExportBody {
+    const uint64_t* run_start; const uint32_t* run_len; const uint32_t* run_hs; const uint32_t* run_ts; const Slot* slots; RunRec* out;
+    AC_D void operator()(uint64_t r) const {
+        RunRec x; x.start = run_start[r]; x.len = run_len[r]; x.pad = 0;
+        x.head_rep = entry_gpos(slots[run_hs[r]].entry); x.tail_rep = entry_gpos(slots[run_ts[r]].entry);
+        out[r] = x;
+    }
+};
+struct RunImportBody {
+    const RunRec* in; const uint32_t* pos_slot; uint64_t* run_start; uint32_t* run_len; uint32_t* run_hs; uint32_t* run_ts;
+    AC_D void operator()(uint64_t r) const {
+        const RunRec x = in[r];
+        run_start[r] = x.start; run_len[r] = x.len; run_hs[r] = pos_slot[x.head_rep]; run_ts[r] = pos_slot[x.tail_rep];
+    }
+};
+// The identity of an occurrence's unitig: a unitig is named by the smaller of the table slots of its two end k-mers
+// (each canonical k-mer belongs to exactly one unitig); `dir` tells from which end this occurrence reads it.  The
+// smallest occurrence index becomes the representative.
+struct RunKeyBody {
+    const uint64_t* packed; uint32_t h; const uint64_t* run_start; const uint32_t* run_hs; const uint32_t* run_ts;
+    uint32_t* run_uk; uint8_t* run_dir; uint32_t* uid_rep;
+    AC_D void operator()(uint64_t r) const {
+        const uint32_t hs = run_hs[r], ts = run_ts[r];
         const uint32_t uk = hs < ts ? hs : ts;
         uint8_t dir;
         if (hs != ts) dir = hs < ts ? 0 : 1;
-        else dir = packed_base(packed, g0 + h) < 2 ? 0 : 1;     // single k-mer: orientation of the window itself
-        run_len[r] = (uint32_t)(g1 - g0 + 1);
+        else dir = packed_base(packed, run_start[r] + h) < 2 ? 0 : 1;     // single k-mer: orientation of the window itself
         run_uk[r] = uk; run_dir[r] = dir;
         ac_atomic_min(&uid_rep[uk], (uint32_t)r);
     }
@@ -309,21 +389,65 @@ struct RepFlagBody {
 
 struct RunAssignBody {
     const uint64_t* run_start; const uint32_t* run_len; const uint32_t* run_uk; const uint8_t* run_dir;
-    const uint32_t* uid_rep; const uint32_t* rep_idx; const uint32_t* pos_slot; const Slot* slots;
+    const uint32_t* uid_rep; const uint32_t* rep_idx; const uint32_t* run_hs; const uint32_t* run_ts; const Slot* slots;
     uint32_t* run_unitig; DeviceUnitig* unitigs; uint32_t* slot_unitig;
     AC_D void operator()(uint64_t r) const {
         const uint32_t rep = uid_rep[run_uk[r]];
         const uint32_t j = rep_idx[rep];
         run_unitig[r] = (j << 1) | (run_dir[r] == run_dir[rep] ? 1u : 0u);
         if (rep == (uint32_t)r) {
-            const uint64_t g0 = run_start[r]; const uint32_t len = run_len[r];
-            const uint32_t hs = pos_slot[g0], ts = pos_slot[g0 + len - 1];
+            const uint32_t hs = run_hs[r], ts = run_ts[r];
             DeviceUnitig u;
-            u.start = g0; u.len = len; u.depth = slots[hs].count; u.flip = 0; u.min_d = 0;
+            u.start = run_start[r]; u.len = run_len[r]; u.depth = slots[hs].count; u.flip = 0; u.min_d = 0;
+            u.head_slot = hs; u.tail_slot = ts;
             for (int w = 0; w < AC_MAX_W; ++w) u.min_w[w] = 0;
             unitigs[j] = u;
             slot_unitig[hs] = j; slot_unitig[ts] = j;
         }
+    }
+};
+
+// Multi-GPU exchange of the deduplicated local tables ("k-mer buckets"): the occupied slots, compacted.
+struct ExportFlagBody {
+    const Slot* slots; uint32_t* flag;
+    AC_D void operator()(uint64_t i) const { flag[i] = slots[i].entry != AC_EMPTY_ENTRY ? 1u : 0u; }
+};
+struct OccupiedListBody {
+    const Slot* slots; const uint32_t* off; uint32_t* list;
+    AC_D void operator()(uint64_t i) const { if (slots[i].entry != AC_EMPTY_ENTRY) list[off[i]] = (uint32_t)i; }
+};
+struct ExportScatterBody {
+    const Slot* slots; const uint32_t* off; Slot* out;
+    AC_D void operator()(uint64_t i) const { const Slot s = slots[i]; if (s.entry != AC_EMPTY_ENTRY) out[off[i]] = s; }
+};
+// Folding another rank's entries into this rank's table: counts add, first/last flags OR, the entry keeps the smaller
+// occurrence.  Every rank holds all packed sequences, so the k-mer behind a remote entry is read from `packed`.
+template <int W> struct MergeBody {
+    TableView t; KParams p; const Slot* in; uint32_t* pos_slot; unsigned long long* counters;
+    AC_D void operator()(uint64_t i) const {
+        const Slot r = in[i];
+        const uint64_t g = entry_gpos(r.entry);
+        const bool dotted = entry_dotted(r.entry);
+        const Key<W> fwd = window_key<W>(t, g, dotted, p);
+        const Key<W> rc = key_rc(fwd, p);
+        const uint64_t h = key_hash(key_is_canonical(fwd, p) ? fwd : rc);
+        const uint64_t mine = make_entry(g, dotted, h);
+        uint64_t slot = ac_umul64hi(h, t.cap);
+        for (;;) {
+            uint64_t e = ac_ld_volatile(&t.slots[slot].entry);
+            if (e == AC_EMPTY_ENTRY) {
+                e = ac_atomic_cas(&t.slots[slot].entry, (uint64_t)AC_EMPTY_ENTRY, mine);
+                if (e == AC_EMPTY_ENTRY) { ac_atomic_add(&counters[2 * (i % AC_STRIPES)], 1ull); if (dotted) ac_atomic_add(&counters[2 * (i % AC_STRIPES) + 1], 1ull); break; }
+            }
+            if (entry_tag(e) == entry_tag(mine)) {
+                const Key<W> rep = window_key<W>(t, entry_gpos(e), dotted, p);
+                if (key_eq(rep, fwd) || key_eq(rep, rc)) { if (mine < e) ac_atomic_min(&t.slots[slot].entry, mine); break; }
+            }
+            if (++slot == t.cap) slot = 0;
+        }
+        ac_atomic_add(&t.slots[slot].count, r.count);
+        if (r.aux & AC_AUX_MERGE_MASK) ac_atomic_or(&t.slots[slot].aux, r.aux & AC_AUX_MERGE_MASK);
+        pos_slot[g] = (uint32_t)slot;
     }
 };
 
@@ -407,7 +531,7 @@ template <int W> struct LinkBody {
             const DeviceUnitig v = unitigs[j2];
             // `a` heads unitig j2 read in its representative direction iff it is the forward k-mer of v's first window
             const bool a_canon = key_is_canonical(a, p);
-            const bool head_fwd = pos_slot[v.start] == s2 && ((packed_base(t.packed, v.start + p.h) < 2) == a_canon);
+            const bool head_fwd = v.head_slot == s2 && ((packed_base(t.packed, v.start + p.h) < 2) == a_canon);
             if (n < AC_MAX_LINKS) links[i * AC_MAX_LINKS + n] = (j2 << 1) | (head_fwd ? 0u : 1u);
             ++n;
         });
@@ -609,6 +733,48 @@ struct ScanApplyBody {
     }
 };
 
+#ifndef AC_EMULATE
+// Product scan: tiles of 4096 values, coalesced loads, warp-shuffle block scans (the functor bodies above are the
+// host-emulation form of the same two phases).
+#define AC_SCAN_TILE 4096
+__global__ void __launch_bounds__(256) ac_scan_reduce_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ sums) {
+    const uint64_t tile0 = (uint64_t)blockIdx.x * AC_SCAN_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int r = 0; r < AC_SCAN_TILE / 256; ++r) { const uint64_t i = tile0 + (uint64_t)r * 256 + threadIdx.x; if (i < n) s += in[i]; }
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+    __shared__ uint32_t w[8];
+    if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int i = 0; i < 8; ++i) t += w[i]; sums[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(256) ac_scan_apply_kernel(const uint32_t* in, uint64_t n, const uint32_t* __restrict__ block_off, uint32_t* out) {
+    __shared__ uint32_t warp_tot[8];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry = block_off ? block_off[blockIdx.x] : 0;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * AC_SCAN_TILE;
+#pragma unroll 1
+    for (int r = 0; r < AC_SCAN_TILE / 1024; ++r) {            // 1024 values per round, 4 consecutive values per thread
+        const uint64_t i = tile0 + (uint64_t)r * 1024 + threadIdx.x * 4;
+        uint32_t v[4];
+        if (i + 3 < n) { const uint4 q = *reinterpret_cast<const uint4*>(in + i); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+        else { for (int j = 0; j < 4; ++j) v[j] = (i + j < n) ? in[i + j] : 0; }
+        const uint32_t t = v[0] + v[1] + v[2] + v[3];
+        uint32_t inc = t;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= (uint32_t)o) inc += u; }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+        for (uint32_t w2 = 0; w2 < 8; ++w2) { const uint32_t x = warp_tot[w2]; if (w2 < warp) wbase += x; total += x; }
+        uint32_t e = carry + wbase + inc - t;
+        if (i + 3 < n) { uint4 q; q.x = e; q.y = e + v[0]; q.z = q.y + v[1]; q.w = q.z + v[2]; *reinterpret_cast<uint4*>(out + i) = q; }
+        else { for (int j = 0; j < 4; ++j) { if (i + j < n) out[i + j] = e; e += v[j]; } }
+        carry += total;
+        __syncthreads();
+    }
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
@@ -639,7 +805,7 @@ struct DevicePipeline::Impl {
     DevBuf d_rec;
     PinBuf h_rec, h_depth, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
-    cudaEvent_t ev[16];
+    cudaEvent_t ev[20];
 #endif
 
     void mark(int i) {
@@ -657,26 +823,67 @@ struct DevicePipeline::Impl {
 #endif
     }
 
-    // exclusive scan of n uint32 values; returns the total.  out may alias in.
+    // exclusive scan of n uint32 values; returns the total (when asked: it costs the one host round trip).  out may alias in.
     uint32_t exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, int level = 0, bool want_total = true) {
         if (n == 0) return 0;
         if (level >= 4) throw std::runtime_error("scan too deep");
-        const uint64_t nb = (n + 255) / 256;
-        scan_tmp[level].ensure((nb + 1) * sizeof(uint32_t));
+#ifndef AC_EMULATE
+        const uint64_t tile = AC_SCAN_TILE;
+#else
+        const uint64_t tile = 256;
+#endif
+        const uint64_t nb = (n + tile - 1) / tile;
+        scan_tmp[level].ensure((nb + 4) * sizeof(uint32_t));
         uint32_t* sums = scan_tmp[level].as<uint32_t>();
-        ac_launch("scan_reduce", &stream, ScanReduceBody{in, n, sums}, nb);
+        auto reduce = [&]() {
+#ifndef AC_EMULATE
+            ac_scan_reduce_kernel<<<(unsigned)nb, 256, 0, stream.s>>>(in, n, sums); ++g_ac_kernel_launches;
+#else
+            ac_launch("scan_reduce", &stream, ScanReduceBody{in, n, sums}, nb);
+#endif
+        };
+        auto apply = [&](const uint32_t* block_off) {
+#ifndef AC_EMULATE
+            ac_scan_apply_kernel<<<(unsigned)nb, 256, 0, stream.s>>>(in, n, block_off, out); ++g_ac_kernel_launches;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) throw std::runtime_error(std::string("launch scan: ") + cudaGetErrorString(e));
+#else
+            ac_launch("scan_apply", &stream, ScanApplyBody{in, n, block_off, out}, nb);
+#endif
+        };
+        if (nb > 0x7FFFFFFFull) throw std::runtime_error("scan too large");
+        reduce();
         uint32_t total_sum = 0;
         if (nb == 1) {
-            if (want_total) { ac_d2h(&total_sum, sums, sizeof(uint32_t), &stream); ac_sync(&stream); }   // the only host round trip
-            ac_launch("scan_apply", &stream, ScanApplyBody{in, n, nullptr, out}, nb);
+            if (want_total) { ac_d2h(&total_sum, sums, sizeof(uint32_t), &stream); ac_sync(&stream); }
+            apply(nullptr);
         } else {
             total_sum = exclusive_scan(sums, sums, nb, level + 1, want_total);
-            ac_launch("scan_apply", &stream, ScanApplyBody{in, n, sums, out}, nb);
+            apply(sums);
         }
         return total_sum;
     }
 
-    template <int W> void build_w(PipelineResult& out, bool keep_positions);
+    // pipeline state shared by the stages
+    std::vector<SeqInfo> host_seqs;
+    uint64_t cap = 0, n_windows = 0, n_runs = 0, g_begin = 0, g_end = 0, n_slots_used = 0, n_dotted = 0;
+    bool any_dotted = false, is_multi = false;
+    int stage = 0;
+    DevBuf run_hs, run_ts, exp_flag, occ_list, bloom;
+    void set_device() {
+#ifndef AC_EMULATE
+        AC_CUDA_CHECK(cudaSetDevice(device));
+#endif
+    }
+    template <int W> void local_w(uint32_t seq_lo, uint32_t seq_hi, bool multi);
+    template <int W> void merge_w(const void* dev_ptr, uint64_t n);
+    template <int W> void runs_local_w();
+    template <int W> void finish_w(PipelineResult& out, bool keep_positions);
+    uint64_t exp_n = 0;
+    uint64_t do_count_entries();
+    void do_export_entries(void* dst, uint64_t cap_records);
+    void do_export_runs(void* dst, uint64_t cap_records);
+    void do_import_runs(const void* dev_ptr, uint64_t n);
 };
 
 DevicePipeline::DevicePipeline(int device, void* stream) : impl(new Impl) {
@@ -723,7 +930,8 @@ void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo*
     if (W > AC_MAX_W) throw std::runtime_error("k-mer sizes above 127 are not supported by the GPU path (no CPU fallback exists)");
     if (total >= (1ull << 36)) throw std::runtime_error("more than 2^36 padded input bytes are not supported");
     if (n_seqs == 0 || total == 0) throw std::runtime_error("no sequences");
-    m.total = total; m.n_seqs = n_seqs; m.k = k; m.W = W;
+    m.total = total; m.n_seqs = n_seqs; m.k = k; m.W = W; m.stage = 0;
+    m.host_seqs.assign(seqs, seqs + n_seqs);
     m.mark(0);
     m.ascii.ensure(total);
     ac_h2d(m.ascii.p, ascii, total, &m.stream);
@@ -732,18 +940,20 @@ void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo*
     m.mark(1);
 }
 
-template <int W> void DevicePipeline::Impl::build_w(PipelineResult& out, bool keep_positions) {
+// ---- stage 1: pack + k-mer table over this rank's sequences ----
+template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t seq_hi, bool multi) {
     const KParams p = make_kparams(k, W);
-    out = PipelineResult();
-    out.W = W;
-
-    // windows = total - n_seqs*(k-1); a canonical table can hold at most that many entries
-    const uint64_t n_windows = total - (uint64_t)n_seqs * (k - 1);
-    uint64_t cap = n_windows + n_windows / 2 + 64;
+    if (seq_lo > seq_hi || seq_hi > n_seqs) throw std::runtime_error("bad sequence shard");
+    const SeqInfo* hs = host_seqs.data();
+    if (seq_lo == seq_hi) { g_begin = g_end = 0; }       // a rank without sequences still merges, and computes the replicated stages
+    else { g_begin = hs[seq_lo].start; g_end = hs[seq_hi - 1].start + hs[seq_hi - 1].len; }
+    is_multi = multi;
+    // windows = total - n_seqs*(k-1); a canonical table can hold at most that many entries (all ranks' windows: after
+    // the exchange every rank's table holds the k-mers of every sequence)
+    n_windows = total - (uint64_t)n_seqs * (k - 1);
+    cap = n_windows + n_windows / 2 + 64;
     if (cap >= 0xFFFFFFF0ull) throw std::runtime_error("input too large for 32-bit slot indices");
-    out.capacity = cap;
 
-    // ---- pack ----
     mark(2);
     const uint64_t n_words = (total + 31) / 32;
     packed.ensure((n_words + W + 2) * sizeof(uint64_t));
@@ -751,45 +961,113 @@ template <int W> void DevicePipeline::Impl::build_w(PipelineResult& out, bool ke
     ac_launch("pack", &stream, PackBody{ascii.as<uint8_t>(), total, packed.as<uint64_t>()}, n_words);
     mark(3);
 
-    // ---- insert ----
     slots.ensure(cap * sizeof(Slot));
     ac_launch("init_slots", &stream, InitSlotsBody{slots.as<Slot>()}, cap);
     pos_slot.ensure(total * sizeof(uint32_t));
-    counters.ensure(2 * sizeof(unsigned long long));
-    ac_memset(counters.p, 0, 2 * sizeof(unsigned long long), &stream);
-    TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
-    ac_launch("insert", &stream, InsertBody<W>{tv, p, total, pos_slot.as<uint32_t>(), counters.as<unsigned long long>()},
-              (total + AC_CHUNK - 1) / AC_CHUNK);
+    counters.ensure(2 * AC_STRIPES * sizeof(unsigned long long));
+    ac_memset(counters.p, 0, 2 * AC_STRIPES * sizeof(unsigned long long), &stream);
+    const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
+    ac_launch("insert", &stream, InsertBody<W>{tv, p, g_begin, g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>()},
+              (g_end - g_begin + AC_CHUNK - 1) / AC_CHUNK);
     mark(4);
-    unsigned long long hc[2];
-    ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
-    out.n_slots_used = hc[0]; out.n_dotted = hc[1];
-    const bool any_dotted = hc[1] != 0;
+    stage = 1;
+}
 
-    // ---- adjacency ----
+uint64_t DevicePipeline::Impl::do_count_entries() {
+    if (stage < 1) throw std::runtime_error("build_local must precede the entry export");
+    exp_flag.ensure(cap * 4);
+    ac_launch("export_flag", &stream, ExportFlagBody{slots.as<Slot>(), exp_flag.as<uint32_t>()}, cap);
+    exp_n = exclusive_scan(exp_flag.as<uint32_t>(), exp_flag.as<uint32_t>(), cap);
+    return exp_n;
+}
+void DevicePipeline::Impl::do_export_entries(void* dst, uint64_t cap_records) {
+    if (cap_records < exp_n) throw std::runtime_error("entry buffer too small");
+    ac_launch("export_scatter", &stream, ExportScatterBody{slots.as<Slot>(), exp_flag.as<uint32_t>(), (Slot*)dst}, cap);
+    ac_sync(&stream);
+}
+
+template <int W> void DevicePipeline::Impl::merge_w(const void* dev_ptr, uint64_t n) {
+    if (stage < 1) throw std::runtime_error("build_local must precede merge_entries");
+    const KParams p = make_kparams(k, W);
+    const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
+    ac_launch("merge", &stream, MergeBody<W>{tv, p, (const Slot*)dev_ptr, pos_slot.as<uint32_t>(), counters.as<unsigned long long>()}, n);
+}
+
+// ---- stage 2: adjacency over the (now global) table, unitig occurrences along this rank's sequences ----
+template <int W> void DevicePipeline::Impl::runs_local_w() {
+    if (stage < 1) throw std::runtime_error("build_local must precede runs_local");
+    const KParams p = make_kparams(k, W);
+    const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
+    mark(13);
+    std::vector<unsigned long long> hc(2 * AC_STRIPES);
+    ac_d2h(hc.data(), counters.p, hc.size() * sizeof(unsigned long long), &stream); ac_sync(&stream);
+    n_slots_used = 0; n_dotted = 0;
+    for (int x = 0; x < AC_STRIPES; ++x) { n_slots_used += hc[2 * x]; n_dotted += hc[2 * x + 1]; }
+    any_dotted = n_dotted != 0;
+
     flags8.ensure(cap);
-    ac_launch("adjacency", &stream, AdjacencyBody<W>{tv, p, any_dotted, flags8.as<uint8_t>()}, cap);
+    exp_flag.ensure(cap * 4); occ_list.ensure((n_slots_used + 1) * 4);
+    ac_launch("occupied_flag", &stream, ExportFlagBody{slots.as<Slot>(), exp_flag.as<uint32_t>()}, cap);
+    exclusive_scan(exp_flag.as<uint32_t>(), exp_flag.as<uint32_t>(), cap, 0, false);
+    ac_launch("occupied_list", &stream, OccupiedListBody{slots.as<Slot>(), exp_flag.as<uint32_t>(), occ_list.as<uint32_t>()}, cap);
+    const uint64_t bloom_words = n_slots_used / 4 + 64;       // 16 bits per distinct k-mer
+    bloom.ensure(bloom_words * 8);
+    ac_memset(bloom.p, 0, bloom_words * 8, &stream);
+    ac_launch("bloom_build", &stream, BloomBuildBody<W>{tv, p, occ_list.as<uint32_t>(), bloom.as<uint64_t>(), bloom_words}, n_slots_used);
+    ac_launch("adjacency", &stream, AdjacencyBody<W>{tv, p, any_dotted, occ_list.as<uint32_t>(), flags8.as<uint8_t>(), bloom.as<uint64_t>(), bloom_words}, n_slots_used);
     mark(5);
 
-    // ---- unitig occurrences along the sequences ----
     const uint64_t n_bwords = (total + 63) / 64;
     bmask.ensure(n_bwords * sizeof(uint64_t)); bcount.ensure(n_bwords * sizeof(uint32_t)); boff.ensure(n_bwords * sizeof(uint32_t));
-    ac_launch("boundaries", &stream, BoundaryBody{packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, p.h, total, pos_slot.as<uint32_t>(),
+    ac_launch("boundaries", &stream, BoundaryBody{packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, p.h, g_begin, g_end, pos_slot.as<uint32_t>(),
                                                   flags8.as<uint8_t>(), bmask.as<uint64_t>(), bcount.as<uint32_t>()}, n_bwords);
-    const uint64_t n_runs = exclusive_scan(bcount.as<uint32_t>(), boff.as<uint32_t>(), n_bwords);
+    n_runs = exclusive_scan(bcount.as<uint32_t>(), boff.as<uint32_t>(), n_bwords);
     mark(6);
-    run_start.ensure(n_runs * sizeof(uint64_t)); run_len.ensure(n_runs * 4); run_uk.ensure(n_runs * 4); run_dir.ensure(n_runs);
+    run_start.ensure(n_runs * sizeof(uint64_t)); run_len.ensure(n_runs * 4); run_hs.ensure(n_runs * 4); run_ts.ensure(n_runs * 4);
+    ac_launch("run_scatter", &stream, RunScatterBody{bmask.as<uint64_t>(), boff.as<uint32_t>(), run_start.as<uint64_t>()}, n_bwords);
+    ac_launch("run_ends", &stream, RunEndsLocalBody{seqs.as<SeqInfo>(), n_seqs, run_start.as<uint64_t>(), n_runs, pos_slot.as<uint32_t>(),
+                                                    run_len.as<uint32_t>(), run_hs.as<uint32_t>(), run_ts.as<uint32_t>()}, n_runs);
+    stage = 2;
+}
+
+void DevicePipeline::Impl::do_export_runs(void* dst, uint64_t cap_records) {
+    if (stage < 2) throw std::runtime_error("runs_local must precede export_runs");
+    if (cap_records < n_runs) throw std::runtime_error("run buffer too small");
+    ac_launch("run_export", &stream, RunExportBody{run_start.as<uint64_t>(), run_len.as<uint32_t>(), run_hs.as<uint32_t>(), run_ts.as<uint32_t>(),
+                                                   slots.as<Slot>(), (RunRec*)dst}, n_runs);
+    ac_sync(&stream);
+}
+
+void DevicePipeline::Impl::do_import_runs(const void* dev_ptr, uint64_t n) {
+    if (stage < 2) throw std::runtime_error("runs_local must precede import_runs");
+    n_runs = n;
+    run_start.ensure(n_runs * sizeof(uint64_t)); run_len.ensure(n_runs * 4); run_hs.ensure(n_runs * 4); run_ts.ensure(n_runs * 4);
+    ac_launch("run_import", &stream, RunImportBody{(const RunRec*)dev_ptr, pos_slot.as<uint32_t>(), run_start.as<uint64_t>(), run_len.as<uint32_t>(),
+                                                   run_hs.as<uint32_t>(), run_ts.as<uint32_t>()}, n_runs);
+}
+
+// ---- stage 3: unitigs, seeds, links, seed order and the host-ready arrays (over every occurrence handed to it) ----
+template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool keep_positions) {
+    if (stage < 2) throw std::runtime_error("runs_local must precede finish");
+    const KParams p = make_kparams(k, W);
+    const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
+    out = PipelineResult();
+    out.W = W; out.capacity = cap; out.n_slots_used = n_slots_used; out.n_dotted = n_dotted;
+    const uint64_t n_runs = this->n_runs;
+    const bool any_dotted = this->any_dotted;
+    const uint64_t n_windows = this->n_windows;
+    mark(14);
+    run_uk.ensure(n_runs * 4); run_dir.ensure(n_runs);
     is_rep.ensure(n_runs * 4); rep_idx.ensure(n_runs * 4); run_unitig.ensure(n_runs * 4);
     uid_rep.ensure(cap * 4); slot_unitig.ensure(cap * 4);
     ac_memset(uid_rep.p, 0xFF, cap * 4, &stream);
-    ac_launch("run_scatter", &stream, RunScatterBody{bmask.as<uint64_t>(), boff.as<uint32_t>(), run_start.as<uint64_t>()}, n_bwords);
-    ac_launch("run_info", &stream, RunInfoBody{packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, p.h, run_start.as<uint64_t>(), n_runs, pos_slot.as<uint32_t>(),
-                                               run_len.as<uint32_t>(), run_uk.as<uint32_t>(), run_dir.as<uint8_t>(), uid_rep.as<uint32_t>()}, n_runs);
+    ac_launch("run_key", &stream, RunKeyBody{packed.as<uint64_t>(), p.h, run_start.as<uint64_t>(), run_hs.as<uint32_t>(), run_ts.as<uint32_t>(),
+                                             run_uk.as<uint32_t>(), run_dir.as<uint8_t>(), uid_rep.as<uint32_t>()}, n_runs);
     ac_launch("rep_flag", &stream, RepFlagBody{run_uk.as<uint32_t>(), uid_rep.as<uint32_t>(), is_rep.as<uint32_t>()}, n_runs);
     const uint32_t n_unitigs = exclusive_scan(is_rep.as<uint32_t>(), rep_idx.as<uint32_t>(), n_runs);
     unitigs.ensure((size_t)n_unitigs * sizeof(DeviceUnitig));
     ac_launch("run_assign", &stream, RunAssignBody{run_start.as<uint64_t>(), run_len.as<uint32_t>(), run_uk.as<uint32_t>(), run_dir.as<uint8_t>(),
-                                                   uid_rep.as<uint32_t>(), rep_idx.as<uint32_t>(), pos_slot.as<uint32_t>(), slots.as<Slot>(),
+                                                   uid_rep.as<uint32_t>(), rep_idx.as<uint32_t>(), run_hs.as<uint32_t>(), run_ts.as<uint32_t>(), slots.as<Slot>(),
                                                    run_unitig.as<uint32_t>(), unitigs.as<DeviceUnitig>(), slot_unitig.as<uint32_t>()}, n_runs);
     mark(7);
 
@@ -884,21 +1162,38 @@ template <int W> void DevicePipeline::Impl::build_w(PipelineResult& out, bool ke
     out.next_off = h_next_off.as<uint32_t>(); out.next = h_next.as<UStrand>(); out.prev_off = h_prev_off.as<uint32_t>(); out.prev = h_prev.as<UStrand>();
     out.path_off = h_path_off.as<uint64_t>(); out.path = h_path.as<UStrand>();
     out.run_start = keep_positions ? h_run_start.as<uint64_t>() : nullptr; out.run_len = keep_positions ? h_run_len.as<uint32_t>() : nullptr;
-    out.t.h2d = between(0, 1); out.t.pack = between(2, 3); out.t.insert = between(3, 4); out.t.adjacency = between(4, 5);
-    out.t.boundaries = between(5, 6); out.t.runs = between(6, 7); out.t.unitigs = between(7, 8); out.t.links = between(8, 9);
-    out.t.seed_sort = between(9, 10); out.t.emit = between(10, 11); out.t.d2h = between(11, 12); out.t.total = between(2, 12);
+    out.t.h2d = between(0, 1); out.t.pack = between(2, 3); out.t.insert = between(3, 4); out.t.adjacency = between(13, 5);
+    out.t.boundaries = between(5, 6); out.t.runs = between(14, 7); out.t.unitigs = between(7, 8); out.t.links = between(8, 9);
+    out.t.seed_sort = between(9, 10); out.t.emit = between(10, 11); out.t.d2h = between(11, 12); out.t.total = between(2, 4) + between(13, 6) + between(14, 12);
 }
 
-void DevicePipeline::build(PipelineResult& out, bool keep_positions) {
-    Impl& m = *impl;
-#ifndef AC_EMULATE
-    AC_CUDA_CHECK(cudaSetDevice(m.device));
-#endif
-    switch (m.W) {
-        case 1: m.build_w<1>(out, keep_positions); break;
-        case 2: m.build_w<2>(out, keep_positions); break;
-        case 3: m.build_w<3>(out, keep_positions); break;
-        case 4: m.build_w<4>(out, keep_positions); break;
-        default: throw std::runtime_error("upload() must precede build()");
-    }
+#define AC_DISPATCH_W(fn, ...) switch (W) { case 1: fn<1>(__VA_ARGS__); break; case 2: fn<2>(__VA_ARGS__); break; \
+    case 3: fn<3>(__VA_ARGS__); break; case 4: fn<4>(__VA_ARGS__); break; default: throw std::runtime_error("upload() must precede build()"); }
+
+void DevicePipeline::build_local(uint32_t seq_lo, uint32_t seq_hi, bool multi) {
+    Impl& m = *impl; m.set_device(); const int W = m.W;
+    AC_DISPATCH_W(m.local_w, seq_lo, seq_hi, multi)
+}
+uint64_t DevicePipeline::count_entries() { impl->set_device(); return impl->do_count_entries(); }
+void DevicePipeline::export_entries(void* dst, uint64_t cap_records) { impl->set_device(); impl->do_export_entries(dst, cap_records); }
+void DevicePipeline::merge_entries(const void* dev_ptr, uint64_t n) {
+    Impl& m = *impl; m.set_device(); const int W = m.W;
+    AC_DISPATCH_W(m.merge_w, dev_ptr, n)
+}
+void DevicePipeline::runs_local() {
+    Impl& m = *impl; m.set_device(); const int W = m.W;
+    AC_DISPATCH_W(m.runs_local_w)
+}
+uint64_t DevicePipeline::local_runs() const { return impl->n_runs; }
+void DevicePipeline::export_runs(void* dst, uint64_t cap_records) { impl->set_device(); impl->do_export_runs(dst, cap_records); }
+void DevicePipeline::import_runs(const void* dev_ptr, uint64_t n) { impl->set_device(); impl->do_import_runs(dev_ptr, n); }
+void DevicePipeline::finish(PipelineResult& out, bool keep_positions) {
+    Impl& m = *impl; m.set_device(); const int W = m.W;
+    AC_DISPATCH_W(m.finish_w, out, keep_positions)
+}
+
+void DevicePipeline::build(PipelineResult& out, bool keep_positions) {   // single GPU: every sequence is local, nothing to exchange
+    build_local(0, impl->n_seqs, false);
+    runs_local();
+    finish(out, keep_positions);
 }

@@ -23,7 +23,12 @@ struct DeviceUnitig {
     uint32_t flip;            // 1: the unitig's forward strand is the reverse complement of the representative occurrence
     int32_t min_d;            // smallest k-mer of both strands (kmer_graph.rs:168-173 order) = the walk's seed
     uint64_t min_w[AC_MAX_W];
+    uint32_t head_slot, tail_slot;   // table slots of the representative occurrence's first and last k-mer
 };
+
+// One unitig occurrence in rank-independent terms (multi-GPU exchange): where it lies and the smallest occurrence
+// of its first and last k-mer.
+struct RunRec { uint64_t start; uint32_t len; uint32_t pad; uint64_t head_rep, tail_rep; };
 
 // The mutable per-unitig state in one 32-byte record (one cache line touch per unitig during repeat expansion).
 struct UnitigRec {
@@ -70,7 +75,17 @@ public:
     ~DevicePipeline();
     // ascii: all padded, end-repaired forward strands concatenated (bytes in "ACGT."); seqs: their layout.
     void upload(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t k);
-    void build(PipelineResult& out, bool keep_positions);   // kernels + D2H of the results
+    void build(PipelineResult& out, bool keep_positions);   // kernels + D2H of the results (single GPU: all the stages below)
+    // Multi-GPU stages (one process per GPU; the collectives between them are done by the caller on device pointers):
+    void build_local(uint32_t seq_lo, uint32_t seq_hi, bool multi);     // table over this rank's sequences [seq_lo, seq_hi)
+    uint64_t count_entries();                                           // occupied slots of the local table
+    void export_entries(void* dst, uint64_t cap_records);               // their 16-byte Slot records, compacted into caller-owned device memory
+    void merge_entries(const void* dev_ptr, uint64_t n);                // fold another rank's records into the local table
+    void runs_local();                                                  // adjacency + this rank's unitig occurrences
+    uint64_t local_runs() const;
+    void export_runs(void* dst, uint64_t cap_records);                  // 32-byte RunRec records, ascending coordinate, into caller-owned device memory
+    void import_runs(const void* dev_ptr, uint64_t n);                  // rank 0: every rank's records, concatenated in rank order
+    void finish(PipelineResult& out, bool keep_positions);              // unitigs, seeds, links, seed order, host-ready arrays
     unsigned long long kernel_launches() const;
     struct Impl;
 private:

@@ -96,6 +96,21 @@ int ac_clear_sequences(ac_handle* h);
 int ac_upload(ac_handle* h);            /* host -> HBM copy of the added sequences */
 int ac_build(ac_handle* h);             /* k-mer table, unitigs, links, renumber: the graph after from_kmer_graph */
 int ac_simplify(ac_handle* h);          /* simplify_structure */
+
+/* Multi-GPU form of ac_build: one process per GPU, every process adds and uploads ALL sequences, owns the
+ * contiguous block [seq_lo, seq_hi) of them (index = order of ac_add_sequence), and the caller (e.g. torch.distributed over
+ * NCCL) moves the exported records between the processes.  Buffers are device memory on the handle's device.
+ *   ac_build_local -> ac_entries_count/export -> [all-gather] -> ac_entries_merge (every other rank's records)
+ *   -> ac_runs_local -> ac_runs_export -> [gather to rank 0] -> rank 0: ac_runs_import (all ranks, rank order) -> ac_build_finish
+ * Records are opaque: 16 bytes per k-mer entry, 32 bytes per unitig occurrence. */
+int ac_build_local(ac_handle* h, uint32_t seq_lo, uint32_t seq_hi, uint32_t multi);
+int ac_entries_count(ac_handle* h, uint64_t* n);
+int ac_entries_export(ac_handle* h, void* dst, uint64_t cap_records);
+int ac_entries_merge(ac_handle* h, const void* src, uint64_t n);
+int ac_runs_local(ac_handle* h, uint64_t* n_runs);
+int ac_runs_export(ac_handle* h, void* dst, uint64_t cap_records);
+int ac_runs_import(ac_handle* h, const void* src, uint64_t n);
+int ac_build_finish(ac_handle* h);      /* on the rank that imported the runs: the graph after from_kmer_graph */
 int ac_counts_get(const ac_handle* h, ac_counts* out);
 int ac_unitigs_copy(const ac_handle* h, ac_unitigs* out);
 int ac_path_copy(const ac_handle* h, uint64_t seq_index, int32_t* out, uint64_t cap, uint64_t* n);  /* get_unitig_path_for_sequence_i32 */
