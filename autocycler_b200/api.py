@@ -58,7 +58,7 @@ EXPORTS = ["ac_last_error", "ac_version", "ac_create", "ac_destroy", "ac_add_seq
            "ac_build", "ac_simplify", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
            "ac_timings_get", "ac_compress_dir", "ac_load_sequences", "ac_sequence_get",
            "ac_build_local", "ac_entries_count", "ac_entries_export", "ac_entries_merge", "ac_runs_local", "ac_runs_export",
-           "ac_runs_import", "ac_build_finish"]
+           "ac_runs_import", "ac_build_finish", "ac_gfa_data"]
 
 _libs = {}
 
@@ -100,6 +100,7 @@ def load_library(path=None):
     lib.ac_runs_export.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.ac_runs_import.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.ac_build_finish.argtypes = [C.c_void_p]
+    lib.ac_gfa_data.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     _libs[path] = lib
     return lib
 
@@ -244,6 +245,11 @@ class UnitigGraph:
             self._h.check(self._h.lib.ac_gfa_copy(self._h.ptr, buf, n.value))
             del buf
         return out
+
+    def gfa_view(self):             # the same bytes without a copy: a memoryview of the library's buffer, valid until the next call on this graph
+        n = C.c_uint64(); ptr = C.c_void_p()
+        self._h.check(self._h.lib.ac_gfa_data(self._h.ptr, C.byref(ptr), C.byref(n)))
+        return memoryview((C.c_char * n.value).from_address(ptr.value)) if n.value else memoryview(b"")
 
     def save_gfa(self, gfa_filename, sequences=None, use_other_colour=False):   # unitig_graph.rs:317-331
         with open(gfa_filename, "wb") as f:

@@ -333,6 +333,14 @@ int ac_gfa_size(ac_handle* h, uint64_t* n_bytes) {
     AC_GUARD_END(h)
 }
 
+int ac_gfa_data(ac_handle* h, const char** data, uint64_t* n_bytes) {   // borrowed pointer, valid until the next call on this handle
+    if (!data) return set_error(h, AC_EINVAL, "null argument");
+    int rc = ac_gfa_size(h, n_bytes);
+    if (rc != AC_OK) return rc;
+    *data = h->gfa.data();
+    return AC_OK;
+}
+
 int ac_gfa_copy(ac_handle* h, char* buf, uint64_t cap) {
     uint64_t n = 0;
     int rc = ac_gfa_size(h, &n);

@@ -28,6 +28,12 @@ def from_kmer_graph_distributed(kmer_graph, seq_lo, seq_hi, device, group=None, 
     from .api import UnitigGraph
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+    def settle():
+        # The library may run on its own stream: make every collective's result visible before a kernel reads it.
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize(device)
+
     h = kmer_graph._h
     lib = h.lib
     h.check(lib.ac_build_local(h.ptr, seq_lo, seq_hi, 1))
@@ -43,6 +49,7 @@ def from_kmer_graph_distributed(kmer_graph, seq_lo, seq_hi, device, group=None, 
     h.check(lib.ac_entries_export(h.ptr, send.data_ptr(), max_n))
     recv = [torch.empty_like(send) for _ in range(world)]
     dist.all_gather(recv, send, group=group)
+    settle()
     for r in range(world):
         if r != rank and sizes[r]:
             h.check(lib.ac_entries_merge(h.ptr, recv[r].data_ptr(), sizes[r]))
@@ -61,9 +68,11 @@ def from_kmer_graph_distributed(kmer_graph, seq_lo, seq_hi, device, group=None, 
     h.check(lib.ac_runs_export(h.ptr, rsend.data_ptr(), max_r))
     rrecv = [torch.empty_like(rsend) for _ in range(world)] if rank == 0 else None
     dist.gather(rsend, rrecv, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    settle()
     if rank != 0:
         return None
     all_runs = torch.cat([rrecv[r][:rsizes[r] * RUN_BYTES] for r in range(world)])   # rank order == coordinate order
+    settle()
     h.check(lib.ac_runs_import(h.ptr, all_runs.data_ptr(), sum(rsizes)))
     h.check(lib.ac_build_finish(h.ptr))
     if stats is not None:

@@ -89,10 +89,10 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
-    if world > 1:
-        raise SystemExit("multi-GPU bench path not built yet")
-
-    assemblies = synth.make_assemblies("cfg2")
+    from autocycler_b200 import dist as acdist
+    # Weak scaling: 8 assemblies of the cfg2 genome per rank (N=1 is exactly cfg2; N=8 is 64 assemblies, the shape of cfg5).
+    # Every rank stages all sequences (end repair needs all of them anyway) and owns a contiguous block.
+    assemblies = synth.make_assemblies("cfg2", n_assemblies=8 * world)
     n_bases = synth.total_bases(assemblies)
     stream = torch.cuda.current_stream()
     # stage A once, untimed: product loader + end repair, then a handle bound to torch's current stream
@@ -100,13 +100,26 @@ def run_gpu(args):
     kg = api.KmerGraph(K, device=local, stream=stream.cuda_stream)
     kg.add_sequences(seqs, count, upload=False)          # strands staged in pinned host memory
     lib = kg._h.lib
+    dev = torch.device("cuda", local)
+    # sequences of assemblies [8*rank, 8*rank+8): contiguous because files are loaded in sorted order
+    first_of = {}
+    for i, sq in enumerate(seqs):
+        first_of.setdefault(sq.filename, i)
+    files = sorted(first_of, key=first_of.get)
+    bounds = [first_of[f] for f in files] + [len(seqs)]
+    seq_lo, seq_hi = bounds[8 * rank], bounds[8 * (rank + 1)]
 
     def step(upload):
         if upload:
             kg.upload()
-        g = api.UnitigGraph.from_kmer_graph(kg)
+        if world == 1:
+            g = api.UnitigGraph.from_kmer_graph(kg)
+        else:
+            g = acdist.from_kmer_graph_distributed(kg, seq_lo, seq_hi, dev)
+            if g is None:
+                return None, None
         api.simplify_structure(g)
-        return g, g.gfa_bytes()
+        return g, g.gfa_view()
 
     def barrier():
         torch.cuda.synchronize()
@@ -126,7 +139,7 @@ def run_gpu(args):
         last = None
         for _ in range(args.steps):
             g, gfa = step(upload)
-            t = g.timings()
+            t = api.AcTimings(); lib.ac_timings_get(kg._h.ptr, t)
             ins.append(t.insert); dev.append(t.as_dict()); last = (g, gfa, t)
         e1.record(stream)
         barrier()
@@ -144,11 +157,16 @@ def run_gpu(args):
     clocks = sampler.stop()
 
     g, gfa, t = last
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     W = (2 * K + 63) // 64
     bytes_per_window = 8 * W + 20.25        # entry 8 + representative key 8W + count RMW 8 + slot id 4 + packed base 0.25
     insert_ms = sum(ins_ms) / len(ins_ms)
     peak, peak_kind = measured_peak()
-    achieved = t.insert_occurrences * bytes_per_window / (insert_ms * 1e-3) / 1e9
+    own_windows = sum(sq.length for sq in seqs[seq_lo:seq_hi])     # the insert kernel only hashes this rank's sequences
+    achieved = own_windows * bytes_per_window / (insert_ms * 1e-3) / 1e9
     value = n_bases * args.steps / (ms_res * 1e-3) / 1e6
     e2e = n_bases * args.steps / (ms_e2e * 1e-3) / 1e6
     mean = lambda key: sum(d[key] for d in dev_t) / len(dev_t)
@@ -156,7 +174,8 @@ def run_gpu(args):
         "metric": METRIC, "value": round(value, 3), "unit": "Mbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic (splitmix64 genomes, SURVEY.md §8d)",
-        "config": {"workload": WORKLOAD, "k": K, "input_bases": n_bases, "sequences": len(seqs),
+        "config": {"workload": WORKLOAD if world == 1 else f"{8 * world} synthetic 4.64 Mbp assemblies (cfg2 genome), 8 per rank, k=51", "k": K, "input_bases": n_bases, "sequences": len(seqs),
+                   "exchange": None if world == 1 else "all-gather of deduplicated k-mer entries (16 B each) over NCCL, then gather of unitig occurrences to rank 0",
                    "l2": "working set per step (table %.0f MB + per-position arrays) exceeds the 126 MB L2 and is re-initialised every step" % (t.table_capacity * 16 / 1e6),
                    "gfa_bytes": len(gfa), "unitigs": int(g.counts().n_unitigs)},
         "e2e": {"value": round(e2e, 3), "unit": "Mbp/s", "ms_per_step": round(ms_e2e / args.steps, 3),
@@ -165,7 +184,7 @@ def run_gpu(args):
         "clocks": clocks,
         "roofline": {"kernel": "InsertBody<%d> (k-mer hash insert)" % W, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "peak_kind": peak_kind, "traffic": None,
-                     "algorithmic_bytes_per_window": bytes_per_window, "windows_per_launch": int(t.insert_occurrences), "kernel_ms": round(insert_ms, 3)},
+                     "algorithmic_bytes_per_window": bytes_per_window, "windows_per_launch": int(own_windows), "kernel_ms": round(insert_ms, 3)},
         "stage_ms": {k2: round(mean(k2), 3) for k2 in ("pack", "insert", "adjacency", "boundaries", "runs", "unitigs", "links", "seed_sort", "emit", "d2h", "device_total",
                                                         "host_graph", "host_simplify", "host_gfa")},
     }

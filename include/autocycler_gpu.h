@@ -116,6 +116,7 @@ int ac_unitigs_copy(const ac_handle* h, ac_unitigs* out);
 int ac_path_copy(const ac_handle* h, uint64_t seq_index, int32_t* out, uint64_t cap, uint64_t* n);  /* get_unitig_path_for_sequence_i32 */
 int ac_gfa_size(ac_handle* h, uint64_t* n_bytes);
 int ac_gfa_copy(ac_handle* h, char* buf, uint64_t cap);
+int ac_gfa_data(ac_handle* h, const char** data, uint64_t* n_bytes);   /* the same bytes, borrowed: valid until the next call on h */
 int ac_timings_get(const ac_handle* h, ac_timings* out);
 
 /* `autocycler compress -i assemblies_dir -a autocycler_dir --kmer k --max_contigs m -t threads`
