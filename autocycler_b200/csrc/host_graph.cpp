@@ -156,16 +156,22 @@ uint64_t HostGraph::link_count_single() const {   // unitig_graph.rs:478-507: a 
 // ------------------------------------------------------------------------------------------------
 // arena growth
 // ------------------------------------------------------------------------------------------------
+void HostGraph::reserve_arena(uint64_t extra) {   // make room for `extra` more bytes (single-threaded)
+    if (arena_used + extra <= arena_cap) return;
+    std::vector<char> bigger((arena_used + extra) * 2);
+    memcpy(bigger.data(), arena, arena_used);
+    arena_overflow.swap(bigger);
+    arena = arena_overflow.data(); arena_cap = arena_overflow.size();
+}
 void HostGraph::relocate(uint32_t idx, uint32_t before, uint32_t after) {
     const uint64_t need = (uint64_t)before + rec[idx].len + after;
-    if (arena_used + need > arena_cap) {   // outgrew the pinned arena: continue in ordinary host memory
-        std::vector<char> bigger((arena_used + need) * 2);
-        memcpy(bigger.data(), arena, arena_used);
-        arena_overflow.swap(bigger);
-        arena = arena_overflow.data(); arena_cap = arena_overflow.size();
+    const uint64_t at = __atomic_fetch_add(&arena_used, need, __ATOMIC_RELAXED);
+    if (at + need > arena_cap) {
+        // only reachable from the sequential passes (the parallel pass reserves its worst case up front)
+        __atomic_fetch_sub(&arena_used, need, __ATOMIC_RELAXED);
+        reserve_arena(need);
+        return relocate(idx, before, after);
     }
-    const uint64_t at = arena_used;
-    arena_used += need;
     memmove(arena + at + before, arena + rec[idx].seq_off, rec[idx].len);
     rec[idx].seq_off = at + before; rec[idx].room_before = before; rec[idx].room_after = after;
 }
@@ -290,14 +296,81 @@ void HostGraph::compute_dependents() {
     });
 }
 
-void HostGraph::mark_dependents(uint32_t u) {
+void HostGraph::mark_dependents(uint32_t u, bool shared, int64_t below) {
     const Deps& d = deps[u];
-    for (int i = 0; i < 6; ++i) if (d.c[i] >= 0) dirty[(size_t)d.c[i] >> 6] |= 1ull << (d.c[i] & 63);
+    for (int i = 0; i < 6; ++i) if (d.c[i] >= 0 && d.c[i] < below) {
+        const uint64_t m = 1ull << (d.c[i] & 63);
+        if (shared) __atomic_fetch_or(&dirty[(size_t)d.c[i] >> 6], m, __ATOMIC_RELAXED); else dirty[(size_t)d.c[i] >> 6] |= m;
+    }
+}
+
+// One evaluation of candidate ci: graph_simplification.rs:64-84 for one (unitig, side).  Returns the bases moved.
+// `shared` = other threads are applying candidates with disjoint unitig sets at the same time (bitmap and arena bump
+// go through atomics).
+size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
+    const size_t w = ci >> 6; const uint64_t bit_mask = 1ull << (ci & 63);
+    const Candidate cand = cands[ci];
+    const uint32_t idx = cand.idx;
+    const UStrand* grp = cand.src; const uint32_t gn = cand.gn;
+
+    bool dup = false, pristine = first_pass; uint32_t min_len = 0xFFFFFFFFu;
+    for (uint32_t a = 0; a < gn; ++a) {
+        const uint32_t s = us_index(grp[a]);
+        if (rec[s].len < min_len) min_len = rec[s].len;
+        if (rec[s].flags) pristine = false;
+        for (uint32_t b = 0; b < a; ++b) if (s == us_index(grp[b])) dup = true;
+    }
+    const size_t common_len = pristine ? spec_len[ci] : common_length(cand);
+    size_t c = common_len;
+    // avoid_zero_len_unitigs (:141-158) and avoid_start_of_path (:161-181) trim the common piece on the far side
+    if (c > 0) c = std::min<size_t>(c, (min_len - 1) / (dup ? 2 : 1));
+    const uint32_t min_pos = cand.side == 0 ? rec[idx].min_fpos : rec[idx].min_rpos;
+    if (c > 0) c = min_pos == 0 ? 0 : std::min<size_t>(c, min_pos - 1);
+    if (c == 0) return 0;
+
+    common.resize(c);
+    {
+        const uint32_t u0 = us_index(grp[0]); const unsigned char* p0 = (const unsigned char*)seq_ptr(u0);
+        const bool at_back = (cand.side == 0) != us_reverse(grp[0]);
+        const Cursor first{at_back ? p0 + rec[u0].len - 1 : p0, at_back ? -1 : 1, us_reverse(grp[0]) ? g_lut.comp : g_lut.same};
+        if (cand.side == 0) for (size_t i = 0; i < c; ++i) common[c - 1 - i] = (char)first.at(i);
+        else for (size_t i = 0; i < c; ++i) common[i] = (char)first.at(i);
+    }
+    if (cand.side == 0) {   // shift_sequence_1 (:89-116): common end of the inputs moves to the start of this unitig
+        for (uint32_t a = 0; a < gn; ++a) {
+            const uint32_t s = us_index(grp[a]);
+            if (!us_reverse(grp[a])) { rec[s].min_rpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].room_after += (uint32_t)c; }                 // remove_seq_from_end, unitig.rs:225-232
+            else { rec[s].min_fpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].seq_off += c; rec[s].room_before += (uint32_t)c; }                // remove_seq_from_start, unitig.rs:216-223
+        }
+        grow_front(idx, (uint32_t)c);                                                                                                    // add_seq_to_start, unitig.rs:234-240
+        rec[idx].seq_off -= c; rec[idx].room_before -= (uint32_t)c; rec[idx].len += (uint32_t)c; rec[idx].min_fpos -= (uint32_t)c;
+        memcpy(arena + rec[idx].seq_off, common.data(), c);
+    } else {                // shift_sequence_2 (:119-138): common start of the outputs moves to the end of this unitig
+        for (uint32_t a = 0; a < gn; ++a) {
+            const uint32_t s = us_index(grp[a]);
+            if (!us_reverse(grp[a])) { rec[s].min_fpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].seq_off += c; rec[s].room_before += (uint32_t)c; }
+            else { rec[s].min_rpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].room_after += (uint32_t)c; }
+        }
+        grow_back(idx, (uint32_t)c);                                                                                                     // add_seq_to_end, unitig.rs:242-248
+        memcpy(arena + rec[idx].seq_off + rec[idx].len, common.data(), c);
+        rec[idx].room_after -= (uint32_t)c; rec[idx].len += (uint32_t)c; rec[idx].min_rpos -= (uint32_t)c;
+    }
+    // In the first pass every candidate after this one is still marked; only those already visited need the mark.
+    const int64_t below = first_pass ? (int64_t)ci : (int64_t)1 << 40;
+    rec[idx].flags = 1; mark_dependents(idx, shared, below);
+    for (uint32_t a = 0; a < gn; ++a) { rec[us_index(grp[a])].flags = 1; mark_dependents(us_index(grp[a]), shared, below); }
+    // The whole common piece moved: what is left of the sources has no common end/start any more, so this candidate can
+    // only find something again after another shift touches one of its unitigs (which marks it again).  Otherwise
+    // (the piece was capped) it has to be looked at again in the next pass.
+    if (c == common_len) { if (shared) __atomic_fetch_and(&dirty[w], ~bit_mask, __ATOMIC_RELAXED); else dirty[w] &= ~bit_mask; }
+    else { if (shared) __atomic_fetch_or(&dirty[w], bit_mask, __ATOMIC_RELAXED); else dirty[w] |= bit_mask; }
+    return c;
 }
 
 size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
     const double t0 = now_ms();
     if (!cands_ready) { compute_candidates(); prof.seqs = now_ms() - t0; }
+    size_t total_shifted = 0;
     if (first_pass) {   // every candidate is evaluated in the first pass; do the byte comparisons for all of them in parallel
         spec_len.resize(cands.size());
         const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads() * 4, cands.size() / 1024));
@@ -306,87 +379,37 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
         });
         prof.check = now_ms() - t0;
     }
-    size_t total_shifted = 0;
-    std::string common;
-    for (size_t w = 0; w < dirty.size(); ++w) {
-        uint64_t passed = 0;                       // candidates of this word already visited in this pass
-        for (;;) {
-            // a candidate marked again at or behind the current position waits for the next pass, exactly as the
-            // reference's loop would only reach it again in its next call
-            const uint64_t avail = dirty[w] & ~passed;
-            if (!avail) break;
-            const int bit = __builtin_ctzll(avail);
-            passed = bit == 63 ? ~0ull : ((2ull << bit) - 1);
-            dirty[w] &= ~(1ull << bit);
-            const size_t ci = w * 64 + (size_t)bit;
-            const Candidate cand = cands[ci];
-            const uint32_t idx = cand.idx;
-            const UStrand* grp = cand.src; const uint32_t gn = cand.gn;
-            if (first_pass) {   // the first pass walks the list in order: pull the next candidates' records and sequence ends into cache
-                if (ci + 16 < cands.size()) {
-                    const Candidate& f = cands[ci + 16];
-                    __builtin_prefetch(&rec[f.idx]); __builtin_prefetch(&deps[f.idx]);
-                    for (uint32_t a = 0; a < f.gn; ++a) { __builtin_prefetch(&rec[us_index(f.src[a])]); __builtin_prefetch(&deps[us_index(f.src[a])]); }
-                }
-                if (ci + 6 < cands.size()) {
-                    const Candidate& f = cands[ci + 6];
-                    __builtin_prefetch(arena + rec[f.idx].seq_off - (f.side == 0 ? 32 : 0) + (f.side == 0 ? 0 : rec[f.idx].len));
-                    for (uint32_t a = 0; a < f.gn; ++a) {
-                        const UnitigRec& r = rec[us_index(f.src[a])];
-                        const bool at_back = (f.side == 0) != us_reverse(f.src[a]);
-                        __builtin_prefetch(arena + r.seq_off + (at_back ? (r.len > 32 ? r.len - 32 : 0) : 0));
+    {
+        std::string common;
+        for (size_t w = 0; w < dirty.size(); ++w) {
+            uint64_t passed = 0;                       // candidates of this word already visited in this pass
+            for (;;) {
+                // a candidate marked again at or behind the current position waits for the next pass, exactly as the
+                // reference's loop would only reach it again in its next call
+                const uint64_t avail = dirty[w] & ~passed;
+                if (!avail) break;
+                const int bit = __builtin_ctzll(avail);
+                passed = bit == 63 ? ~0ull : ((2ull << bit) - 1);
+                dirty[w] &= ~(1ull << bit);
+                const size_t ci = w * 64 + (size_t)bit;
+                if (first_pass) {   // the first pass walks the list in order: pull the next candidates' records and sequence ends into cache
+                    if (ci + 16 < cands.size()) {
+                        const Candidate& f = cands[ci + 16];
+                        __builtin_prefetch(&rec[f.idx]); __builtin_prefetch(&deps[f.idx]);
+                        for (uint32_t a = 0; a < f.gn; ++a) { __builtin_prefetch(&rec[us_index(f.src[a])]); __builtin_prefetch(&deps[us_index(f.src[a])]); }
+                    }
+                    if (ci + 6 < cands.size()) {
+                        const Candidate& f = cands[ci + 6];
+                        __builtin_prefetch(arena + rec[f.idx].seq_off - (f.side == 0 ? 32 : 0) + (f.side == 0 ? 0 : rec[f.idx].len));
+                        for (uint32_t a = 0; a < f.gn; ++a) {
+                            const UnitigRec& r = rec[us_index(f.src[a])];
+                            const bool at_back = (f.side == 0) != us_reverse(f.src[a]);
+                            __builtin_prefetch(arena + r.seq_off + (at_back ? (r.len > 32 ? r.len - 32 : 0) : 0));
+                        }
                     }
                 }
+                total_shifted += apply_candidate(ci, false, common);
             }
-
-            bool dup = false, pristine = first_pass; uint32_t min_len = 0xFFFFFFFFu;
-            for (uint32_t a = 0; a < gn; ++a) {
-                const uint32_t s = us_index(grp[a]);
-                if (rec[s].len < min_len) min_len = rec[s].len;
-                if (rec[s].flags) pristine = false;
-                for (uint32_t b = 0; b < a; ++b) if (s == us_index(grp[b])) dup = true;
-            }
-            const size_t common_len = pristine ? spec_len[ci] : common_length(cand);
-            size_t c = common_len;
-            // avoid_zero_len_unitigs (:141-158) and avoid_start_of_path (:161-181) trim the common piece on the far side
-            if (c > 0) c = std::min<size_t>(c, (min_len - 1) / (dup ? 2 : 1));
-            const uint32_t min_pos = cand.side == 0 ? rec[idx].min_fpos : rec[idx].min_rpos;
-            if (c > 0) c = min_pos == 0 ? 0 : std::min<size_t>(c, min_pos - 1);
-            if (c == 0) continue;
-
-            common.resize(c);
-            {
-                const uint32_t u0 = us_index(grp[0]); const unsigned char* p0 = (const unsigned char*)seq_ptr(u0);
-                const bool at_back = (cand.side == 0) != us_reverse(grp[0]);
-                const Cursor first{at_back ? p0 + rec[u0].len - 1 : p0, at_back ? -1 : 1, us_reverse(grp[0]) ? g_lut.comp : g_lut.same};
-                if (cand.side == 0) for (size_t i = 0; i < c; ++i) common[c - 1 - i] = (char)first.at(i);
-                else for (size_t i = 0; i < c; ++i) common[i] = (char)first.at(i);
-            }
-            if (cand.side == 0) {   // shift_sequence_1 (:89-116): common end of the inputs moves to the start of this unitig
-                for (uint32_t a = 0; a < gn; ++a) {
-                    const uint32_t s = us_index(grp[a]);
-                    if (!us_reverse(grp[a])) { rec[s].min_rpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].room_after += (uint32_t)c; }                 // remove_seq_from_end, unitig.rs:225-232
-                    else { rec[s].min_fpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].seq_off += c; rec[s].room_before += (uint32_t)c; }                // remove_seq_from_start, unitig.rs:216-223
-                }
-                grow_front(idx, (uint32_t)c);                                                                                                    // add_seq_to_start, unitig.rs:234-240
-                rec[idx].seq_off -= c; rec[idx].room_before -= (uint32_t)c; rec[idx].len += (uint32_t)c; rec[idx].min_fpos -= (uint32_t)c;
-                memcpy(arena + rec[idx].seq_off, common.data(), c);
-            } else {                // shift_sequence_2 (:119-138): common start of the outputs moves to the end of this unitig
-                for (uint32_t a = 0; a < gn; ++a) {
-                    const uint32_t s = us_index(grp[a]);
-                    if (!us_reverse(grp[a])) { rec[s].min_fpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].seq_off += c; rec[s].room_before += (uint32_t)c; }
-                    else { rec[s].min_rpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].room_after += (uint32_t)c; }
-                }
-                grow_back(idx, (uint32_t)c);                                                                                                     // add_seq_to_end, unitig.rs:242-248
-                memcpy(arena + rec[idx].seq_off + rec[idx].len, common.data(), c);
-                rec[idx].room_after -= (uint32_t)c; rec[idx].len += (uint32_t)c; rec[idx].min_rpos -= (uint32_t)c;
-            }
-            total_shifted += c;
-            rec[idx].flags = 1; mark_dependents(idx);
-            for (uint32_t a = 0; a < gn; ++a) { rec[us_index(grp[a])].flags = 1; mark_dependents(us_index(grp[a])); }
-            // The whole common piece moved: what is left of the sources has no common end/start any more, so this candidate
-            // can only find something again after another shift touches one of its unitigs (which marks it again).
-            if (c == common_len) dirty[w] &= ~(1ull << bit);
         }
     }
     first_pass = false;

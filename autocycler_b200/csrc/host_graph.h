@@ -80,7 +80,9 @@ private:
     struct Deps { int32_t c[6]; };            // candidates that read unitig u: its own two, and those it exclusively feeds / is fed by
     std::vector<Deps> deps;
     void compute_dependents();
-    void mark_dependents(uint32_t u);
+    void mark_dependents(uint32_t u, bool shared, int64_t below);
+    size_t apply_candidate(size_t ci, bool shared, std::string& common);
+    void reserve_arena(uint64_t extra);
     void grow_front(uint32_t idx, uint32_t need);
     void grow_back(uint32_t idx, uint32_t need);
     void relocate(uint32_t idx, uint32_t before, uint32_t after);

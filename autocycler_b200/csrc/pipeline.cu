@@ -12,6 +12,7 @@
 #include "pipeline.h"
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #ifndef AC_EMULATE
@@ -125,16 +126,19 @@ struct InitSlotsBody {
 template <int W> struct InsertBody {
     TableView t; KParams p; uint64_t g_begin, g_end;   // coordinates of the sequences this rank owns
     bool track_min;                     // multi-GPU: the entry must end up pointing at the SMALLEST occurrence (a rank-independent name for the k-mer)
-    uint32_t* pos_slot;                 // [total] slot of the window starting at each global coordinate
-    unsigned long long* counters;       // [2*stripe] slots claimed, [2*stripe+1] dotted k-mers claimed
+    uint32_t* pos_slot;                 // [total] slot of the window starting at each global coordinate (null in the sampling pass)
+    unsigned long long* counters;       // [2*stripe] slots claimed, [2*stripe+1] dotted k-mers claimed, [2*AC_STRIPES] table-overflow flag
+    uint64_t sample_mask;               // != 0: the sizing pre-pass, only k-mers whose hash has these bits clear are entered
     AC_D void insert(const Key<W>& fwd, const Key<W>& rc, uint64_t g, uint64_t fs, uint32_t len, uint32_t obs, uint32_t& claimed, uint32_t& claimed_dotted) const {
         const bool canon_fwd = key_is_canonical(fwd, p);
         const Key<W>& canon = canon_fwd ? fwd : rc;
         const uint64_t h = key_hash(canon);
+        if (h & sample_mask) return;
         const bool dotted = fwd.d != 0;
         const uint64_t mine = make_entry(g, dotted, h);
         uint64_t slot = ac_umul64hi(h, t.cap);
-        for (;;) {
+        for (uint32_t probes = 0;; ++probes) {
+            if (probes > 8192) { counters[2 * AC_STRIPES] = 1; return; }    // the table was sized too small: the host retries with the safe size
             uint64_t e = ac_ld_volatile(&t.slots[slot].entry);
             if (e == AC_EMPTY_ENTRY) {
                 e = ac_atomic_cas(&t.slots[slot].entry, (uint64_t)AC_EMPTY_ENTRY, mine);
@@ -156,7 +160,7 @@ template <int W> struct InsertBody {
         if (fs == 0) bits |= canon_fwd ? AC_AUX_FIRST_CANON : AC_AUX_FIRST_RC;
         if (fs + 1 == len) bits |= canon_fwd ? AC_AUX_FIRST_RC : AC_AUX_FIRST_CANON;
         if (bits && (ac_ld_volatile(&t.slots[slot].aux) & bits) != bits) ac_atomic_or(&t.slots[slot].aux, bits);   // usually already there
-        pos_slot[g] = (uint32_t)slot;
+        if (pos_slot) pos_slot[g] = (uint32_t)slot;
     }
     AC_D void operator()(uint64_t i) const {
         uint64_t g = g_begin + i * AC_CHUNK;
@@ -433,7 +437,8 @@ template <int W> struct MergeBody {
         const uint64_t h = key_hash(key_is_canonical(fwd, p) ? fwd : rc);
         const uint64_t mine = make_entry(g, dotted, h);
         uint64_t slot = ac_umul64hi(h, t.cap);
-        for (;;) {
+        for (uint32_t probes = 0;; ++probes) {
+            if (probes > 8192) { counters[2 * AC_STRIPES] = 1; return; }
             uint64_t e = ac_ld_volatile(&t.slots[slot].entry);
             if (e == AC_EMPTY_ENTRY) {
                 e = ac_atomic_cas(&t.slots[slot].entry, (uint64_t)AC_EMPTY_ENTRY, mine);
@@ -961,14 +966,44 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
     ac_launch("pack", &stream, PackBody{ascii.as<uint8_t>(), total, packed.as<uint64_t>()}, n_words);
     mark(3);
 
-    slots.ensure(cap * sizeof(Slot));
-    ac_launch("init_slots", &stream, InitSlotsBody{slots.as<Slot>()}, cap);
+    // ---- size the table: distinct canonical k-mers estimated from the 1/64 of them whose hash ends in six zero bits ----
+    // (sampling by hash value keeps or drops a k-mer with ALL its occurrences, so 64 x the sample's distinct count is an
+    // unbiased estimate; every rank samples every sequence because after the exchange its table holds all of them.)
+    const uint64_t safe_cap = cap;
+    const size_t counter_words = 2 * AC_STRIPES + 2;
+    counters.ensure(counter_words * sizeof(unsigned long long));
+    const double load = getenv("AC_TABLE_LOAD") ? atof(getenv("AC_TABLE_LOAD")) : 0.45;
+    if (load > 0 && n_windows > (1u << 16)) {
+        const uint64_t sample_cap = n_windows / 64 * 2 + 4096;
+        slots.ensure(sample_cap * sizeof(Slot));
+        ac_launch("init_slots", &stream, InitSlotsBody{slots.as<Slot>()}, sample_cap);
+        ac_memset(counters.p, 0, counter_words * sizeof(unsigned long long), &stream);
+        const TableView sv{slots.as<Slot>(), sample_cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
+        ac_launch("sample", &stream, InsertBody<W>{sv, p, 0, total, false, nullptr, counters.as<unsigned long long>(), 63}, (total + AC_CHUNK - 1) / AC_CHUNK);
+        std::vector<unsigned long long> hc(counter_words);
+        ac_d2h(hc.data(), counters.p, hc.size() * sizeof(unsigned long long), &stream); ac_sync(&stream);
+        unsigned long long sampled = 0; for (int x = 0; x < AC_STRIPES; ++x) sampled += hc[2 * x];
+        if (!hc[2 * AC_STRIPES]) {
+            const uint64_t est = (sampled + 3 * (uint64_t)std::sqrt((double)sampled) + 16) * 64;      // + 3 sigma
+            cap = std::min<uint64_t>(safe_cap, (uint64_t)((double)est / load) + 4096);
+        }
+    }
+    mark(15);
+
     pos_slot.ensure(total * sizeof(uint32_t));
-    counters.ensure(2 * AC_STRIPES * sizeof(unsigned long long));
-    ac_memset(counters.p, 0, 2 * AC_STRIPES * sizeof(unsigned long long), &stream);
-    const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
-    ac_launch("insert", &stream, InsertBody<W>{tv, p, g_begin, g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>()},
-              (g_end - g_begin + AC_CHUNK - 1) / AC_CHUNK);
+    for (int attempt = 0;; ++attempt) {
+        slots.ensure(cap * sizeof(Slot));
+        ac_launch("init_slots", &stream, InitSlotsBody{slots.as<Slot>()}, cap);
+        ac_memset(counters.p, 0, counter_words * sizeof(unsigned long long), &stream);
+        const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
+        ac_launch("insert", &stream, InsertBody<W>{tv, p, g_begin, g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), 0},
+                  (g_end - g_begin + AC_CHUNK - 1) / AC_CHUNK);
+        if (cap == safe_cap) break;                      // cannot overflow: one slot and a half per window
+        unsigned long long overflow = 0;
+        ac_d2h(&overflow, counters.as<unsigned long long>() + 2 * AC_STRIPES, sizeof overflow, &stream); ac_sync(&stream);
+        if (!overflow) break;
+        cap = safe_cap;                                  // the estimate was off (it is an estimate): start again with the safe size
+    }
     mark(4);
     stage = 1;
 }
@@ -999,8 +1034,9 @@ template <int W> void DevicePipeline::Impl::runs_local_w() {
     const KParams p = make_kparams(k, W);
     const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
     mark(13);
-    std::vector<unsigned long long> hc(2 * AC_STRIPES);
+    std::vector<unsigned long long> hc(2 * AC_STRIPES + 2);
     ac_d2h(hc.data(), counters.p, hc.size() * sizeof(unsigned long long), &stream); ac_sync(&stream);
+    if (hc[2 * AC_STRIPES]) throw std::runtime_error("k-mer table overflow while merging");
     n_slots_used = 0; n_dotted = 0;
     for (int x = 0; x < AC_STRIPES; ++x) { n_slots_used += hc[2 * x]; n_dotted += hc[2 * x + 1]; }
     any_dotted = n_dotted != 0;
@@ -1162,7 +1198,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     out.next_off = h_next_off.as<uint32_t>(); out.next = h_next.as<UStrand>(); out.prev_off = h_prev_off.as<uint32_t>(); out.prev = h_prev.as<UStrand>();
     out.path_off = h_path_off.as<uint64_t>(); out.path = h_path.as<UStrand>();
     out.run_start = keep_positions ? h_run_start.as<uint64_t>() : nullptr; out.run_len = keep_positions ? h_run_len.as<uint32_t>() : nullptr;
-    out.t.h2d = between(0, 1); out.t.pack = between(2, 3); out.t.insert = between(3, 4); out.t.adjacency = between(13, 5);
+    out.t.h2d = between(0, 1); out.t.pack = between(2, 3); out.t.insert = between(15, 4); out.t.sample = between(3, 15); out.t.adjacency = between(13, 5);
     out.t.boundaries = between(5, 6); out.t.runs = between(14, 7); out.t.unitigs = between(7, 8); out.t.links = between(8, 9);
     out.t.seed_sort = between(9, 10); out.t.emit = between(10, 11); out.t.d2h = between(11, 12); out.t.total = between(2, 4) + between(13, 6) + between(14, 12);
 }
