@@ -26,6 +26,7 @@ template <class T> inline T ac_atomic_or(T* p, T v) { T old = *p; *p = (T)(old |
 template <class T> inline T ac_atomic_min(T* p, T v) { T old = *p; if (v < old) *p = v; return old; }
 template <class T> inline T ac_atomic_max(T* p, T v) { T old = *p; if (v > old) *p = v; return old; }
 template <class T> inline T ac_ld_volatile(const T* p) { return *p; }
+template <class T> inline T ac_ld_16(const T* p) { return *p; }   // one 16-byte load of a 16-byte record
 inline uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 inline uint32_t ac_popc(uint32_t v) { return (uint32_t)__builtin_popcount(v); }
 
@@ -72,6 +73,10 @@ AC_D uint32_t ac_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 AC_D uint32_t ac_atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
 AC_D uint64_t ac_atomic_min(uint64_t* p, uint64_t v) { return (uint64_t)atomicMin((unsigned long long*)p, (unsigned long long)v); }
 template <class T> AC_D T ac_ld_volatile(const T* p) { return *(const volatile T*)p; }
+template <class T> AC_D T ac_ld_16(const T* p) {   // one 16-byte L2 (cache-global) load of a 16-byte record: sees other threads' atomics
+    static_assert(sizeof(T) == 16, "16-byte records only");
+    const uint4 q = __ldcg(reinterpret_cast<const uint4*>(p)); T r; memcpy(&r, &q, 16); return r;
+}
 AC_D uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 AC_D uint32_t ac_popc(uint32_t v) { return (uint32_t)__popc(v); }
 AC_D uint64_t ac_atomic_or(uint64_t* p, uint64_t v) { return (uint64_t)atomicOr((unsigned long long*)p, (unsigned long long)v); }

@@ -242,8 +242,7 @@ void HostGraph::compute_candidates() {
     cand_at.assign(2 * (size_t)U, -1);
     for (size_t i = 0; i < cands.size(); ++i) cand_at[2 * (size_t)cands[i].idx + cands[i].side] = (int32_t)i;
     compute_dependents();
-    dirty.assign((cands.size() + 63) / 64, ~0ull);
-    if (cands.size() % 64) dirty.back() = (1ull << (cands.size() % 64)) - 1;
+    dirty.assign((cands.size() + 63) / 64, 0);     // the first pass visits every candidate; the bitmap collects work for later passes
     for (uint32_t u = 0; u < U; ++u) rec[u].flags = 0;
     first_pass = true;
     cands_ready = true;
@@ -362,15 +361,84 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
     // The whole common piece moved: what is left of the sources has no common end/start any more, so this candidate can
     // only find something again after another shift touches one of its unitigs (which marks it again).  Otherwise
     // (the piece was capped) it has to be looked at again in the next pass.
-    if (c == common_len) { if (shared) __atomic_fetch_and(&dirty[w], ~bit_mask, __ATOMIC_RELAXED); else dirty[w] &= ~bit_mask; }
-    else { if (shared) __atomic_fetch_or(&dirty[w], bit_mask, __ATOMIC_RELAXED); else dirty[w] |= bit_mask; }
+    if (c != common_len) { if (shared) __atomic_fetch_or(&dirty[w], bit_mask, __ATOMIC_RELAXED); else dirty[w] |= bit_mask; }
+    else if (!first_pass) dirty[w] &= ~bit_mask;      // (later passes are sequential; in the first pass nobody can have marked it yet)
     return c;
+}
+
+// First pass, in parallel.  Two candidates conflict when they share a unitig (destination or source); the reference's
+// result only depends on the relative order of conflicting candidates.  Candidates are therefore levelled
+// (level = 1 + the highest level among earlier conflicting candidates), and every level is applied by all threads at
+// once: within a level no two candidates touch the same unitig.  The only shared writes are the rare marks for the
+// next pass (atomic) and arena bumps (atomic; the worst case is reserved up front so the arena never moves).
+size_t HostGraph::first_pass_parallel() {
+    const size_t n = cands.size();
+    std::vector<uint32_t> level_of_unitig(U, 0), level(n);
+    uint32_t n_levels = 0;
+    uint64_t reloc_bound = 0;
+    for (size_t ci = 0; ci < n; ++ci) {
+        const Candidate& cd = cands[ci];
+        uint32_t lv = level_of_unitig[cd.idx];
+        for (uint32_t a = 0; a < cd.gn; ++a) lv = std::max(lv, level_of_unitig[us_index(cd.src[a])]);
+        ++lv;
+        level_of_unitig[cd.idx] = lv;
+        for (uint32_t a = 0; a < cd.gn; ++a) level_of_unitig[us_index(cd.src[a])] = lv;
+        level[ci] = lv;
+        if (lv > n_levels) n_levels = lv;
+        if (spec_len[ci] + 64 > AC_SEQ_SLACK) reloc_bound += (uint64_t)rec[cd.idx].len + 2ull * spec_len[ci] + 8 * AC_SEQ_SLACK + 64;   // it may have to move
+    }
+    if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[host] expand levels %u for %zu candidates\n", n_levels, n);
+    if (n_levels > 1024) return (size_t)-1;                   // a long dependency chain: not worth the barriers
+    reserve_arena(reloc_bound);                               // no reallocation while several threads hold pointers into the arena
+    std::vector<uint32_t> start(n_levels + 2, 0), by_level(n);
+    for (size_t ci = 0; ci < n; ++ci) start[level[ci] + 1] += 1;
+    for (uint32_t l = 1; l <= n_levels + 1; ++l) start[l] += start[l - 1];
+    { std::vector<uint32_t> cur(start.begin(), start.end() - 1); for (size_t ci = 0; ci < n; ++ci) by_level[cur[level[ci]]++] = (uint32_t)ci; }
+
+    const unsigned T = std::min<unsigned>(host_threads(), 16);
+    std::vector<std::atomic<uint32_t>> next(n_levels + 2);
+    for (auto& x : next) x.store(0);
+    std::atomic<uint32_t> arrived{0}; std::atomic<uint32_t> generation{0};
+    std::atomic<uint64_t> total{0};
+    std::exception_ptr err = nullptr; std::atomic<bool> failed{false};
+    const uint32_t CHUNK = 128;
+    auto work = [&]() {
+        std::string common; uint64_t mine = 0;
+        for (uint32_t l = 1; l <= n_levels; ++l) {
+            const uint32_t lo = start[l], hi = start[l + 1];
+            try {
+                for (uint32_t c0; (c0 = next[l].fetch_add(CHUNK)) < hi - lo;) {
+                    const uint32_t c1 = std::min(hi - lo, c0 + CHUNK);
+                    for (uint32_t x = c0; x < c1; ++x) {
+                        if (x + 8 < c1) {
+                            const Candidate& f = cands[by_level[lo + x + 8]];
+                            __builtin_prefetch(&rec[f.idx]); __builtin_prefetch(&deps[f.idx]);
+                            for (uint32_t a = 0; a < f.gn; ++a) { __builtin_prefetch(&rec[us_index(f.src[a])]); __builtin_prefetch(&deps[us_index(f.src[a])]); }
+                        }
+                        mine += apply_candidate(by_level[lo + x], true, common);
+                    }
+                }
+            } catch (...) { if (!failed.exchange(true)) err = std::current_exception(); }
+            // barrier: nobody starts level l+1 before level l is complete
+            const uint32_t gen = generation.load(std::memory_order_acquire);
+            if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == T) { arrived.store(0, std::memory_order_relaxed); generation.store(gen + 1, std::memory_order_release); }
+            else while (generation.load(std::memory_order_acquire) == gen) { __builtin_ia32_pause(); }
+        }
+        total.fetch_add(mine);
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < T; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    if (err) std::rethrow_exception(err);
+    return (size_t)total.load();
 }
 
 size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
     const double t0 = now_ms();
     if (!cands_ready) { compute_candidates(); prof.seqs = now_ms() - t0; }
     size_t total_shifted = 0;
+    std::string common;
     if (first_pass) {   // every candidate is evaluated in the first pass; do the byte comparisons for all of them in parallel
         spec_len.resize(cands.size());
         const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads() * 4, cands.size() / 1024));
@@ -378,9 +446,18 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
             for (size_t i = cands.size() * t / T; i < cands.size() * (t + 1) / T; ++i) spec_len[i] = common_length(cands[i]);
         });
         prof.check = now_ms() - t0;
-    }
-    {
-        std::string common;
+        size_t r = (size_t)-1;
+        if (cands.size() >= 8192 && host_threads() > 1 && getenv("AC_EXPAND_PARALLEL")) r = first_pass_parallel();   // opt-in: see DESIGN.md §5 (measured slower than the sequential pass on the 2-socket bench host)
+        if (r != (size_t)-1) total_shifted = r;
+        else for (size_t ci = 0; ci < cands.size(); ++ci) {
+            if (ci + 16 < cands.size()) {   // pull the next candidates' records into cache
+                const Candidate& f = cands[ci + 16];
+                __builtin_prefetch(&rec[f.idx]); __builtin_prefetch(&deps[f.idx]);
+                for (uint32_t a = 0; a < f.gn; ++a) { __builtin_prefetch(&rec[us_index(f.src[a])]); __builtin_prefetch(&deps[us_index(f.src[a])]); }
+            }
+            total_shifted += apply_candidate(ci, false, common);
+        }
+    } else {
         for (size_t w = 0; w < dirty.size(); ++w) {
             uint64_t passed = 0;                       // candidates of this word already visited in this pass
             for (;;) {
@@ -391,24 +468,7 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
                 const int bit = __builtin_ctzll(avail);
                 passed = bit == 63 ? ~0ull : ((2ull << bit) - 1);
                 dirty[w] &= ~(1ull << bit);
-                const size_t ci = w * 64 + (size_t)bit;
-                if (first_pass) {   // the first pass walks the list in order: pull the next candidates' records and sequence ends into cache
-                    if (ci + 16 < cands.size()) {
-                        const Candidate& f = cands[ci + 16];
-                        __builtin_prefetch(&rec[f.idx]); __builtin_prefetch(&deps[f.idx]);
-                        for (uint32_t a = 0; a < f.gn; ++a) { __builtin_prefetch(&rec[us_index(f.src[a])]); __builtin_prefetch(&deps[us_index(f.src[a])]); }
-                    }
-                    if (ci + 6 < cands.size()) {
-                        const Candidate& f = cands[ci + 6];
-                        __builtin_prefetch(arena + rec[f.idx].seq_off - (f.side == 0 ? 32 : 0) + (f.side == 0 ? 0 : rec[f.idx].len));
-                        for (uint32_t a = 0; a < f.gn; ++a) {
-                            const UnitigRec& r = rec[us_index(f.src[a])];
-                            const bool at_back = (f.side == 0) != us_reverse(f.src[a]);
-                            __builtin_prefetch(arena + r.seq_off + (at_back ? (r.len > 32 ? r.len - 32 : 0) : 0));
-                        }
-                    }
-                }
-                total_shifted += apply_candidate(ci, false, common);
+                total_shifted += apply_candidate(w * 64 + (size_t)bit, false, common);
             }
         }
     }

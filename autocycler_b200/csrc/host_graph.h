@@ -82,6 +82,7 @@ private:
     void compute_dependents();
     void mark_dependents(uint32_t u, bool shared, int64_t below);
     size_t apply_candidate(size_t ci, bool shared, std::string& common);
+    size_t first_pass_parallel();
     void reserve_arena(uint64_t extra);
     void grow_front(uint32_t idx, uint32_t need);
     void grow_back(uint32_t idx, uint32_t need);

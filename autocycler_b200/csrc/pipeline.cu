@@ -137,9 +137,11 @@ template <int W> struct InsertBody {
         const bool dotted = fwd.d != 0;
         const uint64_t mine = make_entry(g, dotted, h);
         uint64_t slot = ac_umul64hi(h, t.cap);
+        uint32_t aux_seen = 0;
         for (uint32_t probes = 0;; ++probes) {
             if (probes > 8192) { counters[2 * AC_STRIPES] = 1; return; }    // the table was sized too small: the host retries with the safe size
-            uint64_t e = ac_ld_volatile(&t.slots[slot].entry);
+            const Slot q = ac_ld_16(&t.slots[slot]);      // entry, count and flags in one transaction
+            uint64_t e = q.entry; aux_seen = q.aux;
             if (e == AC_EMPTY_ENTRY) {
                 e = ac_atomic_cas(&t.slots[slot].entry, (uint64_t)AC_EMPTY_ENTRY, mine);
                 if (e == AC_EMPTY_ENTRY) { ++claimed; if (dotted) ++claimed_dotted; break; }
@@ -159,7 +161,7 @@ template <int W> struct InsertBody {
         uint32_t bits = obs;
         if (fs == 0) bits |= canon_fwd ? AC_AUX_FIRST_CANON : AC_AUX_FIRST_RC;
         if (fs + 1 == len) bits |= canon_fwd ? AC_AUX_FIRST_RC : AC_AUX_FIRST_CANON;
-        if (bits && (ac_ld_volatile(&t.slots[slot].aux) & bits) != bits) ac_atomic_or(&t.slots[slot].aux, bits);   // usually already there
+        if (bits && (aux_seen & bits) != bits) ac_atomic_or(&t.slots[slot].aux, bits);   // usually already there (aux_seen may be stale: then the OR is merely redundant)
         if (pos_slot) pos_slot[g] = (uint32_t)slot;
     }
     AC_D void operator()(uint64_t i) const {

@@ -25,7 +25,12 @@ sys.path.insert(0, ROOT)
 
 METRIC = "input-assembly Mbp/sec through compress->unitig GFA"
 K = 51
-WORKLOAD = "cfg2: 8 synthetic E. coli-sized (4.64 Mbp) assemblies, k=51"
+WORKLOADS = {   # BASELINE.json configs (SURVEY.md §8d generator); the default is the config the metric is quoted on
+    "cfg2": "cfg2: 8 synthetic E. coli-sized (4.64 Mbp) assemblies",
+    "cfg3": "cfg3: 12 synthetic K. pneumoniae-sized assemblies (5.5 Mbp chromosome + 5 plasmids)",
+    "cfg4": "cfg4: 24 synthetic 10 Mbp assemblies",
+}
+WORKLOAD = WORKLOADS["cfg2"] + ", k=51"
 
 
 def measured_peak():
@@ -92,7 +97,11 @@ def run_gpu(args):
     from autocycler_b200 import dist as acdist
     # Weak scaling: 8 assemblies of the cfg2 genome per rank (N=1 is exactly cfg2; N=8 is 64 assemblies, the shape of cfg5).
     # Every rank stages all sequences (end repair needs all of them anyway) and owns a contiguous block.
-    assemblies = synth.make_assemblies("cfg2", n_assemblies=8 * world)
+    global K, WORKLOAD
+    K = args.k
+    per_rank = synth.CONFIGS[args.workload][2]
+    WORKLOAD = f"{WORKLOADS[args.workload]}, k={K}"
+    assemblies = synth.make_assemblies(args.workload, n_assemblies=per_rank * world)
     n_bases = synth.total_bases(assemblies)
     stream = torch.cuda.current_stream()
     # stage A once, untimed: product loader + end repair, then a handle bound to torch's current stream
@@ -107,7 +116,7 @@ def run_gpu(args):
         first_of.setdefault(sq.filename, i)
     files = sorted(first_of, key=first_of.get)
     bounds = [first_of[f] for f in files] + [len(seqs)]
-    seq_lo, seq_hi = bounds[8 * rank], bounds[8 * (rank + 1)]
+    seq_lo, seq_hi = bounds[per_rank * rank], bounds[per_rank * (rank + 1)]
 
     def step(upload):
         if upload:
@@ -174,7 +183,7 @@ def run_gpu(args):
         "metric": METRIC, "value": round(value, 3), "unit": "Mbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic (splitmix64 genomes, SURVEY.md §8d)",
-        "config": {"workload": WORKLOAD if world == 1 else f"{8 * world} synthetic 4.64 Mbp assemblies (cfg2 genome), 8 per rank, k=51", "k": K, "input_bases": n_bases, "sequences": len(seqs),
+        "config": {"workload": WORKLOAD if world == 1 else f"{per_rank * world} assemblies of the {args.workload} genome, {per_rank} per rank, k={K}", "k": K, "input_bases": n_bases, "sequences": len(seqs),
                    "exchange": None if world == 1 else "all-gather of deduplicated k-mer entries (16 B each) over NCCL, then gather of unitig occurrences to rank 0",
                    "l2": "working set per step (table %.0f MB + per-position arrays) exceeds the 126 MB L2 and is re-initialised every step" % (t.table_capacity * 16 / 1e6),
                    "gfa_bytes": len(gfa), "unitigs": int(g.counts().n_unitigs)},
@@ -253,6 +262,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="BASELINE.json config to run (default: the one the metric is quoted on)")
+    ap.add_argument("--k", type=int, default=51)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

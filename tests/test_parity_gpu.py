@@ -87,6 +87,23 @@ def test_config2_full_size_golden_and_round_trip(lib, tmp_path):
         assert open(os.path.join(rec, fn), "rb").read() == open(os.path.join(d, fn), "rb").read()
 
 
+@pytest.mark.parametrize("name,k", [("cfg3", 51), ("cfg4", 51), ("cfg4", 31), ("cfg4", 91)])
+def test_larger_configs_against_committed_oracle_hashes(lib, tmp_path, name, k):
+    """BASELINE.json configs[2] and configs[3] (k sweep): SHA-256 of the oracle's GFA, generated in the build container by
+    tests/golden/make_config_goldens.py (the oracle needs 3-15 minutes per entry, so only the hash travels)."""
+    goldens = json.load(open(os.path.join(ROOT, "tests", "golden", "config_goldens.json")))
+    key = f"{name}_k{k}"
+    if key not in goldens:
+        pytest.skip(f"no committed oracle hash for {key}")
+    g = goldens[key]
+    d = str(tmp_path / name)
+    synth.write_assemblies(synth.make_assemblies(name), d)
+    got = run_library(lib, d, k)
+    assert got["before"].n_kmers == g["n_kmers"]
+    assert (got["after"].n_unitigs, got["after"].n_links, len(got["gfa"])) == (g["unitigs_after"], g["links_after"], g["gfa_bytes"])
+    assert hashlib.sha256(got["gfa"].encode()).hexdigest() == g["sha256"]
+
+
 def test_handle_reuse_and_determinism(lib, tmp_path):
     """Two builds on one handle and a build on a fresh handle give the same bytes (atomics race for slots, the
     output must not depend on who wins)."""
