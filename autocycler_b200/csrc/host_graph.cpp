@@ -243,6 +243,7 @@ void HostGraph::compute_candidates() {
     for (size_t i = 0; i < cands.size(); ++i) cand_at[2 * (size_t)cands[i].idx + cands[i].side] = (int32_t)i;
     compute_dependents();
     dirty.assign((cands.size() + 63) / 64, 0);     // the first pass visits every candidate; the bitmap collects work for later passes
+    exhausted.assign(cands.size(), 0);
     for (uint32_t u = 0; u < U; ++u) rec[u].flags = 0;
     first_pass = true;
     cands_ready = true;
@@ -295,13 +296,6 @@ void HostGraph::compute_dependents() {
     });
 }
 
-void HostGraph::mark_dependents(uint32_t u, bool shared, int64_t below) {
-    const Deps& d = deps[u];
-    for (int i = 0; i < 6; ++i) if (d.c[i] >= 0 && d.c[i] < below) {
-        const uint64_t m = 1ull << (d.c[i] & 63);
-        if (shared) __atomic_fetch_or(&dirty[(size_t)d.c[i] >> 6], m, __ATOMIC_RELAXED); else dirty[(size_t)d.c[i] >> 6] |= m;
-    }
-}
 
 // One evaluation of candidate ci: graph_simplification.rs:64-84 for one (unitig, side).  Returns the bases moved.
 // `shared` = other threads are applying candidates with disjoint unitig sets at the same time (bitmap and arena bump
@@ -325,6 +319,7 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
     if (c > 0) c = std::min<size_t>(c, (min_len - 1) / (dup ? 2 : 1));
     const uint32_t min_pos = cand.side == 0 ? rec[idx].min_fpos : rec[idx].min_rpos;
     if (c > 0) c = min_pos == 0 ? 0 : std::min<size_t>(c, min_pos - 1);
+    exhausted[ci] = c == common_len;       // nothing (more) in common: only an extension of a compared end can change that
     if (c == 0) return 0;
 
     common.resize(c);
@@ -354,13 +349,31 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
         memcpy(arena + rec[idx].seq_off + rec[idx].len, common.data(), c);
         rec[idx].room_after -= (uint32_t)c; rec[idx].len += (uint32_t)c; rec[idx].min_rpos -= (uint32_t)c;
     }
-    // In the first pass every candidate after this one is still marked; only those already visited need the mark.
+    // Who has to look again?  (In the first pass every candidate after this one is still to come; only those already
+    // visited need a mark.)  deps[u]: c[0]/c[1] read u's min_fpos/min_rpos; c[3],c[4] compare u's first bases, c[2],c[5] its
+    // last bases.  A candidate that has nothing left in common ("exhausted") cannot be revived by a length or position
+    // change, only by new bases at an end it compares (a "hard" mark).
     const int64_t below = first_pass ? (int64_t)ci : (int64_t)1 << 40;
-    rec[idx].flags = 1; mark_dependents(idx, shared, below);
-    for (uint32_t a = 0; a < gn; ++a) { rec[us_index(grp[a])].flags = 1; mark_dependents(us_index(grp[a]), shared, below); }
-    // The whole common piece moved: what is left of the sources has no common end/start any more, so this candidate can
-    // only find something again after another shift touches one of its unitigs (which marks it again).  Otherwise
-    // (the piece was capped) it has to be looked at again in the next pass.
+    auto mark = [&](int32_t cnd, bool hard) {
+        if (cnd < 0 || cnd >= below || (!hard && exhausted[cnd])) return;
+        const uint64_t m = 1ull << (cnd & 63);
+        if (shared) __atomic_fetch_or(&dirty[(size_t)cnd >> 6], m, __ATOMIC_RELAXED); else dirty[(size_t)cnd >> 6] |= m;
+    };
+    rec[idx].flags = 1;
+    {
+        const Deps& dd = deps[idx];      // the destination grew at its start (side 0) or end (side 1); its length changed
+        const bool grew_start = cand.side == 0;
+        mark(dd.c[3], grew_start); mark(dd.c[4], grew_start); mark(dd.c[2], !grew_start); mark(dd.c[5], !grew_start);
+    }
+    for (uint32_t a = 0; a < gn; ++a) {
+        const uint32_t s = us_index(grp[a]);
+        rec[s].flags = 1;
+        const Deps& ds = deps[s];
+        const bool trimmed_end = (cand.side == 0) != us_reverse(grp[a]);     // which physical end of s lost bases (its reader is this candidate)
+        if (trimmed_end) { mark(ds.c[3], false); mark(ds.c[4], false); mark(ds.c[1], false); }   // readers of the other end see a new length; min_rpos moved
+        else { mark(ds.c[2], false); mark(ds.c[5], false); mark(ds.c[0], false); }               // ... min_fpos moved
+    }
+    // A capped shift has to be looked at again in the next pass; after a complete one the bit must be off.
     if (c != common_len) { if (shared) __atomic_fetch_or(&dirty[w], bit_mask, __ATOMIC_RELAXED); else dirty[w] |= bit_mask; }
     else if (!first_pass) dirty[w] &= ~bit_mask;      // (later passes are sequential; in the first pass nobody can have marked it yet)
     return c;
@@ -385,7 +398,7 @@ size_t HostGraph::first_pass_parallel() {
         for (uint32_t a = 0; a < cd.gn; ++a) level_of_unitig[us_index(cd.src[a])] = lv;
         level[ci] = lv;
         if (lv > n_levels) n_levels = lv;
-        if (spec_len[ci] + 64 > AC_SEQ_SLACK) reloc_bound += (uint64_t)rec[cd.idx].len + 2ull * spec_len[ci] + 8 * AC_SEQ_SLACK + 64;   // it may have to move
+        if (spec_len[ci] > AC_SEQ_SLACK) reloc_bound += (uint64_t)rec[cd.idx].len + 2ull * spec_len[ci] + 8 * AC_SEQ_SLACK + 64;   // it may have to move
     }
     if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[host] expand levels %u for %zu candidates\n", n_levels, n);
     if (n_levels > 1024) return (size_t)-1;                   // a long dependency chain: not worth the barriers
@@ -447,7 +460,7 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
         });
         prof.check = now_ms() - t0;
         size_t r = (size_t)-1;
-        if (cands.size() >= 8192 && host_threads() > 1 && getenv("AC_EXPAND_PARALLEL")) r = first_pass_parallel();   // opt-in: see DESIGN.md §5 (measured slower than the sequential pass on the 2-socket bench host)
+        if (cands.size() >= 8192 && host_threads() >= 4 && !getenv("AC_EXPAND_SERIAL")) r = first_pass_parallel();
         if (r != (size_t)-1) total_shifted = r;
         else for (size_t ci = 0; ci < cands.size(); ++ci) {
             if (ci + 16 < cands.size()) {   // pull the next candidates' records into cache

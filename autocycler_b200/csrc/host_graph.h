@@ -73,6 +73,7 @@ private:
     std::vector<Candidate> cands;
     std::vector<int32_t> cand_at;             // [2U] candidate index of (unitig, side), -1 if none
     std::vector<uint64_t> dirty;              // bitmap over cands: must be (re-)evaluated
+    std::vector<uint8_t> exhausted;           // per candidate: its sources had nothing in common after its last evaluation
     std::vector<uint32_t> spec_len;           // common-piece lengths computed in parallel from the untouched graph
     bool cands_ready = false, first_pass = true;
     void compute_candidates();
@@ -80,7 +81,6 @@ private:
     struct Deps { int32_t c[6]; };            // candidates that read unitig u: its own two, and those it exclusively feeds / is fed by
     std::vector<Deps> deps;
     void compute_dependents();
-    void mark_dependents(uint32_t u, bool shared, int64_t below);
     size_t apply_candidate(size_t ci, bool shared, std::string& common);
     size_t first_pass_parallel();
     void reserve_arena(uint64_t extra);

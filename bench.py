@@ -33,6 +33,16 @@ WORKLOADS = {   # BASELINE.json configs (SURVEY.md §8d generator); the default 
 WORKLOAD = WORKLOADS["cfg2"] + ", k=51"
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/kernel_traffic.json, written by
+    profiles/extract_traffic.py from the .ncu-rep): dram__bytes_read.sum + dram__bytes_write.sum.  None if no capture matches."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        return t.get(kernel, {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
@@ -192,7 +202,8 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "InsertBody<%d> (k-mer hash insert)" % W, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "peak_kind": peak_kind, "traffic": None,
+                     "frac": round(achieved / peak, 4), "peak_kind": peak_kind,
+                     "traffic": measured_traffic("InsertBody<%d>:%s:k%d" % (W, args.workload, K)) if world == 1 else None,
                      "algorithmic_bytes_per_window": bytes_per_window, "windows_per_launch": int(own_windows), "kernel_ms": round(insert_ms, 3)},
         "stage_ms": {k2: round(mean(k2), 3) for k2 in ("pack", "insert", "adjacency", "boundaries", "runs", "unitigs", "links", "seed_sort", "emit", "d2h", "device_total",
                                                         "host_graph", "host_simplify", "host_gfa")},
