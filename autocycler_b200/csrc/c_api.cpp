@@ -325,7 +325,7 @@ int ac_gfa_size(ac_handle* h, uint64_t* n_bytes) {
         if (getenv("AC_HOST_PROFILE")) {
             const HostProfile& p = h->graph.prof;
             fprintf(stderr, "[host] adopt %.1f renumber(total) %.1f expand %.1f (%d passes; candidates %.1f, +compare %.1f, pass1 %.1f) gfa %.1f ms; U=%u\n",
-                    p.paths, p.renumber, p.expand, p.passes, p.seqs, p.check, p.links, (double)h->t.host_gfa, h->graph.U);
+                    p.adopt, p.renumber, p.expand, p.passes, p.candidates, p.compare, p.pass1, (double)h->t.host_gfa, h->graph.U);
         }
     }
     *n_bytes = h->gfa.size();

@@ -81,7 +81,7 @@ void HostGraph::build(const PipelineResult& r, const std::vector<HostSeq>& seqs,
             rpos[at] = ((uint64_t)(plus ? mirrored : fs) << 16) | (uint64_t)(s.id | (plus ? 0u : 0x8000u));
         }
     }
-    prof.paths = now_ms() - t0;
+    prof.adopt = now_ms() - t0;
 
     order.resize(U);
     for (uint32_t s = 0; s < U; ++s) order[s] = s;
@@ -449,7 +449,7 @@ size_t HostGraph::first_pass_parallel() {
 
 size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
     const double t0 = now_ms();
-    if (!cands_ready) { compute_candidates(); prof.seqs = now_ms() - t0; }
+    if (!cands_ready) { compute_candidates(); prof.candidates = now_ms() - t0; }
     size_t total_shifted = 0;
     std::string common;
     if (first_pass) {   // every candidate is evaluated in the first pass; do the byte comparisons for all of them in parallel
@@ -458,7 +458,7 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
         parallel_tasks(T, [&](size_t t) {
             for (size_t i = cands.size() * t / T; i < cands.size() * (t + 1) / T; ++i) spec_len[i] = common_length(cands[i]);
         });
-        prof.check = now_ms() - t0;
+        prof.compare = now_ms() - t0;
         size_t r = (size_t)-1;
         if (cands.size() >= 8192 && host_threads() >= 4 && !getenv("AC_EXPAND_SERIAL")) r = first_pass_parallel();
         if (r != (size_t)-1) total_shifted = r;
@@ -486,7 +486,7 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
         }
     }
     first_pass = false;
-    if (prof.passes == 0) prof.links = now_ms() - t0;      // first pass (incl. candidate listing)
+    if (prof.passes == 0) prof.pass1 = now_ms() - t0;      // first pass (incl. candidate listing)
     prof.expand += now_ms() - t0; prof.passes += 1;
     return total_shifted;
 }

@@ -26,7 +26,7 @@ static inline bool us_reverse(UStrand s) { return s & 1; }
 static inline UStrand us_make(uint32_t idx, bool reverse) { return (idx << 1) | (reverse ? 1u : 0u); }
 static inline UStrand us_flip(UStrand s) { return s ^ 1u; }
 
-struct HostProfile { double seed_sort = 0, seqs = 0, links = 0, paths = 0, renumber = 0, check = 0, expand = 0, gfa = 0; int passes = 0; };
+struct HostProfile { double adopt = 0, renumber = 0, candidates = 0, compare = 0, pass1 = 0, expand = 0; int passes = 0; };   // milliseconds (AC_HOST_PROFILE=1 prints them)
 
 class HostGraph {
 public:

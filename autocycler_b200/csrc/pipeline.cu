@@ -598,7 +598,6 @@ struct MergePassBody {
     }
 };
 
-struct IotaBody { uint32_t* out; AC_D void operator()(uint64_t i) const { out[i] = (uint32_t)i; } };
 
 // perm[s] = device unitig at seed position s.  Fills rank, the seed-ordered scalars and the arena space request.
 struct SeedGatherBody {
