@@ -361,7 +361,8 @@ int ac_load_sequences(ac_handle* h, const char* dir, uint32_t max_contigs, uint3
     if (!h || !dir) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     ac_clear_sequences(h);
-    LoadedInput in = load_sequences(dir, h->cfg.k, max_contigs, threads ? threads : 1, false);
+    // end repair runs on the device unless the literals are too long for it (k > 127 is refused earlier anyway) or AC_HOST_END_REPAIR is set
+    LoadedInput in = load_sequences(dir, h->cfg.k, max_contigs, threads ? threads : 1, false, getenv("AC_HOST_END_REPAIR") ? nullptr : h->pipe.get());
     for (size_t i = 0; i < in.seqs.size(); ++i) {
         int rc = ac_add_sequence(h, in.seqs[i].id, (const uint8_t*)in.padded[i].data(), in.padded[i].size(),
                                  in.seqs[i].filename.c_str(), in.seqs[i].contig_header.c_str());

@@ -219,8 +219,81 @@ void sequence_end_repair(std::vector<std::string>& padded, uint32_t k, uint32_t 
     }
 }
 
+// The same end repair with the match enumeration on the device: the literal halves of the 2S patterns and their reverse
+// complements are searched on the forward strands by one kernel (a hit of rc(l) at forward offset q is a hit of l on the
+// reverse strand at n-q-h); leftmost non-overlapping selection, ranking and splicing stay here (a few hits per pattern).
+void sequence_end_repair_device(DevicePipeline& pipe, std::vector<std::string>& padded, uint32_t k) {
+    const size_t m = k - 1, h = k / 2;
+    if (m == 0 || padded.empty()) return;
+    const size_t S = padded.size();
+    std::vector<SeqInfo> infos(S);
+    std::string all;
+    for (size_t i = 0; i < S; ++i) {
+        SeqInfo q{}; q.start = all.size(); q.len = (uint32_t)(padded[i].size() - m); q.lead = (uint16_t)h; q.trail = (uint16_t)h; q.id = (uint16_t)(i + 1);
+        infos[i] = q; all += padded[i];
+    }
+    // needles: distinct literals (and reverse complements), each with the patterns it stands for
+    struct Use { uint32_t pattern; bool rc; };
+    std::unordered_map<std::string, uint32_t> needle_of;
+    std::vector<std::vector<Use>> uses;
+    std::vector<uint64_t> words;
+    auto add = [&](const std::string& lit, uint32_t pattern, bool is_rc) {
+        auto it = needle_of.find(lit);
+        if (it == needle_of.end()) {
+            it = needle_of.emplace(lit, (uint32_t)uses.size()).first; uses.emplace_back();
+            unsigned __int128 v = 0;
+            for (char c : lit) v = (v << 2) | (unsigned)(c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3);
+            words.push_back((uint64_t)(v >> 64)); words.push_back((uint64_t)v);
+        }
+        uses[it->second].push_back({pattern, is_rc});
+    };
+    for (size_t i = 0; i < S; ++i) {
+        const std::string start_lit = padded[i].substr(h, h), end_lit = padded[i].substr(padded[i].size() - m, h);
+        add(start_lit, (uint32_t)(2 * i), false); add(revcomp(start_lit), (uint32_t)(2 * i), true);
+        add(end_lit, (uint32_t)(2 * i + 1), false); add(revcomp(end_lit), (uint32_t)(2 * i + 1), true);
+    }
+    std::vector<LiteralHit> hits;
+    pipe.find_literals((const uint8_t*)all.data(), all.size(), infos.data(), (uint32_t)S, (uint32_t)h, words.data(), (uint32_t)uses.size(), hits);
+
+    // candidates per (pattern, strand): start offset of the k-1 byte window on that strand
+    struct Cand { uint32_t pattern, strand; uint64_t start; };
+    std::vector<Cand> cands;
+    for (const LiteralHit& hit : hits) {
+        size_t si = std::upper_bound(infos.begin(), infos.end(), hit.gpos, [](uint64_t g, const SeqInfo& q) { return g < q.start; }) - infos.begin() - 1;
+        const uint64_t n = padded[si].size(), q = hit.gpos - infos[si].start;
+        for (const Use& u : uses[hit.needle]) {
+            const uint64_t j = u.rc ? n - q - h : q;                  // literal offset on the strand the pattern matched
+            const bool literal_last = (u.pattern & 1) == 0;            // start pattern: wildcards then literal
+            if (literal_last ? j < h : j + m > n) continue;            // the wildcard half must fit
+            cands.push_back({u.pattern, (uint32_t)(2 * si + (u.rc ? 1 : 0)), literal_last ? j - h : j});
+        }
+    }
+    std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) {
+        if (a.pattern != b.pattern) return a.pattern < b.pattern;
+        if (a.strand != b.strand) return a.strand < b.strand;
+        return a.start < b.start; });
+    std::vector<MatchTally> tally(2 * S);
+    for (size_t x = 0; x < cands.size();) {
+        size_t y = x; uint64_t next_free = 0;
+        while (y < cands.size() && cands[y].pattern == cands[x].pattern && cands[y].strand == cands[x].strand) {
+            const Cand& c = cands[y++];
+            if (c.start < next_free) continue;                         // overlaps the previous match of this regex on this strand
+            next_free = c.start + m;
+            const std::string& fwd = padded[c.strand >> 1];
+            tally[c.pattern].count[(c.strand & 1) ? revcomp(fwd.substr(fwd.size() - c.start - m, m)) : fwd.substr(c.start, m)] += 1;
+        }
+        x = y;
+    }
+    std::vector<std::string> repaired = padded;                       // matches refer to the pre-repair strands (compress.rs:209)
+    for (size_t i = 0; i < S; ++i) {
+        repaired[i].replace(0, m, best_match(tally[2 * i]));                                   // compress.rs:223
+        repaired[i].replace(repaired[i].size() - m, m, best_match(tally[2 * i + 1]));        // compress.rs:232
+    }
+    padded.swap(repaired);
+}
+
 // ------------------------------------------------------------------------------------------------
-LoadedInput load_sequences(const std::string& dir, uint32_t k, uint32_t max_contigs, uint32_t threads, bool verbose) {
+LoadedInput load_sequences(const std::string& dir, uint32_t k, uint32_t max_contigs, uint32_t threads, bool verbose, DevicePipeline* device) {
     LoadedInput in;
     const std::vector<std::string> assemblies = find_all_assemblies(dir);
     in.assembly_count = assemblies.size();
@@ -260,7 +333,7 @@ LoadedInput load_sequences(const std::string& dir, uint32_t k, uint32_t max_cont
                                   "Are your input assemblies fragmented or contaminated?", mean, max_contigs);
         fail(buf);
     }
-    sequence_end_repair(in.padded, k, threads);
+    if (device) sequence_end_repair_device(*device, in.padded, k); else sequence_end_repair(in.padded, k, threads);
     return in;
 }
 

@@ -22,6 +22,7 @@ struct LoadedInput {
 std::vector<std::string> find_all_assemblies(const std::string& dir);                 // misc.rs:64-95
 struct FastaRecord { std::string name, header, seq; };
 std::vector<FastaRecord> load_fasta(const std::string& path);                         // misc.rs:144-321
-LoadedInput load_sequences(const std::string& dir, uint32_t k, uint32_t max_contigs, uint32_t threads, bool verbose);
+LoadedInput load_sequences(const std::string& dir, uint32_t k, uint32_t max_contigs, uint32_t threads, bool verbose, DevicePipeline* device);
+void sequence_end_repair_device(DevicePipeline& pipe, std::vector<std::string>& padded, uint32_t k);   // compress.rs:202-270, matches found on the GPU
 void sequence_end_repair(std::vector<std::string>& padded, uint32_t k, uint32_t threads);   // compress.rs:202-270
 std::string metrics_yaml(const LoadedInput& in, uint64_t unitig_count, uint64_t unitig_total_length);  // metrics.rs:65-73,250-254

@@ -739,6 +739,44 @@ struct ScanApplyBody {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// End repair (compress.rs:202-236): where do the k/2-base literals of the repair patterns occur?
+// ------------------------------------------------------------------------------------------------
+struct NeedleSlot { uint64_t w[2]; uint32_t id; uint32_t used; };
+template <int WH> struct LiteralScanBody {
+    const uint64_t* packed; const SeqInfo* seqs; uint32_t n_seqs; KParams p; uint64_t total;     // p describes an h-mer (p.k == h)
+    const NeedleSlot* table; uint64_t table_mask;
+    LiteralHit* hits; uint64_t hit_cap; unsigned long long* n_hits;
+    AC_D void operator()(uint64_t i) const {
+        uint64_t g = i * 64;
+        const uint64_t g1 = (g + 64 < total) ? g + 64 : total;
+        uint32_t si = find_seq(seqs, n_seqs, g);
+        while (g < g1) {
+            const SeqInfo s = seqs[si];
+            // windows of h bases that lie entirely inside the contig: padded offsets [lead, lead + len - h]
+            const uint64_t lo = s.start + s.lead, hi = s.start + s.lead + s.len - p.k;     // inclusive range of window starts
+            if (g > hi || s.len < p.k) { if (si + 1 >= n_seqs) return; ++si; if (seqs[si].start > g) g = seqs[si].start; continue; }
+            if (g < lo) g = lo;
+            if (g >= g1) return;
+            const uint64_t stop = (hi + 1 < g1) ? hi + 1 : g1;
+            Key<WH> key = fetch_codes<WH>(packed, g, p);
+            for (;;) {
+                uint64_t slot = key_hash(key) & table_mask;
+                for (;;) {
+                    const NeedleSlot n = table[slot];
+                    if (!n.used) break;
+                    bool eq = n.w[0] == key.w[0];
+                    if (WH > 1) eq = eq && n.w[1] == key.w[WH - 1];
+                    if (eq) { const unsigned long long at = ac_atomic_add(n_hits, 1ull); if (at < hit_cap) { LiteralHit hh; hh.needle = n.id; hh.pad = 0; hh.gpos = g; hits[at] = hh; } break; }
+                    slot = (slot + 1) & table_mask;
+                }
+                if (++g >= stop) break;
+                key_push_right(key, packed_base(packed, g + p.k - 1), p);
+            }
+        }
+    }
+};
+
 #ifndef AC_EMULATE
 // Product scan: tiles of 4096 values, coalesced loads, warp-shuffle block scans (the functor bodies above are the
 // host-emulation form of the same two phases).
@@ -875,7 +913,7 @@ struct DevicePipeline::Impl {
     uint64_t cap = 0, n_windows = 0, n_runs = 0, g_begin = 0, g_end = 0, n_slots_used = 0, n_dotted = 0;
     bool any_dotted = false, is_multi = false;
     int stage = 0;
-    DevBuf run_hs, run_ts, exp_flag, occ_list, bloom;
+    DevBuf run_hs, run_ts, exp_flag, occ_list, bloom, needles, hits;
     void set_device() {
 #ifndef AC_EMULATE
         AC_CUDA_CHECK(cudaSetDevice(device));
@@ -944,6 +982,49 @@ void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo*
     m.seqs.ensure(n_seqs * sizeof(SeqInfo));
     ac_h2d(m.seqs.p, seqs, n_seqs * sizeof(SeqInfo), &m.stream);
     m.mark(1);
+}
+
+void DevicePipeline::find_literals(const uint8_t* ascii_host, uint64_t total_bytes, const SeqInfo* host_seq, uint32_t n, uint32_t h,
+                                   const uint64_t* needle_words, uint32_t n_needles, std::vector<LiteralHit>& out) {
+    Impl& m = *impl; m.set_device();
+    const int WH = (int)((2 * h + 63) / 64);
+    if (WH > 2) throw std::runtime_error("end repair literals longer than 64 bases are not supported by the GPU path");
+    const KParams p = make_kparams(h, WH);
+    m.ascii.ensure(total_bytes); ac_h2d(m.ascii.p, ascii_host, total_bytes, &m.stream);
+    m.seqs.ensure(n * sizeof(SeqInfo)); ac_h2d(m.seqs.p, host_seq, n * sizeof(SeqInfo), &m.stream);
+    const uint64_t n_words = (total_bytes + 31) / 32;
+    m.packed.ensure((n_words + 6) * sizeof(uint64_t));
+    ac_memset(m.packed.as<uint64_t>() + n_words, 0, 6 * sizeof(uint64_t), &m.stream);
+    ac_launch("pack", &m.stream, PackBody{m.ascii.as<uint8_t>(), total_bytes, m.packed.as<uint64_t>()}, n_words);
+    // needle table (host-built, tiny)
+    uint64_t cap = 64; while (cap < 4ull * n_needles) cap <<= 1;
+    std::vector<NeedleSlot> table(cap);
+    for (auto& t : table) { t.w[0] = t.w[1] = 0; t.id = 0; t.used = 0; }
+    for (uint32_t i = 0; i < n_needles; ++i) {
+        Key<2> k2; k2.w[0] = needle_words[2 * i]; k2.w[1] = needle_words[2 * i + 1]; k2.d = 0;
+        uint64_t hsh;
+        if (WH == 1) { Key<1> k1; k1.w[0] = k2.w[1]; k1.d = 0; hsh = key_hash(k1); } else hsh = key_hash(k2);
+        uint64_t slot = hsh & (cap - 1);
+        while (table[slot].used) slot = (slot + 1) & (cap - 1);
+        // stored the way the scan compares: w[0] = most significant word of the WH-word key, w[1] = its last word
+        table[slot].w[0] = WH == 1 ? k2.w[1] : k2.w[0]; table[slot].w[1] = k2.w[1]; table[slot].id = i; table[slot].used = 1;
+    }
+    m.needles.ensure(cap * sizeof(NeedleSlot)); ac_h2d(m.needles.p, table.data(), cap * sizeof(NeedleSlot), &m.stream);
+    m.counters.ensure((2 * AC_STRIPES + 2) * sizeof(unsigned long long));
+    uint64_t hit_cap = 1u << 20;
+    for (;;) {
+        m.hits.ensure(hit_cap * sizeof(LiteralHit));
+        ac_memset(m.counters.p, 0, sizeof(unsigned long long), &m.stream);
+        if (WH == 1) ac_launch("literal_scan", &m.stream, LiteralScanBody<1>{m.packed.as<uint64_t>(), m.seqs.as<SeqInfo>(), n, p, total_bytes, m.needles.as<NeedleSlot>(), cap - 1,
+                                                                           m.hits.as<LiteralHit>(), hit_cap, m.counters.as<unsigned long long>()}, (total_bytes + 63) / 64);
+        else ac_launch("literal_scan", &m.stream, LiteralScanBody<2>{m.packed.as<uint64_t>(), m.seqs.as<SeqInfo>(), n, p, total_bytes, m.needles.as<NeedleSlot>(), cap - 1,
+                                                                     m.hits.as<LiteralHit>(), hit_cap, m.counters.as<unsigned long long>()}, (total_bytes + 63) / 64);
+        unsigned long long found = 0;
+        ac_d2h(&found, m.counters.p, sizeof found, &m.stream); ac_sync(&m.stream);
+        if (found <= hit_cap) { out.resize(found); if (found) { ac_d2h(out.data(), m.hits.p, found * sizeof(LiteralHit), &m.stream); ac_sync(&m.stream); } break; }
+        hit_cap = found + 1024;        // short literals match often: run again with room for all of them
+    }
+    m.stage = 0;
 }
 
 // ---- stage 1: pack + k-mer table over this rank's sequences ----

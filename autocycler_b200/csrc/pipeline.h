@@ -69,6 +69,10 @@ struct PipelineResult {
     PipelineTimings t;
 };
 
+// End repair on the device (compress.rs:202-236): every occurrence of one of the k/2-base literals (the fixed halves of the
+// 2S repair patterns and their reverse complements) on the forward strands.
+struct LiteralHit { uint32_t needle; uint32_t pad; uint64_t gpos; };   // needle index, global coordinate of the matching window
+
 class DevicePipeline {
 public:
     DevicePipeline(int device, void* stream);
@@ -86,6 +90,9 @@ public:
     void export_runs(void* dst, uint64_t cap_records);                  // 32-byte RunRec records, ascending coordinate, into caller-owned device memory
     void import_runs(const void* dev_ptr, uint64_t n);                  // rank 0: every rank's records, concatenated in rank order
     void finish(PipelineResult& out, bool keep_positions);              // unitigs, seeds, links, seed order, host-ready arrays
+    // needles: n_needles keys of h bases each (2 words per key, kmer_key.h layout for k = h), pairwise distinct.
+    void find_literals(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t h,
+                       const uint64_t* needle_words, uint32_t n_needles, std::vector<LiteralHit>& hits);
     unsigned long long kernel_launches() const;
     struct Impl;
 private:
