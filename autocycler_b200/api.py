@@ -55,7 +55,7 @@ class AcTimings(C.Structure):
 
 
 EXPORTS = ["ac_last_error", "ac_version", "ac_create", "ac_destroy", "ac_add_sequence", "ac_clear_sequences", "ac_upload",
-           "ac_build", "ac_simplify", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
+           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
            "ac_timings_get", "ac_compress_dir", "ac_load_sequences", "ac_sequence_get",
            "ac_build_local", "ac_entries_count", "ac_entries_export", "ac_entries_merge", "ac_runs_local", "ac_runs_export",
            "ac_runs_import", "ac_build_finish", "ac_gfa_data"]
@@ -82,6 +82,7 @@ def load_library(path=None):
     lib.ac_clear_sequences.argtypes = [C.c_void_p]
     for name in ("ac_upload", "ac_build", "ac_simplify"):
         getattr(lib, name).argtypes = [C.c_void_p]
+    lib.ac_merge_linear_paths.argtypes = [C.c_void_p, C.c_int]
     lib.ac_counts_get.argtypes = [C.c_void_p, C.POINTER(AcCounts)]
     lib.ac_unitigs_copy.argtypes = [C.c_void_p, C.POINTER(AcUnitigs)]
     lib.ac_path_copy.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), C.c_uint64, C.POINTER(C.c_uint64)]
@@ -258,6 +259,10 @@ class UnitigGraph:
 
 def simplify_structure(graph, seqs=None):   # graph_simplification.rs:26-40
     graph._h.check(graph._h.lib.ac_simplify(graph._h.ptr))
+
+
+def merge_linear_paths(graph, seqs=()):   # graph_simplification.rs:315-371; seqs=None/[] merges without regard to the paths
+    graph._h.check(graph._h.lib.ac_merge_linear_paths(graph._h.ptr, 1 if seqs is not None and len(seqs) else 0))
 
 
 def load_sequences(assemblies_dir, k_size, max_contigs=25, threads=8, lib=None, device=0):

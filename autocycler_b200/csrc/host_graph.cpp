@@ -523,11 +523,11 @@ void HostGraph::gfa_text(const std::vector<HostSeq>& seqs, std::string& out) con
     parallel_tasks(TU, [&](size_t t) {
         for (uint32_t n = ub(t); n < ub(t + 1); ++n) {
             const uint32_t idx = order[n];
-            char buf[24]; const uint32_t d = (uint32_t)(put_uint(buf, (uint64_t)n + 1) - buf);
+            if (number[idx] >= 100000000u) throw std::runtime_error("unitig numbers above 99,999,999 are not supported by the GFA writer");
+            char buf[24]; const uint32_t d = (uint32_t)(put_uint(buf, (uint64_t)number[idx]) - buf);
             uint64_t v = 0; memcpy(&v, buf, d < 8 ? d : 8); num_txt[idx] = v; num_len[idx] = (uint8_t)d;
         }
     });
-    if (U >= 100000000u) throw std::runtime_error("more than 99,999,999 unitigs are not supported by the GFA writer");
     parallel_tasks(TU, [&](size_t t) {
         uint64_t ss = 0, ls = 0;
         for (uint32_t n = ub(t); n < ub(t + 1); ++n) {
@@ -569,7 +569,7 @@ void HostGraph::gfa_text(const std::vector<HostSeq>& seqs, std::string& out) con
             char* p = base + s_at[task];
             for (uint32_t n = ub(task); n < ub(task + 1); ++n) {
                 const uint32_t idx = order[n];
-                *p++ = 'S'; *p++ = '\t'; p = put_uint(p, (uint64_t)n + 1); *p++ = '\t';
+                *p++ = 'S'; *p++ = '\t'; p = put_uint(p, (uint64_t)number[idx]); *p++ = '\t';
                 p = put_str(p, seq_ptr(idx), rec[idx].len);
                 p = put_str(p, "\tDP:f:", 6); p = put_uint(p, depth[idx]); p = put_str(p, ".00\n", 4);
             }
@@ -583,7 +583,7 @@ void HostGraph::gfa_text(const std::vector<HostSeq>& seqs, std::string& out) con
                     const UStrand from = us_make(idx, rev != 0);
                     for (uint32_t x = next_off[from]; x < next_off[from + 1]; ++x) {
                         const UStrand to = next[x];
-                        *p++ = 'L'; *p++ = '\t'; p = put_uint(p, (uint64_t)n + 1); *p++ = '\t'; *p++ = rev ? '-' : '+'; *p++ = '\t';
+                        *p++ = 'L'; *p++ = '\t'; p = put_uint(p, (uint64_t)number[idx]); *p++ = '\t'; *p++ = rev ? '-' : '+'; *p++ = '\t';
                         p = put_uint(p, number[us_index(to)]); *p++ = '\t'; *p++ = us_reverse(to) ? '-' : '+'; p = put_str(p, "\t0M\n", 4);
                     }
                 }

@@ -56,6 +56,7 @@ public:
     void check_links() const;                 // unitig_graph.rs:752-793
     void simplify_structure();                // graph_simplification.rs:26-40
     size_t expand_repeats();                  // graph_simplification.rs:43-86
+    void merge_linear_paths(bool use_paths);  // graph_simplification.rs:315-371 (host_merge.cpp); use_paths=false is the reference's `seqs` = [] and drops the paths
     void gfa_text(const std::vector<HostSeq>& seqs, std::string& out) const;   // unitig_graph.rs:317-360
     uint64_t total_length() const;
     uint64_t link_count_single() const;       // unitig_graph.rs:478-507 (.1)
@@ -65,6 +66,9 @@ public:
     const UStrand* prev_begin(UStrand s) const { return prev + prev_off[s]; }
     uint32_t prev_size(UStrand s) const { return prev_off[s + 1] - prev_off[s]; }
 private:
+    // storage of the graph once merge_linear_paths has rebuilt it (the pinned pipeline buffers are left behind)
+    std::vector<UnitigRec> own_rec; std::vector<uint32_t> own_depth, own_next_off, own_prev_off;
+    std::vector<UStrand> own_next, own_prev, own_path; std::vector<uint64_t> own_path_off;
     std::vector<uint8_t> fixed_start, fixed_end;
     bool fixed_ready = false;
     void compute_fixed();

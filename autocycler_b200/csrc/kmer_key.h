@@ -79,8 +79,11 @@ template <int W> AC_HD void key_push_left(Key<W>& key, uint64_t code, const KPar
 
 // code of base at index i (0 = first base).
 template <int W> AC_HD uint32_t key_base(const Key<W>& key, uint32_t i, const KParams& p) {
-    uint32_t bit = 2 * (p.k - 1 - i);
-    return (uint32_t)(key.w[W - 1 - (bit >> 6)] >> (bit & 63)) & 3u;
+    const uint32_t bit = 2 * (p.k - 1 - i), word = W - 1 - (bit >> 6);
+    uint64_t v = 0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) v = (word == (uint32_t)j) ? key.w[j] : v;     // no dynamic indexing: keeps the key in registers
+    return (uint32_t)(v >> (bit & 63)) & 3u;
 }
 
 // The centre base is never a dot; the strand whose centre base is A or C is the stored ("canonical")
@@ -114,8 +117,10 @@ template <int W> AC_HD Key<W> key_rc(const Key<W>& key, const KParams& p) {
         uint32_t nd = (uint32_t)(key.d > 0 ? key.d : -key.d);
         for (uint32_t i = 0; i < nd; ++i) {
             uint32_t idx = key.d > 0 ? (p.k - 1 - i) : i;     // old leading dots become trailing and vice versa
-            uint32_t bit = 2 * (p.k - 1 - idx);
-            r.w[W - 1 - (bit >> 6)] &= ~(3ull << (bit & 63));
+            const uint32_t bit = 2 * (p.k - 1 - idx), word = W - 1 - (bit >> 6);
+            const uint64_t keep = ~(3ull << (bit & 63));
+#pragma unroll
+            for (int j = 0; j < W; ++j) r.w[j] &= (word == (uint32_t)j) ? keep : ~0ull;
         }
     }
     return r;

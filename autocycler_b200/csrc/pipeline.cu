@@ -164,6 +164,21 @@ template <int W> struct InsertBody {
         if (bits && (aux_seen & bits) != bits) ac_atomic_or(&t.slots[slot].aux, bits);   // usually already there (aux_seen may be stale: then the OR is merely redundant)
         if (pos_slot) pos_slot[g] = (uint32_t)slot;
     }
+    AC_D uint32_t observed(const Key<W>& fwd, const SeqInfo& s, uint64_t g, uint64_t fs) const {
+        uint32_t obs = 0;
+        if (fwd.d == 0) {
+            const bool cf = key_is_canonical(fwd, p);
+            if (fs + 1 < s.len && window_dots(s, fs + 1, p.k) == 0) {
+                const uint32_t b = packed_base(t.packed, g + p.k);
+                obs |= cf ? (1u << (AC_AUX_OBS_OUT_SHIFT + b)) : (1u << (AC_AUX_OBS_IN_SHIFT + 3 - b));
+            }
+            if (fs > 0 && window_dots(s, fs - 1, p.k) == 0) {
+                const uint32_t b = packed_base(t.packed, g - 1);
+                obs |= cf ? (1u << (AC_AUX_OBS_IN_SHIFT + b)) : (1u << (AC_AUX_OBS_OUT_SHIFT + 3 - b));
+            }
+        }
+        return obs;
+    }
     AC_D void operator()(uint64_t i) const {
         uint64_t g = g_begin + i * AC_CHUNK;
         const uint64_t g1 = (g + AC_CHUNK < g_end) ? g + AC_CHUNK : g_end;
@@ -195,23 +210,53 @@ template <int W> struct InsertBody {
                 }
                 // Neighbouring bases seen next to this k-mer, in the canonical strand's terms: a lower bound on the node-centric
                 // degrees that spares the adjacency kernel the probes for neighbours it already knows to exist.
-                uint32_t obs = 0;
-                if (d == 0) {
-                    const bool cf = key_is_canonical(fwd, p);
-                    if (fs + 1 < s.len && window_dots(s, fs + 1, p.k) == 0) {
-                        const uint32_t b = packed_base(t.packed, g + p.k);
-                        obs |= cf ? (1u << (AC_AUX_OBS_OUT_SHIFT + b)) : (1u << (AC_AUX_OBS_IN_SHIFT + 3 - b));
-                    }
-                    if (fs > 0 && window_dots(s, fs - 1, p.k) == 0) {
-                        const uint32_t b = packed_base(t.packed, g - 1);
-                        obs |= cf ? (1u << (AC_AUX_OBS_IN_SHIFT + b)) : (1u << (AC_AUX_OBS_OUT_SHIFT + 3 - b));
-                    }
-                }
-                insert(fwd, rc, g, fs, s.len, obs, claimed, claimed_dotted);
+                insert(fwd, rc, g, fs, s.len, observed(fwd, s, g, fs), claimed, claimed_dotted);
             }
         }
         if (claimed) ac_atomic_add(&counters[2 * (i % AC_STRIPES)], (unsigned long long)claimed);
         if (claimed_dotted) ac_atomic_add(&counters[2 * (i % AC_STRIPES) + 1], (unsigned long long)claimed_dotted);
+    }
+};
+
+// The same insertion with ONE window per thread: the lanes of a warp take 32 consecutive windows, so the pos_slot
+// stores coalesce, the packed-sequence reads of a warp fall in two or three sectors, and no lane waits for a
+// neighbour's longer probe chain across a whole AC_CHUNK of windows.  Costs a key_rc per window instead of a roll.
+template <int W> struct InsertLaneBody {
+    InsertBody<W> b;
+    AC_D void operator()(uint64_t i) const {
+        const uint64_t g = b.g_begin + i;
+        uint32_t si;
+#ifdef __CUDA_ARCH__
+        const unsigned mask = __activemask();
+        const int leader = __ffs(mask) - 1;            // the lowest active lane holds the smallest coordinate
+        si = 0;
+        if ((int)(threadIdx.x & 31) == leader) si = find_seq(b.t.seqs, b.t.n_seqs, g);
+        si = __shfl_sync(mask, si, leader);
+        while (si + 1 < b.t.n_seqs && b.t.seqs[si + 1].start <= g) ++si;
+#else
+        si = find_seq(b.t.seqs, b.t.n_seqs, g);
+#endif
+        const SeqInfo s = b.t.seqs[si];
+        const uint64_t fs = g - s.start;
+        uint32_t claimed = 0, claimed_dotted = 0;
+        if (fs < s.len) {                                // else: one of the k-1 padded bytes that start no window
+            Key<W> fwd = fetch_codes<W>(b.t.packed, g, b.p);
+            fwd.d = window_dots(s, fs, b.p.k);
+            const Key<W> rc = key_rc(fwd, b.p);
+            b.insert(fwd, rc, g, fs, s.len, b.observed(fwd, s, g, fs), claimed, claimed_dotted);
+        }
+#ifdef __CUDA_ARCH__
+        const unsigned again = __activemask();
+        const uint32_t n_claimed = __reduce_add_sync(again, claimed), n_dotted = __reduce_add_sync(again, claimed_dotted);
+        if ((int)(threadIdx.x & 31) == __ffs(again) - 1) {
+            const uint64_t stripe = (i >> 5) % AC_STRIPES;
+            if (n_claimed) ac_atomic_add(&b.counters[2 * stripe], (unsigned long long)n_claimed);
+            if (n_dotted) ac_atomic_add(&b.counters[2 * stripe + 1], (unsigned long long)n_dotted);
+        }
+#else
+        if (claimed) ac_atomic_add(&b.counters[2 * (i % AC_STRIPES)], (unsigned long long)claimed);
+        if (claimed_dotted) ac_atomic_add(&b.counters[2 * (i % AC_STRIPES) + 1], (unsigned long long)claimed_dotted);
+#endif
     }
 };
 
@@ -1078,8 +1123,9 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
         ac_launch("init_slots", &stream, InitSlotsBody{slots.as<Slot>()}, cap);
         ac_memset(counters.p, 0, counter_words * sizeof(unsigned long long), &stream);
         const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
-        ac_launch("insert", &stream, InsertBody<W>{tv, p, g_begin, g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), 0},
-                  (g_end - g_begin + AC_CHUNK - 1) / AC_CHUNK);
+        const InsertBody<W> ins{tv, p, g_begin, g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), 0};
+        if (getenv("AC_INSERT_CHUNKED")) ac_launch("insert", &stream, ins, (g_end - g_begin + AC_CHUNK - 1) / AC_CHUNK);
+        else ac_launch("insert", &stream, InsertLaneBody<W>{ins}, g_end - g_begin);
         if (cap == safe_cap) break;                      // cannot overflow: one slot and a half per window
         unsigned long long overflow = 0;
         ac_d2h(&overflow, counters.as<unsigned long long>() + 2 * AC_STRIPES, sizeof overflow, &stream); ac_sync(&stream);

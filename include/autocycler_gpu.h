@@ -10,6 +10,7 @@
  *   UnitigGraph::from_kmer_graph            unitig_graph.rs:36-48    -> ac_build
  *   (the UnitigGraph / Unitig fields)       unitig_graph.rs:28-33, unitig.rs:30-45 -> ac_counts_get, ac_unitigs_copy
  *   simplify_structure                      graph_simplification.rs:26-40 -> ac_simplify
+ *   merge_linear_paths (downstream, 8f)     graph_simplification.rs:315-371 -> ac_merge_linear_paths
  *   UnitigGraph::save_gfa                   unitig_graph.rs:317-331  -> ac_gfa_size, ac_gfa_copy
  *   compress (the whole subcommand)         compress.rs:32-50        -> ac_compress_dir
  *
@@ -96,6 +97,11 @@ int ac_clear_sequences(ac_handle* h);
 int ac_upload(ac_handle* h);            /* host -> HBM copy of the added sequences */
 int ac_build(ac_handle* h);             /* k-mer table, unitigs, links, renumber: the graph after from_kmer_graph */
 int ac_simplify(ac_handle* h);          /* simplify_structure */
+/* merge_linear_paths (graph_simplification.rs:315-371), what cluster/trim/resolve/clean first do to a loaded compress
+ * graph (cluster.rs:804): chains of exclusively linked unitigs become one unitig numbered max+1, max+2, ...; merged
+ * unitigs follow the surviving ones in the S lines.  use_paths != 0 keeps sequence-path ends fixed (the reference's
+ * `seqs` argument); 0 is its `&vec![]` form: everything mergeable is merged and the P lines lose their paths. */
+int ac_merge_linear_paths(ac_handle* h, int use_paths);
 
 /* Multi-GPU form of ac_build: one process per GPU, every process adds and uploads ALL sequences, owns the
  * contiguous block [seq_lo, seq_hi) of them (index = order of ac_add_sequence), and the caller (e.g. torch.distributed over

@@ -446,6 +446,9 @@ Unitig Unitig::from_segment_line(const std::string& line) {   // unitig.rs:62-91
             break;   // Iterator::find stops at the first DP:f: part
         }
     if (!found) quit_with_error("Could not find a depth tag (e.g. DP:f:10.00) in the GFA segment line.");
+    auto has = [&](const char* tag) { for (auto& p : parts) if (p == tag) return true; return false; };   // unitig.rs:78-86
+    u.unitig_type = has("CL:Z:steelblue") ? UnitigType::Consentig : has("CL:Z:forestgreen") ? UnitigType::Anchor
+                  : has("CL:Z:pink") ? UnitigType::Bridge : UnitigType::Other;
     return u;
 }
 
@@ -482,9 +485,11 @@ void Unitig::trim_overlaps(size_t k_size) {   // unitig.rs:157-165
     ORC_ASSERT(!forward_seq.empty(), "empty unitig after trim");
 }
 
-std::string Unitig::gfa_segment_line() const {   // unitig.rs:167-171 with use_other_colour=false, type Other
+std::string Unitig::gfa_segment_line() const {   // unitig.rs:167-181 with use_other_colour=false
     char dp[64]; snprintf(dp, sizeof dp, "%.2f", depth);
-    return "S\t" + std::to_string(number) + "\t" + forward_seq + "\tDP:f:" + dp;
+    const char* colour = unitig_type == UnitigType::Consentig ? "\tCL:Z:steelblue" : unitig_type == UnitigType::Anchor ? "\tCL:Z:forestgreen"
+                       : unitig_type == UnitigType::Bridge ? "\tCL:Z:pink" : "";
+    return "S\t" + std::to_string(number) + "\t" + forward_seq + "\tDP:f:" + dp + colour;
 }
 
 void Unitig::remove_seq_from_start(size_t amount) {   // unitig.rs:216-223
@@ -959,6 +964,168 @@ size_t expand_repeats(UnitigGraph& graph, const std::vector<Sequence>& seqs) {  
 void simplify_structure(UnitigGraph& graph, const std::vector<Sequence>& seqs) {   // :26-40
     while (expand_repeats(graph, seqs) > 0) {}
     graph.renumber_unitigs();
+}
+
+// ---------------------------------------------------------------------------------------------
+// graph_simplification.rs:315-526 merge_linear_paths and the UnitigGraph helpers it uses
+// ---------------------------------------------------------------------------------------------
+void UnitigGraph::delete_dangling_links() {   // unitig_graph.rs:547-564: links are kept or dropped by unitig NUMBER
+    std::unordered_set<uint32_t> numbers;
+    for (auto& u : unitigs) numbers.insert(u->number);
+    auto prune = [&](std::vector<UnitigStrand>& v) {
+        std::vector<UnitigStrand> kept;
+        for (auto& l : v) if (numbers.count(l.number())) kept.push_back(l);
+        v.swap(kept);
+    };
+    for (auto& u : unitigs) { prune(u->forward_next); prune(u->forward_prev); prune(u->reverse_next); prune(u->reverse_prev); }
+}
+
+uint32_t UnitigGraph::max_unitig_number() const {   // unitig_graph.rs:901-903
+    uint32_t m = 0; for (auto& u : unitigs) m = std::max(m, u->number); return m;
+}
+
+std::vector<std::vector<uint32_t>> UnitigGraph::connected_components() const {   // unitig_graph.rs:905-947
+    std::unordered_set<uint32_t> visited;
+    std::vector<std::vector<uint32_t>> components;
+    for (auto& u : unitigs) {
+        if (visited.count(u->number)) continue;
+        std::vector<uint32_t> component, stack{u->number};
+        while (!stack.empty()) {
+            const uint32_t cur = stack.back(); stack.pop_back();
+            if (!visited.insert(cur).second) continue;
+            component.push_back(cur);
+            auto it = unitig_index.find(cur);
+            if (it == unitig_index.end()) continue;
+            const Unitig* c = it->second;
+            for (auto* v : {&c->forward_next, &c->forward_prev, &c->reverse_next, &c->reverse_prev})
+                for (auto& l : *v) if (!visited.count(l.number())) stack.push_back(l.number());
+        }
+        std::sort(component.begin(), component.end());
+        components.push_back(std::move(component));
+    }
+    std::sort(components.begin(), components.end());
+    return components;
+}
+
+bool UnitigGraph::component_is_circular_loop(const std::vector<uint32_t>& component) const {   // unitig_graph.rs:949-967
+    if (component.empty()) return false;
+    const uint32_t first = component[0];
+    uint32_t num = first; bool strand = strand::FORWARD;
+    std::unordered_set<uint32_t> visited;
+    while (num != first || visited.empty()) {
+        if (!visited.insert(num).second) return false;
+        const Unitig* u = unitig_index.at(num);
+        if (u->forward_next.size() != 1 || u->forward_prev.size() != 1 || u->reverse_next.size() != 1 || u->reverse_prev.size() != 1) return false;
+        const UnitigStrand& next = strand ? u->forward_next[0] : u->reverse_next[0];
+        num = next.number(); strand = next.strand;
+    }
+    return visited.size() == component.size();
+}
+
+void merge_fixed_sets(const UnitigGraph& graph, const std::vector<Sequence>& seqs, std::unordered_set<uint32_t>& fixed_starts,
+                      std::unordered_set<uint32_t>& fixed_ends) {   // :330-331, fix_circular_loops :374-384
+    get_fixed_unitig_starts_and_ends(graph, seqs, fixed_starts, fixed_ends);
+    for (auto& component : graph.connected_components())
+        if (graph.component_is_circular_loop(component)) fixed_starts.insert(component[0]);
+}
+
+static bool cannot_merge_start(uint32_t n, bool s, const std::unordered_set<uint32_t>& fs, const std::unordered_set<uint32_t>& fe) {   // :387-390
+    return (s && fs.count(n)) || (!s && fe.count(n));
+}
+static bool cannot_merge_end(uint32_t n, bool s, const std::unordered_set<uint32_t>& fs, const std::unordered_set<uint32_t>& fe) {     // :398-401
+    return (s && fe.count(n)) || (!s && fs.count(n));
+}
+
+std::string merge_unitig_seqs(const std::vector<UnitigStrand>& path) {   // :490-500
+    std::string merged;
+    for (auto& u : path) merged += u.unitig->get_seq(u.strand);
+    return merged;
+}
+
+static double get_merge_path_depth(const std::vector<UnitigStrand>& path, const std::vector<Position>& forward_positions) {   // :503-526
+    if (!forward_positions.empty()) return (double)forward_positions.size();
+    for (auto& u : path) if (u.unitig->unitig_type == UnitigType::Anchor) return u.unitig->depth;
+    double total = 0.0, sum = 0.0;
+    { uint32_t t = 0; for (auto& u : path) t += u.unitig->length(); total = (double)t; }
+    for (auto& u : path) sum += u.unitig->depth * (double)u.unitig->length();
+    return sum / total;
+}
+
+static void merge_path(UnitigGraph& graph, const std::vector<UnitigStrand>& path, uint32_t new_number) {   // :410-487
+    const UnitigStrand first = path.front(), last = path.back();
+    auto nu = std::make_unique<Unitig>();
+    Unitig* n = nu.get();
+    n->number = new_number;
+    n->forward_seq = merge_unitig_seqs(path);
+    n->reverse_seq = reverse_complement(n->forward_seq);
+    n->forward_positions = first.strand ? first.unitig->forward_positions : first.unitig->reverse_positions;
+    n->reverse_positions = last.strand ? last.unitig->reverse_positions : last.unitig->forward_positions;
+    const bool end_to_start = graph.link_exists(last.number(), last.strand, first.number(), first.strand);
+    const bool start_flip = graph.link_exists(first.number(), !first.strand, first.number(), first.strand);
+    const bool end_flip = graph.link_exists(last.number(), last.strand, last.number(), !last.strand);
+    n->forward_prev = first.strand ? first.unitig->forward_prev : first.unitig->reverse_prev;
+    n->reverse_next = first.strand ? first.unitig->reverse_next : first.unitig->forward_next;
+    n->forward_next = last.strand ? last.unitig->forward_next : last.unitig->reverse_next;
+    n->reverse_prev = last.strand ? last.unitig->reverse_prev : last.unitig->forward_prev;
+    n->depth = get_merge_path_depth(path, n->forward_positions);
+    for (auto& p : path)
+        if (p.unitig->unitig_type == UnitigType::Anchor || p.unitig->unitig_type == UnitigType::Consentig) n->unitig_type = UnitigType::Consentig;
+    graph.unitigs.push_back(std::move(nu));
+
+    // links from the neighbours to the new unitig (:446-461); copies, because a neighbour may be the new unitig's own list owner
+    const auto f_next = n->forward_next, f_prev = n->forward_prev, r_next = n->reverse_next, r_prev = n->reverse_prev;
+    for (auto& u : f_next) (u.strand ? u.unitig->forward_prev : u.unitig->reverse_prev).push_back(UnitigStrand{n, strand::FORWARD});
+    for (auto& u : f_prev) (u.strand ? u.unitig->forward_next : u.unitig->reverse_next).push_back(UnitigStrand{n, strand::FORWARD});
+    for (auto& u : r_next) (u.strand ? u.unitig->forward_prev : u.unitig->reverse_prev).push_back(UnitigStrand{n, strand::REVERSE});
+    for (auto& u : r_prev) (u.strand ? u.unitig->forward_next : u.unitig->reverse_next).push_back(UnitigStrand{n, strand::REVERSE});
+
+    if (end_to_start) {   // :464-470
+        n->forward_next.push_back(UnitigStrand{n, strand::FORWARD}); n->forward_prev.push_back(UnitigStrand{n, strand::FORWARD});
+        n->reverse_next.push_back(UnitigStrand{n, strand::REVERSE}); n->reverse_prev.push_back(UnitigStrand{n, strand::REVERSE});
+    }
+    if (start_flip) { n->reverse_next.push_back(UnitigStrand{n, strand::FORWARD}); n->forward_prev.push_back(UnitigStrand{n, strand::REVERSE}); }
+    if (end_flip) { n->forward_next.push_back(UnitigStrand{n, strand::REVERSE}); n->reverse_prev.push_back(UnitigStrand{n, strand::FORWARD}); }
+
+    std::unordered_set<uint32_t> path_numbers;   // :485-486
+    for (auto& p : path) path_numbers.insert(p.number());
+    std::vector<std::unique_ptr<Unitig>> kept;
+    for (auto& u : graph.unitigs) { if (path_numbers.count(u->number)) graph.retired.push_back(std::move(u)); else kept.push_back(std::move(u)); }
+    graph.unitigs.swap(kept);
+}
+
+void merge_linear_paths(UnitigGraph& graph, const std::vector<Sequence>& seqs) {   // :315-371
+    std::unordered_set<uint32_t> fixed_starts, fixed_ends;
+    merge_fixed_sets(graph, seqs, fixed_starts, fixed_ends);
+    std::unordered_set<uint32_t> already_used;
+    std::vector<std::vector<UnitigStrand>> merge_paths;
+    for (auto& up : graph.unitigs) {
+        Unitig* unitig = up.get();
+        for (bool unitig_strand : {strand::FORWARD, strand::REVERSE}) {
+            if (already_used.count(unitig->number)) continue;
+            const auto inputs = unitig_strand ? get_exclusive_inputs(unitig) : get_exclusive_outputs(unitig);
+            if (inputs.size() == 1 && !cannot_merge_start(unitig->number, unitig_strand, fixed_starts, fixed_ends)) continue;
+            std::vector<UnitigStrand> current{UnitigStrand{unitig, unitig_strand}};
+            already_used.insert(unitig->number);
+            for (;;) {
+                const UnitigStrand u = current.back();
+                if (cannot_merge_end(u.number(), u.strand, fixed_starts, fixed_ends)) break;
+                auto outputs = u.strand ? get_exclusive_outputs(u.unitig) : get_exclusive_inputs(u.unitig);
+                if (outputs.size() != 1) break;
+                UnitigStrand output = outputs[0];
+                if (!u.strand) output.strand = !output.strand;
+                if (already_used.count(output.number())) break;
+                if (cannot_merge_start(output.number(), output.strand, fixed_starts, fixed_ends)) break;
+                current.push_back(output);
+                already_used.insert(output.number());
+            }
+            if (current.size() > 1) merge_paths.push_back(current);
+        }
+    }
+    uint32_t new_number = graph.max_unitig_number();
+    for (auto& path : merge_paths) merge_path(graph, path, ++new_number);
+    graph.delete_dangling_links();
+    graph.build_unitig_index();
+    graph.check_links();
 }
 
 // ---------------------------------------------------------------------------------------------

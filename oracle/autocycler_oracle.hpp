@@ -121,9 +121,12 @@ private:
 struct Unitig;
 struct UnitigStrand { Unitig* unitig; bool strand; uint32_t number() const; };
 
+enum class UnitigType { Anchor, Bridge, Consentig, Other };   // unitig.rs:385-392 (default Other)
+
 // unitig.rs:30-248
 struct Unitig {
     uint32_t number = 0;
+    UnitigType unitig_type = UnitigType::Other;
     std::deque<Kmer*> forward_kmers, reverse_kmers;
     std::string forward_seq, reverse_seq;
     double depth = 0.0;
@@ -163,6 +166,13 @@ public:
     std::pair<size_t, size_t> link_count() const;
     bool link_exists(uint32_t a, bool as, uint32_t b, bool bs) const;
     bool link_exists_prev(uint32_t a, bool as, uint32_t b, bool bs) const;
+    void delete_dangling_links();                                           // unitig_graph.rs:547-564
+    uint32_t max_unitig_number() const;                                     // unitig_graph.rs:901-903
+    std::vector<std::vector<uint32_t>> connected_components() const;        // unitig_graph.rs:905-947
+    bool component_is_circular_loop(const std::vector<uint32_t>& component) const;   // unitig_graph.rs:949-967
+    // Unitigs dropped from `unitigs` stay alive here until the graph dies: the reference holds them through Rc, and
+    // links to them are still walked (by number) until delete_dangling_links has run.
+    std::vector<std::unique_ptr<Unitig>> retired;
 
     // stages of from_kmer_graph, public so tests can inspect the pre-renumber ("seed order") state
     void build_unitigs_from_kmer_graph(KmerGraph& kg);
@@ -182,6 +192,11 @@ std::vector<UnitigStrand> get_exclusive_inputs(const Unitig* u);
 std::vector<UnitigStrand> get_exclusive_outputs(const Unitig* u);
 std::string get_common_start_seq(const std::vector<UnitigStrand>& unitigs);
 std::string get_common_end_seq(const std::vector<UnitigStrand>& unitigs);
+// graph_simplification.rs:315-526
+void merge_linear_paths(UnitigGraph& graph, const std::vector<Sequence>& seqs);
+void merge_fixed_sets(const UnitigGraph& graph, const std::vector<Sequence>& seqs, std::unordered_set<uint32_t>& fixed_starts,
+                      std::unordered_set<uint32_t>& fixed_ends);           // the two sets merge_linear_paths works from (:330-331)
+std::string merge_unitig_seqs(const std::vector<UnitigStrand>& path);      // :490-500
 
 // decompress.rs:83-114
 void save_original_seqs_to_dir(const std::string& out_dir, const UnitigGraph& g, const std::vector<Sequence>& seqs);

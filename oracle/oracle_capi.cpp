@@ -182,6 +182,32 @@ int orc_decompress(const char* gfa_text, const char* out_dir) {
     ORC_CATCH(1)
 }
 
+// graph_simplification.rs:743-803: from_gfa_lines, merge_linear_paths (with or without the paths), save again
+char* orc_gfa_merge_linear_paths(const char* gfa_text, int use_paths) {
+    ORC_TRY
+    auto r = UnitigGraph::from_gfa_lines(split_lines(gfa_text));
+    std::vector<Sequence> none;
+    merge_linear_paths(r.first, use_paths ? r.second : none);
+    return dup_out(r.first.gfa_text(use_paths ? r.second : none));   // without the paths the merged graph no longer carries them
+    ORC_CATCH(nullptr)
+}
+
+// graph_simplification.rs:702-707: the fixed starts / ends merge_linear_paths works from, "s s s\ne e e\n" ascending
+char* orc_gfa_merge_fixed_sets(const char* gfa_text) {
+    ORC_TRY
+    auto r = UnitigGraph::from_gfa_lines(split_lines(gfa_text));
+    std::unordered_set<uint32_t> fs, fe;
+    merge_fixed_sets(r.first, r.second, fs, fe);
+    std::string out;
+    for (auto* set : {&fs, &fe}) {
+        std::vector<uint32_t> v(set->begin(), set->end()); std::sort(v.begin(), v.end());
+        for (size_t i = 0; i < v.size(); ++i) { if (i) out += ' '; out += std::to_string(v[i]); }
+        out += '\n';
+    }
+    return dup_out(out);
+    ORC_CATCH(nullptr)
+}
+
 // graph_simplification.rs:627-671: from_gfa_lines, optionally simplify_structure, dump "number\tseq" in graph order
 char* orc_gfa_unitig_seqs(const char* gfa_text, int simplify, int use_paths) {
     ORC_TRY

@@ -39,7 +39,8 @@ def lib():
         for name in ("orc_kmers_sorted", "orc_neighbour_kmers", "orc_find_best_match", "orc_load_sequences",
                      "orc_compress_dir", "orc_compress_seqs", "orc_gfa_roundtrip", "orc_gfa_unitig_seqs",
                      "orc_gfa_exclusive", "orc_gfa_common_seq", "orc_unitig_shift", "orc_unitig_from_kmers",
-                     "orc_position_display", "orc_reverse_complement"):
+                     "orc_position_display", "orc_reverse_complement", "orc_gfa_merge_linear_paths",
+                     "orc_gfa_merge_fixed_sets"):
             getattr(_lib, name).restype = C.c_void_p
     return _lib
 
@@ -109,6 +110,15 @@ def gfa_roundtrip(gfa_text):
 def decompress(gfa_text, out_dir):
     if lib().orc_decompress(gfa_text.encode(), out_dir.encode()) != 0:
         raise OracleError(lib().orc_last_error().decode())
+
+
+def gfa_merge_linear_paths(gfa_text, use_paths=True):
+    return _take(lib().orc_gfa_merge_linear_paths(gfa_text.encode(), int(use_paths)))
+
+
+def gfa_merge_fixed_sets(gfa_text):
+    out = _take(lib().orc_gfa_merge_fixed_sets(gfa_text.encode())).split("\n")
+    return [int(x) for x in out[0].split()], [int(x) for x in out[1].split()]
 
 
 def gfa_unitig_seqs(gfa_text, simplify=False, use_paths=False):

@@ -151,6 +151,41 @@ def test_simplify_structure_2(golden_dir):  # graph_simplification.rs:656-671
     assert after == ["CACCGCTGCGCTCGCTTCGCTCTAT", "CG", "G"]
 
 
+def _merged(golden_dir, n):
+    text = o.gfa_merge_linear_paths(gfa(golden_dir, n))
+    segs = {int(l.split("\t")[1]): l.split("\t")[2] for l in text.splitlines() if l[0] == "S"}
+    links = sorted(tuple(l.split("\t")[1:5]) for l in text.splitlines() if l[0] == "L")
+    return segs, links
+
+
+def test_can_merge(golden_dir):  # graph_simplification.rs:701-740
+    starts, ends = o.gfa_merge_fixed_sets(gfa(golden_dir, 14))
+    assert starts == [5, 8, 12, 19, 22]
+    assert ends == [8, 17, 19, 22, 37]
+
+
+def test_merge_linear_paths_1(golden_dir):  # graph_simplification.rs:742-764
+    segs, links = _merged(golden_dir, 3)
+    assert segs == {8: "TTCGCTGCGCTCGCTTCGCTTTTGCACAGCGACGACGGCATGCCTGAATCGCCTA", 9: "GCTCGGCTCGATGGTTCG", 10: "TACTTGTAAGGC"}
+    assert links == sorted([("8", "+", "9", "+"), ("9", "-", "8", "-"), ("9", "+", "9", "-"), ("8", "+", "10", "+"),
+                            ("10", "-", "8", "-"), ("10", "+", "10", "+"), ("10", "-", "10", "-")])
+
+
+def test_merge_linear_paths_2(golden_dir):  # graph_simplification.rs:766-783
+    segs, links = _merged(golden_dir, 4)
+    assert segs == {6: "ACGACTACGAGCACGAGTCGTCGTCGTAACTGACT", 7: "GCTCGGTG"}
+    assert links == sorted([("6", "+", "6", "+"), ("6", "-", "6", "-"), ("7", "+", "7", "+"), ("7", "-", "7", "-")])
+
+
+def test_merge_linear_paths_3(golden_dir):  # graph_simplification.rs:785-793
+    segs, _ = _merged(golden_dir, 5)
+    assert len(segs) == 5 and segs[7] == "AAATGCGACTGTG"
+
+
+def test_merge_linear_paths_4(golden_dir):  # graph_simplification.rs:795-801
+    assert len(_merged(golden_dir, 14)[0]) == 11
+
+
 @pytest.mark.parametrize("n", range(1, 15))
 def test_reference_gfa_fixtures_load_and_check_links(golden_dir, n):  # test_gfa.rs:15-287 via from_gfa_lines
     text = gfa(golden_dir, n)
