@@ -55,7 +55,7 @@ class AcTimings(C.Structure):
 
 
 EXPORTS = ["ac_last_error", "ac_version", "ac_create", "ac_destroy", "ac_add_sequence", "ac_clear_sequences", "ac_upload",
-           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
+           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
            "ac_timings_get", "ac_compress_dir", "ac_load_sequences", "ac_sequence_get",
            "ac_build_local", "ac_entries_count", "ac_entries_export", "ac_entries_merge", "ac_runs_local", "ac_runs_export",
            "ac_runs_import", "ac_build_finish", "ac_gfa_data"]
@@ -83,6 +83,7 @@ def load_library(path=None):
     for name in ("ac_upload", "ac_build", "ac_simplify"):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.ac_merge_linear_paths.argtypes = [C.c_void_p, C.c_int]
+    lib.ac_sequence_reconstruct.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.ac_counts_get.argtypes = [C.c_void_p, C.POINTER(AcCounts)]
     lib.ac_unitigs_copy.argtypes = [C.c_void_p, C.POINTER(AcUnitigs)]
     lib.ac_path_copy.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), C.c_uint64, C.POINTER(C.c_uint64)]
@@ -251,6 +252,13 @@ class UnitigGraph:
         n = C.c_uint64(); ptr = C.c_void_p()
         self._h.check(self._h.lib.ac_gfa_data(self._h.ptr, C.byref(ptr), C.byref(n)))
         return memoryview((C.c_char * n.value).from_address(ptr.value)) if n.value else memoryview(b"")
+
+    def reconstruct_original_sequence(self, index):   # unitig_graph.rs:383-388, by position in the sequence list
+        n = C.c_uint64()
+        self._h.check(self._h.lib.ac_sequence_reconstruct(self._h.ptr, index, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(max(1, n.value))
+        self._h.check(self._h.lib.ac_sequence_reconstruct(self._h.ptr, index, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value].decode()
 
     def save_gfa(self, gfa_filename, sequences=None, use_other_colour=False):   # unitig_graph.rs:317-331
         with open(gfa_filename, "wb") as f:

@@ -98,8 +98,17 @@ inline void ac_host_free(void* p) { if (p) cudaFreeHost(p); }
 // feeds bench.py's "gpu_launches".
 extern unsigned long long g_ac_kernel_launches;
 
+// The trip count is the same for every lane of a warp and the lanes meet again after each unit: bodies with data-dependent
+// latency (hash probes) otherwise let the lanes drift into different iterations and the warp issues every instruction for a
+// third of its lanes (ncu: 12 of 32 threads per instruction before this, profiles/r1e_summary.md).
 template <class Body> __global__ void __launch_bounds__(256) ac_body_kernel(const Body body, uint64_t n) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) body(i);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += stride) {
+        const uint64_t i = base + lane;
+        if (i < n) body(i);
+        __syncwarp();
+    }
 }
 
 template <class Body> inline void ac_launch(const char* name, AcStream* st, const Body& body, uint64_t n) {

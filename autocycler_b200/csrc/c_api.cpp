@@ -399,6 +399,30 @@ int ac_sequence_get(const ac_handle* h, uint64_t index, uint16_t* seq_id, uint64
     return AC_OK;
 }
 
+// reconstruct_original_sequence / get_sequence_from_path (unitig_graph.rs:383-400): the unitig strands of the sequence's
+// path, concatenated; equals the input contig (tests.rs:114-127).
+int ac_sequence_reconstruct(const ac_handle* h, uint64_t index, char* out, uint64_t cap, uint64_t* length) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    AC_GUARD_BEGIN
+    if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_sequence_reconstruct");
+    if (index >= h->seqs.size()) return set_error(h, AC_EINVAL, "no such sequence");
+    const HostGraph& g = h->graph;
+    uint64_t total = 0;
+    for (uint64_t x = g.path_off[index]; x < g.path_off[index + 1]; ++x) total += g.rec[us_index(g.path[x])].len;
+    if (length) *length = total;
+    if (!out) return AC_OK;
+    if (cap < total) return set_error(h, AC_ERANGE, "buffer too small");
+    char* p = out;
+    for (uint64_t x = g.path_off[index]; x < g.path_off[index + 1]; ++x) {
+        const UStrand s = g.path[x]; const uint32_t n = g.rec[us_index(s)].len; const char* src = g.seq_ptr(us_index(s));
+        if (!us_reverse(s)) memcpy(p, src, n);
+        else for (uint32_t j = 0; j < n; ++j) { const char b = src[n - 1 - j]; p[j] = b == 'A' ? 'T' : b == 'C' ? 'G' : b == 'G' ? 'C' : b == 'T' ? 'A' : b; }
+        p += n;
+    }
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
 int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint32_t k, uint32_t max_contigs, uint32_t threads,
                     int32_t device, int32_t verbose) {
     if (!assemblies_dir || !autocycler_dir) return set_error(nullptr, AC_EINVAL, "null argument");

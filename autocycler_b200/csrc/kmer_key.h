@@ -91,6 +91,10 @@ template <int W> AC_HD uint32_t key_base(const Key<W>& key, uint32_t i, const KP
 template <int W> AC_HD bool key_is_canonical(const Key<W>& key, const KParams& p) { return key_base(key, p.h, p) < 2; }
 
 AC_HD uint64_t rev2_64(uint64_t x) {   // reverse the order of the 32 2-bit groups
+#ifdef __CUDA_ARCH__
+    x = __brevll(x);                                                                  // all 64 bits reversed: the groups are in place, their two bits swapped
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+#endif
     x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
     x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
     x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);

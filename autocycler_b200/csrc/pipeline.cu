@@ -232,7 +232,8 @@ template <int W> struct InsertLaneBody {
         si = 0;
         if ((int)(threadIdx.x & 31) == leader) si = find_seq(b.t.seqs, b.t.n_seqs, g);
         si = __shfl_sync(mask, si, leader);
-        while (si + 1 < b.t.n_seqs && b.t.seqs[si + 1].start <= g) ++si;
+        if (b.t.seqs[si].start > g) si = find_seq(b.t.seqs, b.t.n_seqs, g);   // lanes that met here from different iterations
+        else while (si + 1 < b.t.n_seqs && b.t.seqs[si + 1].start <= g) ++si;
 #else
         si = find_seq(b.t.seqs, b.t.n_seqs, g);
 #endif

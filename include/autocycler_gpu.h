@@ -138,6 +138,10 @@ int ac_load_sequences(ac_handle* h, const char* assemblies_dir, uint32_t max_con
 int ac_sequence_get(const ac_handle* h, uint64_t index, uint16_t* seq_id, uint64_t* length,
                     char* fwd_padded, uint64_t cap_fwd, char* filename, uint64_t cap_fn, char* header, uint64_t cap_hd);
 
+/* reconstruct_original_sequence (unitig_graph.rs:383-400; decompress.rs:83-105 writes these out): the sequence spelled by
+ * the path of loaded/added sequence `index` through the current graph.  `out` may be null to query `length` only. */
+int ac_sequence_reconstruct(const ac_handle* h, uint64_t index, char* out, uint64_t cap, uint64_t* length);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,8 +47,12 @@ def check_case(lib, files, k, tmpdir=None):
         assert (got["after"].n_unitigs, got["after"].n_links, got["after"].total_length) == \
                (st.unitigs_after, st.links_after, st.length_after)
         assert got["gfa"] == expected, "GFA differs from the oracle"
+        originals = [s.forward_seq[k // 2: len(s.forward_seq) - k // 2] for s in got["seqs"]]
+        # tests.rs:114-127: every input contig comes back from its path (end repair only ever touches the dots)
+        assert [got["graph"].reconstruct_original_sequence(i) for i in range(len(originals))] == originals
         # what every downstream command does next (cluster.rs:804): merge_linear_paths on the loaded graph
         api.merge_linear_paths(got["graph"], got["seqs"])
         got["merged_gfa"] = got["graph"].gfa_bytes().decode()
         assert got["merged_gfa"] == o.gfa_merge_linear_paths(expected), "merged GFA differs from the oracle"
+        assert [got["graph"].reconstruct_original_sequence(i) for i in range(len(originals))] == originals
         return got
