@@ -84,8 +84,15 @@ void HostGraph::build(const PipelineResult& r, const std::vector<HostSeq>& seqs,
     prof.adopt = now_ms() - t0;
 
     order.resize(U);
-    for (uint32_t s = 0; s < U; ++s) order[s] = s;
-    renumber();
+    if (r.order) {                            // sorted on the device while the sequences were still in HBM
+        const double t1 = now_ms();
+        memcpy(order.data(), r.order, (size_t)U * 4);
+        for (uint32_t n = 0; n < U; ++n) number[order[n]] = n + 1;
+        prof.renumber += now_ms() - t1;
+    } else {
+        for (uint32_t s = 0; s < U; ++s) order[s] = s;
+        renumber();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -611,8 +611,8 @@ struct SeedLess {
     }
 };
 #define AC_SORT_LEAF 8
-struct SortLeafBody {   // insertion sort of AC_SORT_LEAF consecutive unitigs: the first three merge levels in one launch
-    SeedLess less; uint32_t n; uint32_t* idx;
+template <class Less> struct SortLeafBody {   // insertion sort of AC_SORT_LEAF consecutive unitigs: the first three merge levels in one launch
+    Less less; uint32_t n; uint32_t* idx;
     AC_D void operator()(uint64_t c) const {
         const uint32_t a = (uint32_t)c * AC_SORT_LEAF, b = a + AC_SORT_LEAF < n ? a + AC_SORT_LEAF : n;
         uint32_t v[AC_SORT_LEAF];
@@ -624,8 +624,8 @@ struct SortLeafBody {   // insertion sort of AC_SORT_LEAF consecutive unitigs: t
         for (uint32_t x = a; x < b; ++x) idx[x] = v[x - a];
     }
 };
-struct MergePassBody {
-    SeedLess less; uint32_t n, width; const uint32_t* in; uint32_t* out;
+template <class Less> struct MergePassBody {
+    Less less; uint32_t n, width; const uint32_t* in; uint32_t* out;
     AC_D void operator()(uint64_t i) const {
         const uint32_t me = in[i];
         const uint32_t run = (uint32_t)i / width, pair_start = (run & ~1u) * width, run_start = run * width;
@@ -641,6 +641,31 @@ struct MergePassBody {
             if (before) lo = mid + 1; else hi = mid;
         }
         out[pair_start + ((uint32_t)i - run_start) + (lo - base)] = me;
+    }
+};
+
+// renumber_unitigs (unitig_graph.rs:295-315) for the graph as built: length descending, sequence ascending, depth descending,
+// ties in creation (seed) order because the reference's sort is stable.  The first 8 bases ride along as a big-endian word.
+struct NumberKeyBody {
+    const UnitigRec* rec; const char* arena; uint64_t* prefix;
+    AC_D void operator()(uint64_t s) const {
+        const unsigned char* q = (const unsigned char*)(arena + rec[s].seq_off);
+        const uint32_t m = rec[s].len < 8 ? rec[s].len : 8;
+        uint64_t v = 0;
+        for (uint32_t i = 0; i < m; ++i) v |= (uint64_t)q[i] << (56 - 8 * i);
+        prefix[s] = v;
+    }
+};
+struct NumberLess {
+    const UnitigRec* rec; const uint32_t* depth; const char* arena; const uint64_t* prefix;
+    AC_D bool operator()(uint32_t a, uint32_t b) const {
+        const uint32_t la = rec[a].len, lb = rec[b].len;
+        if (la != lb) return la > lb;
+        if (prefix[a] != prefix[b]) return prefix[a] < prefix[b];
+        const char* x = arena + rec[a].seq_off; const char* y = arena + rec[b].seq_off;
+        for (uint32_t i = 8; i < la; ++i) if (x[i] != y[i]) return (unsigned char)x[i] < (unsigned char)y[i];
+        if (depth[a] != depth[b]) return depth[a] > depth[b];
+        return a < b;
     }
 };
 
@@ -890,10 +915,10 @@ struct DevicePipeline::Impl {
     DevBuf ascii, packed, seqs, slots, pos_slot, flags8, bmask, bcount, boff, counters, uid_rep, slot_unitig;
     DevBuf run_start, run_len, run_uk, run_dir, is_rep, rep_idx, run_unitig, unitigs, nchunks, chunk_off, partial, link_count, links;
     DevBuf scan_tmp[4];
-    DevBuf sort_a, sort_b, rank, d_len, d_depth, need, d_seq_off, d_arena, d_min_fpos, d_min_rpos;
+    DevBuf sort_a, sort_b, num_prefix, rank, d_len, d_depth, need, d_seq_off, d_arena, d_min_fpos, d_min_rpos;
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
-    PinBuf h_rec, h_depth, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
+    PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
     cudaEvent_t ev[20];
 #endif
@@ -1258,9 +1283,9 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     sort_a.ensure((size_t)U * 4); sort_b.ensure((size_t)U * 4);
     uint32_t* idx_in = sort_a.as<uint32_t>(); uint32_t* idx_out = sort_b.as<uint32_t>();
     const SeedLess seed_less{unitigs.as<DeviceUnitig>(), W};
-    ac_launch("sort_leaf", &stream, SortLeafBody{seed_less, U, idx_in}, ((uint64_t)U + AC_SORT_LEAF - 1) / AC_SORT_LEAF);
+    ac_launch("sort_leaf", &stream, SortLeafBody<SeedLess>{seed_less, U, idx_in}, ((uint64_t)U + AC_SORT_LEAF - 1) / AC_SORT_LEAF);
     for (uint64_t width = AC_SORT_LEAF; width < U; width *= 2) {
-        ac_launch("merge_pass", &stream, MergePassBody{seed_less, U, (uint32_t)width, idx_in, idx_out}, U);
+        ac_launch("merge_pass", &stream, MergePassBody<SeedLess>{seed_less, U, (uint32_t)width, idx_in, idx_out}, U);
         std::swap(idx_in, idx_out);
     }
     const uint32_t* perm = idx_in;
@@ -1301,6 +1326,16 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     d_rec.ensure((size_t)U * sizeof(UnitigRec));
     ac_launch("pack_rec", &stream, PackRecBody{d_seq_off.as<uint64_t>(), d_len.as<uint32_t>(), d_min_fpos.as<uint32_t>(), d_min_rpos.as<uint32_t>(), d_rec.as<UnitigRec>()}, U);
     ac_launch("path_off", &stream, PathOffBody{seqs.as<SeqInfo>(), n_seqs, run_start.as<uint64_t>(), n_runs, d_path_off.as<uint64_t>()}, (uint64_t)n_seqs + 1);
+    // the unitig numbers of the freshly built graph (the rank buffer is free again and holds the 8-base prefixes)
+    num_prefix.ensure((size_t)U * 8);
+    ac_launch("number_key", &stream, NumberKeyBody{d_rec.as<UnitigRec>(), d_arena.as<char>(), num_prefix.as<uint64_t>()}, U);
+    const NumberLess number_less{d_rec.as<UnitigRec>(), d_depth.as<uint32_t>(), d_arena.as<char>(), num_prefix.as<uint64_t>()};
+    uint32_t* ord_in = sort_a.as<uint32_t>(); uint32_t* ord_out = sort_b.as<uint32_t>();
+    ac_launch("number_leaf", &stream, SortLeafBody<NumberLess>{number_less, U, ord_in}, ((uint64_t)U + AC_SORT_LEAF - 1) / AC_SORT_LEAF);
+    for (uint64_t width = AC_SORT_LEAF; width < U; width *= 2) {
+        ac_launch("number_merge", &stream, MergePassBody<NumberLess>{number_less, U, (uint32_t)width, ord_in, ord_out}, U);
+        std::swap(ord_in, ord_out);
+    }
     mark(11);
 
     // ---- results to the host (pinned) ----
@@ -1311,6 +1346,8 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     uint64_t d2h = 0;
     auto pull = [&](PinBuf& dst, DevBuf& src, size_t bytes) { if (bytes) ac_d2h(dst.p, src.p, bytes, &stream); d2h += bytes; };
     pull(h_rec, d_rec, (size_t)U * sizeof(UnitigRec)); pull(h_depth, d_depth, (size_t)U * 4); pull(h_arena, d_arena, arena_bytes);
+    h_order.ensure((size_t)U * 4 + 4);
+    if (U) { ac_d2h(h_order.p, ord_in, (size_t)U * 4, &stream); d2h += (size_t)U * 4; }
     pull(h_next_off, d_next_off, ((size_t)n_strands + 1) * 4); pull(h_prev_off, d_prev_off, ((size_t)n_strands + 1) * 4);
     pull(h_next, d_next, n_links * 4); pull(h_prev, d_prev, n_links * 4); pull(h_path, d_path, n_runs * 4); pull(h_path_off, d_path_off, ((size_t)n_seqs + 1) * 8);
     if (keep_positions) {
@@ -1322,7 +1359,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     mark(12);
     ac_sync(&stream);
     out.n_unitigs = U; out.n_runs = n_runs; out.n_seqs = n_seqs; out.n_links = n_links;
-    out.rec = h_rec.as<UnitigRec>(); out.depth = h_depth.as<uint32_t>();
+    out.rec = h_rec.as<UnitigRec>(); out.depth = h_depth.as<uint32_t>(); out.order = h_order.as<uint32_t>();
     out.arena = h_arena.as<char>(); out.arena_used = arena_bytes; out.arena_cap = arena_cap;
     out.next_off = h_next_off.as<uint32_t>(); out.next = h_next.as<UStrand>(); out.prev_off = h_prev_off.as<uint32_t>(); out.prev = h_prev.as<UStrand>();
     out.path_off = h_path_off.as<uint64_t>(); out.path = h_path.as<UStrand>();

@@ -56,6 +56,7 @@ struct PipelineResult {
     uint32_t n_seqs = 0;
     UnitigRec* rec = nullptr;                  // [U]
     uint32_t* depth = nullptr;                 // [U]
+    uint32_t* order = nullptr;                 // [U] order[n-1] = seed index of unitig number n (renumber_unitigs, unitig_graph.rs:295-315)
     char* arena = nullptr; uint64_t arena_used = 0, arena_cap = 0;
     uint32_t* next_off = nullptr;              // [2U+1] CSR over strands: forward_next / reverse_next in the reference's push order
     UStrand* next = nullptr;
