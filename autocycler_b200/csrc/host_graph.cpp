@@ -6,8 +6,12 @@
 #include <charconv>
 #include <chrono>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
+#include <type_traits>
+#include <unistd.h>
 
 namespace {
 inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -25,21 +29,87 @@ unsigned host_threads() {
     return n;
 }
 
+// Persistent worker threads for parallel_tasks: the host stages issue a few dozen short parallel regions per graph, and
+// spawning + joining 15 threads for each of them costs more than several of the regions themselves.  Workers spin briefly
+// after a job (the next region usually follows within microseconds) and then sleep on a condition variable.
+class WorkerPool {
+public:
+    static WorkerPool& get() { static WorkerPool pool; return pool; }
+    // Runs job(ctx) on the caller and on `helpers` workers; returns when all of them have left the job.
+    void run(unsigned helpers, void (*job)(void*), void* ctx) {
+        std::lock_guard<std::mutex> one_job_at_a_time(entry);
+        {
+            std::lock_guard<std::mutex> lk(m);
+            if (owner != getpid()) { new std::vector<std::thread>(std::move(workers)); workers.clear(); owner = getpid(); }   // after fork(): the threads stayed behind
+            while (workers.size() < helpers) { const unsigned id = (unsigned)workers.size(); workers.emplace_back([this, id] { loop(id); }); }
+            fn = job; arg = ctx; wanted = helpers;
+            pending.store(helpers, std::memory_order_relaxed);
+            generation.fetch_add(1, std::memory_order_release);
+        }
+        cv.notify_all();
+        job(ctx);
+        for (unsigned spins = 0; pending.load(std::memory_order_acquire) != 0; ++spins) { if (spins > 2000) std::this_thread::yield(); }
+    }
+    ~WorkerPool() {
+        { std::lock_guard<std::mutex> lk(m); stopping = true; generation.fetch_add(1, std::memory_order_release); }
+        cv.notify_all();
+        if (owner == getpid()) for (auto& w : workers) w.join();
+        else new std::vector<std::thread>(std::move(workers));
+    }
+private:
+    void loop(unsigned id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const auto spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(200);
+            while (generation.load(std::memory_order_acquire) == seen && std::chrono::steady_clock::now() < spin_until) {}
+            void (*job)(void*); void* ctx; bool mine;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return generation.load(std::memory_order_relaxed) != seen; });
+                if (stopping) return;
+                seen = generation.load(std::memory_order_relaxed);
+                job = fn; ctx = arg; mine = id < wanted;
+            }
+            if (!mine) continue;
+            job(ctx);
+            pending.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::mutex entry, m;
+    std::condition_variable cv;
+    std::vector<std::thread> workers;
+    std::atomic<uint64_t> generation{0};
+    std::atomic<unsigned> pending{0};
+    void (*fn)(void*) = nullptr; void* arg = nullptr; unsigned wanted = 0; bool stopping = false;
+    pid_t owner = getpid();
+};
+
 // Runs fn(task) for task in [0, n_tasks) on up to host_threads() threads (dynamic scheduling).
 template <class F> void parallel_tasks(size_t n_tasks, F&& fn) {
-    const unsigned nt = (unsigned)std::min<size_t>(host_threads(), n_tasks);
+    static thread_local bool inside = false;
+    const unsigned nt = inside ? 1u : (unsigned)std::min<size_t>(host_threads(), n_tasks);
     if (nt <= 1) { for (size_t t = 0; t < n_tasks; ++t) fn(t); return; }
-    std::atomic<size_t> next{0};
-    std::exception_ptr err = nullptr; std::atomic<bool> failed{false};
-    auto work = [&]() {
-        try { for (size_t t; (t = next.fetch_add(1)) < n_tasks;) fn(t); }
-        catch (...) { if (!failed.exchange(true)) err = std::current_exception(); }
+    struct Job {
+        std::remove_reference_t<F>* fn; size_t n_tasks; std::atomic<size_t> next{0};
+        std::exception_ptr err = nullptr; std::atomic<bool> failed{false};
+    } job;
+    job.fn = &fn; job.n_tasks = n_tasks;
+    auto work = [](void* p) {
+        Job& j = *static_cast<Job*>(p);
+        inside = true;
+        try { for (size_t t; (t = j.next.fetch_add(1)) < j.n_tasks;) (*j.fn)(t); }
+        catch (...) { if (!j.failed.exchange(true)) j.err = std::current_exception(); }
+        inside = false;
     };
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work);
-    work();
-    for (auto& th : pool) th.join();
-    if (err) std::rethrow_exception(err);
+    static const bool pooled = !(getenv("AC_HOST_POOL") && atoi(getenv("AC_HOST_POOL")) == 0);
+    if (pooled) WorkerPool::get().run(nt - 1, work, &job);
+    else {                                   // one-shot threads (kept for comparison)
+        std::vector<std::thread> once;
+        for (unsigned t = 1; t < nt; ++t) once.emplace_back(work, &job);
+        work(&job);
+        for (auto& th : once) th.join();
+    }
+    if (job.err) std::rethrow_exception(job.err);
 }
 }  // namespace
 

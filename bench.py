@@ -33,6 +33,9 @@ WORKLOADS = {   # BASELINE.json configs (SURVEY.md §8d generator); the default 
 WORKLOAD = WORKLOADS["cfg2"] + ", k=51"
 
 
+INSERT_BODY = "InsertBody" if os.environ.get("AC_INSERT_CHUNKED") else "InsertLaneBody"   # pipeline.cu local_w picks the same way
+
+
 def measured_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/kernel_traffic.json, written by
     profiles/extract_traffic.py from the .ncu-rep): dram__bytes_read.sum + dram__bytes_write.sum.  None if no capture matches."""
@@ -201,9 +204,9 @@ def run_gpu(args):
                 "h2d_bytes_per_step": int(last2[2].h2d_bytes), "d2h_bytes_per_step": int(last2[2].d2h_bytes)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "InsertBody<%d> (k-mer hash insert)" % W, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": "%s<%d> (k-mer hash insert)" % (INSERT_BODY, W), "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "peak_kind": peak_kind,
-                     "traffic": measured_traffic("InsertBody<%d>:%s:k%d" % (W, args.workload, K)) if world == 1 else None,
+                     "traffic": measured_traffic("%s<%d>:%s:k%d" % (INSERT_BODY, W, args.workload, K)) if world == 1 else None,
                      "algorithmic_bytes_per_window": bytes_per_window, "windows_per_launch": int(own_windows), "kernel_ms": round(insert_ms, 3)},
         "stage_ms": {k2: round(mean(k2), 3) for k2 in ("pack", "insert", "adjacency", "boundaries", "runs", "unitigs", "links", "seed_sort", "emit", "d2h", "device_total",
                                                         "host_graph", "host_simplify", "host_gfa")},
