@@ -41,6 +41,8 @@ inline void ac_sync(AcStream*) {}
 inline void* ac_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 inline void ac_host_free(void* p) { free(p); }
 
+template <class Body> inline void ac_launch(const char*, AcStream*, const Body& body, uint64_t n);
+template <class Body> inline void ac_launch_occ(const char* name, AcStream* st, const Body& body, uint64_t n, int) { ac_launch(name, st, body, n); }
 template <class Body> inline void ac_launch(const char*, AcStream*, const Body& body, uint64_t n) {
     for (uint64_t i = 0; i < n; ++i) body(i);
 }
@@ -109,6 +111,32 @@ template <class Body> __global__ void __launch_bounds__(256) ac_body_kernel(cons
         if (i < n) body(i);
         __syncwarp();
     }
+}
+
+// The same loop compiled for a given number of resident 256-thread CTAs per SM (a register budget): latency-bound bodies
+// trade a few spills for more loads in flight.
+template <class Body, int CTAS> __global__ void __launch_bounds__(256, CTAS) ac_body_kernel_occ(const Body body, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += stride) {
+        const uint64_t i = base + lane;
+        if (i < n) body(i);
+        __syncwarp();
+    }
+}
+template <class Body> inline void ac_launch_occ(const char* name, AcStream* st, const Body& body, uint64_t n, int ctas_per_sm) {
+    if (n == 0) return;
+    const int threads = 256;
+    const uint64_t want = (n + threads - 1) / threads, max_blocks = 148ull * (uint64_t)ctas_per_sm * 2;   // two waves of resident CTAs, grid-stride beyond
+    const unsigned blocks = (unsigned)(want < max_blocks ? want : max_blocks);
+    switch (ctas_per_sm) {
+        case 8: ac_body_kernel_occ<Body, 8><<<blocks, threads, 0, st->s>>>(body, n); break;
+        case 6: ac_body_kernel_occ<Body, 6><<<blocks, threads, 0, st->s>>>(body, n); break;
+        default: ac_body_kernel_occ<Body, 5><<<blocks, threads, 0, st->s>>>(body, n); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("launch ") + name + ": " + cudaGetErrorString(e));
+    ++g_ac_kernel_launches;
 }
 
 template <class Body> inline void ac_launch(const char* name, AcStream* st, const Body& body, uint64_t n) {

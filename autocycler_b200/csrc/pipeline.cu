@@ -129,17 +129,18 @@ template <int W> struct InsertBody {
     uint32_t* pos_slot;                 // [total] slot of the window starting at each global coordinate (null in the sampling pass)
     unsigned long long* counters;       // [2*stripe] slots claimed, [2*stripe+1] dotted k-mers claimed, [2*AC_STRIPES] table-overflow flag
     uint64_t sample_mask;               // != 0: the sizing pre-pass, only k-mers whose hash has these bits clear are entered
-    AC_D void insert(const Key<W>& fwd, const Key<W>& rc, uint64_t g, uint64_t fs, uint32_t len, uint32_t obs, uint32_t& claimed, uint32_t& claimed_dotted) const {
-        const bool canon_fwd = key_is_canonical(fwd, p);
+    // Finds the k-mer's slot or claims an empty one.  False: skipped by the sampling mask, or the probe limit was hit.
+    AC_D bool find_or_claim(const Key<W>& fwd, const Key<W>& rc, uint64_t g, uint64_t& slot_out, uint32_t& aux_seen, bool& canon_fwd,
+                            uint32_t& claimed, uint32_t& claimed_dotted) const {
+        canon_fwd = key_is_canonical(fwd, p);
         const Key<W>& canon = canon_fwd ? fwd : rc;
         const uint64_t h = key_hash(canon);
-        if (h & sample_mask) return;
+        if (h & sample_mask) return false;
         const bool dotted = fwd.d != 0;
         const uint64_t mine = make_entry(g, dotted, h);
         uint64_t slot = ac_umul64hi(h, t.cap);
-        uint32_t aux_seen = 0;
         for (uint32_t probes = 0;; ++probes) {
-            if (probes > 8192) { counters[2 * AC_STRIPES] = 1; return; }    // the table was sized too small: the host retries with the safe size
+            if (probes > 8192) { counters[2 * AC_STRIPES] = 1; return false; }    // the table was sized too small: the host retries with the safe size
             const Slot q = ac_ld_16(&t.slots[slot]);      // entry, count and flags in one transaction
             uint64_t e = q.entry; aux_seen = q.aux;
             if (e == AC_EMPTY_ENTRY) {
@@ -155,6 +156,11 @@ template <int W> struct InsertBody {
             }
             if (++slot == t.cap) slot = 0;
         }
+        slot_out = slot;
+        return true;
+    }
+    // Counts the occurrence and records what it tells about the k-mer.
+    AC_D void commit(uint64_t slot, uint32_t aux_seen, bool canon_fwd, uint64_t g, uint64_t fs, uint32_t len, uint32_t obs) const {
         ac_atomic_add(&t.slots[slot].count, 1u);
         // Kmer::first_position (kmer_graph.rs:57-60): position 0 of the forward strand is window 0; position 0
         // of the reverse strand is the reverse complement of the last window (kmer_graph.rs:103-108).
@@ -163,6 +169,10 @@ template <int W> struct InsertBody {
         if (fs + 1 == len) bits |= canon_fwd ? AC_AUX_FIRST_RC : AC_AUX_FIRST_CANON;
         if (bits && (aux_seen & bits) != bits) ac_atomic_or(&t.slots[slot].aux, bits);   // usually already there (aux_seen may be stale: then the OR is merely redundant)
         if (pos_slot) pos_slot[g] = (uint32_t)slot;
+    }
+    AC_D void insert(const Key<W>& fwd, const Key<W>& rc, uint64_t g, uint64_t fs, uint32_t len, uint32_t obs, uint32_t& claimed, uint32_t& claimed_dotted) const {
+        uint64_t slot = 0; uint32_t aux_seen = 0; bool canon_fwd = false;
+        if (find_or_claim(fwd, rc, g, slot, aux_seen, canon_fwd, claimed, claimed_dotted)) commit(slot, aux_seen, canon_fwd, g, fs, len, obs);
     }
     AC_D uint32_t observed(const Key<W>& fwd, const SeqInfo& s, uint64_t g, uint64_t fs) const {
         uint32_t obs = 0;
@@ -223,33 +233,37 @@ template <int W> struct InsertBody {
 // neighbour's longer probe chain across a whole AC_CHUNK of windows.  Costs a key_rc per window instead of a roll.
 template <int W> struct InsertLaneBody {
     InsertBody<W> b;
+    // Launched over a multiple of 32 units so that whole warps enter: the lanes meet once more between the probe (whose
+    // length differs from lane to lane) and the bookkeeping that follows it.
     AC_D void operator()(uint64_t i) const {
         const uint64_t g = b.g_begin + i;
-        uint32_t si;
+        const bool in_range = g < b.g_end;
+        uint32_t si = 0;
 #ifdef __CUDA_ARCH__
-        const unsigned mask = __activemask();
-        const int leader = __ffs(mask) - 1;            // the lowest active lane holds the smallest coordinate
-        si = 0;
-        if ((int)(threadIdx.x & 31) == leader) si = find_seq(b.t.seqs, b.t.n_seqs, g);
-        si = __shfl_sync(mask, si, leader);
-        if (b.t.seqs[si].start > g) si = find_seq(b.t.seqs, b.t.n_seqs, g);   // lanes that met here from different iterations
-        else while (si + 1 < b.t.n_seqs && b.t.seqs[si + 1].start <= g) ++si;
+        if ((threadIdx.x & 31) == 0) si = find_seq(b.t.seqs, b.t.n_seqs, g);     // lane 0 holds the warp's smallest coordinate
+        si = __shfl_sync(0xFFFFFFFFu, si, 0);
+        while (si + 1 < b.t.n_seqs && b.t.seqs[si + 1].start <= g) ++si;
 #else
         si = find_seq(b.t.seqs, b.t.n_seqs, g);
 #endif
         const SeqInfo s = b.t.seqs[si];
         const uint64_t fs = g - s.start;
-        uint32_t claimed = 0, claimed_dotted = 0;
-        if (fs < s.len) {                                // else: one of the k-1 padded bytes that start no window
+        uint32_t claimed = 0, claimed_dotted = 0, aux_seen = 0, obs = 0;
+        uint64_t slot = 0; bool canon_fwd = false, found = false;
+        if (in_range && fs < s.len) {                    // else: past the end, or one of the k-1 padded bytes that start no window
             Key<W> fwd = fetch_codes<W>(b.t.packed, g, b.p);
             fwd.d = window_dots(s, fs, b.p.k);
             const Key<W> rc = key_rc(fwd, b.p);
-            b.insert(fwd, rc, g, fs, s.len, b.observed(fwd, s, g, fs), claimed, claimed_dotted);
+            obs = b.observed(fwd, s, g, fs);
+            found = b.find_or_claim(fwd, rc, g, slot, aux_seen, canon_fwd, claimed, claimed_dotted);
         }
 #ifdef __CUDA_ARCH__
-        const unsigned again = __activemask();
-        const uint32_t n_claimed = __reduce_add_sync(again, claimed), n_dotted = __reduce_add_sync(again, claimed_dotted);
-        if ((int)(threadIdx.x & 31) == __ffs(again) - 1) {
+        __syncwarp();
+#endif
+        if (found) b.commit(slot, aux_seen, canon_fwd, g, fs, s.len, obs);
+#ifdef __CUDA_ARCH__
+        const uint32_t n_claimed = __reduce_add_sync(0xFFFFFFFFu, claimed), n_dotted = __reduce_add_sync(0xFFFFFFFFu, claimed_dotted);
+        if ((threadIdx.x & 31) == 0) {
             const uint64_t stripe = (i >> 5) % AC_STRIPES;
             if (n_claimed) ac_atomic_add(&b.counters[2 * stripe], (unsigned long long)n_claimed);
             if (n_dotted) ac_atomic_add(&b.counters[2 * stripe + 1], (unsigned long long)n_dotted);
@@ -915,6 +929,7 @@ struct DevicePipeline::Impl {
     DevBuf ascii, packed, seqs, slots, pos_slot, flags8, bmask, bcount, boff, counters, uid_rep, slot_unitig;
     DevBuf run_start, run_len, run_uk, run_dir, is_rep, rep_idx, run_unitig, unitigs, nchunks, chunk_off, partial, link_count, links;
     DevBuf scan_tmp[4];
+    int insert_occupancy = getenv("AC_INSERT_OCC") ? atoi(getenv("AC_INSERT_OCC")) : 5;   // resident CTAs per SM the insert kernel is compiled for (5, 6 or 8)
     DevBuf sort_a, sort_b, num_prefix, rank, d_len, d_depth, need, d_seq_off, d_arena, d_min_fpos, d_min_rpos;
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
@@ -1151,7 +1166,7 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
         const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
         const InsertBody<W> ins{tv, p, g_begin, g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), 0};
         if (getenv("AC_INSERT_CHUNKED")) ac_launch("insert", &stream, ins, (g_end - g_begin + AC_CHUNK - 1) / AC_CHUNK);
-        else ac_launch("insert", &stream, InsertLaneBody<W>{ins}, g_end - g_begin);
+        else ac_launch_occ("insert", &stream, InsertLaneBody<W>{ins}, (g_end - g_begin + 31) / 32 * 32, insert_occupancy);
         if (cap == safe_cap) break;                      // cannot overflow: one slot and a half per window
         unsigned long long overflow = 0;
         ac_d2h(&overflow, counters.as<unsigned long long>() + 2 * AC_STRIPES, sizeof overflow, &stream); ac_sync(&stream);
