@@ -24,7 +24,7 @@ unsigned host_threads() {
     static const unsigned n = [] {
         unsigned hw = std::thread::hardware_concurrency();
         if (const char* e = getenv("AC_HOST_THREADS")) { int v = atoi(e); if (v > 0) return (unsigned)v; }
-        return hw == 0 ? 4u : (hw > 16 ? 16u : hw);
+        return hw == 0 ? 4u : (hw > 48 ? 48u : hw);   // measured on the 128-core B200 host: cfg4 gains up to 48 threads, cfg2 is flat beyond 16
     }();
     return n;
 }
@@ -83,6 +83,12 @@ private:
     void (*fn)(void*) = nullptr; void* arg = nullptr; unsigned wanted = 0; bool stopping = false;
     pid_t owner = getpid();
 };
+
+// Runs fn() exactly once on each of T threads (the caller and T-1 workers): for loops with their own barriers.
+template <class F> void run_on_threads(unsigned T, F& fn) {
+    if (T <= 1) { fn(); return; }
+    WorkerPool::get().run(T - 1, [](void* p) { (*static_cast<F*>(p))(); }, &fn);
+}
 
 // Runs fn(task) for task in [0, n_tasks) on up to host_threads() threads (dynamic scheduling).
 template <class F> void parallel_tasks(size_t n_tasks, F&& fn) {
@@ -240,20 +246,19 @@ void HostGraph::reserve_arena(uint64_t extra) {   // make room for `extra` more 
     arena_overflow.swap(bigger);
     arena = arena_overflow.data(); arena_cap = arena_overflow.size();
 }
-void HostGraph::relocate(uint32_t idx, uint32_t before, uint32_t after) {
+bool HostGraph::relocate(uint32_t idx, uint32_t before, uint32_t after, bool shared) {
     const uint64_t need = (uint64_t)before + rec[idx].len + after;
-    const uint64_t at = __atomic_fetch_add(&arena_used, need, __ATOMIC_RELAXED);
+    uint64_t at = __atomic_fetch_add(&arena_used, need, __ATOMIC_RELAXED);
     if (at + need > arena_cap) {
-        // only reachable from the sequential passes (the parallel pass reserves its worst case up front)
         __atomic_fetch_sub(&arena_used, need, __ATOMIC_RELAXED);
+        if (shared) return false;             // other threads hold pointers into the arena: it cannot move now
         reserve_arena(need);
-        return relocate(idx, before, after);
+        at = arena_used; arena_used += need;
     }
     memmove(arena + at + before, arena + rec[idx].seq_off, rec[idx].len);
     rec[idx].seq_off = at + before; rec[idx].room_before = before; rec[idx].room_after = after;
+    return true;
 }
-void HostGraph::grow_front(uint32_t idx, uint32_t need) { if (rec[idx].room_before < need) relocate(idx, need + 4 * AC_SEQ_SLACK, rec[idx].room_after < AC_SEQ_SLACK ? AC_SEQ_SLACK : rec[idx].room_after); }
-void HostGraph::grow_back(uint32_t idx, uint32_t need) { if (rec[idx].room_after < need) relocate(idx, rec[idx].room_before < AC_SEQ_SLACK ? AC_SEQ_SLACK : rec[idx].room_before, need + 4 * AC_SEQ_SLACK); }
 
 // ------------------------------------------------------------------------------------------------
 // graph_simplification.rs:26-312
@@ -319,6 +324,7 @@ void HostGraph::compute_candidates() {
     cand_at.assign(2 * (size_t)U, -1);
     for (size_t i = 0; i < cands.size(); ++i) cand_at[2 * (size_t)cands[i].idx + cands[i].side] = (int32_t)i;
     compute_dependents();
+    compute_levels();
     dirty.assign((cands.size() + 63) / 64, 0);     // the first pass visits every candidate; the bitmap collects work for later passes
     exhausted.assign(cands.size(), 0);
     for (uint32_t u = 0; u < U; ++u) rec[u].flags = 0;
@@ -383,11 +389,12 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
     const uint32_t idx = cand.idx;
     const UStrand* grp = cand.src; const uint32_t gn = cand.gn;
 
-    bool dup = false, pristine = first_pass; uint32_t min_len = 0xFFFFFFFFu;
+    // the comparison made in parallel at the start of this pass still holds if none of the sources changed since
+    bool dup = false, pristine = spec_pass[ci] == pass_id; uint32_t min_len = 0xFFFFFFFFu;
     for (uint32_t a = 0; a < gn; ++a) {
         const uint32_t s = us_index(grp[a]);
         if (rec[s].len < min_len) min_len = rec[s].len;
-        if (rec[s].flags) pristine = false;
+        if (rec[s].flags == pass_id) pristine = false;
         for (uint32_t b = 0; b < a; ++b) if (s == us_index(grp[b])) dup = true;
     }
     const size_t common_len = pristine ? spec_len[ci] : common_length(cand);
@@ -399,6 +406,13 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
     exhausted[ci] = c == common_len;       // nothing (more) in common: only an extension of a compared end can change that
     if (c == 0) return 0;
 
+    // make room at the destination BEFORE anything is modified: when several threads share the arena it cannot be
+    // reallocated, and a candidate that does not fit is handed back untouched (the caller applies it alone later)
+    if (cand.side == 0 ? rec[idx].room_before < c : rec[idx].room_after < c) {
+        const uint32_t before = cand.side == 0 ? (uint32_t)c + 4 * AC_SEQ_SLACK : std::max<uint32_t>(rec[idx].room_before, AC_SEQ_SLACK);
+        const uint32_t after = cand.side == 0 ? std::max<uint32_t>(rec[idx].room_after, AC_SEQ_SLACK) : (uint32_t)c + 4 * AC_SEQ_SLACK;
+        if (!relocate(idx, before, after, shared)) return POSTPONED;
+    }
     common.resize(c);
     {
         const uint32_t u0 = us_index(grp[0]); const unsigned char* p0 = (const unsigned char*)seq_ptr(u0);
@@ -413,7 +427,7 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
             if (!us_reverse(grp[a])) { rec[s].min_rpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].room_after += (uint32_t)c; }                 // remove_seq_from_end, unitig.rs:225-232
             else { rec[s].min_fpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].seq_off += c; rec[s].room_before += (uint32_t)c; }                // remove_seq_from_start, unitig.rs:216-223
         }
-        grow_front(idx, (uint32_t)c);                                                                                                    // add_seq_to_start, unitig.rs:234-240
+        // add_seq_to_start, unitig.rs:234-240
         rec[idx].seq_off -= c; rec[idx].room_before -= (uint32_t)c; rec[idx].len += (uint32_t)c; rec[idx].min_fpos -= (uint32_t)c;
         memcpy(arena + rec[idx].seq_off, common.data(), c);
     } else {                // shift_sequence_2 (:119-138): common start of the outputs moves to the end of this unitig
@@ -422,7 +436,7 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
             if (!us_reverse(grp[a])) { rec[s].min_fpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].seq_off += c; rec[s].room_before += (uint32_t)c; }
             else { rec[s].min_rpos += (uint32_t)c; rec[s].len -= (uint32_t)c; rec[s].room_after += (uint32_t)c; }
         }
-        grow_back(idx, (uint32_t)c);                                                                                                     // add_seq_to_end, unitig.rs:242-248
+        // add_seq_to_end, unitig.rs:242-248
         memcpy(arena + rec[idx].seq_off + rec[idx].len, common.data(), c);
         rec[idx].room_after -= (uint32_t)c; rec[idx].len += (uint32_t)c; rec[idx].min_rpos -= (uint32_t)c;
     }
@@ -436,7 +450,7 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
         const uint64_t m = 1ull << (cnd & 63);
         if (shared) __atomic_fetch_or(&dirty[(size_t)cnd >> 6], m, __ATOMIC_RELAXED); else dirty[(size_t)cnd >> 6] |= m;
     };
-    rec[idx].flags = 1;
+    rec[idx].flags = pass_id;
     {
         const Deps& dd = deps[idx];      // the destination grew at its start (side 0) or end (side 1); its length changed
         const bool grew_start = cand.side == 0;
@@ -444,7 +458,7 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
     }
     for (uint32_t a = 0; a < gn; ++a) {
         const uint32_t s = us_index(grp[a]);
-        rec[s].flags = 1;
+        rec[s].flags = pass_id;
         const Deps& ds = deps[s];
         const bool trimmed_end = (cand.side == 0) != us_reverse(grp[a]);     // which physical end of s lost bases (its reader is this candidate)
         if (trimmed_end) { mark(ds.c[3], false); mark(ds.c[4], false); mark(ds.c[1], false); }   // readers of the other end see a new length; min_rpos moved
@@ -452,20 +466,21 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
     }
     // A capped shift has to be looked at again in the next pass; after a complete one the bit must be off.
     if (c != common_len) { if (shared) __atomic_fetch_or(&dirty[w], bit_mask, __ATOMIC_RELAXED); else dirty[w] |= bit_mask; }
-    else if (!first_pass) dirty[w] &= ~bit_mask;      // (later passes are sequential; in the first pass nobody can have marked it yet)
     return c;
 }
 
-// First pass, in parallel.  Two candidates conflict when they share a unitig (destination or source); the reference's
-// result only depends on the relative order of conflicting candidates.  Candidates are therefore levelled
-// (level = 1 + the highest level among earlier conflicting candidates), and every level is applied by all threads at
-// once: within a level no two candidates touch the same unitig.  The only shared writes are the rare marks for the
-// next pass (atomic) and arena bumps (atomic; the worst case is reserved up front so the arena never moves).
-size_t HostGraph::first_pass_parallel() {
+// Passes in parallel.  Two candidates conflict when they share a unitig (destination or source); the reference's result only
+// depends on the relative order of conflicting candidates.  Candidates are therefore levelled once (level = 1 + the highest
+// level among earlier conflicting candidates) and every pass walks the levels in order, all threads applying the due
+// candidates of one level at once: within a level no two candidates touch the same unitig.  A candidate marked during the
+// pass conflicts with its marker, so it sits on another level: a later one if it comes later in the reference's order (then
+// this pass still reaches it, as the reference's loop would), an earlier one otherwise (then it waits for the next pass).
+// Shared writes: the work-list bits (atomic) and arena bumps (atomic; a candidate that finds the arena full is applied by one
+// thread at the level's barrier, which is as good as any other place in its level).
+void HostGraph::compute_levels() {
     const size_t n = cands.size();
     std::vector<uint32_t> level_of_unitig(U, 0), level(n);
-    uint32_t n_levels = 0;
-    uint64_t reloc_bound = 0;
+    n_levels = 0;
     for (size_t ci = 0; ci < n; ++ci) {
         const Candidate& cd = cands[ci];
         uint32_t lv = level_of_unitig[cd.idx];
@@ -475,52 +490,71 @@ size_t HostGraph::first_pass_parallel() {
         for (uint32_t a = 0; a < cd.gn; ++a) level_of_unitig[us_index(cd.src[a])] = lv;
         level[ci] = lv;
         if (lv > n_levels) n_levels = lv;
-        if (spec_len[ci] > AC_SEQ_SLACK) reloc_bound += (uint64_t)rec[cd.idx].len + 2ull * spec_len[ci] + 8 * AC_SEQ_SLACK + 64;   // it may have to move
     }
     if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[host] expand levels %u for %zu candidates\n", n_levels, n);
-    if (n_levels > 1024) return (size_t)-1;                   // a long dependency chain: not worth the barriers
-    reserve_arena(reloc_bound);                               // no reallocation while several threads hold pointers into the arena
-    std::vector<uint32_t> start(n_levels + 2, 0), by_level(n);
-    for (size_t ci = 0; ci < n; ++ci) start[level[ci] + 1] += 1;
-    for (uint32_t l = 1; l <= n_levels + 1; ++l) start[l] += start[l - 1];
-    { std::vector<uint32_t> cur(start.begin(), start.end() - 1); for (size_t ci = 0; ci < n; ++ci) by_level[cur[level[ci]]++] = (uint32_t)ci; }
+    level_start.assign(n_levels + 2, 0); by_level.resize(n);
+    for (size_t ci = 0; ci < n; ++ci) level_start[level[ci] + 1] += 1;
+    for (uint32_t l = 1; l <= n_levels + 1; ++l) level_start[l] += level_start[l - 1];
+    { std::vector<uint32_t> cur(level_start.begin(), level_start.end() - 1); for (size_t ci = 0; ci < n; ++ci) by_level[cur[level[ci]]++] = (uint32_t)ci; }
+}
 
-    const unsigned T = std::min<unsigned>(host_threads(), 16);
+size_t HostGraph::pass_parallel(bool all_due) {
+    static const bool tight = getenv("AC_EXPAND_TIGHT_ARENA") != nullptr;   // test hook: every relocation meets a full arena
+    if (tight) arena_cap = arena_used;
+    else if (all_due) {   // room for the relocations the first pass is known to need, so that (almost) nobody is handed back
+        uint64_t reloc_bound = 0;
+        for (size_t ci = 0; ci < cands.size(); ++ci)
+            if (spec_len[ci] > AC_SEQ_SLACK) reloc_bound += (uint64_t)rec[cands[ci].idx].len + 2ull * spec_len[ci] + 8 * AC_SEQ_SLACK + 64;
+        reserve_arena(reloc_bound);
+    }
+    const unsigned T = std::max<unsigned>(1, std::min<unsigned>(host_threads(), 16));
     std::vector<std::atomic<uint32_t>> next(n_levels + 2);
     for (auto& x : next) x.store(0);
-    std::atomic<uint32_t> arrived{0}; std::atomic<uint32_t> generation{0};
-    std::atomic<uint64_t> total{0};
+    std::atomic<uint32_t> arrived{0}, generation{0};
+    std::atomic<uint64_t> total{0}, evaluated{0};
     std::exception_ptr err = nullptr; std::atomic<bool> failed{false};
+    std::mutex postponed_lock; std::vector<uint32_t> postponed;
     const uint32_t CHUNK = 128;
+    struct Ctx { HostGraph* g; } ;
     auto work = [&]() {
-        std::string common; uint64_t mine = 0;
+        std::string common; uint64_t mine = 0, evals = 0;
         for (uint32_t l = 1; l <= n_levels; ++l) {
-            const uint32_t lo = start[l], hi = start[l + 1];
+            const uint32_t lo = level_start[l], hi = level_start[l + 1];
             try {
                 for (uint32_t c0; (c0 = next[l].fetch_add(CHUNK)) < hi - lo;) {
                     const uint32_t c1 = std::min(hi - lo, c0 + CHUNK);
                     for (uint32_t x = c0; x < c1; ++x) {
-                        if (x + 8 < c1) {
-                            const Candidate& f = cands[by_level[lo + x + 8]];
-                            __builtin_prefetch(&rec[f.idx]); __builtin_prefetch(&deps[f.idx]);
-                            for (uint32_t a = 0; a < f.gn; ++a) { __builtin_prefetch(&rec[us_index(f.src[a])]); __builtin_prefetch(&deps[us_index(f.src[a])]); }
+                        const uint32_t ci = by_level[lo + x];
+                        if (!all_due) {
+                            const uint64_t m = 1ull << (ci & 63);
+                            if (!(__atomic_load_n(&dirty[ci >> 6], __ATOMIC_RELAXED) & m)) continue;
+                            __atomic_fetch_and(&dirty[ci >> 6], ~m, __ATOMIC_RELAXED);
                         }
-                        mine += apply_candidate(by_level[lo + x], true, common);
+                        const size_t r = apply_candidate(ci, true, common);
+                        ++evals;
+                        if (r == POSTPONED) { std::lock_guard<std::mutex> lk(postponed_lock); postponed.push_back(ci); }
+                        else mine += r;
                     }
                 }
             } catch (...) { if (!failed.exchange(true)) err = std::current_exception(); }
-            // barrier: nobody starts level l+1 before level l is complete
+            // barrier: nobody starts level l+1 before level l is complete; the last one in settles what was handed back
             const uint32_t gen = generation.load(std::memory_order_acquire);
-            if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == T) { arrived.store(0, std::memory_order_relaxed); generation.store(gen + 1, std::memory_order_release); }
-            else while (generation.load(std::memory_order_acquire) == gen) { __builtin_ia32_pause(); }
+            if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == T) {
+                try {
+                    std::sort(postponed.begin(), postponed.end());
+                    for (uint32_t ci : postponed) mine += apply_candidate(ci, false, common);
+                } catch (...) { if (!failed.exchange(true)) err = std::current_exception(); }
+                postponed.clear();
+                arrived.store(0, std::memory_order_relaxed); generation.store(gen + 1, std::memory_order_release);
+            } else {
+                for (unsigned spins = 0; generation.load(std::memory_order_acquire) == gen; ++spins) { if (spins < 4096) __builtin_ia32_pause(); else std::this_thread::yield(); }
+            }
         }
-        total.fetch_add(mine);
+        total.fetch_add(mine); evaluated.fetch_add(evals);
     };
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < T; ++t) pool.emplace_back(work);
-    work();
-    for (auto& th : pool) th.join();
+    run_on_threads(T, work);
     if (err) std::rethrow_exception(err);
+    last_evaluations = (size_t)evaluated.load();
     return (size_t)total.load();
 }
 
@@ -528,40 +562,40 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
     const double t0 = now_ms();
     if (!cands_ready) { compute_candidates(); prof.candidates = now_ms() - t0; }
     size_t total_shifted = 0;
-    std::string common;
-    if (first_pass) {   // every candidate is evaluated in the first pass; do the byte comparisons for all of them in parallel
-        spec_len.resize(cands.size());
-        const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads() * 4, cands.size() / 1024));
+    ++pass_id;                                      // unitigs modified during this pass carry it in rec[].flags
+    // the candidates known to be due (all of them in the first pass): compare their ends in parallel before they are applied
+    std::vector<uint32_t> due;
+    if (first_pass) { spec_len.resize(cands.size()); spec_pass.assign(cands.size(), 0); due.resize(cands.size()); for (size_t i = 0; i < due.size(); ++i) due[i] = (uint32_t)i; }
+    else for (size_t w = 0; w < dirty.size(); ++w) for (uint64_t b = dirty[w]; b; b &= b - 1) due.push_back((uint32_t)(w * 64 + (size_t)__builtin_ctzll(b)));
+    static const size_t min_due = getenv("AC_EXPAND_MIN_DUE") ? (size_t)atoll(getenv("AC_EXPAND_MIN_DUE")) : 2048;   // tests lower it to drive small graphs through the levels
+    const bool parallel = due.size() >= min_due && host_threads() >= 4 && n_levels <= 1024 && !getenv("AC_EXPAND_SERIAL");
+    if (parallel || first_pass) {
+        const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads() * 4, due.size() / 512));
         parallel_tasks(T, [&](size_t t) {
-            for (size_t i = cands.size() * t / T; i < cands.size() * (t + 1) / T; ++i) spec_len[i] = common_length(cands[i]);
+            for (size_t x = due.size() * t / T; x < due.size() * (t + 1) / T; ++x) { spec_len[due[x]] = common_length(cands[due[x]]); spec_pass[due[x]] = pass_id; }
         });
-        prof.compare = now_ms() - t0;
-        size_t r = (size_t)-1;
-        if (cands.size() >= 8192 && host_threads() >= 4 && !getenv("AC_EXPAND_SERIAL")) r = first_pass_parallel();
-        if (r != (size_t)-1) total_shifted = r;
-        else for (size_t ci = 0; ci < cands.size(); ++ci) {
-            if (ci + 16 < cands.size()) {   // pull the next candidates' records into cache
-                const Candidate& f = cands[ci + 16];
-                __builtin_prefetch(&rec[f.idx]); __builtin_prefetch(&deps[f.idx]);
-                for (uint32_t a = 0; a < f.gn; ++a) { __builtin_prefetch(&rec[us_index(f.src[a])]); __builtin_prefetch(&deps[us_index(f.src[a])]); }
-            }
-            total_shifted += apply_candidate(ci, false, common);
-        }
-    } else {
-        for (size_t w = 0; w < dirty.size(); ++w) {
+    }
+    if (first_pass) prof.compare = now_ms() - t0;
+    if (parallel) { total_shifted = pass_parallel(first_pass); }
+    else {
+        std::string common;
+        last_evaluations = 0;
+        for (size_t w = 0; w < dirty.size() || (first_pass && w * 64 < cands.size()); ++w) {
             uint64_t passed = 0;                       // candidates of this word already visited in this pass
             for (;;) {
                 // a candidate marked again at or behind the current position waits for the next pass, exactly as the
                 // reference's loop would only reach it again in its next call
-                const uint64_t avail = dirty[w] & ~passed;
+                const uint64_t avail = (first_pass ? ~0ull : dirty[w]) & ~passed;
                 if (!avail) break;
                 const int bit = __builtin_ctzll(avail);
+                if (w * 64 + (size_t)bit >= cands.size()) break;
                 passed = bit == 63 ? ~0ull : ((2ull << bit) - 1);
-                dirty[w] &= ~(1ull << bit);
-                total_shifted += apply_candidate(w * 64 + (size_t)bit, false, common);
+                if (!first_pass) dirty[w] &= ~(1ull << bit);
+                total_shifted += apply_candidate(w * 64 + (size_t)bit, false, common); ++last_evaluations;
             }
         }
     }
+    if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[host] pass %d%s: %zu evaluations, %zu bases, %.2f ms\n", prof.passes + 1, parallel ? " (by levels)" : "", last_evaluations, total_shifted, now_ms() - t0);
     first_pass = false;
     if (prof.passes == 0) prof.pass1 = now_ms() - t0;      // first pass (incl. candidate listing)
     prof.expand += now_ms() - t0; prof.passes += 1;

@@ -78,17 +78,21 @@ private:
     std::vector<int32_t> cand_at;             // [2U] candidate index of (unitig, side), -1 if none
     std::vector<uint64_t> dirty;              // bitmap over cands: must be (re-)evaluated
     std::vector<uint8_t> exhausted;           // per candidate: its sources had nothing in common after its last evaluation
-    std::vector<uint32_t> spec_len;           // common-piece lengths computed in parallel from the untouched graph
+    std::vector<uint32_t> spec_len;           // common-piece lengths computed in parallel at the start of a pass
+    std::vector<uint32_t> spec_pass;          // ... and the pass they were computed for
+    uint32_t pass_id = 0;                     // expand_repeats calls so far; rec[].flags holds the pass a unitig last changed in
     bool cands_ready = false, first_pass = true;
     void compute_candidates();
     uint32_t common_length(const Candidate& cand) const;
     struct Deps { int32_t c[6]; };            // candidates that read unitig u: its own two, and those it exclusively feeds / is fed by
     std::vector<Deps> deps;
     void compute_dependents();
+    static constexpr size_t POSTPONED = (size_t)-1;   // apply_candidate: the shared arena was full, nothing was changed
     size_t apply_candidate(size_t ci, bool shared, std::string& common);
-    size_t first_pass_parallel();
+    std::vector<uint32_t> level_start, by_level; uint32_t n_levels = 0;   // candidates grouped by conflict level (compute_levels)
+    size_t last_evaluations = 0;
+    void compute_levels();
+    size_t pass_parallel(bool all_due);
     void reserve_arena(uint64_t extra);
-    void grow_front(uint32_t idx, uint32_t need);
-    void grow_back(uint32_t idx, uint32_t need);
-    void relocate(uint32_t idx, uint32_t before, uint32_t after);
+    bool relocate(uint32_t idx, uint32_t before, uint32_t after, bool shared);
 };

@@ -299,10 +299,27 @@ LoadedInput load_sequences(const std::string& dir, uint32_t k, uint32_t max_cont
     in.assembly_count = assemblies.size();
     const uint32_t h = k / 2;
     size_t seq_id = 0;
-    for (const std::string& path : assemblies) {
+    // the files are independent until ids are handed out: read and parse them on `threads` threads, then number in file order
+    std::vector<std::vector<FastaRecord>> loaded(assemblies.size());
+    std::vector<std::string> errors(assemblies.size());
+    {
+        std::atomic<size_t> next_file{0};
+        auto work = [&]() {
+            for (size_t f; (f = next_file.fetch_add(1)) < assemblies.size();) {
+                try { loaded[f] = load_fasta(assemblies[f]); } catch (const InputError& e) { errors[f] = e.msg.empty() ? "unable to load " + assemblies[f] : e.msg; }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < std::min<size_t>(std::max<uint32_t>(threads, 1), assemblies.size()); ++t) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+    }
+    for (size_t file = 0; file < assemblies.size(); ++file) {
+        const std::string& path = assemblies[file];
+        if (!errors[file].empty()) fail(errors[file]);           // raised where the serial loop of the reference would have met it
         AssemblyDetails det; det.filename = path;
         const std::string filename = path.substr(path.rfind('/') + 1);
-        for (FastaRecord& rec : load_fasta(path)) {
+        for (FastaRecord& rec : loaded[file]) {
             if (rec.seq.size() < k) continue;                                      // compress.rs:109
             if (++seq_id > 32767) fail("no more than 32767 input sequences are allowed");
             std::string header;                                                    // split_whitespace().join(" "), compress.rs:115

@@ -929,7 +929,7 @@ struct DevicePipeline::Impl {
     DevBuf ascii, packed, seqs, slots, pos_slot, flags8, bmask, bcount, boff, counters, uid_rep, slot_unitig;
     DevBuf run_start, run_len, run_uk, run_dir, is_rep, rep_idx, run_unitig, unitigs, nchunks, chunk_off, partial, link_count, links;
     DevBuf scan_tmp[4];
-    int insert_occupancy = getenv("AC_INSERT_OCC") ? atoi(getenv("AC_INSERT_OCC")) : 5;   // resident CTAs per SM the insert kernel is compiled for (5, 6 or 8)
+    int insert_occupancy = getenv("AC_INSERT_OCC") ? atoi(getenv("AC_INSERT_OCC")) : 6;   // resident CTAs per SM the insert kernel is compiled for (5, 6 or 8)
     DevBuf sort_a, sort_b, num_prefix, rank, d_len, d_depth, need, d_seq_off, d_arena, d_min_fpos, d_min_rpos;
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;

@@ -118,3 +118,19 @@ def test_cli_yaml_and_gfa_files(emu, tmp_path):
     expected, yaml, st = o.compress_dir(d, 51)
     assert open(os.path.join(out, "input_assemblies.gfa")).read() == expected
     assert open(os.path.join(out, "input_assemblies.yaml")).read() == yaml
+
+
+@pytest.mark.parametrize("env", [{"AC_EXPAND_MIN_DUE": "1"}, {"AC_EXPAND_MIN_DUE": "1", "AC_EXPAND_TIGHT_ARENA": "1"}, {"AC_EXPAND_SERIAL": "1"},
+                                 {"AC_HOST_POOL": "0", "AC_HOST_THREADS": "3"}])
+def test_repeat_expansion_schedules_agree(emu, env):
+    """simplify_structure has three schedules (serial sweep; conflict levels on several threads; the same with every
+    relocation handed back to the barrier).  The switches are read once per process, so each runs in a child."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import cases\nfrom autocycler_b200 import api\nfrom parity_common import check_case\n"
+            "lib = api.load_library(%r)\n"
+            "for k in (5, 9, 31, 51):\n"
+            "    for seed in range(25):\n"
+            "        check_case(lib, cases.random_case(7000 * k + seed, k), k)\n"
+            "print('AGREE')\n") % (os.path.join(ROOT, "tests"), ROOT, os.path.join(ROOT, "tests", "emu", "libautocycler_emu.so"))
+    r = subprocess.run([os.sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "AGREE" in r.stdout, r.stderr[-2000:]
