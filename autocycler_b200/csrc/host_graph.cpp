@@ -198,16 +198,31 @@ void HostGraph::renumber() {   // unitig_graph.rs:295-315: stable sort by length
             for (uint32_t i = 0; i < m; ++i) v |= (uint64_t)p[i] << (56 - 8 * i);
             key.prefix = v;
         }
-        std::sort(keys.begin() + bounds(t), keys.begin() + bounds(t + 1), less);
     });
-    for (size_t width = 1; width < T; width *= 2) {   // pairwise merges of the sorted pieces, each level in parallel
-        const size_t pairs = (T + 2 * width - 1) / (2 * width);
-        parallel_tasks(pairs, [&](size_t q) {
-            const size_t a = q * 2 * width, m = std::min(T, a + width), b = std::min(T, a + 2 * width);
-            if (m < b) std::inplace_merge(keys.begin() + bounds(a), keys.begin() + bounds(m), keys.begin() + bounds(b), less);
+    if (T == 1) std::sort(keys.begin(), keys.end(), less);
+    else {   // sample sort: splitters from a sample, every thread scatters its piece into the buckets, every bucket is sorted on its own
+        const size_t B = T, per = 16;
+        std::vector<Key> sample;
+        for (size_t x = 0; x < B * per; ++x) sample.push_back(keys[(size_t)((uint64_t)U * x / (B * per))]);
+        std::sort(sample.begin(), sample.end(), less);
+        std::vector<Key> split;
+        for (size_t b = 1; b < B; ++b) split.push_back(sample[b * per]);
+        auto bucket_of = [&](const Key& key) { return (size_t)(std::upper_bound(split.begin(), split.end(), key, less) - split.begin()); };
+        std::vector<uint32_t> count(T * B, 0);
+        std::vector<uint8_t> which(U);
+        parallel_tasks(T, [&](size_t t) {
+            for (size_t n = bounds(t); n < bounds(t + 1); ++n) { const size_t b = bucket_of(keys[n]); which[n] = (uint8_t)b; count[t * B + b] += 1; }
         });
+        std::vector<uint32_t> at(T * B), bucket_start(B + 1, 0);
+        { uint32_t run = 0; for (size_t b = 0; b < B; ++b) { bucket_start[b] = run; for (size_t t = 0; t < T; ++t) { at[t * B + b] = run; run += count[t * B + b]; } } bucket_start[B] = run; }
+        std::vector<Key> sorted(U);
+        parallel_tasks(T, [&](size_t t) {
+            for (size_t n = bounds(t); n < bounds(t + 1); ++n) sorted[at[t * B + which[n]]++] = keys[n];
+        });
+        parallel_tasks(B, [&](size_t b) { std::sort(sorted.begin() + bucket_start[b], sorted.begin() + bucket_start[b + 1], less); });
+        keys.swap(sorted);
     }
-    for (uint32_t n = 0; n < U; ++n) { order[n] = keys[n].idx; number[keys[n].idx] = n + 1; }
+    parallel_tasks(T, [&](size_t t) { for (size_t n = bounds(t); n < bounds(t + 1); ++n) { order[n] = keys[n].idx; number[keys[n].idx] = (uint32_t)n + 1; } });
     prof.renumber += now_ms() - t0;
 }
 
@@ -289,7 +304,10 @@ void HostGraph::compute_fixed() {   // graph_simplification.rs:190-230; paths an
 // while `while expand_repeats() > 0 {}` runs (graph_simplification.rs:26-27; the renumbering comes after), so the
 // candidates are listed once, in the iteration order of the reference's loop (graph.unitigs order; inputs side first).
 void HostGraph::compute_candidates() {
+    const bool prof_on = getenv("AC_HOST_PROFILE") != nullptr; double tt = now_ms();
+    auto lap = [&](const char* what) { if (prof_on) { const double t = now_ms(); fprintf(stderr, "[host]   candidates/%s %.2f ms\n", what, t - tt); tt = t; } };
     if (!fixed_ready) compute_fixed();
+    lap("fixed");
     const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads(), U / 8192));
     std::vector<std::vector<Candidate>> part(T);
     parallel_tasks(T, [&](size_t t) {
@@ -319,12 +337,25 @@ void HostGraph::compute_candidates() {
             }
         }
     });
-    cands.clear();
-    for (auto& v : part) cands.insert(cands.end(), v.begin(), v.end());
-    cand_at.assign(2 * (size_t)U, -1);
-    for (size_t i = 0; i < cands.size(); ++i) cand_at[2 * (size_t)cands[i].idx + cands[i].side] = (int32_t)i;
+    lap("list");
+    std::vector<size_t> part_at(T + 1, 0);
+    for (size_t t = 0; t < T; ++t) part_at[t + 1] = part_at[t] + part[t].size();
+    cands.resize(part_at[T]);
+    cand_at.resize(2 * (size_t)U);
+    parallel_tasks(T, [&](size_t t) {                    // the pieces are in graph order already: copy them side by side and index them
+        const size_t a = (size_t)((uint64_t)U * t / T), b = (size_t)((uint64_t)U * (t + 1) / T);
+        for (size_t n = a; n < b; ++n) { cand_at[2 * (size_t)order[n]] = -1; cand_at[2 * (size_t)order[n] + 1] = -1; }
+        for (size_t x = 0; x < part[t].size(); ++x) {
+            const Candidate& c = part[t][x];
+            cands[part_at[t] + x] = c;
+            cand_at[2 * (size_t)c.idx + c.side] = (int32_t)(part_at[t] + x);
+        }
+    });
+    lap("concat+index");
     compute_dependents();
+    lap("dependents");
     compute_levels();
+    lap("levels");
     dirty.assign((cands.size() + 63) / 64, 0);     // the first pass visits every candidate; the bitmap collects work for later passes
     exhausted.assign(cands.size(), 0);
     for (uint32_t u = 0; u < U; ++u) rec[u].flags = 0;
@@ -478,17 +509,19 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
 // Shared writes: the work-list bits (atomic) and arena bumps (atomic; a candidate that finds the arena full is applied by one
 // thread at the level's barrier, which is as good as any other place in its level).
 void HostGraph::compute_levels() {
+    // One serial sweep in candidate order; a byte per unitig keeps the table cache resident (beyond 250 levels the
+    // passes are not worth their barriers and run as the plain sweep).
     const size_t n = cands.size();
-    std::vector<uint32_t> level_of_unitig(U, 0), level(n);
+    std::vector<uint8_t> level_of_unitig(U, 0), level(n);
     n_levels = 0;
     for (size_t ci = 0; ci < n; ++ci) {
         const Candidate& cd = cands[ci];
         uint32_t lv = level_of_unitig[cd.idx];
-        for (uint32_t a = 0; a < cd.gn; ++a) lv = std::max(lv, level_of_unitig[us_index(cd.src[a])]);
-        ++lv;
-        level_of_unitig[cd.idx] = lv;
-        for (uint32_t a = 0; a < cd.gn; ++a) level_of_unitig[us_index(cd.src[a])] = lv;
-        level[ci] = lv;
+        for (uint32_t a = 0; a < cd.gn; ++a) lv = std::max<uint32_t>(lv, level_of_unitig[us_index(cd.src[a])]);
+        if (++lv > 250) { n_levels = 0xFFFFFFFFu; level_start.clear(); by_level.clear(); return; }
+        level_of_unitig[cd.idx] = (uint8_t)lv;
+        for (uint32_t a = 0; a < cd.gn; ++a) level_of_unitig[us_index(cd.src[a])] = (uint8_t)lv;
+        level[ci] = (uint8_t)lv;
         if (lv > n_levels) n_levels = lv;
     }
     if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[host] expand levels %u for %zu candidates\n", n_levels, n);
@@ -558,6 +591,11 @@ size_t HostGraph::pass_parallel(bool all_due) {
     return (size_t)total.load();
 }
 
+void HostGraph::prepare_simplify() {   // the structural part of expand_repeats: no sequence is read
+    const double t0 = now_ms();
+    if (!cands_ready) { compute_candidates(); prof.candidates = now_ms() - t0; }
+}
+
 size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
     const double t0 = now_ms();
     if (!cands_ready) { compute_candidates(); prof.candidates = now_ms() - t0; }
@@ -568,7 +606,7 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
     if (first_pass) { spec_len.resize(cands.size()); spec_pass.assign(cands.size(), 0); due.resize(cands.size()); for (size_t i = 0; i < due.size(); ++i) due[i] = (uint32_t)i; }
     else for (size_t w = 0; w < dirty.size(); ++w) for (uint64_t b = dirty[w]; b; b &= b - 1) due.push_back((uint32_t)(w * 64 + (size_t)__builtin_ctzll(b)));
     static const size_t min_due = getenv("AC_EXPAND_MIN_DUE") ? (size_t)atoll(getenv("AC_EXPAND_MIN_DUE")) : 2048;   // tests lower it to drive small graphs through the levels
-    const bool parallel = due.size() >= min_due && host_threads() >= 4 && n_levels <= 1024 && !getenv("AC_EXPAND_SERIAL");
+    const bool parallel = due.size() >= min_due && host_threads() >= 4 && n_levels <= 250 && !getenv("AC_EXPAND_SERIAL");
     if (parallel || first_pass) {
         const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads() * 4, due.size() / 512));
         parallel_tasks(T, [&](size_t t) {

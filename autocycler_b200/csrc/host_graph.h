@@ -56,6 +56,7 @@ public:
     void check_links() const;                 // unitig_graph.rs:752-793
     void simplify_structure();                // graph_simplification.rs:26-40
     size_t expand_repeats();                  // graph_simplification.rs:43-86
+    void prepare_simplify();                  // lists the candidates of expand_repeats ahead of time (links and paths only, no sequence bytes)
     void merge_linear_paths(bool use_paths);  // graph_simplification.rs:315-371 (host_merge.cpp); use_paths=false is the reference's `seqs` = [] and drops the paths
     void gfa_text(const std::vector<HostSeq>& seqs, std::string& out) const;   // unitig_graph.rs:317-360
     uint64_t total_length() const;

@@ -945,6 +945,15 @@ struct DevicePipeline::Impl {
         (void)i;
 #endif
     }
+    void wait_mark(int i) {
+#ifndef AC_EMULATE
+        AC_CUDA_CHECK(cudaEventSynchronize(ev[i]));
+#else
+        (void)i;
+#endif
+    }
+    bool arena_pending = false;
+    void do_complete(PipelineResult& out);
     float between(int a, int b) {
 #ifndef AC_EMULATE
         float ms = 0; AC_CUDA_CHECK(cudaEventElapsedTime(&ms, ev[a], ev[b])); return ms;
@@ -1360,7 +1369,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     h_next.ensure(n_links * 4 + 4); h_prev.ensure(n_links * 4 + 4); h_path.ensure(n_runs * 4 + 4); h_path_off.ensure(((size_t)n_seqs + 1) * 8);
     uint64_t d2h = 0;
     auto pull = [&](PinBuf& dst, DevBuf& src, size_t bytes) { if (bytes) ac_d2h(dst.p, src.p, bytes, &stream); d2h += bytes; };
-    pull(h_rec, d_rec, (size_t)U * sizeof(UnitigRec)); pull(h_depth, d_depth, (size_t)U * 4); pull(h_arena, d_arena, arena_bytes);
+    pull(h_rec, d_rec, (size_t)U * sizeof(UnitigRec)); pull(h_depth, d_depth, (size_t)U * 4);
     h_order.ensure((size_t)U * 4 + 4);
     if (U) { ac_d2h(h_order.p, ord_in, (size_t)U * 4, &stream); d2h += (size_t)U * 4; }
     pull(h_next_off, d_next_off, ((size_t)n_strands + 1) * 4); pull(h_prev_off, d_prev_off, ((size_t)n_strands + 1) * 4);
@@ -1369,16 +1378,27 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
         h_run_start.ensure(n_runs * 8 + 8); h_run_len.ensure(n_runs * 4 + 4);
         pull(h_run_start, run_start, n_runs * 8); pull(h_run_len, run_len, n_runs * 4);
     }
+    // The sequences (most of the bytes) go last: the caller gets the graph structure as soon as the small arrays have
+    // landed and lists the repeat-expansion candidates while the arena is still on its way (complete() waits for it).
+    mark(16);
+    pull(h_arena, d_arena, arena_bytes);
     out.d2h_bytes = d2h + 2 * sizeof(unsigned long long) + 8 * sizeof(uint32_t);
     out.h2d_bytes = total + (uint64_t)n_seqs * sizeof(SeqInfo);
     mark(12);
-    ac_sync(&stream);
+    wait_mark(16);
     out.n_unitigs = U; out.n_runs = n_runs; out.n_seqs = n_seqs; out.n_links = n_links;
     out.rec = h_rec.as<UnitigRec>(); out.depth = h_depth.as<uint32_t>(); out.order = h_order.as<uint32_t>();
     out.arena = h_arena.as<char>(); out.arena_used = arena_bytes; out.arena_cap = arena_cap;
     out.next_off = h_next_off.as<uint32_t>(); out.next = h_next.as<UStrand>(); out.prev_off = h_prev_off.as<uint32_t>(); out.prev = h_prev.as<UStrand>();
     out.path_off = h_path_off.as<uint64_t>(); out.path = h_path.as<UStrand>();
     out.run_start = keep_positions ? h_run_start.as<uint64_t>() : nullptr; out.run_len = keep_positions ? h_run_len.as<uint32_t>() : nullptr;
+    arena_pending = true;
+}
+
+void DevicePipeline::Impl::do_complete(PipelineResult& out) {
+    if (!arena_pending) return;
+    ac_sync(&stream);
+    arena_pending = false;
     out.t.h2d = between(0, 1); out.t.pack = between(2, 3); out.t.insert = between(15, 4); out.t.sample = between(3, 15); out.t.adjacency = between(13, 5);
     out.t.boundaries = between(5, 6); out.t.runs = between(14, 7); out.t.unitigs = between(7, 8); out.t.links = between(8, 9);
     out.t.seed_sort = between(9, 10); out.t.emit = between(10, 11); out.t.d2h = between(11, 12); out.t.total = between(2, 4) + between(13, 6) + between(14, 12);
@@ -1408,6 +1428,8 @@ void DevicePipeline::finish(PipelineResult& out, bool keep_positions) {
     Impl& m = *impl; m.set_device(); const int W = m.W;
     AC_DISPATCH_W(m.finish_w, out, keep_positions)
 }
+
+void DevicePipeline::complete(PipelineResult& out) { impl->set_device(); impl->do_complete(out); }
 
 void DevicePipeline::build(PipelineResult& out, bool keep_positions) {   // single GPU: every sequence is local, nothing to exchange
     build_local(0, impl->n_seqs, false);

@@ -80,6 +80,9 @@ public:
     ~DevicePipeline();
     // ascii: all padded, end-repaired forward strands concatenated (bytes in "ACGT."); seqs: their layout.
     void upload(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t k);
+    // build() / finish() return once the graph structure is in `out`; the sequence arena and the timings are only valid
+    // after complete(), which the caller invokes when it has finished the host work that needs neither.
+    void complete(PipelineResult& out);
     void build(PipelineResult& out, bool keep_positions);   // kernels + D2H of the results (single GPU: all the stages below)
     // Multi-GPU stages (one process per GPU; the collectives between them are done by the caller on device pointers):
     void build_local(uint32_t seq_lo, uint32_t seq_hi, bool multi);     // table over this rank's sequences [seq_lo, seq_hi)
