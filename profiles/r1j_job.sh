@@ -8,3 +8,4 @@ timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/j
 timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:InsertLaneBody -c 1 -o gpurun_out/insert_r1j python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/j_ncu_insert.log 2>&1; tail -1 gpurun_out/j_ncu_insert.log | cut -c1-200
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -c 600 --csv --log-file gpurun_out/j_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/j_ncu_launches.log 2>&1; tail -1 gpurun_out/j_ncu_launches.log | cut -c1-200
 timeout 300 python profiles/cli_wall.py > gpurun_out/j_cli.log 2>&1; grep -E "^rep|load\+repair" gpurun_out/j_cli.log
+timeout 120 python profiles/pcie_probe.py > gpurun_out/j_pcie.log 2>&1; cat gpurun_out/j_pcie.log
