@@ -55,7 +55,7 @@ class AcTimings(C.Structure):
 
 
 EXPORTS = ["ac_last_error", "ac_version", "ac_create", "ac_destroy", "ac_add_sequence", "ac_clear_sequences", "ac_upload",
-           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
+           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_renumber_unitigs", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
            "ac_timings_get", "ac_compress_dir", "ac_load_sequences", "ac_sequence_get",
            "ac_build_local", "ac_entries_count", "ac_entries_export", "ac_entries_merge", "ac_runs_local", "ac_runs_export",
            "ac_runs_import", "ac_build_finish", "ac_gfa_data"]
@@ -80,7 +80,7 @@ def load_library(path=None):
     lib.ac_destroy.restype = None
     lib.ac_add_sequence.argtypes = [C.c_void_p, C.c_uint16, C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p]
     lib.ac_clear_sequences.argtypes = [C.c_void_p]
-    for name in ("ac_upload", "ac_build", "ac_simplify"):
+    for name in ("ac_upload", "ac_build", "ac_simplify", "ac_renumber_unitigs"):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.ac_merge_linear_paths.argtypes = [C.c_void_p, C.c_int]
     lib.ac_sequence_reconstruct.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -252,6 +252,9 @@ class UnitigGraph:
         n = C.c_uint64(); ptr = C.c_void_p()
         self._h.check(self._h.lib.ac_gfa_data(self._h.ptr, C.byref(ptr), C.byref(n)))
         return memoryview((C.c_char * n.value).from_address(ptr.value)) if n.value else memoryview(b"")
+
+    def renumber_unitigs(self):   # unitig_graph.rs:295-315
+        self._h.check(self._h.lib.ac_renumber_unitigs(self._h.ptr))
 
     def reconstruct_original_sequence(self, index):   # unitig_graph.rs:383-388, by position in the sequence list
         n = C.c_uint64()

@@ -254,6 +254,16 @@ int ac_merge_linear_paths(ac_handle* h, int use_paths) {
     AC_GUARD_END(h)
 }
 
+int ac_renumber_unitigs(ac_handle* h) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    AC_GUARD_BEGIN
+    if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_renumber_unitigs");
+    h->graph.renumber();
+    h->gfa_ready = false;
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
 int ac_counts_get(const ac_handle* h, ac_counts* out) {
     if (!h || !out) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN

@@ -102,6 +102,8 @@ int ac_simplify(ac_handle* h);          /* simplify_structure */
  * unitigs follow the surviving ones in the S lines.  use_paths != 0 keeps sequence-path ends fixed (the reference's
  * `seqs` argument); 0 is its `&vec![]` form: everything mergeable is merged and the P lines lose their paths. */
 int ac_merge_linear_paths(ac_handle* h, int use_paths);
+/* renumber_unitigs (unitig_graph.rs:295-315) on the current graph, e.g. after ac_merge_linear_paths as trim.rs:266-268 does. */
+int ac_renumber_unitigs(ac_handle* h);
 
 /* Multi-GPU form of ac_build: one process per GPU, every process adds and uploads ALL sequences, owns the
  * contiguous block [seq_lo, seq_hi) of them (index = order of ac_add_sequence), and the caller (e.g. torch.distributed over

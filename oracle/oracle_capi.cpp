@@ -183,11 +183,12 @@ int orc_decompress(const char* gfa_text, const char* out_dir) {
 }
 
 // graph_simplification.rs:743-803: from_gfa_lines, merge_linear_paths (with or without the paths), save again
-char* orc_gfa_merge_linear_paths(const char* gfa_text, int use_paths) {
+char* orc_gfa_merge_linear_paths(const char* gfa_text, int use_paths, int renumber) {
     ORC_TRY
     auto r = UnitigGraph::from_gfa_lines(split_lines(gfa_text));
     std::vector<Sequence> none;
     merge_linear_paths(r.first, use_paths ? r.second : none);
+    if (renumber) r.first.renumber_unitigs();      // trim.rs:266-268
     return dup_out(r.first.gfa_text(use_paths ? r.second : none));   // without the paths the merged graph no longer carries them
     ORC_CATCH(nullptr)
 }

@@ -112,8 +112,8 @@ def decompress(gfa_text, out_dir):
         raise OracleError(lib().orc_last_error().decode())
 
 
-def gfa_merge_linear_paths(gfa_text, use_paths=True):
-    return _take(lib().orc_gfa_merge_linear_paths(gfa_text.encode(), int(use_paths)))
+def gfa_merge_linear_paths(gfa_text, use_paths=True, renumber=False):
+    return _take(lib().orc_gfa_merge_linear_paths(gfa_text.encode(), int(use_paths), int(renumber)))
 
 
 def gfa_merge_fixed_sets(gfa_text):

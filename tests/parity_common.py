@@ -55,4 +55,6 @@ def check_case(lib, files, k, tmpdir=None):
         got["merged_gfa"] = got["graph"].gfa_bytes().decode()
         assert got["merged_gfa"] == o.gfa_merge_linear_paths(expected), "merged GFA differs from the oracle"
         assert [got["graph"].reconstruct_original_sequence(i) for i in range(len(originals))] == originals
+        got["graph"].renumber_unitigs()     # trim.rs:266-268: merge, then renumber
+        assert got["graph"].gfa_bytes().decode() == o.gfa_merge_linear_paths(expected, renumber=True), "renumbered merged GFA differs"
         return got
