@@ -37,6 +37,7 @@ inline void ac_dev_free(void* p) { free(p); }
 inline void ac_memset(void* p, int v, size_t bytes, AcStream*) { memset(p, v, bytes); }
 inline void ac_h2d(void* d, const void* h, size_t bytes, AcStream*) { memcpy(d, h, bytes); }
 inline void ac_d2h(void* h, const void* d, size_t bytes, AcStream*) { memcpy(h, d, bytes); }
+inline void ac_copy_dd(void* dst, const void* src, size_t bytes, AcStream*) { memcpy(dst, src, bytes); }
 inline void ac_sync(AcStream*) {}
 inline void* ac_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 inline void ac_host_free(void* p) { free(p); }
@@ -91,6 +92,7 @@ inline void ac_dev_free(void* p) { if (p) cudaFree(p); }
 inline void ac_memset(void* p, int v, size_t bytes, AcStream* st) { AC_CUDA_CHECK(cudaMemsetAsync(p, v, bytes, st->s)); }
 inline void ac_h2d(void* d, const void* h, size_t bytes, AcStream* st) { AC_CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st->s)); }
 inline void ac_d2h(void* h, const void* d, size_t bytes, AcStream* st) { AC_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st->s)); }
+inline void ac_copy_dd(void* dst, const void* src, size_t bytes, AcStream* st) { AC_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st->s)); }
 inline void ac_sync(AcStream* st) { AC_CUDA_CHECK(cudaStreamSynchronize(st->s)); }
 inline void* ac_host_alloc(size_t bytes) { void* p = nullptr; AC_CUDA_CHECK(cudaMallocHost(&p, bytes ? bytes : 1)); return p; }
 inline void ac_host_free(void* p) { if (p) cudaFreeHost(p); }

@@ -74,7 +74,7 @@ private:
     bool fixed_ready = false;
     void compute_fixed();
     // repeat expansion work list: (unitig, side) pairs that satisfy the structural conditions of expand_repeats
-    struct Candidate { uint32_t idx; uint16_t side, gn; UStrand src[6]; };   // 32 B: destination, side (0 inputs / 1 outputs) and its sources inline
+    typedef ExpandCandidate Candidate;        // 32 B: destination, side (0 inputs / 1 outputs) and its sources inline (pipeline.h)
     std::vector<Candidate> cands;
     std::vector<int32_t> cand_at;             // [2U] candidate index of (unitig, side), -1 if none
     std::vector<uint64_t> dirty;              // bitmap over cands: must be (re-)evaluated
@@ -84,8 +84,10 @@ private:
     uint32_t pass_id = 0;                     // expand_repeats calls so far; rec[].flags holds the pass a unitig last changed in
     bool cands_ready = false, first_pass = true;
     void compute_candidates();
+    bool adopt_candidates(const PipelineResult& r);   // the same lists as compute_candidates(), made on the device
+    bool spec_from_device = false;
     uint32_t common_length(const Candidate& cand) const;
-    struct Deps { int32_t c[6]; };            // candidates that read unitig u: its own two, and those it exclusively feeds / is fed by
+    typedef ExpandDeps Deps;                  // candidates that read unitig u (pipeline.h)
     std::vector<Deps> deps;
     void compute_dependents();
     static constexpr size_t POSTPONED = (size_t)-1;   // apply_candidate: the shared arena was full, nothing was changed

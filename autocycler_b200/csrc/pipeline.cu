@@ -795,6 +795,104 @@ struct PackRecBody {   // structure-of-arrays -> the host's 32-byte records
         rec[s] = r;
     }
 };
+// ---- expand_repeats work list on the device (graph_simplification.rs:43-86, 190-280): everything below is decided by links,
+// paths and fixed sets; host_graph.cpp holds the same logic for graphs that were edited on the host ----
+struct FixedSeedBody {      // the ends of every sequence path are fixed (:199-208)
+    const uint64_t* path_off; const UStrand* path; uint8_t* fixed_start; uint8_t* fixed_end;
+    AC_D void operator()(uint64_t i) const {
+        if (path_off[i + 1] == path_off[i]) return;
+        const UStrand first = path[path_off[i]], last = path[path_off[i + 1] - 1];
+        if (!(first & 1u)) fixed_start[first >> 1] = 1; else fixed_end[first >> 1] = 1;
+        if (!(last & 1u)) fixed_end[last >> 1] = 1; else fixed_start[last >> 1] = 1;
+    }
+};
+struct FixedSpreadBody {    // upstream of a fixed start the end is fixed, downstream of a fixed end the start is (:213-227); reads the seeds only
+    const uint8_t* seed_start; const uint8_t* seed_end; const uint32_t* next_off; const UStrand* next; const uint32_t* prev_off; const UStrand* prev;
+    uint8_t* fixed_start; uint8_t* fixed_end;
+    AC_D void operator()(uint64_t u) const {
+        const uint32_t s = (uint32_t)u << 1;
+        if (seed_start[u]) for (uint32_t x = prev_off[s]; x < prev_off[s + 1]; ++x) { const UStrand up = prev[x]; if (!(up & 1u)) fixed_end[up >> 1] = 1; else fixed_start[up >> 1] = 1; }
+        if (seed_end[u]) for (uint32_t x = next_off[s]; x < next_off[s + 1]; ++x) { const UStrand down = next[x]; if (!(down & 1u)) fixed_start[down >> 1] = 1; else fixed_end[down >> 1] = 1; }
+    }
+};
+struct CandidateView {
+    const uint32_t* order; const uint32_t* next_off; const UStrand* next; const uint32_t* prev_off; const UStrand* prev;
+    const uint8_t* fixed_start; const uint8_t* fixed_end;
+    // get_exclusive_inputs / outputs with the guards of expand_repeats (:64-84, :233-280) for the unitig at position n of the graph order
+    AC_D bool eligible(uint32_t idx, uint32_t side) const {
+        const UStrand self = idx << 1;
+        const uint32_t* off = side == 0 ? prev_off : next_off; const UStrand* lst = side == 0 ? prev : next;
+        const uint32_t* back_off = side == 0 ? next_off : prev_off; const UStrand* back = side == 0 ? next : prev;
+        const uint32_t gn = off[self + 1] - off[self];
+        if (gn < 2 || (side == 0 ? fixed_start[idx] : fixed_end[idx])) return false;
+        for (uint32_t a = 0; a < gn; ++a) {
+            const UStrand p = lst[off[self] + a];
+            if (back_off[p + 1] - back_off[p] != 1 || back[back_off[p]] != self || (p >> 1) == idx) return false;
+            const bool rev = p & 1u;
+            if (side == 0 ? ((!rev && fixed_end[p >> 1]) || (rev && fixed_start[p >> 1])) : ((!rev && fixed_start[p >> 1]) || (rev && fixed_end[p >> 1]))) return false;
+        }
+        return true;
+    }
+};
+struct CandidateFlagBody {  // one thread per (graph position, side), in the reference's iteration order: unitig by unitig, inputs side first
+    CandidateView v; uint32_t n; uint32_t* flag;
+    AC_D void operator()(uint64_t x) const {
+        if (x == 2ull * n) { flag[x] = 0; return; }
+        flag[x] = v.eligible(v.order[x >> 1], (uint32_t)(x & 1)) ? 1u : 0u;
+    }
+};
+struct CandidateFillBody {
+    CandidateView v; const uint32_t* flag_in; const uint32_t* index; ExpandCandidate* cands; int32_t* cand_at;
+    AC_D void operator()(uint64_t x) const {
+        const uint32_t idx = v.order[x >> 1], side = (uint32_t)(x & 1);
+        const bool is_cand = index[x + 1] != index[x];
+        cand_at[2 * (size_t)idx + side] = is_cand ? (int32_t)index[x] : -1;
+        if (!is_cand) return;
+        const UStrand self = idx << 1;
+        const uint32_t* off = side == 0 ? v.prev_off : v.next_off; const UStrand* lst = side == 0 ? v.prev : v.next;
+        ExpandCandidate c; c.idx = idx; c.side = (uint16_t)side; c.gn = (uint16_t)(off[self + 1] - off[self]);
+        for (uint32_t a = 0; a < 6; ++a) c.src[a] = a < c.gn ? lst[off[self] + a] : 0u;
+        cands[index[x]] = c;
+        (void)flag_in;
+    }
+};
+struct DependentsBody {     // host_graph.cpp compute_dependents
+    const uint32_t* next_off; const UStrand* next; const uint32_t* prev_off; const UStrand* prev; const int32_t* cand_at; ExpandDeps* deps;
+    AC_D void operator()(uint64_t u) const {
+        ExpandDeps d;
+        d.c[0] = cand_at[2 * u]; d.c[1] = cand_at[2 * u + 1];
+        for (uint32_t rev = 0; rev < 2; ++rev) {
+            const UStrand s = ((uint32_t)u << 1) | rev;
+            const bool one_next = next_off[s + 1] - next_off[s] == 1, one_prev = prev_off[s + 1] - prev_off[s] == 1;
+            d.c[2 + 2 * rev] = (one_next && !(next[next_off[s]] & 1u)) ? cand_at[2 * (size_t)(next[next_off[s]] >> 1)] : -1;
+            d.c[3 + 2 * rev] = (one_prev && !(prev[prev_off[s]] & 1u)) ? cand_at[2 * (size_t)(prev[prev_off[s]] >> 1) + 1] : -1;
+        }
+        deps[u] = d;
+    }
+};
+AC_D inline char ac_complement(char c) { return c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c; }
+struct CommonLengthBody {   // get_common_end_seq (:298-312) for side 0, get_common_start_seq (:283-295) for side 1: length only
+    const ExpandCandidate* cands; const UnitigRec* rec; const char* arena; uint32_t* spec_len;
+    AC_D char at(UStrand s, uint32_t side, uint32_t i) const {
+        const UnitigRec& r = rec[s >> 1]; const char* p = arena + r.seq_off;
+        const bool at_back = (side == 0) != (bool)(s & 1u);
+        const char b = at_back ? p[r.len - 1 - i] : p[i];
+        return (s & 1u) ? ac_complement(b) : b;
+    }
+    AC_D void operator()(uint64_t ci) const {
+        const ExpandCandidate& cd = cands[ci];
+        uint32_t c = rec[cd.src[0] >> 1].len;
+        for (uint32_t a = 1; a < cd.gn; ++a) {
+            const uint32_t la = rec[cd.src[a] >> 1].len;
+            if (la < c) c = la;
+            uint32_t m = 0;
+            while (m < c && at(cd.src[a], cd.side, m) == at(cd.src[0], cd.side, m)) ++m;
+            c = m;
+        }
+        spec_len[ci] = c;
+    }
+};
+
 struct PathOffBody {
     const SeqInfo* seqs; uint32_t n_seqs; const uint64_t* run_start; uint64_t n_runs; uint64_t* path_off;
     AC_D void operator()(uint64_t i) const {
@@ -930,9 +1028,11 @@ struct DevicePipeline::Impl {
     DevBuf run_start, run_len, run_uk, run_dir, is_rep, rep_idx, run_unitig, unitigs, nchunks, chunk_off, partial, link_count, links;
     DevBuf scan_tmp[4];
     int insert_occupancy = getenv("AC_INSERT_OCC") ? atoi(getenv("AC_INSERT_OCC")) : 6;   // resident CTAs per SM the insert kernel is compiled for (5, 6 or 8)
+    DevBuf d_fixed, cand_flag, cand_index, d_cands, d_cand_at, d_deps, d_spec;
     DevBuf sort_a, sort_b, num_prefix, rank, d_len, d_depth, need, d_seq_off, d_arena, d_min_fpos, d_min_rpos;
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
+    PinBuf h_cands, h_deps, h_spec, h_fixed;
     PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
     cudaEvent_t ev[20];
@@ -1360,6 +1460,22 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
         ac_launch("number_merge", &stream, MergePassBody<NumberLess>{number_less, U, (uint32_t)width, ord_in, ord_out}, U);
         std::swap(ord_in, ord_out);
     }
+    // the work list of expand_repeats, in the numbering order just found
+    d_fixed.ensure((size_t)U * 4); ac_memset(d_fixed.p, 0, (size_t)U * 4, &stream);
+    uint8_t* seed_start = d_fixed.as<uint8_t>(); uint8_t* seed_end = seed_start + U; uint8_t* fix_start = seed_end + U; uint8_t* fix_end = fix_start + U;
+    ac_launch("fixed_seed", &stream, FixedSeedBody{d_path_off.as<uint64_t>(), d_path.as<UStrand>(), seed_start, seed_end}, n_seqs);
+    ac_copy_dd(fix_start, seed_start, (size_t)U * 2, &stream);
+    ac_launch("fixed_spread", &stream, FixedSpreadBody{seed_start, seed_end, d_next_off.as<uint32_t>(), d_next.as<UStrand>(), d_prev_off.as<uint32_t>(), d_prev.as<UStrand>(),
+                                                       fix_start, fix_end}, U);
+    const CandidateView cview{ord_in, d_next_off.as<uint32_t>(), d_next.as<UStrand>(), d_prev_off.as<uint32_t>(), d_prev.as<UStrand>(), fix_start, fix_end};
+    cand_flag.ensure((2 * (size_t)U + 1) * 4); cand_index.ensure((2 * (size_t)U + 1) * 4);
+    ac_launch("candidate_flag", &stream, CandidateFlagBody{cview, U, cand_flag.as<uint32_t>()}, 2ull * U + 1);
+    const uint64_t n_cands = exclusive_scan(cand_flag.as<uint32_t>(), cand_index.as<uint32_t>(), 2ull * U + 1);
+    d_cands.ensure((n_cands + 1) * sizeof(ExpandCandidate)); d_cand_at.ensure(2 * (size_t)U * 4 + 4); d_deps.ensure((size_t)U * sizeof(ExpandDeps) + 4); d_spec.ensure((n_cands + 1) * 4);
+    ac_launch("candidate_fill", &stream, CandidateFillBody{cview, cand_flag.as<uint32_t>(), cand_index.as<uint32_t>(), d_cands.as<ExpandCandidate>(), d_cand_at.as<int32_t>()}, 2ull * U);
+    ac_launch("dependents", &stream, DependentsBody{d_next_off.as<uint32_t>(), d_next.as<UStrand>(), d_prev_off.as<uint32_t>(), d_prev.as<UStrand>(), d_cand_at.as<int32_t>(),
+                                                    d_deps.as<ExpandDeps>()}, U);
+    ac_launch("common_length", &stream, CommonLengthBody{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_arena.as<char>(), d_spec.as<uint32_t>()}, n_cands);
     mark(11);
 
     // ---- results to the host (pinned) ----
@@ -1378,6 +1494,9 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
         h_run_start.ensure(n_runs * 8 + 8); h_run_len.ensure(n_runs * 4 + 4);
         pull(h_run_start, run_start, n_runs * 8); pull(h_run_len, run_len, n_runs * 4);
     }
+    h_cands.ensure((n_cands + 1) * sizeof(ExpandCandidate)); h_deps.ensure((size_t)U * sizeof(ExpandDeps) + 4); h_spec.ensure((n_cands + 1) * 4); h_fixed.ensure((size_t)U * 2 + 4);
+    pull(h_cands, d_cands, n_cands * sizeof(ExpandCandidate)); pull(h_deps, d_deps, (size_t)U * sizeof(ExpandDeps)); pull(h_spec, d_spec, n_cands * 4);
+    if (U) { ac_d2h(h_fixed.p, fix_start, (size_t)U * 2, &stream); d2h += (size_t)U * 2; }
     // The sequences (most of the bytes) go last: the caller gets the graph structure as soon as the small arrays have
     // landed and lists the repeat-expansion candidates while the arena is still on its way (complete() waits for it).
     mark(16);
@@ -1388,6 +1507,8 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     wait_mark(16);
     out.n_unitigs = U; out.n_runs = n_runs; out.n_seqs = n_seqs; out.n_links = n_links;
     out.rec = h_rec.as<UnitigRec>(); out.depth = h_depth.as<uint32_t>(); out.order = h_order.as<uint32_t>();
+    out.n_cands = n_cands; out.cands = h_cands.as<ExpandCandidate>(); out.deps = h_deps.as<ExpandDeps>(); out.spec_len = h_spec.as<uint32_t>();
+    out.fixed_start = h_fixed.as<uint8_t>(); out.fixed_end = h_fixed.as<uint8_t>() + U;
     out.arena = h_arena.as<char>(); out.arena_used = arena_bytes; out.arena_cap = arena_cap;
     out.next_off = h_next_off.as<uint32_t>(); out.next = h_next.as<UStrand>(); out.prev_off = h_prev_off.as<uint32_t>(); out.prev = h_prev.as<UStrand>();
     out.path_off = h_path_off.as<uint64_t>(); out.path = h_path.as<UStrand>();

@@ -39,6 +39,11 @@ struct UnitigRec {
     uint32_t flags;                            // host scratch
 };
 
+// Repeat expansion work list (graph_simplification.rs:43-86): one record per (unitig, side) that can ever shift, listed on the
+// device right after the graph is built (links, paths and fixed sets decide it; sequences only enter through spec_len).
+struct ExpandCandidate { uint32_t idx; uint16_t side, gn; uint32_t src[6]; };   // 32 B: destination, side (0 inputs / 1 outputs), its sources (UStrand)
+struct ExpandDeps { int32_t c[6]; };          // candidates that read unitig u: its own two, and those it exclusively feeds / is fed by
+
 // A unitig strand: (seed index << 1) | reverse.  The seed index is the position the unitig would have had in the
 // reference's `unitigs` vector straight after build_unitigs_from_kmer_graph (unitig_graph.rs:179-225).
 typedef uint32_t UStrand;
@@ -57,6 +62,12 @@ struct PipelineResult {
     UnitigRec* rec = nullptr;                  // [U]
     uint32_t* depth = nullptr;                 // [U]
     uint32_t* order = nullptr;                 // [U] order[n-1] = seed index of unitig number n (renumber_unitigs, unitig_graph.rs:295-315)
+    // expand_repeats candidates in the reference's iteration order, with what the host needs to apply them
+    uint64_t n_cands = 0;
+    ExpandCandidate* cands = nullptr;          // [n_cands]
+    uint32_t* spec_len = nullptr;              // [n_cands] length of the common piece of each candidate's sources on the untouched graph
+    ExpandDeps* deps = nullptr;                // [U]
+    uint8_t* fixed_start = nullptr; uint8_t* fixed_end = nullptr;   // [U] get_fixed_unitig_starts_and_ends (graph_simplification.rs:190-230)
     char* arena = nullptr; uint64_t arena_used = 0, arena_cap = 0;
     uint32_t* next_off = nullptr;              // [2U+1] CSR over strands: forward_next / reverse_next in the reference's push order
     UStrand* next = nullptr;
