@@ -145,7 +145,7 @@ static void adopt_result(ac_handle* h) {   // host graph over the device result 
     const double t0 = now_ms();
     h->graph.build(h->res, h->seqs, h->cfg.k, h->cfg.keep_positions != 0);
     h->graph.check_links();
-    h->graph.prepare_simplify();      // needs links and paths only: runs while the sequences are still being copied
+    if (!h->graph.adopt_candidates(h->res)) h->graph.prepare_simplify();   // the expand_repeats work list: made on the device, or (needing links and paths only) here while the sequences are still being copied
     h->pipe->complete(h->res);
     const double t1 = now_ms();
     const PipelineTimings& pt = h->res.t;

@@ -360,7 +360,7 @@ void HostGraph::compute_candidates() {
     exhausted.assign(cands.size(), 0);
     for (uint32_t u = 0; u < U; ++u) rec[u].flags = 0;
     first_pass = true;
-    cands_ready = true;
+    cands_ready = true; spec_from_device = false;
 }
 
 namespace {
@@ -596,6 +596,39 @@ void HostGraph::prepare_simplify() {   // the structural part of expand_repeats:
     if (!cands_ready) { compute_candidates(); prof.candidates = now_ms() - t0; }
 }
 
+// The lists compute_candidates() makes, taken from the device (pipeline.cu: CandidateFlagBody ... CommonLengthBody), which
+// listed them in the numbering order it had just sorted.  Only valid for the graph exactly as built.
+bool HostGraph::adopt_candidates(const PipelineResult& r) {
+    static const bool on_host = getenv("AC_HOST_CANDIDATES") != nullptr, cross_check = getenv("AC_CHECK_CANDIDATES") != nullptr;
+    if (!r.cands || !r.deps || !r.fixed_start || on_host) return false;
+    const double t0 = now_ms();
+    if (cross_check) {                        // tests: the host listing of the same graph must agree field by field
+        compute_candidates();
+        bool same = cands.size() == r.n_cands && memcmp(fixed_start.data(), r.fixed_start, U) == 0 && memcmp(fixed_end.data(), r.fixed_end, U) == 0;
+        for (size_t i = 0; same && i < cands.size(); ++i) {
+            same = cands[i].idx == r.cands[i].idx && cands[i].side == r.cands[i].side && cands[i].gn == r.cands[i].gn && common_length(cands[i]) == r.spec_len[i];
+            for (uint32_t a = 0; same && a < cands[i].gn; ++a) same = cands[i].src[a] == r.cands[i].src[a];
+        }
+        for (uint32_t u = 0; same && u < U; ++u) same = memcmp(&deps[u], &r.deps[u], sizeof(Deps)) == 0;
+        if (!same) throw std::runtime_error("device and host candidate lists differ");
+    }
+    const size_t n = r.n_cands;
+    const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads(), (n + U) / 32768));
+    cands.resize(n); deps.resize(U); spec_len.resize(n); spec_pass.resize(n); fixed_start.resize(U); fixed_end.resize(U);
+    parallel_tasks(T, [&](size_t t) {
+        const size_t a = n * t / T, b = n * (t + 1) / T, ua = (size_t)U * t / T, ub = (size_t)U * (t + 1) / T;
+        if (b > a) { memcpy(&cands[a], r.cands + a, (b - a) * sizeof(Candidate)); memcpy(&spec_len[a], r.spec_len + a, (b - a) * 4); }
+        if (ub > ua) { memcpy(&deps[ua], r.deps + ua, (ub - ua) * sizeof(Deps)); memcpy(&fixed_start[ua], r.fixed_start + ua, ub - ua); memcpy(&fixed_end[ua], r.fixed_end + ua, ub - ua); }
+    });
+    fixed_ready = true;
+    compute_levels();
+    dirty.assign((n + 63) / 64, 0);
+    exhausted.assign(n, 0);
+    first_pass = true; cands_ready = true; spec_from_device = true;
+    prof.candidates = now_ms() - t0;
+    return true;
+}
+
 size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
     const double t0 = now_ms();
     if (!cands_ready) { compute_candidates(); prof.candidates = now_ms() - t0; }
@@ -607,7 +640,10 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
     else for (size_t w = 0; w < dirty.size(); ++w) for (uint64_t b = dirty[w]; b; b &= b - 1) due.push_back((uint32_t)(w * 64 + (size_t)__builtin_ctzll(b)));
     static const size_t min_due = getenv("AC_EXPAND_MIN_DUE") ? (size_t)atoll(getenv("AC_EXPAND_MIN_DUE")) : 2048;   // tests lower it to drive small graphs through the levels
     const bool parallel = due.size() >= min_due && host_threads() >= 4 && n_levels <= 250 && !getenv("AC_EXPAND_SERIAL");
-    if (parallel || first_pass) {
+    if (first_pass && spec_from_device) {         // compared on the device; the records were untouched since
+        std::fill(spec_pass.begin(), spec_pass.end(), pass_id);
+        spec_from_device = false;
+    } else if (parallel || first_pass) {
         const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads() * 4, due.size() / 512));
         parallel_tasks(T, [&](size_t t) {
             for (size_t x = due.size() * t / T; x < due.size() * (t + 1) / T; ++x) { spec_len[due[x]] = common_length(cands[due[x]]); spec_pass[due[x]] = pass_id; }

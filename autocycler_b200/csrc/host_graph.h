@@ -57,6 +57,7 @@ public:
     void simplify_structure();                // graph_simplification.rs:26-40
     size_t expand_repeats();                  // graph_simplification.rs:43-86
     void prepare_simplify();                  // lists the candidates of expand_repeats ahead of time (links and paths only, no sequence bytes)
+    bool adopt_candidates(const PipelineResult& r);   // ... or takes the same lists from the device result (graph as built only)
     void merge_linear_paths(bool use_paths);  // graph_simplification.rs:315-371 (host_merge.cpp); use_paths=false is the reference's `seqs` = [] and drops the paths
     void gfa_text(const std::vector<HostSeq>& seqs, std::string& out) const;   // unitig_graph.rs:317-360
     uint64_t total_length() const;
@@ -84,7 +85,6 @@ private:
     uint32_t pass_id = 0;                     // expand_repeats calls so far; rec[].flags holds the pass a unitig last changed in
     bool cands_ready = false, first_pass = true;
     void compute_candidates();
-    bool adopt_candidates(const PipelineResult& r);   // the same lists as compute_candidates(), made on the device
     bool spec_from_device = false;
     uint32_t common_length(const Candidate& cand) const;
     typedef ExpandDeps Deps;                  // candidates that read unitig u (pipeline.h)

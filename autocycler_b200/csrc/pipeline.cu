@@ -870,7 +870,7 @@ struct DependentsBody {     // host_graph.cpp compute_dependents
         deps[u] = d;
     }
 };
-AC_D inline char ac_complement(char c) { return c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c; }
+AC_D char ac_complement(char c) { return c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c; }
 struct CommonLengthBody {   // get_common_end_seq (:298-312) for side 0, get_common_start_seq (:283-295) for side 1: length only
     const ExpandCandidate* cands; const UnitigRec* rec; const char* arena; uint32_t* spec_len;
     AC_D char at(UStrand s, uint32_t side, uint32_t i) const {
