@@ -13,6 +13,8 @@
 #include "backend.h"
 #include "host_graph.h"
 #include "host_io.h"
+#include <immintrin.h>
+#include <thread>
 #include "pipeline.h"
 
 namespace {
@@ -141,6 +143,46 @@ int ac_upload(ac_handle* h) {
     AC_GUARD_END(h)
 }
 
+// The host stages edit the pinned result buffers in place, so after a graph has been processed their lines sit (dirty) in the
+// CPU caches, and the next build's device->host copies onto the same lines run at a fraction of the link rate (measured:
+// 56 GB/s onto untouched pinned memory, 33 GB/s and less onto lines the CPU wrote; profiles/r1k_pcie_probe2.log).  When a handle
+// is reused, the previous result is therefore flushed from the caches while the GPU is busy building the next one.
+namespace {
+bool cpu_has_clflushopt() { unsigned a, b, c2, d; __asm__("cpuid" : "=a"(a), "=b"(b), "=c"(c2), "=d"(d) : "a"(7), "c"(0)); return (b >> 23) & 1; }
+__attribute__((target("clflushopt"))) void flush_lines_opt(const char* p, size_t n) { for (size_t i = 0; i < n; i += 64) _mm_clflushopt((void*)(p + i)); _mm_sfence(); }
+void flush_lines(const char* p, size_t n) {
+    static const bool opt = cpu_has_clflushopt();
+    if (opt) { flush_lines_opt(p, n); return; }
+    for (size_t i = 0; i < n; i += 64) _mm_clflush(p + i);
+    _mm_sfence();
+}
+struct ResultFlusher {
+    std::vector<std::thread> threads;
+    void start(const PipelineResult& r) {
+        static const bool off = getenv("AC_NO_RESULT_FLUSH") != nullptr;
+        if (off || !r.rec) return;
+        const size_t U = r.n_unitigs, strands = 2 * U + 1;
+        std::vector<std::pair<const char*, size_t>> ranges = {
+            {(const char*)r.rec, U * sizeof(UnitigRec)}, {(const char*)r.depth, U * 4}, {(const char*)r.order, U * 4}, {r.arena, (size_t)r.arena_cap},
+            {(const char*)r.next_off, strands * 4}, {(const char*)r.prev_off, strands * 4}, {(const char*)r.next, (size_t)r.n_links * 4}, {(const char*)r.prev, (size_t)r.n_links * 4},
+            {(const char*)r.path, (size_t)r.n_runs * 4}, {(const char*)r.path_off, ((size_t)r.n_seqs + 1) * 8}, {(const char*)r.cands, (size_t)r.n_cands * sizeof(ExpandCandidate)},
+            {(const char*)r.deps, U * sizeof(ExpandDeps)}, {(const char*)r.spec_len, (size_t)r.n_cands * 4}, {(const char*)r.fixed_start, 2 * U}};
+        size_t total = 0; for (auto& x : ranges) if (x.first) total += x.second;
+        const size_t T = std::max<size_t>(1, std::min<size_t>(8, total >> 20));
+        for (size_t t = 0; t < T; ++t)
+            threads.emplace_back([ranges, t, T] {
+                for (auto& x : ranges) {
+                    if (!x.first || !x.second) continue;
+                    const size_t lines = (x.second + 63) / 64, a = lines * t / T, b = lines * (t + 1) / T;
+                    if (b > a) flush_lines(x.first + a * 64, (b - a) * 64);
+                }
+            });
+    }
+    void join() { for (auto& th : threads) th.join(); threads.clear(); }
+    ~ResultFlusher() { join(); }
+};
+}  // namespace
+
 static void adopt_result(ac_handle* h) {   // host graph over the device result + bookkeeping shared by ac_build / ac_build_finish
     const double t0 = now_ms();
     h->graph.build(h->res, h->seqs, h->cfg.k, h->cfg.keep_positions != 0);
@@ -164,7 +206,11 @@ int ac_build(ac_handle* h) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     AC_GUARD_BEGIN
     if (!h->uploaded) return set_error(h, AC_EINVAL, "ac_upload must precede ac_build");
+    ResultFlusher flusher;
+    if (h->built) flusher.start(h->res);
+    h->pipe->before_results = [&flusher] { flusher.join(); };
     h->pipe->build(h->res, h->cfg.keep_positions != 0);
+    h->pipe->before_results = nullptr;
     adopt_result(h);
     return AC_OK;
     AC_GUARD_END(h)
@@ -226,7 +272,11 @@ int ac_runs_import(ac_handle* h, const void* src, uint64_t n) {
 int ac_build_finish(ac_handle* h) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     AC_GUARD_BEGIN
+    ResultFlusher flusher;
+    if (h->built) flusher.start(h->res);
+    h->pipe->before_results = [&flusher] { flusher.join(); };
     h->pipe->finish(h->res, h->cfg.keep_positions != 0);
+    h->pipe->before_results = nullptr;
     adopt_result(h);
     return AC_OK;
     AC_GUARD_END(h)

@@ -1053,6 +1053,7 @@ struct DevicePipeline::Impl {
 #endif
     }
     bool arena_pending = false;
+    const std::function<void()>* before_results = nullptr;   // -> DevicePipeline::before_results
     void do_complete(PipelineResult& out);
     float between(int a, int b) {
 #ifndef AC_EMULATE
@@ -1126,7 +1127,7 @@ struct DevicePipeline::Impl {
 };
 
 DevicePipeline::DevicePipeline(int device, void* stream) : impl(new Impl) {
-    impl->device = device;
+    impl->device = device; impl->before_results = &before_results;
 #ifndef AC_EMULATE
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -1479,6 +1480,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     mark(11);
 
     // ---- results to the host (pinned) ----
+    if (before_results && *before_results) (*before_results)();
     const uint64_t arena_cap = arena_bytes + arena_bytes / 4 + (1u << 20);     // head room for relocations during repeat expansion
     h_rec.ensure((size_t)U * sizeof(UnitigRec)); h_depth.ensure((size_t)U * 4);
     h_arena.ensure(arena_cap); h_next_off.ensure(((size_t)n_strands + 1) * 4); h_prev_off.ensure(((size_t)n_strands + 1) * 4);

@@ -3,6 +3,7 @@
 // order-free formulation that runs as data-parallel kernels; see DESIGN.md.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -94,6 +95,9 @@ public:
     // build() / finish() return once the graph structure is in `out`; the sequence arena and the timings are only valid
     // after complete(), which the caller invokes when it has finished the host work that needs neither.
     void complete(PipelineResult& out);
+    // called once per finish(), right before the pinned result buffers are (re)allocated and written (the caller may still be
+    // cleaning the previous result out of the CPU caches on other threads)
+    std::function<void()> before_results;
     void build(PipelineResult& out, bool keep_positions);   // kernels + D2H of the results (single GPU: all the stages below)
     // Multi-GPU stages (one process per GPU; the collectives between them are done by the caller on device pointers):
     void build_local(uint32_t seq_lo, uint32_t seq_hi, bool multi);     // table over this rank's sequences [seq_lo, seq_hi)
