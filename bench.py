@@ -54,33 +54,67 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  NVML is polled from a
+    thread every 5 ms (the timed region lasts a few hundred ms; `nvidia-smi -lms` needs longer than that to print its first
+    line); if NVML is unavailable the recipe's `nvidia-smi --query-gpu` loop is used instead."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.stop_flag, self.thread, self.max_mhz, self.source = index, [], None, False, None, None, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        mhz = int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        try:
+                            mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.samples.append((mhz, mask))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.source = "nvml"
+            self.thread = threading.Thread(target=poll, daemon=True); self.thread.start()
+            return
+        except Exception:
+            self.source = None
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        inv = {v: k for k, v in self.REASONS.items()}
         for line in self.proc.stdout:
-            self.samples.append([x.strip() for x in line.split(",")])
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 6 and f[0].isdigit():
+                if f[1].isdigit():
+                    self.max_mhz = max(self.max_mhz or 0, int(f[1]))
+                self.samples.append((int(f[0]), sum(inv[names[i]] for i in range(4) if f[2 + i].lower().startswith("active"))))
 
     def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1)
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        sm = sorted(m for m, _ in self.samples)
+        reasons = sorted({name for _, mask in self.samples for bit, name in self.REASONS.items() if mask & bit})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 def prepare_sequences(assemblies, k, threads=8):
@@ -273,7 +307,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="BASELINE.json config to run (default: the one the metric is quoted on)")
