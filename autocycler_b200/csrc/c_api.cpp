@@ -186,10 +186,15 @@ struct ResultFlusher {
 static void adopt_result(ac_handle* h) {   // host graph over the device result + bookkeeping shared by ac_build / ac_build_finish
     const double t0 = now_ms();
     h->graph.build(h->res, h->seqs, h->cfg.k, h->cfg.keep_positions != 0);
+    if (!h->graph.device_sort) { DevicePipeline* pipe = h->pipe.get(); h->graph.device_sort = [pipe](const NumberKey* k, uint32_t n, uint32_t* out) { pipe->sort_number_keys(k, n, out); }; }
+    const double ta = now_ms();
     h->graph.check_links();
+    const double tb = now_ms();
     if (!h->graph.adopt_candidates(h->res)) h->graph.prepare_simplify();   // the expand_repeats work list: made on the device, or (needing links and paths only) here while the sequences are still being copied
+    const double tc = now_ms();
     h->pipe->complete(h->res);
     const double t1 = now_ms();
+    if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[host] adopt: graph %.2f, check_links %.2f, work list %.2f, wait for sequences %.2f ms\n", ta - t0, tb - ta, tc - tb, t1 - tc);
     const PipelineTimings& pt = h->res.t;
     ac_timings& t = h->t;
     t.h2d = pt.h2d; t.pack = pt.pack; t.insert = pt.insert; t.adjacency = pt.adjacency; t.boundaries = pt.boundaries; t.runs = pt.runs;

@@ -199,7 +199,31 @@ void HostGraph::renumber() {   // unitig_graph.rs:295-315: stable sort by length
             key.prefix = v;
         }
     });
-    if (T == 1) std::sort(keys.begin(), keys.end(), less);
+    const double t_keys = now_ms();
+    static const bool host_only = getenv("AC_HOST_RENUMBER") != nullptr;
+    static const uint32_t device_min = getenv("AC_DEVICE_SORT_MIN") ? (uint32_t)atoi(getenv("AC_DEVICE_SORT_MIN")) : 16384;   // tests lower it
+    if (device_sort && !host_only && U >= device_min) {
+        // The device orders by (length, first 8 bases, current position); what 16 bytes cannot decide — equal length and prefix — is
+        // settled here, run by run, with the full comparison (rest of the sequence, depth, position).
+        std::vector<NumberKey> nk(U); std::vector<uint32_t> sorted(U);
+        parallel_tasks(T, [&](size_t t) { for (size_t n = bounds(t); n < bounds(t + 1); ++n) { nk[n].prefix = keys[n].prefix; nk[n].len = keys[n].len; nk[n].pad = 0; } });
+        device_sort(nk.data(), U, sorted.data());
+        std::vector<Key> arranged(U);
+        parallel_tasks(T, [&](size_t t) { for (size_t n = bounds(t); n < bounds(t + 1); ++n) arranged[n] = keys[sorted[n]]; });
+        keys.swap(arranged);
+        // run boundaries, then the runs of each piece (a run straddling a piece boundary belongs to the piece it starts in)
+        parallel_tasks(T, [&](size_t t) {
+            size_t n = bounds(t); const size_t stop = bounds(t + 1);
+            auto same = [&](size_t x, size_t y) { return keys[x].len == keys[y].len && keys[x].prefix == keys[y].prefix; };
+            while (n > 0 && n < stop && same(n - 1, n)) ++n;           // the run that began in the previous piece is theirs
+            while (n < stop) {
+                size_t e = n + 1;
+                while (e < U && same(n, e)) ++e;
+                if (e - n > 1) std::sort(keys.begin() + n, keys.begin() + e, less);
+                n = e;
+            }
+        });
+    } else if (T == 1) std::sort(keys.begin(), keys.end(), less);
     else {   // sample sort: splitters from a sample, every thread scatters its piece into the buckets, every bucket is sorted on its own
         const size_t B = T, per = 16;
         std::vector<Key> sample;
@@ -222,8 +246,10 @@ void HostGraph::renumber() {   // unitig_graph.rs:295-315: stable sort by length
         parallel_tasks(B, [&](size_t b) { std::sort(sorted.begin() + bucket_start[b], sorted.begin() + bucket_start[b + 1], less); });
         keys.swap(sorted);
     }
+    const double t_sort = now_ms();
     parallel_tasks(T, [&](size_t t) { for (size_t n = bounds(t); n < bounds(t + 1); ++n) { order[n] = keys[n].idx; number[keys[n].idx] = (uint32_t)n + 1; } });
     prof.renumber += now_ms() - t0;
+    if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[host] renumber: keys %.2f, sort %.2f, write %.2f ms (%zu threads)\n", t_keys - t0, t_sort - t_keys, now_ms() - t_sort, T);
 }
 
 void HostGraph::check_links() const {   // unitig_graph.rs:752-793: every link has its mirror and its prev entry

@@ -8,6 +8,7 @@
 // unitig so that repeat expansion moves bytes without reallocating.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -53,6 +54,8 @@ public:
     // unitig_graph.rs:36-48 from the device result (build, simplify_seqs, create_links, trim_overlaps, renumber, check)
     void build(const PipelineResult& r, const std::vector<HostSeq>& seqs, uint32_t k, bool keep_positions);
     void renumber();                          // unitig_graph.rs:295-315
+    // optional: sorts NumberKeys on the device (DevicePipeline::sort_number_keys); unset = the host sample sort
+    std::function<void(const NumberKey*, uint32_t, uint32_t*)> device_sort;
     void check_links() const;                 // unitig_graph.rs:752-793
     void simplify_structure();                // graph_simplification.rs:26-40
     size_t expand_repeats();                  // graph_simplification.rs:43-86

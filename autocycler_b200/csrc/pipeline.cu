@@ -670,6 +670,14 @@ struct NumberKeyBody {
         prefix[s] = v;
     }
 };
+struct NumberKeyLess {      // sort_number_keys: the part of renumber_unitigs' order that 16 bytes per unitig can decide
+    const NumberKey* key;
+    AC_D bool operator()(uint32_t a, uint32_t b) const {
+        if (key[a].len != key[b].len) return key[a].len > key[b].len;
+        if (key[a].prefix != key[b].prefix) return key[a].prefix < key[b].prefix;
+        return a < b;
+    }
+};
 struct NumberLess {
     const UnitigRec* rec; const uint32_t* depth; const char* arena; const uint64_t* prefix;
     AC_D bool operator()(uint32_t a, uint32_t b) const {
@@ -1032,7 +1040,8 @@ struct DevicePipeline::Impl {
     DevBuf sort_a, sort_b, num_prefix, rank, d_len, d_depth, need, d_seq_off, d_arena, d_min_fpos, d_min_rpos;
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
-    PinBuf h_cands, h_deps, h_spec, h_fixed;
+    PinBuf h_cands, h_deps, h_spec, h_fixed, h_keys, h_sorted;
+    DevBuf d_keys;
     PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
     cudaEvent_t ev[20];
@@ -1178,6 +1187,26 @@ void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo*
     m.seqs.ensure(n_seqs * sizeof(SeqInfo));
     ac_h2d(m.seqs.p, seqs, n_seqs * sizeof(SeqInfo), &m.stream);
     m.mark(1);
+}
+
+void DevicePipeline::sort_number_keys(const NumberKey* keys, uint32_t n, uint32_t* sorted) {
+    Impl& m = *impl; m.set_device();
+    if (n == 0) return;
+    m.h_keys.ensure((size_t)n * sizeof(NumberKey));                 // pinned staging: the copy runs at link speed and the call stays asynchronous until the sync
+    memcpy(m.h_keys.p, keys, (size_t)n * sizeof(NumberKey));
+    m.d_keys.ensure((size_t)n * sizeof(NumberKey)); m.sort_a.ensure((size_t)n * 4); m.sort_b.ensure((size_t)n * 4);
+    ac_h2d(m.d_keys.p, m.h_keys.p, (size_t)n * sizeof(NumberKey), &m.stream);
+    const NumberKeyLess less{m.d_keys.as<NumberKey>()};
+    uint32_t* in = m.sort_a.as<uint32_t>(); uint32_t* out = m.sort_b.as<uint32_t>();
+    ac_launch("number_leaf", &m.stream, SortLeafBody<NumberKeyLess>{less, n, in}, ((uint64_t)n + AC_SORT_LEAF - 1) / AC_SORT_LEAF);
+    for (uint64_t width = AC_SORT_LEAF; width < n; width *= 2) {
+        ac_launch("number_merge", &m.stream, MergePassBody<NumberKeyLess>{less, n, (uint32_t)width, in, out}, n);
+        std::swap(in, out);
+    }
+    m.h_sorted.ensure((size_t)n * 4);
+    ac_d2h(m.h_sorted.p, in, (size_t)n * 4, &m.stream);
+    ac_sync(&m.stream);
+    memcpy(sorted, m.h_sorted.p, (size_t)n * 4);
 }
 
 void DevicePipeline::find_literals(const uint8_t* ascii_host, uint64_t total_bytes, const SeqInfo* host_seq, uint32_t n, uint32_t h,

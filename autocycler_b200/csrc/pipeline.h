@@ -45,6 +45,8 @@ struct UnitigRec {
 struct ExpandCandidate { uint32_t idx; uint16_t side, gn; uint32_t src[6]; };   // 32 B: destination, side (0 inputs / 1 outputs), its sources (UStrand)
 struct ExpandDeps { int32_t c[6]; };          // candidates that read unitig u: its own two, and those it exclusively feeds / is fed by
 
+struct NumberKey { uint64_t prefix; uint32_t len; uint32_t pad; };   // first 8 bases (big-endian) and length of one unitig
+
 // A unitig strand: (seed index << 1) | reverse.  The seed index is the position the unitig would have had in the
 // reference's `unitigs` vector straight after build_unitigs_from_kmer_graph (unitig_graph.rs:179-225).
 typedef uint32_t UStrand;
@@ -110,6 +112,9 @@ public:
     void import_runs(const void* dev_ptr, uint64_t n);                  // rank 0: every rank's records, concatenated in rank order
     void finish(PipelineResult& out, bool keep_positions);              // unitigs, seeds, links, seed order, host-ready arrays
     // needles: n_needles keys of h bases each (2 words per key, kmer_key.h layout for k = h), pairwise distinct.
+    // renumber_unitigs for a graph the host has edited: sorts n keys by (length descending, first 8 bases ascending, index
+    // ascending) and writes the sorted indices; the host settles the rare ties beyond the prefix.  `keys` may be any host memory.
+    void sort_number_keys(const NumberKey* keys, uint32_t n, uint32_t* sorted);
     void find_literals(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t h,
                        const uint64_t* needle_words, uint32_t n_needles, std::vector<LiteralHit>& hits);
     unsigned long long kernel_launches() const;
