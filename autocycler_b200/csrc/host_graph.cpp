@@ -200,9 +200,11 @@ void HostGraph::renumber() {   // unitig_graph.rs:295-315: stable sort by length
         }
     });
     const double t_keys = now_ms();
-    static const bool host_only = getenv("AC_HOST_RENUMBER") != nullptr;
+    // Opt-in (AC_DEVICE_RENUMBER=1): measured on the B200 box the round trip (14 small launches, two copies, the tie pass) costs
+    // what the host sample sort costs (2.5 ms vs 2.45 ms for 106 k unitigs, profiles/r1p_*), so the host sort is the default.
+    static const bool on_device = getenv("AC_DEVICE_RENUMBER") != nullptr;
     static const uint32_t device_min = getenv("AC_DEVICE_SORT_MIN") ? (uint32_t)atoi(getenv("AC_DEVICE_SORT_MIN")) : 16384;   // tests lower it
-    if (device_sort && !host_only && U >= device_min) {
+    if (device_sort && on_device && U >= device_min) {
         // The device orders by (length, first 8 bases, current position); what 16 bytes cannot decide — equal length and prefix — is
         // settled here, run by run, with the full comparison (rest of the sequence, depth, position).
         std::vector<NumberKey> nk(U); std::vector<uint32_t> sorted(U);
