@@ -85,6 +85,15 @@ def test_config2_full_size_golden_and_round_trip(lib, tmp_path):
     o.decompress(got["gfa"], str(rec))
     for fn, recs in assemblies:
         assert open(os.path.join(rec, fn), "rb").read() == open(os.path.join(d, fn), "rb").read()
+    # the same invariants through the library itself, and the step every downstream command takes next
+    graph, originals = got["graph"], [bytes(s).decode() for _, recs in assemblies for _, s in recs]
+    assert [graph.reconstruct_original_sequence(i) for i in range(len(originals))] == originals
+    api.simplify_structure(graph)                                  # idempotent: nothing left to expand, same numbering
+    assert graph.gfa_bytes().decode() == got["gfa"]
+    api.merge_linear_paths(graph, got["seqs"])
+    merged = graph.gfa_bytes().decode()
+    assert merged == o.gfa_merge_linear_paths(got["gfa"])
+    assert [graph.reconstruct_original_sequence(i) for i in range(len(originals))] == originals
 
 
 @pytest.mark.parametrize("name,k", [("cfg3", 51), ("cfg4", 51), ("cfg4", 31), ("cfg4", 91)])
