@@ -55,7 +55,7 @@ class AcTimings(C.Structure):
 
 
 EXPORTS = ["ac_last_error", "ac_version", "ac_create", "ac_destroy", "ac_add_sequence", "ac_clear_sequences", "ac_upload",
-           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_renumber_unitigs", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
+           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_renumber_unitigs", "ac_load_gfa", "ac_decompress_gfa", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
            "ac_timings_get", "ac_compress_dir", "ac_load_sequences", "ac_sequence_get",
            "ac_build_local", "ac_entries_count", "ac_entries_export", "ac_entries_merge", "ac_runs_local", "ac_runs_export",
            "ac_runs_import", "ac_build_finish", "ac_gfa_data"]
@@ -83,6 +83,8 @@ def load_library(path=None):
     for name in ("ac_upload", "ac_build", "ac_simplify", "ac_renumber_unitigs"):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.ac_merge_linear_paths.argtypes = [C.c_void_p, C.c_int]
+    lib.ac_load_gfa.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+    lib.ac_decompress_gfa.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32]
     lib.ac_sequence_reconstruct.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.ac_counts_get.argtypes = [C.c_void_p, C.POINTER(AcCounts)]
     lib.ac_unitigs_copy.argtypes = [C.c_void_p, C.POINTER(AcUnitigs)]
@@ -185,6 +187,28 @@ class UnitigGraph:
         g._h.check(g._h.lib.ac_build(g._h.ptr))
         return g
 
+    @staticmethod
+    def from_gfa_lines(gfa_lines, lib=None, device=0):   # unitig_graph.rs:55-74 -> (UnitigGraph, [Sequence without bytes])
+        text = gfa_lines if isinstance(gfa_lines, (bytes, str)) else "\n".join(l.rstrip("\n") for l in gfa_lines) + "\n"
+        text = text.encode() if isinstance(text, str) else text
+        kg = KmerGraph(51, device=device, lib=lib)          # the handle's k is replaced by the file's KM:i: value
+        g = UnitigGraph(kg)
+        g._h.check(g._h.lib.ac_load_gfa(g._h.ptr, text, len(text)))
+        g.k_size = None
+        seqs = []
+        n = g.counts().n_sequences
+        for i in range(n):
+            sid, ln = C.c_uint16(), C.c_uint64()
+            fn, hd = C.create_string_buffer(4096), C.create_string_buffer(65536)
+            g._h.check(g._h.lib.ac_sequence_get(g._h.ptr, i, C.byref(sid), C.byref(ln), None, 0, fn, len(fn), hd, len(hd)))
+            seqs.append(Sequence(sid.value, None, fn.value.decode(), hd.value.decode(), ln.value))
+        return g, seqs
+
+    @staticmethod
+    def from_gfa_file(gfa_filename, lib=None, device=0):   # unitig_graph.rs:50-53
+        with open(gfa_filename, "rb") as f:
+            return UnitigGraph.from_gfa_lines(f.read(), lib=lib, device=device)
+
     def counts(self):
         c = AcCounts()
         self._h.check(self._h.lib.ac_counts_get(self._h.ptr, C.byref(c)))
@@ -270,6 +294,13 @@ class UnitigGraph:
 
 def simplify_structure(graph, seqs=None):   # graph_simplification.rs:26-40
     graph._h.check(graph._h.lib.ac_simplify(graph._h.ptr))
+
+
+def decompress(in_gfa, out_dir=None, out_file=None, lib=None, device=0):   # decompress.rs:27-38
+    lib = lib or load_library()
+    rc = lib.ac_decompress_gfa(os.fsencode(in_gfa), os.fsencode(out_dir) if out_dir else None, os.fsencode(out_file) if out_file else None, device, 0)
+    if rc != AC_OK:
+        raise AutocyclerGpuError(rc, lib.ac_last_error(None).decode())
 
 
 def merge_linear_paths(graph, seqs=()):   # graph_simplification.rs:315-371; seqs=None/[] merges without regard to the paths

@@ -2,7 +2,9 @@
 #include "../../include/autocycler_gpu.h"
 
 #include <sys/stat.h>
+#include <zlib.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -309,6 +311,19 @@ int ac_merge_linear_paths(ac_handle* h, int use_paths) {
     AC_GUARD_END(h)
 }
 
+int ac_load_gfa(ac_handle* h, const char* gfa_text, uint64_t length) {
+    if (!h || !gfa_text) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    h->built = false; h->gfa_ready = false; h->uploaded = false;
+    h->infos.clear(); h->loaded = LoadedInput(); h->res = PipelineResult(); h->t = ac_timings{};
+    h->graph.device_sort = nullptr;
+    h->graph.load_gfa(gfa_text, (size_t)length, h->seqs);
+    h->cfg.k = h->graph.k;
+    h->built = true;
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
 int ac_renumber_unitigs(ac_handle* h) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     AC_GUARD_BEGIN
@@ -460,7 +475,11 @@ int ac_sequence_get(const ac_handle* h, uint64_t index, uint16_t* seq_id, uint64
     const uint64_t padded = s.length + h->cfg.k - 1;
     if (seq_id) *seq_id = s.id;
     if (length) *length = s.length;
-    if (fwd) { if (cap_fwd < padded + 1) return set_error(h, AC_ERANGE, "buffer too small"); memcpy(fwd, h->ascii.p + s.start, padded); fwd[padded] = 0; }
+    if (fwd) {
+        if (!h->ascii.p || h->infos.empty()) return set_error(h, AC_EINVAL, "this handle holds a loaded graph: its sequences have no bytes (use ac_sequence_reconstruct)");
+        if (cap_fwd < padded + 1) return set_error(h, AC_ERANGE, "buffer too small");
+        memcpy(fwd, h->ascii.p + s.start, padded); fwd[padded] = 0;
+    }
     if (filename) { if (cap_fn < s.filename.size() + 1) return set_error(h, AC_ERANGE, "buffer too small"); memcpy(filename, s.filename.c_str(), s.filename.size() + 1); }
     if (header) { if (cap_hd < s.contig_header.size() + 1) return set_error(h, AC_ERANGE, "buffer too small"); memcpy(header, s.contig_header.c_str(), s.contig_header.size() + 1); }
     return AC_OK;
@@ -542,6 +561,94 @@ int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint
         fprintf(stderr, "load+repair %.1f ms | h2d %.2f pack %.2f insert %.2f adjacency %.2f boundaries %.2f runs %.2f unitigs %.2f links %.2f d2h %.2f ms"
                         " | host graph %.1f simplify %.1f gfa %.1f ms | total %.1f ms\n\n",
                 t1 - t0, t.h2d, t.pack, t.insert, t.adjacency, t.boundaries, t.runs, t.unitigs, t.links, t.d2h, t.host_graph, t.host_simplify, t.host_gfa, now_ms() - t0);
+    }
+    return AC_OK;
+    AC_GUARD_END(nullptr)
+}
+
+// `autocycler decompress` (decompress.rs:27-114): reconstructs every input contig from its path and writes them back per
+// original file (FASTA, gzip when the name ends in .gz) and/or into one FASTA file.
+int ac_decompress_gfa(const char* in_gfa, const char* out_dir, const char* out_file, int32_t device, int32_t verbose) {
+    if (!in_gfa) return set_error(nullptr, AC_EINVAL, "null argument");
+    ac_handle* h = nullptr;
+    AC_GUARD_BEGIN
+    struct stat st;
+    if (stat(in_gfa, &st) != 0) return set_error(nullptr, AC_EINPUT, std::string("file does not exist: ") + in_gfa);            // misc.rs:98-107
+    if (!S_ISREG(st.st_mode)) return set_error(nullptr, AC_EINPUT, std::string(in_gfa) + " is not a file");
+    const bool to_dir = out_dir && *out_dir, to_file = out_file && *out_file;
+    if (!to_dir && !to_file) return set_error(nullptr, AC_EINPUT, "either --out_dir or --out_file is required");                  // decompress.rs:45-47
+    if (to_dir && stat(out_dir, &st) == 0 && !S_ISDIR(st.st_mode)) return set_error(nullptr, AC_EINPUT, std::string(out_dir) + " exists but is not a directory");
+    std::string text;
+    {
+        FILE* f = fopen(in_gfa, "rb");
+        if (!f) return set_error(nullptr, AC_EIO, std::string("cannot read ") + in_gfa);
+        text.resize((size_t)st.st_size);
+        const size_t got = text.empty() ? 0 : fread(&text[0], 1, text.size(), f);
+        fclose(f);
+        if (got != text.size()) return set_error(nullptr, AC_EIO, std::string("cannot read ") + in_gfa);
+    }
+    ac_config cfg{}; cfg.k = 51; cfg.device = device;
+    int rc = ac_create(&h, &cfg);
+    if (rc != AC_OK) return rc;
+    std::unique_ptr<ac_handle, void (*)(ac_handle*)> guard(h, ac_destroy);
+    if ((rc = ac_load_gfa(h, text.data(), text.size())) != AC_OK) { g_error = h->err; return rc; }
+    if (verbose) {
+        ac_counts c{}; ac_counts_get(h, &c);
+        fprintf(stderr, "%llu unitig%s, %llu link%s\ntotal length: %llu bp\n\n", (unsigned long long)c.n_unitigs, c.n_unitigs == 1 ? "" : "s",
+                (unsigned long long)c.n_links, c.n_links == 1 ? "" : "s", (unsigned long long)c.total_length);
+    }
+    // reconstruct_original_sequences (unitig_graph.rs:362-370): per filename, in sequence order; filenames sorted when written
+    std::vector<std::string> seqs(h->seqs.size());
+    for (size_t i = 0; i < h->seqs.size(); ++i) {
+        uint64_t n = 0;
+        if ((rc = ac_sequence_reconstruct(h, i, nullptr, 0, &n)) != AC_OK) { g_error = h->err; return rc; }
+        if (n != h->seqs[i].length) return set_error(nullptr, AC_EINPUT, "reconstructed sequence does not have expected length");   // unitig_graph.rs:386
+        seqs[i].resize(n);
+        if (n && (rc = ac_sequence_reconstruct(h, i, &seqs[i][0], n, &n)) != AC_OK) { g_error = h->err; return rc; }
+    }
+    std::vector<std::string> names;
+    for (auto& s : h->seqs) names.push_back(s.filename);
+    std::sort(names.begin(), names.end()); names.erase(std::unique(names.begin(), names.end()), names.end());
+    auto first_word = [](const std::string& hd) { return hd.substr(0, hd.find(' ')); };
+    if (to_dir) {
+        { std::string d = out_dir; for (size_t i = 1; i <= d.size(); ++i) if (i == d.size() || d[i] == '/') mkdir(d.substr(0, i).c_str(), 0777); }
+        for (const std::string& name : names) {
+            const std::string path = std::string(out_dir) + "/" + name;
+            if (verbose) fprintf(stderr, "%s:\n", path.c_str());
+            std::string body;
+            for (size_t i = 0; i < h->seqs.size(); ++i)
+                if (h->seqs[i].filename == name) {
+                    if (verbose) fprintf(stderr, "  %s (%zu bp)\n", first_word(h->seqs[i].contig_header).c_str(), seqs[i].size());
+                    body += ">" + h->seqs[i].contig_header + "\n" + seqs[i] + "\n";
+                }
+            const bool gz = path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0;       // decompress.rs:96
+            if (gz) {
+                gzFile g = gzopen(path.c_str(), "wb");
+                if (!g || (body.size() && gzwrite(g, body.data(), (unsigned)body.size()) != (int)body.size())) { if (g) gzclose(g); return set_error(nullptr, AC_EIO, "cannot write " + path); }
+                gzclose(g);
+            } else {
+                FILE* f = fopen(path.c_str(), "wb");
+                if (!f || fwrite(body.data(), 1, body.size(), f) != body.size()) { if (f) fclose(f); return set_error(nullptr, AC_EIO, "cannot write " + path); }
+                fclose(f);
+            }
+            if (verbose) fprintf(stderr, "\n");
+        }
+    }
+    if (to_file) {   // decompress.rs:116-137
+        if (verbose) fprintf(stderr, "%s:\n", out_file);
+        std::string body;
+        for (const std::string& name : names) {
+            std::string clean = name; for (char& ch : clean) if (ch == ' ') ch = '_';
+            for (size_t i = 0; i < h->seqs.size(); ++i)
+                if (h->seqs[i].filename == name) {
+                    if (verbose) fprintf(stderr, "  %s__%s (%zu bp)\n", name.c_str(), first_word(h->seqs[i].contig_header).c_str(), seqs[i].size());
+                    body += ">" + clean + "__" + h->seqs[i].contig_header + "\n" + seqs[i] + "\n";
+                }
+        }
+        FILE* f = fopen(out_file, "wb");
+        if (!f || fwrite(body.data(), 1, body.size(), f) != body.size()) { if (f) fclose(f); return set_error(nullptr, AC_EIO, std::string("cannot write ") + out_file); }
+        fclose(f);
+        if (verbose) fprintf(stderr, "\n");
     }
     return AC_OK;
     AC_GUARD_END(nullptr)

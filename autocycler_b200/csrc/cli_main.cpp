@@ -1,4 +1,4 @@
-// `autocycler compress` with the reference's flags (main.rs:126-147), messages and exit codes
+// `autocycler compress` and `autocycler decompress` with the reference's flags (main.rs:126-162), messages and exit codes
 // (misc.rs:130-136: "Error: <text>" on stderr, exit 1), running the B200 path through the C ABI.
 #include <cstdio>
 #include <cstdlib>
@@ -19,7 +19,30 @@ static void usage() {
             "      --device <ORDINAL>       CUDA device [default: 0]\n");
 }
 
+// `autocycler decompress` (main.rs:150-162, decompress.rs:27-57)
+static int decompress_main(int argc, char** argv) {
+    std::string in, out_dir, out_file; int device = 0;
+    for (int i = 2; i < argc; ++i) {
+        std::string a = argv[i];
+        auto value = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "error: a value is required for '%s'\n", a.c_str()); exit(2); } return argv[++i]; };
+        if (a == "-i" || a == "--in_gfa") in = value();
+        else if (a == "-o" || a == "--out_dir") out_dir = value();
+        else if (a == "-f" || a == "--out_file") out_file = value();
+        else if (a == "--device") device = atoi(value());
+        else { fprintf(stderr, "error: unexpected argument '%s'\nUsage: autocycler decompress --in_gfa <IN_GFA> [--out_dir <DIR>] [--out_file <FASTA>]\n", a.c_str()); return 2; }
+    }
+    if (in.empty()) { fprintf(stderr, "Usage: autocycler decompress --in_gfa <IN_GFA> [--out_dir <DIR>] [--out_file <FASTA>]\n"); return 2; }
+    fprintf(stderr, "\nStarting autocycler decompress (%s)\n\nSettings:\n  --in_gfa %s\n", ac_version(), in.c_str());
+    if (!out_dir.empty()) fprintf(stderr, "  --out_dir %s\n", out_dir.c_str());
+    if (!out_file.empty()) fprintf(stderr, "  --out_file %s\n", out_file.c_str());
+    fprintf(stderr, "\n");
+    const int rc = ac_decompress_gfa(in.c_str(), out_dir.empty() ? nullptr : out_dir.c_str(), out_file.empty() ? nullptr : out_file.c_str(), device, 1);
+    if (rc != AC_OK) { fprintf(stderr, "\nError: %s\n", ac_last_error(nullptr)); return 1; }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && strcmp(argv[1], "decompress") == 0) return decompress_main(argc, argv);
     if (argc < 2 || strcmp(argv[1], "compress") != 0) { usage(); return 2; }
     std::string in, out; unsigned k = 51, max_contigs = 25, threads = 8; int device = 0;
     for (int i = 2; i < argc; ++i) {

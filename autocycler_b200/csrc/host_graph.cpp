@@ -762,6 +762,7 @@ void HostGraph::gfa_text(const std::vector<HostSeq>& seqs, std::string& out) con
         if (pc.b == path_off[pc.seq + 1]) {
             if (pc.b > pc.a) sz -= 1;                                                                                  // no comma after the last step
             sz += 8 + digits10(s.length) + 6 + s.filename.size() + 6 + s.contig_header.size() + 1;
+            if (s.cluster > 0) sz += 6 + digits10(s.cluster);                                                          // "\tCL:i:" n (unitig_graph.rs:358)
         }
         p_size[q] = sz;
     });
@@ -819,7 +820,9 @@ void HostGraph::gfa_text(const std::vector<HostSeq>& seqs, std::string& out) con
             if (last_piece) {
                 p = put_str(p, "\t*\tLN:i:", 8); p = put_uint(p, s.length);
                 p = put_str(p, "\tFN:Z:", 6); p = put_str(p, s.filename.data(), s.filename.size());
-                p = put_str(p, "\tHD:Z:", 6); p = put_str(p, s.contig_header.data(), s.contig_header.size()); *p++ = '\n';
+                p = put_str(p, "\tHD:Z:", 6); p = put_str(p, s.contig_header.data(), s.contig_header.size());
+                if (s.cluster > 0) { p = put_str(p, "\tCL:i:", 6); p = put_uint(p, s.cluster); }
+                *p++ = '\n';
             }
             if ((uint64_t)(p - base) != p_at[q] + p_size[q]) throw std::runtime_error("GFA P-line size mismatch");
         }

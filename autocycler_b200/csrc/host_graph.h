@@ -19,6 +19,7 @@ struct HostSeq {              // sequence.rs:19-28 minus the bytes (they live in
     std::string filename, contig_header;
     uint64_t length;          // L
     uint64_t start;           // global coordinate of padded byte 0
+    uint16_t cluster = 0;     // Sequence.cluster: 0 on the compress path; carried through from a loaded GFA's CL:i: tag
 };
 
 // A unitig strand: (seed index << 1) | reverse (UStrand, pipeline.h).
@@ -61,6 +62,8 @@ public:
     size_t expand_repeats();                  // graph_simplification.rs:43-86
     void prepare_simplify();                  // lists the candidates of expand_repeats ahead of time (links and paths only, no sequence bytes)
     bool adopt_candidates(const PipelineResult& r);   // ... or takes the same lists from the device result (graph as built only)
+    // UnitigGraph::from_gfa_lines (unitig_graph.rs:55-174; host_gfa_load.cpp): replaces the graph by the one in `text`, returns its sequences
+    void load_gfa(const char* text, size_t len, std::vector<HostSeq>& seqs);
     void merge_linear_paths(bool use_paths);  // graph_simplification.rs:315-371 (host_merge.cpp); use_paths=false is the reference's `seqs` = [] and drops the paths
     void gfa_text(const std::vector<HostSeq>& seqs, std::string& out) const;   // unitig_graph.rs:317-360
     uint64_t total_length() const;

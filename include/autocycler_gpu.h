@@ -140,6 +140,17 @@ int ac_load_sequences(ac_handle* h, const char* assemblies_dir, uint32_t max_con
 int ac_sequence_get(const ac_handle* h, uint64_t index, uint16_t* seq_id, uint64_t* length,
                     char* fwd_padded, uint64_t cap_fwd, char* filename, uint64_t cap_fn, char* header, uint64_t cap_hd);
 
+/* UnitigGraph::from_gfa_lines (unitig_graph.rs:55-174): replaces whatever the handle holds by the graph and the sequences of an
+ * Autocycler GFA (H/S/L/P lines; `length` bytes of text), so that the calls above that work on a built graph — ac_gfa_*,
+ * ac_sequence_reconstruct (decompress.rs:83-105), ac_merge_linear_paths, ac_simplify, ac_renumber_unitigs, ac_counts_get,
+ * ac_unitigs_copy, ac_path_copy — apply to a file written earlier.  Host only.  Errors: the reference's own (missing tags,
+ * unknown unitigs, non-zero overlaps ...), plus non-integral DP:f: depths and CL:Z: colour tags, which compress never writes. */
+int ac_load_gfa(ac_handle* h, const char* gfa_text, uint64_t length);
+
+/* `autocycler decompress` (decompress.rs:27-137): every contig of the GFA's paths written back per original file under out_dir
+ * (gzip when the name ends in .gz) and/or as one FASTA (out_file); either may be NULL, not both. */
+int ac_decompress_gfa(const char* in_gfa, const char* out_dir, const char* out_file, int32_t device, int32_t verbose);
+
 /* reconstruct_original_sequence (unitig_graph.rs:383-400; decompress.rs:83-105 writes these out): the sequence spelled by
  * the path of loaded/added sequence `index` through the current graph.  `out` may be null to query `length` only. */
 int ac_sequence_reconstruct(const ac_handle* h, uint64_t index, char* out, uint64_t cap, uint64_t* length);

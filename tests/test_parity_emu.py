@@ -137,3 +137,84 @@ def test_repeat_expansion_schedules_agree(emu, env):
             "print('AGREE')\n") % (os.path.join(ROOT, "tests"), ROOT, os.path.join(ROOT, "tests", "emu", "libautocycler_emu.so"))
     r = subprocess.run([os.sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "AGREE" in r.stdout, r.stderr[-2000:]
+
+
+def _load(emu, text):
+    g, seqs = api.UnitigGraph.from_gfa_lines(text, lib=emu)
+    return g, seqs
+
+
+@pytest.mark.parametrize("n", range(1, 15))
+def test_gfa_loader_on_the_reference_fixtures(emu, golden_dir, n):   # test_gfa.rs:15-287 through ac_load_gfa
+    text = open(os.path.join(golden_dir, f"ref_test_gfa_{n}.gfa")).read()
+    try:
+        g, seqs = _load(emu, text)
+    except api.AutocyclerGpuError as e:
+        assert "non-integral depth" in str(e) or "colour tags" in str(e), str(e)      # the two documented restrictions
+        return
+    assert g.gfa_bytes().decode() == o.gfa_roundtrip(text)                            # save(load(x)) as the reference's loader + writer give it
+    api.merge_linear_paths(g, seqs)
+    assert g.gfa_bytes().decode() == o.gfa_merge_linear_paths(text)
+
+
+def test_gfa_loader_round_trip_on_compress_output(emu):
+    """load(save(graph)) behaves like the graph: same text again, every sequence reconstructed (decompress.rs:83-105),
+    simplify_structure idempotent, merge_linear_paths + renumber as the oracle does them on the loaded file."""
+    for k, seed in [(5, 1), (9, 2), (31, 3), (51, 4), (91, 5), (51, 6), (9, 7), (31, 8)]:
+        files = cases.random_case(8800 * k + seed, k)
+        got = check_case(emu, files, k)
+        if got is None:
+            continue
+        gfa = got["gfa"]
+        g, seqs = _load(emu, gfa)
+        assert g.gfa_bytes().decode() == gfa
+        originals = [s.forward_seq[k // 2: len(s.forward_seq) - k // 2] for s in got["seqs"]]
+        assert [g.reconstruct_original_sequence(i) for i in range(len(originals))] == originals
+        assert [(s.id, s.filename, s.contig_header, s.length) for s in seqs] == [(s.id, s.filename, s.contig_header, s.length) for s in got["seqs"]]
+        api.simplify_structure(g)
+        assert g.gfa_bytes().decode() == gfa
+        api.merge_linear_paths(g, seqs)
+        assert g.gfa_bytes().decode() == o.gfa_merge_linear_paths(gfa)
+        g.renumber_unitigs()
+        assert g.gfa_bytes().decode() == o.gfa_merge_linear_paths(gfa, renumber=True)
+        g2, seqs2 = _load(emu, gfa)                        # the `&vec![]` form on a loaded graph (clean.rs:114)
+        api.merge_linear_paths(g2, None)
+        strip = lambda t: [l for l in t.splitlines() if l[0] != "P"]
+        assert strip(g2.gfa_bytes().decode()) == strip(o.gfa_merge_linear_paths(gfa, use_paths=False))
+
+
+def test_gfa_loader_errors(emu):   # unitig_graph.rs:91-157, unitig.rs:62-77
+    base = "H\tVN:Z:1.0\tKM:i:9\nS\t1\tACGT\tDP:f:2.00\nS\t2\tTTGCA\tDP:f:1.00\nL\t1\t+\t2\t+\t0M\nL\t2\t-\t1\t-\t0M\nP\t1\t1+,2+\t*\tLN:i:9\tFN:Z:a.fasta\tHD:Z:c1\n"
+    g, seqs = _load(emu, base)
+    assert g.gfa_bytes().decode() == base and g.reconstruct_original_sequence(0) == "ACGTTTGCA"
+    for bad, msg in [(base.replace("DP:f:2.00", "DP:f:2.50"), "non-integral depth"), (base.replace("\tDP:f:1.00", ""), "depth tag"),
+                     (base.replace("0M\nL", "3M\nL"), "non-zero overlap"), (base.replace("L\t1\t+\t2", "L\t1\t+\t7"), "nonexistent unitig: 7"),
+                     (base.replace("\tFN:Z:a.fasta", ""), "missing required tag"), (base.replace("LN:i:9", "LN:i:10"), "Position calculation mismatch"),
+                     (base.replace("1+,2+", "1+,3+"), "unitig 3 not found"), (base.replace("1+,2+", "1+,2"), "Invalid path strand")]:
+        with pytest.raises(api.AutocyclerGpuError, match=msg):
+            _load(emu, bad)
+
+
+def test_decompress_command(emu, tmp_path):   # decompress.rs:83-137 against the oracle's restatement of save_original_seqs_to_dir
+    import gzip
+    files = cases.random_case(424242, 31)
+    files = [(fn + (".gz" if i == 1 else ""), recs) for i, (fn, recs) in enumerate(files)]      # one gzipped input -> one gzipped output
+    d = tmp_path / "in"; cases.write_case(files, str(d))
+    gfa, yaml, st = o.compress_dir(str(d), 31)
+    gfa_path = tmp_path / "g.gfa"; gfa_path.write_text(gfa)
+    want, got = tmp_path / "want", tmp_path / "got"
+    want.mkdir()
+    o.decompress(gfa, str(want))
+    api.decompress(str(gfa_path), out_dir=str(got), out_file=str(tmp_path / "all.fasta"), lib=emu)
+    assert sorted(os.listdir(want)) == sorted(os.listdir(got))
+    single = ""
+    for fn in sorted(os.listdir(want)):
+        rd = (lambda p: gzip.open(p, "rb").read()) if fn.endswith(".gz") else (lambda p: open(p, "rb").read())
+        assert rd(os.path.join(want, fn)) == rd(os.path.join(got, fn))
+        for block in rd(os.path.join(want, fn)).decode().split(">")[1:]:
+            single += ">" + fn.replace(" ", "_") + "__" + block
+    assert open(tmp_path / "all.fasta").read() == single
+    with pytest.raises(api.AutocyclerGpuError, match="either --out_dir or --out_file is required"):
+        api.decompress(str(gfa_path), lib=emu)
+    with pytest.raises(api.AutocyclerGpuError, match="file does not exist"):
+        api.decompress(str(tmp_path / "missing.gfa"), out_dir=str(got), lib=emu)
