@@ -218,3 +218,28 @@ def test_decompress_command(emu, tmp_path):   # decompress.rs:83-137 against the
         api.decompress(str(gfa_path), lib=emu)
     with pytest.raises(api.AutocyclerGpuError, match="file does not exist"):
         api.decompress(str(tmp_path / "missing.gfa"), out_dir=str(got), lib=emu)
+
+
+def test_reference_simplify_kats_through_the_library(emu, golden_dir):
+    """graph_simplification.rs:627-671 (test_simplify_structure_1 / _2) run on the product: fixture -> ac_load_gfa ->
+    simplify_structure -> unitig sequences in graph order, against the expectations the reference's own tests hold."""
+    expect = {1: (["TTCGCTGCGCTCGCTTCGCTTT", "TGCCGTCGTCGCTGTGCA", "TGCCTGAATCGCCTA", "GCTCGGCTCG", "CGAACCAT", "TACTTGT", "GCCTT", "ATCT", "GC", "T"],
+                  ["GCATTCGCTGCGCTCGCTTCGCTTT", "TGCCGTCGTCGCTGT", "CTGAATCGCCTA", "GCTCGGCTCGA", "CGAACCAT", "TACTTGT", "GCCT", "TCT", "GC", "T"]),
+              2: (["ACCGCTGCGCTCGCTTCGCTCT", "ATGAT", "GCGC"], ["CACCGCTGCGCTCGCTTCGCTCTAT", "CG", "G"])}
+    for n, (before, after) in expect.items():
+        g, seqs = _load(emu, open(os.path.join(golden_dir, f"ref_test_gfa_{n}.gfa")).read())
+        assert [u["seq"] for u in g.unitigs()] == before
+        api.simplify_structure(g)
+        assert [u["seq"] for u in g.unitigs()] == after
+
+
+def test_reference_merge_kats_through_the_library(emu, golden_dir):   # graph_simplification.rs:742-801 on the product
+    def merged(n):
+        g, seqs = _load(emu, open(os.path.join(golden_dir, f"ref_test_gfa_{n}.gfa")).read())
+        api.merge_linear_paths(g, seqs)
+        return {u["number"]: u["seq"] for u in g.unitigs()}
+    assert merged(3) == {8: "TTCGCTGCGCTCGCTTCGCTTTTGCACAGCGACGACGGCATGCCTGAATCGCCTA", 9: "GCTCGGCTCGATGGTTCG", 10: "TACTTGTAAGGC"}
+    assert merged(4) == {6: "ACGACTACGAGCACGAGTCGTCGTCGTAACTGACT", 7: "GCTCGGTG"}
+    m5 = merged(5)
+    assert len(m5) == 5 and m5[7] == "AAATGCGACTGTG"
+    assert len(merged(14)) == 11

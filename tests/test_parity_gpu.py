@@ -141,3 +141,26 @@ def test_cli_binary(lib, tmp_path):
     assert open(os.path.join(out, "input_assemblies.yaml")).read() == yaml
     r = subprocess.run([exe, "compress", "-i", d, "-a", out, "--kmer", "50"], capture_output=True, text=True)
     assert r.returncode == 1 and "Error: --kmer must be odd" in r.stderr      # compress.rs:58, misc.rs:130-136
+
+
+def test_loaded_graphs_and_reference_kats(lib, golden_dir, tmp_path):
+    """The host-side rows after compress, in the CUDA build: the reference's simplify / merge KATs on its own GFA fixtures
+    (graph_simplification.rs:627-671, 742-801) through ac_load_gfa, and decompress of a graph this GPU just built."""
+    text = lambda n: open(os.path.join(golden_dir, f"ref_test_gfa_{n}.gfa")).read()
+    g, seqs = api.UnitigGraph.from_gfa_lines(text(1), lib=lib)
+    api.simplify_structure(g)
+    assert [u["seq"] for u in g.unitigs()] == ["GCATTCGCTGCGCTCGCTTCGCTTT", "TGCCGTCGTCGCTGT", "CTGAATCGCCTA", "GCTCGGCTCGA", "CGAACCAT", "TACTTGT", "GCCT", "TCT", "GC", "T"]
+    g, seqs = api.UnitigGraph.from_gfa_lines(text(3), lib=lib)
+    api.merge_linear_paths(g, seqs)
+    assert {u["number"]: u["seq"] for u in g.unitigs()} == {8: "TTCGCTGCGCTCGCTTCGCTTTTGCACAGCGACGACGGCATGCCTGAATCGCCTA", 9: "GCTCGGCTCGATGGTTCG", 10: "TACTTGTAAGGC"}
+    for n in range(1, 15):
+        g, seqs = api.UnitigGraph.from_gfa_lines(text(n), lib=lib)
+        assert g.gfa_bytes().decode() == o.gfa_roundtrip(text(n))
+    d = str(tmp_path / "in"); out = str(tmp_path / "out")
+    assemblies = synth.make_assemblies("d", n_assemblies=4, replicon_lengths=[60_000, 4_000], seed=21)
+    synth.write_assemblies(assemblies, d)
+    got = run_library(lib, d, 51)
+    gfa_path = str(tmp_path / "g.gfa"); open(gfa_path, "w").write(got["gfa"])
+    api.decompress(gfa_path, out_dir=out, lib=lib)
+    for fn, recs in assemblies:
+        assert open(os.path.join(out, fn), "rb").read() == open(os.path.join(d, fn), "rb").read()
