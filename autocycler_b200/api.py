@@ -55,7 +55,7 @@ class AcTimings(C.Structure):
 
 
 EXPORTS = ["ac_last_error", "ac_version", "ac_create", "ac_destroy", "ac_add_sequence", "ac_clear_sequences", "ac_upload",
-           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_renumber_unitigs", "ac_load_gfa", "ac_decompress_gfa", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
+           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_renumber_unitigs", "ac_load_gfa", "ac_decompress_gfa", "ac_pairwise_distances", "ac_distance_matrix_text", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
            "ac_timings_get", "ac_compress_dir", "ac_load_sequences", "ac_sequence_get",
            "ac_build_local", "ac_entries_count", "ac_entries_export", "ac_entries_merge", "ac_runs_local", "ac_runs_export",
            "ac_runs_import", "ac_build_finish", "ac_gfa_data"]
@@ -84,6 +84,8 @@ def load_library(path=None):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.ac_merge_linear_paths.argtypes = [C.c_void_p, C.c_int]
     lib.ac_load_gfa.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+    lib.ac_pairwise_distances.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint64]
+    lib.ac_distance_matrix_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.ac_decompress_gfa.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32]
     lib.ac_sequence_reconstruct.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.ac_counts_get.argtypes = [C.c_void_p, C.POINTER(AcCounts)]
@@ -276,6 +278,19 @@ class UnitigGraph:
         n = C.c_uint64(); ptr = C.c_void_p()
         self._h.check(self._h.lib.ac_gfa_data(self._h.ptr, C.byref(ptr), C.byref(n)))
         return memoryview((C.c_char * n.value).from_address(ptr.value)) if n.value else memoryview(b"")
+
+    def pairwise_contig_distances(self):   # cluster.rs:132-151 -> S x S list of lists (row a, column b)
+        S = self.counts().n_sequences
+        buf = (C.c_double * max(1, S * S))()
+        self._h.check(self._h.lib.ac_pairwise_distances(self._h.ptr, buf, S * S))
+        return [[buf[a * S + b] for b in range(S)] for a in range(S)]
+
+    def distance_matrix_text(self):   # cluster.rs:160-176
+        n = C.c_uint64()
+        self._h.check(self._h.lib.ac_distance_matrix_text(self._h.ptr, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(max(1, n.value))
+        self._h.check(self._h.lib.ac_distance_matrix_text(self._h.ptr, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value].decode()
 
     def renumber_unitigs(self):   # unitig_graph.rs:295-315
         self._h.check(self._h.lib.ac_renumber_unitigs(self._h.ptr))

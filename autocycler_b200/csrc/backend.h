@@ -29,6 +29,7 @@ template <class T> inline T ac_ld_volatile(const T* p) { return *p; }
 template <class T> inline T ac_ld_16(const T* p) { return *p; }   // one 16-byte load of a 16-byte record
 inline uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 inline uint32_t ac_popc(uint32_t v) { return (uint32_t)__builtin_popcount(v); }
+inline int ac_ctz(uint32_t v) { return __builtin_ctz(v); }
 
 struct AcStream { int dummy; };
 
@@ -82,6 +83,7 @@ template <class T> AC_D T ac_ld_16(const T* p) {   // one 16-byte L2 (cache-glob
 }
 AC_D uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 AC_D uint32_t ac_popc(uint32_t v) { return (uint32_t)__popc(v); }
+AC_D int ac_ctz(uint32_t v) { return __ffs((int)v) - 1; }
 AC_D uint64_t ac_atomic_or(uint64_t* p, uint64_t v) { return (uint64_t)atomicOr((unsigned long long*)p, (unsigned long long)v); }
 #endif
 

@@ -324,6 +324,75 @@ int ac_load_gfa(ac_handle* h, const char* gfa_text, uint64_t length) {
     AC_GUARD_END(h)
 }
 
+// cluster.rs:132-151: distances[a][b] = 1 - (length of the unitigs shared by a's and b's paths) / (length of a's unitigs), in the order
+// of the handle's sequences.  The shared lengths are whole numbers found on the device; the one division per pair is done here in
+// f64 exactly as the reference does it.
+int ac_pairwise_distances(ac_handle* h, double* out, uint64_t cap) {
+    if (!h || !out) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    if (!h->built) return set_error(h, AC_EINVAL, "a graph must be built or loaded before ac_pairwise_distances");
+    const HostGraph& g = h->graph;
+    const uint64_t S = h->seqs.size();
+    if (cap < S * S) return set_error(h, AC_ERANGE, "buffer too small");
+    std::vector<uint32_t> len(g.U);
+    for (uint32_t u = 0; u < g.U; ++u) len[u] = g.rec[u].len;
+    std::vector<uint64_t> shared(S * S);
+    h->pipe->pair_shared_lengths(g.path, g.path_off, (uint32_t)S, len.data(), g.U, shared.data());
+    for (uint64_t a = 0; a < S; ++a) {
+        const double a_len = (double)(uint32_t)shared[a * S + a];                    // the reference sums u32 lengths, then converts
+        for (uint64_t b = 0; b < S; ++b) out[a * S + b] = 1.0 - ((double)shared[a * S + b] / a_len);
+    }
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
+// save_distance_matrix (cluster.rs:160-176): count, then one row per sequence: its Display form (sequence.rs:112-135) and the
+// distances with eight decimals.
+int ac_distance_matrix_text(ac_handle* h, char* out, uint64_t cap, uint64_t* length) {
+    if (!h || !length) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    const uint64_t S = h->seqs.size();
+    std::vector<double> d(std::max<uint64_t>(1, S * S));
+    const int rc = ac_pairwise_distances(h, d.data(), S * S);
+    if (rc != AC_OK) return rc;
+    auto lower = [](std::string s) { for (char& c : s) if (c >= 'A' && c <= 'Z') c = (char)(c + 32); return s; };
+    auto weight = [&](const std::string& header, const std::string& key) -> uint64_t {   // sequence.rs:96-108
+        const std::string low = lower(header);
+        for (size_t a = 0; a < low.size();) {
+            while (a < low.size() && isspace((unsigned char)low[a])) ++a;
+            size_t b = a; while (b < low.size() && !isspace((unsigned char)low[b])) ++b;
+            if (b > a && low.compare(a, key.size(), key) == 0 && b - a > key.size()) {
+                const std::string v = low.substr(a + key.size(), b - a - key.size());
+                const size_t first = v[0] == '+' ? 1 : 0;
+                if (v.size() > first && v.find_first_not_of("0123456789", first) == std::string::npos) return strtoull(v.c_str(), nullptr, 10);
+            }
+            a = b;
+        }
+        return 1;
+    };
+    std::string text = std::to_string(S) + "\n";
+    for (uint64_t a = 0; a < S; ++a) {
+        const HostSeq& s = h->seqs[a];
+        const std::string low = lower(s.contig_header);
+        std::vector<std::string> extras;
+        if (low.find("autocycler_trusted") != std::string::npos) extras.push_back("trusted");
+        if (low.find("autocycler_ignore") != std::string::npos) extras.push_back("ignored");
+        const uint64_t cw = weight(s.contig_header, "autocycler_cluster_weight="), nw = weight(s.contig_header, "autocycler_consensus_weight=");
+        if (cw != 1) extras.push_back("cluster weight = " + std::to_string(cw));
+        if (nw != 1) extras.push_back("consensus weight = " + std::to_string(nw));
+        text += s.filename + " " + s.contig_header.substr(0, s.contig_header.find(' ')) + " (" + std::to_string(s.length) + " bp)";
+        if (!extras.empty()) { text += " ["; for (size_t i = 0; i < extras.size(); ++i) { if (i) text += ", "; text += extras[i]; } text += "]"; }
+        for (uint64_t b = 0; b < S; ++b) { char buf[64]; snprintf(buf, sizeof buf, "\t%.8f", d[a * S + b]); text += buf; }
+        text += "\n";
+    }
+    *length = text.size();
+    if (!out) return AC_OK;
+    if (cap < text.size()) return set_error(h, AC_ERANGE, "buffer too small");
+    memcpy(out, text.data(), text.size());
+    return AC_OK;
+    AC_GUARD_END(h)
+}
+
 int ac_renumber_unitigs(ac_handle* h) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     AC_GUARD_BEGIN

@@ -901,6 +901,30 @@ struct CommonLengthBody {   // get_common_end_seq (:298-312) for side 0, get_com
     }
 };
 
+// ---- contig distances (cluster.rs:132-151): which sequences pass through each unitig, then every pair of them shares its length ----
+struct PathMemberBody {
+    const UStrand* path; const uint64_t* path_off; uint32_t n_seqs, words; uint32_t* member;
+    AC_D void operator()(uint64_t x) const {
+        uint32_t lo = 0, hi = n_seqs;                    // the sequence whose path holds step x
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (path_off[mid] <= x) lo = mid; else hi = mid; }
+        ac_atomic_or(&member[(size_t)(path[x] >> 1) * words + (lo >> 5)], 1u << (lo & 31));
+    }
+};
+struct PairShareBody {
+    const uint32_t* member; const uint32_t* unitig_len; uint32_t n_seqs, words; unsigned long long* shared;
+    AC_D void operator()(uint64_t u) const {
+        const uint32_t* m = member + (size_t)u * words;
+        const unsigned long long len = unitig_len[u];
+        for (uint32_t wa = 0; wa < words; ++wa)
+            for (uint32_t ba = m[wa]; ba; ba &= ba - 1) {
+                const uint32_t a = (wa << 5) + (uint32_t)ac_ctz(ba);
+                for (uint32_t wb = 0; wb < words; ++wb)
+                    for (uint32_t bb = m[wb]; bb; bb &= bb - 1)
+                        ac_atomic_add(&shared[(size_t)a * n_seqs + (wb << 5) + (uint32_t)ac_ctz(bb)], len);
+            }
+    }
+};
+
 struct PathOffBody {
     const SeqInfo* seqs; uint32_t n_seqs; const uint64_t* run_start; uint64_t n_runs; uint64_t* path_off;
     AC_D void operator()(uint64_t i) const {
@@ -1041,7 +1065,7 @@ struct DevicePipeline::Impl {
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
     PinBuf h_cands, h_deps, h_spec, h_fixed, h_keys, h_sorted;
-    DevBuf d_keys;
+    DevBuf d_keys, dist_member, dist_shared;
     PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
     cudaEvent_t ev[20];
@@ -1207,6 +1231,24 @@ void DevicePipeline::sort_number_keys(const NumberKey* keys, uint32_t n, uint32_
     ac_d2h(m.h_sorted.p, in, (size_t)n * 4, &m.stream);
     ac_sync(&m.stream);
     memcpy(sorted, m.h_sorted.p, (size_t)n * 4);
+}
+
+void DevicePipeline::pair_shared_lengths(const UStrand* path, const uint64_t* path_off, uint32_t n, const uint32_t* unitig_len, uint32_t U, uint64_t* shared) {
+    Impl& m = *impl; m.set_device();
+    if (n == 0) return;
+    const uint64_t steps = path_off[n];
+    const uint32_t words = (n + 31) / 32;
+    m.d_path.ensure(steps * 4 + 4); m.d_path_off.ensure(((size_t)n + 1) * 8); m.d_len.ensure((size_t)U * 4 + 4);
+    m.dist_member.ensure((size_t)U * words * 4 + 4); m.dist_shared.ensure((size_t)n * n * 8);
+    if (steps) ac_h2d(m.d_path.p, path, steps * 4, &m.stream);
+    ac_h2d(m.d_path_off.p, path_off, ((size_t)n + 1) * 8, &m.stream);
+    if (U) ac_h2d(m.d_len.p, unitig_len, (size_t)U * 4, &m.stream);
+    ac_memset(m.dist_member.p, 0, (size_t)U * words * 4 + 4, &m.stream);
+    ac_memset(m.dist_shared.p, 0, (size_t)n * n * 8, &m.stream);
+    ac_launch("path_member", &m.stream, PathMemberBody{m.d_path.as<UStrand>(), m.d_path_off.as<uint64_t>(), n, words, m.dist_member.as<uint32_t>()}, steps);
+    ac_launch("pair_share", &m.stream, PairShareBody{m.dist_member.as<uint32_t>(), m.d_len.as<uint32_t>(), n, words, m.dist_shared.as<unsigned long long>()}, U);
+    ac_d2h(shared, m.dist_shared.p, (size_t)n * n * 8, &m.stream);
+    ac_sync(&m.stream);
 }
 
 void DevicePipeline::find_literals(const uint8_t* ascii_host, uint64_t total_bytes, const SeqInfo* host_seq, uint32_t n, uint32_t h,

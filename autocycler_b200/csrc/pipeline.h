@@ -115,6 +115,9 @@ public:
     // renumber_unitigs for a graph the host has edited: sorts n keys by (length descending, first 8 bases ascending, index
     // ascending) and writes the sorted indices; the host settles the rare ties beyond the prefix.  `keys` may be any host memory.
     void sort_number_keys(const NumberKey* keys, uint32_t n, uint32_t* sorted);
+    // cluster.rs:132-151 pairwise_contig_distances, the integer part: shared[a * n_seqs + b] = total length of the unitigs that the
+    // paths of sequences a and b have in common (the diagonal is the length of a's own unitig set).  Host arrays in, host array out.
+    void pair_shared_lengths(const UStrand* path, const uint64_t* path_off, uint32_t n_seqs, const uint32_t* unitig_len, uint32_t n_unitigs, uint64_t* shared);
     void find_literals(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t h,
                        const uint64_t* needle_words, uint32_t n_needles, std::vector<LiteralHit>& hits);
     unsigned long long kernel_launches() const;

@@ -147,6 +147,12 @@ int ac_sequence_get(const ac_handle* h, uint64_t index, uint16_t* seq_id, uint64
  * unknown unitigs, non-zero overlaps ...), plus non-integral DP:f: depths and CL:Z: colour tags, which compress never writes. */
 int ac_load_gfa(ac_handle* h, const char* gfa_text, uint64_t length);
 
+/* pairwise_contig_distances (cluster.rs:132-151), the all-against-all step of `autocycler cluster`: out[a * S + b] for the S sequences of
+ * the handle (built or loaded graph); the unitig-set intersections are computed on the GPU.  ac_distance_matrix_text renders
+ * save_distance_matrix's file (cluster.rs:160-176); `out` may be NULL to query the length. */
+int ac_pairwise_distances(ac_handle* h, double* out, uint64_t cap);
+int ac_distance_matrix_text(ac_handle* h, char* out, uint64_t cap, uint64_t* length);
+
 /* `autocycler decompress` (decompress.rs:27-137): every contig of the GFA's paths written back per original file under out_dir
  * (gzip when the name ends in .gz) and/or as one FASTA (out_file); either may be NULL, not both. */
 int ac_decompress_gfa(const char* in_gfa, const char* out_dir, const char* out_file, int32_t device, int32_t verbose);

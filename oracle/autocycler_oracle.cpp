@@ -188,10 +188,25 @@ std::string Sequence::contig_description() const {   // misc.rs:467-471 after_fi
 }
 bool Sequence::is_ignored() const { return lower(contig_header).find("autocycler_ignore") != std::string::npos; }
 bool Sequence::is_trusted() const { return lower(contig_header).find("autocycler_trusted") != std::string::npos; }
-std::string Sequence::display() const {   // sequence.rs:112-135 (extras other than trusted/ignored omitted: stderr only)
+static size_t header_weight(const std::string& contig_header, const std::string& key) {   // sequence.rs:96-108
+    const std::string low = lower(contig_header);
+    for (const std::string& token : split_whitespace(low))
+        if (token.compare(0, key.size(), key) == 0) {
+            const std::string v = token.substr(key.size());
+            if (!v.empty() && v.find_first_not_of("0123456789", v[0] == '+' ? 1 : 0) == std::string::npos && v != "+") return (size_t)strtoull(v.c_str(), nullptr, 10);
+        }
+    return 1;
+}
+size_t Sequence::cluster_weight() const { return header_weight(contig_header, "autocycler_cluster_weight="); }
+size_t Sequence::consensus_weight() const { return header_weight(contig_header, "autocycler_consensus_weight="); }
+std::string Sequence::display() const {   // sequence.rs:112-135
+    std::vector<std::string> extras;
+    if (is_trusted()) extras.push_back("trusted");
+    if (is_ignored()) extras.push_back("ignored");
+    if (cluster_weight() != 1) extras.push_back("cluster weight = " + std::to_string(cluster_weight()));
+    if (consensus_weight() != 1) extras.push_back("consensus weight = " + std::to_string(consensus_weight()));
     std::string s = filename + " " + contig_name() + " (" + std::to_string(length) + " bp)";
-    if (is_trusted()) s += " [trusted]";
-    if (is_ignored()) s += " [ignored]";
+    if (!extras.empty()) { s += " ["; for (size_t i = 0; i < extras.size(); ++i) { if (i) s += ", "; s += extras[i]; } s += "]"; }
     return s;
 }
 
@@ -1126,6 +1141,39 @@ void merge_linear_paths(UnitigGraph& graph, const std::vector<Sequence>& seqs) {
     graph.delete_dangling_links();
     graph.build_unitig_index();
     graph.check_links();
+}
+
+// ---------------------------------------------------------------------------------------------
+// cluster.rs:132-176 pairwise_contig_distances + save_distance_matrix
+// ---------------------------------------------------------------------------------------------
+std::string pairwise_distance_matrix(const UnitigGraph& graph, const std::vector<Sequence>& sequences) {
+    std::unordered_map<uint32_t, uint32_t> unitig_lengths;
+    for (auto& u : graph.unitigs) unitig_lengths[u->number] = u->length();
+    std::unordered_map<uint16_t, std::unordered_set<uint32_t>> sequence_unitigs;
+    for (auto& s : sequences) {
+        std::unordered_set<uint32_t> set;
+        for (auto& step : graph.get_unitig_path_for_sequence(s)) set.insert(step.first);
+        sequence_unitigs[s.id] = std::move(set);
+    }
+    std::map<std::pair<uint16_t, uint16_t>, double> distances;
+    for (auto& seq_a : sequences) {
+        const auto& a = sequence_unitigs.at(seq_a.id);
+        uint32_t a_sum = 0; for (uint32_t u : a) a_sum += unitig_lengths.at(u);      // sum::<u32>()
+        const double a_len = (double)a_sum;
+        for (auto& seq_b : sequences) {
+            const auto& b = sequence_unitigs.at(seq_b.id);
+            double ab_len = 0.0;                                                       // f64 sum of whole numbers: exact in any order
+            for (uint32_t u : a) if (b.count(u)) ab_len += (double)unitig_lengths.at(u);
+            distances[{seq_a.id, seq_b.id}] = 1.0 - (ab_len / a_len);
+        }
+    }
+    std::string out = std::to_string(sequences.size()) + "\n";
+    for (auto& seq_a : sequences) {
+        out += seq_a.display();
+        for (auto& seq_b : sequences) { char buf[64]; snprintf(buf, sizeof buf, "\t%.8f", distances.at({seq_a.id, seq_b.id})); out += buf; }
+        out += "\n";
+    }
+    return out;
 }
 
 // ---------------------------------------------------------------------------------------------

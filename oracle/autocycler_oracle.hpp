@@ -58,6 +58,8 @@ struct Sequence {
     bool is_ignored() const;
     bool is_trusted() const;
     std::string display() const;
+    size_t cluster_weight() const;      // sequence.rs:96-101
+    size_t consensus_weight() const;    // sequence.rs:103-108
 };
 
 std::string reverse_complement(const std::string& s);                       // misc.rs:324-342
@@ -93,6 +95,8 @@ struct Kmer {
     size_t depth() const { return positions.size(); }
     bool first_position() const { for (auto& p : positions) if (p.pos == 0) return true; return false; }
     std::string display() const;
+    size_t cluster_weight() const;      // sequence.rs:96-101
+    size_t consensus_weight() const;    // sequence.rs:103-108
 };
 
 // kmer_graph.rs:73-181
@@ -197,6 +201,9 @@ void merge_linear_paths(UnitigGraph& graph, const std::vector<Sequence>& seqs);
 void merge_fixed_sets(const UnitigGraph& graph, const std::vector<Sequence>& seqs, std::unordered_set<uint32_t>& fixed_starts,
                       std::unordered_set<uint32_t>& fixed_ends);           // the two sets merge_linear_paths works from (:330-331)
 std::string merge_unitig_seqs(const std::vector<UnitigStrand>& path);      // :490-500
+
+// cluster.rs:132-176: all-against-all contig distances from the unitig sets of the paths, as the PHYLIP-style matrix file
+std::string pairwise_distance_matrix(const UnitigGraph& graph, const std::vector<Sequence>& sequences);
 
 // decompress.rs:83-114
 void save_original_seqs_to_dir(const std::string& out_dir, const UnitigGraph& g, const std::vector<Sequence>& seqs);

@@ -182,6 +182,14 @@ int orc_decompress(const char* gfa_text, const char* out_dir) {
     ORC_CATCH(1)
 }
 
+// cluster.rs:132-176: the distance matrix file for the sequences of a GFA
+char* orc_pairwise_distances(const char* gfa_text) {
+    ORC_TRY
+    auto r = UnitigGraph::from_gfa_lines(split_lines(gfa_text));
+    return dup_out(pairwise_distance_matrix(r.first, r.second));
+    ORC_CATCH(nullptr)
+}
+
 // graph_simplification.rs:743-803: from_gfa_lines, merge_linear_paths (with or without the paths), save again
 char* orc_gfa_merge_linear_paths(const char* gfa_text, int use_paths, int renumber) {
     ORC_TRY

@@ -40,7 +40,7 @@ def lib():
                      "orc_compress_dir", "orc_compress_seqs", "orc_gfa_roundtrip", "orc_gfa_unitig_seqs",
                      "orc_gfa_exclusive", "orc_gfa_common_seq", "orc_unitig_shift", "orc_unitig_from_kmers",
                      "orc_position_display", "orc_reverse_complement", "orc_gfa_merge_linear_paths",
-                     "orc_gfa_merge_fixed_sets"):
+                     "orc_gfa_merge_fixed_sets", "orc_pairwise_distances"):
             getattr(_lib, name).restype = C.c_void_p
     return _lib
 
@@ -110,6 +110,10 @@ def gfa_roundtrip(gfa_text):
 def decompress(gfa_text, out_dir):
     if lib().orc_decompress(gfa_text.encode(), out_dir.encode()) != 0:
         raise OracleError(lib().orc_last_error().decode())
+
+
+def pairwise_distances(gfa_text):   # cluster.rs:132-176 -> text of the distance matrix file
+    return _take(lib().orc_pairwise_distances(gfa_text.encode()))
 
 
 def gfa_merge_linear_paths(gfa_text, use_paths=True, renumber=False):

@@ -47,6 +47,7 @@ def check_case(lib, files, k, tmpdir=None):
         assert (got["after"].n_unitigs, got["after"].n_links, got["after"].total_length) == \
                (st.unitigs_after, st.links_after, st.length_after)
         assert got["gfa"] == expected, "GFA differs from the oracle"
+        assert got["graph"].distance_matrix_text() == o.pairwise_distances(expected), "distance matrix (cluster.rs:132-176) differs from the oracle"
         originals = [s.forward_seq[k // 2: len(s.forward_seq) - k // 2] for s in got["seqs"]]
         # tests.rs:114-127: every input contig comes back from its path (end repair only ever touches the dots)
         assert [got["graph"].reconstruct_original_sequence(i) for i in range(len(originals))] == originals
@@ -58,3 +59,8 @@ def check_case(lib, files, k, tmpdir=None):
         got["graph"].renumber_unitigs()     # trim.rs:266-268: merge, then renumber
         assert got["graph"].gfa_bytes().decode() == o.gfa_merge_linear_paths(expected, renumber=True), "renumbered merged GFA differs"
         return got
+
+
+def check_distances(graph, gfa_text):
+    """cluster.rs:132-176 on the graph `gfa_text` was saved from: same matrix file as the oracle's restatement writes."""
+    assert graph.distance_matrix_text() == o.pairwise_distances(gfa_text)

@@ -243,3 +243,17 @@ def test_reference_merge_kats_through_the_library(emu, golden_dir):   # graph_si
     m5 = merged(5)
     assert len(m5) == 5 and m5[7] == "AAATGCGACTGTG"
     assert len(merged(14)) == 11
+
+
+def test_pairwise_distances_on_loaded_graphs_and_header_flags(emu, golden_dir):   # cluster.rs:132-176, sequence.rs:96-135
+    text = open(os.path.join(golden_dir, "ref_test_gfa_14.gfa")).read()
+    g, seqs = _load(emu, text)
+    assert g.distance_matrix_text() == o.pairwise_distances(text)
+    d = g.pairwise_contig_distances()
+    assert d[0][0] == 0.0 and abs(d[0][1] - 0.01980198) < 1e-8 and abs(d[2][0] - 0.01052632) < 1e-8      # asymmetric by construction
+    flagged = text.replace("HD:Z:a_2", "HD:Z:a_2 Autocycler_Trusted autocycler_cluster_weight=3").replace("HD:Z:b_2", "HD:Z:b_2 autocycler_consensus_weight=2 autocycler_ignore")
+    assert flagged != text
+    g, seqs = _load(emu, flagged)
+    out = g.distance_matrix_text()
+    assert out == o.pairwise_distances(flagged)
+    assert "[trusted, cluster weight = 3]" in out and "[ignored, consensus weight = 2]" in out
