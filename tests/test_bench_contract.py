@@ -1,0 +1,34 @@
+"""The reference arm of bench.py runs on CPU (it times the oracle), so its half of the driver's contract can be checked here:
+one JSON line with the keys the driver reads, the same metric/unit/config as the B200 arm, and no work on ranks other than 0."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(env=None, *args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", *args], capture_output=True, text=True,
+                          env={**os.environ, **(env or {})}, timeout=900, cwd=ROOT)
+
+
+def test_reference_arm_line():
+    r = run(None, "--steps", "1", "--warmup", "0")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "Mbp/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["metric"] == json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"] or "Mbp/sec" in d["metric"]
+    assert d["value"] > 0 and d["e2e"] == {"value": d["value"], "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "workload" in d["config"] and "sample" in d["config"]
+
+
+def test_reference_arm_other_ranks_do_nothing():
+    r = run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2", "--steps", "1", "--warmup", "0")
+    assert r.returncode == 0 and r.stdout.strip() == ""
