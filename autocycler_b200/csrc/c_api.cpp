@@ -139,6 +139,7 @@ int ac_upload(ac_handle* h) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     AC_GUARD_BEGIN
     if (h->seqs.empty()) return set_error(h, AC_EINPUT, "no sequences found in input assemblies");
+    if (h->infos.size() != h->seqs.size()) return set_error(h, AC_EINVAL, "this handle holds a loaded graph: add sequences (after ac_clear_sequences) before ac_upload");
     h->pipe->upload(h->ascii.p, h->ascii.size, h->infos.data(), (uint32_t)h->infos.size(), h->cfg.k);
     h->uploaded = true; h->built = h->gfa_ready = false;
     return AC_OK;
@@ -315,7 +316,7 @@ int ac_load_gfa(ac_handle* h, const char* gfa_text, uint64_t length) {
     if (!h || !gfa_text) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     h->built = false; h->gfa_ready = false; h->uploaded = false;
-    h->infos.clear(); h->loaded = LoadedInput(); h->res = PipelineResult(); h->t = ac_timings{};
+    h->seqs.clear(); h->infos.clear(); h->ascii.clear(); h->loaded = LoadedInput(); h->res = PipelineResult(); h->t = ac_timings{};   // a loaded graph has no sequence bytes: ac_upload / ac_build need ac_add_sequence again
     h->graph.device_sort = nullptr;
     h->graph.load_gfa(gfa_text, (size_t)length, h->seqs);
     h->cfg.k = h->graph.k;
