@@ -55,7 +55,7 @@ class AcTimings(C.Structure):
 
 
 EXPORTS = ["ac_last_error", "ac_version", "ac_create", "ac_destroy", "ac_add_sequence", "ac_clear_sequences", "ac_upload",
-           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_renumber_unitigs", "ac_load_gfa", "ac_decompress_gfa", "ac_pairwise_distances", "ac_distance_matrix_text", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
+           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_renumber_unitigs", "ac_load_gfa", "ac_bind_host_to_device", "ac_decompress_gfa", "ac_pairwise_distances", "ac_distance_matrix_text", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
            "ac_timings_get", "ac_compress_dir", "ac_load_sequences", "ac_sequence_get",
            "ac_build_local", "ac_entries_count", "ac_entries_export", "ac_entries_merge", "ac_runs_local", "ac_runs_export",
            "ac_runs_import", "ac_build_finish", "ac_gfa_data"]
@@ -84,6 +84,7 @@ def load_library(path=None):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.ac_merge_linear_paths.argtypes = [C.c_void_p, C.c_int]
     lib.ac_load_gfa.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+    lib.ac_bind_host_to_device.argtypes = [C.c_int32]
     lib.ac_pairwise_distances.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint64]
     lib.ac_distance_matrix_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.ac_decompress_gfa.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32]

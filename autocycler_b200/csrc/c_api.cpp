@@ -1,6 +1,7 @@
 // extern "C" boundary of libautocycler_gpu.so (include/autocycler_gpu.h).  No exception leaves this file.
 #include "../../include/autocycler_gpu.h"
 
+#include <sched.h>
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -310,6 +311,47 @@ int ac_merge_linear_paths(ac_handle* h, int use_paths) {
     h->gfa_ready = false;
     return AC_OK;
     AC_GUARD_END(h)
+}
+
+// One process per GPU, kept on the CPU socket that GPU hangs off (what `numactl --cpunodebind` does): pinned buffers allocated
+// afterwards are local to the DMA engine and to the host threads that edit them.  Measured on the two-socket B200 host: 11-14 %
+// per step (profiles/r1s_*).  Changes the calling thread's affinity mask (threads created later inherit it); opt-in for that reason.
+int ac_bind_host_to_device(int32_t device) {
+    AC_GUARD_BEGIN
+#ifdef AC_EMULATE
+    (void)device;
+    return set_error(nullptr, AC_ENODEVICE, "no CUDA device in the emulation build");
+#else
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return set_error(nullptr, AC_ENODEVICE, "cannot query the PCI bus id of the device"); }
+    std::string id(bus);
+    for (char& ch : id) ch = (char)tolower((unsigned char)ch);
+    if (id.size() > 12 && id.find(':') == 8) id = id.substr(4);                      // an 8-digit PCI domain where sysfs has 4
+    FILE* f = fopen(("/sys/bus/pci/devices/" + id + "/numa_node").c_str(), "r");
+    int node = -1;
+    if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return set_error(nullptr, AC_EINVAL, "the device reports no NUMA node");
+    f = fopen(("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist").c_str(), "r");
+    if (!f) return set_error(nullptr, AC_EINVAL, "cannot read the CPU list of the device's NUMA node");
+    char list[4096] = {0};
+    const bool got = fgets(list, sizeof list, f) != nullptr;
+    fclose(f);
+    if (!got) return set_error(nullptr, AC_EINVAL, "cannot read the CPU list of the device's NUMA node");
+    cpu_set_t now, want; CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof now, &now) != 0) return set_error(nullptr, AC_EINVAL, "sched_getaffinity failed");
+    int count = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int n = sscanf(tok, "%d-%d", &a, &b);
+        if (n < 1) continue;
+        if (n == 1) b = a;
+        for (int cpu = a; cpu <= b && cpu < CPU_SETSIZE; ++cpu) if (CPU_ISSET(cpu, &now)) { CPU_SET(cpu, &want); ++count; }
+    }
+    if (count < 8) return set_error(nullptr, AC_EINVAL, "fewer than 8 usable CPUs on the device's NUMA node: affinity left alone");
+    if (sched_setaffinity(0, sizeof want, &want) != 0) return set_error(nullptr, AC_EINVAL, "sched_setaffinity failed");
+    return node;
+#endif
+    AC_GUARD_END(nullptr)
 }
 
 int ac_load_gfa(ac_handle* h, const char* gfa_text, uint64_t length) {

@@ -60,6 +60,8 @@ int main(int argc, char** argv) {
     if (in.empty() || out.empty()) { usage(); return 2; }
     fprintf(stderr, "\nStarting autocycler compress (%s)\n\nSettings:\n  --assemblies_dir %s\n  --autocycler_dir %s\n  --kmer %u\n  --threads %u\n\n",
             ac_version(), in.c_str(), out.c_str(), k, threads);
+    const int node = ac_bind_host_to_device(device);   // stay on the GPU's socket; harmless when the topology cannot be read
+    if (node >= 0) fprintf(stderr, "host threads bound to NUMA node %d (device %d)\n\n", node, device);
     int rc = ac_compress_dir(in.c_str(), out.c_str(), k, max_contigs, threads, device, 1);
     if (rc != AC_OK) { fprintf(stderr, "\nError: %s\n", ac_last_error(nullptr)); return 1; }
     return 0;

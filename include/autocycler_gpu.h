@@ -147,6 +147,11 @@ int ac_sequence_get(const ac_handle* h, uint64_t index, uint16_t* seq_id, uint64
  * unknown unitigs, non-zero overlaps ...), plus non-integral DP:f: depths and CL:Z: colour tags, which compress never writes. */
 int ac_load_gfa(ac_handle* h, const char* gfa_text, uint64_t length);
 
+/* Deployment helper, not part of the reference: restricts the calling thread (and the threads created after it) to the CPUs of the
+ * NUMA node the CUDA device is attached to, so that pinned host buffers are local to both.  Returns the node (>= 0) or a negative
+ * AC_E* with the affinity unchanged.  Call it before ac_create; `autocycler compress` and bench.py do. */
+int ac_bind_host_to_device(int32_t device);
+
 /* pairwise_contig_distances (cluster.rs:132-151), the all-against-all step of `autocycler cluster`: out[a * S + b] for the S sequences of
  * the handle (built or loaded graph); the unitig-set intersections are computed on the GPU.  ac_distance_matrix_text renders
  * save_distance_matrix's file (cluster.rs:160-176); `out` may be NULL to query the length. */
