@@ -388,7 +388,7 @@ void HostGraph::compute_candidates() {
     exhausted.assign(cands.size(), 0);
     for (uint32_t u = 0; u < U; ++u) rec[u].flags = 0;
     first_pass = true;
-    cands_ready = true; spec_from_device = false;
+    cands_ready = true; spec_from_device = false; device_pass_total = (size_t)-1;
 }
 
 namespace {
@@ -653,12 +653,27 @@ bool HostGraph::adopt_candidates(const PipelineResult& r) {
     dirty.assign((n + 63) / 64, 0);
     exhausted.assign(n, 0);
     first_pass = true; cands_ready = true; spec_from_device = true;
+    device_pass_total = (size_t)-1;
+    if (r.first_pass_done) {                  // the device has applied pass 1 already: rec / arena hold its result, this is what it left for pass 2
+        memcpy(dirty.data(), r.dirty, dirty.size() * 8);
+        memcpy(exhausted.data(), r.exhausted, n);
+        first_pass = false; spec_from_device = false;
+        pass_id = 1;                          // the unitigs it changed carry flags == 1
+        device_pass_total = (size_t)r.first_pass_total;
+    }
     prof.candidates = now_ms() - t0;
     return true;
 }
 
 size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
     const double t0 = now_ms();
+    if (cands_ready && device_pass_total != (size_t)-1) {   // pass 1 ran on the device: hand its count to the caller's `while expand_repeats() > 0`
+        const size_t moved = device_pass_total;
+        device_pass_total = (size_t)-1;
+        if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[host] pass 1 (on the device): %zu bases\n", moved);
+        prof.passes += 1;
+        return moved;
+    }
     if (!cands_ready) { compute_candidates(); prof.candidates = now_ms() - t0; }
     size_t total_shifted = 0;
     ++pass_id;                                      // unitigs modified during this pass carry it in rec[].flags

@@ -901,6 +901,119 @@ struct CommonLengthBody {   // get_common_end_seq (:298-312) for side 0, get_com
     }
 };
 
+// ---- first pass of expand_repeats on the device (opt-in, AC_DEVICE_FIRST_PASS=1; host_graph.cpp apply_candidate is the model) ----
+// Two candidates conflict when they share a unitig; level = 1 + the highest level of an earlier conflicting candidate.  The earlier
+// readers of a unitig are its deps entries, so the levels are the fixed point of "1 + max over predecessors" (longest path in a DAG
+// whose edges point to higher indices), reached in as many relaxation rounds as there are levels.
+struct LevelPredBody {
+    const ExpandCandidate* cands; const ExpandDeps* deps; int32_t* pred;     // [7 * n]
+    AC_D int32_t before(uint32_t u, int32_t ci) const { int32_t best = -1; for (int x = 0; x < 6; ++x) { const int32_t d = deps[u].c[x]; if (d < ci && d > best) best = d; } return best; }
+    AC_D void operator()(uint64_t ci) const {
+        const ExpandCandidate& cd = cands[ci];
+        pred[ci * 7] = before(cd.idx, (int32_t)ci);
+        for (uint32_t a = 0; a < 6; ++a) pred[ci * 7 + 1 + a] = a < cd.gn ? before(cd.src[a] >> 1, (int32_t)ci) : -1;
+    }
+};
+struct LevelRelaxBody {
+    const int32_t* pred; uint32_t* level; uint32_t* changed_and_max;       // [0] set when a level moved, [1] highest level seen
+    AC_D void operator()(uint64_t ci) const {
+        uint32_t lv = 0;
+        for (int x = 0; x < 7; ++x) { const int32_t q = pred[ci * 7 + x]; if (q >= 0) { const uint32_t l = ac_ld_volatile(&level[q]); if (l > lv) lv = l; } }
+        if (lv + 1 != level[ci]) { level[ci] = lv + 1; changed_and_max[0] = 1; }
+        ac_atomic_max(&changed_and_max[1], lv + 1);
+    }
+};
+struct RelocBoundBody {      // room the pass can ask for at most: every candidate may move its destination once, by no more than its shortest source
+    const ExpandCandidate* cands; const UnitigRec* rec; const int32_t* cand_at; unsigned long long* bound;
+    AC_D uint32_t shortest(const ExpandCandidate& cd) const { uint32_t m = 0xFFFFFFFFu; for (uint32_t a = 0; a < cd.gn; ++a) { const uint32_t l = rec[cd.src[a] >> 1].len; if (l < m) m = l; } return m; }
+    AC_D void operator()(uint64_t ci) const {
+        const ExpandCandidate& cd = cands[ci];
+        const int32_t other = cand_at[2 * (size_t)cd.idx + (cd.side ^ 1u)];
+        const unsigned long long mine = shortest(cd), partner = other >= 0 ? shortest(cands[other]) : 0;
+        ac_atomic_add(bound, (unsigned long long)rec[cd.idx].len + mine + 2 * partner + 10ull * AC_SEQ_SLACK + 64);
+    }
+};
+struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates of one level; within a level no two of them share a unitig
+    const ExpandCandidate* cands; const ExpandDeps* deps; const uint32_t* level; uint32_t this_level; const uint32_t* spec_len;
+    UnitigRec* rec; char* arena; unsigned long long* arena_used; unsigned long long* total_shifted; uint64_t* dirty; uint8_t* exhausted;
+    AC_D char at(UStrand s, uint32_t side, uint32_t i) const {
+        const UnitigRec& r = rec[s >> 1]; const char* p = arena + r.seq_off;
+        const bool at_back = (side == 0) != (bool)(s & 1u);
+        const char b = at_back ? p[r.len - 1 - i] : p[i];
+        return (s & 1u) ? ac_complement(b) : b;
+    }
+    AC_D void mark(int32_t cnd, bool hard, int32_t below) const {
+        if (cnd < 0 || cnd >= below || (!hard && exhausted[cnd])) return;
+        ac_atomic_or(&dirty[(size_t)cnd >> 6], (uint64_t)1 << (cnd & 63));
+    }
+    AC_D void operator()(uint64_t ci) const {
+        if (level[ci] != this_level) return;
+        const ExpandCandidate cd = cands[ci];
+        const uint32_t idx = cd.idx, gn = cd.gn, side = cd.side;
+        bool dup = false, pristine = true; uint32_t min_len = 0xFFFFFFFFu;
+        for (uint32_t a = 0; a < gn; ++a) {
+            const uint32_t s = cd.src[a] >> 1;
+            if (rec[s].len < min_len) min_len = rec[s].len;
+            if (rec[s].flags) pristine = false;
+            for (uint32_t b = 0; b < a; ++b) if (s == (cd.src[b] >> 1)) dup = true;
+        }
+        uint32_t common_len;
+        if (pristine) common_len = spec_len[ci];
+        else {                                            // get_common_end_seq / get_common_start_seq on the graph as it is now
+            common_len = rec[cd.src[0] >> 1].len;
+            for (uint32_t a = 1; a < gn; ++a) {
+                const uint32_t la = rec[cd.src[a] >> 1].len;
+                if (la < common_len) common_len = la;
+                uint32_t m = 0;
+                while (m < common_len && at(cd.src[a], side, m) == at(cd.src[0], side, m)) ++m;
+                common_len = m;
+            }
+        }
+        uint32_t c = common_len;
+        if (c > 0) { const uint32_t cap = (min_len - 1) / (dup ? 2u : 1u); if (cap < c) c = cap; }      // avoid_zero_len_unitigs (:141-158)
+        const uint32_t min_pos = side == 0 ? rec[idx].min_fpos : rec[idx].min_rpos;
+        if (c > 0) { if (min_pos == 0) c = 0; else if (min_pos - 1 < c) c = min_pos - 1; }               // avoid_start_of_path (:161-181)
+        exhausted[ci] = c == common_len;
+        if (c == 0) return;
+        UnitigRec d = rec[idx];
+        if (side == 0 ? d.room_before < c : d.room_after < c) {                                         // move the destination where there is room
+            const uint32_t before = side == 0 ? c + 4 * AC_SEQ_SLACK : (d.room_before > AC_SEQ_SLACK ? d.room_before : AC_SEQ_SLACK);
+            const uint32_t after = side == 0 ? (d.room_after > AC_SEQ_SLACK ? d.room_after : AC_SEQ_SLACK) : c + 4 * AC_SEQ_SLACK;
+            const unsigned long long at_off = ac_atomic_add(arena_used, (unsigned long long)before + d.len + after);
+            for (uint32_t i = 0; i < d.len; ++i) arena[at_off + before + i] = arena[d.seq_off + i];
+            d.seq_off = at_off + before; d.room_before = before; d.room_after = after;
+        }
+        if (side == 0) {      // shift_sequence_1 (:89-116): the common end of the inputs becomes the start of this unitig
+            for (uint32_t j = 0; j < c; ++j) arena[d.seq_off - c + j] = at(cd.src[0], 0, c - 1 - j);
+        } else {              // shift_sequence_2 (:119-138): the common start of the outputs becomes its end
+            for (uint32_t i = 0; i < c; ++i) arena[d.seq_off + d.len + i] = at(cd.src[0], 1, i);
+        }
+        for (uint32_t a = 0; a < gn; ++a) {                // the sources lose the piece (unitig.rs:216-232)
+            UnitigRec& r = rec[cd.src[a] >> 1];
+            const bool rev = cd.src[a] & 1u;
+            if (side == 0) { if (!rev) { r.min_rpos += c; r.len -= c; r.room_after += c; } else { r.min_fpos += c; r.len -= c; r.seq_off += c; r.room_before += c; } }
+            else           { if (!rev) { r.min_fpos += c; r.len -= c; r.seq_off += c; r.room_before += c; } else { r.min_rpos += c; r.len -= c; r.room_after += c; } }
+            r.flags = 1;
+        }
+        if (side == 0) { d.seq_off -= c; d.room_before -= c; d.len += c; d.min_fpos -= c; }            // add_seq_to_start / add_seq_to_end (unitig.rs:234-248)
+        else { d.room_after -= c; d.len += c; d.min_rpos -= c; }
+        d.flags = 1;
+        rec[idx] = d;
+        // who has to look again in the next pass: only candidates already visited (all others are still to come in this pass)
+        const int32_t below = (int32_t)ci;
+        { const ExpandDeps& dd = deps[idx]; const bool grew_start = side == 0;
+          mark(dd.c[3], grew_start, below); mark(dd.c[4], grew_start, below); mark(dd.c[2], !grew_start, below); mark(dd.c[5], !grew_start, below); }
+        for (uint32_t a = 0; a < gn; ++a) {
+            const ExpandDeps& ds = deps[cd.src[a] >> 1];
+            const bool trimmed_end = (side == 0) != (bool)(cd.src[a] & 1u);
+            if (trimmed_end) { mark(ds.c[3], false, below); mark(ds.c[4], false, below); mark(ds.c[1], false, below); }
+            else { mark(ds.c[2], false, below); mark(ds.c[5], false, below); mark(ds.c[0], false, below); }
+        }
+        if (c != common_len) ac_atomic_or(&dirty[(size_t)ci >> 6], (uint64_t)1 << (ci & 63));          // capped: look again next pass
+        ac_atomic_add(total_shifted, (unsigned long long)c);
+    }
+};
+
 // ---- contig distances (cluster.rs:132-151): which sequences pass through each unitig, then every pair of them shares its length ----
 struct PathMemberBody {
     const UStrand* path; const uint64_t* path_off; uint32_t n_seqs, words; uint32_t* member;
@@ -1065,7 +1178,8 @@ struct DevicePipeline::Impl {
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
     PinBuf h_cands, h_deps, h_spec, h_fixed, h_keys, h_sorted;
-    DevBuf d_keys, dist_member, dist_shared;
+    DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2;
+    PinBuf h_dirty, h_exhausted;
     PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
     cudaEvent_t ev[20];
@@ -1548,11 +1662,49 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     ac_launch("dependents", &stream, DependentsBody{d_next_off.as<uint32_t>(), d_next.as<UStrand>(), d_prev_off.as<uint32_t>(), d_prev.as<UStrand>(), d_cand_at.as<int32_t>(),
                                                     d_deps.as<ExpandDeps>()}, U);
     ac_launch("common_length", &stream, CommonLengthBody{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_arena.as<char>(), d_spec.as<uint32_t>()}, n_cands);
+    // Opt-in: the whole first pass of expand_repeats here, level by level (the host then starts at pass 2).
+    static const bool device_first_pass = getenv("AC_DEVICE_FIRST_PASS") != nullptr;
+    uint64_t arena_final = arena_bytes, first_pass_total = 0; uint32_t n_levels = 0; bool first_pass_done = false;
+    if (device_first_pass && n_cands > 0) {
+        d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(16); d_counters64.ensure(32);
+        d_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); d_exhausted.ensure(n_cands + 8);
+        ac_launch("level_pred", &stream, LevelPredBody{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_pred.as<int32_t>()}, n_cands);
+        ac_memset(d_level.p, 0, n_cands * 4, &stream);
+        for (uint32_t round = 0;; ++round) {
+            ac_memset(d_flagmax.p, 0, 8, &stream);
+            ac_launch("level_relax", &stream, LevelRelaxBody{d_pred.as<int32_t>(), d_level.as<uint32_t>(), d_flagmax.as<uint32_t>()}, n_cands);
+            uint32_t fm[2] = {0, 0};
+            ac_d2h(fm, d_flagmax.p, 8, &stream); ac_sync(&stream);
+            n_levels = fm[1];
+            if (!fm[0]) break;
+            if (round > 4096) throw std::runtime_error("candidate levels did not settle");
+        }
+        if (n_levels <= 250) {
+            ac_memset(d_counters64.p, 0, 32, &stream);
+            unsigned long long* c64 = d_counters64.as<unsigned long long>();                     // [0] relocation bound, [1] arena bump, [2] bases moved
+            ac_launch("reloc_bound", &stream, RelocBoundBody{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_cand_at.as<int32_t>(), c64}, n_cands);
+            unsigned long long bound = 0;
+            ac_d2h(&bound, c64, 8, &stream); ac_sync(&stream);
+            if (arena_bytes + bound >= 0xFFFFFFF0ull) throw std::runtime_error("unitig sequence arena would exceed 4 GB");
+            d_arena2.ensure(arena_bytes + bound + 64);
+            ac_copy_dd(d_arena2.p, d_arena.p, arena_bytes, &stream);
+            const unsigned long long start = arena_bytes;
+            ac_h2d(c64 + 1, &start, 8, &stream);
+            ac_memset(d_dirty.p, 0, ((n_cands + 63) / 64) * 8 + 8, &stream); ac_memset(d_exhausted.p, 0, n_cands + 8, &stream);
+            for (uint32_t l = 1; l <= n_levels; ++l)
+                ac_launch("apply_level", &stream, ApplyLevelBody{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_level.as<uint32_t>(), l, d_spec.as<uint32_t>(),
+                                                                 d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64 + 1, c64 + 2, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>()}, n_cands);
+            unsigned long long after[2] = {0, 0};
+            ac_d2h(after, c64 + 1, 16, &stream); ac_sync(&stream);
+            arena_final = after[0]; first_pass_total = after[1]; first_pass_done = true;
+        }
+    }
+    DevBuf& arena_src = first_pass_done ? d_arena2 : d_arena;
     mark(11);
 
     // ---- results to the host (pinned) ----
     if (before_results && *before_results) (*before_results)();
-    const uint64_t arena_cap = arena_bytes + arena_bytes / 4 + (1u << 20);     // head room for relocations during repeat expansion
+    const uint64_t arena_cap = arena_final + arena_final / 4 + (1u << 20);     // head room for relocations during repeat expansion
     h_rec.ensure((size_t)U * sizeof(UnitigRec)); h_depth.ensure((size_t)U * 4);
     h_arena.ensure(arena_cap); h_next_off.ensure(((size_t)n_strands + 1) * 4); h_prev_off.ensure(((size_t)n_strands + 1) * 4);
     h_next.ensure(n_links * 4 + 4); h_prev.ensure(n_links * 4 + 4); h_path.ensure(n_runs * 4 + 4); h_path_off.ensure(((size_t)n_seqs + 1) * 8);
@@ -1573,7 +1725,11 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     // The sequences (most of the bytes) go last: the caller gets the graph structure as soon as the small arrays have
     // landed and lists the repeat-expansion candidates while the arena is still on its way (complete() waits for it).
     mark(16);
-    pull(h_arena, d_arena, arena_bytes);
+    pull(h_arena, arena_src, arena_final);
+    if (first_pass_done) {
+        h_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); h_exhausted.ensure(n_cands + 8);
+        pull(h_dirty, d_dirty, ((n_cands + 63) / 64) * 8); pull(h_exhausted, d_exhausted, n_cands);
+    }
     out.d2h_bytes = d2h + 2 * sizeof(unsigned long long) + 8 * sizeof(uint32_t);
     out.h2d_bytes = total + (uint64_t)n_seqs * sizeof(SeqInfo);
     mark(12);
@@ -1582,7 +1738,9 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     out.rec = h_rec.as<UnitigRec>(); out.depth = h_depth.as<uint32_t>(); out.order = h_order.as<uint32_t>();
     out.n_cands = n_cands; out.cands = h_cands.as<ExpandCandidate>(); out.deps = h_deps.as<ExpandDeps>(); out.spec_len = h_spec.as<uint32_t>();
     out.fixed_start = h_fixed.as<uint8_t>(); out.fixed_end = h_fixed.as<uint8_t>() + U;
-    out.arena = h_arena.as<char>(); out.arena_used = arena_bytes; out.arena_cap = arena_cap;
+    out.arena = h_arena.as<char>(); out.arena_used = arena_final; out.arena_cap = arena_cap;
+    out.first_pass_done = first_pass_done; out.first_pass_total = first_pass_total;
+    out.dirty = first_pass_done ? h_dirty.as<uint64_t>() : nullptr; out.exhausted = first_pass_done ? h_exhausted.as<uint8_t>() : nullptr;
     out.next_off = h_next_off.as<uint32_t>(); out.next = h_next.as<UStrand>(); out.prev_off = h_prev_off.as<uint32_t>(); out.prev = h_prev.as<UStrand>();
     out.path_off = h_path_off.as<uint64_t>(); out.path = h_path.as<UStrand>();
     out.run_start = keep_positions ? h_run_start.as<uint64_t>() : nullptr; out.run_len = keep_positions ? h_run_len.as<uint32_t>() : nullptr;

@@ -71,6 +71,9 @@ struct PipelineResult {
     uint32_t* spec_len = nullptr;              // [n_cands] length of the common piece of each candidate's sources on the untouched graph
     ExpandDeps* deps = nullptr;                // [U]
     uint8_t* fixed_start = nullptr; uint8_t* fixed_end = nullptr;   // [U] get_fixed_unitig_starts_and_ends (graph_simplification.rs:190-230)
+    // set when the device has already applied the first pass of expand_repeats (AC_DEVICE_FIRST_PASS): rec / arena hold its result
+    bool first_pass_done = false; uint64_t first_pass_total = 0;    // bases it moved = the first expand_repeats() return value
+    uint64_t* dirty = nullptr; uint8_t* exhausted = nullptr;        // the work list and the per-candidate state it left for pass 2
     char* arena = nullptr; uint64_t arena_used = 0, arena_cap = 0;
     uint32_t* next_off = nullptr;              // [2U+1] CSR over strands: forward_next / reverse_next in the reference's push order
     UStrand* next = nullptr;

@@ -42,8 +42,9 @@ def check_case(lib, files, k, tmpdir=None):
         assert [(s.id, s.filename, s.contig_header, s.length, s.forward_seq) for s in got["seqs"]] == oseqs, "load/end-repair differs"
         assert got["count"] == count
         assert got["before"].n_kmers == st.n_kmers
-        assert (got["before"].n_unitigs, got["before"].n_links, got["before"].total_length) == \
-               (st.unitigs_before, st.links_before, st.length_before)
+        if not os.environ.get("AC_DEVICE_FIRST_PASS"):      # with that switch ac_build already returns the graph after the first expansion pass
+            assert (got["before"].n_unitigs, got["before"].n_links, got["before"].total_length) == \
+                   (st.unitigs_before, st.links_before, st.length_before)
         assert (got["after"].n_unitigs, got["after"].n_links, got["after"].total_length) == \
                (st.unitigs_after, st.links_after, st.length_after)
         assert got["gfa"] == expected, "GFA differs from the oracle"
