@@ -23,6 +23,7 @@
 template <class T> inline T ac_atomic_cas(T* p, T cmp, T val) { T old = *p; if (old == cmp) *p = val; return old; }
 template <class T> inline T ac_atomic_add(T* p, T v) { T old = *p; *p = (T)(old + v); return old; }
 template <class T> inline T ac_atomic_or(T* p, T v) { T old = *p; *p = (T)(old | v); return old; }
+template <class T> inline T ac_atomic_and(T* p, T v) { T old = *p; *p = (T)(old & v); return old; }
 template <class T> inline T ac_atomic_min(T* p, T v) { T old = *p; if (v < old) *p = v; return old; }
 template <class T> inline T ac_atomic_max(T* p, T v) { T old = *p; if (v > old) *p = v; return old; }
 template <class T> inline T ac_ld_volatile(const T* p) { return *p; }
@@ -85,6 +86,7 @@ AC_D uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 AC_D uint32_t ac_popc(uint32_t v) { return (uint32_t)__popc(v); }
 AC_D int ac_ctz(uint32_t v) { return __ffs((int)v) - 1; }
 AC_D uint64_t ac_atomic_or(uint64_t* p, uint64_t v) { return (uint64_t)atomicOr((unsigned long long*)p, (unsigned long long)v); }
+AC_D uint64_t ac_atomic_and(uint64_t* p, uint64_t v) { return (uint64_t)atomicAnd((unsigned long long*)p, (unsigned long long)v); }
 #endif
 
 struct AcStream { cudaStream_t s; };

@@ -936,6 +936,7 @@ struct RelocBoundBody {      // room the pass can ask for at most: every candida
 struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates of one level; within a level no two of them share a unitig
     const ExpandCandidate* cands; const ExpandDeps* deps; const uint32_t* level; uint32_t this_level; const uint32_t* spec_len;
     UnitigRec* rec; char* arena; unsigned long long* arena_used; unsigned long long* total_shifted; uint64_t* dirty; uint8_t* exhausted;
+    bool all_due;            // the first pass visits every candidate; later passes only those on the work list
     AC_D char at(UStrand s, uint32_t side, uint32_t i) const {
         const UnitigRec& r = rec[s >> 1]; const char* p = arena + r.seq_off;
         const bool at_back = (side == 0) != (bool)(s & 1u);
@@ -948,9 +949,14 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
     }
     AC_D void operator()(uint64_t ci) const {
         if (level[ci] != this_level) return;
+        if (!all_due) {
+            const uint64_t bit = (uint64_t)1 << (ci & 63);
+            if (!(ac_ld_volatile(&dirty[ci >> 6]) & bit)) return;
+            ac_atomic_and(&dirty[ci >> 6], ~bit);
+        }
         const ExpandCandidate cd = cands[ci];
         const uint32_t idx = cd.idx, gn = cd.gn, side = cd.side;
-        bool dup = false, pristine = true; uint32_t min_len = 0xFFFFFFFFu;
+        bool dup = false, pristine = all_due; uint32_t min_len = 0xFFFFFFFFu;
         for (uint32_t a = 0; a < gn; ++a) {
             const uint32_t s = cd.src[a] >> 1;
             if (rec[s].len < min_len) min_len = rec[s].len;
@@ -999,8 +1005,9 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
         else { d.room_after -= c; d.len += c; d.min_rpos -= c; }
         d.flags = 1;
         rec[idx] = d;
-        // who has to look again in the next pass: only candidates already visited (all others are still to come in this pass)
-        const int32_t below = (int32_t)ci;
+        // who has to look again: in the first pass only candidates already visited (all others are still to come); later, anyone —
+        // a marked candidate conflicts with this one, so it sits on another level: a later one is still reached in this pass
+        const int32_t below = all_due ? (int32_t)ci : 0x7FFFFFFF;
         { const ExpandDeps& dd = deps[idx]; const bool grew_start = side == 0;
           mark(dd.c[3], grew_start, below); mark(dd.c[4], grew_start, below); mark(dd.c[2], !grew_start, below); mark(dd.c[5], !grew_start, below); }
         for (uint32_t a = 0; a < gn; ++a) {
@@ -1178,7 +1185,7 @@ struct DevicePipeline::Impl {
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
     PinBuf h_cands, h_deps, h_spec, h_fixed, h_keys, h_sorted;
-    DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2;
+    DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2, d_arena3;
     PinBuf h_dirty, h_exhausted;
     PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
@@ -1663,7 +1670,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
                                                     d_deps.as<ExpandDeps>()}, U);
     ac_launch("common_length", &stream, CommonLengthBody{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_arena.as<char>(), d_spec.as<uint32_t>()}, n_cands);
     // Opt-in: the whole first pass of expand_repeats here, level by level (the host then starts at pass 2).
-    static const bool device_first_pass = getenv("AC_DEVICE_FIRST_PASS") != nullptr;
+    static const bool device_first_pass = getenv("AC_DEVICE_FIRST_PASS") != nullptr || getenv("AC_DEVICE_SIMPLIFY") != nullptr;
     uint64_t arena_final = arena_bytes, first_pass_total = 0; uint32_t n_levels = 0; bool first_pass_done = false;
     if (device_first_pass && n_cands > 0) {
         d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(16); d_counters64.ensure(32);
@@ -1693,10 +1700,31 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
             ac_memset(d_dirty.p, 0, ((n_cands + 63) / 64) * 8 + 8, &stream); ac_memset(d_exhausted.p, 0, n_cands + 8, &stream);
             for (uint32_t l = 1; l <= n_levels; ++l)
                 ac_launch("apply_level", &stream, ApplyLevelBody{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_level.as<uint32_t>(), l, d_spec.as<uint32_t>(),
-                                                                 d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64 + 1, c64 + 2, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>()}, n_cands);
+                                                                 d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64 + 1, c64 + 2, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>(), true}, n_cands);
             unsigned long long after[2] = {0, 0};
             ac_d2h(after, c64 + 1, 16, &stream); ac_sync(&stream);
             arena_final = after[0]; first_pass_total = after[1]; first_pass_done = true;
+            // AC_DEVICE_SIMPLIFY=1: `while expand_repeats() > 0 {}` to its end here; the host is left with the renumbering
+            static const bool device_simplify = getenv("AC_DEVICE_SIMPLIFY") != nullptr;
+            for (uint32_t pass = 2; device_simplify && first_pass_total > 0; ++pass) {
+                ac_memset(c64, 0, 8, &stream);
+                ac_launch("reloc_bound", &stream, RelocBoundBody{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_cand_at.as<int32_t>(), c64}, n_cands);
+                ac_d2h(&bound, c64, 8, &stream); ac_sync(&stream);
+                if (arena_final + bound >= 0xFFFFFFF0ull) throw std::runtime_error("unitig sequence arena would exceed 4 GB");
+                static const bool always_grow = getenv("AC_DEVICE_TIGHT_ARENA") != nullptr;   // test hook: take the growth path before every pass
+                if (always_grow || arena_final + bound + 64 > d_arena2.cap) {             // make room for whatever this pass may relocate
+                    d_arena3.ensure(std::max<size_t>((arena_final + bound) * 2 + 64, d_arena3.cap + (always_grow ? 64 : 0)));
+                    ac_copy_dd(d_arena3.p, d_arena2.p, arena_final, &stream); ac_sync(&stream);
+                    std::swap(d_arena2.p, d_arena3.p); std::swap(d_arena2.cap, d_arena3.cap);
+                }
+                ac_memset(c64 + 2, 0, 8, &stream);
+                for (uint32_t l = 1; l <= n_levels; ++l)
+                    ac_launch("apply_level", &stream, ApplyLevelBody{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_level.as<uint32_t>(), l, d_spec.as<uint32_t>(),
+                                                                     d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64 + 1, c64 + 2, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>(), false}, n_cands);
+                ac_d2h(after, c64 + 1, 16, &stream); ac_sync(&stream);
+                arena_final = after[0]; first_pass_total = after[1];          // what the last expand_repeats() call returned
+                if (pass > 100000) throw std::runtime_error("repeat expansion did not settle");
+            }
         }
     }
     DevBuf& arena_src = first_pass_done ? d_arena2 : d_arena;
