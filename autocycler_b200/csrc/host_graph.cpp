@@ -388,7 +388,7 @@ void HostGraph::compute_candidates() {
     exhausted.assign(cands.size(), 0);
     for (uint32_t u = 0; u < U; ++u) rec[u].flags = 0;
     first_pass = true;
-    cands_ready = true; spec_from_device = false; device_pass_total = (size_t)-1;
+    cands_ready = true; spec_from_device = false; device_pass_total = (size_t)-1; final_order.clear();
 }
 
 namespace {
@@ -660,6 +660,7 @@ bool HostGraph::adopt_candidates(const PipelineResult& r) {
         first_pass = false; spec_from_device = false;
         pass_id = 1;                          // the unitigs it changed carry flags == 1
         device_pass_total = (size_t)r.first_pass_total;
+        if (r.final_order) final_order.assign(r.final_order, r.final_order + U);     // the whole loop ran there, and the renumbering after it
     }
     prof.candidates = now_ms() - t0;
     return true;
@@ -720,8 +721,15 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
 }
 
 void HostGraph::simplify_structure() {   // graph_simplification.rs:26-40
+    const bool on_device = cands_ready && device_pass_total == 0 && final_order.size() == U;    // nothing left to do but adopt the numbering
     while (expand_repeats() > 0) {}
-    renumber();
+    if (on_device) {
+        const double t0 = now_ms();
+        order = final_order;
+        for (uint32_t n = 0; n < U; ++n) number[order[n]] = n + 1;
+        prof.renumber += now_ms() - t0;
+    } else renumber();
+    final_order.clear();
     cands_ready = false;      // the numbering order changed: a later call starts from the new order
 }
 

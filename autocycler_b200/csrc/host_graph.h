@@ -92,6 +92,7 @@ private:
     bool cands_ready = false, first_pass = true;
     void compute_candidates();
     bool spec_from_device = false;
+    std::vector<uint32_t> final_order;        // the numbering after simplify_structure when the device ran all of it (consumed by simplify_structure)
     size_t device_pass_total = (size_t)-1;    // bases moved by a first pass the device already applied ((size_t)-1: none pending)
     uint32_t common_length(const Candidate& cand) const;
     typedef ExpandDeps Deps;                  // candidates that read unitig u (pipeline.h)

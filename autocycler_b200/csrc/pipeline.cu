@@ -678,8 +678,10 @@ struct NumberKeyLess {      // sort_number_keys: the part of renumber_unitigs' o
         return a < b;
     }
 };
+struct InversePermBody { const uint32_t* order; uint32_t* pos; AC_D void operator()(uint64_t n) const { pos[order[n]] = (uint32_t)n; } };
 struct NumberLess {
     const UnitigRec* rec; const uint32_t* depth; const char* arena; const uint64_t* prefix;
+    const uint32_t* pos;     // ties keep the order the unitigs are in: creation order (null) or their place in an earlier numbering
     AC_D bool operator()(uint32_t a, uint32_t b) const {
         const uint32_t la = rec[a].len, lb = rec[b].len;
         if (la != lb) return la > lb;
@@ -687,7 +689,7 @@ struct NumberLess {
         const char* x = arena + rec[a].seq_off; const char* y = arena + rec[b].seq_off;
         for (uint32_t i = 8; i < la; ++i) if (x[i] != y[i]) return (unsigned char)x[i] < (unsigned char)y[i];
         if (depth[a] != depth[b]) return depth[a] > depth[b];
-        return a < b;
+        return pos ? pos[a] < pos[b] : a < b;
     }
 };
 
@@ -1185,8 +1187,8 @@ struct DevicePipeline::Impl {
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
     PinBuf h_cands, h_deps, h_spec, h_fixed, h_keys, h_sorted;
-    DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2, d_arena3;
-    PinBuf h_dirty, h_exhausted;
+    DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2, d_arena3, d_pos, sort_c, sort_d;
+    PinBuf h_dirty, h_exhausted, h_order2;
     PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
     cudaEvent_t ev[20];
@@ -1646,7 +1648,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     // the unitig numbers of the freshly built graph (the rank buffer is free again and holds the 8-base prefixes)
     num_prefix.ensure((size_t)U * 8);
     ac_launch("number_key", &stream, NumberKeyBody{d_rec.as<UnitigRec>(), d_arena.as<char>(), num_prefix.as<uint64_t>()}, U);
-    const NumberLess number_less{d_rec.as<UnitigRec>(), d_depth.as<uint32_t>(), d_arena.as<char>(), num_prefix.as<uint64_t>()};
+    const NumberLess number_less{d_rec.as<UnitigRec>(), d_depth.as<uint32_t>(), d_arena.as<char>(), num_prefix.as<uint64_t>(), nullptr};
     uint32_t* ord_in = sort_a.as<uint32_t>(); uint32_t* ord_out = sort_b.as<uint32_t>();
     ac_launch("number_leaf", &stream, SortLeafBody<NumberLess>{number_less, U, ord_in}, ((uint64_t)U + AC_SORT_LEAF - 1) / AC_SORT_LEAF);
     for (uint64_t width = AC_SORT_LEAF; width < U; width *= 2) {
@@ -1672,6 +1674,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     // Opt-in: the whole first pass of expand_repeats here, level by level (the host then starts at pass 2).
     static const bool device_first_pass = getenv("AC_DEVICE_FIRST_PASS") != nullptr || getenv("AC_DEVICE_SIMPLIFY") != nullptr;
     uint64_t arena_final = arena_bytes, first_pass_total = 0; uint32_t n_levels = 0; bool first_pass_done = false;
+    const uint32_t* final_order = nullptr;      // device pointer: the numbering after simplify_structure, when that ran here
     if (device_first_pass && n_cands > 0) {
         d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(16); d_counters64.ensure(32);
         d_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); d_exhausted.ensure(n_cands + 8);
@@ -1725,6 +1728,19 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
                 arena_final = after[0]; first_pass_total = after[1];          // what the last expand_repeats() call returned
                 if (pass > 100000) throw std::runtime_error("repeat expansion did not settle");
             }
+            if (device_simplify) {      // simplify_structure ends with renumber_unitigs (:38): stable with respect to the numbering the passes ran in
+                d_pos.ensure((size_t)U * 4); sort_c.ensure((size_t)U * 4); sort_d.ensure((size_t)U * 4);
+                ac_launch("inverse_perm", &stream, InversePermBody{ord_in, d_pos.as<uint32_t>()}, U);
+                ac_launch("number_key", &stream, NumberKeyBody{d_rec.as<UnitigRec>(), d_arena2.as<char>(), num_prefix.as<uint64_t>()}, U);
+                const NumberLess final_less{d_rec.as<UnitigRec>(), d_depth.as<uint32_t>(), d_arena2.as<char>(), num_prefix.as<uint64_t>(), d_pos.as<uint32_t>()};
+                uint32_t* fin = sort_c.as<uint32_t>(); uint32_t* fout = sort_d.as<uint32_t>();
+                ac_launch("number_leaf", &stream, SortLeafBody<NumberLess>{final_less, U, fin}, ((uint64_t)U + AC_SORT_LEAF - 1) / AC_SORT_LEAF);
+                for (uint64_t width = AC_SORT_LEAF; width < U; width *= 2) {
+                    ac_launch("number_merge", &stream, MergePassBody<NumberLess>{final_less, U, (uint32_t)width, fin, fout}, U);
+                    std::swap(fin, fout);
+                }
+                final_order = fin;
+            }
         }
     }
     DevBuf& arena_src = first_pass_done ? d_arena2 : d_arena;
@@ -1754,6 +1770,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     // landed and lists the repeat-expansion candidates while the arena is still on its way (complete() waits for it).
     mark(16);
     pull(h_arena, arena_src, arena_final);
+    if (final_order) { h_order2.ensure((size_t)U * 4 + 4); ac_d2h(h_order2.p, final_order, (size_t)U * 4, &stream); d2h += (size_t)U * 4; }
     if (first_pass_done) {
         h_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); h_exhausted.ensure(n_cands + 8);
         pull(h_dirty, d_dirty, ((n_cands + 63) / 64) * 8); pull(h_exhausted, d_exhausted, n_cands);
@@ -1767,7 +1784,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     out.n_cands = n_cands; out.cands = h_cands.as<ExpandCandidate>(); out.deps = h_deps.as<ExpandDeps>(); out.spec_len = h_spec.as<uint32_t>();
     out.fixed_start = h_fixed.as<uint8_t>(); out.fixed_end = h_fixed.as<uint8_t>() + U;
     out.arena = h_arena.as<char>(); out.arena_used = arena_final; out.arena_cap = arena_cap;
-    out.first_pass_done = first_pass_done; out.first_pass_total = first_pass_total;
+    out.first_pass_done = first_pass_done; out.first_pass_total = first_pass_total; out.final_order = final_order ? h_order2.as<uint32_t>() : nullptr;
     out.dirty = first_pass_done ? h_dirty.as<uint64_t>() : nullptr; out.exhausted = first_pass_done ? h_exhausted.as<uint8_t>() : nullptr;
     out.next_off = h_next_off.as<uint32_t>(); out.next = h_next.as<UStrand>(); out.prev_off = h_prev_off.as<uint32_t>(); out.prev = h_prev.as<UStrand>();
     out.path_off = h_path_off.as<uint64_t>(); out.path = h_path.as<UStrand>();

@@ -74,6 +74,7 @@ struct PipelineResult {
     // set when the device has already applied the first pass of expand_repeats (AC_DEVICE_FIRST_PASS): rec / arena hold its result
     bool first_pass_done = false; uint64_t first_pass_total = 0;    // bases it moved = the first expand_repeats() return value
     uint64_t* dirty = nullptr; uint8_t* exhausted = nullptr;        // the work list and the per-candidate state it left for pass 2
+    uint32_t* final_order = nullptr;                                // [U] AC_DEVICE_SIMPLIFY: the numbering simplify_structure ends with (:38)
     char* arena = nullptr; uint64_t arena_used = 0, arena_cap = 0;
     uint32_t* next_off = nullptr;              // [2U+1] CSR over strands: forward_next / reverse_next in the reference's push order
     UStrand* next = nullptr;
