@@ -180,6 +180,6 @@ def test_opt_in_device_expansion_matches_the_oracle(lib, tmp_path, switch):
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "from autocycler_b200 import api\nfrom parity_common import run_library\n"
             "got = run_library(api.load_library(), %r, 51)\nopen(%r, 'w').write(got['gfa'])\n") % (os.path.join(ROOT, "tests"), ROOT, d, str(tmp_path / "out.gfa"))
-    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, switch: "1"}, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, switch: "1"}, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr[-2000:]
     assert open(tmp_path / "out.gfa").read() == expected
