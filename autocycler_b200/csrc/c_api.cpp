@@ -54,6 +54,8 @@ struct ac_handle {
     PipelineResult res;
     HostGraph graph;
     std::string gfa;
+    const char* gfa_ptr = nullptr; uint64_t gfa_len = 0;     // the finished file: h->gfa, or the pinned buffer the device wrote the S and L lines into
+    bool device_text_ok = false;                             // the device-written lines describe the graph as it is now
     bool uploaded = false, built = false, gfa_ready = false;
     ac_timings t{};
     uint64_t links_now = 0;
@@ -141,6 +143,12 @@ int ac_upload(ac_handle* h) {
     AC_GUARD_BEGIN
     if (h->seqs.empty()) return set_error(h, AC_EINPUT, "no sequences found in input assemblies");
     if (h->infos.size() != h->seqs.size()) return set_error(h, AC_EINVAL, "this handle holds a loaded graph: add sequences (after ac_clear_sequences) before ac_upload");
+    {   // what save_gfa prints around every path's unitig list (unitig_graph.rs:352-360): room for it behind device-written S / L lines
+        auto digits = [](uint64_t v) { uint64_t d = 1; while (v >= 10) { v /= 10; ++d; } return d; };
+        uint64_t tail = 0;
+        for (const HostSeq& s : h->seqs) tail += 2 + digits(s.id) + 1 + 8 + digits(s.length) + 6 + s.filename.size() + 6 + s.contig_header.size() + 1 + (s.cluster ? 6 + digits(s.cluster) : 0);
+        h->pipe->set_gfa_tail_bytes(tail);
+    }
     h->pipe->upload(h->ascii.p, h->ascii.size, h->infos.data(), (uint32_t)h->infos.size(), h->cfg.k);
     h->uploaded = true; h->built = h->gfa_ready = false;
     return AC_OK;
@@ -208,7 +216,7 @@ static void adopt_result(ac_handle* h) {   // host graph over the device result 
     t.insert_occurrences = windows; t.table_capacity = h->res.capacity; t.table_used = h->res.n_slots_used;
     t.kernel_launches = h->pipe->kernel_launches();
     t.h2d_bytes = h->res.h2d_bytes; t.d2h_bytes = h->res.d2h_bytes;
-    h->built = true; h->gfa_ready = false;
+    h->built = true; h->gfa_ready = false; h->device_text_ok = false;
 }
 
 int ac_build(ac_handle* h) {
@@ -299,6 +307,7 @@ int ac_simplify(ac_handle* h) {
     h->graph.simplify_structure();
     h->t.host_simplify = (float)(now_ms() - t0);
     h->gfa_ready = false;
+    h->device_text_ok = h->res.gfa_text != nullptr && h->graph.last_simplify_on_device;
     return AC_OK;
     AC_GUARD_END(h)
 }
@@ -308,7 +317,7 @@ int ac_merge_linear_paths(ac_handle* h, int use_paths) {
     AC_GUARD_BEGIN
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_merge_linear_paths");
     h->graph.merge_linear_paths(use_paths != 0);
-    h->gfa_ready = false;
+    h->gfa_ready = false; h->device_text_ok = false;
     return AC_OK;
     AC_GUARD_END(h)
 }
@@ -357,7 +366,7 @@ int ac_bind_host_to_device(int32_t device) {
 int ac_load_gfa(ac_handle* h, const char* gfa_text, uint64_t length) {
     if (!h || !gfa_text) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
-    h->built = false; h->gfa_ready = false; h->uploaded = false;
+    h->built = false; h->gfa_ready = false; h->uploaded = false; h->device_text_ok = false;
     h->seqs.clear(); h->infos.clear(); h->ascii.clear(); h->loaded = LoadedInput(); h->res = PipelineResult(); h->t = ac_timings{};   // a loaded graph has no sequence bytes: ac_upload / ac_build need ac_add_sequence again
     h->graph.device_sort = nullptr;
     h->graph.load_gfa(gfa_text, (size_t)length, h->seqs);
@@ -441,7 +450,7 @@ int ac_renumber_unitigs(ac_handle* h) {
     AC_GUARD_BEGIN
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_renumber_unitigs");
     h->graph.renumber();
-    h->gfa_ready = false;
+    h->gfa_ready = false; h->device_text_ok = false;
     return AC_OK;
     AC_GUARD_END(h)
 }
@@ -523,7 +532,27 @@ int ac_gfa_size(ac_handle* h, uint64_t* n_bytes) {
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_gfa_size");
     if (!h->gfa_ready) {
         const double t0 = now_ms();
-        h->graph.gfa_text(h->seqs, h->gfa);
+        if (h->device_text_ok) {      // H, S and L lines came from the device; wrap every path's unitig list into its P line behind them (unitig_graph.rs:352-360)
+            const PipelineResult& r = h->res;
+            char* p = r.gfa_text + r.gfa_lines_bytes;
+            for (size_t i = 0; i < h->seqs.size(); ++i) {
+                const HostSeq& s = h->seqs[i];
+                p += snprintf(p, 32, "P\t%u\t", (unsigned)s.id);
+                const uint64_t a = r.path_text_off[i], b = r.path_text_off[i + 1];
+                memcpy(p, r.path_text + a, b - a); p += b - a;
+                p += snprintf(p, 64, "\t*\tLN:i:%llu\tFN:Z:", (unsigned long long)s.length);
+                memcpy(p, s.filename.data(), s.filename.size()); p += s.filename.size();
+                memcpy(p, "\tHD:Z:", 6); p += 6;
+                memcpy(p, s.contig_header.data(), s.contig_header.size()); p += s.contig_header.size();
+                if (s.cluster > 0) p += snprintf(p, 32, "\tCL:i:%u", (unsigned)s.cluster);
+                *p++ = '\n';
+            }
+            if ((uint64_t)(p - r.gfa_text) > r.gfa_cap) throw std::runtime_error("GFA text buffer overrun");
+            h->gfa_ptr = r.gfa_text; h->gfa_len = (uint64_t)(p - r.gfa_text);
+        } else {
+            h->graph.gfa_text(h->seqs, h->gfa);
+            h->gfa_ptr = h->gfa.data(); h->gfa_len = h->gfa.size();
+        }
         h->t.host_gfa = (float)(now_ms() - t0);
         h->gfa_ready = true;
         if (getenv("AC_HOST_PROFILE")) {
@@ -532,7 +561,7 @@ int ac_gfa_size(ac_handle* h, uint64_t* n_bytes) {
                     p.adopt, p.renumber, p.expand, p.passes, p.candidates, p.compare, p.pass1, (double)h->t.host_gfa, h->graph.U);
         }
     }
-    *n_bytes = h->gfa.size();
+    *n_bytes = h->gfa_len;
     return AC_OK;
     AC_GUARD_END(h)
 }
@@ -541,7 +570,7 @@ int ac_gfa_data(ac_handle* h, const char** data, uint64_t* n_bytes) {   // borro
     if (!data) return set_error(h, AC_EINVAL, "null argument");
     int rc = ac_gfa_size(h, n_bytes);
     if (rc != AC_OK) return rc;
-    *data = h->gfa.data();
+    *data = h->gfa_ptr;
     return AC_OK;
 }
 
@@ -550,7 +579,7 @@ int ac_gfa_copy(ac_handle* h, char* buf, uint64_t cap) {
     int rc = ac_gfa_size(h, &n);
     if (rc != AC_OK) return rc;
     if (!buf || cap < n) return set_error(h, AC_ERANGE, "GFA buffer too small");
-    memcpy(buf, h->gfa.data(), n);
+    memcpy(buf, h->gfa_ptr, n);
     return AC_OK;
 }
 
@@ -661,7 +690,7 @@ int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint
     if ((rc = ac_gfa_size(h, &n)) != AC_OK) { g_error = h->err; return rc; }
     const std::string out_gfa = std::string(autocycler_dir) + "/input_assemblies.gfa", out_yaml = std::string(autocycler_dir) + "/input_assemblies.yaml";
     FILE* f = fopen(out_gfa.c_str(), "wb");
-    if (!f || fwrite(h->gfa.data(), 1, h->gfa.size(), f) != h->gfa.size()) { if (f) fclose(f); return set_error(nullptr, AC_EIO, "cannot write " + out_gfa); }
+    if (!f || fwrite(h->gfa_ptr, 1, h->gfa_len, f) != h->gfa_len) { if (f) fclose(f); return set_error(nullptr, AC_EIO, "cannot write " + out_gfa); }
     fclose(f);
     const std::string yaml = metrics_yaml(h->loaded, c.n_unitigs, c.total_length);
     f = fopen(out_yaml.c_str(), "wb");

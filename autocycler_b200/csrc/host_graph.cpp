@@ -630,7 +630,7 @@ bool HostGraph::adopt_candidates(const PipelineResult& r) {
     static const bool on_host = getenv("AC_HOST_CANDIDATES") != nullptr, cross_check = getenv("AC_CHECK_CANDIDATES") != nullptr;
     if (!r.cands || !r.deps || !r.fixed_start || on_host) return false;
     const double t0 = now_ms();
-    if (cross_check) {                        // tests: the host listing of the same graph must agree field by field
+    if (cross_check && !r.first_pass_done) {  // tests: the host listing of the same graph must agree field by field (not comparable once the device has applied passes)
         compute_candidates();
         bool same = cands.size() == r.n_cands && memcmp(fixed_start.data(), r.fixed_start, U) == 0 && memcmp(fixed_end.data(), r.fixed_end, U) == 0;
         for (size_t i = 0; same && i < cands.size(); ++i) {
@@ -723,6 +723,7 @@ size_t HostGraph::expand_repeats() {   // graph_simplification.rs:43-86
 void HostGraph::simplify_structure() {   // graph_simplification.rs:26-40
     const bool on_device = cands_ready && device_pass_total == 0 && final_order.size() == U;    // nothing left to do but adopt the numbering
     while (expand_repeats() > 0) {}
+    last_simplify_on_device = on_device;
     if (on_device) {
         const double t0 = now_ms();
         order = final_order;

@@ -60,6 +60,7 @@ public:
     void check_links() const;                 // unitig_graph.rs:752-793
     void simplify_structure();                // graph_simplification.rs:26-40
     size_t expand_repeats();                  // graph_simplification.rs:43-86
+    bool last_simplify_on_device = false;     // simplify_structure found everything done by the device (then its GFA text, if any, describes this graph)
     void prepare_simplify();                  // lists the candidates of expand_repeats ahead of time (links and paths only, no sequence bytes)
     bool adopt_candidates(const PipelineResult& r);   // ... or takes the same lists from the device result (graph as built only)
     // UnitigGraph::from_gfa_lines (unitig_graph.rs:55-174; host_gfa_load.cpp): replaces the graph by the one in `text`, returns its sequences

@@ -1023,6 +1023,75 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
     }
 };
 
+// ---- save_gfa on the device (opt-in with AC_DEVICE_SIMPLIFY + AC_DEVICE_GFA; unitig_graph.rs:317-360, unitig.rs:167-171) ----
+// S and L lines are written straight from the simplified, renumbered graph in HBM; the P lines carry host strings (file names,
+// headers), so only their unitig lists are rendered here and the host wraps them.
+AC_D uint32_t ac_put_dec(char* p, uint32_t v) {            // decimal text of v, returns its length
+    char tmp[10]; uint32_t n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    for (uint32_t i = 0; i < n; ++i) p[i] = tmp[n - 1 - i];
+    return n;
+}
+AC_D uint32_t ac_dec_len(uint32_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; ++n; } return n; }
+struct GfaView {
+    const uint32_t* order; const uint32_t* number_of;     // order[n] = unitig with number n + 1; number_of[idx] = n
+    const UnitigRec* rec; const char* arena; const uint32_t* depth; const uint32_t* next_off; const UStrand* next;
+};
+struct GfaSizeBody {
+    GfaView v; uint32_t n_unitigs; uint32_t* s_size; uint32_t* l_size;
+    AC_D void operator()(uint64_t n) const {
+        if (n == n_unitigs) { s_size[n] = 0; l_size[n] = 0; return; }
+        const uint32_t idx = v.order[n], nl = ac_dec_len((uint32_t)n + 1);
+        s_size[n] = 2 + nl + 1 + v.rec[idx].len + 6 + ac_dec_len(v.depth[idx]) + 4;          // "S\t" num "\t" seq "\tDP:f:" depth ".00\n"
+        uint32_t l = 0;
+        for (uint32_t from = idx << 1; from <= (idx << 1 | 1u); ++from)
+            for (uint32_t x = v.next_off[from]; x < v.next_off[from + 1]; ++x) l += nl + ac_dec_len(v.number_of[v.next[x] >> 1] + 1) + 11;   // "L\t" a "\t+\t" b "\t+" "\t0M\n"
+        l_size[n] = l;
+    }
+};
+struct GfaSegmentBody {
+    GfaView v; const uint32_t* s_off; char* text;
+    AC_D void operator()(uint64_t n) const {
+        const uint32_t idx = v.order[n];
+        char* p = text + s_off[n];
+        *p++ = 'S'; *p++ = '\t'; p += ac_put_dec(p, (uint32_t)n + 1); *p++ = '\t';
+        const char* src = v.arena + v.rec[idx].seq_off; const uint32_t len = v.rec[idx].len;
+        for (uint32_t i = 0; i < len; ++i) p[i] = src[i];
+        p += len;
+        *p++ = '\t'; *p++ = 'D'; *p++ = 'P'; *p++ = ':'; *p++ = 'f'; *p++ = ':'; p += ac_put_dec(p, v.depth[idx]);
+        *p++ = '.'; *p++ = '0'; *p++ = '0'; *p++ = '\n';
+    }
+};
+struct GfaLinkBody {          // get_links_for_gfa (:333-350): forward_next then reverse_next of every unitig, in numbering order
+    GfaView v; const uint32_t* l_off; char* text;
+    AC_D void operator()(uint64_t n) const {
+        const uint32_t idx = v.order[n];
+        char* p = text + l_off[n];
+        for (uint32_t rev = 0; rev < 2; ++rev) {
+            const uint32_t from = idx << 1 | rev;
+            for (uint32_t x = v.next_off[from]; x < v.next_off[from + 1]; ++x) {
+                const UStrand to = v.next[x];
+                *p++ = 'L'; *p++ = '\t'; p += ac_put_dec(p, (uint32_t)n + 1); *p++ = '\t'; *p++ = rev ? '-' : '+'; *p++ = '\t';
+                p += ac_put_dec(p, v.number_of[to >> 1] + 1); *p++ = '\t'; *p++ = (to & 1u) ? '-' : '+'; *p++ = '\t'; *p++ = '0'; *p++ = 'M'; *p++ = '\n';
+            }
+        }
+    }
+};
+struct PathLastBody { const uint64_t* path_off; uint8_t* last; AC_D void operator()(uint64_t i) const { if (path_off[i + 1] > path_off[i]) last[path_off[i + 1] - 1] = 1; } };
+struct PathSizeBody {
+    const UStrand* path; const uint32_t* number_of; const uint8_t* last; uint64_t steps; uint32_t* p_size;
+    AC_D void operator()(uint64_t x) const { p_size[x] = x == steps ? 0u : ac_dec_len(number_of[path[x] >> 1] + 1) + 1 + (last[x] ? 0u : 1u); }   // num sign [,]
+};
+struct PathTextBody {
+    const UStrand* path; const uint32_t* number_of; const uint8_t* last; const uint32_t* p_off; char* text;
+    AC_D void operator()(uint64_t x) const {
+        char* p = text + p_off[x];
+        p += ac_put_dec(p, number_of[path[x] >> 1] + 1); *p++ = (path[x] & 1u) ? '-' : '+';
+        if (!last[x]) *p++ = ',';
+    }
+};
+struct PathBoundBody { const uint64_t* path_off; const uint32_t* p_off; uint64_t steps; uint64_t total; uint64_t* bound; AC_D void operator()(uint64_t i) const { bound[i] = path_off[i] < steps ? p_off[path_off[i]] : total; } };
+
 // ---- contig distances (cluster.rs:132-151): which sequences pass through each unitig, then every pair of them shares its length ----
 struct PathMemberBody {
     const UStrand* path; const uint64_t* path_off; uint32_t n_seqs, words; uint32_t* member;
@@ -1187,8 +1256,9 @@ struct DevicePipeline::Impl {
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
     PinBuf h_cands, h_deps, h_spec, h_fixed, h_keys, h_sorted;
-    DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2, d_arena3, d_pos, sort_c, sort_d;
-    PinBuf h_dirty, h_exhausted, h_order2;
+    DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2, d_arena3, d_pos, sort_c, sort_d, d_pos2, gfa_s_size, gfa_l_size, gfa_p_size, d_text, d_ptext, d_last, d_pbound;
+    PinBuf h_dirty, h_exhausted, h_order2, h_text, h_ptext, h_pbound;
+    uint64_t gfa_tail_bytes = 0;          // room the caller needs behind the device-written lines for its P lines (DevicePipeline::gfa_tail_bytes)
     PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
     cudaEvent_t ev[20];
@@ -1675,6 +1745,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     static const bool device_first_pass = getenv("AC_DEVICE_FIRST_PASS") != nullptr || getenv("AC_DEVICE_SIMPLIFY") != nullptr;
     uint64_t arena_final = arena_bytes, first_pass_total = 0; uint32_t n_levels = 0; bool first_pass_done = false;
     const uint32_t* final_order = nullptr;      // device pointer: the numbering after simplify_structure, when that ran here
+    bool gfa_on_device = false; uint64_t gfa_s_bytes = 0, gfa_l_bytes = 0, gfa_p_bytes = 0;
     if (device_first_pass && n_cands > 0) {
         d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(16); d_counters64.ensure(32);
         d_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); d_exhausted.ensure(n_cands + 8);
@@ -1740,6 +1811,29 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
                     std::swap(fin, fout);
                 }
                 final_order = fin;
+                static const bool device_gfa = getenv("AC_DEVICE_GFA") != nullptr;
+                if (device_gfa && U < 100000000u) {          // save_gfa's S and L lines and the path lists, rendered here
+                    d_pos2.ensure((size_t)U * 4);
+                    ac_launch("inverse_perm", &stream, InversePermBody{fin, d_pos2.as<uint32_t>()}, U);
+                    const GfaView gv{fin, d_pos2.as<uint32_t>(), d_rec.as<UnitigRec>(), d_arena2.as<char>(), d_depth.as<uint32_t>(), d_next_off.as<uint32_t>(), d_next.as<UStrand>()};
+                    gfa_s_size.ensure(((size_t)U + 1) * 4); gfa_l_size.ensure(((size_t)U + 1) * 4);
+                    ac_launch("gfa_size", &stream, GfaSizeBody{gv, U, gfa_s_size.as<uint32_t>(), gfa_l_size.as<uint32_t>()}, (uint64_t)U + 1);
+                    gfa_s_bytes = exclusive_scan(gfa_s_size.as<uint32_t>(), gfa_s_size.as<uint32_t>(), (uint64_t)U + 1);
+                    gfa_l_bytes = exclusive_scan(gfa_l_size.as<uint32_t>(), gfa_l_size.as<uint32_t>(), (uint64_t)U + 1);
+                    d_text.ensure(gfa_s_bytes + gfa_l_bytes + 64);
+                    ac_launch("gfa_segment", &stream, GfaSegmentBody{gv, gfa_s_size.as<uint32_t>(), d_text.as<char>()}, U);
+                    ac_launch("gfa_link", &stream, GfaLinkBody{gv, gfa_l_size.as<uint32_t>(), d_text.as<char>() + gfa_s_bytes}, U);
+                    const uint64_t steps = n_runs;
+                    d_last.ensure(steps + 8); gfa_p_size.ensure((steps + 1) * 4); d_pbound.ensure(((size_t)n_seqs + 1) * 8);
+                    ac_memset(d_last.p, 0, steps + 8, &stream);
+                    ac_launch("path_last", &stream, PathLastBody{d_path_off.as<uint64_t>(), d_last.as<uint8_t>()}, n_seqs);
+                    ac_launch("path_size", &stream, PathSizeBody{d_path.as<UStrand>(), d_pos2.as<uint32_t>(), d_last.as<uint8_t>(), steps, gfa_p_size.as<uint32_t>()}, steps + 1);
+                    gfa_p_bytes = exclusive_scan(gfa_p_size.as<uint32_t>(), gfa_p_size.as<uint32_t>(), steps + 1);
+                    d_ptext.ensure(gfa_p_bytes + 64);
+                    ac_launch("path_text", &stream, PathTextBody{d_path.as<UStrand>(), d_pos2.as<uint32_t>(), d_last.as<uint8_t>(), gfa_p_size.as<uint32_t>(), d_ptext.as<char>()}, steps);
+                    ac_launch("path_bound", &stream, PathBoundBody{d_path_off.as<uint64_t>(), gfa_p_size.as<uint32_t>(), steps, gfa_p_bytes, d_pbound.as<uint64_t>()}, (uint64_t)n_seqs + 1);
+                    gfa_on_device = true;
+                }
             }
         }
     }
@@ -1771,6 +1865,16 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     mark(16);
     pull(h_arena, arena_src, arena_final);
     if (final_order) { h_order2.ensure((size_t)U * 4 + 4); ac_d2h(h_order2.p, final_order, (size_t)U * 4, &stream); d2h += (size_t)U * 4; }
+    uint64_t gfa_head = 0;
+    if (gfa_on_device) {      // [H line][S lines][L lines] land where the finished file will be read from; the host appends the P lines behind them
+        char head[64]; gfa_head = (uint64_t)snprintf(head, sizeof head, "H\tVN:Z:1.0\tKM:i:%u\n", k);
+        h_text.ensure(gfa_head + gfa_s_bytes + gfa_l_bytes + gfa_p_bytes + gfa_tail_bytes + 64);
+        memcpy(h_text.p, head, gfa_head);
+        ac_d2h((char*)h_text.p + gfa_head, d_text.p, gfa_s_bytes + gfa_l_bytes, &stream); d2h += gfa_s_bytes + gfa_l_bytes;
+        h_ptext.ensure(gfa_p_bytes + 64); h_pbound.ensure(((size_t)n_seqs + 1) * 8);
+        if (gfa_p_bytes) { ac_d2h(h_ptext.p, d_ptext.p, gfa_p_bytes, &stream); d2h += gfa_p_bytes; }
+        ac_d2h(h_pbound.p, d_pbound.p, ((size_t)n_seqs + 1) * 8, &stream); d2h += ((size_t)n_seqs + 1) * 8;
+    }
     if (first_pass_done) {
         h_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); h_exhausted.ensure(n_cands + 8);
         pull(h_dirty, d_dirty, ((n_cands + 63) / 64) * 8); pull(h_exhausted, d_exhausted, n_cands);
@@ -1785,6 +1889,8 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     out.fixed_start = h_fixed.as<uint8_t>(); out.fixed_end = h_fixed.as<uint8_t>() + U;
     out.arena = h_arena.as<char>(); out.arena_used = arena_final; out.arena_cap = arena_cap;
     out.first_pass_done = first_pass_done; out.first_pass_total = first_pass_total; out.final_order = final_order ? h_order2.as<uint32_t>() : nullptr;
+    out.gfa_text = gfa_on_device ? h_text.as<char>() : nullptr; out.gfa_lines_bytes = gfa_head + gfa_s_bytes + gfa_l_bytes; out.gfa_cap = gfa_on_device ? h_text.cap : 0;
+    out.path_text = gfa_on_device ? h_ptext.as<char>() : nullptr; out.path_text_off = gfa_on_device ? h_pbound.as<uint64_t>() : nullptr;
     out.dirty = first_pass_done ? h_dirty.as<uint64_t>() : nullptr; out.exhausted = first_pass_done ? h_exhausted.as<uint8_t>() : nullptr;
     out.next_off = h_next_off.as<uint32_t>(); out.next = h_next.as<UStrand>(); out.prev_off = h_prev_off.as<uint32_t>(); out.prev = h_prev.as<UStrand>();
     out.path_off = h_path_off.as<uint64_t>(); out.path = h_path.as<UStrand>();
@@ -1826,6 +1932,7 @@ void DevicePipeline::finish(PipelineResult& out, bool keep_positions) {
     AC_DISPATCH_W(m.finish_w, out, keep_positions)
 }
 
+void DevicePipeline::set_gfa_tail_bytes(uint64_t bytes) { impl->gfa_tail_bytes = bytes; }
 void DevicePipeline::complete(PipelineResult& out) { impl->set_device(); impl->do_complete(out); }
 
 void DevicePipeline::build(PipelineResult& out, bool keep_positions) {   // single GPU: every sequence is local, nothing to exchange

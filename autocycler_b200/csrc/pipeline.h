@@ -75,6 +75,9 @@ struct PipelineResult {
     bool first_pass_done = false; uint64_t first_pass_total = 0;    // bases it moved = the first expand_repeats() return value
     uint64_t* dirty = nullptr; uint8_t* exhausted = nullptr;        // the work list and the per-candidate state it left for pass 2
     uint32_t* final_order = nullptr;                                // [U] AC_DEVICE_SIMPLIFY: the numbering simplify_structure ends with (:38)
+    // AC_DEVICE_GFA: save_gfa's H, S and L lines as text (pinned, with room for the P lines behind them) and the unitig list of every path
+    char* gfa_text = nullptr; uint64_t gfa_lines_bytes = 0, gfa_cap = 0;
+    char* path_text = nullptr; uint64_t* path_text_off = nullptr;   // [S+1] offsets into path_text
     char* arena = nullptr; uint64_t arena_used = 0, arena_cap = 0;
     uint32_t* next_off = nullptr;              // [2U+1] CSR over strands: forward_next / reverse_next in the reference's push order
     UStrand* next = nullptr;
@@ -104,6 +107,7 @@ public:
     // called once per finish(), right before the pinned result buffers are (re)allocated and written (the caller may still be
     // cleaning the previous result out of the CPU caches on other threads)
     std::function<void()> before_results;
+    void set_gfa_tail_bytes(uint64_t bytes);   // AC_DEVICE_GFA: bytes the caller will append behind the device-written lines (its P lines minus the path lists)
     void build(PipelineResult& out, bool keep_positions);   // kernels + D2H of the results (single GPU: all the stages below)
     // Multi-GPU stages (one process per GPU; the collectives between them are done by the caller on device pointers):
     void build_local(uint32_t seq_lo, uint32_t seq_hi, bool multi);     // table over this rank's sequences [seq_lo, seq_hi)

@@ -23,7 +23,7 @@ print("SHA", hashlib.sha256(got["gfa"].encode()).hexdigest(), got["before"].n_km
 """
 
 
-@pytest.mark.parametrize("env", [{}, {"AC_DEVICE_SIMPLIFY": "1"}, {"AC_EXPAND_SERIAL": "1", "AC_HOST_CANDIDATES": "1"}], ids=["default", "device_simplify", "serial_host"])
+@pytest.mark.parametrize("env", [{}, {"AC_DEVICE_SIMPLIFY": "1", "AC_DEVICE_GFA": "1"}, {"AC_EXPAND_SERIAL": "1", "AC_HOST_CANDIDATES": "1"}], ids=["default", "device_simplify_and_gfa", "serial_host"])
 def test_config2_golden_under_emulation(tmp_path, env):
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "autocycler_b200", "csrc"), "emu"], check=True)
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "config_goldens.json")))["cfg2_k51"]
