@@ -168,7 +168,7 @@ def test_loaded_graphs_and_reference_kats(lib, golden_dir, tmp_path):
 
 @pytest.mark.xfail(reason="opt-in device paths (AC_DEVICE_FIRST_PASS / AC_DEVICE_SIMPLIFY) were finished after the round's GPU budget was spent: "
                           "exact under emulation, first GPU run pending", strict=False)
-@pytest.mark.parametrize("switch", ["AC_DEVICE_FIRST_PASS", "AC_DEVICE_SIMPLIFY"])
+@pytest.mark.parametrize("switch", ["AC_DEVICE_FIRST_PASS", "AC_DEVICE_SIMPLIFY", "AC_DEVICE_SIMPLIFY,AC_DEVICE_GFA"])
 def test_opt_in_device_expansion_matches_the_oracle(lib, tmp_path, switch):
     """expand_repeats applied by device kernels (pipeline.cu ApplyLevelBody): same bytes as the oracle on a medium graph.  The switch is
     read once per process, so the build runs in a child."""
@@ -180,6 +180,6 @@ def test_opt_in_device_expansion_matches_the_oracle(lib, tmp_path, switch):
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "from autocycler_b200 import api\nfrom parity_common import run_library\n"
             "got = run_library(api.load_library(), %r, 51)\nopen(%r, 'w').write(got['gfa'])\n") % (os.path.join(ROOT, "tests"), ROOT, d, str(tmp_path / "out.gfa"))
-    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, switch: "1"}, capture_output=True, text=True, timeout=120)
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **{name: "1" for name in switch.split(",")}}, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr[-2000:]
     assert open(tmp_path / "out.gfa").read() == expected
