@@ -1055,11 +1055,25 @@ struct GfaSegmentBody {
         const uint32_t idx = v.order[n];
         char* p = text + s_off[n];
         *p++ = 'S'; *p++ = '\t'; p += ac_put_dec(p, (uint32_t)n + 1); *p++ = '\t';
-        const char* src = v.arena + v.rec[idx].seq_off; const uint32_t len = v.rec[idx].len;
-        for (uint32_t i = 0; i < len; ++i) p[i] = src[i];
-        p += len;
+        p += v.rec[idx].len;                                   // the bases are copied by GfaSequenceBody, 64 at a time
         *p++ = '\t'; *p++ = 'D'; *p++ = 'P'; *p++ = ':'; *p++ = 'f'; *p++ = ':'; p += ac_put_dec(p, v.depth[idx]);
         *p++ = '.'; *p++ = '0'; *p++ = '0'; *p++ = '\n';
+    }
+};
+struct GfaChunkCountBody {    // 64-base pieces of every unitig's sequence, so that long unitigs are copied by many threads
+    GfaView v; uint32_t n_unitigs; uint32_t* pieces;
+    AC_D void operator()(uint64_t n) const { pieces[n] = n == n_unitigs ? 0u : (v.rec[v.order[n]].len + 63) / 64; }
+};
+struct GfaSequenceBody {
+    GfaView v; uint32_t n_unitigs; const uint32_t* piece_off; const uint32_t* s_off; char* text;
+    AC_D void operator()(uint64_t c) const {
+        uint32_t lo = 0, hi = n_unitigs;                      // the unitig this piece belongs to: last n with piece_off[n] <= c
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (piece_off[mid] <= c) lo = mid; else hi = mid; }
+        const uint32_t idx = v.order[lo], first = ((uint32_t)c - piece_off[lo]) * 64, len = v.rec[idx].len;
+        const uint32_t m = len - first < 64 ? len - first : 64;
+        const char* src = v.arena + v.rec[idx].seq_off + first;
+        char* dst = text + s_off[lo] + 2 + ac_dec_len(lo + 1) + 1 + first;
+        for (uint32_t i = 0; i < m; ++i) dst[i] = src[i];
     }
 };
 struct GfaLinkBody {          // get_links_for_gfa (:333-350): forward_next then reverse_next of every unitig, in numbering order
@@ -1256,7 +1270,7 @@ struct DevicePipeline::Impl {
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
     PinBuf h_cands, h_deps, h_spec, h_fixed, h_keys, h_sorted;
-    DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2, d_arena3, d_pos, sort_c, sort_d, d_pos2, gfa_s_size, gfa_l_size, gfa_p_size, d_text, d_ptext, d_last, d_pbound;
+    DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2, d_arena3, d_pos, sort_c, sort_d, d_pos2, gfa_s_size, gfa_l_size, gfa_p_size, gfa_pieces, d_text, d_ptext, d_last, d_pbound;
     PinBuf h_dirty, h_exhausted, h_order2, h_text, h_ptext, h_pbound;
     uint64_t gfa_tail_bytes = 0;          // room the caller needs behind the device-written lines for its P lines (DevicePipeline::gfa_tail_bytes)
     PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
@@ -1822,6 +1836,10 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
                     gfa_l_bytes = exclusive_scan(gfa_l_size.as<uint32_t>(), gfa_l_size.as<uint32_t>(), (uint64_t)U + 1);
                     d_text.ensure(gfa_s_bytes + gfa_l_bytes + 64);
                     ac_launch("gfa_segment", &stream, GfaSegmentBody{gv, gfa_s_size.as<uint32_t>(), d_text.as<char>()}, U);
+                    gfa_pieces.ensure(((size_t)U + 1) * 4);
+                    ac_launch("gfa_chunk_count", &stream, GfaChunkCountBody{gv, U, gfa_pieces.as<uint32_t>()}, (uint64_t)U + 1);
+                    const uint64_t n_pieces = exclusive_scan(gfa_pieces.as<uint32_t>(), gfa_pieces.as<uint32_t>(), (uint64_t)U + 1);
+                    ac_launch("gfa_sequence", &stream, GfaSequenceBody{gv, U, gfa_pieces.as<uint32_t>(), gfa_s_size.as<uint32_t>(), d_text.as<char>()}, n_pieces);
                     ac_launch("gfa_link", &stream, GfaLinkBody{gv, gfa_l_size.as<uint32_t>(), d_text.as<char>() + gfa_s_bytes}, U);
                     const uint64_t steps = n_runs;
                     d_last.ensure(steps + 8); gfa_p_size.ensure((steps + 1) * 4); d_pbound.ensure(((size_t)n_seqs + 1) * 8);
