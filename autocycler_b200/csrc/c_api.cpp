@@ -67,6 +67,12 @@ static int set_error(const ac_handle* h, int code, const std::string& msg) {
     return code;
 }
 
+static int ok(const ac_handle* h) {      // a call that succeeded leaves no stale message behind (ac_last_error)
+    if (h) h->err.clear();
+    g_error.clear();
+    return AC_OK;
+}
+
 #define AC_GUARD_BEGIN try {
 #define AC_GUARD_END(h) } catch (const InputError& e) { return set_error(h, AC_EINPUT, e.msg); } \
     catch (const NoDevice& e) { return set_error(h, AC_ENODEVICE, e.msg); } \
@@ -94,13 +100,13 @@ int ac_create(ac_handle** out, const ac_config* cfg) {
     if (!out || !cfg) return set_error(nullptr, AC_EINVAL, "null argument");
     *out = nullptr;
     if (cfg->k < 3 || (cfg->k & 1) == 0) return set_error(nullptr, AC_EINVAL, "--kmer must be odd");          // compress.rs:58
-    if (cfg->k > 64 * AC_MAX_W / 2 - 1)
-        return set_error(nullptr, AC_EINVAL, "k-mer sizes above 127 are not supported by the GPU path (there is no CPU fallback)");
+    if (cfg->k > AC_MAX_K)
+        return set_error(nullptr, AC_EINVAL, "k-mer sizes above " + std::to_string(AC_MAX_K) + " are not supported by the GPU path (there is no CPU fallback)");
     h = new ac_handle;
     h->cfg = *cfg;
     h->pipe.reset(new DevicePipeline(cfg->device, cfg->stream));
     *out = h;
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(((delete h), (ac_handle*)nullptr))
 }
 
@@ -110,7 +116,7 @@ int ac_clear_sequences(ac_handle* h) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     h->seqs.clear(); h->infos.clear(); h->ascii.clear(); h->loaded = LoadedInput();
     h->uploaded = h->built = h->gfa_ready = false;
-    return AC_OK;
+    return ok(h);
 }
 
 int ac_add_sequence(ac_handle* h, uint16_t seq_id, const uint8_t* fwd, uint64_t n, const char* filename, const char* header) {
@@ -134,7 +140,7 @@ int ac_add_sequence(ac_handle* h, uint16_t seq_id, const uint8_t* fwd, uint64_t 
     h->ascii.append(fwd, n);
     h->seqs.push_back(std::move(s)); h->infos.push_back(info);
     h->uploaded = h->built = h->gfa_ready = false;
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -151,7 +157,7 @@ int ac_upload(ac_handle* h) {
     }
     h->pipe->upload(h->ascii.p, h->ascii.size, h->infos.data(), (uint32_t)h->infos.size(), h->cfg.k);
     h->uploaded = true; h->built = h->gfa_ready = false;
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -193,6 +199,11 @@ struct ResultFlusher {
     void join() { for (auto& th : threads) th.join(); threads.clear(); }
     ~ResultFlusher() { join(); }
 };
+struct CallbackScope {      // DevicePipeline::before_results holds a reference to a stack object: never let it outlive the call
+    DevicePipeline* pipe;
+    CallbackScope(DevicePipeline* p, std::function<void()> f) : pipe(p) { pipe->before_results = std::move(f); }
+    ~CallbackScope() { pipe->before_results = nullptr; }
+};
 }  // namespace
 
 static void adopt_result(ac_handle* h) {   // host graph over the device result + bookkeeping shared by ac_build / ac_build_finish
@@ -225,11 +236,12 @@ int ac_build(ac_handle* h) {
     if (!h->uploaded) return set_error(h, AC_EINVAL, "ac_upload must precede ac_build");
     ResultFlusher flusher;
     if (h->built) flusher.start(h->res);
-    h->pipe->before_results = [&flusher] { flusher.join(); };
-    h->pipe->build(h->res, h->cfg.keep_positions != 0);
-    h->pipe->before_results = nullptr;
+    {
+        CallbackScope scope(h->pipe.get(), [&flusher] { flusher.join(); });      // cleared again on every way out, exceptions included
+        h->pipe->build(h->res, h->cfg.keep_positions != 0);
+    }
     adopt_result(h);
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -240,28 +252,28 @@ int ac_build_local(ac_handle* h, uint32_t seq_lo, uint32_t seq_hi, uint32_t mult
     if (!h->uploaded) return set_error(h, AC_EINVAL, "ac_upload must precede ac_build_local");
     h->built = false;
     h->pipe->build_local(seq_lo, seq_hi, multi != 0);
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 int ac_entries_count(ac_handle* h, uint64_t* n) {
     if (!h || !n) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     *n = h->pipe->count_entries();
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 int ac_entries_export(ac_handle* h, void* dst, uint64_t cap_records) {
     if (!h || !dst) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     h->pipe->export_entries(dst, cap_records);
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 int ac_entries_merge(ac_handle* h, const void* src, uint64_t n) {
     if (!h || (!src && n)) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     h->pipe->merge_entries(src, n);
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 int ac_runs_local(ac_handle* h, uint64_t* n_runs) {
@@ -269,21 +281,21 @@ int ac_runs_local(ac_handle* h, uint64_t* n_runs) {
     AC_GUARD_BEGIN
     h->pipe->runs_local();
     if (n_runs) *n_runs = h->pipe->local_runs();
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 int ac_runs_export(ac_handle* h, void* dst, uint64_t cap_records) {
     if (!h || !dst) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     h->pipe->export_runs(dst, cap_records);
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 int ac_runs_import(ac_handle* h, const void* src, uint64_t n) {
     if (!h || !src) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     h->pipe->import_runs(src, n);
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 int ac_build_finish(ac_handle* h) {
@@ -291,11 +303,12 @@ int ac_build_finish(ac_handle* h) {
     AC_GUARD_BEGIN
     ResultFlusher flusher;
     if (h->built) flusher.start(h->res);
-    h->pipe->before_results = [&flusher] { flusher.join(); };
-    h->pipe->finish(h->res, h->cfg.keep_positions != 0);
-    h->pipe->before_results = nullptr;
+    {
+        CallbackScope scope(h->pipe.get(), [&flusher] { flusher.join(); });
+        h->pipe->finish(h->res, h->cfg.keep_positions != 0);
+    }
     adopt_result(h);
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -308,7 +321,7 @@ int ac_simplify(ac_handle* h) {
     h->t.host_simplify = (float)(now_ms() - t0);
     h->gfa_ready = false;
     h->device_text_ok = h->res.gfa_text != nullptr && h->graph.last_simplify_on_device;
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -318,7 +331,7 @@ int ac_merge_linear_paths(ac_handle* h, int use_paths) {
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_merge_linear_paths");
     h->graph.merge_linear_paths(use_paths != 0);
     h->gfa_ready = false; h->device_text_ok = false;
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -372,7 +385,7 @@ int ac_load_gfa(ac_handle* h, const char* gfa_text, uint64_t length) {
     h->graph.load_gfa(gfa_text, (size_t)length, h->seqs);
     h->cfg.k = h->graph.k;
     h->built = true;
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -394,7 +407,7 @@ int ac_pairwise_distances(ac_handle* h, double* out, uint64_t cap) {
         const double a_len = (double)(uint32_t)shared[a * S + a];                    // the reference sums u32 lengths, then converts
         for (uint64_t b = 0; b < S; ++b) out[a * S + b] = 1.0 - ((double)shared[a * S + b] / a_len);
     }
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -438,10 +451,10 @@ int ac_distance_matrix_text(ac_handle* h, char* out, uint64_t cap, uint64_t* len
         text += "\n";
     }
     *length = text.size();
-    if (!out) return AC_OK;
+    if (!out) return ok(h);
     if (cap < text.size()) return set_error(h, AC_ERANGE, "buffer too small");
     memcpy(out, text.data(), text.size());
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -451,7 +464,7 @@ int ac_renumber_unitigs(ac_handle* h) {
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_renumber_unitigs");
     h->graph.renumber();
     h->gfa_ready = false; h->device_text_ok = false;
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -470,7 +483,7 @@ int ac_counts_get(const ac_handle* h, ac_counts* out) {
     out->n_next = g.n_links;
     out->n_sequences = h->seqs.size();
     out->n_path_steps = g.n_path;
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -485,7 +498,7 @@ int ac_unitigs_copy(const ac_handle* h, ac_unitigs* o) {
     for (uint32_t n = 0; n < g.U; ++n) {
         const uint32_t u = g.order[n];
         if (o->number) o->number[n] = g.number[u];
-        if (o->depth) o->depth[n] = (double)g.depth[u];
+        if (o->depth) o->depth[n] = g.depth_of(u);
         if (o->seq_off) o->seq_off[n] = so;
         if (o->seq) memcpy(o->seq + so, g.seq_ptr(u), g.rec[u].len);
         so += g.rec[u].len;
@@ -508,7 +521,7 @@ int ac_unitigs_copy(const ac_handle* h, ac_unitigs* o) {
     if (o->fpos_off) o->fpos_off[g.U] = fo;
     if (o->rpos_off) o->rpos_off[g.U] = ro;
     if (o->next_off) o->next_off[2 * (size_t)g.U] = no;
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -519,10 +532,10 @@ int ac_path_copy(const ac_handle* h, uint64_t seq_index, int32_t* out, uint64_t 
     if (!h->built || seq_index >= g.n_seqs) return set_error(h, AC_EINVAL, "no such sequence");
     const uint64_t a = g.path_off[seq_index], b = g.path_off[seq_index + 1];
     *n = b - a;
-    if (!out) return AC_OK;
+    if (!out) return ok(h);
     if (cap < b - a) return set_error(h, AC_ERANGE, "path buffer too small");
     for (uint64_t x = a; x < b; ++x) { const int32_t num = (int32_t)g.number[us_index(g.path[x])]; out[x - a] = us_reverse(g.path[x]) ? -num : num; }
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -562,7 +575,7 @@ int ac_gfa_size(ac_handle* h, uint64_t* n_bytes) {
         }
     }
     *n_bytes = h->gfa_len;
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -571,7 +584,7 @@ int ac_gfa_data(ac_handle* h, const char** data, uint64_t* n_bytes) {   // borro
     int rc = ac_gfa_size(h, n_bytes);
     if (rc != AC_OK) return rc;
     *data = h->gfa_ptr;
-    return AC_OK;
+    return ok(h);
 }
 
 int ac_gfa_copy(ac_handle* h, char* buf, uint64_t cap) {
@@ -580,14 +593,14 @@ int ac_gfa_copy(ac_handle* h, char* buf, uint64_t cap) {
     if (rc != AC_OK) return rc;
     if (!buf || cap < n) return set_error(h, AC_ERANGE, "GFA buffer too small");
     memcpy(buf, h->gfa_ptr, n);
-    return AC_OK;
+    return ok(h);
 }
 
 int ac_timings_get(const ac_handle* h, ac_timings* out) {
     if (!h || !out) return set_error(h, AC_EINVAL, "null argument");
     *out = h->t;
     out->kernel_launches = h->pipe->kernel_launches();
-    return AC_OK;
+    return ok(h);
 }
 
 int ac_load_sequences(ac_handle* h, const char* dir, uint32_t max_contigs, uint32_t threads, uint64_t* assembly_count) {
@@ -604,7 +617,7 @@ int ac_load_sequences(ac_handle* h, const char* dir, uint32_t max_contigs, uint3
     if (assembly_count) *assembly_count = in.assembly_count;
     in.padded.clear(); in.padded.shrink_to_fit();
     h->loaded = std::move(in);
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -623,7 +636,7 @@ int ac_sequence_get(const ac_handle* h, uint64_t index, uint16_t* seq_id, uint64
     }
     if (filename) { if (cap_fn < s.filename.size() + 1) return set_error(h, AC_ERANGE, "buffer too small"); memcpy(filename, s.filename.c_str(), s.filename.size() + 1); }
     if (header) { if (cap_hd < s.contig_header.size() + 1) return set_error(h, AC_ERANGE, "buffer too small"); memcpy(header, s.contig_header.c_str(), s.contig_header.size() + 1); }
-    return AC_OK;
+    return ok(h);
 }
 
 // reconstruct_original_sequence / get_sequence_from_path (unitig_graph.rs:383-400): the unitig strands of the sequence's
@@ -637,7 +650,7 @@ int ac_sequence_reconstruct(const ac_handle* h, uint64_t index, char* out, uint6
     uint64_t total = 0;
     for (uint64_t x = g.path_off[index]; x < g.path_off[index + 1]; ++x) total += g.rec[us_index(g.path[x])].len;
     if (length) *length = total;
-    if (!out) return AC_OK;
+    if (!out) return ok(h);
     if (cap < total) return set_error(h, AC_ERANGE, "buffer too small");
     char* p = out;
     for (uint64_t x = g.path_off[index]; x < g.path_off[index + 1]; ++x) {
@@ -646,7 +659,7 @@ int ac_sequence_reconstruct(const ac_handle* h, uint64_t index, char* out, uint6
         else for (uint32_t j = 0; j < n; ++j) { const char b = src[n - 1 - j]; p[j] = b == 'A' ? 'T' : b == 'C' ? 'G' : b == 'G' ? 'C' : b == 'T' ? 'A' : b; }
         p += n;
     }
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(h)
 }
 
@@ -665,6 +678,7 @@ int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint
     if (k % 2 == 0) return set_error(nullptr, AC_EINPUT, "--kmer must be odd");
     if (threads < 1) return set_error(nullptr, AC_EINPUT, "--threads cannot be less than 1");
     if (threads > 100) return set_error(nullptr, AC_EINPUT, "--threads cannot be greater than 100");
+    if (k > AC_MAX_K) return set_error(nullptr, AC_EINPUT, "--kmer above " + std::to_string(AC_MAX_K) + " is not supported by this build of the GPU path (there is no CPU fallback)");
     ac_config cfg{}; cfg.k = k; cfg.device = device; cfg.stream = nullptr; cfg.keep_positions = 0;
     int rc = ac_create(&h, &cfg);
     if (rc != AC_OK) return rc;
@@ -703,7 +717,7 @@ int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint
                         " | host graph %.1f simplify %.1f gfa %.1f ms | total %.1f ms\n\n",
                 t1 - t0, t.h2d, t.pack, t.insert, t.adjacency, t.boundaries, t.runs, t.unitigs, t.links, t.d2h, t.host_graph, t.host_simplify, t.host_gfa, now_ms() - t0);
     }
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(nullptr)
 }
 
@@ -791,7 +805,7 @@ int ac_decompress_gfa(const char* in_gfa, const char* out_dir, const char* out_f
         fclose(f);
         if (verbose) fprintf(stderr, "\n");
     }
-    return AC_OK;
+    return ok(h);
     AC_GUARD_END(nullptr)
 }
 

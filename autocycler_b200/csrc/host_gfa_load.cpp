@@ -2,8 +2,9 @@
 // `input_assemblies.gfa` written earlier (by this library or by the reference) for what follows compress — sequence
 // reconstruction (decompress.rs:83-105), merge_linear_paths, simplify_structure, renumbering, saving again.
 //
-// Restrictions, both reported as errors: depths must be whole numbers (compress only ever writes N.00; graphs that
-// trim / resolve have re-weighted carry fractional depths) and segment colour tags are not carried over.
+// Depths are kept as f64 and the segment colour tags as UnitigType (unitig.rs:72-86), so graphs that trim / resolve have
+// re-weighted or coloured load and save back byte for byte.  Lines are split the way BufRead::lines does it (misc.rs:51-61):
+// at '\n', with one trailing '\r' dropped.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -42,7 +43,8 @@ void HostGraph::load_gfa(const char* text, size_t len, std::vector<HostSeq>& seq
     for (size_t a = 0; a < len;) {
         const char* nl = (const char*)memchr(text + a, '\n', len - a);
         const size_t b = nl ? (size_t)(nl - text) : len;
-        const Span line{text + a, b - a};
+        Span line{text + a, b - a};
+        if (line.n > 0 && nl && line.p[line.n - 1] == '\r') line.n -= 1;         // "\r\n" ends a line too (BufRead::lines)
         if (line.n > 0) {
             const size_t tab = std::min<size_t>(line.n, (size_t)((const char*)memchr(line.p, '\t', line.n) ? (const char*)memchr(line.p, '\t', line.n) - line.p : line.n));
             const Span tag{line.p, tab};
@@ -56,7 +58,7 @@ void HostGraph::load_gfa(const char* text, size_t len, std::vector<HostSeq>& seq
 
     // ---- segments (unitig.rs:62-91), in file order ----
     const uint32_t n_seg = (uint32_t)seg_lines.size();
-    own_rec.assign(n_seg, UnitigRec{}); own_depth.assign(n_seg, 0); number.assign(n_seg, 0); order.resize(n_seg);
+    own_rec.assign(n_seg, UnitigRec{}); own_depth.assign(n_seg, 0); own_depth_f.assign(n_seg, 0.0); own_type.assign(n_seg, 0); number.assign(n_seg, 0); order.resize(n_seg);
     std::unordered_map<uint32_t, uint32_t> index;                       // build_unitig_index (:76-78): the last segment with a number wins
     uint64_t bytes = 0;
     std::vector<Span> seg_seq(n_seg);
@@ -68,16 +70,22 @@ void HostGraph::load_gfa(const char* text, size_t len, std::vector<HostSeq>& seq
         bool found = false;
         for (const Span& part : parts)
             if (part.starts("DP:f:")) {
-                const std::string v(part.p + 5, part.n - 5);
-                char* end = nullptr; const double d = strtod(v.c_str(), &end);
-                if (!v.empty() && end && *end == 0) {
-                    if (!(d >= 0) || d != std::floor(d) || d > 4294967295.0) fail("unitig " + std::to_string(number[i]) + " has the non-integral depth " + v + ": only graphs with whole-number depths (compress output) can be loaded");
-                    own_depth[i] = (uint32_t)d; found = true;
+                const std::string v(part.p + 5, part.n - 5);              // str::parse::<f64>: decimal or exponent form, inf / infinity / nan; no blanks, no hex
+                bool plain = !v.empty();
+                for (char c : v) if (!(isalnum((unsigned char)c) || c == '.' || c == '+' || c == '-') || c == 'x' || c == 'X' || c == 'p' || c == 'P' || c == '(') plain = false;
+                char* end = nullptr; const double d = plain ? strtod(v.c_str(), &end) : 0.0;
+                if (plain && end && *end == 0) {
+                    own_depth_f[i] = d; found = true;
+                    own_depth[i] = (d >= 0 && d <= 4294967295.0) ? (uint32_t)d : 0;     // whole-number view for callers that want one; depth_f is what is saved
                 }
                 break;                                                   // Iterator::find stops at the first DP:f: part
             }
         if (!found) fail("Could not find a depth tag (e.g. DP:f:10.00) in the GFA segment line.\nAre you sure this is an Autocycler-generated GFA file?");
-        for (const Span& part : parts) if (part.starts("CL:Z:")) fail("segment colour tags (CL:Z:) are not supported by this loader");
+        {   // unitig.rs:78-86: consentig, else anchor, else bridge, else other — whichever tags the line carries
+            bool consentig = false, anchor = false, bridge = false;
+            for (const Span& part : parts) { consentig |= part.is("CL:Z:steelblue"); anchor |= part.is("CL:Z:forestgreen"); bridge |= part.is("CL:Z:pink"); }
+            own_type[i] = consentig ? 3 : anchor ? 1 : bridge ? 2 : 0;
+        }
         index[number[i]] = i;
         order[i] = i;
         bytes += parts[2].n + 2 * AC_SEQ_SLACK;
@@ -156,7 +164,7 @@ void HostGraph::load_gfa(const char* text, size_t len, std::vector<HostSeq>& seq
         seqs.push_back(std::move(s));
     }
 
-    rec = own_rec.data(); depth = own_depth.data();
+    rec = own_rec.data(); depth = own_depth.data(); depth_f = own_depth_f.data(); utype = own_type.data();
     next_off = own_next_off.data(); prev_off = own_prev_off.data(); next = own_next.data(); prev = own_prev.data(); n_links = own_next.size();
     path_off = own_path_off.data(); path = own_path.data(); n_path = own_path.size(); n_seqs = (uint32_t)seqs.size();
     fpos_off.clear(); rpos_off.clear(); fpos.clear(); rpos.clear();

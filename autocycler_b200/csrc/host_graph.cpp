@@ -128,7 +128,7 @@ void HostGraph::build(const PipelineResult& r, const std::vector<HostSeq>& seqs,
     k = k_size;
     U = r.n_unitigs;
     fixed_ready = false; cands_ready = false;
-    rec = r.rec; depth = r.depth;
+    rec = r.rec; depth = r.depth; depth_f = nullptr; utype = nullptr;
     arena = r.arena; arena_used = r.arena_used; arena_cap = r.arena_cap; arena_overflow.clear();
     next_off = r.next_off; next = r.next; prev_off = r.prev_off; prev = r.prev; n_links = r.n_links;
     path_off = r.path_off; path = r.path; n_path = r.n_runs; n_seqs = r.n_seqs;
@@ -176,7 +176,7 @@ void HostGraph::build(const PipelineResult& r, const std::vector<HostSeq>& seqs,
 // ------------------------------------------------------------------------------------------------
 void HostGraph::renumber() {   // unitig_graph.rs:295-315: stable sort by length desc, sequence asc, depth desc
     const double t0 = now_ms();
-    struct Key { uint32_t len; uint32_t pos; uint64_t prefix; uint32_t idx; uint32_t depth; };
+    struct Key { uint32_t len; uint32_t pos; uint64_t prefix; uint32_t idx; double depth; };
     std::vector<Key> keys(U);
     const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads(), U / 4096));
     auto bounds = [&](size_t t) { return (size_t)((uint64_t)U * t / T); };
@@ -191,7 +191,7 @@ void HostGraph::renumber() {   // unitig_graph.rs:295-315: stable sort by length
         for (size_t n = bounds(t); n < bounds(t + 1); ++n) {
             const uint32_t idx = order[n];
             Key& key = keys[n];
-            key.len = rec[idx].len; key.pos = (uint32_t)n; key.idx = idx; key.depth = depth[idx];
+            key.len = rec[idx].len; key.pos = (uint32_t)n; key.idx = idx; key.depth = depth_of(idx);
             const unsigned char* p = (const unsigned char*)seq_ptr(idx);
             uint64_t v = 0;
             const uint32_t m = key.len < 8 ? key.len : 8;
@@ -401,7 +401,7 @@ struct Cursor { const unsigned char* base; ptrdiff_t step; const unsigned char* 
 
 // get_common_end_seq (:298-312) for side 0 / get_common_start_seq (:283-295) for side 1: length of the common piece
 uint32_t HostGraph::common_length(const Candidate& cand) const {
-    const UStrand* grp = cand.src; const uint32_t gn = cand.gn;
+    const UStrand* grp = sources(cand); const uint32_t gn = cand.gn;
     auto cursor = [&](UStrand s) {
         const uint32_t u = us_index(s); const unsigned char* p = (const unsigned char*)seq_ptr(u);
         const bool at_back = (cand.side == 0) != us_reverse(s);    // forward strand read from its end, or reverse strand read from its start
@@ -446,7 +446,7 @@ size_t HostGraph::apply_candidate(size_t ci, bool shared, std::string& common) {
     const size_t w = ci >> 6; const uint64_t bit_mask = 1ull << (ci & 63);
     const Candidate cand = cands[ci];
     const uint32_t idx = cand.idx;
-    const UStrand* grp = cand.src; const uint32_t gn = cand.gn;
+    const UStrand* grp = sources(cand); const uint32_t gn = cand.gn;
 
     // the comparison made in parallel at the start of this pass still holds if none of the sources changed since
     bool dup = false, pristine = spec_pass[ci] == pass_id; uint32_t min_len = 0xFFFFFFFFu;
@@ -544,11 +544,12 @@ void HostGraph::compute_levels() {
     n_levels = 0;
     for (size_t ci = 0; ci < n; ++ci) {
         const Candidate& cd = cands[ci];
+        const UStrand* grp = sources(cd);
         uint32_t lv = level_of_unitig[cd.idx];
-        for (uint32_t a = 0; a < cd.gn; ++a) lv = std::max<uint32_t>(lv, level_of_unitig[us_index(cd.src[a])]);
+        for (uint32_t a = 0; a < cd.gn; ++a) lv = std::max<uint32_t>(lv, level_of_unitig[us_index(grp[a])]);
         if (++lv > 250) { n_levels = 0xFFFFFFFFu; level_start.clear(); by_level.clear(); return; }
         level_of_unitig[cd.idx] = (uint8_t)lv;
-        for (uint32_t a = 0; a < cd.gn; ++a) level_of_unitig[us_index(cd.src[a])] = (uint8_t)lv;
+        for (uint32_t a = 0; a < cd.gn; ++a) level_of_unitig[us_index(grp[a])] = (uint8_t)lv;
         level[ci] = (uint8_t)lv;
         if (lv > n_levels) n_levels = lv;
     }
@@ -741,6 +742,14 @@ namespace {
 inline char* put_uint(char* p, uint64_t v) { auto r = std::to_chars(p, p + 24, v); return r.ptr; }
 inline char* put_str(char* p, const char* s, size_t n) { memcpy(p, s, n); return p + n; }
 inline uint32_t digits10(uint64_t v) { uint32_t d = 1; while (v >= 10) { v /= 10; ++d; } return d; }
+// "{:.2}" of an f64 (unitig.rs:169): both Rust and printf render the exact binary value rounded half-to-even; only the
+// spellings of the non-finite values differ.
+inline uint32_t put_depth(char* p, double d) {
+    if (d != d) { memcpy(p, "NaN", 3); return 3; }
+    if (d - d != 0) { const bool neg = d < 0; memcpy(p, neg ? "-inf" : "inf", neg ? 4 : 3); return neg ? 4 : 3; }
+    return (uint32_t)snprintf(p, 400, "%.2f", d);
+}
+const char* const COLOUR_TAG[4] = {"", "\tCL:Z:forestgreen", "\tCL:Z:pink", "\tCL:Z:steelblue"};   // unitig.rs:23-26, colour_tag :173-181 with use_other_colour = false
 }  // namespace
 
 void HostGraph::gfa_text(const std::vector<HostSeq>& seqs, std::string& out) const {
@@ -769,7 +778,8 @@ void HostGraph::gfa_text(const std::vector<HostSeq>& seqs, std::string& out) con
         uint64_t ss = 0, ls = 0;
         for (uint32_t n = ub(t); n < ub(t + 1); ++n) {
             const uint32_t idx = order[n];
-            ss += 2 + num_len[idx] + 1 + rec[idx].len + 6 + digits10(depth[idx]) + 4;            // "S\t" num "\t" seq "\tDP:f:" depth ".00\n"
+            if (!depth_f) ss += 2 + num_len[idx] + 1 + rec[idx].len + 6 + digits10(depth[idx]) + 4;            // "S\t" num "\t" seq "\tDP:f:" depth ".00\n"
+            else { char tmp[400]; ss += 2 + num_len[idx] + 1 + rec[idx].len + 6 + put_depth(tmp, depth_f[idx]) + strlen(COLOUR_TAG[type_of(idx)]) + 1; }
             for (uint32_t rev = 0; rev < 2; ++rev) {
                 const UStrand from = us_make(idx, rev != 0);
                 for (uint32_t x = next_off[from]; x < next_off[from + 1]; ++x)
@@ -809,7 +819,9 @@ void HostGraph::gfa_text(const std::vector<HostSeq>& seqs, std::string& out) con
                 const uint32_t idx = order[n];
                 *p++ = 'S'; *p++ = '\t'; p = put_uint(p, (uint64_t)number[idx]); *p++ = '\t';
                 p = put_str(p, seq_ptr(idx), rec[idx].len);
-                p = put_str(p, "\tDP:f:", 6); p = put_uint(p, depth[idx]); p = put_str(p, ".00\n", 4);
+                p = put_str(p, "\tDP:f:", 6);
+                if (!depth_f) { p = put_uint(p, depth[idx]); p = put_str(p, ".00\n", 4); }
+                else { char tmp[400]; const uint32_t dn = put_depth(tmp, depth_f[idx]); p = put_str(p, tmp, dn); const char* ct = COLOUR_TAG[type_of(idx)]; p = put_str(p, ct, strlen(ct)); *p++ = '\n'; }
             }
             if ((uint64_t)(p - base) != s_at[task] + s_size[task]) throw std::runtime_error("GFA S-line size mismatch");
         } else if (task < 2 * TU) {                             // L lines, get_links_for_gfa :333-350: forward_next then reverse_next

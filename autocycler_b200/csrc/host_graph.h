@@ -38,6 +38,12 @@ public:
     // The arrays below are the pipeline's pinned result buffers, adopted and edited in place.
     std::vector<uint32_t> number;             // Unitig.number (1-based position in `order`)
     const uint32_t* depth = nullptr;          // integral on this path: every k-mer of a chain has the same depth
+    // Loaded graphs (unitig.rs:62-91) carry what compress never writes: any f64 depth and the segment colour (UnitigType, unitig.rs:385-392).
+    // Null for a graph that came from the device; then depth[] is the depth and every unitig is UnitigType::Other.
+    const double* depth_f = nullptr;
+    const uint8_t* utype = nullptr;           // 0 Other, 1 Anchor, 2 Bridge, 3 Consentig
+    double depth_of(uint32_t idx) const { return depth_f ? depth_f[idx] : (double)depth[idx]; }
+    uint8_t type_of(uint32_t idx) const { return utype ? utype[idx] : 0; }
     UnitigRec* rec = nullptr;                 // sequence location, length, minimum positions, arena slack (pipeline.h)
     char* arena = nullptr; uint64_t arena_used = 0, arena_cap = 0;
     std::vector<char> arena_overflow;         // only if repeat expansion outgrows the pinned arena
@@ -77,6 +83,7 @@ public:
 private:
     // storage of the graph once merge_linear_paths has rebuilt it (the pinned pipeline buffers are left behind)
     std::vector<UnitigRec> own_rec; std::vector<uint32_t> own_depth, own_next_off, own_prev_off;
+    std::vector<double> own_depth_f; std::vector<uint8_t> own_type;
     std::vector<UStrand> own_next, own_prev, own_path; std::vector<uint64_t> own_path_off;
     std::vector<uint8_t> fixed_start, fixed_end;
     bool fixed_ready = false;
@@ -96,6 +103,11 @@ private:
     std::vector<uint32_t> final_order;        // the numbering after simplify_structure when the device ran all of it (consumed by simplify_structure)
     size_t device_pass_total = (size_t)-1;    // bases moved by a first pass the device already applied ((size_t)-1: none pending)
     uint32_t common_length(const Candidate& cand) const;
+    // The sources of a candidate: its inline copy (at most 6; a graph built from k-mers has at most 5 neighbours per side), or, for
+    // a loaded graph with more, the link list they were copied from (links never change during simplify_structure).
+    const UStrand* sources(const Candidate& cand) const {
+        return cand.gn <= 6 ? cand.src : (cand.side == 0 ? prev_begin(us_make(cand.idx, false)) : next_begin(us_make(cand.idx, false)));
+    }
     typedef ExpandDeps Deps;                  // candidates that read unitig u (pipeline.h)
     std::vector<Deps> deps;
     void compute_dependents();

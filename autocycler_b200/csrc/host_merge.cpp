@@ -158,10 +158,16 @@ void HostGraph::merge_linear_paths(bool use_paths) {
 
     std::vector<UnitigRec> rec2(U2);
     std::vector<uint32_t> depth2(U2), number2(U2), order2(U2);
+    // Loaded graphs: f64 depths and unitig types travel along; the merged unitig's depth is get_merge_path_depth (:503-526).
+    const bool general = depth_f != nullptr;
+    std::vector<double> depth_f2(general ? U2 : 0); std::vector<uint8_t> type2(general ? U2 : 0);
+    std::vector<uint32_t> visits;              // forward_positions.len() of every unitig = the path steps that pass through it (unitig_graph.rs:160-174)
+    if (general) { visits.assign(U, 0); for (uint64_t x = 0; x < n_path; ++x) visits[us_index(path[x])] += 1; }
     for (uint32_t n = 0; n < U; ++n) {
         const uint32_t u = order[n], v = new_index[u];
         if (v == GONE) continue;
         rec2[v] = rec[u]; depth2[v] = depth[u]; number2[v] = number[u];
+        if (general) { depth_f2[v] = depth_f[u]; type2[v] = type_of(u); }
     }
     for (uint32_t i = 0; i < M; ++i) {
         const uint32_t v = kept + i;
@@ -182,6 +188,24 @@ void HostGraph::merge_linear_paths(bool use_paths) {
         r.min_fpos = us_reverse(first) ? rec[us_index(first)].min_rpos : rec[us_index(first)].min_fpos;
         r.min_rpos = us_reverse(last) ? rec[us_index(last)].min_fpos : rec[us_index(last)].min_rpos;
         depth2[v] = depth[us_index(first)];
+        if (general) {
+            double d; bool has_anchor = false, consentig = false; double anchor_depth = 0;
+            for (size_t x = path_begin[i]; x < path_begin[i + 1]; ++x) {
+                const uint32_t m = us_index(flat[x]);
+                if (type_of(m) == 1 && !has_anchor) { has_anchor = true; anchor_depth = depth_f[m]; }
+                if (type_of(m) == 1 || type_of(m) == 3) consentig = true;
+            }
+            if (visits[us_index(first)] > 0) d = (double)visits[us_index(first)];          // positions exist: their count
+            else if (has_anchor) d = anchor_depth;                                         // the first anchor's depth
+            else {                                                                         // weighted_mean_depth (:517-525)
+                uint32_t total = 0; double sum = 0.0;
+                for (size_t x = path_begin[i]; x < path_begin[i + 1]; ++x) total += rec[us_index(flat[x])].len;
+                for (size_t x = path_begin[i]; x < path_begin[i + 1]; ++x) { const uint32_t m = us_index(flat[x]); sum += depth_f[m] * (double)rec[m].len; }
+                d = sum / (double)total;
+            }
+            depth_f2[v] = d; type2[v] = consentig ? 3 : 0;                                 // :439-441
+            depth2[v] = (d >= 0 && d <= 4294967295.0) ? (uint32_t)d : 0;
+        }
         number2[v] = max_number + 1 + i;
     }
     for (uint32_t v = 0; v < U2; ++v) order2[v] = v;
@@ -239,6 +263,7 @@ void HostGraph::merge_linear_paths(bool use_paths) {
 
     // ---- adopt the new graph (graph.build_unitig_index / check_links, :368-370) ----
     own_rec.swap(rec2); own_depth.swap(depth2); number.swap(number2); order.swap(order2);
+    if (general) { own_depth_f.swap(depth_f2); own_type.swap(type2); depth_f = own_depth_f.data(); utype = own_type.data(); }
     own_next_off.swap(next_off2); own_prev_off.swap(prev_off2); own_next.swap(next2); own_prev.swap(prev2);
     own_path_off.swap(path_off2); own_path.swap(path2);
     U = U2; rec = own_rec.data(); depth = own_depth.data();

@@ -29,6 +29,7 @@ WORKLOADS = {   # BASELINE.json configs (SURVEY.md §8d generator); the default 
     "cfg2": "cfg2: 8 synthetic E. coli-sized (4.64 Mbp) assemblies",
     "cfg3": "cfg3: 12 synthetic K. pneumoniae-sized assemblies (5.5 Mbp chromosome + 5 plasmids)",
     "cfg4": "cfg4: 24 synthetic 10 Mbp assemblies",
+    "cfg5": "cfg5: 64 synthetic 5 Mbp assemblies, 8 per rank",
 }
 WORKLOAD = WORKLOADS["cfg2"] + ", k=51"
 
@@ -42,6 +43,14 @@ def measured_traffic(kernel):
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
         return t.get(kernel, {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
+def golden_for(key):
+    """SHA-256 of the oracle's GFA for a named input (tests/golden/config_goldens.json, made by tests/golden/make_config_goldens.py)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "config_goldens.json")))[key]["sha256"]
     except Exception:
         return None
 
@@ -176,9 +185,15 @@ def run_gpu(args):
     # Every rank stages all sequences (end repair needs all of them anyway) and owns a contiguous block.
     global K, WORKLOAD
     K = args.k
-    per_rank = synth.CONFIGS[args.workload][2]
-    WORKLOAD = f"{WORKLOADS[args.workload]}, k={K}"
-    assemblies = synth.make_assemblies(args.workload, n_assemblies=per_rank * world)
+    # N = 1: the configuration the metric is quoted on (cfg2).  N > 1: BASELINE config 5 — the first 8N assemblies of the cfg5
+    # generator, 8 per rank; N = 8 is cfg5 itself.  Every workload has a committed oracle hash (tests/golden/config_goldens.json).
+    workload = args.workload or ("cfg2" if world == 1 else "cfg5")
+    args.workload = workload
+    per_rank = 8 if workload == "cfg5" else synth.CONFIGS[workload][2]
+    n_assemblies = per_rank * world
+    golden_key = f"{workload}_k{K}" + (f"_n{n_assemblies}" if n_assemblies != synth.CONFIGS[workload][2] or workload == "cfg5" else "")
+    WORKLOAD = f"{WORKLOADS[workload]}, k={K}"
+    assemblies = synth.make_assemblies(workload, n_assemblies=n_assemblies)
     n_bases = synth.total_bases(assemblies)
     stream = torch.cuda.current_stream()
     # stage A once, untimed: product loader + end repair, then a handle bound to torch's current stream
@@ -243,6 +258,14 @@ def run_gpu(args):
     clocks = sampler.stop()
 
     g, gfa, t = last
+    parity = None
+    if rank == 0:      # every timed run is checked: SHA-256 of the last step's GFA against the oracle's committed hash
+        import hashlib
+        sha = hashlib.sha256(bytes(gfa)).hexdigest()
+        sha2 = hashlib.sha256(bytes(last2[1])).hexdigest()
+        golden = golden_for(golden_key)
+        parity = {"sha256": sha, "golden": golden, "golden_key": golden_key, "ok": bool(golden) and sha == golden and sha2 == golden,
+                  "checked": "last step of the resident-input loop and of the host-buffer (e2e) loop"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -260,13 +283,14 @@ def run_gpu(args):
         "metric": METRIC, "value": round(value, 3), "unit": "Mbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic (splitmix64 genomes, SURVEY.md §8d)",
-        "config": {"workload": WORKLOAD if world == 1 else f"{per_rank * world} assemblies of the {args.workload} genome, {per_rank} per rank, k={K}", "k": K, "input_bases": n_bases, "sequences": len(seqs),
+        "config": {"workload": WORKLOAD if n_assemblies == synth.CONFIGS[workload][2] else f"the first {n_assemblies} assemblies of {WORKLOADS[workload]}, k={K}", "k": K, "input_bases": n_bases, "sequences": len(seqs),
                    "exchange": None if world == 1 else "all-gather of deduplicated k-mer entries (16 B each) over NCCL, then gather of unitig occurrences to rank 0",
                    "l2": "working set per step (table %.0f MB + per-position arrays) exceeds the 126 MB L2 and is re-initialised every step" % (t.table_capacity * 16 / 1e6),
                    "gfa_bytes": len(gfa), "unitigs": int(g.counts().n_unitigs), "numa_node": numa_node},
         "e2e": {"value": round(e2e, 3), "unit": "Mbp/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": int(last2[2].h2d_bytes), "d2h_bytes_per_step": int(last2[2].d2h_bytes)},
         "gpu_launches": int(launches),
+        "parity": parity,
         "clocks": clocks,
         "roofline": {"kernel": "%s<%d> (k-mer hash insert)" % (INSERT_BODY, W), "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "peak_kind": peak_kind,
@@ -281,6 +305,9 @@ def run_gpu(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and not parity["ok"] and not os.environ.get("AC_BENCH_ALLOW_UNCHECKED"):
+        sys.stderr.write("bench.py: the timed GFA does not match the oracle's committed SHA-256 (%s)\n" % golden_key)
+        sys.exit(3)
 
 
 def oracle_sample(replicon, n_assemblies=8):
@@ -340,7 +367,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="BASELINE.json config to run (default: the one the metric is quoted on)")
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="BASELINE.json config to run (default: cfg2, the one the metric is quoted on, at N=1; cfg5's first 8N assemblies at N>1)")
     ap.add_argument("--k", type=int, default=51)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs under ncu)")
     args = ap.parse_args()

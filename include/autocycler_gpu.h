@@ -143,8 +143,9 @@ int ac_sequence_get(const ac_handle* h, uint64_t index, uint16_t* seq_id, uint64
 /* UnitigGraph::from_gfa_lines (unitig_graph.rs:55-174): replaces whatever the handle holds by the graph and the sequences of an
  * Autocycler GFA (H/S/L/P lines; `length` bytes of text), so that the calls above that work on a built graph — ac_gfa_*,
  * ac_sequence_reconstruct (decompress.rs:83-105), ac_merge_linear_paths, ac_simplify, ac_renumber_unitigs, ac_counts_get,
- * ac_unitigs_copy, ac_path_copy — apply to a file written earlier.  Host only.  Errors: the reference's own (missing tags,
- * unknown unitigs, non-zero overlaps ...), plus non-integral DP:f: depths and CL:Z: colour tags, which compress never writes. */
+ * ac_unitigs_copy, ac_path_copy — apply to a file written earlier.  Host only.  Any DP:f: value the reference parses (f64) and the
+ * CL:Z: segment colours (UnitigType, unitig.rs:72-86) are carried and written back; lines may end in "\r\n" (misc.rs:51-61).
+ * Errors: the reference's own (missing tags, unknown unitigs, non-zero overlaps ...). */
 int ac_load_gfa(ac_handle* h, const char* gfa_text, uint64_t length);
 
 /* Deployment helper, not part of the reference: restricts the calling thread (and the threads created after it) to the CPUs of the

@@ -150,11 +150,7 @@ def _load(emu, text):
 @pytest.mark.parametrize("n", range(1, 15))
 def test_gfa_loader_on_the_reference_fixtures(emu, golden_dir, n):   # test_gfa.rs:15-287 through ac_load_gfa
     text = open(os.path.join(golden_dir, f"ref_test_gfa_{n}.gfa")).read()
-    try:
-        g, seqs = _load(emu, text)
-    except api.AutocyclerGpuError as e:
-        assert "non-integral depth" in str(e) or "colour tags" in str(e), str(e)      # the two documented restrictions
-        return
+    g, seqs = _load(emu, text)
     assert g.gfa_bytes().decode() == o.gfa_roundtrip(text)                            # save(load(x)) as the reference's loader + writer give it
     api.merge_linear_paths(g, seqs)
     assert g.gfa_bytes().decode() == o.gfa_merge_linear_paths(text)
@@ -190,7 +186,7 @@ def test_gfa_loader_errors(emu):   # unitig_graph.rs:91-157, unitig.rs:62-77
     base = "H\tVN:Z:1.0\tKM:i:9\nS\t1\tACGT\tDP:f:2.00\nS\t2\tTTGCA\tDP:f:1.00\nL\t1\t+\t2\t+\t0M\nL\t2\t-\t1\t-\t0M\nP\t1\t1+,2+\t*\tLN:i:9\tFN:Z:a.fasta\tHD:Z:c1\n"
     g, seqs = _load(emu, base)
     assert g.gfa_bytes().decode() == base and g.reconstruct_original_sequence(0) == "ACGTTTGCA"
-    for bad, msg in [(base.replace("DP:f:2.00", "DP:f:2.50"), "non-integral depth"), (base.replace("\tDP:f:1.00", ""), "depth tag"),
+    for bad, msg in [(base.replace("DP:f:2.00", "DP:f:0x10"), "depth tag"), (base.replace("\tDP:f:1.00", ""), "depth tag"),
                      (base.replace("0M\nL", "3M\nL"), "non-zero overlap"), (base.replace("L\t1\t+\t2", "L\t1\t+\t7"), "nonexistent unitig: 7"),
                      (base.replace("\tFN:Z:a.fasta", ""), "missing required tag"), (base.replace("LN:i:9", "LN:i:10"), "Position calculation mismatch"),
                      (base.replace("1+,2+", "1+,3+"), "unitig 3 not found"), (base.replace("1+,2+", "1+,2"), "Invalid path strand")]:
@@ -260,3 +256,51 @@ def test_pairwise_distances_on_loaded_graphs_and_header_flags(emu, golden_dir): 
     out = g.distance_matrix_text()
     assert out == o.pairwise_distances(flagged)
     assert "[trusted, cluster weight = 3]" in out and "[ignored, consensus weight = 2]" in out
+
+
+def test_general_graphs_fractional_depths_colours_crlf(emu):
+    """What compress never writes but later commands do (unitig.rs:62-91, 167-181): any f64 depth, segment colours, and files with
+    CRLF line ends (BufRead::lines, misc.rs:51-61).  save(load(x)), merge_linear_paths (depth = get_merge_path_depth,
+    graph_simplification.rs:503-526: position count, else the first anchor's depth, else the length-weighted mean; type
+    Consentig when the path holds an anchor or a consentig) and renumbering, all against the oracle."""
+    with_paths = ("H\tVN:Z:1.0\tKM:i:9\nS\t1\tACGT\tDP:f:2.345\tCL:Z:forestgreen\nS\t2\tTTGCA\tDP:f:1.005\nS\t3\tGG\tDP:f:7.5\tCL:Z:pink\n"
+                  "L\t1\t+\t2\t+\t0M\nL\t2\t-\t1\t-\t0M\nL\t2\t+\t3\t+\t0M\nL\t3\t-\t2\t-\t0M\n"
+                  "P\t1\t1+,2+,3+\t*\tLN:i:11\tFN:Z:a.fasta\tHD:Z:c1\nP\t2\t3-,2-,1-\t*\tLN:i:11\tFN:Z:b.fasta\tHD:Z:c2\n")
+    no_paths = "".join(l + "\n" for l in with_paths.splitlines() if not l.startswith("P"))
+    no_anchor = no_paths.replace("\tCL:Z:forestgreen", "").replace("CL:Z:pink", "CL:Z:steelblue")
+    plain = no_paths.replace("\tCL:Z:forestgreen", "").replace("\tCL:Z:pink", "")
+    for text in (with_paths, no_paths, no_anchor, plain, with_paths.replace("\n", "\r\n")):
+        g, seqs = _load(emu, text)
+        assert g.gfa_bytes().decode() == o.gfa_roundtrip(text.replace("\r\n", "\n"))
+    # the advisor's case: (len 4, DP 1) + (len 8, DP 3) merged without positions -> 2.33
+    two = "H\tVN:Z:1.0\tKM:i:9\nS\t1\tACGT\tDP:f:1.00\nS\t2\tTTGCATTG\tDP:f:3.00\nL\t1\t+\t2\t+\t0M\nL\t2\t-\t1\t-\t0M\n"
+    g, seqs = _load(emu, two)
+    api.merge_linear_paths(g, None)
+    out = g.gfa_bytes().decode()
+    assert out == o.gfa_merge_linear_paths(two, use_paths=False) and "DP:f:2.33" in out
+    for text in (with_paths, no_paths, no_anchor, plain):
+        for use_paths in (True, False):
+            g, seqs = _load(emu, text)
+            api.merge_linear_paths(g, seqs if use_paths else None)
+            strip = (lambda t: t) if use_paths else (lambda t: [l for l in t.splitlines() if l[0] != "P"])      # the `&vec![]` form saves no paths
+            assert strip(g.gfa_bytes().decode()) == strip(o.gfa_merge_linear_paths(text, use_paths=use_paths)), (text, use_paths)
+            g.renumber_unitigs()
+            assert strip(g.gfa_bytes().decode()) == strip(o.gfa_merge_linear_paths(text, use_paths=use_paths, renumber=True))
+
+
+def test_simplify_with_more_than_six_exclusive_inputs(emu):
+    """A loaded graph may give one unitig any number of exclusive inputs (the reference handles any count, graph_simplification.rs:233-255);
+    the candidate record holds six inline and reads longer lists from the links."""
+    tail = "ACGTTGCA"
+    lines = ["H\tVN:Z:1.0\tKM:i:9", "S\t1\tGGATCCGATT\tDP:f:1.00"]
+    n_in = 9
+    for i in range(n_in):
+        lines.append("S\t%d\t%s\tDP:f:1.00" % (i + 2, "ACGT"[i % 4] * (3 + i) + "C" + tail))
+    for i in range(n_in):
+        lines += ["L\t%d\t+\t1\t+\t0M" % (i + 2), "L\t1\t-\t%d\t-\t0M" % (i + 2)]
+    text = "\n".join(lines) + "\n"
+    g, seqs = _load(emu, text)
+    api.simplify_structure(g)
+    want = o.gfa_unitig_seqs(text, simplify=True)
+    assert [(str(u["number"]), u["seq"]) for u in g.unitigs()] == [(w[0], w[1]) for w in want]
+    assert any(u["seq"].startswith("C" + tail) or u["seq"].startswith(tail) for u in g.unitigs())      # the common end moved onto unitig 1
