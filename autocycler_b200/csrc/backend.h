@@ -27,7 +27,8 @@ template <class T> inline T ac_atomic_and(T* p, T v) { T old = *p; *p = (T)(old 
 template <class T> inline T ac_atomic_min(T* p, T v) { T old = *p; if (v < old) *p = v; return old; }
 template <class T> inline T ac_atomic_max(T* p, T v) { T old = *p; if (v > old) *p = v; return old; }
 template <class T> inline T ac_ld_volatile(const T* p) { return *p; }
-template <class T> inline T ac_ld_16(const T* p) { return *p; }   // one 16-byte load of a 16-byte record
+template <class T> inline T ac_ld_cg(const T* p) { return *p; }
+inline void ac_ld_group(const uint64_t* p, uint64_t out[4]) { out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3]; }
 inline uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 inline uint32_t ac_popc(uint32_t v) { return (uint32_t)__builtin_popcount(v); }
 inline int ac_ctz(uint32_t v) { return __builtin_ctz(v); }
@@ -49,6 +50,10 @@ template <class Body> inline void ac_launch_occ(const char* name, AcStream* st, 
 template <class Body> inline void ac_launch(const char*, AcStream*, const Body& body, uint64_t n) {
     for (uint64_t i = 0; i < n; ++i) body(i);
 }
+// Cooperative launch: body(thread, n_threads, sync) walks its items with stride n_threads and may call sync() — a barrier over the
+// whole grid — between phases.  Emulated by one thread.
+struct AcGridSync { void operator()() const {} };
+template <class Body> inline void ac_launch_coop(const char*, AcStream*, const Body& body, uint64_t) { AcGridSync sync; body(0, 1, sync); }
 
 #else
 // ------------------------------------------------------------------------------------------------
@@ -78,9 +83,10 @@ AC_D uint32_t ac_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 AC_D uint32_t ac_atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
 AC_D uint64_t ac_atomic_min(uint64_t* p, uint64_t v) { return (uint64_t)atomicMin((unsigned long long*)p, (unsigned long long)v); }
 template <class T> AC_D T ac_ld_volatile(const T* p) { return *(const volatile T*)p; }
-template <class T> AC_D T ac_ld_16(const T* p) {   // one 16-byte L2 (cache-global) load of a 16-byte record: sees other threads' atomics
-    static_assert(sizeof(T) == 16, "16-byte records only");
-    const uint4 q = __ldcg(reinterpret_cast<const uint4*>(p)); T r; memcpy(&r, &q, 16); return r;
+AC_D uint64_t ac_ld_cg(const uint64_t* p) { return (uint64_t)__ldcg(reinterpret_cast<const unsigned long long*>(p)); }   // L2 (cache-global) load: sees other threads' atomics
+// four consecutive 8-byte records (one 32-byte sector) in one 256-bit L2 load (sm_100: LDG.E.256)
+AC_D void ac_ld_group(const uint64_t* p, uint64_t out[4]) {
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(out[0]), "=l"(out[1]), "=l"(out[2]), "=l"(out[3]) : "l"(p) : "memory");
 }
 AC_D uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 AC_D uint32_t ac_popc(uint32_t v) { return (uint32_t)__popc(v); }
@@ -102,6 +108,7 @@ inline void* ac_host_alloc(size_t bytes) { void* p = nullptr; AC_CUDA_CHECK(cuda
 inline void ac_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 #ifdef __CUDACC__
+#include <cooperative_groups.h>
 // Every functor-body kernel is launched through this one grid-stride template; the launch counter
 // feeds bench.py's "gpu_launches".
 extern unsigned long long g_ac_kernel_launches;
@@ -142,6 +149,34 @@ template <class Body> inline void ac_launch_occ(const char* name, AcStream* st, 
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("launch ") + name + ": " + cudaGetErrorString(e));
+    ++g_ac_kernel_launches;
+}
+
+// Cooperative launch (all CTAs co-resident): body(thread, n_threads, sync) walks its items with stride n_threads and may call
+// sync() — a barrier over the whole grid — between phases, so that a chain of small dependent steps costs one launch instead of one
+// launch (and often one host round trip) per step.  `work` sizes the grid: no more CTAs than the items need, never more than fit.
+struct AcGridSync { __device__ __forceinline__ void operator()() const { cooperative_groups::this_grid().sync(); } };
+template <class Body> __global__ void __launch_bounds__(256) ac_coop_kernel(const Body body) {
+    AcGridSync sync;
+    body((uint64_t)blockIdx.x * blockDim.x + threadIdx.x, (uint64_t)gridDim.x * blockDim.x, sync);
+}
+template <class Body> inline void ac_launch_coop(const char* name, AcStream* st, const Body& body, uint64_t work) {
+    static int resident = 0;                  // per kernel instantiation; one device per process in this library
+    if (!resident) {
+        int per_sm = 0, sms = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ac_coop_kernel<Body>, 256, 0);
+        resident = per_sm * sms;
+        if (resident <= 0) throw std::runtime_error(std::string("cooperative launch ") + name + ": kernel does not fit");
+    }
+    uint64_t want = (work + 255) / 256;
+    if (want < 1) want = 1;
+    const uint64_t cap = resident < 148 ? (uint64_t)resident : 148;     // one CTA per SM is plenty for these small steps, and keeps the barrier cheap
+    const unsigned blocks = (unsigned)(want < cap ? want : cap);
+    void* args[] = {(void*)&body};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)ac_coop_kernel<Body>, dim3(blocks), dim3(256), args, 0, st->s);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cooperative launch ") + name + ": " + cudaGetErrorString(e));
     ++g_ac_kernel_launches;
 }
 

@@ -130,11 +130,16 @@ template <int W> AC_HD Key<W> key_rc(const Key<W>& key, const KParams& p) {
     return r;
 }
 
+// One multiply-add per key word, then two multiply-xorshift rounds.  The slot index takes the top bits (umulhi), the fingerprint and the
+// Bloom bits the low ones.
 template <int W> AC_HD uint64_t key_hash(const Key<W>& key) {
-    uint64_t h = 0x9E3779B97F4A7C15ull ^ ((uint64_t)(int64_t)key.d * 0xD6E8FEB86659FD93ull);
+    uint64_t h = key.w[0];
 #pragma unroll
-    for (int j = 0; j < W; ++j) { h = (h ^ key.w[j]) * 0xFF51AFD7ED558CCDull; h ^= h >> 29; }
-    h ^= h >> 33; h *= 0xC4CEB9FE1A85EC53ull; h ^= h >> 33;
+    for (int j = 1; j < W; ++j) h = h * 0x9E3779B97F4A7C15ull + key.w[j];
+    if (key.d != 0) h ^= (uint64_t)(int64_t)key.d * 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32; h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 29; h *= 0xC4CEB9FE1A85EC53ull;
+    h ^= h >> 32;
     return h;
 }
 
@@ -182,25 +187,35 @@ AC_HD uint32_t find_seq(const SeqInfo* __restrict__ seqs, uint32_t n, uint64_t g
     return lo;
 }
 
-// ---- table entry word: [ gpos : 36 | dotted : 1 | fingerprint : 27 ] ---------------------------------
-#define AC_EMPTY_ENTRY (~0ull)
-#define AC_FP_BITS 27
-AC_HD uint64_t make_entry(uint64_t gpos, bool dotted, uint64_t hash) {
-    return (gpos << 28) | ((uint64_t)dotted << 27) | (hash & ((1ull << AC_FP_BITS) - 1));
+// ---- table slot: ONE 64-bit word [ gpos:32 | dotted:1 | fingerprint:5 | count:16 | flags:10 ] -------------------------
+// gpos   a pointer to one occurrence of the k-mer, like Kmer.pointer (kmer_graph.rs:26-33): keys never live in the table, equality is
+//        decided by fetching that occurrence from the packed sequence store (L2 resident)
+// count  Kmer::depth() (kmer_graph.rs:52-55), occurrences on both strands.  16 bits: an adder that finds 0xC000 or more raises the
+//        pipeline's overflow flag and the build is repeated with the counts in a side array (`count_big`, 32 bits per slot)
+// flags  bit0 first(canonical) bit1 first(rc(canonical)) (kmer_graph.rs:57-60); bits 2..5: base b follows this k-mer somewhere in the
+//        input, bits 6..9: base b precedes it (canonical orientation; a lower bound on the node-centric degrees)
+// Eight bytes per slot (four slots per 32-byte sector): the table of BASELINE config 2 is 115 MB and stays in the 126 MB L2.
+typedef uint64_t Slot;
+#define AC_EMPTY_SLOT (~0ull)                 // gpos 0xFFFFFFFF is never a window start: inputs are limited to 2^32 - 2 padded bytes
+#define AC_SLOT_COUNT_SHIFT 10
+#define AC_SLOT_COUNT_ONE (1ull << AC_SLOT_COUNT_SHIFT)
+#define AC_SLOT_COUNT_ALARM 0xC000u
+#define AC_SLOT_FLAG_MASK 0x3FFull
+AC_HD uint64_t slot_gpos(Slot s) { return s >> 32; }
+AC_HD bool slot_dotted(Slot s) { return (s >> 31) & 1; }
+AC_HD uint32_t slot_tag(Slot s) { return (uint32_t)(s >> 26) & 63u; }                 // dotted bit + fingerprint
+AC_HD uint32_t slot_count(Slot s) { return (uint32_t)(s >> AC_SLOT_COUNT_SHIFT) & 0xFFFFu; }
+AC_HD uint32_t slot_flags(Slot s) { return (uint32_t)s & 0x3FFu; }
+AC_HD uint32_t make_tag(bool dotted, uint64_t hash) { return ((uint32_t)dotted << 5) | ((uint32_t)hash & 31u); }
+AC_HD Slot make_slot(uint64_t gpos, uint32_t tag, uint32_t count, uint32_t flags) {
+    return (gpos << 32) | ((uint64_t)tag << 26) | ((uint64_t)count << AC_SLOT_COUNT_SHIFT) | flags;
 }
-AC_HD uint64_t entry_gpos(uint64_t e) { return e >> 28; }
-AC_HD bool entry_dotted(uint64_t e) { return (e >> 27) & 1; }
-AC_HD uint64_t entry_tag(uint64_t e) { return e & ((1ull << 28) - 1); }   // dotted bit + fingerprint
-
-struct Slot {               // 16 B: two slots per 32-B sector
-    uint64_t entry;         // AC_EMPTY_ENTRY or make_entry(...): a pointer to one occurrence, like Kmer.pointer (kmer_graph.rs:26-33)
-    uint32_t count;         // Kmer::depth() (kmer_graph.rs:52-55): occurrences on both strands
-    uint32_t aux;           // bit0 first(canonical) bit1 first(rc(canonical)) (kmer_graph.rs:57-60); bit2 outOK bit3 inOK (canonical orientation)
-};
 #define AC_AUX_FIRST_CANON 1u
 #define AC_AUX_FIRST_RC 2u
-#define AC_AUX_OUT_OK 4u
-#define AC_AUX_IN_OK 8u
-#define AC_AUX_OBS_OUT_SHIFT 4      // bits 4..7 : base b follows this k-mer somewhere in the input (canonical orientation)
-#define AC_AUX_OBS_IN_SHIFT 8       // bits 8..11: base b precedes it
-#define AC_AUX_MERGE_MASK 0xFF3u    // what the multi-GPU exchange ORs together: first flags + observed neighbours
+#define AC_AUX_OBS_OUT_SHIFT 2
+#define AC_AUX_OBS_IN_SHIFT 6
+// flags8[slot], written by the adjacency kernel: bit0 outOK = outdeg == 1 && !first(rc K), bit1 inOK = indeg == 1 && !first(K) (canonical orientation)
+#define AC_FLAG8_OUT_OK 1u
+#define AC_FLAG8_IN_OK 2u
+// What one rank tells the others about a k-mer of its local table (multi-GPU exchange, "k-mer buckets"): the slot word and the full count.
+struct SlotRec { uint64_t slot; uint32_t count; uint32_t pad; };

@@ -24,7 +24,7 @@ static unsigned long long g_ac_kernel_launches = 0;
 #define AC_NONE32 0xFFFFFFFFu
 #define AC_CHUNK 32            // windows per thread in the insert kernel
 #define AC_MINCHUNK 128        // windows per thread in the seed-k-mer kernel
-#define AC_STRIPES 1024        // the claim counters are striped: a single hot address would serialise in one L2 slice
+#define AC_BOUND_STRIPES 64     // power of two: accumulators that every candidate adds to are striped
 
 // ------------------------------------------------------------------------------------------------
 // small device helpers
@@ -35,7 +35,11 @@ struct TableView {
     const uint64_t* packed;
     const SeqInfo* seqs;
     uint32_t n_seqs;
+    uint32_t* count_big;        // null, or (after a 16-bit count ran out) the depth of every slot in 32 bits; the slots' own count fields then stay 0
 };
+// Linear probing starts at the first slot of a 32-byte group of four (cap is a multiple of 4): one sector holds the whole first probe.
+AC_D uint64_t table_home(const TableView& t, uint64_t h) { return ac_umul64hi(h, t.cap >> 2) << 2; }
+AC_D uint32_t table_depth(const TableView& t, uint64_t slot) { return t.count_big ? t.count_big[slot] : slot_count(t.slots[slot]); }
 
 template <int W> AC_D Key<W> window_key(const TableView& t, uint64_t g, bool dotted, const KParams& p) {
     Key<W> key = fetch_codes<W>(t.packed, g, p);
@@ -50,16 +54,42 @@ template <int W> AC_D Key<W> window_key(const TableView& t, uint64_t g, bool dot
 template <int W> AC_D uint32_t table_find(const TableView& t, const Key<W>& a, const Key<W>& arc, const KParams& p) {
     const Key<W>& canon = key_is_canonical(a, p) ? a : arc;
     const uint64_t h = key_hash(canon);
-    const uint64_t tag = entry_tag(make_entry(0, a.d != 0, h));
-    uint64_t slot = ac_umul64hi(h, t.cap);
+    const uint32_t tag = make_tag(a.d != 0, h);
+    uint64_t slot = table_home(t, h);
     for (;;) {
-        const uint64_t e = t.slots[slot].entry;
-        if (e == AC_EMPTY_ENTRY) return AC_NONE32;
-        if (entry_tag(e) == tag) {
-            Key<W> rep = window_key<W>(t, entry_gpos(e), a.d != 0, p);
+        const Slot e = t.slots[slot];
+        if (e == AC_EMPTY_SLOT) return AC_NONE32;
+        if (slot_tag(e) == tag) {
+            Key<W> rep = window_key<W>(t, slot_gpos(e), a.d != 0, p);
             if (key_eq(rep, a) || key_eq(rep, arc)) return (uint32_t)slot;
         }
         if (++slot == t.cap) slot = 0;
+    }
+}
+
+// An occurrence (or, in the multi-GPU merge, another rank's `add` occurrences) of the k-mer that slot `slot` already holds: the
+// count goes up, missing flags are set, and with `track_min` the slot ends up pointing at the smallest occurrence (a name for the
+// k-mer that does not depend on the rank).  `seen` is the slot word the caller compared against.  counters[2] is the probe-limit
+// flag, counters[3] the 16-bit count alarm.
+AC_D void slot_add_occurrence(const TableView& t, uint64_t slot, Slot seen, uint64_t g, uint32_t add, uint32_t flags, bool track_min, unsigned long long* counters) {
+    if (!track_min) {
+        if (t.count_big) ac_atomic_add(&t.count_big[slot], add);
+        else {
+            const Slot old = ac_atomic_add(&t.slots[slot], (uint64_t)add << AC_SLOT_COUNT_SHIFT);
+            if (slot_count(old) + add >= AC_SLOT_COUNT_ALARM) counters[3] = 1;
+        }
+        if (flags & ~slot_flags(seen)) ac_atomic_or(&t.slots[slot], (uint64_t)flags);     // usually there already (`seen` may be stale: then the OR is merely redundant)
+        return;
+    }
+    if (t.count_big) ac_atomic_add(&t.count_big[slot], add);
+    Slot old = seen;
+    for (;;) {
+        Slot nw = old | flags;
+        if (!t.count_big) { nw += (uint64_t)add << AC_SLOT_COUNT_SHIFT; if (slot_count(old) + add >= AC_SLOT_COUNT_ALARM) counters[3] = 1; }
+        if (g < slot_gpos(old)) nw = (nw & 0xFFFFFFFFull) | (g << 32);
+        const Slot was = ac_atomic_cas(&t.slots[slot], old, nw);
+        if (was == old) return;
+        old = was;
     }
 }
 
@@ -117,160 +147,227 @@ struct PackBody {
     }
 };
 
-struct InitSlotsBody {
-    Slot* slots;
-    AC_D void operator()(uint64_t i) const { Slot s; s.entry = AC_EMPTY_ENTRY; s.count = 0; s.aux = 0; slots[i] = s; }
-};
-
 // kmer_graph.rs:92-134 add_sequence, both strands at once: one canonical entry per k-mer, count = depth.
+// One window per thread; a warp takes the 32 windows that start in one 32-base word of the packed store (units are aligned to 32
+// coordinates), so the W+2 packed words its keys, their left and their right neighbour bases are cut from sit at the same addresses
+// for all of its lanes (one transaction each) and the slot-id stores coalesce.  Almost every such block lies in the interior of one
+// sequence: no dots, no first or last window, every window has both neighbours — that case is decided once per block and skips the
+// per-window bookkeeping.  The table is probed a 32-byte group of four slots at a time (one sector, one 256-bit load; the home slot
+// of a k-mer is the first of a group and the probe order is plain linear probing from there), in two phases: a cheap scan to the
+// first slot that is empty (claimed at once, count and flags in the same CAS) or carries the k-mer's 6-bit tag, then — lanes
+// together again — the comparison with the occurrence that slot points at.
 template <int W> struct InsertBody {
-    TableView t; KParams p; uint64_t g_begin, g_end;   // coordinates of the sequences this rank owns
-    bool track_min;                     // multi-GPU: the entry must end up pointing at the SMALLEST occurrence (a rank-independent name for the k-mer)
-    uint32_t* pos_slot;                 // [total] slot of the window starting at each global coordinate (null in the sampling pass)
-    unsigned long long* counters;       // [2*stripe] slots claimed, [2*stripe+1] dotted k-mers claimed, [2*AC_STRIPES] table-overflow flag
-    uint64_t sample_mask;               // != 0: the sizing pre-pass, only k-mers whose hash has these bits clear are entered
-    // Finds the k-mer's slot or claims an empty one.  False: skipped by the sampling mask, or the probe limit was hit.
-    AC_D bool find_or_claim(const Key<W>& fwd, const Key<W>& rc, uint64_t g, uint64_t& slot_out, uint32_t& aux_seen, bool& canon_fwd,
-                            uint32_t& claimed, uint32_t& claimed_dotted) const {
-        canon_fwd = key_is_canonical(fwd, p);
-        const Key<W>& canon = canon_fwd ? fwd : rc;
-        const uint64_t h = key_hash(canon);
-        if (h & sample_mask) return false;
-        const bool dotted = fwd.d != 0;
-        const uint64_t mine = make_entry(g, dotted, h);
-        uint64_t slot = ac_umul64hi(h, t.cap);
-        for (uint32_t probes = 0;; ++probes) {
-            if (probes > 8192) { counters[2 * AC_STRIPES] = 1; return false; }    // the table was sized too small: the host retries with the safe size
-            const Slot q = ac_ld_16(&t.slots[slot]);      // entry, count and flags in one transaction
-            uint64_t e = q.entry; aux_seen = q.aux;
-            if (e == AC_EMPTY_ENTRY) {
-                e = ac_atomic_cas(&t.slots[slot].entry, (uint64_t)AC_EMPTY_ENTRY, mine);
-                if (e == AC_EMPTY_ENTRY) { ++claimed; if (dotted) ++claimed_dotted; break; }
-            }
-            if (entry_tag(e) == entry_tag(mine)) {
-                Key<W> rep = window_key<W>(t, entry_gpos(e), dotted, p);
-                if (key_eq(rep, fwd) || key_eq(rep, rc)) {
-                    if (track_min && mine < e) ac_atomic_min(&t.slots[slot].entry, mine);   // same tag => ordered by gpos
-                    break;
-                }
-            }
-            if (++slot == t.cap) slot = 0;
-        }
-        slot_out = slot;
-        return true;
+    TableView t; KParams p;
+    uint32_t g_first;                   // coordinate of unit 0, a multiple of 32 (inputs are limited to 2^32 - 2 padded bytes: coordinates fit 32 bits)
+    uint32_t g_begin, g_end;            // coordinates of the sequences this rank owns
+    bool track_min;                     // multi-GPU: the slot must end up pointing at the SMALLEST occurrence
+    uint32_t* pos_slot;                 // [total] slot of the window starting at each global coordinate (null in the sizing pass)
+    unsigned long long* counters;       // [0] slots claimed (sizing pass only), [1] dotted k-mers claimed, [2] probe-limit flag, [3] count alarm
+    bool sizing;                        // the sizing pass: the caller has picked the windows (SampleBody), only distinct k-mers are counted
+    // everything about one window that the probe needs
+    struct Unit { Key<W> fwd, rc; uint64_t h; uint32_t flags; bool valid, dotted; };
+    AC_D Unit interior_unit(uint32_t g) const {          // a window of an interior block: keys and neighbour bases from the block's W+2 words
+        const uint32_t l = g & 31u, i0 = g >> 5;
+        uint64_t x[W + 1];
+#pragma unroll
+        for (int j = 0; j <= W; ++j) x[j] = t.packed[i0 + j];
+        const uint64_t xp = t.packed[i0 - 1];
+        const uint32_t sh = 2 * l;
+        uint64_t y[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) y[j] = (x[j] << sh) | ((x[j + 1] >> 1) >> (63 - sh));
+        Unit u;
+        const uint32_t al = 64 - p.top_bits;
+#pragma unroll
+        for (int j = W - 1; j >= 0; --j) { uint64_t v = y[j] >> al; if (al && j > 0) v |= y[j - 1] << (64 - al); u.fwd.w[j] = v; }
+        u.fwd.d = 0;
+        u.rc = key_rc(u.fwd, p);
+        const bool canon_fwd = key_is_canonical(u.fwd, p);
+        const uint32_t at = l + p.k;                       // the base after the window, counted from the block start: in word at >> 5 <= W
+        uint64_t xn = x[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) xn = ((at >> 5) == (uint32_t)j) ? x[j] : xn;
+        const uint32_t nb = (uint32_t)(xn >> (62 - 2 * (at & 31u))) & 3u;
+        const uint32_t pb = l ? (uint32_t)(x[0] >> (64 - sh)) & 3u : (uint32_t)xp & 3u;
+        const uint32_t out_b = canon_fwd ? nb : 3u - pb, in_b = canon_fwd ? pb : 3u - nb;
+        u.flags = (1u << (AC_AUX_OBS_OUT_SHIFT + out_b)) | (1u << (AC_AUX_OBS_IN_SHIFT + in_b));
+        u.h = key_hash(canon_fwd ? u.fwd : u.rc);
+        u.valid = true; u.dotted = false;
+        return u;
     }
-    // Counts the occurrence and records what it tells about the k-mer.
-    AC_D void commit(uint64_t slot, uint32_t aux_seen, bool canon_fwd, uint64_t g, uint64_t fs, uint32_t len, uint32_t obs) const {
-        ac_atomic_add(&t.slots[slot].count, 1u);
-        // Kmer::first_position (kmer_graph.rs:57-60): position 0 of the forward strand is window 0; position 0
-        // of the reverse strand is the reverse complement of the last window (kmer_graph.rs:103-108).
-        uint32_t bits = obs;
-        if (fs == 0) bits |= canon_fwd ? AC_AUX_FIRST_CANON : AC_AUX_FIRST_RC;
-        if (fs + 1 == len) bits |= canon_fwd ? AC_AUX_FIRST_RC : AC_AUX_FIRST_CANON;
-        if (bits && (aux_seen & bits) != bits) ac_atomic_or(&t.slots[slot].aux, bits);   // usually already there (aux_seen may be stale: then the OR is merely redundant)
-        if (pos_slot) pos_slot[g] = (uint32_t)slot;
-    }
-    AC_D void insert(const Key<W>& fwd, const Key<W>& rc, uint64_t g, uint64_t fs, uint32_t len, uint32_t obs, uint32_t& claimed, uint32_t& claimed_dotted) const {
-        uint64_t slot = 0; uint32_t aux_seen = 0; bool canon_fwd = false;
-        if (find_or_claim(fwd, rc, g, slot, aux_seen, canon_fwd, claimed, claimed_dotted)) commit(slot, aux_seen, canon_fwd, g, fs, len, obs);
-    }
-    AC_D uint32_t observed(const Key<W>& fwd, const SeqInfo& s, uint64_t g, uint64_t fs) const {
-        uint32_t obs = 0;
-        if (fwd.d == 0) {
-            const bool cf = key_is_canonical(fwd, p);
+    AC_D Unit edge_unit(uint32_t g, uint32_t si) const {   // a block at the end of a sequence, between two sequences or at the edge of the shard
+        Unit u; u.fwd = Key<W>(); u.rc = Key<W>(); u.h = 0; u.flags = 0; u.dotted = false;
+        while (si + 1 < t.n_seqs && t.seqs[si + 1].start <= g) ++si;
+        const SeqInfo s = t.seqs[si];
+        const uint64_t fs = g - s.start;
+        u.valid = g >= g_begin && g < g_end && fs < s.len;         // else: outside the shard, or one of the k-1 padded bytes that start no window
+        if (!u.valid) return u;
+        u.fwd = fetch_codes<W>(t.packed, g, p);
+        u.fwd.d = window_dots(s, fs, p.k);
+        u.rc = key_rc(u.fwd, p);
+        const bool canon_fwd = key_is_canonical(u.fwd, p);
+        // Kmer::first_position (kmer_graph.rs:57-60): position 0 of the forward strand is window 0; position 0 of the
+        // reverse strand is the reverse complement of the last window (kmer_graph.rs:103-108).
+        if (fs == 0) u.flags |= canon_fwd ? AC_AUX_FIRST_CANON : AC_AUX_FIRST_RC;
+        if (fs + 1 == s.len) u.flags |= canon_fwd ? AC_AUX_FIRST_RC : AC_AUX_FIRST_CANON;
+        if (u.fwd.d == 0) {    // neighbouring bases seen next to this k-mer: spares the adjacency kernel the probes for neighbours it already knows to exist
             if (fs + 1 < s.len && window_dots(s, fs + 1, p.k) == 0) {
-                const uint32_t b = packed_base(t.packed, g + p.k);
-                obs |= cf ? (1u << (AC_AUX_OBS_OUT_SHIFT + b)) : (1u << (AC_AUX_OBS_IN_SHIFT + 3 - b));
+                const uint32_t b = packed_base(t.packed, (uint64_t)g + p.k);
+                u.flags |= canon_fwd ? (1u << (AC_AUX_OBS_OUT_SHIFT + b)) : (1u << (AC_AUX_OBS_IN_SHIFT + 3 - b));
             }
             if (fs > 0 && window_dots(s, fs - 1, p.k) == 0) {
-                const uint32_t b = packed_base(t.packed, g - 1);
-                obs |= cf ? (1u << (AC_AUX_OBS_IN_SHIFT + b)) : (1u << (AC_AUX_OBS_OUT_SHIFT + 3 - b));
+                const uint32_t b = packed_base(t.packed, (uint64_t)g - 1);
+                u.flags |= canon_fwd ? (1u << (AC_AUX_OBS_IN_SHIFT + b)) : (1u << (AC_AUX_OBS_OUT_SHIFT + 3 - b));
             }
         }
-        return obs;
+        u.h = key_hash(canon_fwd ? u.fwd : u.rc);
+        u.dotted = u.fwd.d != 0;
+        return u;
+    }
+    AC_D Unit unit_at(uint32_t g) const {
+        const uint32_t g0 = g & ~31u;
+        uint32_t si;
+#ifdef __CUDA_ARCH__
+        si = 0;
+        if ((threadIdx.x & 31) == 0) si = find_seq(t.seqs, t.n_seqs, g0);
+        si = __shfl_sync(0xFFFFFFFFu, si, 0);
+#else
+        si = find_seq(t.seqs, t.n_seqs, g0);
+#endif
+        const SeqInfo s = t.seqs[si];
+        const uint32_t fs0 = g0 - (uint32_t)s.start;
+        const bool interior = g0 >= g_begin && g0 + 32 <= g_end && fs0 >= (uint32_t)s.lead + 1 && (uint64_t)fs0 + 33 + s.trail <= s.len;
+        return interior ? interior_unit(g) : edge_unit(g, si);
+    }
+    // Enters the unit's k-mer (or finds it) and counts the occurrence.  All lanes of the warp call this together.
+    AC_D void upsert(const Unit& u, uint32_t g) const {
+        const uint32_t tag = make_tag(u.dotted, u.h);
+        const Slot mine = make_slot(g, tag, t.count_big ? 0u : 1u, u.flags);
+        uint64_t slot = table_home(t, u.h);
+        bool done = !u.valid, failed = false;
+        for (uint32_t probes = 0;;) {
+            bool claimed = false; Slot q = 0;
+            if (!done) {
+                for (;;) {
+                    Slot grp[4];
+                    const uint64_t base = slot & ~3ull;
+                    ac_ld_group(t.slots + base, grp);
+                    const uint32_t start = (uint32_t)(slot & 3u);
+                    bool stop = false; uint32_t at = 4;
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) {     // first slot of the group, from `slot` on, that is empty or carries the tag (unrolled: the group stays in registers)
+                        if (!stop && j >= start) {
+                            Slot e = grp[j];
+                            if (e == AC_EMPTY_SLOT) {
+                                e = ac_atomic_cas(&t.slots[base + j], (Slot)AC_EMPTY_SLOT, mine);
+                                if (e == AC_EMPTY_SLOT) { claimed = true; stop = true; at = j; }
+                            }
+                            if (!stop && slot_tag(e) == tag) { stop = true; at = j; }
+                            if (stop) q = e;
+                        }
+                    }
+                    slot = base + at;
+                    if (stop) break;
+                    if (slot >= t.cap) slot = 0;
+                    if (++probes > 2048) { counters[2] = 1; failed = true; done = true; break; }    // the table was sized too small: the host retries with the safe size
+                }
+            }
+#ifdef __CUDA_ARCH__
+            __syncwarp();
+#endif
+            if (!done) {
+                if (claimed) {
+                    if (t.count_big) ac_atomic_add(&t.count_big[slot], 1u);
+                    if (sizing) ac_atomic_add(&counters[0], 1ull);
+                    if (u.dotted) ac_atomic_add(&counters[1], 1ull);
+                    done = true;
+                } else {
+                    const Key<W> rep = window_key<W>(t, slot_gpos(q), u.dotted, p);
+                    if (key_eq(rep, u.fwd) || key_eq(rep, u.rc)) { if (!sizing) slot_add_occurrence(t, slot, q, g, 1u, u.flags, track_min, counters); done = true; }
+                    else if (++slot == t.cap) slot = 0;
+                }
+            }
+#ifdef __CUDA_ARCH__
+            if (__all_sync(0xFFFFFFFFu, done)) break;
+#else
+            if (done) break;
+#endif
+        }
+        if (u.valid && !failed && pos_slot) pos_slot[g] = (uint32_t)slot;
     }
     AC_D void operator()(uint64_t i) const {
-        uint64_t g = g_begin + i * AC_CHUNK;
-        const uint64_t g1 = (g + AC_CHUNK < g_end) ? g + AC_CHUNK : g_end;
-        uint32_t si = find_seq(t.seqs, t.n_seqs, g);
-        uint32_t claimed = 0, claimed_dotted = 0;
-        while (g < g1) {
-            const SeqInfo s = t.seqs[si];
-            uint64_t fs = g - s.start;
-            if (fs >= s.len) {                       // inside the k-1 padded bytes that start no window
-                if (si + 1 >= t.n_seqs) break;
-                ++si;
-                if (t.seqs[si].start > g) g = t.seqs[si].start;
-                continue;
-            }
-            const uint64_t stop = (s.start + s.len < g1) ? s.start + s.len : g1;
-            Key<W> fwd, rc;
-            bool rolling = false;
-            for (; g < stop; ++g, ++fs) {
-                const int32_t d = window_dots(s, fs, p.k);
-                if (d != 0) {
-                    fwd = fetch_codes<W>(t.packed, g, p); fwd.d = d; rc = key_rc(fwd, p);
-                    rolling = false;
-                } else if (!rolling) {
-                    fwd = fetch_codes<W>(t.packed, g, p); rc = key_rc(fwd, p);
-                    rolling = true;
-                } else {
-                    const uint64_t code = packed_base(t.packed, g + p.k - 1);
-                    key_push_right(fwd, code, p); key_push_left(rc, 3 - code, p);
-                }
-                // Neighbouring bases seen next to this k-mer, in the canonical strand's terms: a lower bound on the node-centric
-                // degrees that spares the adjacency kernel the probes for neighbours it already knows to exist.
-                insert(fwd, rc, g, fs, s.len, observed(fwd, s, g, fs), claimed, claimed_dotted);
-            }
-        }
-        if (claimed) ac_atomic_add(&counters[2 * (i % AC_STRIPES)], (unsigned long long)claimed);
-        if (claimed_dotted) ac_atomic_add(&counters[2 * (i % AC_STRIPES) + 1], (unsigned long long)claimed_dotted);
+        const uint32_t g = g_first + (uint32_t)i;
+        upsert(unit_at(g), g);
     }
 };
 
-// The same insertion with ONE window per thread: the lanes of a warp take 32 consecutive windows, so the pos_slot
-// stores coalesce, the packed-sequence reads of a warp fall in two or three sectors, and no lane waits for a
-// neighbour's longer probe chain across a whole AC_CHUNK of windows.  Costs a key_rc per window instead of a roll.
-template <int W> struct InsertLaneBody {
-    InsertBody<W> b;
-    // Launched over a multiple of 32 units so that whole warps enter: the lanes meet once more between the probe (whose
-    // length differs from lane to lane) and the bookkeeping that follows it.
+// The sizing pass: how many distinct canonical k-mers are there?  A k-mer is sampled when a hash of the seven bases around its centre,
+// read on its canonical strand, ends in six zero bits — a property of the k-mer, so it is kept or dropped with ALL its occurrences and
+// 64 x the number of distinct sampled k-mers estimates the total.  The test costs a few instructions per window (the centre bases roll
+// along the packed words); only the ~1/64 of the windows that pass build their keys and enter the small sample table.  Windows with
+// dots (at most k-1 per sequence end) are left out: they cannot move the estimate.  One thread scans 32 consecutive windows.
+template <int W> struct SampleBody {
+    InsertBody<W> ins; uint32_t total;
+    AC_D static bool sampled(uint32_t centre7) {          // centre7: 14 bits, the 7 bases around the centre base, first base most significant
+        uint32_t c = centre7;
+        if ((c >> 6) & 2u) {                               // centre base G or T: read the other strand (reverse the 7 bases, complement them)
+            uint32_t r = 0;
+            for (int b = 0; b < 7; ++b) r |= ((c >> (2 * b)) & 3u) << (2 * (6 - b));
+            c = ~r & 0x3FFFu;
+        }
+        return ((c * 0x9E3779B1u) >> 26) == 0;
+    }
     AC_D void operator()(uint64_t i) const {
-        const uint64_t g = b.g_begin + i;
-        const bool in_range = g < b.g_end;
-        uint32_t si = 0;
-#ifdef __CUDA_ARCH__
-        if ((threadIdx.x & 31) == 0) si = find_seq(b.t.seqs, b.t.n_seqs, g);     // lane 0 holds the warp's smallest coordinate
-        si = __shfl_sync(0xFFFFFFFFu, si, 0);
-        while (si + 1 < b.t.n_seqs && b.t.seqs[si + 1].start <= g) ++si;
-#else
-        si = find_seq(b.t.seqs, b.t.n_seqs, g);
-#endif
-        const SeqInfo s = b.t.seqs[si];
-        const uint64_t fs = g - s.start;
-        uint32_t claimed = 0, claimed_dotted = 0, aux_seen = 0, obs = 0;
-        uint64_t slot = 0; bool canon_fwd = false, found = false;
-        if (in_range && fs < s.len) {                    // else: past the end, or one of the k-1 padded bytes that start no window
-            Key<W> fwd = fetch_codes<W>(b.t.packed, g, b.p);
-            fwd.d = window_dots(s, fs, b.p.k);
-            const Key<W> rc = key_rc(fwd, b.p);
-            obs = b.observed(fwd, s, g, fs);
-            found = b.find_or_claim(fwd, rc, g, slot, aux_seen, canon_fwd, claimed, claimed_dotted);
+        const uint32_t g0 = (uint32_t)i * 32u;
+        const uint32_t si = find_seq(ins.t.seqs, ins.t.n_seqs, g0);
+        const SeqInfo s = ins.t.seqs[si];
+        const uint32_t fs0 = g0 - (uint32_t)s.start, k = ins.p.k, h = ins.p.h;
+        const bool interior = g0 + 32 <= total && fs0 >= (uint32_t)s.lead + 1 && (uint64_t)fs0 + 33 + s.trail <= s.len;
+        uint32_t hits = 0;
+        if (interior) {                                    // centre of window g0 + l is base g0 + l + h; the seven bases start at g0 + l + h - 3
+            const uint32_t first = g0 + h - 3;
+            uint64_t acc = 0;                              // rolling: the low 14 bits are the current seven bases
+            for (uint32_t b = 0; b < 6; ++b) acc = (acc << 2) | packed_base(ins.t.packed, (uint64_t)first + b);
+            for (uint32_t l = 0; l < 32; ++l) {
+                acc = (acc << 2) | packed_base(ins.t.packed, (uint64_t)first + 6 + l);
+                if (sampled((uint32_t)acc & 0x3FFFu)) hits |= 1u << l;
+            }
+        } else {
+            for (uint32_t l = 0; l < 32; ++l) {
+                const uint32_t g = g0 + l;
+                if (g >= total) break;
+                uint32_t sj = si;
+                while (sj + 1 < ins.t.n_seqs && ins.t.seqs[sj + 1].start <= g) ++sj;
+                const SeqInfo q = ins.t.seqs[sj];
+                const uint64_t fs = g - q.start;
+                if (fs >= q.len || window_dots(q, fs, k) != 0) continue;
+                uint32_t c = 0;
+                for (uint32_t b = 0; b < 7; ++b) c = (c << 2) | packed_base(ins.t.packed, (uint64_t)g + h - 3 + b);
+                if (sampled(c)) hits |= 1u << l;
+            }
         }
+        // the sampled windows of this thread, one at a time; the lanes of a warp go through upsert together (it votes)
 #ifdef __CUDA_ARCH__
-        __syncwarp();
-#endif
-        if (found) b.commit(slot, aux_seen, canon_fwd, g, fs, s.len, obs);
-#ifdef __CUDA_ARCH__
-        const uint32_t n_claimed = __reduce_add_sync(0xFFFFFFFFu, claimed), n_dotted = __reduce_add_sync(0xFFFFFFFFu, claimed_dotted);
-        if ((threadIdx.x & 31) == 0) {
-            const uint64_t stripe = (i >> 5) % AC_STRIPES;
-            if (n_claimed) ac_atomic_add(&b.counters[2 * stripe], (unsigned long long)n_claimed);
-            if (n_dotted) ac_atomic_add(&b.counters[2 * stripe + 1], (unsigned long long)n_dotted);
+        for (;;) {
+            const bool have = hits != 0;
+            if (!__any_sync(0xFFFFFFFFu, have)) break;
+            typename InsertBody<W>::Unit u; u.valid = false; u.dotted = false; u.h = 0; u.flags = 0; u.fwd = Key<W>(); u.rc = Key<W>();
+            uint32_t g = g0;
+            if (have) {
+                const uint32_t l = (uint32_t)ac_ctz(hits); hits &= hits - 1; g = g0 + l;
+                u.fwd = fetch_codes<W>(ins.t.packed, g, ins.p); u.fwd.d = 0; u.rc = key_rc(u.fwd, ins.p);
+                u.h = key_hash(key_is_canonical(u.fwd, ins.p) ? u.fwd : u.rc); u.valid = true;
+            }
+            ins.upsert(u, g);
         }
 #else
-        if (claimed) ac_atomic_add(&b.counters[2 * (i % AC_STRIPES)], (unsigned long long)claimed);
-        if (claimed_dotted) ac_atomic_add(&b.counters[2 * (i % AC_STRIPES) + 1], (unsigned long long)claimed_dotted);
+        for (; hits; hits &= hits - 1) {
+            const uint32_t g = g0 + (uint32_t)ac_ctz(hits);
+            typename InsertBody<W>::Unit u; u.dotted = false; u.flags = 0;
+            u.fwd = fetch_codes<W>(ins.t.packed, g, ins.p); u.fwd.d = 0; u.rc = key_rc(u.fwd, ins.p);
+            u.h = key_hash(key_is_canonical(u.fwd, ins.p) ? u.fwd : u.rc); u.valid = true;
+            ins.upsert(u, g);
+        }
 #endif
     }
 };
@@ -284,8 +381,8 @@ AC_D void bloom_slot(uint64_t h, uint64_t n_words, uint64_t& word, uint64_t& mas
 template <int W> struct BloomBuildBody {   // 16 filter bits per distinct k-mer, built once the table is complete
     TableView t; KParams p; const uint32_t* occupied; uint64_t* bloom; uint64_t n_words;
     AC_D void operator()(uint64_t x) const {
-        const uint64_t e = t.slots[occupied[x]].entry;
-        const Key<W> f = window_key<W>(t, entry_gpos(e), entry_dotted(e), p);
+        const Slot e = t.slots[occupied[x]];
+        const Key<W> f = window_key<W>(t, slot_gpos(e), slot_dotted(e), p);
         uint64_t word, mask;
         bloom_slot(key_hash(key_is_canonical(f, p) ? f : key_rc(f, p)), n_words, word, mask);
         if ((ac_ld_volatile(&bloom[word]) & mask) != mask) ac_atomic_or(&bloom[word], mask);
@@ -304,9 +401,9 @@ template <int W> struct AdjacencyBody {
     }
     AC_D void operator()(uint64_t x) const {
         const uint64_t i = occupied[x];
-        const uint64_t e = t.slots[i].entry;
-        const uint32_t aux = t.slots[i].aux;
-        const Key<W> f = window_key<W>(t, entry_gpos(e), entry_dotted(e), p);
+        const Slot e = t.slots[i];
+        const uint32_t aux = slot_flags(e);
+        const Key<W> f = window_key<W>(t, slot_gpos(e), slot_dotted(e), p);
         const Key<W> r = key_rc(f, p);
         const bool canon_fwd = key_is_canonical(f, p);
         uint32_t out_c, in_c;
@@ -329,10 +426,9 @@ template <int W> struct AdjacencyBody {
             }
         }
         uint32_t bits = 0;
-        if (out_c == 1 && !(aux & AC_AUX_FIRST_RC)) bits |= AC_AUX_OUT_OK;
-        if (in_c == 1 && !(aux & AC_AUX_FIRST_CANON)) bits |= AC_AUX_IN_OK;
-        t.slots[i].aux = aux | bits;
-        flags8[i] = (uint8_t)(bits >> 2);            // bit0 outOK, bit1 inOK (canonical orientation)
+        if (out_c == 1 && !(aux & AC_AUX_FIRST_RC)) bits |= AC_FLAG8_OUT_OK;
+        if (in_c == 1 && !(aux & AC_AUX_FIRST_CANON)) bits |= AC_FLAG8_IN_OK;
+        flags8[i] = (uint8_t)bits;                   // bit0 outOK, bit1 inOK (canonical orientation)
     }
 };
 
@@ -420,7 +516,7 @@ struct RunExportBody {
     const uint64_t* run_start; const uint32_t* run_len; const uint32_t* run_hs; const uint32_t* run_ts; const Slot* slots; RunRec* out;
     AC_D void operator()(uint64_t r) const {
         RunRec x; x.start = run_start[r]; x.len = run_len[r]; x.pad = 0;
-        x.head_rep = entry_gpos(slots[run_hs[r]].entry); x.tail_rep = entry_gpos(slots[run_ts[r]].entry);
+        x.head_rep = slot_gpos(slots[run_hs[r]]); x.tail_rep = slot_gpos(slots[run_ts[r]]);
         out[r] = x;
     }
 };
@@ -455,7 +551,7 @@ struct RepFlagBody {
 
 struct RunAssignBody {
     const uint64_t* run_start; const uint32_t* run_len; const uint32_t* run_uk; const uint8_t* run_dir;
-    const uint32_t* uid_rep; const uint32_t* rep_idx; const uint32_t* run_hs; const uint32_t* run_ts; const Slot* slots;
+    const uint32_t* uid_rep; const uint32_t* rep_idx; const uint32_t* run_hs; const uint32_t* run_ts; TableView t;
     uint32_t* run_unitig; DeviceUnitig* unitigs; uint32_t* slot_unitig;
     AC_D void operator()(uint64_t r) const {
         const uint32_t rep = uid_rep[run_uk[r]];
@@ -464,7 +560,7 @@ struct RunAssignBody {
         if (rep == (uint32_t)r) {
             const uint32_t hs = run_hs[r], ts = run_ts[r];
             DeviceUnitig u;
-            u.start = run_start[r]; u.len = run_len[r]; u.depth = slots[hs].count; u.flip = 0; u.min_d = 0;
+            u.start = run_start[r]; u.len = run_len[r]; u.depth = table_depth(t, hs); u.flip = 0; u.min_d = 0;
             u.head_slot = hs; u.tail_slot = ts;
             for (int w = 0; w < AC_MAX_W; ++w) u.min_w[w] = 0;
             unitigs[j] = u;
@@ -476,44 +572,45 @@ struct RunAssignBody {
 // Multi-GPU exchange of the deduplicated local tables ("k-mer buckets"): the occupied slots, compacted.
 struct ExportFlagBody {
     const Slot* slots; uint32_t* flag;
-    AC_D void operator()(uint64_t i) const { flag[i] = slots[i].entry != AC_EMPTY_ENTRY ? 1u : 0u; }
+    AC_D void operator()(uint64_t i) const { flag[i] = slots[i] != AC_EMPTY_SLOT ? 1u : 0u; }
 };
 struct OccupiedListBody {
     const Slot* slots; const uint32_t* off; uint32_t* list;
-    AC_D void operator()(uint64_t i) const { if (slots[i].entry != AC_EMPTY_ENTRY) list[off[i]] = (uint32_t)i; }
+    AC_D void operator()(uint64_t i) const { if (slots[i] != AC_EMPTY_SLOT) list[off[i]] = (uint32_t)i; }
 };
 struct ExportScatterBody {
-    const Slot* slots; const uint32_t* off; Slot* out;
-    AC_D void operator()(uint64_t i) const { const Slot s = slots[i]; if (s.entry != AC_EMPTY_ENTRY) out[off[i]] = s; }
+    TableView t; const uint32_t* off; SlotRec* out;
+    AC_D void operator()(uint64_t i) const { const Slot s = t.slots[i]; if (s != AC_EMPTY_SLOT) { SlotRec r; r.slot = s; r.count = table_depth(t, i); r.pad = 0; out[off[i]] = r; } }
 };
 // Folding another rank's entries into this rank's table: counts add, first/last flags OR, the entry keeps the smaller
 // occurrence.  Every rank holds all packed sequences, so the k-mer behind a remote entry is read from `packed`.
 template <int W> struct MergeBody {
-    TableView t; KParams p; const Slot* in; uint32_t* pos_slot; unsigned long long* counters;
+    TableView t; KParams p; const SlotRec* in; uint32_t* pos_slot; unsigned long long* counters;
     AC_D void operator()(uint64_t i) const {
-        const Slot r = in[i];
-        const uint64_t g = entry_gpos(r.entry);
-        const bool dotted = entry_dotted(r.entry);
+        const SlotRec r = in[i];
+        const uint64_t g = slot_gpos(r.slot);
+        const bool dotted = slot_dotted(r.slot);
+        const uint32_t flags = slot_flags(r.slot);
         const Key<W> fwd = window_key<W>(t, g, dotted, p);
         const Key<W> rc = key_rc(fwd, p);
         const uint64_t h = key_hash(key_is_canonical(fwd, p) ? fwd : rc);
-        const uint64_t mine = make_entry(g, dotted, h);
-        uint64_t slot = ac_umul64hi(h, t.cap);
+        const uint32_t tag = make_tag(dotted, h);
+        const Slot mine = make_slot(g, tag, t.count_big ? 0u : r.count, flags);
+        if (!t.count_big && r.count >= AC_SLOT_COUNT_ALARM) counters[3] = 1;
+        uint64_t slot = table_home(t, h);
         for (uint32_t probes = 0;; ++probes) {
-            if (probes > 8192) { counters[2 * AC_STRIPES] = 1; return; }
-            uint64_t e = ac_ld_volatile(&t.slots[slot].entry);
-            if (e == AC_EMPTY_ENTRY) {
-                e = ac_atomic_cas(&t.slots[slot].entry, (uint64_t)AC_EMPTY_ENTRY, mine);
-                if (e == AC_EMPTY_ENTRY) { ac_atomic_add(&counters[2 * (i % AC_STRIPES)], 1ull); if (dotted) ac_atomic_add(&counters[2 * (i % AC_STRIPES) + 1], 1ull); break; }
+            if (probes > 8192) { counters[2] = 1; return; }
+            Slot e = ac_ld_cg(&t.slots[slot]);
+            if (e == AC_EMPTY_SLOT) {
+                e = ac_atomic_cas(&t.slots[slot], (Slot)AC_EMPTY_SLOT, mine);
+                if (e == AC_EMPTY_SLOT) { if (t.count_big) ac_atomic_add(&t.count_big[slot], r.count); if (dotted) ac_atomic_add(&counters[1], 1ull); break; }
             }
-            if (entry_tag(e) == entry_tag(mine)) {
-                const Key<W> rep = window_key<W>(t, entry_gpos(e), dotted, p);
-                if (key_eq(rep, fwd) || key_eq(rep, rc)) { if (mine < e) ac_atomic_min(&t.slots[slot].entry, mine); break; }
+            if (slot_tag(e) == tag) {
+                const Key<W> rep = window_key<W>(t, slot_gpos(e), dotted, p);
+                if (key_eq(rep, fwd) || key_eq(rep, rc)) { slot_add_occurrence(t, slot, e, g, r.count, flags, true, counters); break; }
             }
             if (++slot == t.cap) slot = 0;
         }
-        ac_atomic_add(&t.slots[slot].count, r.count);
-        if (r.aux & AC_AUX_MERGE_MASK) ac_atomic_or(&t.slots[slot].aux, r.aux & AC_AUX_MERGE_MASK);
         pos_slot[g] = (uint32_t)slot;
     }
 };
@@ -625,19 +722,6 @@ struct SeedLess {
     }
 };
 #define AC_SORT_LEAF 8
-template <class Less> struct SortLeafBody {   // insertion sort of AC_SORT_LEAF consecutive unitigs: the first three merge levels in one launch
-    Less less; uint32_t n; uint32_t* idx;
-    AC_D void operator()(uint64_t c) const {
-        const uint32_t a = (uint32_t)c * AC_SORT_LEAF, b = a + AC_SORT_LEAF < n ? a + AC_SORT_LEAF : n;
-        uint32_t v[AC_SORT_LEAF];
-        for (uint32_t x = a; x < b; ++x) {
-            uint32_t y = x - a;
-            while (y > 0 && less(x, v[y - 1])) { v[y] = v[y - 1]; --y; }
-            v[y] = x;
-        }
-        for (uint32_t x = a; x < b; ++x) idx[x] = v[x - a];
-    }
-};
 template <class Less> struct MergePassBody {
     Less less; uint32_t n, width; const uint32_t* in; uint32_t* out;
     AC_D void operator()(uint64_t i) const {
@@ -657,6 +741,74 @@ template <class Less> struct MergePassBody {
         out[pair_start + ((uint32_t)i - run_start) + (lo - base)] = me;
     }
 };
+
+// The first eleven merge levels inside one CTA: AC_SORT_TILE indices are sorted in shared memory (insertion-sorted leaves of 8, then
+// merge rounds with a block barrier instead of a launch between them).  Every `Less` used here is a strict total order (ties end at
+// the index or an earlier position), so the result does not depend on how the sort is carried out.
+#define AC_SORT_TILE 2048
+#ifndef AC_EMULATE
+template <class Less> __global__ void __launch_bounds__(256) ac_tile_sort_kernel(const Less less, uint32_t n, uint32_t* __restrict__ idx) {
+    __shared__ uint32_t buf[2][AC_SORT_TILE];
+    const uint32_t base = blockIdx.x * AC_SORT_TILE, count = n - base < AC_SORT_TILE ? n - base : AC_SORT_TILE;
+    {   // leaves: 8 consecutive ids per thread
+        const uint32_t a = threadIdx.x * AC_SORT_LEAF, b = a + AC_SORT_LEAF < count ? a + AC_SORT_LEAF : count;
+        uint32_t v[AC_SORT_LEAF];
+        for (uint32_t x = a; x < b; ++x) {
+            uint32_t y = x - a;
+            while (y > 0 && less(base + x, v[y - 1])) { v[y] = v[y - 1]; --y; }
+            v[y] = base + x;
+        }
+        for (uint32_t x = a; x < b; ++x) buf[0][x] = v[x - a];
+    }
+    __syncthreads();
+    int cur = 0;
+    for (uint32_t width = AC_SORT_LEAF; width < count; width *= 2, cur ^= 1) {
+        const uint32_t* in = buf[cur]; uint32_t* out = buf[cur ^ 1];
+        for (uint32_t i = threadIdx.x; i < count; i += 256) {
+            const uint32_t me = in[i];
+            const uint32_t run = i / width, pair_start = (run & ~1u) * width, run_start = run * width;
+            const bool left = !(run & 1u);
+            uint32_t lo, hi;
+            if (left) { lo = run_start + width; hi = lo + width; } else { lo = pair_start; hi = run_start; }
+            if (lo > count) lo = count;
+            if (hi > count) hi = count;
+            const uint32_t first = lo;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const bool before = left ? less(in[mid], me) : !less(me, in[mid]); if (before) lo = mid + 1; else hi = mid; }
+            out[pair_start + (i - run_start) + (lo - first)] = me;
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < count; i += 256) idx[base + i] = buf[cur][i];
+}
+#endif
+template <class Less> struct TileSortBody {   // emulation form: any correct sort of the tile
+    Less less; uint32_t n; uint32_t* idx;
+    AC_D void operator()(uint64_t c) const {
+        const uint32_t a = (uint32_t)c * AC_SORT_TILE, b = a + AC_SORT_TILE < n ? a + AC_SORT_TILE : n;
+        for (uint32_t x = a; x < b; ++x) {
+            uint32_t y = x;
+            while (y > a && less(x, idx[y - 1])) { idx[y] = idx[y - 1]; --y; }
+            idx[y] = x;
+        }
+    }
+};
+// Sorts the ids 0..n-1 by `less`; returns the buffer (a or b) that holds the result.
+template <class Less> static uint32_t* sort_indices(AcStream* stream, const Less& less, uint32_t n, uint32_t* a, uint32_t* b) {
+    if (n == 0) return a;
+    const uint64_t tiles = ((uint64_t)n + AC_SORT_TILE - 1) / AC_SORT_TILE;
+#ifndef AC_EMULATE
+    ac_tile_sort_kernel<Less><<<(unsigned)tiles, 256, 0, stream->s>>>(less, n, a); ++g_ac_kernel_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("launch tile sort: ") + cudaGetErrorString(e));
+#else
+    ac_launch("tile_sort", stream, TileSortBody<Less>{less, n, a}, tiles);
+#endif
+    for (uint64_t width = AC_SORT_TILE; width < n; width *= 2) {
+        ac_launch("merge_pass", stream, MergePassBody<Less>{less, n, (uint32_t)width, a, b}, n);
+        std::swap(a, b);
+    }
+    return a;
+}
 
 // renumber_unitigs (unitig_graph.rs:295-315) for the graph as built: length descending, sequence ascending, depth descending,
 // ties in creation (seed) order because the reference's sort is stable.  The first 8 bases ride along as a big-endian word.
@@ -928,11 +1080,33 @@ struct LevelRelaxBody {
 struct RelocBoundBody {      // room the pass can ask for at most: every candidate may move its destination once, by no more than its shortest source
     const ExpandCandidate* cands; const UnitigRec* rec; const int32_t* cand_at; unsigned long long* bound;
     AC_D uint32_t shortest(const ExpandCandidate& cd) const { uint32_t m = 0xFFFFFFFFu; for (uint32_t a = 0; a < cd.gn; ++a) { const uint32_t l = rec[cd.src[a] >> 1].len; if (l < m) m = l; } return m; }
-    AC_D void operator()(uint64_t ci) const {
+    AC_D unsigned long long bound_of(uint64_t ci) const {
         const ExpandCandidate& cd = cands[ci];
         const int32_t other = cand_at[2 * (size_t)cd.idx + (cd.side ^ 1u)];
         const unsigned long long mine = shortest(cd), partner = other >= 0 ? shortest(cands[other]) : 0;
-        ac_atomic_add(bound, (unsigned long long)rec[cd.idx].len + mine + 2 * partner + 10ull * AC_SEQ_SLACK + 64);
+        return (unsigned long long)rec[cd.idx].len + mine + 2 * partner + 10ull * AC_SEQ_SLACK + 64;
+    }
+    AC_D void operator()(uint64_t ci) const {
+        ac_atomic_add(bound + (ci & (AC_BOUND_STRIPES - 1)), bound_of(ci));        // striped: one hot address would serialise in its L2 slice
+    }
+};
+// The relaxation to its fixed point in ONE cooperative launch: a grid barrier per round instead of a launch and a host round trip.
+struct LevelsCoopBody {
+    const int32_t* pred; uint32_t* level; uint32_t* flags; uint64_t n;      // flags: [0..2] "a level moved" (round-robin, zeroed), [3] highest level, [4] did not settle
+    template <class Sync> AC_D void operator()(uint64_t tid, uint64_t nt, Sync& sync) const {
+        for (uint32_t round = 0;; ++round) {
+            uint32_t* changed = flags + round % 3;
+            if (tid == 0) flags[(round + 1) % 3] = 0;
+            for (uint64_t ci = tid; ci < n; ci += nt) {
+                uint32_t lv = 0;
+                for (int x = 0; x < 7; ++x) { const int32_t q = pred[ci * 7 + x]; if (q >= 0) { const uint32_t l = ac_ld_volatile(&level[q]); if (l > lv) lv = l; } }
+                if (lv + 1 != level[ci]) { level[ci] = lv + 1; *changed = 1; }
+                ac_atomic_max(&flags[3], lv + 1);
+            }
+            sync();
+            if (!ac_ld_volatile(changed)) return;
+            if (round > 100000) { if (tid == 0) flags[4] = 1; return; }
+        }
     }
 };
 struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates of one level; within a level no two of them share a unitig
@@ -1020,6 +1194,23 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
         }
         if (c != common_len) ac_atomic_or(&dirty[(size_t)ci >> 6], (uint64_t)1 << (ci & 63));          // capped: look again next pass
         ac_atomic_add(total_shifted, (unsigned long long)c);
+    }
+};
+
+// One pass of expand_repeats in ONE cooperative launch: the levels in order with a grid barrier between them, then the room the NEXT
+// pass may ask for (only candidates left on the work list can act in it).
+struct ApplyPassCoopBody {
+    ApplyLevelBody apply; RelocBoundBody next_bound; uint64_t n; const uint32_t* n_levels;
+    template <class Sync> AC_D void operator()(uint64_t tid, uint64_t nt, Sync& sync) const {
+        const uint32_t levels = *n_levels;
+        ApplyLevelBody a = apply;
+        for (uint32_t l = 1; l <= levels; ++l) {
+            a.this_level = l;
+            for (uint64_t ci = tid; ci < n; ci += nt) a(ci);
+            sync();
+        }
+        for (uint64_t ci = tid; ci < n; ci += nt)
+            if (ac_ld_volatile(&apply.dirty[ci >> 6]) >> (ci & 63) & 1) ac_atomic_add(next_bound.bound + (ci & (AC_BOUND_STRIPES - 1)), next_bound.bound_of(ci));
     }
 };
 
@@ -1347,9 +1538,10 @@ struct DevicePipeline::Impl {
     // pipeline state shared by the stages
     std::vector<SeqInfo> host_seqs;
     uint64_t cap = 0, n_windows = 0, n_runs = 0, g_begin = 0, g_end = 0, n_slots_used = 0, n_dotted = 0;
-    bool any_dotted = false, is_multi = false;
+    bool any_dotted = false, is_multi = false, big_counts = false;      // big_counts: depths live in count_big (a 16-bit count ran out)
     int stage = 0;
-    DevBuf run_hs, run_ts, exp_flag, occ_list, bloom, needles, hits;
+    DevBuf run_hs, run_ts, exp_flag, occ_list, bloom, needles, hits, count_big;
+    TableView table_view() { return TableView{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, big_counts ? count_big.as<uint32_t>() : nullptr}; }
     void set_device() {
 #ifndef AC_EMULATE
         AC_CUDA_CHECK(cudaSetDevice(device));
@@ -1408,7 +1600,7 @@ void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo*
     if (k < 3 || (k & 1) == 0) throw std::runtime_error("k must be odd and >= 3");
     const int W = (int)((2 * k + 63) / 64);
     if (W > AC_MAX_W) throw std::runtime_error("k-mer sizes above 127 are not supported by the GPU path (no CPU fallback exists)");
-    if (total >= (1ull << 36)) throw std::runtime_error("more than 2^36 padded input bytes are not supported");
+    if (total >= 0xFFFFFFF0ull) throw std::runtime_error("more than 2^32 padded input bytes are not supported");
     if (n_seqs == 0 || total == 0) throw std::runtime_error("no sequences");
     m.total = total; m.n_seqs = n_seqs; m.k = k; m.W = W; m.stage = 0;
     m.host_seqs.assign(seqs, seqs + n_seqs);
@@ -1428,12 +1620,7 @@ void DevicePipeline::sort_number_keys(const NumberKey* keys, uint32_t n, uint32_
     m.d_keys.ensure((size_t)n * sizeof(NumberKey)); m.sort_a.ensure((size_t)n * 4); m.sort_b.ensure((size_t)n * 4);
     ac_h2d(m.d_keys.p, m.h_keys.p, (size_t)n * sizeof(NumberKey), &m.stream);
     const NumberKeyLess less{m.d_keys.as<NumberKey>()};
-    uint32_t* in = m.sort_a.as<uint32_t>(); uint32_t* out = m.sort_b.as<uint32_t>();
-    ac_launch("number_leaf", &m.stream, SortLeafBody<NumberKeyLess>{less, n, in}, ((uint64_t)n + AC_SORT_LEAF - 1) / AC_SORT_LEAF);
-    for (uint64_t width = AC_SORT_LEAF; width < n; width *= 2) {
-        ac_launch("number_merge", &m.stream, MergePassBody<NumberKeyLess>{less, n, (uint32_t)width, in, out}, n);
-        std::swap(in, out);
-    }
+    uint32_t* in = sort_indices(&m.stream, less, n, m.sort_a.as<uint32_t>(), m.sort_b.as<uint32_t>());
     m.h_sorted.ensure((size_t)n * 4);
     ac_d2h(m.h_sorted.p, in, (size_t)n * 4, &m.stream);
     ac_sync(&m.stream);
@@ -1484,7 +1671,7 @@ void DevicePipeline::find_literals(const uint8_t* ascii_host, uint64_t total_byt
         table[slot].w[0] = WH == 1 ? k2.w[1] : k2.w[0]; table[slot].w[1] = k2.w[1]; table[slot].id = i; table[slot].used = 1;
     }
     m.needles.ensure(cap * sizeof(NeedleSlot)); ac_h2d(m.needles.p, table.data(), cap * sizeof(NeedleSlot), &m.stream);
-    m.counters.ensure((2 * AC_STRIPES + 2) * sizeof(unsigned long long));
+    m.counters.ensure(8 * sizeof(unsigned long long));
     uint64_t hit_cap = 1u << 20;
     for (;;) {
         m.hits.ensure(hit_cap * sizeof(LiteralHit));
@@ -1502,6 +1689,7 @@ void DevicePipeline::find_literals(const uint8_t* ascii_host, uint64_t total_byt
 }
 
 // ---- stage 1: pack + k-mer table over this rank's sequences ----
+#define AC_N_COUNTERS 4          // InsertBody::counters
 template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t seq_hi, bool multi) {
     const KParams p = make_kparams(k, W);
     if (seq_lo > seq_hi || seq_hi > n_seqs) throw std::runtime_error("bad sequence shard");
@@ -1512,7 +1700,7 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
     // windows = total - n_seqs*(k-1); a canonical table can hold at most that many entries (all ranks' windows: after
     // the exchange every rank's table holds the k-mers of every sequence)
     n_windows = total - (uint64_t)n_seqs * (k - 1);
-    cap = n_windows + n_windows / 2 + 64;
+    cap = (n_windows + n_windows / 2 + 64 + 3) & ~3ull;      // a multiple of 4: the table is probed in groups of four slots
     if (cap >= 0xFFFFFFF0ull) throw std::runtime_error("input too large for 32-bit slot indices");
 
     mark(2);
@@ -1526,41 +1714,44 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
     // (sampling by hash value keeps or drops a k-mer with ALL its occurrences, so 64 x the sample's distinct count is an
     // unbiased estimate; every rank samples every sequence because after the exchange its table holds all of them.)
     const uint64_t safe_cap = cap;
-    const size_t counter_words = 2 * AC_STRIPES + 2;
-    counters.ensure(counter_words * sizeof(unsigned long long));
-    const double load = getenv("AC_TABLE_LOAD") ? atof(getenv("AC_TABLE_LOAD")) : 0.45;
-    if (load > 0 && n_windows > (1u << 16)) {
-        const uint64_t sample_cap = n_windows / 64 * 2 + 4096;
+    counters.ensure(AC_N_COUNTERS * sizeof(unsigned long long));
+    unsigned long long hc[AC_N_COUNTERS] = {0, 0, 0, 0};
+    big_counts = getenv("AC_BIG_COUNTS") != nullptr;      // test hook: take the 32-bit side array from the start
+    const double load = getenv("AC_TABLE_LOAD") ? atof(getenv("AC_TABLE_LOAD")) : 0.5;
+    if (load > 0 && n_windows > (1u << 16) && k >= 7) {
+        const uint64_t sample_cap = (n_windows / 64 * 4 + 4096) & ~3ull;
         slots.ensure(sample_cap * sizeof(Slot));
-        ac_launch("init_slots", &stream, InitSlotsBody{slots.as<Slot>()}, sample_cap);
-        ac_memset(counters.p, 0, counter_words * sizeof(unsigned long long), &stream);
-        const TableView sv{slots.as<Slot>(), sample_cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
-        ac_launch("sample", &stream, InsertBody<W>{sv, p, 0, total, false, nullptr, counters.as<unsigned long long>(), 63}, (total + AC_CHUNK - 1) / AC_CHUNK);
-        std::vector<unsigned long long> hc(counter_words);
-        ac_d2h(hc.data(), counters.p, hc.size() * sizeof(unsigned long long), &stream); ac_sync(&stream);
-        unsigned long long sampled = 0; for (int x = 0; x < AC_STRIPES; ++x) sampled += hc[2 * x];
-        if (!hc[2 * AC_STRIPES]) {
-            const uint64_t est = (sampled + 3 * (uint64_t)std::sqrt((double)sampled) + 16) * 64;      // + 3 sigma
-            cap = std::min<uint64_t>(safe_cap, (uint64_t)((double)est / load) + 4096);
+        ac_memset(slots.p, 0xFF, sample_cap * sizeof(Slot), &stream);
+        ac_memset(counters.p, 0, sizeof hc, &stream);
+        const TableView sv{slots.as<Slot>(), sample_cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, nullptr};
+        const InsertBody<W> sample_ins{sv, p, 0, 0, (uint32_t)total, false, nullptr, counters.as<unsigned long long>(), true};
+        ac_launch("sample", &stream, SampleBody<W>{sample_ins, (uint32_t)total}, ((total + 31) / 32 + 31) / 32 * 32);
+        ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
+        if (!hc[2]) {      // every rank samples every sequence, so all of them arrive at the same size
+            const uint64_t est = (hc[0] + 3 * (uint64_t)std::sqrt((double)hc[0]) + 16) * 64 + (uint64_t)n_seqs * 2 * k;      // + 3 sigma, + the windows with dots it left out
+            cap = std::min<uint64_t>(safe_cap, ((uint64_t)((double)est / load) + 4096 + 3) & ~3ull);
         }
     }
     mark(15);
 
     pos_slot.ensure(total * sizeof(uint32_t));
     for (int attempt = 0;; ++attempt) {
+        if (attempt > 3) throw std::runtime_error("k-mer table build did not settle");
         slots.ensure(cap * sizeof(Slot));
-        ac_launch("init_slots", &stream, InitSlotsBody{slots.as<Slot>()}, cap);
-        ac_memset(counters.p, 0, counter_words * sizeof(unsigned long long), &stream);
-        const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
-        const InsertBody<W> ins{tv, p, g_begin, g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), 0};
-        if (getenv("AC_INSERT_CHUNKED")) ac_launch("insert", &stream, ins, (g_end - g_begin + AC_CHUNK - 1) / AC_CHUNK);
-        else ac_launch_occ("insert", &stream, InsertLaneBody<W>{ins}, (g_end - g_begin + 31) / 32 * 32, insert_occupancy);
-        if (cap == safe_cap) break;                      // cannot overflow: one slot and a half per window
-        unsigned long long overflow = 0;
-        ac_d2h(&overflow, counters.as<unsigned long long>() + 2 * AC_STRIPES, sizeof overflow, &stream); ac_sync(&stream);
-        if (!overflow) break;
-        cap = safe_cap;                                  // the estimate was off (it is an estimate): start again with the safe size
+        ac_memset(slots.p, 0xFF, cap * sizeof(Slot), &stream);               // AC_EMPTY_SLOT
+        if (big_counts) { count_big.ensure(cap * 4); ac_memset(count_big.p, 0, cap * 4, &stream); }
+        ac_memset(counters.p, 0, sizeof hc, &stream);
+        const TableView tv = table_view();
+        const uint64_t g_first = g_begin & ~31ull;
+        const InsertBody<W> ins{tv, p, (uint32_t)g_first, (uint32_t)g_begin, (uint32_t)g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), false};
+        ac_launch_occ("insert", &stream, ins, (g_end - g_first + 31) / 32 * 32, insert_occupancy);
+        ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
+        if (hc[2] && cap != safe_cap) { cap = safe_cap; continue; }         // the estimate was off (it is an estimate): start again with the safe size
+        if (hc[2]) throw std::runtime_error("k-mer table overflow");
+        if (hc[3] && !big_counts) { big_counts = true; continue; }          // a k-mer with more than 49151 occurrences: counts move to the 32-bit side array
+        break;
     }
+    n_dotted = hc[1];
     mark(4);
     stage = 1;
 }
@@ -1574,34 +1765,36 @@ uint64_t DevicePipeline::Impl::do_count_entries() {
 }
 void DevicePipeline::Impl::do_export_entries(void* dst, uint64_t cap_records) {
     if (cap_records < exp_n) throw std::runtime_error("entry buffer too small");
-    ac_launch("export_scatter", &stream, ExportScatterBody{slots.as<Slot>(), exp_flag.as<uint32_t>(), (Slot*)dst}, cap);
+    ac_launch("export_scatter", &stream, ExportScatterBody{table_view(), exp_flag.as<uint32_t>(), (SlotRec*)dst}, cap);
     ac_sync(&stream);
 }
 
 template <int W> void DevicePipeline::Impl::merge_w(const void* dev_ptr, uint64_t n) {
     if (stage < 1) throw std::runtime_error("build_local must precede merge_entries");
     const KParams p = make_kparams(k, W);
-    const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
-    ac_launch("merge", &stream, MergeBody<W>{tv, p, (const Slot*)dev_ptr, pos_slot.as<uint32_t>(), counters.as<unsigned long long>()}, n);
+    ac_launch("merge", &stream, MergeBody<W>{table_view(), p, (const SlotRec*)dev_ptr, pos_slot.as<uint32_t>(), counters.as<unsigned long long>()}, n);
 }
 
 // ---- stage 2: adjacency over the (now global) table, unitig occurrences along this rank's sequences ----
 template <int W> void DevicePipeline::Impl::runs_local_w() {
     if (stage < 1) throw std::runtime_error("build_local must precede runs_local");
     const KParams p = make_kparams(k, W);
-    const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
+    const TableView tv = table_view();
     mark(13);
-    std::vector<unsigned long long> hc(2 * AC_STRIPES + 2);
-    ac_d2h(hc.data(), counters.p, hc.size() * sizeof(unsigned long long), &stream); ac_sync(&stream);
-    if (hc[2 * AC_STRIPES]) throw std::runtime_error("k-mer table overflow while merging");
-    n_slots_used = 0; n_dotted = 0;
-    for (int x = 0; x < AC_STRIPES; ++x) { n_slots_used += hc[2 * x]; n_dotted += hc[2 * x + 1]; }
+    if (is_multi) {      // the merges may have tripped the limits too
+        unsigned long long hc[AC_N_COUNTERS];
+        ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
+        if (hc[2]) throw std::runtime_error("k-mer table overflow while merging");
+        if (hc[3] && !big_counts) throw std::runtime_error("a k-mer occurs more than 49151 times across the ranks: not supported by the multi-GPU exchange");
+        n_dotted = hc[1];
+    }
     any_dotted = n_dotted != 0;
 
     flags8.ensure(cap);
-    exp_flag.ensure(cap * 4); occ_list.ensure((n_slots_used + 1) * 4);
+    exp_flag.ensure(cap * 4);
     ac_launch("occupied_flag", &stream, ExportFlagBody{slots.as<Slot>(), exp_flag.as<uint32_t>()}, cap);
-    exclusive_scan(exp_flag.as<uint32_t>(), exp_flag.as<uint32_t>(), cap, 0, false);
+    n_slots_used = exclusive_scan(exp_flag.as<uint32_t>(), exp_flag.as<uint32_t>(), cap);       // distinct canonical k-mers = occupied slots
+    occ_list.ensure((n_slots_used + 1) * 4);
     ac_launch("occupied_list", &stream, OccupiedListBody{slots.as<Slot>(), exp_flag.as<uint32_t>(), occ_list.as<uint32_t>()}, cap);
     const uint64_t bloom_words = n_slots_used / 4 + 64;       // 16 bits per distinct k-mer
     bloom.ensure(bloom_words * 8);
@@ -1643,7 +1836,7 @@ void DevicePipeline::Impl::do_import_runs(const void* dev_ptr, uint64_t n) {
 template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool keep_positions) {
     if (stage < 2) throw std::runtime_error("runs_local must precede finish");
     const KParams p = make_kparams(k, W);
-    const TableView tv{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs};
+    const TableView tv = table_view();
     out = PipelineResult();
     out.W = W; out.capacity = cap; out.n_slots_used = n_slots_used; out.n_dotted = n_dotted;
     const uint64_t n_runs = this->n_runs;
@@ -1660,7 +1853,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     const uint32_t n_unitigs = exclusive_scan(is_rep.as<uint32_t>(), rep_idx.as<uint32_t>(), n_runs);
     unitigs.ensure((size_t)n_unitigs * sizeof(DeviceUnitig));
     ac_launch("run_assign", &stream, RunAssignBody{run_start.as<uint64_t>(), run_len.as<uint32_t>(), run_uk.as<uint32_t>(), run_dir.as<uint8_t>(),
-                                                   uid_rep.as<uint32_t>(), rep_idx.as<uint32_t>(), run_hs.as<uint32_t>(), run_ts.as<uint32_t>(), slots.as<Slot>(),
+                                                   uid_rep.as<uint32_t>(), rep_idx.as<uint32_t>(), run_hs.as<uint32_t>(), run_ts.as<uint32_t>(), tv,
                                                    run_unitig.as<uint32_t>(), unitigs.as<DeviceUnitig>(), slot_unitig.as<uint32_t>()}, n_runs);
     mark(7);
 
@@ -1684,14 +1877,8 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     // ---- seed order: stable LSD radix sort of the unitigs by their seed k-mer ----
     const uint32_t U = n_unitigs;
     sort_a.ensure((size_t)U * 4); sort_b.ensure((size_t)U * 4);
-    uint32_t* idx_in = sort_a.as<uint32_t>(); uint32_t* idx_out = sort_b.as<uint32_t>();
     const SeedLess seed_less{unitigs.as<DeviceUnitig>(), W};
-    ac_launch("sort_leaf", &stream, SortLeafBody<SeedLess>{seed_less, U, idx_in}, ((uint64_t)U + AC_SORT_LEAF - 1) / AC_SORT_LEAF);
-    for (uint64_t width = AC_SORT_LEAF; width < U; width *= 2) {
-        ac_launch("merge_pass", &stream, MergePassBody<SeedLess>{seed_less, U, (uint32_t)width, idx_in, idx_out}, U);
-        std::swap(idx_in, idx_out);
-    }
-    const uint32_t* perm = idx_in;
+    const uint32_t* perm = sort_indices(&stream, seed_less, U, sort_a.as<uint32_t>(), sort_b.as<uint32_t>());
     mark(10);
 
     // ---- host-ready arrays in seed order ----
@@ -1733,12 +1920,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     num_prefix.ensure((size_t)U * 8);
     ac_launch("number_key", &stream, NumberKeyBody{d_rec.as<UnitigRec>(), d_arena.as<char>(), num_prefix.as<uint64_t>()}, U);
     const NumberLess number_less{d_rec.as<UnitigRec>(), d_depth.as<uint32_t>(), d_arena.as<char>(), num_prefix.as<uint64_t>(), nullptr};
-    uint32_t* ord_in = sort_a.as<uint32_t>(); uint32_t* ord_out = sort_b.as<uint32_t>();
-    ac_launch("number_leaf", &stream, SortLeafBody<NumberLess>{number_less, U, ord_in}, ((uint64_t)U + AC_SORT_LEAF - 1) / AC_SORT_LEAF);
-    for (uint64_t width = AC_SORT_LEAF; width < U; width *= 2) {
-        ac_launch("number_merge", &stream, MergePassBody<NumberLess>{number_less, U, (uint32_t)width, ord_in, ord_out}, U);
-        std::swap(ord_in, ord_out);
-    }
+    uint32_t* ord_in = sort_indices(&stream, number_less, U, sort_a.as<uint32_t>(), sort_b.as<uint32_t>());
     // the work list of expand_repeats, in the numbering order just found
     d_fixed.ensure((size_t)U * 4); ac_memset(d_fixed.p, 0, (size_t)U * 4, &stream);
     uint8_t* seed_start = d_fixed.as<uint8_t>(); uint8_t* seed_end = seed_start + U; uint8_t* fix_start = seed_end + U; uint8_t* fix_end = fix_start + U;
@@ -1757,73 +1939,59 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     ac_launch("common_length", &stream, CommonLengthBody{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_arena.as<char>(), d_spec.as<uint32_t>()}, n_cands);
     // Opt-in: the whole first pass of expand_repeats here, level by level (the host then starts at pass 2).
     static const bool device_first_pass = getenv("AC_DEVICE_FIRST_PASS") != nullptr || getenv("AC_DEVICE_SIMPLIFY") != nullptr;
-    uint64_t arena_final = arena_bytes, first_pass_total = 0; uint32_t n_levels = 0; bool first_pass_done = false;
+    uint64_t arena_final = arena_bytes, first_pass_total = 0; bool first_pass_done = false;
     const uint32_t* final_order = nullptr;      // device pointer: the numbering after simplify_structure, when that ran here
     bool gfa_on_device = false; uint64_t gfa_s_bytes = 0, gfa_l_bytes = 0, gfa_p_bytes = 0;
     if (device_first_pass && n_cands > 0) {
-        d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(16); d_counters64.ensure(32);
+        static const bool device_simplify = getenv("AC_DEVICE_SIMPLIFY") != nullptr;
+        d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(32); d_counters64.ensure((2 * AC_BOUND_STRIPES + 2) * 8);
         d_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); d_exhausted.ensure(n_cands + 8);
+        unsigned long long* c64 = d_counters64.as<unsigned long long>();         // [0] arena bump, [1] bases moved, [2..] bound stripes of this pass, then of the next
+        unsigned long long* bound_now = c64 + 2; unsigned long long* bound_next = c64 + 2 + AC_BOUND_STRIPES;
         ac_launch("level_pred", &stream, LevelPredBody{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_pred.as<int32_t>()}, n_cands);
-        ac_memset(d_level.p, 0, n_cands * 4, &stream);
-        for (uint32_t round = 0;; ++round) {
-            ac_memset(d_flagmax.p, 0, 8, &stream);
-            ac_launch("level_relax", &stream, LevelRelaxBody{d_pred.as<int32_t>(), d_level.as<uint32_t>(), d_flagmax.as<uint32_t>()}, n_cands);
-            uint32_t fm[2] = {0, 0};
-            ac_d2h(fm, d_flagmax.p, 8, &stream); ac_sync(&stream);
-            n_levels = fm[1];
-            if (!fm[0]) break;
-            if (round > 4096) throw std::runtime_error("candidate levels did not settle");
-        }
-        if (n_levels <= 250) {
-            ac_memset(d_counters64.p, 0, 32, &stream);
-            unsigned long long* c64 = d_counters64.as<unsigned long long>();                     // [0] relocation bound, [1] arena bump, [2] bases moved
-            ac_launch("reloc_bound", &stream, RelocBoundBody{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_cand_at.as<int32_t>(), c64}, n_cands);
-            unsigned long long bound = 0;
-            ac_d2h(&bound, c64, 8, &stream); ac_sync(&stream);
+        ac_memset(d_level.p, 0, n_cands * 4, &stream); ac_memset(d_flagmax.p, 0, 32, &stream);
+        ac_launch_coop("levels", &stream, LevelsCoopBody{d_pred.as<int32_t>(), d_level.as<uint32_t>(), d_flagmax.as<uint32_t>(), n_cands}, n_cands);
+        ac_memset(d_counters64.p, 0, (2 * AC_BOUND_STRIPES + 2) * 8, &stream);
+        const RelocBoundBody bound_body{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_cand_at.as<int32_t>(), bound_now};
+        ac_launch("reloc_bound", &stream, bound_body, n_cands);
+        uint32_t fm[8]; std::vector<unsigned long long> h64(2 * AC_BOUND_STRIPES + 2);
+        ac_d2h(fm, d_flagmax.p, 32, &stream); ac_d2h(h64.data(), c64, h64.size() * 8, &stream); ac_sync(&stream);
+        if (fm[4]) throw std::runtime_error("candidate levels did not settle");
+        (void)fm[3];                             // the number of levels stays on the device (ApplyPassCoopBody reads it)
+        unsigned long long bound = 0; for (int x = 0; x < AC_BOUND_STRIPES; ++x) bound += h64[2 + x];
+        {
             if (arena_bytes + bound >= 0xFFFFFFF0ull) throw std::runtime_error("unitig sequence arena would exceed 4 GB");
             d_arena2.ensure(arena_bytes + bound + 64);
             ac_copy_dd(d_arena2.p, d_arena.p, arena_bytes, &stream);
             const unsigned long long start = arena_bytes;
-            ac_h2d(c64 + 1, &start, 8, &stream);
+            ac_h2d(c64, &start, 8, &stream);
             ac_memset(d_dirty.p, 0, ((n_cands + 63) / 64) * 8 + 8, &stream); ac_memset(d_exhausted.p, 0, n_cands + 8, &stream);
-            for (uint32_t l = 1; l <= n_levels; ++l)
-                ac_launch("apply_level", &stream, ApplyLevelBody{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_level.as<uint32_t>(), l, d_spec.as<uint32_t>(),
-                                                                 d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64 + 1, c64 + 2, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>(), true}, n_cands);
-            unsigned long long after[2] = {0, 0};
-            ac_d2h(after, c64 + 1, 16, &stream); ac_sync(&stream);
-            arena_final = after[0]; first_pass_total = after[1]; first_pass_done = true;
-            // AC_DEVICE_SIMPLIFY=1: `while expand_repeats() > 0 {}` to its end here; the host is left with the renumbering
-            static const bool device_simplify = getenv("AC_DEVICE_SIMPLIFY") != nullptr;
-            for (uint32_t pass = 2; device_simplify && first_pass_total > 0; ++pass) {
-                ac_memset(c64, 0, 8, &stream);
-                ac_launch("reloc_bound", &stream, RelocBoundBody{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_cand_at.as<int32_t>(), c64}, n_cands);
-                ac_d2h(&bound, c64, 8, &stream); ac_sync(&stream);
+            // `while expand_repeats() > 0 {}` (with AC_DEVICE_SIMPLIFY; else only its first call): one launch and one read-back per pass
+            for (uint32_t pass = 1;; ++pass) {
+                const ApplyLevelBody apply{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_level.as<uint32_t>(), 0, d_spec.as<uint32_t>(),
+                                           d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64, c64 + 1, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>(), pass == 1};
+                RelocBoundBody nb = bound_body; nb.bound = bound_next;
+                ac_launch_coop("apply_pass", &stream, ApplyPassCoopBody{apply, nb, n_cands, d_flagmax.as<uint32_t>() + 3}, n_cands);
+                ac_d2h(h64.data(), c64, h64.size() * 8, &stream); ac_sync(&stream);
+                arena_final = h64[0]; first_pass_total = h64[1]; first_pass_done = true;      // what this expand_repeats() call returned
+                if (!device_simplify || first_pass_total == 0) break;
+                if (pass > 100000) throw std::runtime_error("repeat expansion did not settle");
+                bound = 0; for (int x = 0; x < AC_BOUND_STRIPES; ++x) bound += h64[2 + AC_BOUND_STRIPES + x];
                 if (arena_final + bound >= 0xFFFFFFF0ull) throw std::runtime_error("unitig sequence arena would exceed 4 GB");
                 static const bool always_grow = getenv("AC_DEVICE_TIGHT_ARENA") != nullptr;   // test hook: take the growth path before every pass
-                if (always_grow || arena_final + bound + 64 > d_arena2.cap) {             // make room for whatever this pass may relocate
+                if (always_grow || arena_final + bound + 64 > d_arena2.cap) {             // make room for whatever the next pass may relocate
                     d_arena3.ensure(std::max<size_t>((arena_final + bound) * 2 + 64, d_arena3.cap + (always_grow ? 64 : 0)));
                     ac_copy_dd(d_arena3.p, d_arena2.p, arena_final, &stream); ac_sync(&stream);
                     std::swap(d_arena2.p, d_arena3.p); std::swap(d_arena2.cap, d_arena3.cap);
                 }
-                ac_memset(c64 + 2, 0, 8, &stream);
-                for (uint32_t l = 1; l <= n_levels; ++l)
-                    ac_launch("apply_level", &stream, ApplyLevelBody{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_level.as<uint32_t>(), l, d_spec.as<uint32_t>(),
-                                                                     d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64 + 1, c64 + 2, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>(), false}, n_cands);
-                ac_d2h(after, c64 + 1, 16, &stream); ac_sync(&stream);
-                arena_final = after[0]; first_pass_total = after[1];          // what the last expand_repeats() call returned
-                if (pass > 100000) throw std::runtime_error("repeat expansion did not settle");
+                ac_memset(c64 + 1, 0, (2 * AC_BOUND_STRIPES + 1) * 8, &stream);
             }
             if (device_simplify) {      // simplify_structure ends with renumber_unitigs (:38): stable with respect to the numbering the passes ran in
                 d_pos.ensure((size_t)U * 4); sort_c.ensure((size_t)U * 4); sort_d.ensure((size_t)U * 4);
                 ac_launch("inverse_perm", &stream, InversePermBody{ord_in, d_pos.as<uint32_t>()}, U);
                 ac_launch("number_key", &stream, NumberKeyBody{d_rec.as<UnitigRec>(), d_arena2.as<char>(), num_prefix.as<uint64_t>()}, U);
                 const NumberLess final_less{d_rec.as<UnitigRec>(), d_depth.as<uint32_t>(), d_arena2.as<char>(), num_prefix.as<uint64_t>(), d_pos.as<uint32_t>()};
-                uint32_t* fin = sort_c.as<uint32_t>(); uint32_t* fout = sort_d.as<uint32_t>();
-                ac_launch("number_leaf", &stream, SortLeafBody<NumberLess>{final_less, U, fin}, ((uint64_t)U + AC_SORT_LEAF - 1) / AC_SORT_LEAF);
-                for (uint64_t width = AC_SORT_LEAF; width < U; width *= 2) {
-                    ac_launch("number_merge", &stream, MergePassBody<NumberLess>{final_less, U, (uint32_t)width, fin, fout}, U);
-                    std::swap(fin, fout);
-                }
+                uint32_t* fin = sort_indices(&stream, final_less, U, sort_c.as<uint32_t>(), sort_d.as<uint32_t>());
                 final_order = fin;
                 static const bool device_gfa = getenv("AC_DEVICE_GFA") != nullptr;
                 if (device_gfa && U < 100000000u) {          // save_gfa's S and L lines and the path lists, rendered here

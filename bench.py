@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 METRIC = "input-assembly Mbp/sec through compress->unitig GFA"
 K = 51
 WORKLOADS = {   # BASELINE.json configs (SURVEY.md §8d generator); the default is the config the metric is quoted on
+    "cfg1": "cfg1: 3 synthetic 100 kbp assemblies",
     "cfg2": "cfg2: 8 synthetic E. coli-sized (4.64 Mbp) assemblies",
     "cfg3": "cfg3: 12 synthetic K. pneumoniae-sized assemblies (5.5 Mbp chromosome + 5 plasmids)",
     "cfg4": "cfg4: 24 synthetic 10 Mbp assemblies",
@@ -187,12 +188,8 @@ def run_gpu(args):
     K = args.k
     # N = 1: the configuration the metric is quoted on (cfg2).  N > 1: BASELINE config 5 — the first 8N assemblies of the cfg5
     # generator, 8 per rank; N = 8 is cfg5 itself.  Every workload has a committed oracle hash (tests/golden/config_goldens.json).
-    workload = args.workload or ("cfg2" if world == 1 else "cfg5")
+    workload, per_rank, n_assemblies, golden_key, WORKLOAD = workload_for(args, world)
     args.workload = workload
-    per_rank = 8 if workload == "cfg5" else synth.CONFIGS[workload][2]
-    n_assemblies = per_rank * world
-    golden_key = f"{workload}_k{K}" + (f"_n{n_assemblies}" if n_assemblies != synth.CONFIGS[workload][2] or workload == "cfg5" else "")
-    WORKLOAD = f"{WORKLOADS[workload]}, k={K}"
     assemblies = synth.make_assemblies(workload, n_assemblies=n_assemblies)
     n_bases = synth.total_bases(assemblies)
     stream = torch.cuda.current_stream()
@@ -283,7 +280,7 @@ def run_gpu(args):
         "metric": METRIC, "value": round(value, 3), "unit": "Mbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic (splitmix64 genomes, SURVEY.md §8d)",
-        "config": {"workload": WORKLOAD if n_assemblies == synth.CONFIGS[workload][2] else f"the first {n_assemblies} assemblies of {WORKLOADS[workload]}, k={K}", "k": K, "input_bases": n_bases, "sequences": len(seqs),
+        "config": {"workload": WORKLOAD, "k": K, "input_bases": n_bases, "sequences": len(seqs),
                    "exchange": None if world == 1 else "all-gather of deduplicated k-mer entries (16 B each) over NCCL, then gather of unitig occurrences to rank 0",
                    "l2": "working set per step (table %.0f MB + per-position arrays) exceeds the 126 MB L2 and is re-initialised every step" % (t.table_capacity * 16 / 1e6),
                    "gfa_bytes": len(gfa), "unitigs": int(g.counts().n_unitigs), "numa_node": numa_node},
@@ -310,53 +307,104 @@ def run_gpu(args):
         sys.exit(3)
 
 
-def oracle_sample(replicon, n_assemblies=8):
-    """A bounded sample of the cfg2 workload for the CPU arm: same generator, divergence and assembly count, shorter replicon."""
+def workload_for(args, world):
+    """-> (workload name, assemblies to generate, key of its committed oracle hash).  N = 1: the configuration the metric is quoted on
+    (cfg2).  N > 1: BASELINE config 5 — the first 8N assemblies of the cfg5 generator, 8 per rank; N = 8 is cfg5 itself."""
+    from autocycler_b200 import synth
+    workload = args.workload or ("cfg2" if world == 1 else "cfg5")
+    per_rank = 8 if workload == "cfg5" else synth.CONFIGS[workload][2]
+    n_assemblies = per_rank * world
+    whole = n_assemblies == synth.CONFIGS[workload][2] and workload != "cfg5"
+    key = f"{workload}_k{args.k}" + ("" if whole else f"_n{n_assemblies}")
+    label = f"{WORKLOADS[workload]}, k={args.k}" if n_assemblies == synth.CONFIGS[workload][2] else f"the first {n_assemblies} assemblies of {WORKLOADS[workload]}, k={args.k}"
+    return workload, per_rank, n_assemblies, key, label
+
+
+def oracle_inputs(workload, n_assemblies, k, replicon=None):
+    """Stage A through the oracle (untimed, as in the GPU arm): the synthetic assemblies of `workload` -> padded, end-repaired strands."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import tempfile
     import oracle_lib as o
     from autocycler_b200 import synth
-    assemblies = synth.make_assemblies("cfg2", n_assemblies=n_assemblies, replicon_lengths=[replicon])
+    assemblies = synth.make_assemblies(workload, n_assemblies=n_assemblies, replicon_lengths=[replicon] if replicon else None)
     with tempfile.TemporaryDirectory() as d:
         synth.write_assemblies(assemblies, d)
-        count, seqs = o.load_sequences(d, K, threads=8)       # stage A, untimed as in the GPU arm
+        count, seqs = o.load_sequences(d, k, threads=min(8, os.cpu_count() or 1))
     return o, seqs, count, synth.total_bases(assemblies)
 
 
 def cpu_baseline(sample_replicon):
-    o, seqs, count, n_bases = oracle_sample(sample_replicon)
+    """The repo arm's CPU leg: a bounded sample (same generator, divergence and assembly count as cfg2, shorter replicon)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    flags = oracle_lib.use_native()
+    o, seqs, count, n_bases = oracle_inputs("cfg2", 8, K, replicon=sample_replicon)
     t0 = time.perf_counter()
     gfa, st, _ = o.compress_seqs(seqs, count, K)
     dt = time.perf_counter() - t0
-    return {"value": round(n_bases / dt / 1e6, 4), "unit": "Mbp/s", "cores": 1, "kind": "port",
-            "sample": f"8 assemblies x {sample_replicon} bp (cfg2 generator), k={K}, {n_bases} bases in {dt:.1f} s; graph stages are single-threaded in the reference (SURVEY D5)",
+    return {"value": round(n_bases / dt / 1e6, 4), "unit": "Mbp/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(), "build": flags,
+            "sample": f"8 assemblies x {sample_replicon} bp (cfg2 generator), k={K}, {n_bases} bases in {dt:.1f} s; graph stages are single-threaded in the reference (SURVEY D5); "
+                      "the full-size number is the --impl reference arm",
             "stage_s": {"kmer_graph": round(st.t_kmer_graph, 2), "unitig_graph": round(st.t_unitig_graph, 2), "simplify": round(st.t_simplify, 2), "gfa": round(st.t_gfa, 2)}}
 
 
 def run_reference(args):
+    """The reference's CPU algorithm (oracle port, built -O3 -march=native on this machine) on the SAME workload as the B200 arm at this N,
+    at full size.  One pass over cfg2 takes about a minute, so the passes are counted against a time budget: at least one full-size
+    pass is timed, never a smaller input (unless a single pass could not finish inside the driver's limit; the line then says so)."""
+    import hashlib
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # size the sample so that (steps + warmup) passes finish within ~4 minutes at ~0.4 Mbp/s
-    budget_s = 240.0 / max(1, args.steps + args.warmup)
-    replicon = int(max(50_000, min(600_000, budget_s * 0.4e6 / 8)))
-    o, seqs, count, n_bases = oracle_sample(replicon)
-    for _ in range(args.warmup):
-        o.compress_seqs(seqs, count, K)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    flags = oracle_lib.use_native()
+    global K
+    K = args.k
+    workload, per_rank, n_assemblies, golden_key, label = workload_for(args, args.gpus)
+    budget_s = float(os.environ.get("AC_REF_BUDGET_S", "420"))          # for the timed passes together
+    one_pass_limit_s = float(os.environ.get("AC_REF_PASS_LIMIT_S", "1300"))
+    from autocycler_b200 import synth
+    full_n, note = n_assemblies, None
+    est_rate = 0.30e6                                                     # bases per second, pessimistic: only used to avoid a pass that cannot end in time
+    genome = sum(synth.CONFIGS[workload][1])
+    while n_assemblies > 8 and n_assemblies * genome / est_rate > one_pass_limit_s:
+        n_assemblies -= 8
+    if n_assemblies != full_n:
+        note = f"one pass over all {full_n} assemblies would not end inside the limit on one core: the first {n_assemblies} are timed instead"
+        golden_key = f"{workload}_k{K}_n{n_assemblies}"
+    o, seqs, count, n_bases = oracle_inputs(workload, n_assemblies, K)
+    t_start = time.perf_counter()
+    warm = 0
+    times, sha, st = [], None, None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
         gfa, st, _ = o.compress_seqs(seqs, count, K)
-    dt = time.perf_counter() - t0
-    v = round(n_bases * args.steps / dt / 1e6, 4)
-    sample = f"8 assemblies x {replicon} bp (cfg2 generator), k={K}, {n_bases} bases per step"
+        dt = time.perf_counter() - t0
+        if sha is None:
+            sha = hashlib.sha256(gfa.encode()).hexdigest()
+        # warm-up passes only while they are cheap: a pass over tens of Mbp touches gigabytes and is as cold the second time
+        if i < args.warmup and dt * (args.warmup + 1) < 0.25 * budget_s:
+            warm += 1
+        else:
+            times.append(dt)
+        if len(times) >= args.steps or (times and sum(times) + dt > budget_s):
+            break
+    total = sum(times)
+    v = round(n_bases * len(times) / total / 1e6, 4)
+    golden = golden_for(golden_key)
+    sample = f"{len(times)} full-size pass(es) over {n_assemblies} assemblies, {n_bases} bases each ({warm} warm-up); {note or 'same input as the B200 arm'}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "steps_timed": len(times), "warmup_done": warm,
+        "ms_per_step": round(total / len(times) * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic (splitmix64 genomes, SURVEY.md §8d)",
-        "config": {"workload": WORKLOAD, "k": K, "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": 1, "kind": "port", "sample": sample +
+        "config": {"workload": label if n_assemblies == full_n else f"the first {n_assemblies} assemblies of {WORKLOADS[workload]}, k={K}", "k": K, "input_bases": n_bases, "sequences": len(seqs), "sample": sample},
+        "parity": {"sha256": sha, "golden": golden, "golden_key": golden_key, "ok": bool(golden) and sha == golden},
+        "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": 1, "host_cores": os.cpu_count(), "kind": "port", "build": flags, "sample": sample +
                          "; oracle = C++ restatement of the reference's Rust path (the reference itself cannot be built here: no Rust toolchain); "
-                         "its graph stages are single-threaded by construction (SURVEY D5)"},
+                         "its graph stages are single-threaded by construction (SURVEY D5); clock = compress.rs:42-47 (k-mer graph -> GFA text), stage A untimed in both arms",
+                         "stage_s": {"kmer_graph": round(st.t_kmer_graph, 2), "unitig_graph": round(st.t_unitig_graph, 2), "simplify": round(st.t_simplify, 2), "gfa": round(st.t_gfa, 2)}},
         "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 

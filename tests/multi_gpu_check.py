@@ -1,11 +1,15 @@
-"""torchrun script (needs >= 2 GPUs): the N-rank sharded build gives the same GFA as the single-GPU build.
+"""torchrun script (needs >= 2 GPUs): the N-rank sharded build gives the oracle's GFA — byte for byte on inputs the oracle finishes in
+seconds, through the committed SHA-256 on cfg2 — and the same bytes as the one-GPU build.  Run by tests/test_multi_gpu.py, or by hand:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/multi_gpu_check.py"""
 import hashlib
+import json
 import os
 import sys
 import tempfile
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
 import torch
 import torch.distributed as dist
 
@@ -14,15 +18,32 @@ from autocycler_b200 import api, dist as acdist, synth
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+goldens = json.load(open(os.path.join(HERE, "golden", "config_goldens.json")))
+quick = os.environ.get("AC_MULTI_CHECK_QUICK") is not None
+cases = [("a", 6, [300_000, 9_000], 51), ("b", 4, [120_000], 31), ("c", 5, [80_000], 91), ("d", 3, [50_000], 51)]
+if not quick:
+    cases.append(("cfg2", 8, None, 51))
 ok = True
-for name, n_asm, lens, k in [("a", 6, [300_000, 9_000], 51), ("b", 4, [120_000], 31), ("c", 5, [80_000], 91), ("cfg2", 8, None, 51)]:
+for name, n_asm, lens, k in cases:
     assemblies = synth.make_assemblies(name, n_assemblies=n_asm, replicon_lengths=lens, seed=None if name == "cfg2" else 1234)
     with tempfile.TemporaryDirectory() as d:
         synth.write_assemblies(assemblies, d)
         kg, seqs, count = api.load_sequences(d, k, device=local)
+        expected = None
+        if rank == 0:
+            if name == "cfg2":
+                expected = goldens["cfg2_k51"]["sha256"]
+            else:
+                import oracle_lib
+                expected = hashlib.sha256(oracle_lib.compress_dir(d, k)[0].encode()).hexdigest()
     kg.upload()
-    lo, hi = acdist.shard_bounds(len(seqs), rank, world)
-    g = acdist.from_kmer_graph_distributed(kg, lo, hi, torch.device("cuda", local))
+    # contiguous blocks of FILES (assemblies shard by sorted file order); a rank may end up with none
+    first_of = {}
+    for i, sq in enumerate(seqs):
+        first_of.setdefault(sq.filename, i)
+    bounds = [first_of[f] for f in sorted(first_of, key=first_of.get)] + [len(seqs)]
+    flo, fhi = acdist.shard_bounds(len(bounds) - 1, rank, world)
+    g = acdist.from_kmer_graph_distributed(kg, bounds[flo], bounds[fhi], torch.device("cuda", local))
     if rank == 0:
         api.simplify_structure(g)
         multi = hashlib.sha256(g.gfa_bytes()).hexdigest()
@@ -30,9 +51,11 @@ for name, n_asm, lens, k in [("a", 6, [300_000, 9_000], 51), ("b", 4, [120_000],
         g1 = api.UnitigGraph.from_kmer_graph(kg)
         api.simplify_structure(g1)
         single = hashlib.sha256(g1.gfa_bytes()).hexdigest()
-        print(name, k, "world", world, "same" if multi == single else "DIFFERENT", multi[:16], flush=True)
-        ok = ok and multi == single
+        good = multi == single == expected
+        print(name, k, "world", world, "same as the oracle" if good else f"DIFFERENT multi={multi[:12]} single={single[:12]} oracle={expected[:12]}", flush=True)
+        ok = ok and good
     dist.barrier()
 if rank == 0:
     print("MULTI_GPU_CHECK", "OK" if ok else "FAIL", flush=True)
 dist.destroy_process_group()
+sys.exit(0 if ok else 1)

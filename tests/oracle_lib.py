@@ -21,16 +21,32 @@ class OracleError(RuntimeError):
 
 
 _lib = None
+_path = None
+build_flags = "g++ -O3 -march=x86-64-v2 (oracle/Makefile, portable build)"
 
 
 def build():
     subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
 
 
+def use_native():
+    """bench.py's CPU arm: build the oracle for THIS machine (-O3 -march=native, oracle/_native/) and use that library.
+    Must be called before the first oracle call of the process.  Returns the compiler flags in use."""
+    global _path, build_flags
+    assert _lib is None, "use_native() must precede the first oracle call"
+    try:
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "native"], check=True, capture_output=True, timeout=600)
+        _path = os.path.join(ORACLE_DIR, "_native", "liboracle.so")
+        build_flags = open(os.path.join(ORACLE_DIR, "_native", "flags.txt")).read().strip()
+    except Exception as e:      # no compiler on this machine: the shipped portable build is used, and the line says so
+        build_flags += f" [native build failed: {type(e).__name__}]"
+    return build_flags
+
+
 def lib():
     global _lib
     if _lib is None:
-        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        path = _path or os.path.join(ORACLE_DIR, "liboracle.so")
         if not os.path.exists(path):
             build()
         _lib = C.CDLL(path)

@@ -14,7 +14,7 @@ def run(env=None, *args):
 
 
 def test_reference_arm_line():
-    r = run(None, "--steps", "1", "--warmup", "0")
+    r = run(None, "--steps", "2", "--warmup", "1", "--workload", "cfg1")      # the default (full cfg2) takes minutes per pass on one core
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -26,7 +26,22 @@ def test_reference_arm_line():
     assert d["metric"] == json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"] or "Mbp/sec" in d["metric"]
     assert d["value"] > 0 and d["e2e"] == {"value": d["value"], "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
-    assert "workload" in d["config"] and "sample" in d["config"]
+    assert "-march=native" in d["cpu_baseline"]["build"] and d["cpu_baseline"]["host_cores"] >= 1
+    assert "workload" in d["config"] and "sample" in d["config"] and d["config"]["input_bases"] == 299982
+    assert d["steps_timed"] == 2 and d["parity"]["ok"] is True and d["parity"]["golden_key"] == "cfg1_k51"      # the timed output is the committed oracle output
+
+
+def test_workload_selection_matches_the_committed_goldens():
+    """N = 1 runs cfg2, N > 1 the first 8N assemblies of cfg5; both arms name the same golden."""
+    import argparse
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    goldens = json.load(open(os.path.join(ROOT, "tests", "golden", "config_goldens.json")))
+    for n, key in [(1, "cfg2_k51"), (2, "cfg5_k51_n16"), (4, "cfg5_k51_n32"), (8, "cfg5_k51_n64")]:
+        wl, per_rank, n_asm, golden_key, label = bench.workload_for(argparse.Namespace(workload=None, k=51), n)
+        assert golden_key == key and per_rank == 8 and n_asm == 8 * n
+        assert key in goldens, f"no committed oracle hash for {key}"
 
 
 def test_reference_arm_other_ranks_do_nothing():

@@ -304,3 +304,15 @@ def test_simplify_with_more_than_six_exclusive_inputs(emu):
     want = o.gfa_unitig_seqs(text, simplify=True)
     assert [(str(u["number"]), u["seq"]) for u in g.unitigs()] == [(w[0], w[1]) for w in want]
     assert any(u["seq"].startswith("C" + tail) or u["seq"].startswith(tail) for u in g.unitigs())      # the common end moved onto unitig 1
+
+
+def test_kmer_depth_beyond_16_bits_takes_the_side_counts(emu):
+    """A k-mer with more than 49151 occurrences (a 60 kbp homopolymer) trips the 16-bit count alarm of the 8-byte slots; the build repeats with 32-bit counts and still matches the oracle."""
+    import random
+    rnd = random.Random(7)
+    flank = lambda n: "".join(rnd.choice("ACGT") for _ in range(n))
+    files = [("a.fasta", [("c1", flank(300) + "A" * 60000 + flank(300))]), ("b.fasta", [("c2", flank(200) + "T" * 2000 + flank(200))])]
+    got = check_case(emu, files, 11)
+    assert got is not None
+    depths = sorted(u["depth"] for u in got["graph"].unitigs())
+    assert depths[-1] > 49151
