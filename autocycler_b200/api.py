@@ -34,7 +34,7 @@ class AcConfig(C.Structure):
 
 class AcCounts(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_kmers", "n_unitigs", "n_links", "total_length", "seq_bytes", "n_fwd_pos",
-                                         "n_rev_pos", "n_next", "n_sequences", "n_path_steps")]
+                                         "n_rev_pos", "n_next", "n_sequences", "n_path_steps", "length_before_simplify")]
 
 
 class AcUnitigs(C.Structure):
@@ -47,7 +47,7 @@ class AcUnitigs(C.Structure):
 
 class AcTimings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d", "pack", "insert", "adjacency", "boundaries", "runs", "unitigs", "links", "seed_sort", "emit", "d2h",
-                                        "device_total", "host_graph", "host_simplify", "host_gfa")] + \
+                                        "device_total", "host_graph", "host_simplify", "host_gfa", "sample", "device_simplify", "device_gfa")] + \
                [(n, C.c_uint64) for n in ("insert_occurrences", "table_capacity", "table_used", "kernel_launches", "h2d_bytes", "d2h_bytes")]
 
     def as_dict(self):
@@ -55,7 +55,7 @@ class AcTimings(C.Structure):
 
 
 EXPORTS = ["ac_last_error", "ac_version", "ac_create", "ac_destroy", "ac_add_sequence", "ac_clear_sequences", "ac_upload",
-           "ac_build", "ac_simplify", "ac_merge_linear_paths", "ac_renumber_unitigs", "ac_load_gfa", "ac_bind_host_to_device", "ac_decompress_gfa", "ac_pairwise_distances", "ac_distance_matrix_text", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
+           "ac_build", "ac_compress", "ac_simplify", "ac_merge_linear_paths", "ac_renumber_unitigs", "ac_load_gfa", "ac_bind_host_to_device", "ac_decompress_gfa", "ac_pairwise_distances", "ac_distance_matrix_text", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
            "ac_timings_get", "ac_compress_dir", "ac_load_sequences", "ac_sequence_get",
            "ac_build_local", "ac_entries_count", "ac_entries_export", "ac_entries_merge", "ac_runs_local", "ac_runs_export",
            "ac_runs_import", "ac_build_finish", "ac_gfa_data"]
@@ -80,7 +80,7 @@ def load_library(path=None):
     lib.ac_destroy.restype = None
     lib.ac_add_sequence.argtypes = [C.c_void_p, C.c_uint16, C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p]
     lib.ac_clear_sequences.argtypes = [C.c_void_p]
-    for name in ("ac_upload", "ac_build", "ac_simplify", "ac_renumber_unitigs"):
+    for name in ("ac_upload", "ac_build", "ac_compress", "ac_simplify", "ac_renumber_unitigs"):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.ac_merge_linear_paths.argtypes = [C.c_void_p, C.c_int]
     lib.ac_load_gfa.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
@@ -188,6 +188,14 @@ class UnitigGraph:
     def from_kmer_graph(kmer_graph):
         g = UnitigGraph(kmer_graph)
         g._h.check(g._h.lib.ac_build(g._h.ptr))
+        return g
+
+    @staticmethod
+    def compress(kmer_graph):
+        """compress.rs:42-47 as one device pipeline (ac_compress): the simplified, renumbered graph; its GFA text is ready
+        (gfa_view / gfa_bytes / save_gfa), the graph arrays are fetched from HBM when first asked for."""
+        g = UnitigGraph(kmer_graph)
+        g._h.check(g._h.lib.ac_compress(g._h.ptr))
         return g
 
     @staticmethod

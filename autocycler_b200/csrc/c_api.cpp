@@ -55,8 +55,10 @@ struct ac_handle {
     HostGraph graph;
     std::string gfa;
     const char* gfa_ptr = nullptr; uint64_t gfa_len = 0;     // the finished file: h->gfa, or the pinned buffer the device wrote the S and L lines into
-    bool device_text_ok = false;                             // the device-written lines describe the graph as it is now
+    bool device_text_ok = false;                             // the device-written text describes the graph as it is now
     bool uploaded = false, built = false, gfa_ready = false;
+    bool fused = false;                                      // built by ac_compress: simplified on the device; the host graph is adopted on first use
+    bool graph_ready = false;                                // h->graph describes the current graph
     ac_timings t{};
     uint64_t links_now = 0;
 };
@@ -115,7 +117,7 @@ void ac_destroy(ac_handle* h) { delete h; }
 int ac_clear_sequences(ac_handle* h) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     h->seqs.clear(); h->infos.clear(); h->ascii.clear(); h->loaded = LoadedInput();
-    h->uploaded = h->built = h->gfa_ready = false;
+    h->uploaded = h->built = h->gfa_ready = h->fused = h->graph_ready = false;
     return ok(h);
 }
 
@@ -149,14 +151,19 @@ int ac_upload(ac_handle* h) {
     AC_GUARD_BEGIN
     if (h->seqs.empty()) return set_error(h, AC_EINPUT, "no sequences found in input assemblies");
     if (h->infos.size() != h->seqs.size()) return set_error(h, AC_EINVAL, "this handle holds a loaded graph: add sequences (after ac_clear_sequences) before ac_upload");
-    {   // what save_gfa prints around every path's unitig list (unitig_graph.rs:352-360): room for it behind device-written S / L lines
-        auto digits = [](uint64_t v) { uint64_t d = 1; while (v >= 10) { v /= 10; ++d; } return d; };
-        uint64_t tail = 0;
-        for (const HostSeq& s : h->seqs) tail += 2 + digits(s.id) + 1 + 8 + digits(s.length) + 6 + s.filename.size() + 6 + s.contig_header.size() + 1 + (s.cluster ? 6 + digits(s.cluster) : 0);
-        h->pipe->set_gfa_tail_bytes(tail);
+    {   // what save_gfa prints around every path's unitig list (unitig_graph.rs:352-360), for the device writer of the P lines
+        std::string blob; std::vector<uint32_t> pre, suf;
+        for (const HostSeq& q : h->seqs) {
+            const std::string a = "P\t" + std::to_string(q.id) + "\t";
+            std::string b = "\t*\tLN:i:" + std::to_string(q.length) + "\tFN:Z:" + q.filename + "\tHD:Z:" + q.contig_header;
+            if (q.cluster > 0) b += "\tCL:i:" + std::to_string(q.cluster);
+            b += "\n";
+            blob += a; blob += b; pre.push_back((uint32_t)a.size()); suf.push_back((uint32_t)b.size());
+        }
+        h->pipe->set_path_line_texts(blob.data(), pre.data(), suf.data(), (uint32_t)h->seqs.size());
     }
     h->pipe->upload(h->ascii.p, h->ascii.size, h->infos.data(), (uint32_t)h->infos.size(), h->cfg.k);
-    h->uploaded = true; h->built = h->gfa_ready = false;
+    h->uploaded = true; h->built = h->gfa_ready = h->fused = h->graph_ready = false;
     return ok(h);
     AC_GUARD_END(h)
 }
@@ -206,7 +213,19 @@ struct CallbackScope {      // DevicePipeline::before_results holds a reference 
 };
 }  // namespace
 
-static void adopt_result(ac_handle* h) {   // host graph over the device result + bookkeeping shared by ac_build / ac_build_finish
+static void record_timings(ac_handle* h) {
+    const PipelineTimings& pt = h->res.t;
+    ac_timings& t = h->t;
+    t.h2d = pt.h2d; t.pack = pt.pack; t.insert = pt.insert; t.adjacency = pt.adjacency; t.boundaries = pt.boundaries; t.runs = pt.runs;
+    t.unitigs = pt.unitigs; t.links = pt.links; t.seed_sort = pt.seed_sort; t.emit = pt.emit; t.d2h = pt.d2h; t.device_total = pt.total;
+    t.sample = pt.sample; t.device_simplify = pt.simplify; t.device_gfa = pt.gfa;
+    uint64_t windows = 0; for (auto& s : h->seqs) windows += s.length;
+    t.insert_occurrences = windows; t.table_capacity = h->res.capacity; t.table_used = h->res.n_slots_used;
+    t.kernel_launches = h->pipe->kernel_launches();
+    t.h2d_bytes = h->res.h2d_bytes; t.d2h_bytes = h->res.d2h_bytes;
+}
+
+static void adopt_result(ac_handle* h) {   // host graph over the device result + bookkeeping shared by ac_build / ac_build_finish / the first use after ac_compress
     const double t0 = now_ms();
     h->graph.build(h->res, h->seqs, h->cfg.k, h->cfg.keep_positions != 0);
     if (!h->graph.device_sort) { DevicePipeline* pipe = h->pipe.get(); h->graph.device_sort = [pipe](const NumberKey* k, uint32_t n, uint32_t* out) { pipe->sort_number_keys(k, n, out); }; }
@@ -218,16 +237,18 @@ static void adopt_result(ac_handle* h) {   // host graph over the device result 
     h->pipe->complete(h->res);
     const double t1 = now_ms();
     if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[host] adopt: graph %.2f, check_links %.2f, work list %.2f, wait for sequences %.2f ms\n", ta - t0, tb - ta, tc - tb, t1 - tc);
-    const PipelineTimings& pt = h->res.t;
-    ac_timings& t = h->t;
-    t.h2d = pt.h2d; t.pack = pt.pack; t.insert = pt.insert; t.adjacency = pt.adjacency; t.boundaries = pt.boundaries; t.runs = pt.runs;
-    t.unitigs = pt.unitigs; t.links = pt.links; t.seed_sort = pt.seed_sort; t.emit = pt.emit; t.d2h = pt.d2h; t.device_total = pt.total;
-    t.host_graph = (float)(t1 - t0); t.host_simplify = 0; t.host_gfa = 0;
-    uint64_t windows = 0; for (auto& s : h->seqs) windows += s.length;
-    t.insert_occurrences = windows; t.table_capacity = h->res.capacity; t.table_used = h->res.n_slots_used;
-    t.kernel_launches = h->pipe->kernel_launches();
-    t.h2d_bytes = h->res.h2d_bytes; t.d2h_bytes = h->res.d2h_bytes;
-    h->built = true; h->gfa_ready = false; h->device_text_ok = false;
+    if (!h->fused) { record_timings(h); h->t.host_graph = (float)(t1 - t0); h->t.host_simplify = 0; h->t.host_gfa = 0; }
+    h->graph_ready = true;
+}
+
+// After ac_compress the graph arrays are still in HBM: bring them over and adopt them the first time a call needs the host graph.
+static void ensure_graph(const ac_handle* ch) {
+    ac_handle* h = const_cast<ac_handle*>(ch);
+    if (!h->built || h->graph_ready) return;
+    if (!h->fused) throw std::runtime_error("no graph on this handle");
+    h->pipe->fetch_graph(h->res, h->cfg.keep_positions != 0);
+    adopt_result(h);
+    h->graph.simplify_structure();           // everything was done on the device: this adopts its numbering (nothing is recomputed)
 }
 
 int ac_build(ac_handle* h) {
@@ -240,7 +261,36 @@ int ac_build(ac_handle* h) {
         CallbackScope scope(h->pipe.get(), [&flusher] { flusher.join(); });      // cleared again on every way out, exceptions included
         h->pipe->build(h->res, h->cfg.keep_positions != 0);
     }
+    h->fused = false; h->graph_ready = false;
     adopt_result(h);
+    h->built = true; h->gfa_ready = false; h->device_text_ok = false;
+    return ok(h);
+    AC_GUARD_END(h)
+}
+
+// compress.rs:42-47 in one call: build_kmer_graph, build_unitig_graph, simplify_unitig_graph and the text save_gfa writes, all on the
+// device; only the text (and the counts compress prints) come back.  The graph itself is fetched when a later call asks for it.
+int ac_compress(ac_handle* h) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    AC_GUARD_BEGIN
+    if (!h->uploaded) return set_error(h, AC_EINVAL, "ac_upload must precede ac_compress");
+    static const bool host_tail = getenv("AC_HOST_SIMPLIFY") != nullptr;       // comparison only: device graph, then expand_repeats and the text on the host
+    if (host_tail) {
+        int rc = ac_build(h); if (rc != AC_OK) return rc;
+        if ((rc = ac_simplify(h)) != AC_OK) return rc;
+        uint64_t n = 0; return ac_gfa_size(h, &n);
+    }
+    ResultFlusher flusher;
+    if (h->built && h->graph_ready) flusher.start(h->res);                     // the host only ever writes to the graph arrays, and only once they were fetched
+    {
+        CallbackScope scope(h->pipe.get(), [&flusher] { flusher.join(); });
+        h->pipe->build(h->res, h->cfg.keep_positions != 0, true);
+    }
+    h->pipe->complete(h->res);
+    h->fused = true; h->graph_ready = false; h->built = true;
+    h->gfa_ptr = h->res.gfa_text; h->gfa_len = h->res.gfa_bytes; h->gfa_ready = true; h->device_text_ok = true;
+    record_timings(h);
+    h->t.host_graph = h->t.host_simplify = h->t.host_gfa = 0;
     return ok(h);
     AC_GUARD_END(h)
 }
@@ -307,7 +357,9 @@ int ac_build_finish(ac_handle* h) {
         CallbackScope scope(h->pipe.get(), [&flusher] { flusher.join(); });
         h->pipe->finish(h->res, h->cfg.keep_positions != 0);
     }
+    h->fused = false; h->graph_ready = false;
     adopt_result(h);
+    h->built = true; h->gfa_ready = false; h->device_text_ok = false;
     return ok(h);
     AC_GUARD_END(h)
 }
@@ -316,11 +368,12 @@ int ac_simplify(ac_handle* h) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     AC_GUARD_BEGIN
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_simplify");
+    if (h->fused && !h->graph_ready) return ok(h);        // ac_compress has simplified the graph already
     const double t0 = now_ms();
     h->graph.simplify_structure();
     h->t.host_simplify = (float)(now_ms() - t0);
     h->gfa_ready = false;
-    h->device_text_ok = h->res.gfa_text != nullptr && h->graph.last_simplify_on_device;
+    h->device_text_ok = !h->fused && h->res.gfa_text != nullptr && h->graph.last_simplify_on_device;
     return ok(h);
     AC_GUARD_END(h)
 }
@@ -329,6 +382,7 @@ int ac_merge_linear_paths(ac_handle* h, int use_paths) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     AC_GUARD_BEGIN
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_merge_linear_paths");
+    ensure_graph(h);
     h->graph.merge_linear_paths(use_paths != 0);
     h->gfa_ready = false; h->device_text_ok = false;
     return ok(h);
@@ -379,12 +433,12 @@ int ac_bind_host_to_device(int32_t device) {
 int ac_load_gfa(ac_handle* h, const char* gfa_text, uint64_t length) {
     if (!h || !gfa_text) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
-    h->built = false; h->gfa_ready = false; h->uploaded = false; h->device_text_ok = false;
+    h->built = false; h->gfa_ready = false; h->uploaded = false; h->device_text_ok = false; h->fused = false; h->graph_ready = false;
     h->seqs.clear(); h->infos.clear(); h->ascii.clear(); h->loaded = LoadedInput(); h->res = PipelineResult(); h->t = ac_timings{};   // a loaded graph has no sequence bytes: ac_upload / ac_build need ac_add_sequence again
     h->graph.device_sort = nullptr;
     h->graph.load_gfa(gfa_text, (size_t)length, h->seqs);
     h->cfg.k = h->graph.k;
-    h->built = true;
+    h->built = true; h->graph_ready = true;
     return ok(h);
     AC_GUARD_END(h)
 }
@@ -396,6 +450,7 @@ int ac_pairwise_distances(ac_handle* h, double* out, uint64_t cap) {
     if (!h || !out) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     if (!h->built) return set_error(h, AC_EINVAL, "a graph must be built or loaded before ac_pairwise_distances");
+    ensure_graph(h);
     const HostGraph& g = h->graph;
     const uint64_t S = h->seqs.size();
     if (cap < S * S) return set_error(h, AC_ERANGE, "buffer too small");
@@ -462,6 +517,7 @@ int ac_renumber_unitigs(ac_handle* h) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     AC_GUARD_BEGIN
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_renumber_unitigs");
+    ensure_graph(h);
     h->graph.renumber();
     h->gfa_ready = false; h->device_text_ok = false;
     return ok(h);
@@ -473,7 +529,16 @@ int ac_counts_get(const ac_handle* h, ac_counts* out) {
     AC_GUARD_BEGIN
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_counts_get");
     memset(out, 0, sizeof *out);
+    if (h->fused && !h->graph_ready) {       // straight from the device: what compress prints (compress.rs:152, unitig_graph.rs:509-516)
+        const PipelineResult& r = h->res;
+        out->n_kmers = 2 * r.n_slots_used; out->n_unitigs = r.n_unitigs; out->n_links = r.links_single;
+        out->total_length = r.length_after; out->seq_bytes = r.length_after; out->length_before_simplify = r.length_before;
+        out->n_next = r.n_links; out->n_sequences = h->seqs.size(); out->n_path_steps = r.n_runs;
+        if (h->cfg.keep_positions) { out->n_fwd_pos = r.n_runs; out->n_rev_pos = r.n_runs; }
+        return ok(h);
+    }
     const HostGraph& g = h->graph;
+    out->length_before_simplify = h->res.length_before;
     out->n_kmers = 2 * h->res.n_slots_used;
     out->n_unitigs = g.U;
     out->n_links = g.link_count_single();
@@ -491,6 +556,7 @@ int ac_unitigs_copy(const ac_handle* h, ac_unitigs* o) {
     if (!h || !o) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_unitigs_copy");
+    ensure_graph(h);
     const HostGraph& g = h->graph;
     const bool have_pos = !g.fpos_off.empty();
     if ((o->fpos_off || o->fpos || o->rpos_off || o->rpos) && !have_pos) return set_error(h, AC_EINVAL, "positions need ac_config.keep_positions");
@@ -528,6 +594,7 @@ int ac_unitigs_copy(const ac_handle* h, ac_unitigs* o) {
 int ac_path_copy(const ac_handle* h, uint64_t seq_index, int32_t* out, uint64_t cap, uint64_t* n) {
     if (!h || !n) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
+    if (h->built) ensure_graph(h);
     const HostGraph& g = h->graph;
     if (!h->built || seq_index >= g.n_seqs) return set_error(h, AC_EINVAL, "no such sequence");
     const uint64_t a = g.path_off[seq_index], b = g.path_off[seq_index + 1];
@@ -545,24 +612,10 @@ int ac_gfa_size(ac_handle* h, uint64_t* n_bytes) {
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_gfa_size");
     if (!h->gfa_ready) {
         const double t0 = now_ms();
-        if (h->device_text_ok) {      // H, S and L lines came from the device; wrap every path's unitig list into its P line behind them (unitig_graph.rs:352-360)
-            const PipelineResult& r = h->res;
-            char* p = r.gfa_text + r.gfa_lines_bytes;
-            for (size_t i = 0; i < h->seqs.size(); ++i) {
-                const HostSeq& s = h->seqs[i];
-                p += snprintf(p, 32, "P\t%u\t", (unsigned)s.id);
-                const uint64_t a = r.path_text_off[i], b = r.path_text_off[i + 1];
-                memcpy(p, r.path_text + a, b - a); p += b - a;
-                p += snprintf(p, 64, "\t*\tLN:i:%llu\tFN:Z:", (unsigned long long)s.length);
-                memcpy(p, s.filename.data(), s.filename.size()); p += s.filename.size();
-                memcpy(p, "\tHD:Z:", 6); p += 6;
-                memcpy(p, s.contig_header.data(), s.contig_header.size()); p += s.contig_header.size();
-                if (s.cluster > 0) p += snprintf(p, 32, "\tCL:i:%u", (unsigned)s.cluster);
-                *p++ = '\n';
-            }
-            if ((uint64_t)(p - r.gfa_text) > r.gfa_cap) throw std::runtime_error("GFA text buffer overrun");
-            h->gfa_ptr = r.gfa_text; h->gfa_len = (uint64_t)(p - r.gfa_text);
+        if (h->device_text_ok) {      // the whole file was rendered on the device (AC_DEVICE_SIMPLIFY + AC_DEVICE_GFA in a plain build)
+            h->gfa_ptr = h->res.gfa_text; h->gfa_len = h->res.gfa_bytes;
         } else {
+            ensure_graph(h);
             h->graph.gfa_text(h->seqs, h->gfa);
             h->gfa_ptr = h->gfa.data(); h->gfa_len = h->gfa.size();
         }
@@ -646,6 +699,7 @@ int ac_sequence_reconstruct(const ac_handle* h, uint64_t index, char* out, uint6
     AC_GUARD_BEGIN
     if (!h->built) return set_error(h, AC_EINVAL, "ac_build must precede ac_sequence_reconstruct");
     if (index >= h->seqs.size()) return set_error(h, AC_EINVAL, "no such sequence");
+    ensure_graph(h);
     const HostGraph& g = h->graph;
     uint64_t total = 0;
     for (uint64_t x = g.path_off[index]; x < g.path_off[index + 1]; ++x) total += g.rec[us_index(g.path[x])].len;
@@ -690,14 +744,13 @@ int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint
     const double t1 = now_ms();
     if (verbose) fprintf(stderr, "%zu sequence%s loaded from %llu assembl%s\n\n", h->seqs.size(), h->seqs.size() == 1 ? "" : "s",
                          (unsigned long long)assemblies, assemblies == 1 ? "y" : "ies");
-    if ((rc = ac_upload(h)) != AC_OK || (rc = ac_build(h)) != AC_OK) { g_error = h->err; return rc; }
+    if ((rc = ac_upload(h)) != AC_OK || (rc = ac_compress(h)) != AC_OK) { g_error = h->err; return rc; }
     ac_counts c{};
     ac_counts_get(h, &c);
+    // simplify_structure moves bases between unitigs: the counts stay, the total length shrinks (print_basic_graph_info, unitig_graph.rs:509-516)
     if (verbose) fprintf(stderr, "Graph contains %llu k-mers\n\n%llu unitig%s, %llu link%s\ntotal length: %llu bp\n\n", (unsigned long long)c.n_kmers,
                          (unsigned long long)c.n_unitigs, c.n_unitigs == 1 ? "" : "s", (unsigned long long)c.n_links, c.n_links == 1 ? "" : "s",
-                         (unsigned long long)c.total_length);
-    if ((rc = ac_simplify(h)) != AC_OK) { g_error = h->err; return rc; }
-    ac_counts_get(h, &c);
+                         (unsigned long long)c.length_before_simplify);
     if (verbose) fprintf(stderr, "%llu unitig%s, %llu link%s\ntotal length: %llu bp\n\n", (unsigned long long)c.n_unitigs, c.n_unitigs == 1 ? "" : "s",
                          (unsigned long long)c.n_links, c.n_links == 1 ? "" : "s", (unsigned long long)c.total_length);
     uint64_t n = 0;
@@ -714,8 +767,8 @@ int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint
         const ac_timings& t = h->t;
         fprintf(stderr, "Compressed unitig graph: %s\nInput assembly stats:    %s\n", out_gfa.c_str(), out_yaml.c_str());
         fprintf(stderr, "load+repair %.1f ms | h2d %.2f pack %.2f insert %.2f adjacency %.2f boundaries %.2f runs %.2f unitigs %.2f links %.2f d2h %.2f ms"
-                        " | host graph %.1f simplify %.1f gfa %.1f ms | total %.1f ms\n\n",
-                t1 - t0, t.h2d, t.pack, t.insert, t.adjacency, t.boundaries, t.runs, t.unitigs, t.links, t.d2h, t.host_graph, t.host_simplify, t.host_gfa, now_ms() - t0);
+                        " simplify %.2f gfa %.2f | host graph %.1f simplify %.1f gfa %.1f ms | total %.1f ms\n\n",
+                t1 - t0, t.h2d, t.pack, t.insert, t.adjacency, t.boundaries, t.runs, t.unitigs, t.links, t.d2h, t.device_simplify, t.device_gfa, t.host_graph, t.host_simplify, t.host_gfa, now_ms() - t0);
     }
     return ok(h);
     AC_GUARD_END(nullptr)

@@ -187,29 +187,34 @@ AC_HD uint32_t find_seq(const SeqInfo* __restrict__ seqs, uint32_t n, uint64_t g
     return lo;
 }
 
-// ---- table slot: ONE 64-bit word [ gpos:32 | dotted:1 | fingerprint:5 | count:16 | flags:10 ] -------------------------
+// ---- table slot: ONE 64-bit word [ gpos:GB | dotted:1 | fingerprint:37-GB | count:16 | flags:10 ] --------------------------
 // gpos   a pointer to one occurrence of the k-mer, like Kmer.pointer (kmer_graph.rs:26-33): keys never live in the table, equality is
-//        decided by fetching that occurrence from the packed sequence store (L2 resident)
+//        decided by fetching that occurrence from the packed sequence store (L2 resident).  GB = the bits the input's coordinates
+//        need (26 for BASELINE config 2, at most 32); what it leaves goes to the fingerprint (11 bits for config 2, 5 at 4 Gbp), so
+//        that almost no probe has to fetch an occurrence only to find another k-mer behind it.
 // count  Kmer::depth() (kmer_graph.rs:52-55), occurrences on both strands.  16 bits: an adder that finds 0xC000 or more raises the
-//        pipeline's overflow flag and the build is repeated with the counts in a side array (`count_big`, 32 bits per slot)
+//        pipeline's count alarm and the build is repeated with the counts in a side array (`count_big`, 32 bits per slot)
 // flags  bit0 first(canonical) bit1 first(rc(canonical)) (kmer_graph.rs:57-60); bits 2..5: base b follows this k-mer somewhere in the
 //        input, bits 6..9: base b precedes it (canonical orientation; a lower bound on the node-centric degrees)
-// Eight bytes per slot (four slots per 32-byte sector): the table of BASELINE config 2 is 115 MB and stays in the 126 MB L2.
+// Eight bytes per slot (four slots per 32-byte sector): the table of BASELINE config 2 is about 100 MB and stays in the 126 MB L2.
 typedef uint64_t Slot;
-#define AC_EMPTY_SLOT (~0ull)                 // gpos 0xFFFFFFFF is never a window start: inputs are limited to 2^32 - 2 padded bytes
+#define AC_EMPTY_SLOT (~0ull)                 // gpos all ones is never a window start: GB is chosen so that total <= 2^GB - 1
 #define AC_SLOT_COUNT_SHIFT 10
 #define AC_SLOT_COUNT_ONE (1ull << AC_SLOT_COUNT_SHIFT)
 #define AC_SLOT_COUNT_ALARM 0xC000u
 #define AC_SLOT_FLAG_MASK 0x3FFull
-AC_HD uint64_t slot_gpos(Slot s) { return s >> 32; }
-AC_HD bool slot_dotted(Slot s) { return (s >> 31) & 1; }
-AC_HD uint32_t slot_tag(Slot s) { return (uint32_t)(s >> 26) & 63u; }                 // dotted bit + fingerprint
+#define AC_SLOT_TAG_SHIFT 26
+AC_HD uint32_t slot_gpos_bits(uint64_t total) { uint32_t gb = 8; while (gb < 32 && (total >> gb) != 0) ++gb; return gb; }
+AC_HD uint64_t slot_gpos(Slot s, uint32_t gb) { return s >> (64 - gb); }
+AC_HD uint32_t slot_tag(Slot s, uint32_t gb) { return (uint32_t)(s >> AC_SLOT_TAG_SHIFT) & ((1u << (38 - gb)) - 1u); }      // dotted bit + fingerprint
+AC_HD bool slot_dotted(Slot s, uint32_t gb) { return (s >> (63 - gb)) & 1; }
 AC_HD uint32_t slot_count(Slot s) { return (uint32_t)(s >> AC_SLOT_COUNT_SHIFT) & 0xFFFFu; }
 AC_HD uint32_t slot_flags(Slot s) { return (uint32_t)s & 0x3FFu; }
-AC_HD uint32_t make_tag(bool dotted, uint64_t hash) { return ((uint32_t)dotted << 5) | ((uint32_t)hash & 31u); }
-AC_HD Slot make_slot(uint64_t gpos, uint32_t tag, uint32_t count, uint32_t flags) {
-    return (gpos << 32) | ((uint64_t)tag << 26) | ((uint64_t)count << AC_SLOT_COUNT_SHIFT) | flags;
+AC_HD uint32_t make_tag(bool dotted, uint64_t hash, uint32_t gb) { return ((uint32_t)dotted << (37 - gb)) | ((uint32_t)hash & ((1u << (37 - gb)) - 1u)); }
+AC_HD Slot make_slot(uint64_t gpos, uint32_t tag, uint32_t count, uint32_t flags, uint32_t gb) {
+    return (gpos << (64 - gb)) | ((uint64_t)tag << AC_SLOT_TAG_SHIFT) | ((uint64_t)count << AC_SLOT_COUNT_SHIFT) | flags;
 }
+AC_HD Slot slot_with_gpos(Slot s, uint64_t gpos, uint32_t gb) { return (s & ((1ull << (64 - gb)) - 1ull)) | (gpos << (64 - gb)); }
 #define AC_AUX_FIRST_CANON 1u
 #define AC_AUX_FIRST_RC 2u
 #define AC_AUX_OBS_OUT_SHIFT 2

@@ -36,6 +36,7 @@ struct TableView {
     const SeqInfo* seqs;
     uint32_t n_seqs;
     uint32_t* count_big;        // null, or (after a 16-bit count ran out) the depth of every slot in 32 bits; the slots' own count fields then stay 0
+    uint32_t gb;                // bits of a slot's occurrence pointer (slot_gpos_bits(total)); the fingerprint gets the rest
 };
 // Linear probing starts at the first slot of a 32-byte group of four (cap is a multiple of 4): one sector holds the whole first probe.
 AC_D uint64_t table_home(const TableView& t, uint64_t h) { return ac_umul64hi(h, t.cap >> 2) << 2; }
@@ -54,13 +55,13 @@ template <int W> AC_D Key<W> window_key(const TableView& t, uint64_t g, bool dot
 template <int W> AC_D uint32_t table_find(const TableView& t, const Key<W>& a, const Key<W>& arc, const KParams& p) {
     const Key<W>& canon = key_is_canonical(a, p) ? a : arc;
     const uint64_t h = key_hash(canon);
-    const uint32_t tag = make_tag(a.d != 0, h);
+    const uint32_t tag = make_tag(a.d != 0, h, t.gb);
     uint64_t slot = table_home(t, h);
     for (;;) {
         const Slot e = t.slots[slot];
         if (e == AC_EMPTY_SLOT) return AC_NONE32;
-        if (slot_tag(e) == tag) {
-            Key<W> rep = window_key<W>(t, slot_gpos(e), a.d != 0, p);
+        if (slot_tag(e, t.gb) == tag) {
+            Key<W> rep = window_key<W>(t, slot_gpos(e, t.gb), a.d != 0, p);
             if (key_eq(rep, a) || key_eq(rep, arc)) return (uint32_t)slot;
         }
         if (++slot == t.cap) slot = 0;
@@ -86,7 +87,7 @@ AC_D void slot_add_occurrence(const TableView& t, uint64_t slot, Slot seen, uint
     for (;;) {
         Slot nw = old | flags;
         if (!t.count_big) { nw += (uint64_t)add << AC_SLOT_COUNT_SHIFT; if (slot_count(old) + add >= AC_SLOT_COUNT_ALARM) counters[3] = 1; }
-        if (g < slot_gpos(old)) nw = (nw & 0xFFFFFFFFull) | (g << 32);
+        if (g < slot_gpos(old, t.gb)) nw = slot_with_gpos(nw, g, t.gb);
         const Slot was = ac_atomic_cas(&t.slots[slot], old, nw);
         if (was == old) return;
         old = was;
@@ -132,9 +133,11 @@ template <int W, class F> AC_D void for_each_predecessor(const Key<W>& a, const 
 // ------------------------------------------------------------------------------------------------
 // kernel bodies
 // ------------------------------------------------------------------------------------------------
-// ASCII -> 2-bit packed, 32 bases per thread ('.' -> 0; the dot runs are described by SeqInfo).
+// ASCII -> 2-bit packed, 32 bases per thread ('.' -> 0; the dot runs are described by SeqInfo).  The same thread decides whether the 32
+// windows that START in its word form an interior block: all of them, the window before and the window after are windows of one
+// sequence, free of dots, none first or last (one byte per block; the insert kernel reads it instead of searching the sequence table).
 struct PackBody {
-    const uint8_t* ascii; uint64_t total; uint64_t* packed;
+    const uint8_t* ascii; uint64_t total; uint64_t* packed; const SeqInfo* seqs; uint32_t n_seqs; uint8_t* interior;
     AC_D void operator()(uint64_t i) const {
         uint64_t word = 0;
         const uint64_t base = i * 32;
@@ -144,6 +147,11 @@ struct PackBody {
             word |= code << (62 - 2 * j);
         }
         packed[i] = word;
+        if (interior) {
+            const SeqInfo s = seqs[find_seq(seqs, n_seqs, base)];
+            const uint64_t fs0 = base - s.start;
+            interior[i] = fs0 >= (uint64_t)s.lead + 1 && fs0 + 33 + s.trail <= s.len ? 1 : 0;
+        }
     }
 };
 
@@ -158,15 +166,15 @@ struct PackBody {
 // together again — the comparison with the occurrence that slot points at.
 template <int W> struct InsertBody {
     TableView t; KParams p;
+    const uint8_t* interior;            // [total / 32] PackBody's flag per block of 32 coordinates
     uint32_t g_first;                   // coordinate of unit 0, a multiple of 32 (inputs are limited to 2^32 - 2 padded bytes: coordinates fit 32 bits)
     uint32_t g_begin, g_end;            // coordinates of the sequences this rank owns
     bool track_min;                     // multi-GPU: the slot must end up pointing at the SMALLEST occurrence
     uint32_t* pos_slot;                 // [total] slot of the window starting at each global coordinate (null in the sizing pass)
     unsigned long long* counters;       // [0] slots claimed (sizing pass only), [1] dotted k-mers claimed, [2] probe-limit flag, [3] count alarm
     bool sizing;                        // the sizing pass: the caller has picked the windows (SampleBody), only distinct k-mers are counted
-    // everything about one window that the probe needs
-    struct Unit { Key<W> fwd, rc; uint64_t h; uint32_t flags; bool valid, dotted; };
-    AC_D Unit interior_unit(uint32_t g) const {          // a window of an interior block: keys and neighbour bases from the block's W+2 words
+    // a window of an interior block: keys and neighbour bases from the block's W+2 words
+    AC_D void interior_unit(uint32_t g, Key<W>& fwd, Key<W>& rc, uint64_t& h, uint32_t& flags) const {
         const uint32_t l = g & 31u, i0 = g >> 5;
         uint64_t x[W + 1];
 #pragma unroll
@@ -176,13 +184,12 @@ template <int W> struct InsertBody {
         uint64_t y[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) y[j] = (x[j] << sh) | ((x[j + 1] >> 1) >> (63 - sh));
-        Unit u;
         const uint32_t al = 64 - p.top_bits;
 #pragma unroll
-        for (int j = W - 1; j >= 0; --j) { uint64_t v = y[j] >> al; if (al && j > 0) v |= y[j - 1] << (64 - al); u.fwd.w[j] = v; }
-        u.fwd.d = 0;
-        u.rc = key_rc(u.fwd, p);
-        const bool canon_fwd = key_is_canonical(u.fwd, p);
+        for (int j = W - 1; j >= 0; --j) { uint64_t v = y[j] >> al; if (al && j > 0) v |= y[j - 1] << (64 - al); fwd.w[j] = v; }
+        fwd.d = 0;
+        rc = key_rc(fwd, p);
+        const bool canon_fwd = key_is_canonical(fwd, p);
         const uint32_t at = l + p.k;                       // the base after the window, counted from the block start: in word at >> 5 <= W
         uint64_t xn = x[W];
 #pragma unroll
@@ -190,61 +197,44 @@ template <int W> struct InsertBody {
         const uint32_t nb = (uint32_t)(xn >> (62 - 2 * (at & 31u))) & 3u;
         const uint32_t pb = l ? (uint32_t)(x[0] >> (64 - sh)) & 3u : (uint32_t)xp & 3u;
         const uint32_t out_b = canon_fwd ? nb : 3u - pb, in_b = canon_fwd ? pb : 3u - nb;
-        u.flags = (1u << (AC_AUX_OBS_OUT_SHIFT + out_b)) | (1u << (AC_AUX_OBS_IN_SHIFT + in_b));
-        u.h = key_hash(canon_fwd ? u.fwd : u.rc);
-        u.valid = true; u.dotted = false;
-        return u;
+        flags = (1u << (AC_AUX_OBS_OUT_SHIFT + out_b)) | (1u << (AC_AUX_OBS_IN_SHIFT + in_b));
+        h = key_hash(canon_fwd ? fwd : rc);
     }
-    AC_D Unit edge_unit(uint32_t g, uint32_t si) const {   // a block at the end of a sequence, between two sequences or at the edge of the shard
-        Unit u; u.fwd = Key<W>(); u.rc = Key<W>(); u.h = 0; u.flags = 0; u.dotted = false;
-        while (si + 1 < t.n_seqs && t.seqs[si + 1].start <= g) ++si;
-        const SeqInfo s = t.seqs[si];
+    // a block at the end of a sequence, between two sequences or at the edge of the shard; false: no window starts at g
+    AC_D bool edge_unit(uint32_t g, Key<W>& fwd, Key<W>& rc, uint64_t& h, uint32_t& flags) const {
+        const SeqInfo s = t.seqs[find_seq(t.seqs, t.n_seqs, g)];
         const uint64_t fs = g - s.start;
-        u.valid = g >= g_begin && g < g_end && fs < s.len;         // else: outside the shard, or one of the k-1 padded bytes that start no window
-        if (!u.valid) return u;
-        u.fwd = fetch_codes<W>(t.packed, g, p);
-        u.fwd.d = window_dots(s, fs, p.k);
-        u.rc = key_rc(u.fwd, p);
-        const bool canon_fwd = key_is_canonical(u.fwd, p);
+        if (!(g >= g_begin && g < g_end && fs < s.len)) return false;        // outside the shard, or one of the k-1 padded bytes that start no window
+        fwd = fetch_codes<W>(t.packed, g, p);
+        fwd.d = window_dots(s, fs, p.k);
+        rc = key_rc(fwd, p);
+        const bool canon_fwd = key_is_canonical(fwd, p);
+        flags = 0;
         // Kmer::first_position (kmer_graph.rs:57-60): position 0 of the forward strand is window 0; position 0 of the
         // reverse strand is the reverse complement of the last window (kmer_graph.rs:103-108).
-        if (fs == 0) u.flags |= canon_fwd ? AC_AUX_FIRST_CANON : AC_AUX_FIRST_RC;
-        if (fs + 1 == s.len) u.flags |= canon_fwd ? AC_AUX_FIRST_RC : AC_AUX_FIRST_CANON;
-        if (u.fwd.d == 0) {    // neighbouring bases seen next to this k-mer: spares the adjacency kernel the probes for neighbours it already knows to exist
+        if (fs == 0) flags |= canon_fwd ? AC_AUX_FIRST_CANON : AC_AUX_FIRST_RC;
+        if (fs + 1 == s.len) flags |= canon_fwd ? AC_AUX_FIRST_RC : AC_AUX_FIRST_CANON;
+        if (fwd.d == 0) {    // neighbouring bases seen next to this k-mer: spares the adjacency kernel the probes for neighbours it already knows to exist
             if (fs + 1 < s.len && window_dots(s, fs + 1, p.k) == 0) {
                 const uint32_t b = packed_base(t.packed, (uint64_t)g + p.k);
-                u.flags |= canon_fwd ? (1u << (AC_AUX_OBS_OUT_SHIFT + b)) : (1u << (AC_AUX_OBS_IN_SHIFT + 3 - b));
+                flags |= canon_fwd ? (1u << (AC_AUX_OBS_OUT_SHIFT + b)) : (1u << (AC_AUX_OBS_IN_SHIFT + 3 - b));
             }
             if (fs > 0 && window_dots(s, fs - 1, p.k) == 0) {
                 const uint32_t b = packed_base(t.packed, (uint64_t)g - 1);
-                u.flags |= canon_fwd ? (1u << (AC_AUX_OBS_IN_SHIFT + b)) : (1u << (AC_AUX_OBS_OUT_SHIFT + 3 - b));
+                flags |= canon_fwd ? (1u << (AC_AUX_OBS_IN_SHIFT + b)) : (1u << (AC_AUX_OBS_OUT_SHIFT + 3 - b));
             }
         }
-        u.h = key_hash(canon_fwd ? u.fwd : u.rc);
-        u.dotted = u.fwd.d != 0;
-        return u;
+        h = key_hash(canon_fwd ? fwd : rc);
+        return true;
     }
-    AC_D Unit unit_at(uint32_t g) const {
-        const uint32_t g0 = g & ~31u;
-        uint32_t si;
-#ifdef __CUDA_ARCH__
-        si = 0;
-        if ((threadIdx.x & 31) == 0) si = find_seq(t.seqs, t.n_seqs, g0);
-        si = __shfl_sync(0xFFFFFFFFu, si, 0);
-#else
-        si = find_seq(t.seqs, t.n_seqs, g0);
-#endif
-        const SeqInfo s = t.seqs[si];
-        const uint32_t fs0 = g0 - (uint32_t)s.start;
-        const bool interior = g0 >= g_begin && g0 + 32 <= g_end && fs0 >= (uint32_t)s.lead + 1 && (uint64_t)fs0 + 33 + s.trail <= s.len;
-        return interior ? interior_unit(g) : edge_unit(g, si);
-    }
-    // Enters the unit's k-mer (or finds it) and counts the occurrence.  All lanes of the warp call this together.
-    AC_D void upsert(const Unit& u, uint32_t g) const {
-        const uint32_t tag = make_tag(u.dotted, u.h);
-        const Slot mine = make_slot(g, tag, t.count_big ? 0u : 1u, u.flags);
-        uint64_t slot = table_home(t, u.h);
-        bool done = !u.valid, failed = false;
+    // Enters the k-mer (or finds it) and counts the occurrence.  All lanes of the warp call this together.
+    AC_D void upsert(bool valid, const Key<W>& fwd, const Key<W>& rc, uint64_t h, uint32_t flags, uint32_t g) const {
+        const bool dotted = valid && fwd.d != 0;
+        const uint32_t tag = make_tag(dotted, h, t.gb);
+        const Slot mine = make_slot(g, tag, t.count_big ? 0u : 1u, flags, t.gb);
+        const uint32_t tag_mask = (1u << (38 - t.gb)) - 1u;
+        uint64_t slot = table_home(t, h);
+        bool done = !valid, failed = false;
         for (uint32_t probes = 0;;) {
             bool claimed = false; Slot q = 0;
             if (!done) {
@@ -252,24 +242,28 @@ template <int W> struct InsertBody {
                     Slot grp[4];
                     const uint64_t base = slot & ~3ull;
                     ac_ld_group(t.slots + base, grp);
-                    const uint32_t start = (uint32_t)(slot & 3u);
-                    bool stop = false; uint32_t at = 4;
+                    // the first slot of the group, from `slot` on, that is empty or carries the tag
+                    uint32_t hit = 0, empty = 0;
 #pragma unroll
-                    for (uint32_t j = 0; j < 4; ++j) {     // first slot of the group, from `slot` on, that is empty or carries the tag (unrolled: the group stays in registers)
-                        if (!stop && j >= start) {
-                            Slot e = grp[j];
-                            if (e == AC_EMPTY_SLOT) {
-                                e = ac_atomic_cas(&t.slots[base + j], (Slot)AC_EMPTY_SLOT, mine);
-                                if (e == AC_EMPTY_SLOT) { claimed = true; stop = true; at = j; }
-                            }
-                            if (!stop && slot_tag(e) == tag) { stop = true; at = j; }
-                            if (stop) q = e;
-                        }
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        if (grp[j] == AC_EMPTY_SLOT) empty |= 1u << j;
+                        if (((uint32_t)(grp[j] >> AC_SLOT_TAG_SHIFT) & tag_mask) == tag) hit |= 1u << j;
                     }
-                    slot = base + at;
-                    if (stop) break;
-                    if (slot >= t.cap) slot = 0;
-                    if (++probes > 2048) { counters[2] = 1; failed = true; done = true; break; }    // the table was sized too small: the host retries with the safe size
+                    const uint32_t cand = (hit | empty) & (0xFu << (slot & 3u)) & 0xFu;
+                    if (cand == 0) {
+                        slot = base + 4; if (slot >= t.cap) slot = 0;
+                        if (++probes > 2048) { counters[2] = 1; failed = true; done = true; break; }    // the table was sized too small: the host retries with the safe size
+                        continue;
+                    }
+                    const uint32_t j = (uint32_t)ac_ctz(cand);
+                    slot = base + j;
+                    q = j == 0 ? grp[0] : j == 1 ? grp[1] : j == 2 ? grp[2] : grp[3];
+                    if ((empty >> j) & 1u) {
+                        q = ac_atomic_cas(&t.slots[slot], (Slot)AC_EMPTY_SLOT, mine);
+                        if (q == AC_EMPTY_SLOT) { claimed = true; break; }
+                        if (slot_tag(q, t.gb) != tag) { ++slot; if (slot >= t.cap) slot = 0; continue; }      // somebody else's k-mer got there first: on to the next slot
+                    }
+                    break;
                 }
             }
 #ifdef __CUDA_ARCH__
@@ -279,11 +273,11 @@ template <int W> struct InsertBody {
                 if (claimed) {
                     if (t.count_big) ac_atomic_add(&t.count_big[slot], 1u);
                     if (sizing) ac_atomic_add(&counters[0], 1ull);
-                    if (u.dotted) ac_atomic_add(&counters[1], 1ull);
+                    if (dotted) ac_atomic_add(&counters[1], 1ull);
                     done = true;
                 } else {
-                    const Key<W> rep = window_key<W>(t, slot_gpos(q), u.dotted, p);
-                    if (key_eq(rep, u.fwd) || key_eq(rep, u.rc)) { if (!sizing) slot_add_occurrence(t, slot, q, g, 1u, u.flags, track_min, counters); done = true; }
+                    const Key<W> rep = window_key<W>(t, slot_gpos(q, t.gb), dotted, p);
+                    if (key_eq(rep, fwd) || key_eq(rep, rc)) { if (!sizing) slot_add_occurrence(t, slot, q, g, 1u, flags, track_min, counters); done = true; }
                     else if (++slot == t.cap) slot = 0;
                 }
             }
@@ -293,11 +287,14 @@ template <int W> struct InsertBody {
             if (done) break;
 #endif
         }
-        if (u.valid && !failed && pos_slot) pos_slot[g] = (uint32_t)slot;
+        if (valid && !failed && pos_slot) pos_slot[g] = (uint32_t)slot;
     }
     AC_D void operator()(uint64_t i) const {
-        const uint32_t g = g_first + (uint32_t)i;
-        upsert(unit_at(g), g);
+        const uint32_t g = g_first + (uint32_t)i, g0 = g & ~31u;
+        Key<W> fwd = Key<W>(), rc = Key<W>(); uint64_t h = 0; uint32_t flags = 0; bool valid = true;
+        if (interior[g0 >> 5] && g0 >= g_begin && g0 + 32 <= g_end) interior_unit(g, fwd, rc, h, flags);
+        else valid = edge_unit(g, fwd, rc, h, flags);
+        upsert(valid, fwd, rc, h, flags, g);
     }
 };
 
@@ -319,10 +316,8 @@ template <int W> struct SampleBody {
     }
     AC_D void operator()(uint64_t i) const {
         const uint32_t g0 = (uint32_t)i * 32u;
-        const uint32_t si = find_seq(ins.t.seqs, ins.t.n_seqs, g0);
-        const SeqInfo s = ins.t.seqs[si];
-        const uint32_t fs0 = g0 - (uint32_t)s.start, k = ins.p.k, h = ins.p.h;
-        const bool interior = g0 + 32 <= total && fs0 >= (uint32_t)s.lead + 1 && (uint64_t)fs0 + 33 + s.trail <= s.len;
+        const uint32_t k = ins.p.k, h = ins.p.h;
+        const bool interior = g0 + 32 <= total && ins.interior[g0 >> 5];
         uint32_t hits = 0;
         if (interior) {                                    // centre of window g0 + l is base g0 + l + h; the seven bases start at g0 + l + h - 3
             const uint32_t first = g0 + h - 3;
@@ -332,11 +327,11 @@ template <int W> struct SampleBody {
                 acc = (acc << 2) | packed_base(ins.t.packed, (uint64_t)first + 6 + l);
                 if (sampled((uint32_t)acc & 0x3FFFu)) hits |= 1u << l;
             }
-        } else {
+        } else if (g0 < total) {
+            uint32_t sj = find_seq(ins.t.seqs, ins.t.n_seqs, g0);
             for (uint32_t l = 0; l < 32; ++l) {
                 const uint32_t g = g0 + l;
                 if (g >= total) break;
-                uint32_t sj = si;
                 while (sj + 1 < ins.t.n_seqs && ins.t.seqs[sj + 1].start <= g) ++sj;
                 const SeqInfo q = ins.t.seqs[sj];
                 const uint64_t fs = g - q.start;
@@ -351,22 +346,20 @@ template <int W> struct SampleBody {
         for (;;) {
             const bool have = hits != 0;
             if (!__any_sync(0xFFFFFFFFu, have)) break;
-            typename InsertBody<W>::Unit u; u.valid = false; u.dotted = false; u.h = 0; u.flags = 0; u.fwd = Key<W>(); u.rc = Key<W>();
+            Key<W> fwd = Key<W>(), rc = Key<W>(); uint64_t hh = 0;
             uint32_t g = g0;
             if (have) {
                 const uint32_t l = (uint32_t)ac_ctz(hits); hits &= hits - 1; g = g0 + l;
-                u.fwd = fetch_codes<W>(ins.t.packed, g, ins.p); u.fwd.d = 0; u.rc = key_rc(u.fwd, ins.p);
-                u.h = key_hash(key_is_canonical(u.fwd, ins.p) ? u.fwd : u.rc); u.valid = true;
+                fwd = fetch_codes<W>(ins.t.packed, g, ins.p); fwd.d = 0; rc = key_rc(fwd, ins.p);
+                hh = key_hash(key_is_canonical(fwd, ins.p) ? fwd : rc);
             }
-            ins.upsert(u, g);
+            ins.upsert(have, fwd, rc, hh, 0u, g);
         }
 #else
         for (; hits; hits &= hits - 1) {
             const uint32_t g = g0 + (uint32_t)ac_ctz(hits);
-            typename InsertBody<W>::Unit u; u.dotted = false; u.flags = 0;
-            u.fwd = fetch_codes<W>(ins.t.packed, g, ins.p); u.fwd.d = 0; u.rc = key_rc(u.fwd, ins.p);
-            u.h = key_hash(key_is_canonical(u.fwd, ins.p) ? u.fwd : u.rc); u.valid = true;
-            ins.upsert(u, g);
+            Key<W> fwd = fetch_codes<W>(ins.t.packed, g, ins.p); fwd.d = 0; const Key<W> rc = key_rc(fwd, ins.p);
+            ins.upsert(true, fwd, rc, key_hash(key_is_canonical(fwd, ins.p) ? fwd : rc), 0u, g);
         }
 #endif
     }
@@ -382,7 +375,7 @@ template <int W> struct BloomBuildBody {   // 16 filter bits per distinct k-mer,
     TableView t; KParams p; const uint32_t* occupied; uint64_t* bloom; uint64_t n_words;
     AC_D void operator()(uint64_t x) const {
         const Slot e = t.slots[occupied[x]];
-        const Key<W> f = window_key<W>(t, slot_gpos(e), slot_dotted(e), p);
+        const Key<W> f = window_key<W>(t, slot_gpos(e, t.gb), slot_dotted(e, t.gb), p);
         uint64_t word, mask;
         bloom_slot(key_hash(key_is_canonical(f, p) ? f : key_rc(f, p)), n_words, word, mask);
         if ((ac_ld_volatile(&bloom[word]) & mask) != mask) ac_atomic_or(&bloom[word], mask);
@@ -403,7 +396,7 @@ template <int W> struct AdjacencyBody {
         const uint64_t i = occupied[x];
         const Slot e = t.slots[i];
         const uint32_t aux = slot_flags(e);
-        const Key<W> f = window_key<W>(t, slot_gpos(e), slot_dotted(e), p);
+        const Key<W> f = window_key<W>(t, slot_gpos(e, t.gb), slot_dotted(e, t.gb), p);
         const Key<W> r = key_rc(f, p);
         const bool canon_fwd = key_is_canonical(f, p);
         uint32_t out_c, in_c;
@@ -513,10 +506,10 @@ struct RunEndsLocalBody {
 // Multi-GPU: an occurrence in rank-independent terms (its end k-mers are named by their smallest occurrence, which is
 // what every rank's table entry points at after the exchange), and back into this rank's slots.
 struct RunExportBody {
-    const uint64_t* run_start; const uint32_t* run_len; const uint32_t* run_hs; const uint32_t* run_ts; const Slot* slots; RunRec* out;
+    const uint64_t* run_start; const uint32_t* run_len; const uint32_t* run_hs; const uint32_t* run_ts; const Slot* slots; uint32_t gb; RunRec* out;
     AC_D void operator()(uint64_t r) const {
         RunRec x; x.start = run_start[r]; x.len = run_len[r]; x.pad = 0;
-        x.head_rep = slot_gpos(slots[run_hs[r]]); x.tail_rep = slot_gpos(slots[run_ts[r]]);
+        x.head_rep = slot_gpos(slots[run_hs[r]], gb); x.tail_rep = slot_gpos(slots[run_ts[r]], gb);
         out[r] = x;
     }
 };
@@ -588,14 +581,14 @@ template <int W> struct MergeBody {
     TableView t; KParams p; const SlotRec* in; uint32_t* pos_slot; unsigned long long* counters;
     AC_D void operator()(uint64_t i) const {
         const SlotRec r = in[i];
-        const uint64_t g = slot_gpos(r.slot);
-        const bool dotted = slot_dotted(r.slot);
+        const uint64_t g = slot_gpos(r.slot, t.gb);
+        const bool dotted = slot_dotted(r.slot, t.gb);
         const uint32_t flags = slot_flags(r.slot);
         const Key<W> fwd = window_key<W>(t, g, dotted, p);
         const Key<W> rc = key_rc(fwd, p);
         const uint64_t h = key_hash(key_is_canonical(fwd, p) ? fwd : rc);
-        const uint32_t tag = make_tag(dotted, h);
-        const Slot mine = make_slot(g, tag, t.count_big ? 0u : r.count, flags);
+        const uint32_t tag = make_tag(dotted, h, t.gb);
+        const Slot mine = make_slot(g, tag, t.count_big ? 0u : r.count, flags, t.gb);
         if (!t.count_big && r.count >= AC_SLOT_COUNT_ALARM) counters[3] = 1;
         uint64_t slot = table_home(t, h);
         for (uint32_t probes = 0;; ++probes) {
@@ -605,8 +598,8 @@ template <int W> struct MergeBody {
                 e = ac_atomic_cas(&t.slots[slot], (Slot)AC_EMPTY_SLOT, mine);
                 if (e == AC_EMPTY_SLOT) { if (t.count_big) ac_atomic_add(&t.count_big[slot], r.count); if (dotted) ac_atomic_add(&counters[1], 1ull); break; }
             }
-            if (slot_tag(e) == tag) {
-                const Key<W> rep = window_key<W>(t, slot_gpos(e), dotted, p);
+            if (slot_tag(e, t.gb) == tag) {
+                const Key<W> rep = window_key<W>(t, slot_gpos(e, t.gb), dotted, p);
                 if (key_eq(rep, fwd) || key_eq(rep, rc)) { slot_add_occurrence(t, slot, e, g, r.count, flags, true, counters); break; }
             }
             if (++slot == t.cap) slot = 0;
@@ -896,7 +889,7 @@ struct LinkCountBody {
 // iteration x handled x+ -> a+), then a- (self loop), then all b+ ascending, then x- for x > a.
 struct LinkOrderBody {
     const uint32_t* link_count; const uint32_t* links; const uint32_t* rank; const DeviceUnitig* unitigs;
-    const uint32_t* next_off; UStrand* next; uint32_t* prev_cnt;
+    const uint32_t* next_off; UStrand* next; uint32_t* prev_cnt; uint32_t* hairpins;     // hairpins: links that are their own mirror (a+ -> a-), for link_count (unitig_graph.rs:478-507)
     AC_D static uint64_t order_key(UStrand from, UStrand t) {
         const uint32_t a = from >> 1, b = t >> 1; const bool trev = t & 1;
         uint32_t phase;
@@ -915,7 +908,7 @@ struct LinkOrderBody {
             t[y] = v;
         }
         UStrand* out = next + next_off[from];
-        for (uint32_t x = 0; x < n; ++x) { out[x] = t[x]; ac_atomic_add(&prev_cnt[t[x]], 1u); }
+        for (uint32_t x = 0; x < n; ++x) { out[x] = t[x]; ac_atomic_add(&prev_cnt[t[x]], 1u); if (t[x] == (from ^ 1u)) ac_atomic_add(hairpins, 1u); }
     }
 };
 struct PrevFillBody {   // (a,s) -> (b,t) puts (a,s) into prev(b,t)
@@ -1113,6 +1106,7 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
     const ExpandCandidate* cands; const ExpandDeps* deps; const uint32_t* level; uint32_t this_level; const uint32_t* spec_len;
     UnitigRec* rec; char* arena; unsigned long long* arena_used; unsigned long long* total_shifted; uint64_t* dirty; uint8_t* exhausted;
     bool all_due;            // the first pass visits every candidate; later passes only those on the work list
+    unsigned long long* total_removed;   // bases the graph lost: every source gives up the piece, the destination gains it once
     AC_D char at(UStrand s, uint32_t side, uint32_t i) const {
         const UnitigRec& r = rec[s >> 1]; const char* p = arena + r.seq_off;
         const bool at_back = (side == 0) != (bool)(s & 1u);
@@ -1194,6 +1188,7 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
         }
         if (c != common_len) ac_atomic_or(&dirty[(size_t)ci >> 6], (uint64_t)1 << (ci & 63));          // capped: look again next pass
         ac_atomic_add(total_shifted, (unsigned long long)c);
+        ac_atomic_add(total_removed, (unsigned long long)c * (gn - 1));
     }
 };
 
@@ -1295,7 +1290,29 @@ struct PathTextBody {
         if (!last[x]) *p++ = ',';
     }
 };
-struct PathBoundBody { const uint64_t* path_off; const uint32_t* p_off; uint64_t steps; uint64_t total; uint64_t* bound; AC_D void operator()(uint64_t i) const { bound[i] = path_off[i] < steps ? p_off[path_off[i]] : total; } };
+// The P line of sequence i starts at wrap_off[i] + p_off[path_off[i]] of the P section: what the earlier sequences print around their
+// lists, plus all earlier list text; its list follows the prefix, its suffix follows the list (get_gfa_path_line, unitig_graph.rs:352-360).
+struct PathLineView { const uint64_t* path_off; uint32_t n_seqs; const uint32_t* p_off; const uint64_t* wrap_off; const uint32_t* pre_len; const uint32_t* suf_len; const char* blob; const uint64_t* blob_off; };
+struct PathTextFullBody {
+    const UStrand* path; const uint32_t* number_of; const uint8_t* last; PathLineView v; char* text;
+    AC_D void operator()(uint64_t x) const {
+        uint32_t lo = 0, hi = v.n_seqs;                    // the sequence whose path holds step x
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (v.path_off[mid] <= x) lo = mid; else hi = mid; }
+        char* p = text + v.wrap_off[lo] + v.pre_len[lo] + v.p_off[x];
+        p += ac_put_dec(p, number_of[path[x] >> 1] + 1); *p++ = (path[x] & 1u) ? '-' : '+';
+        if (!last[x]) *p++ = ',';
+    }
+};
+struct PathWrapBody {       // one thread per (sequence, prefix or suffix)
+    PathLineView v; char* text;
+    AC_D void operator()(uint64_t t) const {
+        const uint32_t i = (uint32_t)(t >> 1); const bool suffix = t & 1;
+        const char* src = v.blob + v.blob_off[i] + (suffix ? v.pre_len[i] : 0u);
+        char* dst = text + v.wrap_off[i] + (suffix ? v.pre_len[i] + v.p_off[v.path_off[i + 1]] : v.p_off[v.path_off[i]]);
+        const uint32_t n = suffix ? v.suf_len[i] : v.pre_len[i];
+        for (uint32_t b = 0; b < n; ++b) dst[b] = src[b];
+    }
+};
 
 // ---- contig distances (cluster.rs:132-151): which sequences pass through each unitig, then every pair of them shares its length ----
 struct PathMemberBody {
@@ -1463,7 +1480,6 @@ struct DevicePipeline::Impl {
     PinBuf h_cands, h_deps, h_spec, h_fixed, h_keys, h_sorted;
     DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2, d_arena3, d_pos, sort_c, sort_d, d_pos2, gfa_s_size, gfa_l_size, gfa_p_size, gfa_pieces, d_text, d_ptext, d_last, d_pbound;
     PinBuf h_dirty, h_exhausted, h_order2, h_text, h_ptext, h_pbound;
-    uint64_t gfa_tail_bytes = 0;          // room the caller needs behind the device-written lines for its P lines (DevicePipeline::gfa_tail_bytes)
     PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
     cudaEvent_t ev[20];
@@ -1540,8 +1556,8 @@ struct DevicePipeline::Impl {
     uint64_t cap = 0, n_windows = 0, n_runs = 0, g_begin = 0, g_end = 0, n_slots_used = 0, n_dotted = 0;
     bool any_dotted = false, is_multi = false, big_counts = false;      // big_counts: depths live in count_big (a 16-bit count ran out)
     int stage = 0;
-    DevBuf run_hs, run_ts, exp_flag, occ_list, bloom, needles, hits, count_big;
-    TableView table_view() { return TableView{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, big_counts ? count_big.as<uint32_t>() : nullptr}; }
+    DevBuf run_hs, run_ts, exp_flag, occ_list, bloom, needles, hits, count_big, interior8;
+    TableView table_view() { return TableView{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, big_counts ? count_big.as<uint32_t>() : nullptr, slot_gpos_bits(total)}; }
     void set_device() {
 #ifndef AC_EMULATE
         AC_CUDA_CHECK(cudaSetDevice(device));
@@ -1550,7 +1566,23 @@ struct DevicePipeline::Impl {
     template <int W> void local_w(uint32_t seq_lo, uint32_t seq_hi, bool multi);
     template <int W> void merge_w(const void* dev_ptr, uint64_t n);
     template <int W> void runs_local_w();
-    template <int W> void finish_w(PipelineResult& out, bool keep_positions);
+    template <int W> void finish_w(PipelineResult& out, bool keep_positions, bool fused);
+    // what a finished build leaves in HBM for pull_graph() (at once in a plain build, on request after a fused one)
+    struct Pending {
+        uint32_t U = 0, n_strands = 0; uint64_t n_links = 0, n_cands = 0;
+        uint32_t* order_built = nullptr; uint32_t* final_order = nullptr; uint8_t* fix_start = nullptr;
+        DevBuf* arena_src = nullptr; uint64_t arena_final = 0;
+        bool first_pass_done = false, any_moved = false, gfa_on_device = false, hairpins_ready = false;
+        uint64_t first_pass_total = 0, bases_removed = 0, gfa_bytes = 0;
+    } R;
+    bool pending_keep_positions = false;
+    void pull_graph(PipelineResult& out, bool keep_positions);
+    DevBuf d_small, d_totals, d_wrap_off, d_pre_len, d_suf_len, d_blob, d_blob_off;
+    std::vector<char> path_blob; std::vector<uint32_t> path_pre, path_suf; uint64_t path_wrap_total = 0;
+    void scan_keep_total(uint32_t* x, uint64_t n, uint32_t* total_dst) {      // in place; x[n-1] must be 0, so the scanned x[n-1] is the total: kept on the device
+        exclusive_scan(x, x, n, 0, false);
+        ac_copy_dd(total_dst, x + (n - 1), 4, &stream);
+    }
     uint64_t exp_n = 0;
     uint64_t do_count_entries();
     void do_export_entries(void* dst, uint64_t cap_records);
@@ -1609,7 +1641,24 @@ void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo*
     ac_h2d(m.ascii.p, ascii, total, &m.stream);
     m.seqs.ensure(n_seqs * sizeof(SeqInfo));
     ac_h2d(m.seqs.p, seqs, n_seqs * sizeof(SeqInfo), &m.stream);
+    if (m.path_pre.size() == n_seqs) {       // the P-line texts (set_path_line_texts): prefix and suffix of every sequence, and where each line's share starts
+        std::vector<uint64_t> wrap((size_t)n_seqs + 1, 0), boff((size_t)n_seqs + 1, 0);
+        for (uint32_t i = 0; i < n_seqs; ++i) { wrap[i + 1] = wrap[i] + m.path_pre[i] + m.path_suf[i]; boff[i + 1] = wrap[i + 1]; }
+        m.path_wrap_total = wrap[n_seqs];
+        m.d_wrap_off.ensure(wrap.size() * 8); m.d_blob_off.ensure(boff.size() * 8); m.d_pre_len.ensure((size_t)n_seqs * 4); m.d_suf_len.ensure((size_t)n_seqs * 4); m.d_blob.ensure(m.path_blob.size() + 8);
+        ac_h2d(m.d_wrap_off.p, wrap.data(), wrap.size() * 8, &m.stream); ac_h2d(m.d_blob_off.p, boff.data(), boff.size() * 8, &m.stream);
+        ac_h2d(m.d_pre_len.p, m.path_pre.data(), (size_t)n_seqs * 4, &m.stream); ac_h2d(m.d_suf_len.p, m.path_suf.data(), (size_t)n_seqs * 4, &m.stream);
+        if (!m.path_blob.empty()) ac_h2d(m.d_blob.p, m.path_blob.data(), m.path_blob.size(), &m.stream);
+        ac_sync(&m.stream);                  // the staging vectors above are locals
+    } else m.path_wrap_total = 0;
     m.mark(1);
+}
+
+void DevicePipeline::set_path_line_texts(const char* blob, const uint32_t* prefix_len, const uint32_t* suffix_len, uint32_t n) {
+    Impl& m = *impl;
+    m.path_pre.assign(prefix_len, prefix_len + n); m.path_suf.assign(suffix_len, suffix_len + n);
+    uint64_t bytes = 0; for (uint32_t i = 0; i < n; ++i) bytes += (uint64_t)prefix_len[i] + suffix_len[i];
+    m.path_blob.assign(blob, blob + bytes);
 }
 
 void DevicePipeline::sort_number_keys(const NumberKey* keys, uint32_t n, uint32_t* sorted) {
@@ -1656,7 +1705,7 @@ void DevicePipeline::find_literals(const uint8_t* ascii_host, uint64_t total_byt
     const uint64_t n_words = (total_bytes + 31) / 32;
     m.packed.ensure((n_words + 6) * sizeof(uint64_t));
     ac_memset(m.packed.as<uint64_t>() + n_words, 0, 6 * sizeof(uint64_t), &m.stream);
-    ac_launch("pack", &m.stream, PackBody{m.ascii.as<uint8_t>(), total_bytes, m.packed.as<uint64_t>()}, n_words);
+    ac_launch("pack", &m.stream, PackBody{m.ascii.as<uint8_t>(), total_bytes, m.packed.as<uint64_t>(), nullptr, 0, nullptr}, n_words);
     // needle table (host-built, tiny)
     uint64_t cap = 64; while (cap < 4ull * n_needles) cap <<= 1;
     std::vector<NeedleSlot> table(cap);
@@ -1707,7 +1756,8 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
     const uint64_t n_words = (total + 31) / 32;
     packed.ensure((n_words + W + 2) * sizeof(uint64_t));
     ac_memset(packed.as<uint64_t>() + n_words, 0, (W + 2) * sizeof(uint64_t), &stream);
-    ac_launch("pack", &stream, PackBody{ascii.as<uint8_t>(), total, packed.as<uint64_t>()}, n_words);
+    interior8.ensure(n_words + 8);
+    ac_launch("pack", &stream, PackBody{ascii.as<uint8_t>(), total, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, interior8.as<uint8_t>()}, n_words);
     mark(3);
 
     // ---- size the table: distinct canonical k-mers estimated from the 1/64 of them whose hash ends in six zero bits ----
@@ -1723,8 +1773,8 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
         slots.ensure(sample_cap * sizeof(Slot));
         ac_memset(slots.p, 0xFF, sample_cap * sizeof(Slot), &stream);
         ac_memset(counters.p, 0, sizeof hc, &stream);
-        const TableView sv{slots.as<Slot>(), sample_cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, nullptr};
-        const InsertBody<W> sample_ins{sv, p, 0, 0, (uint32_t)total, false, nullptr, counters.as<unsigned long long>(), true};
+        const TableView sv{slots.as<Slot>(), sample_cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, nullptr, slot_gpos_bits(total)};
+        const InsertBody<W> sample_ins{sv, p, interior8.as<uint8_t>(), 0, 0, (uint32_t)total, false, nullptr, counters.as<unsigned long long>(), true};
         ac_launch("sample", &stream, SampleBody<W>{sample_ins, (uint32_t)total}, ((total + 31) / 32 + 31) / 32 * 32);
         ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
         if (!hc[2]) {      // every rank samples every sequence, so all of them arrive at the same size
@@ -1743,7 +1793,7 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
         ac_memset(counters.p, 0, sizeof hc, &stream);
         const TableView tv = table_view();
         const uint64_t g_first = g_begin & ~31ull;
-        const InsertBody<W> ins{tv, p, (uint32_t)g_first, (uint32_t)g_begin, (uint32_t)g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), false};
+        const InsertBody<W> ins{tv, p, interior8.as<uint8_t>(), (uint32_t)g_first, (uint32_t)g_begin, (uint32_t)g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), false};
         ac_launch_occ("insert", &stream, ins, (g_end - g_first + 31) / 32 * 32, insert_occupancy);
         ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
         if (hc[2] && cap != safe_cap) { cap = safe_cap; continue; }         // the estimate was off (it is an estimate): start again with the safe size
@@ -1820,7 +1870,7 @@ void DevicePipeline::Impl::do_export_runs(void* dst, uint64_t cap_records) {
     if (stage < 2) throw std::runtime_error("runs_local must precede export_runs");
     if (cap_records < n_runs) throw std::runtime_error("run buffer too small");
     ac_launch("run_export", &stream, RunExportBody{run_start.as<uint64_t>(), run_len.as<uint32_t>(), run_hs.as<uint32_t>(), run_ts.as<uint32_t>(),
-                                                   slots.as<Slot>(), (RunRec*)dst}, n_runs);
+                                                   slots.as<Slot>(), slot_gpos_bits(total), (RunRec*)dst}, n_runs);
     ac_sync(&stream);
 }
 
@@ -1833,7 +1883,7 @@ void DevicePipeline::Impl::do_import_runs(const void* dev_ptr, uint64_t n) {
 }
 
 // ---- stage 3: unitigs, seeds, links, seed order and the host-ready arrays (over every occurrence handed to it) ----
-template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool keep_positions) {
+template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool keep_positions, bool fused) {
     if (stage < 2) throw std::runtime_error("runs_local must precede finish");
     const KParams p = make_kparams(k, W);
     const TableView tv = table_view();
@@ -1903,8 +1953,9 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     const uint64_t n_links = exclusive_scan(strand_cnt.as<uint32_t>(), d_next_off.as<uint32_t>(), (uint64_t)n_strands + 1);
     d_next.ensure(n_links * 4); d_prev.ensure(n_links * 4);
     ac_memset(prev_cnt.p, 0, ((size_t)n_strands + 1) * 4, &stream);
+    d_small.ensure(64); ac_memset(d_small.p, 0, 64, &stream);           // [0] hairpin links
     ac_launch("link_order", &stream, LinkOrderBody{link_count.as<uint32_t>(), links.as<uint32_t>(), rank.as<uint32_t>(), unitigs.as<DeviceUnitig>(),
-                                                   d_next_off.as<uint32_t>(), d_next.as<UStrand>(), prev_cnt.as<uint32_t>()}, n_strands);
+                                                   d_next_off.as<uint32_t>(), d_next.as<UStrand>(), prev_cnt.as<uint32_t>(), d_small.as<uint32_t>()}, n_strands);
     exclusive_scan(prev_cnt.as<uint32_t>(), d_prev_off.as<uint32_t>(), (uint64_t)n_strands + 1);
     ac_memset(prev_cnt.p, 0, ((size_t)n_strands + 1) * 4, &stream);    // reused as the fill cursor
     ac_launch("prev_fill", &stream, PrevFillBody{d_next_off.as<uint32_t>(), d_next.as<UStrand>(), d_prev_off.as<uint32_t>(), prev_cnt.as<uint32_t>(), d_prev.as<UStrand>()}, n_strands);
@@ -1937,98 +1988,140 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     ac_launch("dependents", &stream, DependentsBody{d_next_off.as<uint32_t>(), d_next.as<UStrand>(), d_prev_off.as<uint32_t>(), d_prev.as<UStrand>(), d_cand_at.as<int32_t>(),
                                                     d_deps.as<ExpandDeps>()}, U);
     ac_launch("common_length", &stream, CommonLengthBody{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_arena.as<char>(), d_spec.as<uint32_t>()}, n_cands);
-    // Opt-in: the whole first pass of expand_repeats here, level by level (the host then starts at pass 2).
-    static const bool device_first_pass = getenv("AC_DEVICE_FIRST_PASS") != nullptr || getenv("AC_DEVICE_SIMPLIFY") != nullptr;
-    uint64_t arena_final = arena_bytes, first_pass_total = 0; bool first_pass_done = false;
-    const uint32_t* final_order = nullptr;      // device pointer: the numbering after simplify_structure, when that ran here
-    bool gfa_on_device = false; uint64_t gfa_s_bytes = 0, gfa_l_bytes = 0, gfa_p_bytes = 0;
+    // ---- simplify_structure and save_gfa on the device: always in a fused build; in a plain build only behind the switches
+    // AC_DEVICE_FIRST_PASS (first expand_repeats call), AC_DEVICE_SIMPLIFY (the whole loop + renumbering), AC_DEVICE_GFA (the text) ----
+    static const bool env_first = getenv("AC_DEVICE_FIRST_PASS") != nullptr, env_simplify = getenv("AC_DEVICE_SIMPLIFY") != nullptr, env_gfa = getenv("AC_DEVICE_GFA") != nullptr;
+    const bool device_simplify = fused || env_simplify, device_first_pass = device_simplify || env_first, device_gfa = fused || (env_simplify && env_gfa);
+    R = Pending();
+    R.U = U; R.n_links = n_links; R.n_cands = n_cands; R.n_strands = n_strands; R.order_built = ord_in; R.fix_start = fix_start;
+    R.arena_final = arena_bytes; R.arena_src = &d_arena;
+    mark(11);
+    if (device_first_pass && n_cands == 0 && device_simplify) { R.first_pass_done = true; R.first_pass_total = 0; }     // nothing can shift: the loop ends at once
     if (device_first_pass && n_cands > 0) {
-        static const bool device_simplify = getenv("AC_DEVICE_SIMPLIFY") != nullptr;
-        d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(32); d_counters64.ensure((2 * AC_BOUND_STRIPES + 2) * 8);
+        d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(32); d_counters64.ensure((2 * AC_BOUND_STRIPES + 3) * 8);
         d_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); d_exhausted.ensure(n_cands + 8);
-        unsigned long long* c64 = d_counters64.as<unsigned long long>();         // [0] arena bump, [1] bases moved, [2..] bound stripes of this pass, then of the next
-        unsigned long long* bound_now = c64 + 2; unsigned long long* bound_next = c64 + 2 + AC_BOUND_STRIPES;
+        unsigned long long* c64 = d_counters64.as<unsigned long long>();         // [0] arena bump, [1] bases moved, [2..] bound stripes of this pass, then of the next, then bases the graph lost
+        unsigned long long* bound_now = c64 + 2; unsigned long long* bound_next = c64 + 2 + AC_BOUND_STRIPES; unsigned long long* removed = c64 + 2 + 2 * AC_BOUND_STRIPES;
         ac_launch("level_pred", &stream, LevelPredBody{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_pred.as<int32_t>()}, n_cands);
         ac_memset(d_level.p, 0, n_cands * 4, &stream); ac_memset(d_flagmax.p, 0, 32, &stream);
         ac_launch_coop("levels", &stream, LevelsCoopBody{d_pred.as<int32_t>(), d_level.as<uint32_t>(), d_flagmax.as<uint32_t>(), n_cands}, n_cands);
-        ac_memset(d_counters64.p, 0, (2 * AC_BOUND_STRIPES + 2) * 8, &stream);
+        ac_memset(d_counters64.p, 0, (2 * AC_BOUND_STRIPES + 3) * 8, &stream);
         const RelocBoundBody bound_body{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_cand_at.as<int32_t>(), bound_now};
         ac_launch("reloc_bound", &stream, bound_body, n_cands);
-        uint32_t fm[8]; std::vector<unsigned long long> h64(2 * AC_BOUND_STRIPES + 2);
+        uint32_t fm[8]; std::vector<unsigned long long> h64(2 * AC_BOUND_STRIPES + 3);
         ac_d2h(fm, d_flagmax.p, 32, &stream); ac_d2h(h64.data(), c64, h64.size() * 8, &stream); ac_sync(&stream);
         if (fm[4]) throw std::runtime_error("candidate levels did not settle");
-        (void)fm[3];                             // the number of levels stays on the device (ApplyPassCoopBody reads it)
         unsigned long long bound = 0; for (int x = 0; x < AC_BOUND_STRIPES; ++x) bound += h64[2 + x];
-        {
-            if (arena_bytes + bound >= 0xFFFFFFF0ull) throw std::runtime_error("unitig sequence arena would exceed 4 GB");
-            d_arena2.ensure(arena_bytes + bound + 64);
-            ac_copy_dd(d_arena2.p, d_arena.p, arena_bytes, &stream);
-            const unsigned long long start = arena_bytes;
-            ac_h2d(c64, &start, 8, &stream);
-            ac_memset(d_dirty.p, 0, ((n_cands + 63) / 64) * 8 + 8, &stream); ac_memset(d_exhausted.p, 0, n_cands + 8, &stream);
-            // `while expand_repeats() > 0 {}` (with AC_DEVICE_SIMPLIFY; else only its first call): one launch and one read-back per pass
-            for (uint32_t pass = 1;; ++pass) {
-                const ApplyLevelBody apply{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_level.as<uint32_t>(), 0, d_spec.as<uint32_t>(),
-                                           d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64, c64 + 1, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>(), pass == 1};
-                RelocBoundBody nb = bound_body; nb.bound = bound_next;
-                ac_launch_coop("apply_pass", &stream, ApplyPassCoopBody{apply, nb, n_cands, d_flagmax.as<uint32_t>() + 3}, n_cands);
-                ac_d2h(h64.data(), c64, h64.size() * 8, &stream); ac_sync(&stream);
-                arena_final = h64[0]; first_pass_total = h64[1]; first_pass_done = true;      // what this expand_repeats() call returned
-                if (!device_simplify || first_pass_total == 0) break;
-                if (pass > 100000) throw std::runtime_error("repeat expansion did not settle");
-                bound = 0; for (int x = 0; x < AC_BOUND_STRIPES; ++x) bound += h64[2 + AC_BOUND_STRIPES + x];
-                if (arena_final + bound >= 0xFFFFFFF0ull) throw std::runtime_error("unitig sequence arena would exceed 4 GB");
-                static const bool always_grow = getenv("AC_DEVICE_TIGHT_ARENA") != nullptr;   // test hook: take the growth path before every pass
-                if (always_grow || arena_final + bound + 64 > d_arena2.cap) {             // make room for whatever the next pass may relocate
-                    d_arena3.ensure(std::max<size_t>((arena_final + bound) * 2 + 64, d_arena3.cap + (always_grow ? 64 : 0)));
-                    ac_copy_dd(d_arena3.p, d_arena2.p, arena_final, &stream); ac_sync(&stream);
-                    std::swap(d_arena2.p, d_arena3.p); std::swap(d_arena2.cap, d_arena3.cap);
-                }
-                ac_memset(c64 + 1, 0, (2 * AC_BOUND_STRIPES + 1) * 8, &stream);
+        if (arena_bytes + bound >= 0xFFFFFFF0ull) throw std::runtime_error("unitig sequence arena would exceed 4 GB");
+        d_arena2.ensure(arena_bytes + bound + 64);
+        ac_copy_dd(d_arena2.p, d_arena.p, arena_bytes, &stream);
+        const unsigned long long start = arena_bytes;
+        ac_h2d(c64, &start, 8, &stream);
+        ac_memset(d_dirty.p, 0, ((n_cands + 63) / 64) * 8 + 8, &stream); ac_memset(d_exhausted.p, 0, n_cands + 8, &stream);
+        // `while expand_repeats() > 0 {}` (only its first call without device_simplify): one launch and one read-back per pass
+        for (uint32_t pass = 1;; ++pass) {
+            const ApplyLevelBody apply{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_level.as<uint32_t>(), 0, d_spec.as<uint32_t>(),
+                                       d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64, c64 + 1, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>(), pass == 1, removed};
+            RelocBoundBody nb = bound_body; nb.bound = bound_next;
+            ac_launch_coop("apply_pass", &stream, ApplyPassCoopBody{apply, nb, n_cands, d_flagmax.as<uint32_t>() + 3}, n_cands);
+            ac_d2h(h64.data(), c64, h64.size() * 8, &stream); ac_sync(&stream);
+            R.arena_final = h64[0]; R.first_pass_total = h64[1]; R.first_pass_done = true;      // what this expand_repeats() call returned
+            R.bases_removed = h64[2 + 2 * AC_BOUND_STRIPES]; R.any_moved = R.any_moved || h64[1] != 0;
+            if (!device_simplify || R.first_pass_total == 0) break;
+            if (pass > 100000) throw std::runtime_error("repeat expansion did not settle");
+            bound = 0; for (int x = 0; x < AC_BOUND_STRIPES; ++x) bound += h64[2 + AC_BOUND_STRIPES + x];
+            if (R.arena_final + bound >= 0xFFFFFFF0ull) throw std::runtime_error("unitig sequence arena would exceed 4 GB");
+            static const bool always_grow = getenv("AC_DEVICE_TIGHT_ARENA") != nullptr;   // test hook: take the growth path before every pass
+            if (always_grow || R.arena_final + bound + 64 > d_arena2.cap) {             // make room for whatever the next pass may relocate
+                d_arena3.ensure(std::max<size_t>((R.arena_final + bound) * 2 + 64, d_arena3.cap + (always_grow ? 64 : 0)));
+                ac_copy_dd(d_arena3.p, d_arena2.p, R.arena_final, &stream); ac_sync(&stream);
+                std::swap(d_arena2.p, d_arena3.p); std::swap(d_arena2.cap, d_arena3.cap);
             }
-            if (device_simplify) {      // simplify_structure ends with renumber_unitigs (:38): stable with respect to the numbering the passes ran in
-                d_pos.ensure((size_t)U * 4); sort_c.ensure((size_t)U * 4); sort_d.ensure((size_t)U * 4);
-                ac_launch("inverse_perm", &stream, InversePermBody{ord_in, d_pos.as<uint32_t>()}, U);
-                ac_launch("number_key", &stream, NumberKeyBody{d_rec.as<UnitigRec>(), d_arena2.as<char>(), num_prefix.as<uint64_t>()}, U);
-                const NumberLess final_less{d_rec.as<UnitigRec>(), d_depth.as<uint32_t>(), d_arena2.as<char>(), num_prefix.as<uint64_t>(), d_pos.as<uint32_t>()};
-                uint32_t* fin = sort_indices(&stream, final_less, U, sort_c.as<uint32_t>(), sort_d.as<uint32_t>());
-                final_order = fin;
-                static const bool device_gfa = getenv("AC_DEVICE_GFA") != nullptr;
-                if (device_gfa && U < 100000000u) {          // save_gfa's S and L lines and the path lists, rendered here
-                    d_pos2.ensure((size_t)U * 4);
-                    ac_launch("inverse_perm", &stream, InversePermBody{fin, d_pos2.as<uint32_t>()}, U);
-                    const GfaView gv{fin, d_pos2.as<uint32_t>(), d_rec.as<UnitigRec>(), d_arena2.as<char>(), d_depth.as<uint32_t>(), d_next_off.as<uint32_t>(), d_next.as<UStrand>()};
-                    gfa_s_size.ensure(((size_t)U + 1) * 4); gfa_l_size.ensure(((size_t)U + 1) * 4);
-                    ac_launch("gfa_size", &stream, GfaSizeBody{gv, U, gfa_s_size.as<uint32_t>(), gfa_l_size.as<uint32_t>()}, (uint64_t)U + 1);
-                    gfa_s_bytes = exclusive_scan(gfa_s_size.as<uint32_t>(), gfa_s_size.as<uint32_t>(), (uint64_t)U + 1);
-                    gfa_l_bytes = exclusive_scan(gfa_l_size.as<uint32_t>(), gfa_l_size.as<uint32_t>(), (uint64_t)U + 1);
-                    d_text.ensure(gfa_s_bytes + gfa_l_bytes + 64);
-                    ac_launch("gfa_segment", &stream, GfaSegmentBody{gv, gfa_s_size.as<uint32_t>(), d_text.as<char>()}, U);
-                    gfa_pieces.ensure(((size_t)U + 1) * 4);
-                    ac_launch("gfa_chunk_count", &stream, GfaChunkCountBody{gv, U, gfa_pieces.as<uint32_t>()}, (uint64_t)U + 1);
-                    const uint64_t n_pieces = exclusive_scan(gfa_pieces.as<uint32_t>(), gfa_pieces.as<uint32_t>(), (uint64_t)U + 1);
-                    ac_launch("gfa_sequence", &stream, GfaSequenceBody{gv, U, gfa_pieces.as<uint32_t>(), gfa_s_size.as<uint32_t>(), d_text.as<char>()}, n_pieces);
-                    ac_launch("gfa_link", &stream, GfaLinkBody{gv, gfa_l_size.as<uint32_t>(), d_text.as<char>() + gfa_s_bytes}, U);
-                    const uint64_t steps = n_runs;
-                    d_last.ensure(steps + 8); gfa_p_size.ensure((steps + 1) * 4); d_pbound.ensure(((size_t)n_seqs + 1) * 8);
-                    ac_memset(d_last.p, 0, steps + 8, &stream);
-                    ac_launch("path_last", &stream, PathLastBody{d_path_off.as<uint64_t>(), d_last.as<uint8_t>()}, n_seqs);
-                    ac_launch("path_size", &stream, PathSizeBody{d_path.as<UStrand>(), d_pos2.as<uint32_t>(), d_last.as<uint8_t>(), steps, gfa_p_size.as<uint32_t>()}, steps + 1);
-                    gfa_p_bytes = exclusive_scan(gfa_p_size.as<uint32_t>(), gfa_p_size.as<uint32_t>(), steps + 1);
-                    d_ptext.ensure(gfa_p_bytes + 64);
-                    ac_launch("path_text", &stream, PathTextBody{d_path.as<UStrand>(), d_pos2.as<uint32_t>(), d_last.as<uint8_t>(), gfa_p_size.as<uint32_t>(), d_ptext.as<char>()}, steps);
-                    ac_launch("path_bound", &stream, PathBoundBody{d_path_off.as<uint64_t>(), gfa_p_size.as<uint32_t>(), steps, gfa_p_bytes, d_pbound.as<uint64_t>()}, (uint64_t)n_seqs + 1);
-                    gfa_on_device = true;
-                }
-            }
+            ac_memset(c64 + 1, 0, (2 * AC_BOUND_STRIPES + 1) * 8, &stream);             // bases moved and both stripe sets; the running total of removed bases stays
+        }
+        R.arena_src = &d_arena2;
+    }
+    mark(17);
+    const bool simplified = device_simplify && R.first_pass_done && R.first_pass_total == 0;
+    if (simplified) {      // simplify_structure ends with renumber_unitigs (:38): stable with respect to the numbering the passes ran in
+        if (R.any_moved) {
+            d_pos.ensure((size_t)U * 4); sort_c.ensure((size_t)U * 4); sort_d.ensure((size_t)U * 4);
+            ac_launch("inverse_perm", &stream, InversePermBody{ord_in, d_pos.as<uint32_t>()}, U);
+            ac_launch("number_key", &stream, NumberKeyBody{d_rec.as<UnitigRec>(), R.arena_src->as<char>(), num_prefix.as<uint64_t>()}, U);
+            const NumberLess final_less{d_rec.as<UnitigRec>(), d_depth.as<uint32_t>(), R.arena_src->as<char>(), num_prefix.as<uint64_t>(), d_pos.as<uint32_t>()};
+            R.final_order = sort_indices(&stream, final_less, U, sort_c.as<uint32_t>(), sort_d.as<uint32_t>());
+        } else R.final_order = ord_in;     // nothing moved: the stable sort would change nothing
+        if (device_gfa && U < 100000000u) {          // save_gfa (unitig_graph.rs:317-360): H, S, L and P lines rendered here
+            uint32_t* fin = R.final_order;
+            d_pos2.ensure((size_t)U * 4);
+            ac_launch("inverse_perm", &stream, InversePermBody{fin, d_pos2.as<uint32_t>()}, U);
+            const GfaView gv{fin, d_pos2.as<uint32_t>(), d_rec.as<UnitigRec>(), R.arena_src->as<char>(), d_depth.as<uint32_t>(), d_next_off.as<uint32_t>(), d_next.as<UStrand>()};
+            gfa_s_size.ensure(((size_t)U + 1) * 4); gfa_l_size.ensure(((size_t)U + 1) * 4); gfa_pieces.ensure(((size_t)U + 1) * 4);
+            const uint64_t steps = n_runs;
+            d_last.ensure(steps + 8); gfa_p_size.ensure((steps + 1) * 4);
+            ac_launch("gfa_size", &stream, GfaSizeBody{gv, U, gfa_s_size.as<uint32_t>(), gfa_l_size.as<uint32_t>()}, (uint64_t)U + 1);
+            ac_launch("gfa_chunk_count", &stream, GfaChunkCountBody{gv, U, gfa_pieces.as<uint32_t>()}, (uint64_t)U + 1);
+            ac_memset(d_last.p, 0, steps + 8, &stream);
+            ac_launch("path_last", &stream, PathLastBody{d_path_off.as<uint64_t>(), d_last.as<uint8_t>()}, n_seqs);
+            ac_launch("path_size", &stream, PathSizeBody{d_path.as<UStrand>(), d_pos2.as<uint32_t>(), d_last.as<uint8_t>(), steps, gfa_p_size.as<uint32_t>()}, steps + 1);
+            // four scans, their totals read back together (one round trip instead of four)
+            d_totals.ensure(64);
+            scan_keep_total(gfa_s_size.as<uint32_t>(), (uint64_t)U + 1, d_totals.as<uint32_t>() + 0);
+            scan_keep_total(gfa_l_size.as<uint32_t>(), (uint64_t)U + 1, d_totals.as<uint32_t>() + 1);
+            scan_keep_total(gfa_pieces.as<uint32_t>(), (uint64_t)U + 1, d_totals.as<uint32_t>() + 2);
+            scan_keep_total(gfa_p_size.as<uint32_t>(), steps + 1, d_totals.as<uint32_t>() + 3);
+            uint32_t tot[4];
+            ac_d2h(tot, d_totals.p, 16, &stream); ac_sync(&stream);
+            const uint64_t s_bytes = tot[0], l_bytes = tot[1], n_pieces = tot[2], p_list_bytes = tot[3];
+            char head[64]; const uint64_t head_bytes = (uint64_t)snprintf(head, sizeof head, "H\tVN:Z:1.0\tKM:i:%u\n", k);
+            if (path_wrap_total == 0 && n_seqs) throw std::runtime_error("set_path_line_texts() must precede a build that renders the GFA");
+            const uint64_t p_bytes = p_list_bytes + path_wrap_total;
+            R.gfa_bytes = head_bytes + s_bytes + l_bytes + p_bytes;
+            d_text.ensure(R.gfa_bytes + 64);
+            char* text = d_text.as<char>();
+            ac_h2d(text, head, head_bytes, &stream);       // `head` is on the stack: synchronised below before it goes out of scope (h2d from pageable memory is staged by the driver at call time)
+            ac_launch("gfa_segment", &stream, GfaSegmentBody{gv, gfa_s_size.as<uint32_t>(), text + head_bytes}, U);
+            ac_launch("gfa_sequence", &stream, GfaSequenceBody{gv, U, gfa_pieces.as<uint32_t>(), gfa_s_size.as<uint32_t>(), text + head_bytes}, n_pieces);
+            ac_launch("gfa_link", &stream, GfaLinkBody{gv, gfa_l_size.as<uint32_t>(), text + head_bytes + s_bytes}, U);
+            const PathLineView pv{d_path_off.as<uint64_t>(), n_seqs, gfa_p_size.as<uint32_t>(), d_wrap_off.as<uint64_t>(), d_pre_len.as<uint32_t>(), d_suf_len.as<uint32_t>(),
+                                  d_blob.as<char>(), d_blob_off.as<uint64_t>()};
+            char* p_text = text + head_bytes + s_bytes + l_bytes;
+            ac_launch("path_text", &stream, PathTextFullBody{d_path.as<UStrand>(), d_pos2.as<uint32_t>(), d_last.as<uint8_t>(), pv, p_text}, steps);
+            ac_launch("path_wrap", &stream, PathWrapBody{pv, p_text}, 2ull * n_seqs);
+            R.gfa_on_device = true;
         }
     }
-    DevBuf& arena_src = first_pass_done ? d_arena2 : d_arena;
-    mark(11);
+    mark(18);
+    R.hairpins_ready = true;
 
     // ---- results to the host (pinned) ----
     if (before_results && *before_results) (*before_results)();
-    const uint64_t arena_cap = arena_final + arena_final / 4 + (1u << 20);     // head room for relocations during repeat expansion
+    out.fused = fused; out.graph_fetched = false;
+    if (fused && !R.gfa_on_device) throw std::runtime_error("fused build: the device GFA writer did not run");
+    uint64_t d2h = 0;
+    if (R.gfa_on_device) {
+        h_text.ensure(R.gfa_bytes + 64);
+        ac_d2h(h_text.p, d_text.p, R.gfa_bytes, &stream); d2h += R.gfa_bytes;
+    }
+    uint32_t small[16];
+    ac_d2h(small, d_small.p, 64, &stream); ac_sync(&stream); d2h += 64;
+    out.links_single = (n_links - small[0]) / 2 + small[0];
+    out.length_before = n_slots_used;                      // every canonical k-mer lies in exactly one unitig and a trimmed unitig is as long as its chain
+    out.length_after = n_slots_used - R.bases_removed;
+    out.gfa_text = R.gfa_on_device ? h_text.as<char>() : nullptr; out.gfa_bytes = R.gfa_on_device ? R.gfa_bytes : 0;
+    out.n_unitigs = U; out.n_runs = n_runs; out.n_seqs = n_seqs; out.n_links = n_links;
+    out.h2d_bytes = total + (uint64_t)n_seqs * sizeof(SeqInfo);
+    out.d2h_bytes = d2h;
+    pending_keep_positions = keep_positions;
+    if (!fused) pull_graph(out, keep_positions);
+    else { mark(16); mark(12); arena_pending = true; }
+}
+
+// The graph arrays (unitig records, sequences, links, paths, work list state) into pinned host memory: at once in a plain build,
+// on request after a fused one.
+void DevicePipeline::Impl::pull_graph(PipelineResult& out, bool keep_positions) {
+    const uint32_t U = R.U; const uint64_t n_links = R.n_links, n_cands = R.n_cands; const uint32_t n_strands = R.n_strands;
+    const uint64_t arena_cap = R.arena_final + R.arena_final / 4 + (1u << 20);     // head room for relocations during repeat expansion
     h_rec.ensure((size_t)U * sizeof(UnitigRec)); h_depth.ensure((size_t)U * 4);
     h_arena.ensure(arena_cap); h_next_off.ensure(((size_t)n_strands + 1) * 4); h_prev_off.ensure(((size_t)n_strands + 1) * 4);
     h_next.ensure(n_links * 4 + 4); h_prev.ensure(n_links * 4 + 4); h_path.ensure(n_runs * 4 + 4); h_path_off.ensure(((size_t)n_seqs + 1) * 8);
@@ -2036,7 +2129,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     auto pull = [&](PinBuf& dst, DevBuf& src, size_t bytes) { if (bytes) ac_d2h(dst.p, src.p, bytes, &stream); d2h += bytes; };
     pull(h_rec, d_rec, (size_t)U * sizeof(UnitigRec)); pull(h_depth, d_depth, (size_t)U * 4);
     h_order.ensure((size_t)U * 4 + 4);
-    if (U) { ac_d2h(h_order.p, ord_in, (size_t)U * 4, &stream); d2h += (size_t)U * 4; }
+    if (U) { ac_d2h(h_order.p, R.order_built, (size_t)U * 4, &stream); d2h += (size_t)U * 4; }
     pull(h_next_off, d_next_off, ((size_t)n_strands + 1) * 4); pull(h_prev_off, d_prev_off, ((size_t)n_strands + 1) * 4);
     pull(h_next, d_next, n_links * 4); pull(h_prev, d_prev, n_links * 4); pull(h_path, d_path, n_runs * 4); pull(h_path_off, d_path_off, ((size_t)n_seqs + 1) * 8);
     if (keep_positions) {
@@ -2045,39 +2138,26 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     }
     h_cands.ensure((n_cands + 1) * sizeof(ExpandCandidate)); h_deps.ensure((size_t)U * sizeof(ExpandDeps) + 4); h_spec.ensure((n_cands + 1) * 4); h_fixed.ensure((size_t)U * 2 + 4);
     pull(h_cands, d_cands, n_cands * sizeof(ExpandCandidate)); pull(h_deps, d_deps, (size_t)U * sizeof(ExpandDeps)); pull(h_spec, d_spec, n_cands * 4);
-    if (U) { ac_d2h(h_fixed.p, fix_start, (size_t)U * 2, &stream); d2h += (size_t)U * 2; }
+    if (U) { ac_d2h(h_fixed.p, R.fix_start, (size_t)U * 2, &stream); d2h += (size_t)U * 2; }
     // The sequences (most of the bytes) go last: the caller gets the graph structure as soon as the small arrays have
     // landed and lists the repeat-expansion candidates while the arena is still on its way (complete() waits for it).
     mark(16);
-    pull(h_arena, arena_src, arena_final);
-    if (final_order) { h_order2.ensure((size_t)U * 4 + 4); ac_d2h(h_order2.p, final_order, (size_t)U * 4, &stream); d2h += (size_t)U * 4; }
-    uint64_t gfa_head = 0;
-    if (gfa_on_device) {      // [H line][S lines][L lines] land where the finished file will be read from; the host appends the P lines behind them
-        char head[64]; gfa_head = (uint64_t)snprintf(head, sizeof head, "H\tVN:Z:1.0\tKM:i:%u\n", k);
-        h_text.ensure(gfa_head + gfa_s_bytes + gfa_l_bytes + gfa_p_bytes + gfa_tail_bytes + 64);
-        memcpy(h_text.p, head, gfa_head);
-        ac_d2h((char*)h_text.p + gfa_head, d_text.p, gfa_s_bytes + gfa_l_bytes, &stream); d2h += gfa_s_bytes + gfa_l_bytes;
-        h_ptext.ensure(gfa_p_bytes + 64); h_pbound.ensure(((size_t)n_seqs + 1) * 8);
-        if (gfa_p_bytes) { ac_d2h(h_ptext.p, d_ptext.p, gfa_p_bytes, &stream); d2h += gfa_p_bytes; }
-        ac_d2h(h_pbound.p, d_pbound.p, ((size_t)n_seqs + 1) * 8, &stream); d2h += ((size_t)n_seqs + 1) * 8;
-    }
-    if (first_pass_done) {
+    pull(h_arena, *R.arena_src, R.arena_final);
+    if (R.final_order) { h_order2.ensure((size_t)U * 4 + 4); ac_d2h(h_order2.p, R.final_order, (size_t)U * 4, &stream); d2h += (size_t)U * 4; }
+    if (R.first_pass_done) {
         h_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); h_exhausted.ensure(n_cands + 8);
-        pull(h_dirty, d_dirty, ((n_cands + 63) / 64) * 8); pull(h_exhausted, d_exhausted, n_cands);
+        if (n_cands) { pull(h_dirty, d_dirty, ((n_cands + 63) / 64) * 8); pull(h_exhausted, d_exhausted, n_cands); }
     }
-    out.d2h_bytes = d2h + 2 * sizeof(unsigned long long) + 8 * sizeof(uint32_t);
-    out.h2d_bytes = total + (uint64_t)n_seqs * sizeof(SeqInfo);
+    out.d2h_bytes += d2h;
     mark(12);
     wait_mark(16);
-    out.n_unitigs = U; out.n_runs = n_runs; out.n_seqs = n_seqs; out.n_links = n_links;
+    out.graph_fetched = true;
     out.rec = h_rec.as<UnitigRec>(); out.depth = h_depth.as<uint32_t>(); out.order = h_order.as<uint32_t>();
     out.n_cands = n_cands; out.cands = h_cands.as<ExpandCandidate>(); out.deps = h_deps.as<ExpandDeps>(); out.spec_len = h_spec.as<uint32_t>();
     out.fixed_start = h_fixed.as<uint8_t>(); out.fixed_end = h_fixed.as<uint8_t>() + U;
-    out.arena = h_arena.as<char>(); out.arena_used = arena_final; out.arena_cap = arena_cap;
-    out.first_pass_done = first_pass_done; out.first_pass_total = first_pass_total; out.final_order = final_order ? h_order2.as<uint32_t>() : nullptr;
-    out.gfa_text = gfa_on_device ? h_text.as<char>() : nullptr; out.gfa_lines_bytes = gfa_head + gfa_s_bytes + gfa_l_bytes; out.gfa_cap = gfa_on_device ? h_text.cap : 0;
-    out.path_text = gfa_on_device ? h_ptext.as<char>() : nullptr; out.path_text_off = gfa_on_device ? h_pbound.as<uint64_t>() : nullptr;
-    out.dirty = first_pass_done ? h_dirty.as<uint64_t>() : nullptr; out.exhausted = first_pass_done ? h_exhausted.as<uint8_t>() : nullptr;
+    out.arena = h_arena.as<char>(); out.arena_used = R.arena_final; out.arena_cap = arena_cap;
+    out.first_pass_done = R.first_pass_done; out.first_pass_total = R.first_pass_total; out.final_order = R.final_order ? h_order2.as<uint32_t>() : nullptr;
+    out.dirty = R.first_pass_done ? h_dirty.as<uint64_t>() : nullptr; out.exhausted = R.first_pass_done ? h_exhausted.as<uint8_t>() : nullptr;
     out.next_off = h_next_off.as<uint32_t>(); out.next = h_next.as<UStrand>(); out.prev_off = h_prev_off.as<uint32_t>(); out.prev = h_prev.as<UStrand>();
     out.path_off = h_path_off.as<uint64_t>(); out.path = h_path.as<UStrand>();
     out.run_start = keep_positions ? h_run_start.as<uint64_t>() : nullptr; out.run_len = keep_positions ? h_run_len.as<uint32_t>() : nullptr;
@@ -2090,7 +2170,8 @@ void DevicePipeline::Impl::do_complete(PipelineResult& out) {
     arena_pending = false;
     out.t.h2d = between(0, 1); out.t.pack = between(2, 3); out.t.insert = between(15, 4); out.t.sample = between(3, 15); out.t.adjacency = between(13, 5);
     out.t.boundaries = between(5, 6); out.t.runs = between(14, 7); out.t.unitigs = between(7, 8); out.t.links = between(8, 9);
-    out.t.seed_sort = between(9, 10); out.t.emit = between(10, 11); out.t.d2h = between(11, 12); out.t.total = between(2, 4) + between(13, 6) + between(14, 12);
+    out.t.seed_sort = between(9, 10); out.t.emit = between(10, 11); out.t.simplify = between(11, 17); out.t.gfa = between(17, 18);
+    out.t.d2h = between(18, 12); out.t.total = between(2, 4) + between(13, 6) + between(14, 12);
 }
 
 #define AC_DISPATCH_W(fn, ...) switch (W) { case 1: fn<1>(__VA_ARGS__); break; case 2: fn<2>(__VA_ARGS__); break; \
@@ -2113,16 +2194,21 @@ void DevicePipeline::runs_local() {
 uint64_t DevicePipeline::local_runs() const { return impl->n_runs; }
 void DevicePipeline::export_runs(void* dst, uint64_t cap_records) { impl->set_device(); impl->do_export_runs(dst, cap_records); }
 void DevicePipeline::import_runs(const void* dev_ptr, uint64_t n) { impl->set_device(); impl->do_import_runs(dev_ptr, n); }
-void DevicePipeline::finish(PipelineResult& out, bool keep_positions) {
+void DevicePipeline::finish(PipelineResult& out, bool keep_positions, bool fused) {
     Impl& m = *impl; m.set_device(); const int W = m.W;
-    AC_DISPATCH_W(m.finish_w, out, keep_positions)
+    AC_DISPATCH_W(m.finish_w, out, keep_positions, fused)
+}
+void DevicePipeline::fetch_graph(PipelineResult& out, bool keep_positions) {
+    Impl& m = *impl; m.set_device();
+    if (m.stage < 2 || !out.fused) throw std::runtime_error("fetch_graph follows a fused build");
+    if (out.graph_fetched) return;
+    m.pull_graph(out, keep_positions);
 }
 
-void DevicePipeline::set_gfa_tail_bytes(uint64_t bytes) { impl->gfa_tail_bytes = bytes; }
 void DevicePipeline::complete(PipelineResult& out) { impl->set_device(); impl->do_complete(out); }
 
-void DevicePipeline::build(PipelineResult& out, bool keep_positions) {   // single GPU: every sequence is local, nothing to exchange
+void DevicePipeline::build(PipelineResult& out, bool keep_positions, bool fused) {   // single GPU: every sequence is local, nothing to exchange
     build_local(0, impl->n_seqs, false);
     runs_local();
-    finish(out, keep_positions);
+    finish(out, keep_positions, fused);
 }

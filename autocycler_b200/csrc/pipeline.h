@@ -15,7 +15,7 @@
 #define AC_SEQ_SLACK 32       // spare bytes on both sides of every unitig in the sequence arena
 
 struct PipelineTimings {      // milliseconds, CUDA events on the pipeline's stream (0 under emulation)
-    float h2d = 0, pack = 0, sample = 0, insert = 0, adjacency = 0, boundaries = 0, runs = 0, unitigs = 0, links = 0, seed_sort = 0, emit = 0, d2h = 0, total = 0;
+    float h2d = 0, pack = 0, sample = 0, insert = 0, adjacency = 0, boundaries = 0, runs = 0, unitigs = 0, links = 0, seed_sort = 0, emit = 0, simplify = 0, gfa = 0, d2h = 0, total = 0;
 };
 
 struct DeviceUnitig {
@@ -76,9 +76,13 @@ struct PipelineResult {
     bool first_pass_done = false; uint64_t first_pass_total = 0;    // bases it moved = the first expand_repeats() return value
     uint64_t* dirty = nullptr; uint8_t* exhausted = nullptr;        // the work list and the per-candidate state it left for pass 2
     uint32_t* final_order = nullptr;                                // [U] AC_DEVICE_SIMPLIFY: the numbering simplify_structure ends with (:38)
-    // AC_DEVICE_GFA: save_gfa's H, S and L lines as text (pinned, with room for the P lines behind them) and the unitig list of every path
-    char* gfa_text = nullptr; uint64_t gfa_lines_bytes = 0, gfa_cap = 0;
-    char* path_text = nullptr; uint64_t* path_text_off = nullptr;   // [S+1] offsets into path_text
+    // The finished file as the device rendered it (fused builds, or AC_DEVICE_SIMPLIFY + AC_DEVICE_GFA): H, S, L and P lines, pinned
+    char* gfa_text = nullptr; uint64_t gfa_bytes = 0;
+    // Fused build (DevicePipeline::build(..., fused = true)): simplify_structure and save_gfa ran on the device and only the text and
+    // these counts came back; the graph arrays below stay in HBM until fetch_graph() is asked for them.
+    bool fused = false, graph_fetched = true;
+    uint64_t links_single = 0;                                      // UnitigGraph::link_count().1 (unitig_graph.rs:478-507)
+    uint64_t length_before = 0, length_after = 0;                   // total_length() before / after simplify_structure
     char* arena = nullptr; uint64_t arena_used = 0, arena_cap = 0;
     uint32_t* next_off = nullptr;              // [2U+1] CSR over strands: forward_next / reverse_next in the reference's push order
     UStrand* next = nullptr;
@@ -102,14 +106,19 @@ public:
     ~DevicePipeline();
     // ascii: all padded, end-repaired forward strands concatenated (bytes in "ACGT."); seqs: their layout.
     void upload(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t k);
+    // What save_gfa prints around the unitig list of every path (unitig_graph.rs:352-360): "P\t<id>\t" before and
+    // "\t*\tLN:i:..\tFN:Z:..\tHD:Z:..\n" behind it, concatenated per sequence (prefix then suffix), with their lengths.  Call before upload().
+    void set_path_line_texts(const char* blob, const uint32_t* prefix_len, const uint32_t* suffix_len, uint32_t n_seqs);
     // build() / finish() return once the graph structure is in `out`; the sequence arena and the timings are only valid
     // after complete(), which the caller invokes when it has finished the host work that needs neither.
     void complete(PipelineResult& out);
     // called once per finish(), right before the pinned result buffers are (re)allocated and written (the caller may still be
     // cleaning the previous result out of the CPU caches on other threads)
     std::function<void()> before_results;
-    void set_gfa_tail_bytes(uint64_t bytes);   // AC_DEVICE_GFA: bytes the caller will append behind the device-written lines (its P lines minus the path lists)
-    void build(PipelineResult& out, bool keep_positions);   // kernels + D2H of the results (single GPU: all the stages below)
+    // kernels + D2H of the results (single GPU: all the stages below).  fused: build_kmer_graph, build_unitig_graph,
+    // simplify_unitig_graph and the text of save_gfa (compress.rs:42-47) in one device pipeline; only the text comes back.
+    void build(PipelineResult& out, bool keep_positions, bool fused = false);
+    void fetch_graph(PipelineResult& out, bool keep_positions);   // after a fused build: the graph arrays (simplified, renumbered) into pinned memory
     // Multi-GPU stages (one process per GPU; the collectives between them are done by the caller on device pointers):
     void build_local(uint32_t seq_lo, uint32_t seq_hi, bool multi);     // table over this rank's sequences [seq_lo, seq_hi)
     uint64_t count_entries();                                           // occupied slots of the local table
@@ -119,7 +128,7 @@ public:
     uint64_t local_runs() const;
     void export_runs(void* dst, uint64_t cap_records);                  // 32-byte RunRec records, ascending coordinate, into caller-owned device memory
     void import_runs(const void* dev_ptr, uint64_t n);                  // rank 0: every rank's records, concatenated in rank order
-    void finish(PipelineResult& out, bool keep_positions);              // unitigs, seeds, links, seed order, host-ready arrays
+    void finish(PipelineResult& out, bool keep_positions, bool fused = false);   // unitigs, seeds, links, seed order, host-ready arrays
     // needles: n_needles keys of h bases each (2 words per key, kmer_key.h layout for k = h), pairwise distinct.
     // renumber_unitigs for a graph the host has edited: sorts n keys by (length descending, first 8 bases ascending, index
     // ascending) and writes the sorted indices; the host settles the rare ties beyond the prefix.  `keys` may be any host memory.

@@ -57,6 +57,7 @@ typedef struct {
     uint64_t n_next;        /* total entries of forward_next + reverse_next */
     uint64_t n_sequences;
     uint64_t n_path_steps;  /* sum of path lengths over all sequences */
+    uint64_t length_before_simplify;   /* total_length() of the graph as built, before simplify_structure moved bases (compress.rs:164) */
 } ac_counts;
 
 /* Unitigs in the graph's current order (after ac_build: the order renumber_unitigs gives, numbers 1..U).
@@ -77,6 +78,7 @@ typedef struct {
 typedef struct {            /* milliseconds */
     float h2d, pack, insert, adjacency, boundaries, runs, unitigs, links, seed_sort, emit, d2h, device_total;
     float host_graph, host_simplify, host_gfa;
+    float sample, device_simplify, device_gfa;   /* sizing pass of the k-mer table; expand_repeats passes + renumbering and the GFA text when they run on the device */
     uint64_t insert_occurrences;   /* k-mer occurrences hashed by the insert kernel (forward windows; each feeds both strands) */
     uint64_t table_capacity, table_used;
     uint64_t kernel_launches;      /* cumulative launches of this library's kernels in the process */
@@ -97,6 +99,12 @@ int ac_clear_sequences(ac_handle* h);
 int ac_upload(ac_handle* h);            /* host -> HBM copy of the added sequences */
 int ac_build(ac_handle* h);             /* k-mer table, unitigs, links, renumber: the graph after from_kmer_graph */
 int ac_simplify(ac_handle* h);          /* simplify_structure */
+/* compress.rs:42-47 in one call — build_kmer_graph, build_unitig_graph, simplify_unitig_graph and the bytes save_gfa writes — as ONE
+ * device pipeline: repeat expansion, the closing renumbering and the H/S/L/P text are produced by kernels and only the text and the
+ * counts compress prints travel back.  Afterwards ac_gfa_* return the file, ac_counts_get the counts (length_before_simplify = the
+ * graph as built); the graph arrays stay in HBM and are fetched the first time a call needs them (ac_unitigs_copy, ac_path_copy,
+ * ac_merge_linear_paths, ...).  `autocycler compress`, ac_compress_dir and bench.py use this call. */
+int ac_compress(ac_handle* h);
 /* merge_linear_paths (graph_simplification.rs:315-371), what cluster/trim/resolve/clean first do to a loaded compress
  * graph (cluster.rs:804): chains of exclusively linked unitigs become one unitig numbered max+1, max+2, ...; merged
  * unitigs follow the surviving ones in the S lines.  use_paths != 0 keeps sequence-path ends fixed (the reference's

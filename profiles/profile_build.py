@@ -19,8 +19,7 @@ with tempfile.TemporaryDirectory() as d:
 
 def build():
     kg.upload()
-    g = api.UnitigGraph.from_kmer_graph(kg)
-    api.simplify_structure(g)
+    g = api.UnitigGraph.compress(kg)
     return len(g.gfa_view())
 
 

@@ -22,7 +22,28 @@ def run_library(lib, directory, k, positions=False):
     api.simplify_structure(graph)
     after = graph.counts()
     return dict(gfa=graph.gfa_bytes().decode(), before=before, after=after, seqs=seqs, count=count, graph=graph,
-                seed_state=seed_state)
+                seed_state=seed_state, kg=kg)
+
+
+def check_fused(kg, expected, st, seqs, k):
+    """ac_compress — compress.rs:42-47 as one device pipeline — on the same sequences: the same file, the counts compress prints, and
+    a graph (fetched from HBM on first use) that behaves like the one the step-by-step calls built."""
+    kg.upload()
+    g = api.UnitigGraph.compress(kg)
+    c = g.counts()                                         # before anything asks for the graph: the device's own counts
+    assert (c.n_kmers, c.n_unitigs, c.n_links, c.total_length, c.length_before_simplify) == \
+           (st.n_kmers, st.unitigs_after, st.links_after, st.length_after, st.length_before)
+    assert bytes(g.gfa_view()).decode() == expected, "fused build: GFA differs from the oracle"
+    assert g.distance_matrix_text() == o.pairwise_distances(expected)
+    c = g.counts()                                         # now from the adopted host graph
+    assert (c.n_unitigs, c.n_links, c.total_length) == (st.unitigs_after, st.links_after, st.length_after)
+    originals = [s.forward_seq[k // 2: len(s.forward_seq) - k // 2] for s in seqs]
+    assert [g.reconstruct_original_sequence(i) for i in range(len(originals))] == originals
+    api.simplify_structure(g)                              # nothing left to do
+    assert g.gfa_bytes().decode() == expected
+    api.merge_linear_paths(g, seqs)
+    assert g.gfa_bytes().decode() == o.gfa_merge_linear_paths(expected)
+    return g
 
 
 def check_case(lib, files, k, tmpdir=None):
@@ -59,6 +80,7 @@ def check_case(lib, files, k, tmpdir=None):
         assert [got["graph"].reconstruct_original_sequence(i) for i in range(len(originals))] == originals
         got["graph"].renumber_unitigs()     # trim.rs:266-268: merge, then renumber
         assert got["graph"].gfa_bytes().decode() == o.gfa_merge_linear_paths(expected, renumber=True), "renumbered merged GFA differs"
+        check_fused(got["kg"], expected, st, got["seqs"], k)
         return got
 
 
