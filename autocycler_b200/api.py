@@ -29,7 +29,8 @@ class AutocyclerGpuError(RuntimeError):
 
 
 class AcConfig(C.Structure):
-    _fields_ = [("k", C.c_uint32), ("device", C.c_int32), ("stream", C.c_void_p), ("keep_positions", C.c_uint32)]
+    _fields_ = [("k", C.c_uint32), ("device", C.c_int32), ("stream", C.c_void_p), ("keep_positions", C.c_uint32),
+                ("n_devices", C.c_int32), ("devices", C.POINTER(C.c_int32))]
 
 
 class AcCounts(C.Structure):
@@ -56,9 +57,9 @@ class AcTimings(C.Structure):
 
 EXPORTS = ["ac_last_error", "ac_version", "ac_create", "ac_destroy", "ac_add_sequence", "ac_clear_sequences", "ac_upload",
            "ac_build", "ac_compress", "ac_simplify", "ac_merge_linear_paths", "ac_renumber_unitigs", "ac_load_gfa", "ac_bind_host_to_device", "ac_decompress_gfa", "ac_pairwise_distances", "ac_distance_matrix_text", "ac_sequence_reconstruct", "ac_counts_get", "ac_unitigs_copy", "ac_path_copy", "ac_gfa_size", "ac_gfa_copy",
-           "ac_timings_get", "ac_compress_dir", "ac_load_sequences", "ac_sequence_get",
+           "ac_timings_get", "ac_compress_dir", "ac_compress_dir_devices", "ac_load_sequences", "ac_sequence_get",
            "ac_build_local", "ac_entries_count", "ac_entries_export", "ac_entries_merge", "ac_runs_local", "ac_runs_export",
-           "ac_runs_import", "ac_build_finish", "ac_gfa_data"]
+           "ac_runs_import", "ac_runs_import_padded", "ac_build_finish", "ac_compress_finish", "ac_gfa_data"]
 
 _libs = {}
 
@@ -96,6 +97,7 @@ def load_library(path=None):
     lib.ac_gfa_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.ac_timings_get.argtypes = [C.c_void_p, C.POINTER(AcTimings)]
     lib.ac_compress_dir.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32]
+    lib.ac_compress_dir_devices.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.c_int32, C.c_int32]
     lib.ac_load_sequences.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
     lib.ac_sequence_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint16), C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64,
                                     C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
@@ -106,7 +108,9 @@ def load_library(path=None):
     lib.ac_runs_local.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.ac_runs_export.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.ac_runs_import.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.ac_runs_import_padded.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
     lib.ac_build_finish.argtypes = [C.c_void_p]
+    lib.ac_compress_finish.argtypes = [C.c_void_p]
     lib.ac_gfa_data.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     _libs[path] = lib
     return lib
@@ -126,11 +130,13 @@ class Sequence:
 
 
 class _Handle:
-    def __init__(self, lib, k, device=0, stream=None, keep_positions=False):
+    def __init__(self, lib, k, device=0, stream=None, keep_positions=False, devices=None):
         self.lib = lib
         self.k = k
+        self.stream = stream or 0        # the cudaStream_t the library was told to run on (0: its own)
         self.ptr = C.c_void_p()
-        cfg = AcConfig(k, device, stream, 1 if keep_positions else 0)
+        devs = (C.c_int32 * len(devices))(*devices) if devices else None      # several GPUs driven by this one process (ac_config.n_devices)
+        cfg = AcConfig(k, device, stream, 1 if keep_positions else 0, len(devices) if devices else 0, devs)
         rc = lib.ac_create(C.byref(self.ptr), C.byref(cfg))
         if rc != AC_OK:
             raise AutocyclerGpuError(rc, lib.ac_last_error(None).decode())
@@ -155,9 +161,9 @@ class KmerGraph:
     """kmer_graph.rs:73-90.  The k-mers live in a hash table in HBM; `add_sequences` stages and uploads the strands,
     the table itself is built by UnitigGraph.from_kmer_graph (one fused device pipeline)."""
 
-    def __init__(self, k_size, device=0, stream=None, lib=None, keep_positions=False):
+    def __init__(self, k_size, device=0, stream=None, lib=None, keep_positions=False, devices=None):
         self.k_size = k_size
-        self._h = _Handle(lib or load_library(), k_size, device, stream, keep_positions)
+        self._h = _Handle(lib or load_library(), k_size, device, stream, keep_positions, devices)
         self.assembly_count = 0
         self.sequences = []
 
@@ -352,10 +358,11 @@ def load_sequences(assemblies_dir, k_size, max_contigs=25, threads=8, lib=None, 
     return kg, seqs, count.value
 
 
-def compress(assemblies_dir, autocycler_dir, k_size=51, max_contigs=25, threads=8, device=0, verbose=False, lib=None):
-    """compress.rs:32-50: writes <autocycler_dir>/input_assemblies.gfa and .yaml."""
+def compress(assemblies_dir, autocycler_dir, k_size=51, max_contigs=25, threads=8, device=0, verbose=False, lib=None, devices=None):
+    """compress.rs:32-50: writes <autocycler_dir>/input_assemblies.gfa and .yaml.  devices=[...]: sharded by file over several GPUs."""
     lib = lib or load_library()
-    rc = lib.ac_compress_dir(os.fsencode(assemblies_dir), os.fsencode(autocycler_dir), k_size, max_contigs, threads, device,
-                             1 if verbose else 0)
+    devs = list(devices) if devices else [device]
+    rc = lib.ac_compress_dir_devices(os.fsencode(assemblies_dir), os.fsencode(autocycler_dir), k_size, max_contigs, threads,
+                                     (C.c_int32 * len(devs))(*devs), len(devs), 1 if verbose else 0)
     if rc != AC_OK:
         raise AutocyclerGpuError(rc, lib.ac_last_error(None).decode())

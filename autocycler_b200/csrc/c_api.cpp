@@ -17,6 +17,7 @@
 #include "host_graph.h"
 #include "host_io.h"
 #include <immintrin.h>
+#include <functional>
 #include <thread>
 #include "pipeline.h"
 
@@ -50,7 +51,9 @@ struct ac_handle {
     std::vector<SeqInfo> infos;
     PinnedBytes ascii;
     LoadedInput loaded;                    // only when filled by ac_load_sequences (keeps the YAML details)
-    std::unique_ptr<DevicePipeline> pipe;
+    std::unique_ptr<DevicePipeline> pipe;                   // the pipeline that finishes the graph (devices[0])
+    std::vector<std::unique_ptr<DevicePipeline>> peers;     // ac_config.n_devices > 1: the pipelines of devices[1..]
+    std::vector<int32_t> devices;
     PipelineResult res;
     HostGraph graph;
     std::string gfa;
@@ -84,6 +87,40 @@ static int ok(const ac_handle* h) {      // a call that succeeded leaves no stal
         return set_error(h, code, m); } \
     catch (...) { return set_error(h, AC_EINVAL, "unknown error"); }
 
+// ac_config.n_devices > 1: the stages of SURVEY.md 8e driven from this one process.  The assemblies are sharded by file (contiguous
+// blocks in the order of ac_add_sequence = sorted file order); every device builds the table of its block, then folds the other
+// devices' deduplicated entries in by reading them where they lie (peer memory over NVLink: the merge kernel is the collective),
+// computes adjacency and its own occurrences; devices[0] reads all occurrences the same way and finishes the graph.
+static void build_on_devices(ac_handle* h, bool fused) {
+    std::vector<DevicePipeline*> pipes{h->pipe.get()};
+    for (auto& p : h->peers) pipes.push_back(p.get());
+    const size_t N = pipes.size();
+    std::vector<uint32_t> first_of_file;                     // index of the first sequence of every file
+    for (size_t i = 0; i < h->seqs.size(); ++i) if (i == 0 || h->seqs[i].filename != h->seqs[i - 1].filename) first_of_file.push_back((uint32_t)i);
+    first_of_file.push_back((uint32_t)h->seqs.size());
+    const size_t F = first_of_file.size() - 1;
+    auto on_all = [&](const std::function<void(size_t)>& work) {
+        std::vector<std::thread> th; std::vector<std::exception_ptr> err(N);
+        for (size_t d = 1; d < N; ++d) th.emplace_back([&, d] { try { work(d); } catch (...) { err[d] = std::current_exception(); } });
+        try { work(0); } catch (...) { err[0] = std::current_exception(); }
+        for (auto& t : th) t.join();
+        for (auto& e : err) if (e) std::rethrow_exception(e);
+    };
+    std::vector<const void*> entries(N), runs(N); std::vector<uint64_t> n_entries(N), n_runs(N);
+    on_all([&](size_t d) {
+        pipes[d]->build_local(first_of_file[F * d / N], first_of_file[F * (d + 1) / N], true);
+        entries[d] = pipes[d]->export_entries_own(&n_entries[d]);
+    });
+    on_all([&](size_t d) {
+        for (size_t r = 0; r < N; ++r) if (r != d && n_entries[r]) pipes[d]->merge_entries(entries[r], n_entries[r]);
+        pipes[d]->runs_local();
+        runs[d] = pipes[d]->export_runs_own(&n_runs[d]);
+    });
+    pipes[0]->import_runs_from(runs.data(), n_runs.data(), (uint32_t)N);
+    pipes[0]->finish(h->res, h->cfg.keep_positions != 0, fused);
+}
+
+
 extern "C" {
 
 const char* ac_last_error(const ac_handle* h) { return h ? h->err.c_str() : g_error.c_str(); }
@@ -106,7 +143,19 @@ int ac_create(ac_handle** out, const ac_config* cfg) {
         return set_error(nullptr, AC_EINVAL, "k-mer sizes above " + std::to_string(AC_MAX_K) + " are not supported by the GPU path (there is no CPU fallback)");
     h = new ac_handle;
     h->cfg = *cfg;
-    h->pipe.reset(new DevicePipeline(cfg->device, cfg->stream));
+    if (cfg->n_devices > 1) {
+        if (!cfg->devices) { delete h; return set_error(nullptr, AC_EINVAL, "ac_config.devices is null"); }
+        if (cfg->n_devices > 16) { delete h; return set_error(nullptr, AC_EINVAL, "at most 16 devices"); }
+        h->devices.assign(cfg->devices, cfg->devices + cfg->n_devices);
+        for (size_t a = 0; a < h->devices.size(); ++a) for (size_t b = 0; b < a; ++b) if (h->devices[a] == h->devices[b]) { delete h; return set_error(nullptr, AC_EINVAL, "ac_config.devices names a device twice"); }
+        h->cfg.device = h->devices[0]; h->cfg.stream = nullptr; h->cfg.devices = nullptr;
+        h->pipe.reset(new DevicePipeline(h->devices[0], nullptr));
+        for (size_t d = 1; d < h->devices.size(); ++d) h->peers.emplace_back(new DevicePipeline(h->devices[d], nullptr));
+        DevicePipeline::enable_peer_access(h->devices.data(), (int)h->devices.size());
+    } else {
+        h->cfg.n_devices = 1; h->cfg.devices = nullptr;
+        h->pipe.reset(new DevicePipeline(cfg->device, cfg->stream));
+    }
     *out = h;
     return ok(h);
     AC_GUARD_END(((delete h), (ac_handle*)nullptr))
@@ -163,6 +212,7 @@ int ac_upload(ac_handle* h) {
         h->pipe->set_path_line_texts(blob.data(), pre.data(), suf.data(), (uint32_t)h->seqs.size());
     }
     h->pipe->upload(h->ascii.p, h->ascii.size, h->infos.data(), (uint32_t)h->infos.size(), h->cfg.k);
+    for (auto& peer : h->peers) peer->upload(h->ascii.p, h->ascii.size, h->infos.data(), (uint32_t)h->infos.size(), h->cfg.k);      // every device holds every sequence (end k-mers of foreign occurrences are read from them)
     h->uploaded = true; h->built = h->gfa_ready = h->fused = h->graph_ready = false;
     return ok(h);
     AC_GUARD_END(h)
@@ -259,7 +309,8 @@ int ac_build(ac_handle* h) {
     if (h->built) flusher.start(h->res);
     {
         CallbackScope scope(h->pipe.get(), [&flusher] { flusher.join(); });      // cleared again on every way out, exceptions included
-        h->pipe->build(h->res, h->cfg.keep_positions != 0);
+        if (h->peers.empty()) h->pipe->build(h->res, h->cfg.keep_positions != 0);
+        else build_on_devices(h, false);
     }
     h->fused = false; h->graph_ready = false;
     adopt_result(h);
@@ -284,7 +335,8 @@ int ac_compress(ac_handle* h) {
     if (h->built && h->graph_ready) flusher.start(h->res);                     // the host only ever writes to the graph arrays, and only once they were fetched
     {
         CallbackScope scope(h->pipe.get(), [&flusher] { flusher.join(); });
-        h->pipe->build(h->res, h->cfg.keep_positions != 0, true);
+        if (h->peers.empty()) h->pipe->build(h->res, h->cfg.keep_positions != 0, true);
+        else build_on_devices(h, true);
     }
     h->pipe->complete(h->res);
     h->fused = true; h->graph_ready = false; h->built = true;
@@ -345,6 +397,37 @@ int ac_runs_import(ac_handle* h, const void* src, uint64_t n) {
     if (!h || !src) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     h->pipe->import_runs(src, n);
+    return ok(h);
+    AC_GUARD_END(h)
+}
+int ac_runs_import_padded(ac_handle* h, const void* src, uint64_t stride_records, const uint64_t* counts, uint32_t n_ranks) {
+    if (!h || !src || !counts) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    h->pipe->import_runs_padded(src, stride_records, counts, n_ranks);
+    return ok(h);
+    AC_GUARD_END(h)
+}
+// ac_compress on the rank that imported every rank's occurrences: simplify_structure and the GFA text on the device as well
+int ac_compress_finish(ac_handle* h) {
+    if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
+    AC_GUARD_BEGIN
+    static const bool host_tail = getenv("AC_HOST_SIMPLIFY") != nullptr;
+    if (host_tail) {
+        int rc = ac_build_finish(h); if (rc != AC_OK) return rc;
+        if ((rc = ac_simplify(h)) != AC_OK) return rc;
+        uint64_t n = 0; return ac_gfa_size(h, &n);
+    }
+    ResultFlusher flusher;
+    if (h->built && h->graph_ready) flusher.start(h->res);
+    {
+        CallbackScope scope(h->pipe.get(), [&flusher] { flusher.join(); });
+        h->pipe->finish(h->res, h->cfg.keep_positions != 0, true);
+    }
+    h->pipe->complete(h->res);
+    h->fused = true; h->graph_ready = false; h->built = true;
+    h->gfa_ptr = h->res.gfa_text; h->gfa_len = h->res.gfa_bytes; h->gfa_ready = true; h->device_text_ok = true;
+    record_timings(h);
+    h->t.host_graph = h->t.host_simplify = h->t.host_gfa = 0;
     return ok(h);
     AC_GUARD_END(h)
 }
@@ -719,7 +802,12 @@ int ac_sequence_reconstruct(const ac_handle* h, uint64_t index, char* out, uint6
 
 int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint32_t k, uint32_t max_contigs, uint32_t threads,
                     int32_t device, int32_t verbose) {
-    if (!assemblies_dir || !autocycler_dir) return set_error(nullptr, AC_EINVAL, "null argument");
+    return ac_compress_dir_devices(assemblies_dir, autocycler_dir, k, max_contigs, threads, &device, 1, verbose);
+}
+
+int ac_compress_dir_devices(const char* assemblies_dir, const char* autocycler_dir, uint32_t k, uint32_t max_contigs, uint32_t threads,
+                            const int32_t* devices, int32_t n_devices, int32_t verbose) {
+    if (!assemblies_dir || !autocycler_dir || !devices || n_devices < 1) return set_error(nullptr, AC_EINVAL, "null argument");
     ac_handle* h = nullptr;
     AC_GUARD_BEGIN
     // check_settings, compress.rs:53-62
@@ -733,7 +821,7 @@ int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint
     if (threads < 1) return set_error(nullptr, AC_EINPUT, "--threads cannot be less than 1");
     if (threads > 100) return set_error(nullptr, AC_EINPUT, "--threads cannot be greater than 100");
     if (k > AC_MAX_K) return set_error(nullptr, AC_EINPUT, "--kmer above " + std::to_string(AC_MAX_K) + " is not supported by this build of the GPU path (there is no CPU fallback)");
-    ac_config cfg{}; cfg.k = k; cfg.device = device; cfg.stream = nullptr; cfg.keep_positions = 0;
+    ac_config cfg{}; cfg.k = k; cfg.device = devices[0]; cfg.stream = nullptr; cfg.keep_positions = 0; cfg.n_devices = n_devices; cfg.devices = devices;
     int rc = ac_create(&h, &cfg);
     if (rc != AC_OK) return rc;
     std::unique_ptr<ac_handle, void (*)(ac_handle*)> guard(h, ac_destroy);

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/autocycler_gpu.h"
 
@@ -16,7 +17,8 @@ static void usage() {
             "      --kmer <KMER>            K-mer size for De Bruijn graph [default: 51]\n"
             "      --max_contigs <N>        refuse to run if mean contigs per assembly exceeds this value [default: 25]\n"
             "  -t, --threads <THREADS>      Number of CPU threads (end repair) [default: 8]\n"
-            "      --device <ORDINAL>       CUDA device [default: 0]\n");
+            "      --device <ORDINAL>       CUDA device [default: 0]\n"
+            "      --devices <A,B,...>      several CUDA devices of this box: the assemblies are sharded by file over them\n");
 }
 
 // `autocycler decompress` (main.rs:150-162, decompress.rs:27-57)
@@ -45,6 +47,7 @@ int main(int argc, char** argv) {
     if (argc >= 2 && strcmp(argv[1], "decompress") == 0) return decompress_main(argc, argv);
     if (argc < 2 || strcmp(argv[1], "compress") != 0) { usage(); return 2; }
     std::string in, out; unsigned k = 51, max_contigs = 25, threads = 8; int device = 0;
+    std::vector<int32_t> devices;
     for (int i = 2; i < argc; ++i) {
         std::string a = argv[i];
         auto value = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "error: a value is required for '%s'\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -54,15 +57,17 @@ int main(int argc, char** argv) {
         else if (a == "--max_contigs") max_contigs = (unsigned)strtoul(value(), nullptr, 10);
         else if (a == "-t" || a == "--threads") threads = (unsigned)strtoul(value(), nullptr, 10);
         else if (a == "--device") device = atoi(value());
+        else if (a == "--devices") { devices.clear(); for (const char* q = value(); *q;) { devices.push_back((int32_t)strtol(q, (char**)&q, 10)); if (*q == ',') ++q; else if (*q) { fprintf(stderr, "error: --devices wants a comma-separated list of ordinals\n"); return 2; } } }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else { fprintf(stderr, "error: unexpected argument '%s'\n", a.c_str()); usage(); return 2; }
     }
     if (in.empty() || out.empty()) { usage(); return 2; }
     fprintf(stderr, "\nStarting autocycler compress (%s)\n\nSettings:\n  --assemblies_dir %s\n  --autocycler_dir %s\n  --kmer %u\n  --threads %u\n\n",
             ac_version(), in.c_str(), out.c_str(), k, threads);
-    const int node = ac_bind_host_to_device(device);   // stay on the GPU's socket; harmless when the topology cannot be read
-    if (node >= 0) fprintf(stderr, "host threads bound to NUMA node %d (device %d)\n\n", node, device);
-    int rc = ac_compress_dir(in.c_str(), out.c_str(), k, max_contigs, threads, device, 1);
+    if (devices.empty()) devices.push_back(device);
+    const int node = ac_bind_host_to_device(devices[0]);   // stay on the socket of the GPU that finishes the graph; harmless when the topology cannot be read
+    if (node >= 0) fprintf(stderr, "host threads bound to NUMA node %d (device %d)\n\n", node, devices[0]);
+    int rc = ac_compress_dir_devices(in.c_str(), out.c_str(), k, max_contigs, threads, devices.data(), (int32_t)devices.size(), 1);
     if (rc != AC_OK) { fprintf(stderr, "\nError: %s\n", ac_last_error(nullptr)); return 1; }
     return 0;
 }

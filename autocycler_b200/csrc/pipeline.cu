@@ -24,6 +24,7 @@ static unsigned long long g_ac_kernel_launches = 0;
 #define AC_NONE32 0xFFFFFFFFu
 #define AC_CHUNK 32            // windows per thread in the insert kernel
 #define AC_MINCHUNK 128        // windows per thread in the seed-k-mer kernel
+#define AC_MAX_RANKS 16         // ranks of one multi-GPU build (one box)
 #define AC_BOUND_STRIPES 64     // power of two: accumulators that every candidate adds to are striped
 
 // ------------------------------------------------------------------------------------------------
@@ -508,15 +509,18 @@ struct RunEndsLocalBody {
 struct RunExportBody {
     const uint64_t* run_start; const uint32_t* run_len; const uint32_t* run_hs; const uint32_t* run_ts; const Slot* slots; uint32_t gb; RunRec* out;
     AC_D void operator()(uint64_t r) const {
-        RunRec x; x.start = run_start[r]; x.len = run_len[r]; x.pad = 0;
-        x.head_rep = slot_gpos(slots[run_hs[r]], gb); x.tail_rep = slot_gpos(slots[run_ts[r]], gb);
+        RunRec x; x.start = (uint32_t)run_start[r]; x.len = run_len[r];
+        x.head_rep = (uint32_t)slot_gpos(slots[run_hs[r]], gb); x.tail_rep = (uint32_t)slot_gpos(slots[run_ts[r]], gb);
         out[r] = x;
     }
 };
 struct RunImportBody {
     const RunRec* in; const uint32_t* pos_slot; uint64_t* run_start; uint32_t* run_len; uint32_t* run_hs; uint32_t* run_ts;
+    uint32_t n_ranks; uint64_t first[AC_MAX_RANKS + 1]; const RunRec* src[AC_MAX_RANKS];     // n_ranks == 0: `in` is dense; else rank q's records [first[q], first[q+1]) start at src[q] (possibly a peer's memory)
     AC_D void operator()(uint64_t r) const {
-        const RunRec x = in[r];
+        const RunRec* from = in + r;
+        if (n_ranks) { uint32_t q = 0; while (q + 1 < n_ranks && first[q + 1] <= r) ++q; from = src[q] + (r - first[q]); }
+        const RunRec x = *from;
         run_start[r] = x.start; run_len[r] = x.len; run_hs[r] = pos_slot[x.head_rep]; run_ts[r] = pos_slot[x.tail_rep];
     }
 };
@@ -1588,6 +1592,8 @@ struct DevicePipeline::Impl {
     void do_export_entries(void* dst, uint64_t cap_records);
     void do_export_runs(void* dst, uint64_t cap_records);
     void do_import_runs(const void* dev_ptr, uint64_t n);
+    void do_import_runs_from(const void* const* ptrs, const uint64_t* counts, uint32_t n_ranks);
+    DevBuf own_entries, own_runs;
 };
 
 DevicePipeline::DevicePipeline(int device, void* stream) : impl(new Impl) {
@@ -1878,8 +1884,19 @@ void DevicePipeline::Impl::do_import_runs(const void* dev_ptr, uint64_t n) {
     if (stage < 2) throw std::runtime_error("runs_local must precede import_runs");
     n_runs = n;
     run_start.ensure(n_runs * sizeof(uint64_t)); run_len.ensure(n_runs * 4); run_hs.ensure(n_runs * 4); run_ts.ensure(n_runs * 4);
-    ac_launch("run_import", &stream, RunImportBody{(const RunRec*)dev_ptr, pos_slot.as<uint32_t>(), run_start.as<uint64_t>(), run_len.as<uint32_t>(),
-                                                   run_hs.as<uint32_t>(), run_ts.as<uint32_t>()}, n_runs);
+    RunImportBody body{(const RunRec*)dev_ptr, pos_slot.as<uint32_t>(), run_start.as<uint64_t>(), run_len.as<uint32_t>(), run_hs.as<uint32_t>(), run_ts.as<uint32_t>(), 0, {0}, {nullptr}};
+    ac_launch("run_import", &stream, body, n_runs);
+}
+
+void DevicePipeline::Impl::do_import_runs_from(const void* const* ptrs, const uint64_t* counts, uint32_t n_ranks) {
+    if (stage < 2) throw std::runtime_error("runs_local must precede import_runs");
+    if (n_ranks == 0 || n_ranks > AC_MAX_RANKS) throw std::runtime_error("import_runs: bad rank count");
+    RunImportBody body{nullptr, pos_slot.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, n_ranks, {0}, {nullptr}};
+    for (uint32_t q = 0; q < n_ranks; ++q) { body.first[q + 1] = body.first[q] + counts[q]; body.src[q] = (const RunRec*)ptrs[q]; }
+    n_runs = body.first[n_ranks];
+    run_start.ensure(n_runs * sizeof(uint64_t)); run_len.ensure(n_runs * 4); run_hs.ensure(n_runs * 4); run_ts.ensure(n_runs * 4);
+    body.run_start = run_start.as<uint64_t>(); body.run_len = run_len.as<uint32_t>(); body.run_hs = run_hs.as<uint32_t>(); body.run_ts = run_ts.as<uint32_t>();
+    ac_launch("run_import", &stream, body, n_runs);
 }
 
 // ---- stage 3: unitigs, seeds, links, seed order and the host-ready arrays (over every occurrence handed to it) ----
@@ -2194,6 +2211,45 @@ void DevicePipeline::runs_local() {
 uint64_t DevicePipeline::local_runs() const { return impl->n_runs; }
 void DevicePipeline::export_runs(void* dst, uint64_t cap_records) { impl->set_device(); impl->do_export_runs(dst, cap_records); }
 void DevicePipeline::import_runs(const void* dev_ptr, uint64_t n) { impl->set_device(); impl->do_import_runs(dev_ptr, n); }
+void DevicePipeline::import_runs_padded(const void* dev_ptr, uint64_t stride, const uint64_t* counts, uint32_t n_ranks) {
+    if (n_ranks == 0 || n_ranks > AC_MAX_RANKS) throw std::runtime_error("import_runs_padded: bad rank count");
+    const void* ptrs[AC_MAX_RANKS];
+    for (uint32_t q = 0; q < n_ranks; ++q) { if (counts[q] > stride) throw std::runtime_error("import_runs_padded: a rank holds more records than the stride"); ptrs[q] = (const char*)dev_ptr + (size_t)q * stride * sizeof(RunRec); }
+    import_runs_from(ptrs, counts, n_ranks);
+}
+void DevicePipeline::import_runs_from(const void* const* ptrs, const uint64_t* counts, uint32_t n_ranks) { impl->set_device(); impl->do_import_runs_from(ptrs, counts, n_ranks); }
+const void* DevicePipeline::export_entries_own(uint64_t* n) {
+    Impl& m = *impl; m.set_device();
+    const uint64_t count = m.do_count_entries();
+    m.own_entries.ensure((count + 1) * sizeof(SlotRec));
+    m.do_export_entries(m.own_entries.p, count);
+    *n = count;
+    return m.own_entries.p;
+}
+const void* DevicePipeline::export_runs_own(uint64_t* n) {
+    Impl& m = *impl; m.set_device();
+    m.own_runs.ensure((m.n_runs + 1) * sizeof(RunRec));
+    m.do_export_runs(m.own_runs.p, m.n_runs);
+    *n = m.n_runs;
+    return m.own_runs.p;
+}
+void DevicePipeline::enable_peer_access(const int* devices, int n) {
+#ifndef AC_EMULATE
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            if (a == b) continue;
+            int can = 0;
+            AC_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, devices[a], devices[b]));
+            if (!can) throw std::runtime_error("device " + std::to_string(devices[a]) + " cannot map the memory of device " + std::to_string(devices[b]) + " (no peer access)");
+            AC_CUDA_CHECK(cudaSetDevice(devices[a]));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) throw std::runtime_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+#else
+    (void)devices; (void)n;
+#endif
+}
 void DevicePipeline::finish(PipelineResult& out, bool keep_positions, bool fused) {
     Impl& m = *impl; m.set_device(); const int W = m.W;
     AC_DISPATCH_W(m.finish_w, out, keep_positions, fused)

@@ -30,7 +30,7 @@ struct DeviceUnitig {
 
 // One unitig occurrence in rank-independent terms (multi-GPU exchange): where it lies and the smallest occurrence
 // of its first and last k-mer.
-struct RunRec { uint64_t start; uint32_t len; uint32_t pad; uint64_t head_rep, tail_rep; };
+struct RunRec { uint32_t start, len, head_rep, tail_rep; };     // 16 bytes: coordinates fit 32 bits (inputs are limited to 2^32 - 2 padded bytes)
 
 // The mutable per-unitig state in one 32-byte record (one cache line touch per unitig during repeat expansion).
 struct UnitigRec {
@@ -126,8 +126,16 @@ public:
     void merge_entries(const void* dev_ptr, uint64_t n);                // fold another rank's records into the local table
     void runs_local();                                                  // adjacency + this rank's unitig occurrences
     uint64_t local_runs() const;
-    void export_runs(void* dst, uint64_t cap_records);                  // 32-byte RunRec records, ascending coordinate, into caller-owned device memory
+    void export_runs(void* dst, uint64_t cap_records);                  // 16-byte RunRec records, ascending coordinate, into caller-owned device memory
     void import_runs(const void* dev_ptr, uint64_t n);                  // rank 0: every rank's records, concatenated in rank order
+    // the same from the buffer a padded gather leaves behind: rank r's counts[r] records start at record r * stride
+    void import_runs_padded(const void* dev_ptr, uint64_t stride, const uint64_t* counts, uint32_t n_ranks);
+    // Several GPUs driven by ONE process (ac_config.n_devices): the exports stay in the exporting pipeline's HBM and the peers' kernels
+    // read them in place over NVLink (peer access), so the exchange needs no staging copy and no collective library.
+    static void enable_peer_access(const int* devices, int n);          // every device of the set can map every other one's memory
+    const void* export_entries_own(uint64_t* n);                        // compacted 16-byte entry records of the local table; valid until the next build
+    const void* export_runs_own(uint64_t* n);                           // this rank's 16-byte occurrence records
+    void import_runs_from(const void* const* ptrs, const uint64_t* counts, uint32_t n_ranks);   // rank q's records at ptrs[q] (peer memory)
     void finish(PipelineResult& out, bool keep_positions, bool fused = false);   // unitigs, seeds, links, seed order, host-ready arrays
     // needles: n_needles keys of h bases each (2 words per key, kmer_key.h layout for k = h), pairwise distinct.
     // renumber_unitigs for a graph the host has edited: sorts n keys by (length descending, first 8 bases ascending, index

@@ -213,11 +213,14 @@ def run_gpu(args):
         if world == 1:
             g = api.UnitigGraph.compress(kg)                 # compress.rs:42-47 in one call: k-mer graph -> unitig graph -> simplify -> GFA text
         else:
-            g = acdist.from_kmer_graph_distributed(kg, seq_lo, seq_hi, dev)
+            st = {}
+            g = acdist.compress_distributed(kg, seq_lo, seq_hi, dev, stats=st)      # the same, sharded: one all-gather of k-mer buckets, rank 0 finishes
+            exchange_stats.append(st)
             if g is None:
                 return None, None
-            api.simplify_structure(g)
         return g, g.gfa_view()
+
+    exchange_stats = []
 
     def barrier():
         torch.cuda.synchronize()
@@ -230,6 +233,7 @@ def run_gpu(args):
         step(True)
 
     def timed(upload):
+        exchange_stats.clear()
         ins, dev, launches0 = [], [], kg_launches()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -242,16 +246,18 @@ def run_gpu(args):
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
+        for st in exchange_stats:
+            acdist.finish_stats(st)
         if world > 1:
             tt = torch.tensor([ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
-        return ms, ins, dev, last, kg_launches() - launches0
+        return ms, ins, dev, last, kg_launches() - launches0, list(exchange_stats)
 
     def kg_launches():
         t = api.AcTimings(); lib.ac_timings_get(kg._h.ptr, t); return t.kernel_launches
 
     sampler = ClockSampler(local); sampler.start()
-    ms_res, ins_ms, dev_t, last, launches = timed(upload=False)      # inputs resident in HBM
-    ms_e2e, _, _, last2, _ = timed(upload=True)                      # host buffers -> GFA bytes on the host
+    ms_res, ins_ms, dev_t, last, launches, xstats = timed(upload=False)      # inputs resident in HBM
+    ms_e2e, _, _, last2, _, _ = timed(upload=True)                           # host buffers -> GFA bytes on the host
     clocks = sampler.stop()
 
     g, gfa, t = last
@@ -281,7 +287,7 @@ def run_gpu(args):
         "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic (splitmix64 genomes, SURVEY.md §8d)",
         "config": {"workload": WORKLOAD, "k": K, "input_bases": n_bases, "sequences": len(seqs),
-                   "exchange": None if world == 1 else "all-gather of deduplicated k-mer entries (16 B each) over NCCL, then gather of unitig occurrences to rank 0",
+                   "exchange": None if world == 1 else "all-gather of deduplicated k-mer entries (16 B each) over NCCL, then gather of unitig occurrences (16 B each) to rank 0",
                    "l2": "working set per step (table %.0f MB + per-position arrays) exceeds the 126 MB L2 and is re-initialised every step" % (t.table_capacity * 16 / 1e6),
                    "gfa_bytes": len(gfa), "unitigs": int(g.counts().n_unitigs), "numa_node": numa_node},
         "e2e": {"value": round(e2e, 3), "unit": "Mbp/s", "ms_per_step": round(ms_e2e / args.steps, 3),
@@ -296,6 +302,12 @@ def run_gpu(args):
         "stage_ms": {k2: round(mean(k2), 3) for k2 in ("pack", "sample", "insert", "adjacency", "boundaries", "runs", "unitigs", "links", "seed_sort", "emit", "device_simplify", "device_gfa", "d2h", "device_total",
                                                         "host_graph", "host_simplify", "host_gfa")},
     }
+    if world > 1 and xstats:       # rank 0's view of the sharded stages: where the step goes when it does not scale
+        keys = [k2 for k2 in xstats[0] if k2.endswith("_ms")]
+        out["stage_ms"].update({k2: round(sum(st[k2] for st in xstats) / len(xstats), 3) for k2 in keys})
+        out["exchange"] = {k2: int(xstats[-1][k2]) for k2 in xstats[-1] if not k2.endswith("_ms")}
+        tail = {k2: v for k2, v in out["stage_ms"].items() if k2 in ("unitigs", "links", "seed_sort", "emit", "device_simplify", "device_gfa", "d2h")}
+        out["limiting_stage"] = max(tail, key=tail.get) + " (rank 0 finishes the union graph alone)"
     if rank == 0:
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sample_replicon=600_000)

@@ -45,6 +45,8 @@ typedef struct {
     int32_t device;         /* CUDA device ordinal */
     void* stream;           /* cudaStream_t to run on, or NULL for a private stream */
     uint32_t keep_positions;/* non-zero: ac_unitigs_copy can return full forward/reverse position lists */
+    int32_t n_devices;      /* > 1: this ONE process drives several GPUs: the assemblies are sharded by file over */
+    const int32_t* devices; /* devices[0..n_devices) (devices[0] finishes the graph; `device` and `stream` are ignored); 0/1: one GPU, `device` */
 } ac_config;
 
 typedef struct {
@@ -118,7 +120,9 @@ int ac_renumber_unitigs(ac_handle* h);
  * NCCL) moves the exported records between the processes.  Buffers are device memory on the handle's device.
  *   ac_build_local -> ac_entries_count/export -> [all-gather] -> ac_entries_merge (every other rank's records)
  *   -> ac_runs_local -> ac_runs_export -> [gather to rank 0] -> rank 0: ac_runs_import (all ranks, rank order) -> ac_build_finish
- * Records are opaque: 16 bytes per k-mer entry, 32 bytes per unitig occurrence. */
+ * Records are opaque: 16 bytes per k-mer entry, 16 bytes per unitig occurrence.  ac_runs_import_padded reads the buffer a padded
+ * gather leaves behind (rank r's counts[r] records start at record r * stride_records); ac_compress_finish is ac_compress for the
+ * importing rank (simplify_structure and the GFA text on the device as well). */
 int ac_build_local(ac_handle* h, uint32_t seq_lo, uint32_t seq_hi, uint32_t multi);
 int ac_entries_count(ac_handle* h, uint64_t* n);
 int ac_entries_export(ac_handle* h, void* dst, uint64_t cap_records);
@@ -126,7 +130,9 @@ int ac_entries_merge(ac_handle* h, const void* src, uint64_t n);
 int ac_runs_local(ac_handle* h, uint64_t* n_runs);
 int ac_runs_export(ac_handle* h, void* dst, uint64_t cap_records);
 int ac_runs_import(ac_handle* h, const void* src, uint64_t n);
+int ac_runs_import_padded(ac_handle* h, const void* src, uint64_t stride_records, const uint64_t* counts, uint32_t n_ranks);
 int ac_build_finish(ac_handle* h);      /* on the rank that imported the runs: the graph after from_kmer_graph */
+int ac_compress_finish(ac_handle* h);
 int ac_counts_get(const ac_handle* h, ac_counts* out);
 int ac_unitigs_copy(const ac_handle* h, ac_unitigs* out);
 int ac_path_copy(const ac_handle* h, uint64_t seq_index, int32_t* out, uint64_t cap, uint64_t* n);  /* get_unitig_path_for_sequence_i32 */
@@ -136,9 +142,13 @@ int ac_gfa_data(ac_handle* h, const char** data, uint64_t* n_bytes);   /* the sa
 int ac_timings_get(const ac_handle* h, ac_timings* out);
 
 /* `autocycler compress -i assemblies_dir -a autocycler_dir --kmer k --max_contigs m -t threads`
- * (main.rs:126-147, compress.rs:32-50): writes input_assemblies.gfa and input_assemblies.yaml. */
+ * (main.rs:126-147, compress.rs:32-50): writes input_assemblies.gfa and input_assemblies.yaml.
+ * ac_compress_dir_devices is the same on several GPUs of one box (`autocycler compress --devices 0,1,...`): the assemblies are
+ * sharded by file, one contiguous block of files per device, the k-mer buckets are read across NVLink by the peers' merge kernels. */
 int ac_compress_dir(const char* assemblies_dir, const char* autocycler_dir, uint32_t k, uint32_t max_contigs,
                     uint32_t threads, int32_t device, int32_t verbose);
+int ac_compress_dir_devices(const char* assemblies_dir, const char* autocycler_dir, uint32_t k, uint32_t max_contigs,
+                            uint32_t threads, const int32_t* devices, int32_t n_devices, int32_t verbose);
 
 /* Host-side stage A of compress (compress.rs:98-133): directory scan, FASTA load, padding, end repair.
  * Fills a handle created with the same k, ready for ac_upload.  Returns the number of assemblies. */

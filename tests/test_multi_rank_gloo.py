@@ -38,14 +38,19 @@ for ci, (files, k) in enumerate(todo):
     lo, hi = acdist.shard_bounds(len(seqs), rank, world)
     if hi == lo:            # more ranks than sequences: give the empty ranks nothing to do but still take part
         lo, hi = 0, 0
-    g = acdist.from_kmer_graph_distributed(kg, lo, hi, "cpu") if hi > lo or True else None
+    g = acdist.from_kmer_graph_distributed(kg, lo, hi, "cpu")
+    want = o.compress_seqs(oseqs, count, k)[0] if rank == 0 else None
     if rank == 0:
         api.simplify_structure(g)
         got = g.gfa_bytes().decode()
-        want = o.compress_seqs(oseqs, count, k)[0]
         if got != want:
             ok = False
             print("MISMATCH case", ci, "k", k, flush=True)
+    kg.upload()
+    g = acdist.compress_distributed(kg, lo, hi, "cpu")          # the fused form: expansion, renumbering and text on rank 0's device
+    if rank == 0 and bytes(g.gfa_view()).decode() != want:
+        ok = False
+        print("MISMATCH (fused) case", ci, "k", k, flush=True)
 dist.barrier()
 if rank == 0:
     print("RESULT", "OK" if ok else "FAIL", flush=True)

@@ -316,3 +316,31 @@ def test_kmer_depth_beyond_16_bits_takes_the_side_counts(emu):
     assert got is not None
     depths = sorted(u["depth"] for u in got["graph"].unitigs())
     assert depths[-1] > 49151
+
+
+@pytest.mark.parametrize("n_devices", [2, 3, 5])
+def test_several_devices_in_one_process(emu, tmp_path, n_devices):
+    """ac_config.n_devices > 1: one process, one pipeline per device, the assemblies sharded by file, the peers' exports read in place
+    (peer memory on the GPU box, plain memory under emulation).  Same bytes as the oracle, through the handle API and through
+    ac_compress_dir_devices (`autocycler compress --devices`)."""
+    for seed, k in [(31, 9), (32, 31), (33, 51), (34, 91)]:
+        files = cases.random_case(7000 * k + seed, k)
+        d = str(tmp_path / f"in{seed}"); cases.write_case(files, d)
+        try:
+            expected, yaml, st = o.compress_dir(d, k)
+        except o.OracleError:
+            continue
+        count, oseqs = o.load_sequences(d, k)
+        seqs = [api.Sequence(t[0], t[4], t[1], t[2], t[3]) for t in oseqs]
+        kg = api.KmerGraph(k, lib=emu, devices=list(range(n_devices)))
+        kg.add_sequences(seqs, count)
+        g = api.UnitigGraph.compress(kg)
+        assert bytes(g.gfa_view()).decode() == expected
+        kg.upload()
+        g = api.UnitigGraph.from_kmer_graph(kg)                       # the step-by-step form on the same devices
+        api.simplify_structure(g)
+        assert g.gfa_bytes().decode() == expected
+        out = str(tmp_path / f"out{seed}")
+        api.compress(d, out, k_size=max(k, 11) if k >= 11 else k, lib=emu, devices=list(range(n_devices))) if k >= 11 else None
+        if k >= 11:
+            assert open(os.path.join(out, "input_assemblies.gfa")).read() == expected and open(os.path.join(out, "input_assemblies.yaml")).read() == yaml
