@@ -28,6 +28,7 @@ template <class T> inline T ac_atomic_min(T* p, T v) { T old = *p; if (v < old) 
 template <class T> inline T ac_atomic_max(T* p, T v) { T old = *p; if (v > old) *p = v; return old; }
 template <class T> inline T ac_ld_volatile(const T* p) { return *p; }
 template <class T> inline T ac_ld_cg(const T* p) { return *p; }
+inline void ac_st_stream(uint32_t* p, uint32_t v) { *p = v; }
 inline void ac_ld_group(const uint64_t* p, uint64_t out[4]) { out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3]; }
 inline uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 inline uint32_t ac_popc(uint32_t v) { return (uint32_t)__builtin_popcount(v); }
@@ -42,6 +43,7 @@ inline void ac_h2d(void* d, const void* h, size_t bytes, AcStream*) { memcpy(d, 
 inline void ac_d2h(void* h, const void* d, size_t bytes, AcStream*) { memcpy(h, d, bytes); }
 inline void ac_copy_dd(void* dst, const void* src, size_t bytes, AcStream*) { memcpy(dst, src, bytes); }
 inline void ac_sync(AcStream*) {}
+inline void ac_l2_keep(AcStream*, void*, size_t) {}
 inline void* ac_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 inline void ac_host_free(void* p) { free(p); }
 
@@ -53,7 +55,7 @@ template <class Body> inline void ac_launch(const char*, AcStream*, const Body& 
 // Cooperative launch: body(thread, n_threads, sync) walks its items with stride n_threads and may call sync() — a barrier over the
 // whole grid — between phases.  Emulated by one thread.
 struct AcGridSync { void operator()() const {} };
-template <class Body> inline void ac_launch_coop(const char*, AcStream*, const Body& body, uint64_t) { AcGridSync sync; body(0, 1, sync); }
+template <class Body> inline void ac_launch_coop(const char*, AcStream*, const Body& body, uint64_t, uint64_t = 256) { AcGridSync sync; body(0, 1, sync); }
 
 #else
 // ------------------------------------------------------------------------------------------------
@@ -88,6 +90,7 @@ AC_D uint64_t ac_ld_cg(const uint64_t* p) { return (uint64_t)__ldcg(reinterpret_
 AC_D void ac_ld_group(const uint64_t* p, uint64_t out[4]) {
     asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(out[0]), "=l"(out[1]), "=l"(out[2]), "=l"(out[3]) : "l"(p) : "memory");
 }
+AC_D void ac_st_stream(uint32_t* p, uint32_t v) { __stcs(p, v); }      // written once, read much later: evict first, leave the L2 to the table
 AC_D uint64_t ac_umul64hi(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 AC_D uint32_t ac_popc(uint32_t v) { return (uint32_t)__popc(v); }
 AC_D int ac_ctz(uint32_t v) { return __ffs((int)v) - 1; }
@@ -104,6 +107,28 @@ inline void ac_h2d(void* d, const void* h, size_t bytes, AcStream* st) { AC_CUDA
 inline void ac_d2h(void* h, const void* d, size_t bytes, AcStream* st) { AC_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st->s)); }
 inline void ac_copy_dd(void* dst, const void* src, size_t bytes, AcStream* st) { AC_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st->s)); }
 inline void ac_sync(AcStream* st) { AC_CUDA_CHECK(cudaStreamSynchronize(st->s)); }
+// Asks the L2 to keep [base, base + bytes) resident for the kernels that follow on the stream (the k-mer table while it is probed at
+// random): as much of it as the device lets a process pin, the rest of the range competes normally.  bytes == 0 ends the window.
+inline void ac_l2_keep(AcStream* st, void* base, size_t bytes) {
+    static int max_persist = -1, max_window = 0;
+    if (max_persist < 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+        if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[device] persisting L2 up to %d MB, window up to %d MB\n", max_persist >> 20, max_window >> 20);
+        cudaGetLastError();
+    }
+    if (max_persist <= 0 || max_window <= 0) return;
+    cudaStreamAttrValue v; memset(&v, 0, sizeof v);
+    const size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+    v.accessPolicyWindow.base_ptr = base; v.accessPolicyWindow.num_bytes = win;
+    v.accessPolicyWindow.hitRatio = win == 0 ? 0.f : (win <= (size_t)max_persist ? 1.f : (float)((double)max_persist / (double)win));
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    cudaStreamSetAttribute(st->s, cudaStreamAttributeAccessPolicyWindow, &v);
+    if (bytes == 0) cudaCtxResetPersistingL2Cache();
+    cudaGetLastError();
+}
 inline void* ac_host_alloc(size_t bytes) { void* p = nullptr; AC_CUDA_CHECK(cudaMallocHost(&p, bytes ? bytes : 1)); return p; }
 inline void ac_host_free(void* p) { if (p) cudaFreeHost(p); }
 
@@ -154,13 +179,14 @@ template <class Body> inline void ac_launch_occ(const char* name, AcStream* st, 
 
 // Cooperative launch (all CTAs co-resident): body(thread, n_threads, sync) walks its items with stride n_threads and may call
 // sync() — a barrier over the whole grid — between phases, so that a chain of small dependent steps costs one launch instead of one
-// launch (and often one host round trip) per step.  `work` sizes the grid: no more CTAs than the items need, never more than fit.
+// launch (and often one host round trip) per step.  `work` / `per_block` sizes the grid — a barrier over few CTAs is cheap (a microsecond
+// or two against five to ten over 148), so steps with little work per phase ask for few — never more CTAs than fit.
 struct AcGridSync { __device__ __forceinline__ void operator()() const { cooperative_groups::this_grid().sync(); } };
 template <class Body> __global__ void __launch_bounds__(256) ac_coop_kernel(const Body body) {
     AcGridSync sync;
     body((uint64_t)blockIdx.x * blockDim.x + threadIdx.x, (uint64_t)gridDim.x * blockDim.x, sync);
 }
-template <class Body> inline void ac_launch_coop(const char* name, AcStream* st, const Body& body, uint64_t work) {
+template <class Body> inline void ac_launch_coop(const char* name, AcStream* st, const Body& body, uint64_t work, uint64_t per_block = 256) {
     static int resident = 0;                  // per kernel instantiation; one device per process in this library
     if (!resident) {
         int per_sm = 0, sms = 0, dev = 0;
@@ -170,7 +196,7 @@ template <class Body> inline void ac_launch_coop(const char* name, AcStream* st,
         resident = per_sm * sms;
         if (resident <= 0) throw std::runtime_error(std::string("cooperative launch ") + name + ": kernel does not fit");
     }
-    uint64_t want = (work + 255) / 256;
+    uint64_t want = (work + per_block - 1) / per_block;
     if (want < 1) want = 1;
     const uint64_t cap = resident < 148 ? (uint64_t)resident : 148;     // one CTA per SM is plenty for these small steps, and keeps the barrier cheap
     const unsigned blocks = (unsigned)(want < cap ? want : cap);

@@ -743,8 +743,9 @@ int ac_load_sequences(ac_handle* h, const char* dir, uint32_t max_contigs, uint3
     if (!h || !dir) return set_error(h, AC_EINVAL, "null argument");
     AC_GUARD_BEGIN
     ac_clear_sequences(h);
-    // end repair runs on the device unless the literals are too long for it (k > 127 is refused earlier anyway) or AC_HOST_END_REPAIR is set
-    LoadedInput in = load_sequences(dir, h->cfg.k, max_contigs, threads ? threads : 1, false, getenv("AC_HOST_END_REPAIR") ? nullptr : h->pipe.get());
+    // end repair runs on the device unless its k/2-base literals are longer than the scan kernel's two key words (k > 129) or AC_HOST_END_REPAIR is set
+    const bool device_repair = !getenv("AC_HOST_END_REPAIR") && h->cfg.k / 2 <= 64;
+    LoadedInput in = load_sequences(dir, h->cfg.k, max_contigs, threads ? threads : 1, false, device_repair ? h->pipe.get() : nullptr);
     for (size_t i = 0; i < in.seqs.size(); ++i) {
         int rc = ac_add_sequence(h, in.seqs[i].id, (const uint8_t*)in.padded[i].data(), in.padded[i].size(),
                                  in.seqs[i].filename.c_str(), in.seqs[i].contig_header.c_str());

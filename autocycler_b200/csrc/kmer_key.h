@@ -187,30 +187,35 @@ AC_HD uint32_t find_seq(const SeqInfo* __restrict__ seqs, uint32_t n, uint64_t g
     return lo;
 }
 
-// ---- table slot: ONE 64-bit word [ gpos:GB | dotted:1 | fingerprint:37-GB | count:16 | flags:10 ] --------------------------
+// ---- table slot: ONE 64-bit word [ gpos:GB | dotted:1 | fingerprint:33-GB | count:20 | flags:10 ] --------------------------
 // gpos   a pointer to one occurrence of the k-mer, like Kmer.pointer (kmer_graph.rs:26-33): keys never live in the table, equality is
 //        decided by fetching that occurrence from the packed sequence store (L2 resident).  GB = the bits the input's coordinates
-//        need (26 for BASELINE config 2, at most 32); what it leaves goes to the fingerprint (11 bits for config 2, 5 at 4 Gbp), so
-//        that almost no probe has to fetch an occurrence only to find another k-mer behind it.
-// count  Kmer::depth() (kmer_graph.rs:52-55), occurrences on both strands.  16 bits: an adder that finds 0xC000 or more raises the
-//        pipeline's count alarm and the build is repeated with the counts in a side array (`count_big`, 32 bits per slot)
+//        need (26 for BASELINE config 2, at most 32); what it leaves goes to the fingerprint (7 bits for config 2), which spares most
+//        probes the fetch of an occurrence that turns out to be another k-mer.
+// count  Kmer::depth() (kmer_graph.rs:52-55), occurrences on both strands, 20 bits.  Occurrences are added with fire-and-forget
+//        atomics (nobody waits for the old value); an adder whose LOADED copy of the slot already shows 2^19 or more raises the count
+//        alarm and the build is repeated with the counts in a side array (`count_big`, 32 bits per slot).  The loaded copy lags the
+//        true count by at most the adds in flight — fewer than the 303,104 threads a B200 holds — so a count cannot pass from 2^19 to
+//        the wrap at 2^20 (524,288 more adds) without some adder loading a value of at least 2^19 on the way: the alarm is exact.
 // flags  bit0 first(canonical) bit1 first(rc(canonical)) (kmer_graph.rs:57-60); bits 2..5: base b follows this k-mer somewhere in the
 //        input, bits 6..9: base b precedes it (canonical orientation; a lower bound on the node-centric degrees)
-// Eight bytes per slot (four slots per 32-byte sector): the table of BASELINE config 2 is about 100 MB and stays in the 126 MB L2.
+// Eight bytes per slot, four slots per 32-byte sector; the table of BASELINE config 2 is about 100 MB.
 typedef uint64_t Slot;
 #define AC_EMPTY_SLOT (~0ull)                 // gpos all ones is never a window start: GB is chosen so that total <= 2^GB - 1
 #define AC_SLOT_COUNT_SHIFT 10
+#define AC_SLOT_COUNT_BITS 20
 #define AC_SLOT_COUNT_ONE (1ull << AC_SLOT_COUNT_SHIFT)
-#define AC_SLOT_COUNT_ALARM 0xC000u
+#define AC_SLOT_COUNT_ALARM (1u << (AC_SLOT_COUNT_BITS - 1))
 #define AC_SLOT_FLAG_MASK 0x3FFull
-#define AC_SLOT_TAG_SHIFT 26
+#define AC_SLOT_TAG_SHIFT (AC_SLOT_COUNT_SHIFT + AC_SLOT_COUNT_BITS)
+#define AC_SLOT_TAG_BITS(gb) (64u - AC_SLOT_TAG_SHIFT - (gb))
 AC_HD uint32_t slot_gpos_bits(uint64_t total) { uint32_t gb = 8; while (gb < 32 && (total >> gb) != 0) ++gb; return gb; }
 AC_HD uint64_t slot_gpos(Slot s, uint32_t gb) { return s >> (64 - gb); }
-AC_HD uint32_t slot_tag(Slot s, uint32_t gb) { return (uint32_t)(s >> AC_SLOT_TAG_SHIFT) & ((1u << (38 - gb)) - 1u); }      // dotted bit + fingerprint
+AC_HD uint32_t slot_tag(Slot s, uint32_t gb) { return (uint32_t)(s >> AC_SLOT_TAG_SHIFT) & ((1u << AC_SLOT_TAG_BITS(gb)) - 1u); }      // dotted bit + fingerprint
 AC_HD bool slot_dotted(Slot s, uint32_t gb) { return (s >> (63 - gb)) & 1; }
-AC_HD uint32_t slot_count(Slot s) { return (uint32_t)(s >> AC_SLOT_COUNT_SHIFT) & 0xFFFFu; }
+AC_HD uint32_t slot_count(Slot s) { return (uint32_t)(s >> AC_SLOT_COUNT_SHIFT) & ((1u << AC_SLOT_COUNT_BITS) - 1u); }
 AC_HD uint32_t slot_flags(Slot s) { return (uint32_t)s & 0x3FFu; }
-AC_HD uint32_t make_tag(bool dotted, uint64_t hash, uint32_t gb) { return ((uint32_t)dotted << (37 - gb)) | ((uint32_t)hash & ((1u << (37 - gb)) - 1u)); }
+AC_HD uint32_t make_tag(bool dotted, uint64_t hash, uint32_t gb) { const uint32_t fb = AC_SLOT_TAG_BITS(gb) - 1u; return ((uint32_t)dotted << fb) | ((uint32_t)hash & ((1u << fb) - 1u)); }
 AC_HD Slot make_slot(uint64_t gpos, uint32_t tag, uint32_t count, uint32_t flags, uint32_t gb) {
     return (gpos << (64 - gb)) | ((uint64_t)tag << AC_SLOT_TAG_SHIFT) | ((uint64_t)count << AC_SLOT_COUNT_SHIFT) | flags;
 }

@@ -36,8 +36,9 @@ struct TableView {
     const uint64_t* packed;
     const SeqInfo* seqs;
     uint32_t n_seqs;
-    uint32_t* count_big;        // null, or (after a 16-bit count ran out) the depth of every slot in 32 bits; the slots' own count fields then stay 0
+    uint32_t* count_big;        // null, or (after a 20-bit count neared its end) the depth of every slot in 32 bits; the slots' own count fields then stay 0
     uint32_t gb;                // bits of a slot's occurrence pointer (slot_gpos_bits(total)); the fingerprint gets the rest
+    uint32_t alarm;             // a loaded slot count of this much or more raises the count alarm (AC_SLOT_COUNT_ALARM; tests lower it)
 };
 // Linear probing starts at the first slot of a 32-byte group of four (cap is a multiple of 4): one sector holds the whole first probe.
 AC_D uint64_t table_home(const TableView& t, uint64_t h) { return ac_umul64hi(h, t.cap >> 2) << 2; }
@@ -72,14 +73,12 @@ template <int W> AC_D uint32_t table_find(const TableView& t, const Key<W>& a, c
 // An occurrence (or, in the multi-GPU merge, another rank's `add` occurrences) of the k-mer that slot `slot` already holds: the
 // count goes up, missing flags are set, and with `track_min` the slot ends up pointing at the smallest occurrence (a name for the
 // k-mer that does not depend on the rank).  `seen` is the slot word the caller compared against.  counters[2] is the probe-limit
-// flag, counters[3] the 16-bit count alarm.
+// flag, counters[3] the count alarm.
 AC_D void slot_add_occurrence(const TableView& t, uint64_t slot, Slot seen, uint64_t g, uint32_t add, uint32_t flags, bool track_min, unsigned long long* counters) {
+    if (!t.count_big && slot_count(seen) + add >= t.alarm) counters[3] = 1;       // from the copy the caller loaded: see the slot layout in kmer_key.h
     if (!track_min) {
         if (t.count_big) ac_atomic_add(&t.count_big[slot], add);
-        else {
-            const Slot old = ac_atomic_add(&t.slots[slot], (uint64_t)add << AC_SLOT_COUNT_SHIFT);
-            if (slot_count(old) + add >= AC_SLOT_COUNT_ALARM) counters[3] = 1;
-        }
+        else ac_atomic_add(&t.slots[slot], (uint64_t)add << AC_SLOT_COUNT_SHIFT);            // result unused: a fire-and-forget reduction, nobody waits for the old value
         if (flags & ~slot_flags(seen)) ac_atomic_or(&t.slots[slot], (uint64_t)flags);     // usually there already (`seen` may be stale: then the OR is merely redundant)
         return;
     }
@@ -87,7 +86,7 @@ AC_D void slot_add_occurrence(const TableView& t, uint64_t slot, Slot seen, uint
     Slot old = seen;
     for (;;) {
         Slot nw = old | flags;
-        if (!t.count_big) { nw += (uint64_t)add << AC_SLOT_COUNT_SHIFT; if (slot_count(old) + add >= AC_SLOT_COUNT_ALARM) counters[3] = 1; }
+        if (!t.count_big) { nw += (uint64_t)add << AC_SLOT_COUNT_SHIFT; if (slot_count(old) + add >= t.alarm) counters[3] = 1; }
         if (g < slot_gpos(old, t.gb)) nw = slot_with_gpos(nw, g, t.gb);
         const Slot was = ac_atomic_cas(&t.slots[slot], old, nw);
         if (was == old) return;
@@ -191,11 +190,8 @@ template <int W> struct InsertBody {
         fwd.d = 0;
         rc = key_rc(fwd, p);
         const bool canon_fwd = key_is_canonical(fwd, p);
-        const uint32_t at = l + p.k;                       // the base after the window, counted from the block start: in word at >> 5 <= W
-        uint64_t xn = x[W];
-#pragma unroll
-        for (int j = 0; j < W; ++j) xn = ((at >> 5) == (uint32_t)j) ? x[j] : xn;
-        const uint32_t nb = (uint32_t)(xn >> (62 - 2 * (at & 31u))) & 3u;
+        // the base after the window is base k of the stream that starts at the window: 32(W-1) < k < 32W, so it lies in y[W-1]
+        const uint32_t nb = (uint32_t)(y[W - 1] >> (62 - 2 * (p.k & 31u))) & 3u;
         const uint32_t pb = l ? (uint32_t)(x[0] >> (64 - sh)) & 3u : (uint32_t)xp & 3u;
         const uint32_t out_b = canon_fwd ? nb : 3u - pb, in_b = canon_fwd ? pb : 3u - nb;
         flags = (1u << (AC_AUX_OBS_OUT_SHIFT + out_b)) | (1u << (AC_AUX_OBS_IN_SHIFT + in_b));
@@ -233,7 +229,7 @@ template <int W> struct InsertBody {
         const bool dotted = valid && fwd.d != 0;
         const uint32_t tag = make_tag(dotted, h, t.gb);
         const Slot mine = make_slot(g, tag, t.count_big ? 0u : 1u, flags, t.gb);
-        const uint32_t tag_mask = (1u << (38 - t.gb)) - 1u;
+        const uint32_t tag_mask = (1u << AC_SLOT_TAG_BITS(t.gb)) - 1u;
         uint64_t slot = table_home(t, h);
         bool done = !valid, failed = false;
         for (uint32_t probes = 0;;) {
@@ -288,7 +284,7 @@ template <int W> struct InsertBody {
             if (done) break;
 #endif
         }
-        if (valid && !failed && pos_slot) pos_slot[g] = (uint32_t)slot;
+        if (valid && !failed && pos_slot) ac_st_stream(&pos_slot[g], (uint32_t)slot);
     }
     AC_D void operator()(uint64_t i) const {
         const uint32_t g = g_first + (uint32_t)i, g0 = g & ~31u;
@@ -593,7 +589,7 @@ template <int W> struct MergeBody {
         const uint64_t h = key_hash(key_is_canonical(fwd, p) ? fwd : rc);
         const uint32_t tag = make_tag(dotted, h, t.gb);
         const Slot mine = make_slot(g, tag, t.count_big ? 0u : r.count, flags, t.gb);
-        if (!t.count_big && r.count >= AC_SLOT_COUNT_ALARM) counters[3] = 1;
+        if (!t.count_big && r.count >= t.alarm) counters[3] = 1;
         uint64_t slot = table_home(t, h);
         for (uint32_t probes = 0;; ++probes) {
             if (probes > 8192) { counters[2] = 1; return; }
@@ -707,8 +703,22 @@ template <int W> struct LinkBody {
 // seed k-mers.  The seeds are minima, so their leading bits are heavily skewed and bucketing on them does not work;
 // a bottom-up merge sort does: in every pass each element finds its place in the merged pair of runs with one binary
 // search in the sibling run (thread per element, U <= ~10^6 keys, all of them L2 resident).
+struct SortKey24 { uint64_t a, b; uint32_t c, d; };     // what a comparator stages in shared memory for the tile sort: 24 bytes per element
 struct SeedLess {
     const DeviceUnitig* unitigs; int W;
+    typedef SortKey24 Key;      // a: first key word, b: second (0 for W = 1), c: leading dots, d: trailing dots
+    AC_D Key load(uint32_t id) const {
+        const DeviceUnitig& x = unitigs[id];
+        Key k; k.a = x.min_w[0]; k.b = W > 1 ? x.min_w[1] : 0; k.c = x.min_d > 0 ? (uint32_t)x.min_d : 0u; k.d = x.min_d < 0 ? (uint32_t)-x.min_d : 0u;
+        return k;
+    }
+    AC_D bool less_keys(const Key& x, const Key& y, uint32_t ia, uint32_t ib) const {
+        if (x.c != y.c) return x.c > y.c;
+        if (x.a != y.a) return x.a < y.a;
+        if (x.b != y.b) return x.b < y.b;
+        if (W > 2) return (*this)(ia, ib);             // the first 128 key bits tie: the full comparison
+        return x.d > y.d;
+    }
     AC_D bool operator()(uint32_t a, uint32_t b) const {
         const DeviceUnitig& x = unitigs[a]; const DeviceUnitig& y = unitigs[b];
         const int lx = x.min_d > 0 ? x.min_d : 0, ly = y.min_d > 0 ? y.min_d : 0;
@@ -744,24 +754,29 @@ template <class Less> struct MergePassBody {
 // the index or an earlier position), so the result does not depend on how the sort is carried out.
 #define AC_SORT_TILE 2048
 #ifndef AC_EMULATE
-template <class Less> __global__ void __launch_bounds__(256) ac_tile_sort_kernel(const Less less, uint32_t n, uint32_t* __restrict__ idx) {
-    __shared__ uint32_t buf[2][AC_SORT_TILE];
+template <class Less> __global__ void __launch_bounds__(512) ac_tile_sort_kernel(const Less less, uint32_t n, uint32_t* __restrict__ idx) {
+    extern __shared__ unsigned char tile_smem[];
+    typename Less::Key* keys = reinterpret_cast<typename Less::Key*>(tile_smem);                    // [AC_SORT_TILE] the comparison keys, staged once
+    uint16_t* buf0 = reinterpret_cast<uint16_t*>(tile_smem + AC_SORT_TILE * sizeof(typename Less::Key));   // local ids, ping
+    uint16_t* buf1 = buf0 + AC_SORT_TILE;                                                            // pong
     const uint32_t base = blockIdx.x * AC_SORT_TILE, count = n - base < AC_SORT_TILE ? n - base : AC_SORT_TILE;
-    {   // leaves: 8 consecutive ids per thread
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) keys[i] = less.load(base + i);
+    __syncthreads();
+    auto before = [&](uint32_t x, uint32_t y) { return less.less_keys(keys[x], keys[y], base + x, base + y); };
+    if (threadIdx.x < AC_SORT_TILE / AC_SORT_LEAF) {   // leaves: 8 consecutive ids per thread
         const uint32_t a = threadIdx.x * AC_SORT_LEAF, b = a + AC_SORT_LEAF < count ? a + AC_SORT_LEAF : count;
-        uint32_t v[AC_SORT_LEAF];
+        uint16_t v[AC_SORT_LEAF];
         for (uint32_t x = a; x < b; ++x) {
             uint32_t y = x - a;
-            while (y > 0 && less(base + x, v[y - 1])) { v[y] = v[y - 1]; --y; }
-            v[y] = base + x;
+            while (y > 0 && before(x, v[y - 1])) { v[y] = v[y - 1]; --y; }
+            v[y] = (uint16_t)x;
         }
-        for (uint32_t x = a; x < b; ++x) buf[0][x] = v[x - a];
+        for (uint32_t x = a; x < b; ++x) buf0[x] = v[x - a];
     }
     __syncthreads();
-    int cur = 0;
-    for (uint32_t width = AC_SORT_LEAF; width < count; width *= 2, cur ^= 1) {
-        const uint32_t* in = buf[cur]; uint32_t* out = buf[cur ^ 1];
-        for (uint32_t i = threadIdx.x; i < count; i += 256) {
+    uint16_t* in = buf0; uint16_t* out = buf1;
+    for (uint32_t width = AC_SORT_LEAF; width < count; width *= 2) {
+        for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
             const uint32_t me = in[i];
             const uint32_t run = i / width, pair_start = (run & ~1u) * width, run_start = run * width;
             const bool left = !(run & 1u);
@@ -770,12 +785,13 @@ template <class Less> __global__ void __launch_bounds__(256) ac_tile_sort_kernel
             if (lo > count) lo = count;
             if (hi > count) hi = count;
             const uint32_t first = lo;
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const bool before = left ? less(in[mid], me) : !less(me, in[mid]); if (before) lo = mid + 1; else hi = mid; }
-            out[pair_start + (i - run_start) + (lo - first)] = me;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const bool bf = left ? before(in[mid], me) : !before(me, in[mid]); if (bf) lo = mid + 1; else hi = mid; }
+            out[pair_start + (i - run_start) + (lo - first)] = (uint16_t)me;
         }
         __syncthreads();
+        uint16_t* t = in; in = out; out = t;
     }
-    for (uint32_t i = threadIdx.x; i < count; i += 256) idx[base + i] = buf[cur][i];
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) idx[base + i] = base + in[i];
 }
 #endif
 template <class Less> struct TileSortBody {   // emulation form: any correct sort of the tile
@@ -794,7 +810,9 @@ template <class Less> static uint32_t* sort_indices(AcStream* stream, const Less
     if (n == 0) return a;
     const uint64_t tiles = ((uint64_t)n + AC_SORT_TILE - 1) / AC_SORT_TILE;
 #ifndef AC_EMULATE
-    ac_tile_sort_kernel<Less><<<(unsigned)tiles, 256, 0, stream->s>>>(less, n, a); ++g_ac_kernel_launches;
+    const size_t smem = AC_SORT_TILE * (sizeof(typename Less::Key) + 2 * sizeof(uint16_t));
+    AC_CUDA_CHECK(cudaFuncSetAttribute(ac_tile_sort_kernel<Less>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      // per device: cheap enough to repeat
+    ac_tile_sort_kernel<Less><<<(unsigned)tiles, 512, smem, stream->s>>>(less, n, a); ++g_ac_kernel_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("launch tile sort: ") + cudaGetErrorString(e));
 #else
@@ -821,6 +839,13 @@ struct NumberKeyBody {
 };
 struct NumberKeyLess {      // sort_number_keys: the part of renumber_unitigs' order that 16 bytes per unitig can decide
     const NumberKey* key;
+    typedef SortKey24 Key;
+    AC_D Key load(uint32_t id) const { Key k; k.a = key[id].prefix; k.b = 0; k.c = key[id].len; k.d = 0; return k; }
+    AC_D bool less_keys(const Key& x, const Key& y, uint32_t ia, uint32_t ib) const {
+        if (x.c != y.c) return x.c > y.c;
+        if (x.a != y.a) return x.a < y.a;
+        return ia < ib;
+    }
     AC_D bool operator()(uint32_t a, uint32_t b) const {
         if (key[a].len != key[b].len) return key[a].len > key[b].len;
         if (key[a].prefix != key[b].prefix) return key[a].prefix < key[b].prefix;
@@ -831,6 +856,15 @@ struct InversePermBody { const uint32_t* order; uint32_t* pos; AC_D void operato
 struct NumberLess {
     const UnitigRec* rec; const uint32_t* depth; const char* arena; const uint64_t* prefix;
     const uint32_t* pos;     // ties keep the order the unitigs are in: creation order (null) or their place in an earlier numbering
+    typedef SortKey24 Key;      // a: first 8 bases, b: position that settles ties, c: length, d: depth
+    AC_D Key load(uint32_t id) const { Key k; k.a = prefix[id]; k.b = pos ? pos[id] : id; k.c = rec[id].len; k.d = depth[id]; return k; }
+    AC_D bool less_keys(const Key& x, const Key& y, uint32_t ia, uint32_t ib) const {
+        if (x.c != y.c) return x.c > y.c;
+        if (x.a != y.a) return x.a < y.a;
+        if (x.c > 8) return (*this)(ia, ib);           // equal length and first 8 bases: the rest of the sequences decides first
+        if (x.d != y.d) return x.d > y.d;
+        return x.b < y.b;
+    }
     AC_D bool operator()(uint32_t a, uint32_t b) const {
         const uint32_t la = rec[a].len, lb = rec[b].len;
         if (la != lb) return la > lb;
@@ -1209,7 +1243,10 @@ struct ApplyPassCoopBody {
             sync();
         }
         for (uint64_t ci = tid; ci < n; ci += nt)
-            if (ac_ld_volatile(&apply.dirty[ci >> 6]) >> (ci & 63) & 1) ac_atomic_add(next_bound.bound + (ci & (AC_BOUND_STRIPES - 1)), next_bound.bound_of(ci));
+            if (ac_ld_volatile(&apply.dirty[ci >> 6]) >> (ci & 63) & 1) {
+                ac_atomic_add(next_bound.bound + (ci & (AC_BOUND_STRIPES - 1)), next_bound.bound_of(ci));
+                ac_atomic_add(next_bound.bound + AC_BOUND_STRIPES, 1ull);       // candidates left on the work list: sizes the next pass's grid
+            }
     }
 };
 
@@ -1558,10 +1595,11 @@ struct DevicePipeline::Impl {
     // pipeline state shared by the stages
     std::vector<SeqInfo> host_seqs;
     uint64_t cap = 0, n_windows = 0, n_runs = 0, g_begin = 0, g_end = 0, n_slots_used = 0, n_dotted = 0;
-    bool any_dotted = false, is_multi = false, big_counts = false;      // big_counts: depths live in count_big (a 16-bit count ran out)
+    bool any_dotted = false, is_multi = false, big_counts = false;      // big_counts: depths live in count_big (a 20-bit slot count neared its end)
     int stage = 0;
     DevBuf run_hs, run_ts, exp_flag, occ_list, bloom, needles, hits, count_big, interior8;
-    TableView table_view() { return TableView{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, big_counts ? count_big.as<uint32_t>() : nullptr, slot_gpos_bits(total)}; }
+    TableView table_view() { return TableView{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, big_counts ? count_big.as<uint32_t>() : nullptr, slot_gpos_bits(total), count_alarm()}; }
+    static uint32_t count_alarm() { static const uint32_t a = getenv("AC_COUNT_ALARM") ? (uint32_t)atoi(getenv("AC_COUNT_ALARM")) : AC_SLOT_COUNT_ALARM; return a; }      // test hook: a lower threshold
     void set_device() {
 #ifndef AC_EMULATE
         AC_CUDA_CHECK(cudaSetDevice(device));
@@ -1637,7 +1675,7 @@ void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo*
 #endif
     if (k < 3 || (k & 1) == 0) throw std::runtime_error("k must be odd and >= 3");
     const int W = (int)((2 * k + 63) / 64);
-    if (W > AC_MAX_W) throw std::runtime_error("k-mer sizes above 127 are not supported by the GPU path (no CPU fallback exists)");
+    if (W > AC_MAX_W) throw std::runtime_error("k-mer sizes above " + std::to_string(AC_MAX_K) + " are not supported by the GPU path (no CPU fallback exists)");
     if (total >= 0xFFFFFFF0ull) throw std::runtime_error("more than 2^32 padded input bytes are not supported");
     if (n_seqs == 0 || total == 0) throw std::runtime_error("no sequences");
     m.total = total; m.n_seqs = n_seqs; m.k = k; m.W = W; m.stage = 0;
@@ -1779,7 +1817,7 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
         slots.ensure(sample_cap * sizeof(Slot));
         ac_memset(slots.p, 0xFF, sample_cap * sizeof(Slot), &stream);
         ac_memset(counters.p, 0, sizeof hc, &stream);
-        const TableView sv{slots.as<Slot>(), sample_cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, nullptr, slot_gpos_bits(total)};
+        const TableView sv{slots.as<Slot>(), sample_cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, nullptr, slot_gpos_bits(total), AC_SLOT_COUNT_ALARM};
         const InsertBody<W> sample_ins{sv, p, interior8.as<uint8_t>(), 0, 0, (uint32_t)total, false, nullptr, counters.as<unsigned long long>(), true};
         ac_launch("sample", &stream, SampleBody<W>{sample_ins, (uint32_t)total}, ((total + 31) / 32 + 31) / 32 * 32);
         ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
@@ -1794,6 +1832,8 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
     for (int attempt = 0;; ++attempt) {
         if (attempt > 3) throw std::runtime_error("k-mer table build did not settle");
         slots.ensure(cap * sizeof(Slot));
+        static const bool l2_keep = getenv("AC_L2_PERSIST") != nullptr;
+        if (l2_keep) ac_l2_keep(&stream, slots.p, cap * sizeof(Slot));
         ac_memset(slots.p, 0xFF, cap * sizeof(Slot), &stream);               // AC_EMPTY_SLOT
         if (big_counts) { count_big.ensure(cap * 4); ac_memset(count_big.p, 0, cap * 4, &stream); }
         ac_memset(counters.p, 0, sizeof hc, &stream);
@@ -1804,7 +1844,7 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
         ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
         if (hc[2] && cap != safe_cap) { cap = safe_cap; continue; }         // the estimate was off (it is an estimate): start again with the safe size
         if (hc[2]) throw std::runtime_error("k-mer table overflow");
-        if (hc[3] && !big_counts) { big_counts = true; continue; }          // a k-mer with more than 49151 occurrences: counts move to the 32-bit side array
+        if (hc[3] && !big_counts) { big_counts = true; continue; }          // a k-mer with half a million occurrences: counts move to the 32-bit side array
         break;
     }
     n_dotted = hc[1];
@@ -1841,7 +1881,7 @@ template <int W> void DevicePipeline::Impl::runs_local_w() {
         unsigned long long hc[AC_N_COUNTERS];
         ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
         if (hc[2]) throw std::runtime_error("k-mer table overflow while merging");
-        if (hc[3] && !big_counts) throw std::runtime_error("a k-mer occurs more than 49151 times across the ranks: not supported by the multi-GPU exchange");
+        if (hc[3] && !big_counts) throw std::runtime_error("a k-mer occurs more than 524287 times across the ranks: not supported by the multi-GPU exchange");
         n_dotted = hc[1];
     }
     any_dotted = n_dotted != 0;
@@ -1939,6 +1979,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     link_count.ensure((size_t)n_unitigs * 2 * 4); links.ensure((size_t)n_unitigs * 2 * AC_MAX_LINKS * 4);
     ac_launch("links", &stream, LinkBody<W>{tv, p, any_dotted, unitigs.as<DeviceUnitig>(), pos_slot.as<uint32_t>(), slot_unitig.as<uint32_t>(),
                                             link_count.as<uint32_t>(), links.as<uint32_t>()}, (uint64_t)n_unitigs * 2);
+    if (getenv("AC_L2_PERSIST")) ac_l2_keep(&stream, nullptr, 0);        // the table has had its last random access
     mark(9);
 
     // ---- seed order: stable LSD radix sort of the unitigs by their seed k-mer ----
@@ -2015,17 +2056,18 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     mark(11);
     if (device_first_pass && n_cands == 0 && device_simplify) { R.first_pass_done = true; R.first_pass_total = 0; }     // nothing can shift: the loop ends at once
     if (device_first_pass && n_cands > 0) {
-        d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(32); d_counters64.ensure((2 * AC_BOUND_STRIPES + 3) * 8);
+        d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(32); d_counters64.ensure((2 * AC_BOUND_STRIPES + 4) * 8);
         d_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); d_exhausted.ensure(n_cands + 8);
         unsigned long long* c64 = d_counters64.as<unsigned long long>();         // [0] arena bump, [1] bases moved, [2..] bound stripes of this pass, then of the next, then bases the graph lost
-        unsigned long long* bound_now = c64 + 2; unsigned long long* bound_next = c64 + 2 + AC_BOUND_STRIPES; unsigned long long* removed = c64 + 2 + 2 * AC_BOUND_STRIPES;
+        unsigned long long* bound_now = c64 + 2; unsigned long long* bound_next = c64 + 2 + AC_BOUND_STRIPES; unsigned long long* removed = c64 + 3 + 2 * AC_BOUND_STRIPES;   // [2 + 2 stripes]: candidates left for the next pass
         ac_launch("level_pred", &stream, LevelPredBody{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_pred.as<int32_t>()}, n_cands);
         ac_memset(d_level.p, 0, n_cands * 4, &stream); ac_memset(d_flagmax.p, 0, 32, &stream);
-        ac_launch_coop("levels", &stream, LevelsCoopBody{d_pred.as<int32_t>(), d_level.as<uint32_t>(), d_flagmax.as<uint32_t>(), n_cands}, n_cands);
-        ac_memset(d_counters64.p, 0, (2 * AC_BOUND_STRIPES + 3) * 8, &stream);
+        ac_launch_coop("levels", &stream, LevelsCoopBody{d_pred.as<int32_t>(), d_level.as<uint32_t>(), d_flagmax.as<uint32_t>(), n_cands}, n_cands, 4096);
+        ac_memset(d_counters64.p, 0, (2 * AC_BOUND_STRIPES + 4) * 8, &stream);
         const RelocBoundBody bound_body{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_cand_at.as<int32_t>(), bound_now};
         ac_launch("reloc_bound", &stream, bound_body, n_cands);
-        uint32_t fm[8]; std::vector<unsigned long long> h64(2 * AC_BOUND_STRIPES + 3);
+        uint32_t fm[8]; std::vector<unsigned long long> h64(2 * AC_BOUND_STRIPES + 4);
+        uint64_t due = n_cands;                  // candidates the coming pass has to look at
         ac_d2h(fm, d_flagmax.p, 32, &stream); ac_d2h(h64.data(), c64, h64.size() * 8, &stream); ac_sync(&stream);
         if (fm[4]) throw std::runtime_error("candidate levels did not settle");
         unsigned long long bound = 0; for (int x = 0; x < AC_BOUND_STRIPES; ++x) bound += h64[2 + x];
@@ -2040,10 +2082,12 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
             const ApplyLevelBody apply{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_level.as<uint32_t>(), 0, d_spec.as<uint32_t>(),
                                        d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64, c64 + 1, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>(), pass == 1, removed};
             RelocBoundBody nb = bound_body; nb.bound = bound_next;
-            ac_launch_coop("apply_pass", &stream, ApplyPassCoopBody{apply, nb, n_cands, d_flagmax.as<uint32_t>() + 3}, n_cands);
+            // every pass walks all candidates at every level (a cheap test), so few CTAs when few are due: the barriers dominate then
+            ac_launch_coop("apply_pass", &stream, ApplyPassCoopBody{apply, nb, n_cands, d_flagmax.as<uint32_t>() + 3}, std::max<uint64_t>(due * 32, n_cands / 2), 512);
             ac_d2h(h64.data(), c64, h64.size() * 8, &stream); ac_sync(&stream);
             R.arena_final = h64[0]; R.first_pass_total = h64[1]; R.first_pass_done = true;      // what this expand_repeats() call returned
-            R.bases_removed = h64[2 + 2 * AC_BOUND_STRIPES]; R.any_moved = R.any_moved || h64[1] != 0;
+            R.bases_removed = h64[3 + 2 * AC_BOUND_STRIPES]; R.any_moved = R.any_moved || h64[1] != 0;
+            due = h64[2 + 2 * AC_BOUND_STRIPES];
             if (!device_simplify || R.first_pass_total == 0) break;
             if (pass > 100000) throw std::runtime_error("repeat expansion did not settle");
             bound = 0; for (int x = 0; x < AC_BOUND_STRIPES; ++x) bound += h64[2 + AC_BOUND_STRIPES + x];
@@ -2054,7 +2098,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
                 ac_copy_dd(d_arena3.p, d_arena2.p, R.arena_final, &stream); ac_sync(&stream);
                 std::swap(d_arena2.p, d_arena3.p); std::swap(d_arena2.cap, d_arena3.cap);
             }
-            ac_memset(c64 + 1, 0, (2 * AC_BOUND_STRIPES + 1) * 8, &stream);             // bases moved and both stripe sets; the running total of removed bases stays
+            ac_memset(c64 + 1, 0, (2 * AC_BOUND_STRIPES + 2) * 8, &stream);             // bases moved, both stripe sets, the work-list count; the running total of removed bases stays
         }
         R.arena_src = &d_arena2;
     }
@@ -2156,15 +2200,15 @@ void DevicePipeline::Impl::pull_graph(PipelineResult& out, bool keep_positions) 
     h_cands.ensure((n_cands + 1) * sizeof(ExpandCandidate)); h_deps.ensure((size_t)U * sizeof(ExpandDeps) + 4); h_spec.ensure((n_cands + 1) * 4); h_fixed.ensure((size_t)U * 2 + 4);
     pull(h_cands, d_cands, n_cands * sizeof(ExpandCandidate)); pull(h_deps, d_deps, (size_t)U * sizeof(ExpandDeps)); pull(h_spec, d_spec, n_cands * 4);
     if (U) { ac_d2h(h_fixed.p, R.fix_start, (size_t)U * 2, &stream); d2h += (size_t)U * 2; }
-    // The sequences (most of the bytes) go last: the caller gets the graph structure as soon as the small arrays have
-    // landed and lists the repeat-expansion candidates while the arena is still on its way (complete() waits for it).
-    mark(16);
-    pull(h_arena, *R.arena_src, R.arena_final);
     if (R.final_order) { h_order2.ensure((size_t)U * 4 + 4); ac_d2h(h_order2.p, R.final_order, (size_t)U * 4, &stream); d2h += (size_t)U * 4; }
     if (R.first_pass_done) {
         h_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); h_exhausted.ensure(n_cands + 8);
         if (n_cands) { pull(h_dirty, d_dirty, ((n_cands + 63) / 64) * 8); pull(h_exhausted, d_exhausted, n_cands); }
     }
+    // The sequences (most of the bytes) go last: the caller gets the graph structure as soon as everything else has
+    // landed and lists the repeat-expansion candidates while the arena is still on its way (complete() waits for it).
+    mark(16);
+    pull(h_arena, *R.arena_src, R.arena_final);
     out.d2h_bytes += d2h;
     mark(12);
     wait_mark(16);
@@ -2191,8 +2235,12 @@ void DevicePipeline::Impl::do_complete(PipelineResult& out) {
     out.t.d2h = between(18, 12); out.t.total = between(2, 4) + between(13, 6) + between(14, 12);
 }
 
-#define AC_DISPATCH_W(fn, ...) switch (W) { case 1: fn<1>(__VA_ARGS__); break; case 2: fn<2>(__VA_ARGS__); break; \
-    case 3: fn<3>(__VA_ARGS__); break; case 4: fn<4>(__VA_ARGS__); break; default: throw std::runtime_error("upload() must precede build()"); }
+// One instantiation of every k-mer kernel per key width: W = ceil(2k / 64) words, k up to 511.
+#define AC_W_CASE(fn, n, ...) case n: fn<n>(__VA_ARGS__); break;
+#define AC_DISPATCH_W(fn, ...) switch (W) { AC_W_CASE(fn, 1, __VA_ARGS__) AC_W_CASE(fn, 2, __VA_ARGS__) AC_W_CASE(fn, 3, __VA_ARGS__) AC_W_CASE(fn, 4, __VA_ARGS__) \
+    AC_W_CASE(fn, 5, __VA_ARGS__) AC_W_CASE(fn, 6, __VA_ARGS__) AC_W_CASE(fn, 7, __VA_ARGS__) AC_W_CASE(fn, 8, __VA_ARGS__) AC_W_CASE(fn, 9, __VA_ARGS__) AC_W_CASE(fn, 10, __VA_ARGS__) \
+    AC_W_CASE(fn, 11, __VA_ARGS__) AC_W_CASE(fn, 12, __VA_ARGS__) AC_W_CASE(fn, 13, __VA_ARGS__) AC_W_CASE(fn, 14, __VA_ARGS__) AC_W_CASE(fn, 15, __VA_ARGS__) AC_W_CASE(fn, 16, __VA_ARGS__) \
+    default: throw std::runtime_error("upload() must precede build()"); }
 
 void DevicePipeline::build_local(uint32_t seq_lo, uint32_t seq_hi, bool multi) {
     Impl& m = *impl; m.set_device(); const int W = m.W;

@@ -9,7 +9,7 @@
 
 #include "kmer_key.h"
 
-#define AC_MAX_W 4            // k <= 127
+#define AC_MAX_W 16           // 64-bit words of a k-mer key: k <= 511 (compress.rs:56-58 allows 11..501)
 #define AC_MAX_K (32 * AC_MAX_W - 1)
 #define AC_MAX_LINKS 5        // successors over the 5-letter alphabet (kmer_graph.rs:142)
 #define AC_SEQ_SLACK 32       // spare bytes on both sides of every unitig in the sequence arena

@@ -41,7 +41,7 @@ extern "C" {
 typedef struct ac_handle ac_handle;
 
 typedef struct {
-    uint32_t k;             /* odd; 3..127 on the GPU path (compress.rs:56-58 restricts the CLI to 11..501) */
+    uint32_t k;             /* odd; 3..511 (compress.rs:56-58 restricts the CLI to 11..501) */
     int32_t device;         /* CUDA device ordinal */
     void* stream;           /* cudaStream_t to run on, or NULL for a private stream */
     uint32_t keep_positions;/* non-zero: ac_unitigs_copy can return full forward/reverse position lists */

@@ -21,7 +21,7 @@ def emu():
     return api.load_library(path)
 
 
-@pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 31, 33, 51, 63, 65, 91, 127])
+@pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 31, 33, 51, 63, 65, 91, 127, 129, 159, 161, 255, 257, 319, 321, 401, 501, 511])
 def test_random_adversarial_cases(emu, k):
     for seed in range(40):
         check_case(emu, cases.random_case(1000 * k + seed, k), k)
@@ -71,11 +71,12 @@ def test_positions_match_oracle_seed_state(emu, tmp_path):
 
 
 def test_error_behaviour(emu, tmp_path):
-    # even k / tiny k are refused like compress.rs:56-58 (the C ABI accepts 3..127 odd)
+    # even k / tiny k are refused like compress.rs:56-58 (the C ABI accepts 3..511 odd; the CLI the reference's 11..501)
     with pytest.raises(api.AutocyclerGpuError):
         api.KmerGraph(10, lib=emu)
     with pytest.raises(api.AutocyclerGpuError):
-        api.KmerGraph(129, lib=emu)
+        api.KmerGraph(513, lib=emu)
+    api.KmerGraph(501, lib=emu)
     # non-ACGT input (sequence.rs:40-42)
     d = tmp_path / "bad"; d.mkdir(); (d / "a.fasta").write_text(">a\nACGTNNACGTACGTACGT\n")
     with pytest.raises(api.AutocyclerGpuError, match="non-ACGT"):
@@ -306,16 +307,21 @@ def test_simplify_with_more_than_six_exclusive_inputs(emu):
     assert any(u["seq"].startswith("C" + tail) or u["seq"].startswith(tail) for u in g.unitigs())      # the common end moved onto unitig 1
 
 
-def test_kmer_depth_beyond_16_bits_takes_the_side_counts(emu):
-    """A k-mer with more than 49151 occurrences (a 60 kbp homopolymer) trips the 16-bit count alarm of the 8-byte slots; the build repeats with 32-bit counts and still matches the oracle."""
-    import random
-    rnd = random.Random(7)
-    flank = lambda n: "".join(rnd.choice("ACGT") for _ in range(n))
-    files = [("a.fasta", [("c1", flank(300) + "A" * 60000 + flank(300))]), ("b.fasta", [("c2", flank(200) + "T" * 2000 + flank(200))])]
-    got = check_case(emu, files, 11)
-    assert got is not None
-    depths = sorted(u["depth"] for u in got["graph"].unitigs())
-    assert depths[-1] > 49151
+def test_kmer_depth_beyond_the_slot_count_takes_the_side_counts(tmp_path):
+    """A k-mer with more occurrences than the 20-bit slot count may show (2^19; the test lowers the alarm to 1000, AC_COUNT_ALARM) trips
+    the count alarm; the build repeats with 32-bit counts in the side array and still matches the oracle.  Runs in a child: the
+    threshold is read once per process."""
+    import subprocess
+    import sys
+    code = ("import sys, random; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from autocycler_b200 import api\nfrom parity_common import check_case\n"
+            "rnd = random.Random(7); flank = lambda n: ''.join(rnd.choice('ACGT') for _ in range(n))\n"
+            "files = [('a.fasta', [('c1', flank(300) + 'A' * 3000 + flank(300))]), ('b.fasta', [('c2', flank(200) + 'T' * 800 + flank(200))])]\n"
+            "got = check_case(api.load_library(%r), files, 11)\n"
+            "assert max(u['depth'] for u in got['graph'].unitigs()) > 1000\nprint('SIDE COUNTS OK')\n") % (os.path.join(ROOT, "tests"), ROOT, os.path.join(ROOT, "tests", "emu", "libautocycler_emu.so"))
+    for env in ({"AC_COUNT_ALARM": "1000"}, {"AC_BIG_COUNTS": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "SIDE COUNTS OK" in r.stdout, r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("n_devices", [2, 3, 5])

@@ -22,7 +22,7 @@ def lib():
     return lib
 
 
-@pytest.mark.parametrize("k", [3, 5, 9, 11, 31, 33, 51, 63, 65, 91, 127])
+@pytest.mark.parametrize("k", [3, 5, 9, 11, 31, 33, 51, 63, 65, 91, 127, 129, 255, 321, 501])
 def test_random_adversarial_cases(lib, k):
     for seed in range(10):
         check_case(lib, cases.random_case(1000 * k + seed, k), k)
