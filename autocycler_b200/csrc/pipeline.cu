@@ -1140,29 +1140,82 @@ struct LevelsCoopBody {
         }
     }
 };
+// A strand of bases read without materialising it (UnitigStrand::get_seq): byte i is base[i * step], complemented when comp.
+struct StrandCursor { const char* base; int32_t step; uint32_t comp; };
+AC_D char cursor_at(const StrandCursor& c, uint32_t i) { const char b = c.base[(int64_t)i * c.step]; return c.comp ? ac_complement(b) : b; }
+// The byte loops of a candidate, shared by the warp: the candidates of one level are scattered over the threads, so a warp seldom holds
+// more than one or two active lanes — and each of those would walk hundreds of bases alone.  Every lane calls these functions (active
+// or not); the lanes that own a job publish it and all 32 work through the jobs one after another.  Under emulation: plain loops.
+AC_D uint32_t warp_first_mismatch(bool have, const StrandCursor& x, const StrandCursor& y, uint32_t limit) {     // owner lanes get their own result
+#ifdef __CUDA_ARCH__
+    uint32_t mine = limit;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (unsigned jobs = __ballot_sync(0xFFFFFFFFu, have); jobs; jobs &= jobs - 1) {
+        const int o = __ffs((int)jobs) - 1;
+        StrandCursor a, b;
+        a.base = (const char*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)x.base, o); a.step = __shfl_sync(0xFFFFFFFFu, x.step, o); a.comp = __shfl_sync(0xFFFFFFFFu, x.comp, o);
+        b.base = (const char*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)y.base, o); b.step = __shfl_sync(0xFFFFFFFFu, y.step, o); b.comp = __shfl_sync(0xFFFFFFFFu, y.comp, o);
+        const uint32_t n = __shfl_sync(0xFFFFFFFFu, limit, o);
+        uint32_t found = n;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool differs = i < n && cursor_at(a, i) != cursor_at(b, i);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, differs);
+            if (m) { found = i0 + (uint32_t)(__ffs((int)m) - 1); break; }
+        }
+        if ((int)lane == o) mine = found;
+    }
+    return mine;
+#else
+    if (!have) return limit;
+    uint32_t m = 0;
+    while (m < limit && cursor_at(x, m) == cursor_at(y, m)) ++m;
+    return m;
+#endif
+}
+AC_D void warp_copy(bool have, char* dst, const StrandCursor& src, uint32_t n) {      // dst[i] = src[i] for i < n, for every lane that has a job
+#ifdef __CUDA_ARCH__
+    const uint32_t lane = threadIdx.x & 31u;
+    for (unsigned jobs = __ballot_sync(0xFFFFFFFFu, have); jobs; jobs &= jobs - 1) {
+        const int o = __ffs((int)jobs) - 1;
+        StrandCursor a;
+        a.base = (const char*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)src.base, o); a.step = __shfl_sync(0xFFFFFFFFu, src.step, o); a.comp = __shfl_sync(0xFFFFFFFFu, src.comp, o);
+        char* d = (char*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)dst, o);
+        const uint32_t m = __shfl_sync(0xFFFFFFFFu, n, o);
+        for (uint32_t i = lane; i < m; i += 32) d[i] = cursor_at(a, i);
+    }
+    __syncwarp();
+#else
+    if (have) for (uint32_t i = 0; i < n; ++i) dst[i] = cursor_at(src, i);
+#endif
+}
+
 struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates of one level; within a level no two of them share a unitig
     const ExpandCandidate* cands; const ExpandDeps* deps; const uint32_t* level; uint32_t this_level; const uint32_t* spec_len;
     UnitigRec* rec; char* arena; unsigned long long* arena_used; unsigned long long* total_shifted; uint64_t* dirty; uint8_t* exhausted;
     bool all_due;            // the first pass visits every candidate; later passes only those on the work list
     unsigned long long* total_removed;   // bases the graph lost: every source gives up the piece, the destination gains it once
-    AC_D char at(UStrand s, uint32_t side, uint32_t i) const {
+    // strand s read from the end that candidate side `side` compares: its last bases backwards (inputs, side 0) or its first bases (outputs)
+    AC_D StrandCursor cursor(UStrand s, uint32_t side) const {
         const UnitigRec& r = rec[s >> 1]; const char* p = arena + r.seq_off;
         const bool at_back = (side == 0) != (bool)(s & 1u);
-        const char b = at_back ? p[r.len - 1 - i] : p[i];
-        return (s & 1u) ? ac_complement(b) : b;
+        StrandCursor c; c.base = at_back ? p + r.len - 1 : p; c.step = at_back ? -1 : 1; c.comp = s & 1u;
+        return c;
     }
     AC_D void mark(int32_t cnd, bool hard, int32_t below) const {
         if (cnd < 0 || cnd >= below || (!hard && exhausted[cnd])) return;
         ac_atomic_or(&dirty[(size_t)cnd >> 6], (uint64_t)1 << (cnd & 63));
     }
-    AC_D void operator()(uint64_t ci) const {
-        if (level[ci] != this_level) return;
-        if (!all_due) {
+    // Every lane of a warp calls this together (ci may lie beyond the list: such a lane only helps).
+    AC_D void operator()(uint64_t ci, uint64_t n) const {
+        bool active = ci < n && level[ci] == this_level;
+        if (active && !all_due) {
             const uint64_t bit = (uint64_t)1 << (ci & 63);
-            if (!(ac_ld_volatile(&dirty[ci >> 6]) & bit)) return;
-            ac_atomic_and(&dirty[ci >> 6], ~bit);
+            if (!(ac_ld_volatile(&dirty[ci >> 6]) & bit)) active = false;
+            else ac_atomic_and(&dirty[ci >> 6], ~bit);
         }
-        const ExpandCandidate cd = cands[ci];
+        ExpandCandidate cd; cd.idx = 0; cd.side = 0; cd.gn = 0;
+        if (active) cd = cands[ci];
         const uint32_t idx = cd.idx, gn = cd.gn, side = cd.side;
         bool dup = false, pristine = all_due; uint32_t min_len = 0xFFFFFFFFu;
         for (uint32_t a = 0; a < gn; ++a) {
@@ -1171,37 +1224,41 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
             if (rec[s].flags) pristine = false;
             for (uint32_t b = 0; b < a; ++b) if (s == (cd.src[b] >> 1)) dup = true;
         }
-        uint32_t common_len;
-        if (pristine) common_len = spec_len[ci];
-        else {                                            // get_common_end_seq / get_common_start_seq on the graph as it is now
-            common_len = rec[cd.src[0] >> 1].len;
-            for (uint32_t a = 1; a < gn; ++a) {
-                const uint32_t la = rec[cd.src[a] >> 1].len;
-                if (la < common_len) common_len = la;
-                uint32_t m = 0;
-                while (m < common_len && at(cd.src[a], side, m) == at(cd.src[0], side, m)) ++m;
-                common_len = m;
-            }
+        // get_common_end_seq / get_common_start_seq (:283-312) on the graph as it is now, unless the comparison made before the pass still holds
+        uint32_t common_len = 0;
+        const bool compare = active && !pristine;
+        if (active) common_len = pristine ? spec_len[ci] : rec[cd.src[0] >> 1].len;
+        const StrandCursor first = active ? cursor(cd.src[0], side) : StrandCursor{nullptr, 0, 0};
+        for (uint32_t a = 1; a < 6; ++a) {                 // the warp walks the source lists in step: lane-uniform trip count
+            const bool have = compare && a < gn;
+            StrandCursor other = first;
+            if (have) { const uint32_t la = rec[cd.src[a] >> 1].len; if (la < common_len) common_len = la; other = cursor(cd.src[a], side); }
+            const uint32_t m = warp_first_mismatch(have, other, first, common_len);
+            if (have) common_len = m;
         }
         uint32_t c = common_len;
         if (c > 0) { const uint32_t cap = (min_len - 1) / (dup ? 2u : 1u); if (cap < c) c = cap; }      // avoid_zero_len_unitigs (:141-158)
-        const uint32_t min_pos = side == 0 ? rec[idx].min_fpos : rec[idx].min_rpos;
+        const uint32_t min_pos = active ? (side == 0 ? rec[idx].min_fpos : rec[idx].min_rpos) : 0;
         if (c > 0) { if (min_pos == 0) c = 0; else if (min_pos - 1 < c) c = min_pos - 1; }               // avoid_start_of_path (:161-181)
-        exhausted[ci] = c == common_len;
-        if (c == 0) return;
-        UnitigRec d = rec[idx];
-        if (side == 0 ? d.room_before < c : d.room_after < c) {                                         // move the destination where there is room
+        if (active) exhausted[ci] = c == common_len;
+        const bool moving = active && c > 0;
+        UnitigRec d = rec[moving ? idx : 0];
+        // move the destination where there is room
+        const bool relocate = moving && (side == 0 ? d.room_before < c : d.room_after < c);
+        StrandCursor old_seq{arena + d.seq_off, 1, 0};
+        if (relocate) {
             const uint32_t before = side == 0 ? c + 4 * AC_SEQ_SLACK : (d.room_before > AC_SEQ_SLACK ? d.room_before : AC_SEQ_SLACK);
             const uint32_t after = side == 0 ? (d.room_after > AC_SEQ_SLACK ? d.room_after : AC_SEQ_SLACK) : c + 4 * AC_SEQ_SLACK;
             const unsigned long long at_off = ac_atomic_add(arena_used, (unsigned long long)before + d.len + after);
-            for (uint32_t i = 0; i < d.len; ++i) arena[at_off + before + i] = arena[d.seq_off + i];
             d.seq_off = at_off + before; d.room_before = before; d.room_after = after;
         }
-        if (side == 0) {      // shift_sequence_1 (:89-116): the common end of the inputs becomes the start of this unitig
-            for (uint32_t j = 0; j < c; ++j) arena[d.seq_off - c + j] = at(cd.src[0], 0, c - 1 - j);
-        } else {              // shift_sequence_2 (:119-138): the common start of the outputs becomes its end
-            for (uint32_t i = 0; i < c; ++i) arena[d.seq_off + d.len + i] = at(cd.src[0], 1, i);
-        }
+        warp_copy(relocate, arena + d.seq_off, old_seq, d.len);
+        // shift_sequence_1 (:89-116): the common end of the inputs becomes the start of this unitig; shift_sequence_2 (:119-138): the common
+        // start of the outputs becomes its end
+        StrandCursor piece = first;
+        if (moving && side == 0) { piece.base = first.base + (int64_t)(c - 1) * first.step; piece.step = -first.step; }      // byte j of the piece is compared byte c-1-j
+        warp_copy(moving, side == 0 ? arena + d.seq_off - c : arena + d.seq_off + d.len, piece, c);
+        if (!moving) return;
         for (uint32_t a = 0; a < gn; ++a) {                // the sources lose the piece (unitig.rs:216-232)
             UnitigRec& r = rec[cd.src[a] >> 1];
             const bool rev = cd.src[a] & 1u;
@@ -1239,7 +1296,7 @@ struct ApplyPassCoopBody {
         ApplyLevelBody a = apply;
         for (uint32_t l = 1; l <= levels; ++l) {
             a.this_level = l;
-            for (uint64_t ci = tid; ci < n; ci += nt) a(ci);
+            for (uint64_t base = 0; base < n; base += nt) a(base + tid, n);      // whole warps go in: a lane without a candidate still helps its warp
             sync();
         }
         for (uint64_t ci = tid; ci < n; ci += nt)

@@ -1,0 +1,11 @@
+# r2f (1 GPU): GPU suite incl. k up to 501, bench cfg2 + cfg4 (fused), ncu of the hot kernels, launch list
+set -x
+mkdir -p gpurun_out
+( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2f_pytest.log 2>&1; tail -3 gpurun_out/r2f_pytest.log
+run() { env $1 timeout 300 python bench.py --workload ${2:-cfg2} --no-cpu-baseline --steps 10 --warmup 3 2>gpurun_out/r2f_err.log | tee gpurun_out/r2f_bench_${2:-cfg2}_$3.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); s=d['stage_ms']; print('$1 ${2:-cfg2}', d['value'], d['ms_per_step'], d['e2e']['value'], d['parity']['ok'], d['roofline']['frac'], s)"; }
+run "AC_X=0" cfg2 a
+run "AC_X=0" cfg4 a
+run "AC_INSERT_OCC=8" cfg2 occ8
+timeout 600 ncu --profile-from-start off --set full --import-source on --clock-control none --kernel-name-base demangled -k regex:'InsertBody|AdjacencyBody|BoundaryBody|ApplyPass|tile_sort|Levels' -o gpurun_out/r2f_kernels_cfg2 -f python profiles/profile_build.py cfg2 51 > gpurun_out/r2f_ncu_full.log 2>&1; tail -2 gpurun_out/r2f_ncu_full.log
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled --csv --log-file gpurun_out/r2f_launches_cfg2.csv python profiles/profile_build.py cfg2 51 > gpurun_out/r2f_launches_cfg2.log 2>&1
