@@ -146,16 +146,36 @@ template <int W> AC_HD uint64_t key_hash(const Key<W>& key) {
 // 2-bit packed sequence store: base j of the global coordinate system sits in word j>>5 at bits
 // [62 - 2*(j&31), 64 - 2*(j&31)), i.e. the words read as one big-endian base stream.  The buffer carries
 // W+1 words of zero padding at the end so that fetches never run off it.
+// y[0..W) = the 64W bits that start at bit `sh` (0..62, even) of the big-endian bit stream x[0], x[1], ..., x[W].  On the device: the
+// stream as 32-bit words, a one-word step when sh >= 32 and one funnel shift per output word (a 64-bit shift pair costs four times that).
+template <int W> AC_HD void ac_stream_window(const uint64_t (&x)[W + 1], uint32_t sh, uint64_t (&y)[W]) {
+#ifdef __CUDA_ARCH__
+    uint32_t z[2 * W + 1];
+    const bool step = sh >= 32u;
+#pragma unroll
+    for (int i = 0; i <= 2 * W; ++i) {
+        const uint32_t a = (i & 1) ? (uint32_t)x[i >> 1] : (uint32_t)(x[i >> 1] >> 32);                  // 32-bit word i of the stream
+        const uint32_t b = ((i + 1) & 1) ? (uint32_t)x[(i + 1) >> 1] : (uint32_t)(x[(i + 1) >> 1] >> 32);  // word i + 1 (i = 2W: the low half of x[W])
+        z[i] = step ? b : a;
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const uint32_t hi = __funnelshift_l(z[2 * j + 1], z[2 * j], sh), lo = __funnelshift_l(z[2 * j + 2], z[2 * j + 1], sh);   // the shift count is taken modulo 32
+        y[j] = ((uint64_t)hi << 32) | lo;
+    }
+#else
+#pragma unroll
+    for (int j = 0; j < W; ++j) y[j] = sh ? (x[j] << sh) | (x[j + 1] >> (64 - sh)) : x[j];
+#endif
+}
+
 template <int W> AC_HD Key<W> fetch_codes(const uint64_t* __restrict__ packed, uint64_t gpos, const KParams& p) {
     const uint64_t i0 = gpos >> 5;
     const uint32_t o = 2 * (uint32_t)(gpos & 31);
-    uint64_t y[W];
+    uint64_t x[W + 1], y[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-        uint64_t v = packed[i0 + j] << o;
-        if (o) v |= packed[i0 + j + 1] >> (64 - o);
-        y[j] = v;
-    }
+    for (int j = 0; j <= W; ++j) x[j] = packed[i0 + j];
+    ac_stream_window<W>(x, o, y);
     Key<W> r;
     const uint32_t sh = 64 - p.top_bits;
 #pragma unroll
@@ -211,6 +231,13 @@ typedef uint64_t Slot;
 #define AC_SLOT_TAG_BITS(gb) (64u - AC_SLOT_TAG_SHIFT - (gb))
 AC_HD uint32_t slot_gpos_bits(uint64_t total) { uint32_t gb = 8; while (gb < 32 && (total >> gb) != 0) ++gb; return gb; }
 AC_HD uint64_t slot_gpos(Slot s, uint32_t gb) { return s >> (64 - gb); }
+AC_HD uint32_t slot_tag_word(Slot s) {          // bits 30..61 of the slot: the tag in its low bits, the low end of the occurrence pointer above it
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r((uint32_t)s, (uint32_t)(s >> 32), AC_SLOT_TAG_SHIFT);
+#else
+    return (uint32_t)(s >> AC_SLOT_TAG_SHIFT);
+#endif
+}
 AC_HD uint32_t slot_tag(Slot s, uint32_t gb) { return (uint32_t)(s >> AC_SLOT_TAG_SHIFT) & ((1u << AC_SLOT_TAG_BITS(gb)) - 1u); }      // dotted bit + fingerprint
 AC_HD bool slot_dotted(Slot s, uint32_t gb) { return (s >> (63 - gb)) & 1; }
 AC_HD uint32_t slot_count(Slot s) { return (uint32_t)(s >> AC_SLOT_COUNT_SHIFT) & ((1u << AC_SLOT_COUNT_BITS) - 1u); }

@@ -182,8 +182,7 @@ template <int W> struct InsertBody {
         const uint64_t xp = t.packed[i0 - 1];
         const uint32_t sh = 2 * l;
         uint64_t y[W];
-#pragma unroll
-        for (int j = 0; j < W; ++j) y[j] = (x[j] << sh) | ((x[j + 1] >> 1) >> (63 - sh));
+        ac_stream_window<W>(x, sh, y);       // y = the 64W bits of the base stream that start at bit `sh` of x[0]
         const uint32_t al = 64 - p.top_bits;
 #pragma unroll
         for (int j = W - 1; j >= 0; --j) { uint64_t v = y[j] >> al; if (al && j > 0) v |= y[j - 1] << (64 - al); fwd.w[j] = v; }
@@ -230,6 +229,9 @@ template <int W> struct InsertBody {
         const uint32_t tag = make_tag(dotted, h, t.gb);
         const Slot mine = make_slot(g, tag, t.count_big ? 0u : 1u, flags, t.gb);
         const uint32_t tag_mask = (1u << AC_SLOT_TAG_BITS(t.gb)) - 1u;
+        // An empty slot is all ones and no window starts at coordinate 2^gb - 1, so "empty" is a test of the occurrence pointer alone: the
+        // high word at or above this value.  The tag sits at bits 30.. of the slot; slot_tag_word() brings it down with one funnel shift.
+        const uint32_t empty_hi = 0xFFFFFFFFu << (32u - t.gb);
         uint64_t slot = table_home(t, h);
         bool done = !valid, failed = false;
         for (uint32_t probes = 0;;) {
@@ -240,13 +242,14 @@ template <int W> struct InsertBody {
                     const uint64_t base = slot & ~3ull;
                     ac_ld_group(t.slots + base, grp);
                     // the first slot of the group, from `slot` on, that is empty or carries the tag
-                    uint32_t hit = 0, empty = 0;
+                    uint32_t cand = 0;
 #pragma unroll
                     for (uint32_t j = 0; j < 4; ++j) {
-                        if (grp[j] == AC_EMPTY_SLOT) empty |= 1u << j;
-                        if (((uint32_t)(grp[j] >> AC_SLOT_TAG_SHIFT) & tag_mask) == tag) hit |= 1u << j;
+                        const bool is_empty = (uint32_t)(grp[j] >> 32) >= empty_hi;
+                        const bool has_tag = ((slot_tag_word(grp[j]) ^ tag) & tag_mask) == 0;
+                        cand |= (is_empty || has_tag) ? 1u << j : 0u;
                     }
-                    const uint32_t cand = (hit | empty) & (0xFu << (slot & 3u)) & 0xFu;
+                    cand &= 0xFu << (slot & 3u);
                     if (cand == 0) {
                         slot = base + 4; if (slot >= t.cap) slot = 0;
                         if (++probes > 2048) { counters[2] = 1; failed = true; done = true; break; }    // the table was sized too small: the host retries with the safe size
@@ -255,7 +258,7 @@ template <int W> struct InsertBody {
                     const uint32_t j = (uint32_t)ac_ctz(cand);
                     slot = base + j;
                     q = j == 0 ? grp[0] : j == 1 ? grp[1] : j == 2 ? grp[2] : grp[3];
-                    if ((empty >> j) & 1u) {
+                    if ((uint32_t)(q >> 32) >= empty_hi) {
                         q = ac_atomic_cas(&t.slots[slot], (Slot)AC_EMPTY_SLOT, mine);
                         if (q == AC_EMPTY_SLOT) { claimed = true; break; }
                         if (slot_tag(q, t.gb) != tag) { ++slot; if (slot >= t.cap) slot = 0; continue; }      // somebody else's k-mer got there first: on to the next slot
@@ -422,66 +425,66 @@ template <int W> struct AdjacencyBody {
     }
 };
 
-// One thread per 64 global coordinates: bit j set <=> a unitig occurrence starts at coordinate 64i+j,
-// i.e. it is window 0 of a sequence or the edge from the previous window is not merged.
+// Where the unitig occurrences start: bit j of word w set <=> an occurrence starts at coordinate 32w+j, i.e. it is window 0 of a
+// sequence or the edge from the previous window is not merged.  One thread per coordinate, a warp per word: the slot ids are read
+// coalesced, the flag gathers of 32 windows are in flight together, the previous window's state comes from the lane below (lane 0
+// fetches it), and a ballot assembles the word.
 struct BoundaryBody {
     const uint64_t* packed; const SeqInfo* seqs; uint32_t n_seqs; uint32_t h; uint64_t g_begin, g_end;   // this rank's coordinates
-    const uint32_t* pos_slot; const uint8_t* flags8;
-    uint64_t* bmask; uint32_t* bcount;
-    AC_D void operator()(uint64_t i) const {
-        uint64_t g = i * 64 > g_begin ? i * 64 : g_begin;
-        const uint64_t g1 = (i * 64 + 64 < g_end) ? i * 64 + 64 : g_end;
-        if (g >= g1) { bmask[i] = 0; bcount[i] = 0; return; }
-        uint64_t bits = 0;
-        uint32_t si = find_seq(seqs, n_seqs, g);
-        while (g < g1) {
-            const SeqInfo s = seqs[si];
-            uint64_t fs = g - s.start;
-            if (fs >= s.len) {
-                if (si + 1 >= n_seqs) break;
-                ++si;
-                if (seqs[si].start > g) g = seqs[si].start;
-                continue;
-            }
-            const uint64_t stop = (s.start + s.len < g1) ? s.start + s.len : g1;
-            uint32_t prev_slot = 0; bool prev_out = false;
-            if (fs > 0) {
-                prev_slot = pos_slot[g - 1];
-                const uint8_t fl = flags8[prev_slot];
-                const bool o = packed_base(packed, g - 1 + h) < 2;
-                prev_out = o ? (fl & 1) : (fl & 2);
-            }
-            for (; g < stop; ++g, ++fs) {
-                const uint32_t slot = pos_slot[g];
-                const uint8_t fl = flags8[slot];
-                const bool o = packed_base(packed, g + h) < 2;     // forward window is the stored orientation
-                const bool in_ok = o ? (fl & 2) : (fl & 1);
-                const bool merged = fs > 0 && prev_out && in_ok && slot != prev_slot;   // slot equality covers K'==K and K'==rc(K)
-                if (!merged) bits |= 1ull << (g & 63);
-                prev_slot = slot; prev_out = o ? (fl & 1) : (fl & 2);
-            }
+    const uint32_t* pos_slot; const uint8_t* flags8; const uint8_t* interior;
+    uint32_t* bmask; uint32_t* bcount;
+    struct State { uint32_t slot; bool valid, first, in_ok, out_ok; };
+    AC_D State state(uint64_t g, bool known_interior) const {
+        State st; st.slot = 0; st.valid = false; st.first = false; st.in_ok = false; st.out_ok = false;
+        if (!known_interior) {
+            if (g < g_begin || g >= g_end) return st;
+            const SeqInfo s = seqs[find_seq(seqs, n_seqs, g)];
+            const uint64_t fs = g - s.start;
+            if (fs >= s.len) return st;
+            st.first = fs == 0;
         }
-        bmask[i] = bits;
-#ifdef AC_EMULATE
-        bcount[i] = (uint32_t)__builtin_popcountll(bits);
+        st.valid = true;
+        st.slot = pos_slot[g];
+        const uint8_t fl = flags8[st.slot];
+        const bool o = packed_base(packed, g + h) < 2;     // forward window is the stored orientation
+        st.in_ok = o ? (fl & 2) : (fl & 1); st.out_ok = o ? (fl & 1) : (fl & 2);
+        return st;
+    }
+    AC_D static bool starts(const State& me, const State& prev) {
+        if (!me.valid) return false;
+        const bool merged = !me.first && prev.out_ok && me.in_ok && me.slot != prev.slot;   // slot equality covers K'==K and K'==rc(K)
+        return !merged;
+    }
+    AC_D void operator()(uint64_t g) const {
+        const uint64_t g0 = g & ~31ull;
+        const bool inside = interior[g0 >> 5] && g0 >= g_begin && g0 + 32 <= g_end;        // PackBody's flag: 32 windows of one sequence, none of them its first
+#ifdef __CUDA_ARCH__
+        const uint32_t lane = (uint32_t)g & 31u;
+        const State me = state(g, inside);
+        State prev; prev.slot = __shfl_up_sync(0xFFFFFFFFu, me.slot, 1); prev.out_ok = __shfl_up_sync(0xFFFFFFFFu, (int)me.out_ok, 1) != 0;
+        prev.valid = true; prev.first = false; prev.in_ok = false;
+        if (lane == 0 && me.valid && !me.first) prev = state(g - 1, false);                   // the window before a word's first one (same sequence: me is not its first window)
+        const uint32_t word = __ballot_sync(0xFFFFFFFFu, starts(me, prev));
+        if (lane == 0) { bmask[g0 >> 5] = word; bcount[g0 >> 5] = (uint32_t)__popc(word); }
 #else
-        bcount[i] = (uint32_t)__popcll(bits);
+        if (g != g0) return;
+        uint32_t word = 0;
+        State prev = state(g0, inside);
+        if (prev.valid && !prev.first) { const State before = state(g0 - 1, false); if (starts(prev, before)) word |= 1u; } else if (prev.valid) word |= 1u;
+        for (uint32_t j = 1; j < 32; ++j) { const State me = state(g0 + j, inside); if (starts(me, prev)) word |= 1u << j; prev = me; }
+        bmask[g0 >> 5] = word; bcount[g0 >> 5] = (uint32_t)__builtin_popcount(word);
 #endif
     }
 };
 
 struct RunScatterBody {
-    const uint64_t* bmask; const uint32_t* boff; uint64_t* run_start;
+    const uint32_t* bmask; const uint32_t* boff; uint64_t* run_start;
     AC_D void operator()(uint64_t i) const {
-        uint64_t bits = bmask[i];
+        uint32_t bits = bmask[i];
         uint32_t off = boff[i];
         while (bits) {
-#ifdef AC_EMULATE
-            const int b = __builtin_ctzll(bits);
-#else
-            const int b = __ffsll((long long)bits) - 1;
-#endif
-            run_start[off++] = i * 64 + (uint64_t)b;
+            const int b = ac_ctz(bits);
+            run_start[off++] = i * 32 + (uint64_t)b;
             bits &= bits - 1;
         }
     }
@@ -1214,6 +1217,11 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
             if (!(ac_ld_volatile(&dirty[ci >> 6]) & bit)) active = false;
             else ac_atomic_and(&dirty[ci >> 6], ~bit);
         }
+#ifdef __CUDA_ARCH__
+        if (!__any_sync(0xFFFFFFFFu, active)) return;       // nothing for this warp at this level: most warps in most levels of the later passes
+#else
+        if (!active) return;
+#endif
         ExpandCandidate cd; cd.idx = 0; cd.side = 0; cd.gn = 0;
         if (active) cd = cands[ci];
         const uint32_t idx = cd.idx, gn = cd.gn, side = cd.side;
@@ -1287,23 +1295,49 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
     }
 };
 
-// One pass of expand_repeats in ONE cooperative launch: the levels in order with a grid barrier between them, then the room the NEXT
-// pass may ask for (only candidates left on the work list can act in it).
-struct ApplyPassCoopBody {
+// `while expand_repeats() > 0 {}` in ONE cooperative launch: every pass walks the levels in order with a grid barrier between them, then
+// adds up the room the NEXT pass may ask for (only candidates left on the work list can act in it) and goes on while bases moved and
+// the arena can take that much.  Counters (c64): [0] arena bump, [3 + 2 stripes] bases the graph lost — both running totals — and two
+// sets, used by alternate passes, of { bases moved, bound stripes, candidates left }: set q lives at c64 + AC_PASS_SET(q).  A pass adds
+// to its own set and, once everybody is past its first barrier (so nobody still reads the other set), thread 0 zeroes the other one for
+// the pass after it: no barrier is spent on resetting counters.  res: [0] bases the last pass moved, [1] bases moved at all, [2] passes
+// made by this launch, [3] the next pass's bound, [4] candidates it left, [5] the set that pass must use, [6] the arena bump.
+#define AC_PASS_SET_WORDS (AC_BOUND_STRIPES + 3)
+#define AC_PASS_SET(q) (1 + (q) * AC_PASS_SET_WORDS)          // [+0] bases moved, [+1 .. +stripes] bound, [+1+stripes] candidates left, [+2+stripes] arena bump once the levels are through
+#define AC_PASS_REMOVED (1 + 2 * AC_PASS_SET_WORDS)
+#define AC_PASS_WORDS (2 + 2 * AC_PASS_SET_WORDS)
+struct SimplifyCoopBody {
     ApplyLevelBody apply; RelocBoundBody next_bound; uint64_t n; const uint32_t* n_levels;
+    unsigned long long* c64; unsigned long long* res; uint64_t arena_cap; uint32_t first_set; bool first_is_pass_one, single_pass;
     template <class Sync> AC_D void operator()(uint64_t tid, uint64_t nt, Sync& sync) const {
         const uint32_t levels = *n_levels;
         ApplyLevelBody a = apply;
-        for (uint32_t l = 1; l <= levels; ++l) {
-            a.this_level = l;
-            for (uint64_t base = 0; base < n; base += nt) a(base + tid, n);      // whole warps go in: a lane without a candidate still helps its warp
-            sync();
-        }
-        for (uint64_t ci = tid; ci < n; ci += nt)
-            if (ac_ld_volatile(&apply.dirty[ci >> 6]) >> (ci & 63) & 1) {
-                ac_atomic_add(next_bound.bound + (ci & (AC_BOUND_STRIPES - 1)), next_bound.bound_of(ci));
-                ac_atomic_add(next_bound.bound + AC_BOUND_STRIPES, 1ull);       // candidates left on the work list: sizes the next pass's grid
+        RelocBoundBody nb = next_bound;
+        for (uint32_t pass = 0;; ++pass) {
+            const uint32_t q = (first_set + pass) & 1u;
+            unsigned long long* mine = c64 + AC_PASS_SET(q); unsigned long long* other = c64 + AC_PASS_SET(q ^ 1u);
+            a.all_due = first_is_pass_one && pass == 0; a.total_shifted = mine;
+            for (uint32_t l = 1; l <= levels; ++l) {
+                a.this_level = l;
+                for (uint64_t base = 0; base < n; base += nt) a(base + tid, n);      // whole warps go in: a lane without a candidate still helps its warp
+                sync();
+                if (l == 1 && tid == 0) for (uint32_t x = 0; x < AC_PASS_SET_WORDS; ++x) other[x] = 0;
+                if (l == levels && tid == 0) mine[2 + AC_BOUND_STRIPES] = ac_ld_volatile(c64);       // nothing is relocated after the last level: the same value for every thread's decision below
             }
+            nb.bound = mine + 1;
+            for (uint64_t ci = tid; ci < n; ci += nt)
+                if (ac_ld_volatile(&a.dirty[ci >> 6]) >> (ci & 63) & 1) {
+                    ac_atomic_add(nb.bound + (ci & (AC_BOUND_STRIPES - 1)), nb.bound_of(ci));
+                    ac_atomic_add(mine + 1 + AC_BOUND_STRIPES, 1ull);       // candidates left on the work list
+                }
+            sync();
+            const unsigned long long moved = ac_ld_volatile(mine), used = ac_ld_volatile(mine + 2 + AC_BOUND_STRIPES);
+            unsigned long long bound = 0;
+            for (uint32_t x = 0; x < AC_BOUND_STRIPES; ++x) bound += ac_ld_volatile(mine + 1 + x);
+            const bool go_on = moved != 0 && !single_pass && used + bound + 64 <= arena_cap && pass < 1000000u;
+            if (tid == 0) { res[0] = moved; res[1] += moved; res[2] = pass + 1; res[3] = bound; res[4] = ac_ld_volatile(mine + 1 + AC_BOUND_STRIPES); res[5] = q ^ 1u; res[6] = used; }
+            if (!go_on) return;
+        }
     }
 };
 
@@ -1956,14 +1990,14 @@ template <int W> void DevicePipeline::Impl::runs_local_w() {
     ac_launch("adjacency", &stream, AdjacencyBody<W>{tv, p, any_dotted, occ_list.as<uint32_t>(), flags8.as<uint8_t>(), bloom.as<uint64_t>(), bloom_words}, n_slots_used);
     mark(5);
 
-    const uint64_t n_bwords = (total + 63) / 64;
-    bmask.ensure(n_bwords * sizeof(uint64_t)); bcount.ensure(n_bwords * sizeof(uint32_t)); boff.ensure(n_bwords * sizeof(uint32_t));
+    const uint64_t n_bwords = (total + 31) / 32;
+    bmask.ensure(n_bwords * sizeof(uint32_t)); bcount.ensure(n_bwords * sizeof(uint32_t)); boff.ensure(n_bwords * sizeof(uint32_t));
     ac_launch("boundaries", &stream, BoundaryBody{packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, p.h, g_begin, g_end, pos_slot.as<uint32_t>(),
-                                                  flags8.as<uint8_t>(), bmask.as<uint64_t>(), bcount.as<uint32_t>()}, n_bwords);
+                                                  flags8.as<uint8_t>(), interior8.as<uint8_t>(), bmask.as<uint32_t>(), bcount.as<uint32_t>()}, n_bwords * 32);
     n_runs = exclusive_scan(bcount.as<uint32_t>(), boff.as<uint32_t>(), n_bwords);
     mark(6);
     run_start.ensure(n_runs * sizeof(uint64_t)); run_len.ensure(n_runs * 4); run_hs.ensure(n_runs * 4); run_ts.ensure(n_runs * 4);
-    ac_launch("run_scatter", &stream, RunScatterBody{bmask.as<uint64_t>(), boff.as<uint32_t>(), run_start.as<uint64_t>()}, n_bwords);
+    ac_launch("run_scatter", &stream, RunScatterBody{bmask.as<uint32_t>(), boff.as<uint32_t>(), run_start.as<uint64_t>()}, n_bwords);
     ac_launch("run_ends", &stream, RunEndsLocalBody{seqs.as<SeqInfo>(), n_seqs, run_start.as<uint64_t>(), n_runs, pos_slot.as<uint32_t>(),
                                                     run_len.as<uint32_t>(), run_hs.as<uint32_t>(), run_ts.as<uint32_t>()}, n_runs);
     stage = 2;
@@ -2113,49 +2147,48 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     mark(11);
     if (device_first_pass && n_cands == 0 && device_simplify) { R.first_pass_done = true; R.first_pass_total = 0; }     // nothing can shift: the loop ends at once
     if (device_first_pass && n_cands > 0) {
-        d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(32); d_counters64.ensure((2 * AC_BOUND_STRIPES + 4) * 8);
+        d_pred.ensure(n_cands * 7 * 4); d_level.ensure(n_cands * 4); d_flagmax.ensure(32); d_counters64.ensure((AC_PASS_WORDS + 8) * 8);
         d_dirty.ensure(((n_cands + 63) / 64) * 8 + 8); d_exhausted.ensure(n_cands + 8);
-        unsigned long long* c64 = d_counters64.as<unsigned long long>();         // [0] arena bump, [1] bases moved, [2..] bound stripes of this pass, then of the next, then bases the graph lost
-        unsigned long long* bound_now = c64 + 2; unsigned long long* bound_next = c64 + 2 + AC_BOUND_STRIPES; unsigned long long* removed = c64 + 3 + 2 * AC_BOUND_STRIPES;   // [2 + 2 stripes]: candidates left for the next pass
+        unsigned long long* c64 = d_counters64.as<unsigned long long>();         // SimplifyCoopBody's counters, then its eight result words
+        unsigned long long* res = c64 + AC_PASS_WORDS;
         ac_launch("level_pred", &stream, LevelPredBody{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_pred.as<int32_t>()}, n_cands);
         ac_memset(d_level.p, 0, n_cands * 4, &stream); ac_memset(d_flagmax.p, 0, 32, &stream);
         ac_launch_coop("levels", &stream, LevelsCoopBody{d_pred.as<int32_t>(), d_level.as<uint32_t>(), d_flagmax.as<uint32_t>(), n_cands}, n_cands, 4096);
-        ac_memset(d_counters64.p, 0, (2 * AC_BOUND_STRIPES + 4) * 8, &stream);
-        const RelocBoundBody bound_body{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_cand_at.as<int32_t>(), bound_now};
+        ac_memset(d_counters64.p, 0, (AC_PASS_WORDS + 8) * 8, &stream);
+        const RelocBoundBody bound_body{d_cands.as<ExpandCandidate>(), d_rec.as<UnitigRec>(), d_cand_at.as<int32_t>(), c64 + AC_PASS_SET(1) + 1};     // the first pass's bound: into the set it does not use
         ac_launch("reloc_bound", &stream, bound_body, n_cands);
-        uint32_t fm[8]; std::vector<unsigned long long> h64(2 * AC_BOUND_STRIPES + 4);
-        uint64_t due = n_cands;                  // candidates the coming pass has to look at
-        ac_d2h(fm, d_flagmax.p, 32, &stream); ac_d2h(h64.data(), c64, h64.size() * 8, &stream); ac_sync(&stream);
+        uint32_t fm[8]; unsigned long long h64[AC_PASS_WORDS + 8];
+        ac_d2h(fm, d_flagmax.p, 32, &stream); ac_d2h(h64, c64, sizeof h64, &stream); ac_sync(&stream);
         if (fm[4]) throw std::runtime_error("candidate levels did not settle");
-        unsigned long long bound = 0; for (int x = 0; x < AC_BOUND_STRIPES; ++x) bound += h64[2 + x];
+        unsigned long long bound = 0; for (int x = 0; x < AC_BOUND_STRIPES; ++x) bound += h64[AC_PASS_SET(1) + 1 + x];
         if (arena_bytes + bound >= 0xFFFFFFF0ull) throw std::runtime_error("unitig sequence arena would exceed 4 GB");
-        d_arena2.ensure(arena_bytes + bound + 64);
+        // room for the first pass and, usually, for all that follow (each later pass can ask for less than the one before it asked for at most)
+        d_arena2.ensure(arena_bytes + 2 * bound + 64);
         ac_copy_dd(d_arena2.p, d_arena.p, arena_bytes, &stream);
         const unsigned long long start = arena_bytes;
         ac_h2d(c64, &start, 8, &stream);
+        ac_memset(c64 + AC_PASS_SET(1), 0, AC_PASS_SET_WORDS * 8, &stream);
         ac_memset(d_dirty.p, 0, ((n_cands + 63) / 64) * 8 + 8, &stream); ac_memset(d_exhausted.p, 0, n_cands + 8, &stream);
-        // `while expand_repeats() > 0 {}` (only its first call without device_simplify): one launch and one read-back per pass
-        for (uint32_t pass = 1;; ++pass) {
+        // `while expand_repeats() > 0 {}` (only its first call without device_simplify): one launch for as many passes as the arena has room for
+        static const bool always_grow = getenv("AC_DEVICE_TIGHT_ARENA") != nullptr;   // test hook: one pass per launch, the growth path before every pass
+        uint32_t next_set = 0; uint64_t passes = 0;
+        for (bool first = true;; first = false) {
             const ApplyLevelBody apply{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_level.as<uint32_t>(), 0, d_spec.as<uint32_t>(),
-                                       d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64, c64 + 1, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>(), pass == 1, removed};
-            RelocBoundBody nb = bound_body; nb.bound = bound_next;
-            // every pass walks all candidates at every level (a cheap test), so few CTAs when few are due: the barriers dominate then
-            ac_launch_coop("apply_pass", &stream, ApplyPassCoopBody{apply, nb, n_cands, d_flagmax.as<uint32_t>() + 3}, std::max<uint64_t>(due * 32, n_cands / 2), 512);
-            ac_d2h(h64.data(), c64, h64.size() * 8, &stream); ac_sync(&stream);
-            R.arena_final = h64[0]; R.first_pass_total = h64[1]; R.first_pass_done = true;      // what this expand_repeats() call returned
-            R.bases_removed = h64[3 + 2 * AC_BOUND_STRIPES]; R.any_moved = R.any_moved || h64[1] != 0;
-            due = h64[2 + 2 * AC_BOUND_STRIPES];
+                                       d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64, c64, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>(), first, c64 + AC_PASS_REMOVED};
+            const uint64_t room = always_grow ? 0 : d_arena2.cap;
+            ac_launch_coop("simplify", &stream, SimplifyCoopBody{apply, bound_body, n_cands, d_flagmax.as<uint32_t>() + 3, c64, res, room, next_set, first, !device_simplify}, n_cands, 64);
+            ac_d2h(h64, c64, sizeof h64, &stream); ac_sync(&stream);
+            const unsigned long long* r = h64 + AC_PASS_WORDS;
+            R.arena_final = h64[0]; R.first_pass_total = r[0]; R.first_pass_done = true;      // what the last expand_repeats() call returned
+            R.bases_removed = h64[AC_PASS_REMOVED]; R.any_moved = r[1] != 0;
+            passes += r[2]; next_set = (uint32_t)r[5];
             if (!device_simplify || R.first_pass_total == 0) break;
-            if (pass > 100000) throw std::runtime_error("repeat expansion did not settle");
-            bound = 0; for (int x = 0; x < AC_BOUND_STRIPES; ++x) bound += h64[2 + AC_BOUND_STRIPES + x];
+            if (passes > 1000000) throw std::runtime_error("repeat expansion did not settle");
+            bound = r[3];                                                                  // the launch stopped for want of room: make it
             if (R.arena_final + bound >= 0xFFFFFFF0ull) throw std::runtime_error("unitig sequence arena would exceed 4 GB");
-            static const bool always_grow = getenv("AC_DEVICE_TIGHT_ARENA") != nullptr;   // test hook: take the growth path before every pass
-            if (always_grow || R.arena_final + bound + 64 > d_arena2.cap) {             // make room for whatever the next pass may relocate
-                d_arena3.ensure(std::max<size_t>((R.arena_final + bound) * 2 + 64, d_arena3.cap + (always_grow ? 64 : 0)));
-                ac_copy_dd(d_arena3.p, d_arena2.p, R.arena_final, &stream); ac_sync(&stream);
-                std::swap(d_arena2.p, d_arena3.p); std::swap(d_arena2.cap, d_arena3.cap);
-            }
-            ac_memset(c64 + 1, 0, (2 * AC_BOUND_STRIPES + 2) * 8, &stream);             // bases moved, both stripe sets, the work-list count; the running total of removed bases stays
+            d_arena3.ensure(std::max<size_t>((R.arena_final + bound) * 2 + 64, d_arena3.cap + (always_grow ? 64 : 0)));
+            ac_copy_dd(d_arena3.p, d_arena2.p, R.arena_final, &stream); ac_sync(&stream);
+            std::swap(d_arena2.p, d_arena3.p); std::swap(d_arena2.cap, d_arena3.cap);
         }
         R.arena_src = &d_arena2;
     }

@@ -166,7 +166,7 @@ def test_loaded_graphs_and_reference_kats(lib, golden_dir, tmp_path):
         assert open(os.path.join(out, fn), "rb").read() == open(os.path.join(d, fn), "rb").read()
 
 
-@pytest.mark.parametrize("switch", ["AC_DEVICE_FIRST_PASS", "AC_DEVICE_SIMPLIFY", "AC_DEVICE_SIMPLIFY,AC_DEVICE_GFA"])
+@pytest.mark.parametrize("switch", ["AC_DEVICE_FIRST_PASS", "AC_DEVICE_SIMPLIFY", "AC_DEVICE_SIMPLIFY,AC_DEVICE_GFA", "AC_DEVICE_SIMPLIFY,AC_DEVICE_TIGHT_ARENA"])
 def test_device_expansion_switches_match_the_oracle(lib, tmp_path, switch):
     """expand_repeats applied by device kernels (pipeline.cu ApplyLevelBody), alone and with the device GFA writer: same bytes as the oracle
     on a medium graph.  The switches are read once per process, so the build runs in a child."""
