@@ -173,6 +173,7 @@ template <int W> struct InsertBody {
     uint32_t* pos_slot;                 // [total] slot of the window starting at each global coordinate (null in the sizing pass)
     unsigned long long* counters;       // [0] slots claimed (sizing pass only), [1] dotted k-mers claimed, [2] probe-limit flag, [3] count alarm
     bool sizing;                        // the sizing pass: the caller has picked the windows (SampleBody), only distinct k-mers are counted
+    uint32_t* claimed_bits;             // [total / 32] bit j of word w: the window at coordinate 32w + j claimed its slot, i.e. it is the first occurrence of a distinct k-mer (the list of distinct k-mers is made from these); null in the sizing pass
     // a window of an interior block: keys and neighbour bases from the block's W+2 words
     AC_D void interior_unit(uint32_t g, Key<W>& fwd, Key<W>& rc, uint64_t& h, uint32_t& flags) const {
         const uint32_t l = g & 31u, i0 = g >> 5;
@@ -224,7 +225,7 @@ template <int W> struct InsertBody {
         return true;
     }
     // Enters the k-mer (or finds it) and counts the occurrence.  All lanes of the warp call this together.
-    AC_D void upsert(bool valid, const Key<W>& fwd, const Key<W>& rc, uint64_t h, uint32_t flags, uint32_t g) const {
+    AC_D void upsert(bool valid, const Key<W>& fwd, const Key<W>& rc, uint64_t h, uint32_t flags, uint32_t g, const Slot* home_group = nullptr) const {
         const bool dotted = valid && fwd.d != 0;
         const uint32_t tag = make_tag(dotted, h, t.gb);
         const Slot mine = make_slot(g, tag, t.count_big ? 0u : 1u, flags, t.gb);
@@ -234,13 +235,15 @@ template <int W> struct InsertBody {
         const uint32_t empty_hi = 0xFFFFFFFFu << (32u - t.gb);
         uint64_t slot = table_home(t, h);
         bool done = !valid, failed = false;
+        uint32_t fresh = 0;                 // lanes of this warp whose window claimed a slot
         for (uint32_t probes = 0;;) {
             bool claimed = false; Slot q = 0;
             if (!done) {
-                for (;;) {
+                for (bool fetched = home_group != nullptr;; fetched = false) {
                     Slot grp[4];
                     const uint64_t base = slot & ~3ull;
-                    ac_ld_group(t.slots + base, grp);
+                    if (fetched) { grp[0] = home_group[0]; grp[1] = home_group[1]; grp[2] = home_group[2]; grp[3] = home_group[3]; }      // loaded while the previous unit was probed; may lag the table, as any load may (see slot_add_occurrence)
+                    else ac_ld_group(t.slots + base, grp);
                     // the first slot of the group, from `slot` on, that is empty or carries the tag
                     uint32_t cand = 0;
 #pragma unroll
@@ -269,6 +272,11 @@ template <int W> struct InsertBody {
 #ifdef __CUDA_ARCH__
             __syncwarp();
 #endif
+#ifdef __CUDA_ARCH__
+            fresh |= __ballot_sync(0xFFFFFFFFu, !done && claimed);          // a claimed slot is a new distinct k-mer
+#else
+            if (!done && claimed) fresh = 1;
+#endif
             if (!done) {
                 if (claimed) {
                     if (t.count_big) ac_atomic_add(&t.count_big[slot], 1u);
@@ -288,15 +296,68 @@ template <int W> struct InsertBody {
 #endif
         }
         if (valid && !failed && pos_slot) ac_st_stream(&pos_slot[g], (uint32_t)slot);
+        if (claimed_bits) {
+#ifdef __CUDA_ARCH__
+            if ((threadIdx.x & 31u) == 0) claimed_bits[g >> 5] = fresh;      // the warp's 32 windows start in one word of coordinates
+#else
+            if (fresh) claimed_bits[g >> 5] |= 1u << (g & 31u);
+#endif
+        }
+    }
+    struct Unit { Key<W> fwd, rc; uint64_t h; uint32_t flags, g; bool valid; };
+    AC_D void prepare(uint64_t i, Unit& u) const {
+        u.g = g_first + (uint32_t)i; u.fwd = Key<W>(); u.rc = Key<W>(); u.h = 0; u.flags = 0; u.valid = true;
+        const uint32_t g0 = u.g & ~31u;
+        if (interior[g0 >> 5] && g0 >= g_begin && g0 + 32 <= g_end) interior_unit(u.g, u.fwd, u.rc, u.h, u.flags);
+        else u.valid = edge_unit(u.g, u.fwd, u.rc, u.h, u.flags);
     }
     AC_D void operator()(uint64_t i) const {
-        const uint32_t g = g_first + (uint32_t)i, g0 = g & ~31u;
-        Key<W> fwd = Key<W>(), rc = Key<W>(); uint64_t h = 0; uint32_t flags = 0; bool valid = true;
-        if (interior[g0 >> 5] && g0 >= g_begin && g0 + 32 <= g_end) interior_unit(g, fwd, rc, h, flags);
-        else valid = edge_unit(g, fwd, rc, h, flags);
-        upsert(valid, fwd, rc, h, flags, g);
+        Unit u; prepare(i, u);
+        upsert(u.valid, u.fwd, u.rc, u.h, u.flags, u.g);
     }
 };
+#ifndef AC_EMULATE
+// The insert kernel proper: the grid-stride loop of ac_body_kernel_occ, software-pipelined — while a unit is probed, the keys of the
+// thread's NEXT unit are already built and the load of its home group is in flight, so the table's latency (most of the kernel's stall
+// samples, profiles/r2h) overlaps the probing of the unit before.  n is a multiple of 32: whole warps walk the loop together.
+template <int W, int CTAS> __global__ void __launch_bounds__(256, CTAS) ac_insert_kernel(const InsertBody<W> body, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename InsertBody<W>::Unit cur, nxt;
+    Slot grp[4], grp_next[4];
+    body.prepare(i, cur);
+    if (cur.valid) ac_ld_group(body.t.slots + table_home(body.t, cur.h), grp);
+    for (;;) {
+        const uint64_t j = i + stride;
+        const bool more = j < n;
+        if (more) {
+            body.prepare(j, nxt);
+            if (nxt.valid) ac_ld_group(body.t.slots + table_home(body.t, nxt.h), grp_next);
+        }
+        body.upsert(cur.valid, cur.fwd, cur.rc, cur.h, cur.flags, cur.g, grp);
+        if (!more) break;
+        cur = nxt; i = j;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) grp[x] = grp_next[x];
+        __syncwarp();
+    }
+}
+template <int W> static void ac_launch_insert(AcStream* st, const InsertBody<W>& body, uint64_t n, int ctas_per_sm) {
+    if (n == 0) return;
+    const uint64_t want = (n + 255) / 256, max_blocks = 148ull * (uint64_t)ctas_per_sm * 2;
+    const unsigned blocks = (unsigned)(want < max_blocks ? want : max_blocks);
+    switch (ctas_per_sm) {
+        case 6: ac_insert_kernel<W, 6><<<blocks, 256, 0, st->s>>>(body, n); break;
+        case 5: ac_insert_kernel<W, 5><<<blocks, 256, 0, st->s>>>(body, n); break;
+        case 3: ac_insert_kernel<W, 3><<<blocks, 256, 0, st->s>>>(body, n); break;
+        default: ac_insert_kernel<W, 4><<<blocks, 256, 0, st->s>>>(body, n); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("launch insert: ") + cudaGetErrorString(e));
+    ++g_ac_kernel_launches;
+}
+#endif
 
 // The sizing pass: how many distinct canonical k-mers are there?  A k-mer is sampled when a hash of the seven bases around its centre,
 // read on its canonical strand, ends in six zero bits — a property of the k-mer, so it is kept or dropped with ALL its occurrences and
@@ -367,11 +428,11 @@ template <int W> struct SampleBody {
 
 // Node-centric degrees (kmer_graph.rs:136-166) and the per-k-mer halves of the merge rule
 // (unitig_graph.rs:192-223): outOK(K) = outdeg(K)==1 && !first(rc K); inOK(K) = indeg(K)==1 && !first(K).
-AC_D void bloom_slot(uint64_t h, uint64_t n_words, uint64_t& word, uint64_t& mask) {   // 2 bits in one 64-bit word: one L2 access per test
+AC_D void bloom_slot(uint64_t h, uint64_t n_words, uint64_t& word, uint64_t& mask) {   // 3 bits in one 64-bit word: one L2 access per test
     word = ac_umul64hi(h * 0x9E3779B97F4A7C15ull, n_words);
-    mask = (1ull << (h & 63)) | (1ull << ((h >> 6) & 63));
+    mask = (1ull << (h & 63)) | (1ull << ((h >> 6) & 63)) | (1ull << ((h >> 12) & 63));
 }
-template <int W> struct BloomBuildBody {   // 16 filter bits per distinct k-mer, built once the table is complete
+template <int W> struct BloomBuildBody {   // 32 filter bits per distinct k-mer, built once the table is complete
     TableView t; KParams p; const uint32_t* occupied; uint64_t* bloom; uint64_t n_words;
     AC_D void operator()(uint64_t x) const {
         const Slot e = t.slots[occupied[x]];
@@ -414,8 +475,8 @@ template <int W> struct AdjacencyBody {
                 if (!((obs_in >> b) & 1u)) { Key<W> s = c, src = crc; key_push_left(s, b, p); key_push_right(src, 3 - b, p); if (present(s, src)) ++in_c; }
             }
             if (any_dotted) {   // "X." after c and ".X" before it (kmer_graph.rs:142,158 try '.' too)
-                { Key<W> s = c; key_push_right(s, 0, p); s.d = -1; if (table_find<W>(t, s, key_rc(s, p), p) != AC_NONE32) ++out_c; }
-                { Key<W> s = c; key_push_left(s, 0, p); s.d = 1; if (table_find<W>(t, s, key_rc(s, p), p) != AC_NONE32) ++in_c; }
+                { Key<W> s = c; key_push_right(s, 0, p); s.d = -1; if (present(s, key_rc(s, p))) ++out_c; }       // through the filter as well: nearly always absent
+                { Key<W> s = c; key_push_left(s, 0, p); s.d = 1; if (present(s, key_rc(s, p))) ++in_c; }
             }
         }
         uint32_t bits = 0;
@@ -460,10 +521,20 @@ struct BoundaryBody {
         const bool inside = interior[g0 >> 5] && g0 >= g_begin && g0 + 32 <= g_end;        // PackBody's flag: 32 windows of one sequence, none of them its first
 #ifdef __CUDA_ARCH__
         const uint32_t lane = (uint32_t)g & 31u;
-        const State me = state(g, inside);
-        State prev; prev.slot = __shfl_up_sync(0xFFFFFFFFu, me.slot, 1); prev.out_ok = __shfl_up_sync(0xFFFFFFFFu, (int)me.out_ok, 1) != 0;
-        prev.valid = true; prev.first = false; prev.in_ok = false;
-        if (lane == 0 && me.valid && !me.first) prev = state(g - 1, false);                   // the window before a word's first one (same sequence: me is not its first window)
+        State me, prev; prev.valid = true; prev.first = false; prev.in_ok = false;
+        if (inside) {         // 32 windows of one sequence and the window before them: no sequence lookups; lane 0 fetches both windows' slots together
+            const bool extra = lane == 0;
+            const uint32_t slot = pos_slot[g], slot_b = extra ? pos_slot[g - 1] : 0u;
+            const uint32_t fl = flags8[slot], fl_b = extra ? flags8[slot_b] : 0u;
+            const bool o = packed_base(packed, g + h) < 2, o_b = extra && packed_base(packed, g - 1 + h) < 2;
+            me.valid = true; me.first = false; me.slot = slot; me.in_ok = o ? (fl & 2u) : (fl & 1u); me.out_ok = o ? (fl & 1u) : (fl & 2u);
+            prev.slot = __shfl_up_sync(0xFFFFFFFFu, slot, 1); prev.out_ok = __shfl_up_sync(0xFFFFFFFFu, (int)me.out_ok, 1) != 0;
+            if (extra) { prev.slot = slot_b; prev.out_ok = o_b ? (fl_b & 1u) : (fl_b & 2u); }
+        } else {
+            me = state(g, false);
+            prev.slot = __shfl_up_sync(0xFFFFFFFFu, me.slot, 1); prev.out_ok = __shfl_up_sync(0xFFFFFFFFu, (int)me.out_ok, 1) != 0;
+            if (lane == 0 && me.valid && !me.first) prev = state(g - 1, false);               // the window before a word's first one (same sequence: me is not its first window)
+        }
         const uint32_t word = __ballot_sync(0xFFFFFFFFu, starts(me, prev));
         if (lane == 0) { bmask[g0 >> 5] = word; bcount[g0 >> 5] = (uint32_t)__popc(word); }
 #else
@@ -565,23 +636,24 @@ struct RunAssignBody {
     }
 };
 
-// Multi-GPU exchange of the deduplicated local tables ("k-mer buckets"): the occupied slots, compacted.
-struct ExportFlagBody {
-    const Slot* slots; uint32_t* flag;
-    AC_D void operator()(uint64_t i) const { flag[i] = slots[i] != AC_EMPTY_SLOT ? 1u : 0u; }
+// The distinct k-mers as a list of their slots: the windows that claimed a slot (InsertBody::claimed_bits), compacted.
+struct ClaimedCountBody { const uint32_t* bits; uint64_t n_words; uint32_t* cnt; AC_D void operator()(uint64_t w) const { cnt[w] = w < n_words ? ac_popc(bits[w]) : 0u; } };
+struct ClaimedListBody {
+    const uint32_t* bits; const uint32_t* off; const uint32_t* pos_slot; uint32_t* list;
+    AC_D void operator()(uint64_t w) const {
+        uint32_t m = bits[w], at = off[w];
+        while (m) { const int b = ac_ctz(m); list[at++] = pos_slot[w * 32 + (uint64_t)b]; m &= m - 1; }
+    }
 };
-struct OccupiedListBody {
-    const Slot* slots; const uint32_t* off; uint32_t* list;
-    AC_D void operator()(uint64_t i) const { if (slots[i] != AC_EMPTY_SLOT) list[off[i]] = (uint32_t)i; }
-};
+// Multi-GPU exchange of the deduplicated local tables ("k-mer buckets"): the occupied slots, by the list the insert kernel made.
 struct ExportScatterBody {
-    TableView t; const uint32_t* off; SlotRec* out;
-    AC_D void operator()(uint64_t i) const { const Slot s = t.slots[i]; if (s != AC_EMPTY_SLOT) { SlotRec r; r.slot = s; r.count = table_depth(t, i); r.pad = 0; out[off[i]] = r; } }
+    TableView t; const uint32_t* occupied; SlotRec* out;
+    AC_D void operator()(uint64_t x) const { const uint64_t i = occupied[x]; SlotRec r; r.slot = t.slots[i]; r.count = table_depth(t, i); r.pad = 0; out[x] = r; }
 };
 // Folding another rank's entries into this rank's table: counts add, first/last flags OR, the entry keeps the smaller
 // occurrence.  Every rank holds all packed sequences, so the k-mer behind a remote entry is read from `packed`.
 template <int W> struct MergeBody {
-    TableView t; KParams p; const SlotRec* in; uint32_t* pos_slot; unsigned long long* counters;
+    TableView t; KParams p; const SlotRec* in; uint32_t* pos_slot; unsigned long long* counters; uint32_t* claimed_bits;
     AC_D void operator()(uint64_t i) const {
         const SlotRec r = in[i];
         const uint64_t g = slot_gpos(r.slot, t.gb);
@@ -599,7 +671,7 @@ template <int W> struct MergeBody {
             Slot e = ac_ld_cg(&t.slots[slot]);
             if (e == AC_EMPTY_SLOT) {
                 e = ac_atomic_cas(&t.slots[slot], (Slot)AC_EMPTY_SLOT, mine);
-                if (e == AC_EMPTY_SLOT) { if (t.count_big) ac_atomic_add(&t.count_big[slot], r.count); if (dotted) ac_atomic_add(&counters[1], 1ull); break; }
+                if (e == AC_EMPTY_SLOT) { if (t.count_big) ac_atomic_add(&t.count_big[slot], r.count); if (dotted) ac_atomic_add(&counters[1], 1ull); ac_atomic_or(&claimed_bits[g >> 5], 1u << (g & 31u)); break; }
             }
             if (slot_tag(e, t.gb) == tag) {
                 const Key<W> rep = window_key<W>(t, slot_gpos(e, t.gb), dotted, p);
@@ -706,13 +778,13 @@ template <int W> struct LinkBody {
 // seed k-mers.  The seeds are minima, so their leading bits are heavily skewed and bucketing on them does not work;
 // a bottom-up merge sort does: in every pass each element finds its place in the merged pair of runs with one binary
 // search in the sibling run (thread per element, U <= ~10^6 keys, all of them L2 resident).
-struct SortKey24 { uint64_t a, b; uint32_t c, d; };     // what a comparator stages in shared memory for the tile sort: 24 bytes per element
+struct alignas(16) SortRec { uint64_t a, b; uint32_t c, d, id, pad; };     // what the sorts move around: a comparator's 24-byte key and the id it belongs to
 struct SeedLess {
     const DeviceUnitig* unitigs; int W;
-    typedef SortKey24 Key;      // a: first key word, b: second (0 for W = 1), c: leading dots, d: trailing dots
+    typedef SortRec Key;      // a: first key word, b: second (0 for W = 1), c: leading dots, d: trailing dots
     AC_D Key load(uint32_t id) const {
         const DeviceUnitig& x = unitigs[id];
-        Key k; k.a = x.min_w[0]; k.b = W > 1 ? x.min_w[1] : 0; k.c = x.min_d > 0 ? (uint32_t)x.min_d : 0u; k.d = x.min_d < 0 ? (uint32_t)-x.min_d : 0u;
+        Key k; k.id = id; k.pad = 0; k.a = x.min_w[0]; k.b = W > 1 ? x.min_w[1] : 0; k.c = x.min_d > 0 ? (uint32_t)x.min_d : 0u; k.d = x.min_d < 0 ? (uint32_t)-x.min_d : 0u;
         return k;
     }
     AC_D bool less_keys(const Key& x, const Key& y, uint32_t ia, uint32_t ib) const {
@@ -732,38 +804,61 @@ struct SeedLess {
     }
 };
 #define AC_SORT_LEAF 8
-template <class Less> struct MergePassBody {
-    Less less; uint32_t n, width; const uint32_t* in; uint32_t* out;
+#define AC_SORT_WAYS 8          // runs merged per global pass: 2048 -> 16 Ki -> 128 Ki -> 1 Mi elements
+// One merge pass over self-contained 32-byte records (the comparison key with the id inside): AC_SORT_WAYS sorted runs of `width`
+// become one.  Every element finds how many elements of each sibling run go before it — for an earlier run those not above it, for a
+// later run those strictly below it — with the binary searches in the siblings advanced in lockstep, so that their loads (one record per
+// step and sibling, nothing to chase) are in flight together.  A pass costs about one search's latency; three passes sort a million.
+template <class Less> struct MergeWaysBody {
+    Less less; uint32_t n, width, steps; const SortRec* in; SortRec* out; uint32_t* idx_out;
     AC_D void operator()(uint64_t i) const {
-        const uint32_t me = in[i];
-        const uint32_t run = (uint32_t)i / width, pair_start = (run & ~1u) * width, run_start = run * width;
-        uint32_t lo, hi;                                   // the sibling run
-        const bool left = !(run & 1u);
-        if (left) { lo = run_start + width; hi = lo + width; } else { lo = pair_start; hi = run_start; }
-        if (lo > n) lo = n;
-        if (hi > n) hi = n;
-        const uint32_t base = lo;
-        while (lo < hi) {                                  // left run: elements of the sibling strictly below me; right run: not above me
-            const uint32_t mid = (lo + hi) >> 1;
-            const bool before = left ? less(in[mid], me) : !less(me, in[mid]);
-            if (before) lo = mid + 1; else hi = mid;
+        const SortRec me = in[i];
+        const uint64_t run = i / width, group = run / AC_SORT_WAYS, group_start = group * AC_SORT_WAYS * (uint64_t)width;
+        uint32_t lo[AC_SORT_WAYS], hi[AC_SORT_WAYS];
+#pragma unroll
+        for (int s = 0; s < AC_SORT_WAYS; ++s) {
+            const uint64_t first = group_start + (uint64_t)s * width, last = first + width;
+            lo[s] = (uint32_t)(first < n ? first : n); hi[s] = (uint32_t)(last < n ? last : n);
+            if (group * AC_SORT_WAYS + s == run) hi[s] = lo[s];          // my own run: nothing to count
         }
-        out[pair_start + ((uint32_t)i - run_start) + (lo - base)] = me;
+        for (uint32_t step = 0; step < steps; ++step) {
+#pragma unroll
+            for (int s = 0; s < AC_SORT_WAYS; ++s) {
+                if (lo[s] < hi[s]) {
+                    const uint32_t mid = (lo[s] + hi[s]) >> 1;
+                    const SortRec x = in[mid];
+                    const bool earlier = group * AC_SORT_WAYS + s < run;
+                    const bool before = earlier ? !less.less_keys(me, x, me.id, x.id) : less.less_keys(x, me, x.id, me.id);
+                    if (before) lo[s] = mid + 1; else hi[s] = mid;
+                }
+            }
+        }
+        uint64_t pos = group_start + (i - run * width);
+#pragma unroll
+        for (int s = 0; s < AC_SORT_WAYS; ++s) {
+            const uint64_t first = group_start + (uint64_t)s * width;
+            if (group * AC_SORT_WAYS + s != run && first < n) pos += lo[s] - (uint32_t)first;
+        }
+        out[pos] = me; idx_out[pos] = me.id;
     }
 };
 
-// The first eleven merge levels inside one CTA: AC_SORT_TILE indices are sorted in shared memory (insertion-sorted leaves of 8, then
-// merge rounds with a block barrier instead of a launch between them).  Every `Less` used here is a strict total order (ties end at
-// the index or an earlier position), so the result does not depend on how the sort is carried out.
-#define AC_SORT_TILE 2048
+// The first eleven merge levels inside one CTA: AC_SORT_TILE records are sorted in shared memory (insertion-sorted leaves of 8, then
+// merge rounds with a block barrier instead of a launch between them; 4-way rounds were tried and lost, r2i).  Every `Less` used here is a strict total order (ties
+// end at the index or an earlier position), so the result does not depend on how the sort is carried out.
 #ifndef AC_EMULATE
-template <class Less> __global__ void __launch_bounds__(512) ac_tile_sort_kernel(const Less less, uint32_t n, uint32_t* __restrict__ idx) {
-    extern __shared__ unsigned char tile_smem[];
-    typename Less::Key* keys = reinterpret_cast<typename Less::Key*>(tile_smem);                    // [AC_SORT_TILE] the comparison keys, staged once
-    uint16_t* buf0 = reinterpret_cast<uint16_t*>(tile_smem + AC_SORT_TILE * sizeof(typename Less::Key));   // local ids, ping
+#define AC_SORT_TILE 2048
+#else
+#define AC_SORT_TILE 16          // small tiles: the CPU suite's graphs then go through several merge passes
+#endif
+#ifndef AC_EMULATE
+template <class Less> __global__ void __launch_bounds__(512) ac_tile_sort_kernel(const Less less, uint32_t n, uint32_t* __restrict__ idx, SortRec* __restrict__ recs) {
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    SortRec* keys = reinterpret_cast<SortRec*>(tile_smem);                                           // [AC_SORT_TILE] the records, staged once
+    uint16_t* buf0 = reinterpret_cast<uint16_t*>(tile_smem + AC_SORT_TILE * sizeof(SortRec));         // local ids, ping
     uint16_t* buf1 = buf0 + AC_SORT_TILE;                                                            // pong
     const uint32_t base = blockIdx.x * AC_SORT_TILE, count = n - base < AC_SORT_TILE ? n - base : AC_SORT_TILE;
-    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) keys[i] = less.load(base + i);
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) { SortRec r = less.load(base + i); r.id = base + i; r.pad = 0; keys[i] = r; }
     __syncthreads();
     auto before = [&](uint32_t x, uint32_t y) { return less.less_keys(keys[x], keys[y], base + x, base + y); };
     if (threadIdx.x < AC_SORT_TILE / AC_SORT_LEAF) {   // leaves: 8 consecutive ids per thread
@@ -794,11 +889,11 @@ template <class Less> __global__ void __launch_bounds__(512) ac_tile_sort_kernel
         __syncthreads();
         uint16_t* t = in; in = out; out = t;
     }
-    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) idx[base + i] = base + in[i];
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) { const SortRec r = keys[in[i]]; recs[base + i] = r; idx[base + i] = r.id; }
 }
 #endif
 template <class Less> struct TileSortBody {   // emulation form: any correct sort of the tile
-    Less less; uint32_t n; uint32_t* idx;
+    Less less; uint32_t n; uint32_t* idx; SortRec* recs;
     AC_D void operator()(uint64_t c) const {
         const uint32_t a = (uint32_t)c * AC_SORT_TILE, b = a + AC_SORT_TILE < n ? a + AC_SORT_TILE : n;
         for (uint32_t x = a; x < b; ++x) {
@@ -806,24 +901,26 @@ template <class Less> struct TileSortBody {   // emulation form: any correct sor
             while (y > a && less(x, idx[y - 1])) { idx[y] = idx[y - 1]; --y; }
             idx[y] = x;
         }
+        for (uint32_t x = a; x < b; ++x) { SortRec r = less.load(idx[x]); r.id = idx[x]; r.pad = 0; recs[x] = r; }
     }
 };
-// Sorts the ids 0..n-1 by `less`; returns the buffer (a or b) that holds the result.
-template <class Less> static uint32_t* sort_indices(AcStream* stream, const Less& less, uint32_t n, uint32_t* a, uint32_t* b) {
+// Sorts the ids 0..n-1 by `less`; returns the buffer (a or b) that holds the result.  ra / rb: n records each.
+template <class Less> static uint32_t* sort_indices(AcStream* stream, const Less& less, uint32_t n, uint32_t* a, uint32_t* b, SortRec* ra, SortRec* rb) {
     if (n == 0) return a;
     const uint64_t tiles = ((uint64_t)n + AC_SORT_TILE - 1) / AC_SORT_TILE;
 #ifndef AC_EMULATE
-    const size_t smem = AC_SORT_TILE * (sizeof(typename Less::Key) + 2 * sizeof(uint16_t));
+    const size_t smem = AC_SORT_TILE * (sizeof(SortRec) + 2 * sizeof(uint16_t));
     AC_CUDA_CHECK(cudaFuncSetAttribute(ac_tile_sort_kernel<Less>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      // per device: cheap enough to repeat
-    ac_tile_sort_kernel<Less><<<(unsigned)tiles, 512, smem, stream->s>>>(less, n, a); ++g_ac_kernel_launches;
+    ac_tile_sort_kernel<Less><<<(unsigned)tiles, 512, smem, stream->s>>>(less, n, a, ra); ++g_ac_kernel_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("launch tile sort: ") + cudaGetErrorString(e));
 #else
-    ac_launch("tile_sort", stream, TileSortBody<Less>{less, n, a}, tiles);
+    ac_launch("tile_sort", stream, TileSortBody<Less>{less, n, a, ra}, tiles);
 #endif
-    for (uint64_t width = AC_SORT_TILE; width < n; width *= 2) {
-        ac_launch("merge_pass", stream, MergePassBody<Less>{less, n, (uint32_t)width, a, b}, n);
-        std::swap(a, b);
+    for (uint64_t width = AC_SORT_TILE; width < n; width *= AC_SORT_WAYS) {
+        uint32_t steps = 1; while ((1ull << steps) <= width) ++steps;          // a search over at most `width` elements ends within this many halvings
+        ac_launch("merge_pass", stream, MergeWaysBody<Less>{less, n, (uint32_t)width, steps, ra, rb, b}, n);
+        std::swap(a, b); std::swap(ra, rb);
     }
     return a;
 }
@@ -842,8 +939,8 @@ struct NumberKeyBody {
 };
 struct NumberKeyLess {      // sort_number_keys: the part of renumber_unitigs' order that 16 bytes per unitig can decide
     const NumberKey* key;
-    typedef SortKey24 Key;
-    AC_D Key load(uint32_t id) const { Key k; k.a = key[id].prefix; k.b = 0; k.c = key[id].len; k.d = 0; return k; }
+    typedef SortRec Key;
+    AC_D Key load(uint32_t id) const { Key k; k.id = id; k.pad = 0; k.a = key[id].prefix; k.b = 0; k.c = key[id].len; k.d = 0; return k; }
     AC_D bool less_keys(const Key& x, const Key& y, uint32_t ia, uint32_t ib) const {
         if (x.c != y.c) return x.c > y.c;
         if (x.a != y.a) return x.a < y.a;
@@ -859,8 +956,8 @@ struct InversePermBody { const uint32_t* order; uint32_t* pos; AC_D void operato
 struct NumberLess {
     const UnitigRec* rec; const uint32_t* depth; const char* arena; const uint64_t* prefix;
     const uint32_t* pos;     // ties keep the order the unitigs are in: creation order (null) or their place in an earlier numbering
-    typedef SortKey24 Key;      // a: first 8 bases, b: position that settles ties, c: length, d: depth
-    AC_D Key load(uint32_t id) const { Key k; k.a = prefix[id]; k.b = pos ? pos[id] : id; k.c = rec[id].len; k.d = depth[id]; return k; }
+    typedef SortRec Key;      // a: first 8 bases, b: position that settles ties, c: length, d: depth
+    AC_D Key load(uint32_t id) const { Key k; k.id = id; k.pad = 0; k.a = prefix[id]; k.b = pos ? pos[id] : id; k.c = rec[id].len; k.d = depth[id]; return k; }
     AC_D bool less_keys(const Key& x, const Key& y, uint32_t ia, uint32_t ib) const {
         if (x.c != y.c) return x.c > y.c;
         if (x.a != y.a) return x.a < y.a;
@@ -1577,6 +1674,74 @@ __global__ void __launch_bounds__(256) ac_scan_apply_kernel(const uint32_t* in, 
         __syncthreads();
     }
 }
+// The same scan in ONE launch ("chained scan with decoupled look-back"): a CTA takes the next tile by ticket, publishes the tile's sum,
+// finds its exclusive prefix by looking back over the tiles before it — their sums until one of them has its inclusive prefix out — and
+// scans its tile from registers (out may alias in).  A state word is [scan number:30 | status:2 | value:32], so words left by earlier
+// scans never match and nothing has to be cleared between scans; tickets count up for ever (the host passes where this scan's begin).
+#define AC_SCAN_STATE(epoch, status, value) (((unsigned long long)(epoch) << 34) | ((unsigned long long)(status) << 32) | (unsigned long long)(value))
+__global__ void __launch_bounds__(256) ac_scan_chained_kernel(const uint32_t* in, uint64_t n, uint32_t* out, unsigned long long* state, unsigned long long epoch,
+                                                               unsigned long long* ticket, unsigned long long ticket_base, uint32_t n_tiles, uint32_t* total_out) {
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t s_tile, s_prefix;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = (uint32_t)(atomicAdd(ticket, 1ull) - ticket_base);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tile0 = (uint64_t)tile * AC_SCAN_TILE;
+    uint32_t v[AC_SCAN_TILE / 1024][4], t[AC_SCAN_TILE / 1024], mine = 0;
+#pragma unroll
+    for (int r = 0; r < AC_SCAN_TILE / 1024; ++r) {
+        const uint64_t i = tile0 + (uint64_t)r * 1024 + threadIdx.x * 4;
+        if (i + 3 < n) { const uint4 q = *reinterpret_cast<const uint4*>(in + i); v[r][0] = q.x; v[r][1] = q.y; v[r][2] = q.z; v[r][3] = q.w; }
+        else { for (int j = 0; j < 4; ++j) v[r][j] = (i + j < n) ? in[i + j] : 0; }
+        t[r] = v[r][0] + v[r][1] + v[r][2] + v[r][3]; mine += t[r];
+    }
+    uint32_t sum = mine;
+    for (int o = 16; o; o >>= 1) sum += __shfl_down_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) warp_tot[warp] = sum;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t total = 0;
+        for (int w2 = 0; w2 < 8; ++w2) total += warp_tot[w2];
+        uint32_t prefix = 0;
+        if (tile > 0) {
+            if (lane == 0) *(volatile unsigned long long*)&state[tile] = AC_SCAN_STATE(epoch, 1, total);
+            for (int64_t first = (int64_t)tile - 1; first >= 0; first -= 32) {      // 32 predecessors at a time, nearest first
+                const int64_t j = first - lane;
+                unsigned long long w = AC_SCAN_STATE(epoch, 2, 0);                  // lanes past tile 0: an inclusive prefix of nothing
+                if (j >= 0) do { w = *(volatile unsigned long long*)&state[j]; } while ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0);
+                const unsigned closed = __ballot_sync(0xFFFFFFFFu, ((w >> 32) & 3ull) == 2);
+                const int stop = closed ? __ffs((int)closed) - 1 : 31;               // the nearest tile whose inclusive prefix is out
+                uint32_t part = (int)lane <= stop ? (uint32_t)w : 0u;
+                for (int o = 16; o; o >>= 1) part += __shfl_down_sync(0xFFFFFFFFu, part, o);
+                prefix += __shfl_sync(0xFFFFFFFFu, part, 0);
+                if (closed) break;
+            }
+        }
+        if (lane == 0) {
+            *(volatile unsigned long long*)&state[tile] = AC_SCAN_STATE(epoch, 2, prefix + total);
+            s_prefix = prefix;
+            if (tile + 1 == n_tiles && total_out) *total_out = prefix + total;
+        }
+    }
+    __syncthreads();
+    uint32_t carry = s_prefix;
+#pragma unroll
+    for (int r = 0; r < AC_SCAN_TILE / 1024; ++r) {
+        const uint64_t i = tile0 + (uint64_t)r * 1024 + threadIdx.x * 4;
+        uint32_t inc = t[r];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= (uint32_t)o) inc += u; }
+        __syncthreads();                  // warp_tot is reused every round
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+        for (uint32_t w2 = 0; w2 < 8; ++w2) { const uint32_t x = warp_tot[w2]; if (w2 < warp) wbase += x; total += x; }
+        uint32_t e = carry + wbase + inc - t[r];
+        if (i + 3 < n) { uint4 q; q.x = e; q.y = e + v[r][0]; q.z = q.y + v[r][1]; q.w = q.z + v[r][2]; *reinterpret_cast<uint4*>(out + i) = q; }
+        else { for (int j = 0; j < 4; ++j) { if (i + j < n) out[i + j] = e; e += v[r][j]; } }
+        carry += total;
+    }
+}
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -1604,9 +1769,9 @@ struct DevicePipeline::Impl {
     DevBuf ascii, packed, seqs, slots, pos_slot, flags8, bmask, bcount, boff, counters, uid_rep, slot_unitig;
     DevBuf run_start, run_len, run_uk, run_dir, is_rep, rep_idx, run_unitig, unitigs, nchunks, chunk_off, partial, link_count, links;
     DevBuf scan_tmp[4];
-    int insert_occupancy = getenv("AC_INSERT_OCC") ? atoi(getenv("AC_INSERT_OCC")) : 6;   // resident CTAs per SM the insert kernel is compiled for (5, 6 or 8)
+    int insert_occupancy = getenv("AC_INSERT_OCC") ? atoi(getenv("AC_INSERT_OCC")) : 4;   // resident CTAs per SM the insert kernel is compiled for (3 to 6)
     DevBuf d_fixed, cand_flag, cand_index, d_cands, d_cand_at, d_deps, d_spec;
-    DevBuf sort_a, sort_b, num_prefix, rank, d_len, d_depth, need, d_seq_off, d_arena, d_min_fpos, d_min_rpos;
+    DevBuf sort_a, sort_b, sort_ra, sort_rb, num_prefix, rank, d_len, d_depth, need, d_seq_off, d_arena, d_min_fpos, d_min_rpos;
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
     PinBuf h_cands, h_deps, h_spec, h_fixed, h_keys, h_sorted;
@@ -1643,52 +1808,55 @@ struct DevicePipeline::Impl {
     }
 
     // exclusive scan of n uint32 values; returns the total (when asked: it costs the one host round trip).  out may alias in.
+#ifndef AC_EMULATE
+    DevBuf scan_state; unsigned long long scan_epoch = 0, scan_tickets = 0;
+    uint32_t exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, int = 0, bool want_total = true) {
+        if (n == 0) return 0;
+        const uint64_t nb = (n + AC_SCAN_TILE - 1) / AC_SCAN_TILE;
+        if (nb > 0x7FFFFFFFull) throw std::runtime_error("scan too large");
+        if ((nb + 4) * 8 > scan_state.cap) {      // [0] ticket counter, [1] the total, [2..] one state word per tile; zeroed once: scan numbers start at 1
+            scan_state.ensure((nb + 4) * 8 * 2);
+            ac_memset(scan_state.p, 0, scan_state.cap, &stream);
+            scan_tickets = 0;
+        }
+        unsigned long long* st = scan_state.as<unsigned long long>();
+        scan_epoch = (scan_epoch + 1) & 0x3FFFFFFFull; if (scan_epoch == 0) scan_epoch = 1;
+        ac_scan_chained_kernel<<<(unsigned)nb, 256, 0, stream.s>>>(in, n, out, st + 2, scan_epoch, st, scan_tickets, (uint32_t)nb, (uint32_t*)(st + 1)); ++g_ac_kernel_launches;
+        scan_tickets += nb;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) throw std::runtime_error(std::string("launch scan: ") + cudaGetErrorString(e));
+        uint32_t total_sum = 0;
+        if (want_total) { ac_d2h(&total_sum, st + 1, sizeof(uint32_t), &stream); ac_sync(&stream); }
+        return total_sum;
+    }
+#else
     uint32_t exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, int level = 0, bool want_total = true) {
         if (n == 0) return 0;
         if (level >= 4) throw std::runtime_error("scan too deep");
-#ifndef AC_EMULATE
-        const uint64_t tile = AC_SCAN_TILE;
-#else
         const uint64_t tile = 256;
-#endif
         const uint64_t nb = (n + tile - 1) / tile;
         scan_tmp[level].ensure((nb + 4) * sizeof(uint32_t));
         uint32_t* sums = scan_tmp[level].as<uint32_t>();
-        auto reduce = [&]() {
-#ifndef AC_EMULATE
-            ac_scan_reduce_kernel<<<(unsigned)nb, 256, 0, stream.s>>>(in, n, sums); ++g_ac_kernel_launches;
-#else
-            ac_launch("scan_reduce", &stream, ScanReduceBody{in, n, sums}, nb);
-#endif
-        };
-        auto apply = [&](const uint32_t* block_off) {
-#ifndef AC_EMULATE
-            ac_scan_apply_kernel<<<(unsigned)nb, 256, 0, stream.s>>>(in, n, block_off, out); ++g_ac_kernel_launches;
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) throw std::runtime_error(std::string("launch scan: ") + cudaGetErrorString(e));
-#else
-            ac_launch("scan_apply", &stream, ScanApplyBody{in, n, block_off, out}, nb);
-#endif
-        };
         if (nb > 0x7FFFFFFFull) throw std::runtime_error("scan too large");
-        reduce();
+        ac_launch("scan_reduce", &stream, ScanReduceBody{in, n, sums}, nb);
         uint32_t total_sum = 0;
         if (nb == 1) {
             if (want_total) { ac_d2h(&total_sum, sums, sizeof(uint32_t), &stream); ac_sync(&stream); }
-            apply(nullptr);
+            ac_launch("scan_apply", &stream, ScanApplyBody{in, n, nullptr, out}, nb);
         } else {
             total_sum = exclusive_scan(sums, sums, nb, level + 1, want_total);
-            apply(sums);
+            ac_launch("scan_apply", &stream, ScanApplyBody{in, n, sums, out}, nb);
         }
         return total_sum;
     }
+#endif
 
     // pipeline state shared by the stages
     std::vector<SeqInfo> host_seqs;
     uint64_t cap = 0, n_windows = 0, n_runs = 0, g_begin = 0, g_end = 0, n_slots_used = 0, n_dotted = 0;
     bool any_dotted = false, is_multi = false, big_counts = false;      // big_counts: depths live in count_big (a 20-bit slot count neared its end)
     int stage = 0;
-    DevBuf run_hs, run_ts, exp_flag, occ_list, bloom, needles, hits, count_big, interior8;
+    DevBuf run_hs, run_ts, claimed, claimed_cnt, occ_list, bloom, needles, hits, count_big, interior8;
     TableView table_view() { return TableView{slots.as<Slot>(), cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, big_counts ? count_big.as<uint32_t>() : nullptr, slot_gpos_bits(total), count_alarm()}; }
     static uint32_t count_alarm() { static const uint32_t a = getenv("AC_COUNT_ALARM") ? (uint32_t)atoi(getenv("AC_COUNT_ALARM")) : AC_SLOT_COUNT_ALARM; return a; }      // test hook: a lower threshold
     void set_device() {
@@ -1717,6 +1885,7 @@ struct DevicePipeline::Impl {
         ac_copy_dd(total_dst, x + (n - 1), 4, &stream);
     }
     uint64_t exp_n = 0;
+    uint64_t list_claimed();
     uint64_t do_count_entries();
     void do_export_entries(void* dst, uint64_t cap_records);
     void do_export_runs(void* dst, uint64_t cap_records);
@@ -1801,10 +1970,10 @@ void DevicePipeline::sort_number_keys(const NumberKey* keys, uint32_t n, uint32_
     if (n == 0) return;
     m.h_keys.ensure((size_t)n * sizeof(NumberKey));                 // pinned staging: the copy runs at link speed and the call stays asynchronous until the sync
     memcpy(m.h_keys.p, keys, (size_t)n * sizeof(NumberKey));
-    m.d_keys.ensure((size_t)n * sizeof(NumberKey)); m.sort_a.ensure((size_t)n * 4); m.sort_b.ensure((size_t)n * 4);
+    m.d_keys.ensure((size_t)n * sizeof(NumberKey)); m.sort_a.ensure((size_t)n * 4); m.sort_b.ensure((size_t)n * 4); m.sort_ra.ensure((size_t)n * sizeof(SortRec)); m.sort_rb.ensure((size_t)n * sizeof(SortRec));
     ac_h2d(m.d_keys.p, m.h_keys.p, (size_t)n * sizeof(NumberKey), &m.stream);
     const NumberKeyLess less{m.d_keys.as<NumberKey>()};
-    uint32_t* in = sort_indices(&m.stream, less, n, m.sort_a.as<uint32_t>(), m.sort_b.as<uint32_t>());
+    uint32_t* in = sort_indices(&m.stream, less, n, m.sort_a.as<uint32_t>(), m.sort_b.as<uint32_t>(), m.sort_ra.as<SortRec>(), m.sort_rb.as<SortRec>());
     m.h_sorted.ensure((size_t)n * 4);
     ac_d2h(m.h_sorted.p, in, (size_t)n * 4, &m.stream);
     ac_sync(&m.stream);
@@ -1909,7 +2078,7 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
         ac_memset(slots.p, 0xFF, sample_cap * sizeof(Slot), &stream);
         ac_memset(counters.p, 0, sizeof hc, &stream);
         const TableView sv{slots.as<Slot>(), sample_cap, packed.as<uint64_t>(), seqs.as<SeqInfo>(), n_seqs, nullptr, slot_gpos_bits(total), AC_SLOT_COUNT_ALARM};
-        const InsertBody<W> sample_ins{sv, p, interior8.as<uint8_t>(), 0, 0, (uint32_t)total, false, nullptr, counters.as<unsigned long long>(), true};
+        const InsertBody<W> sample_ins{sv, p, interior8.as<uint8_t>(), 0, 0, (uint32_t)total, false, nullptr, counters.as<unsigned long long>(), true, nullptr};
         ac_launch("sample", &stream, SampleBody<W>{sample_ins, (uint32_t)total}, ((total + 31) / 32 + 31) / 32 * 32);
         ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
         if (!hc[2]) {      // every rank samples every sequence, so all of them arrive at the same size
@@ -1930,8 +2099,14 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
         ac_memset(counters.p, 0, sizeof hc, &stream);
         const TableView tv = table_view();
         const uint64_t g_first = g_begin & ~31ull;
-        const InsertBody<W> ins{tv, p, interior8.as<uint8_t>(), (uint32_t)g_first, (uint32_t)g_begin, (uint32_t)g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), false};
-        ac_launch_occ("insert", &stream, ins, (g_end - g_first + 31) / 32 * 32, insert_occupancy);
+        claimed.ensure((n_words + 8) * 4); ac_memset(claimed.p, 0, (n_words + 8) * 4, &stream);
+        const InsertBody<W> ins{tv, p, interior8.as<uint8_t>(), (uint32_t)g_first, (uint32_t)g_begin, (uint32_t)g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), false, claimed.as<uint32_t>()};
+#ifndef AC_EMULATE
+        static const bool plain_loop = getenv("AC_INSERT_PLAIN") != nullptr;      // comparison: the loop without the prefetch of the next unit's home group
+        if (!plain_loop) ac_launch_insert<W>(&stream, ins, (g_end - g_first + 31) / 32 * 32, insert_occupancy);
+        else
+#endif
+        ac_launch_occ("insert", &stream, ins, (g_end - g_first + 31) / 32 * 32, insert_occupancy == 4 || insert_occupancy == 3 ? 5 : insert_occupancy);
         ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
         if (hc[2] && cap != safe_cap) { cap = safe_cap; continue; }         // the estimate was off (it is an estimate): start again with the safe size
         if (hc[2]) throw std::runtime_error("k-mer table overflow");
@@ -1943,23 +2118,31 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
     stage = 1;
 }
 
+// The list of distinct k-mers (their slots) from the claim bits; returns how many there are.
+uint64_t DevicePipeline::Impl::list_claimed() {
+    const uint64_t n_words = (total + 31) / 32;
+    claimed_cnt.ensure((n_words + 1) * 4);
+    ac_launch("claimed_count", &stream, ClaimedCountBody{claimed.as<uint32_t>(), n_words, claimed_cnt.as<uint32_t>()}, n_words + 1);
+    const uint64_t n = exclusive_scan(claimed_cnt.as<uint32_t>(), claimed_cnt.as<uint32_t>(), n_words + 1);
+    occ_list.ensure((n + 1) * 4);
+    ac_launch("claimed_list", &stream, ClaimedListBody{claimed.as<uint32_t>(), claimed_cnt.as<uint32_t>(), pos_slot.as<uint32_t>(), occ_list.as<uint32_t>()}, n_words);
+    return n;
+}
 uint64_t DevicePipeline::Impl::do_count_entries() {
     if (stage < 1) throw std::runtime_error("build_local must precede the entry export");
-    exp_flag.ensure(cap * 4);
-    ac_launch("export_flag", &stream, ExportFlagBody{slots.as<Slot>(), exp_flag.as<uint32_t>()}, cap);
-    exp_n = exclusive_scan(exp_flag.as<uint32_t>(), exp_flag.as<uint32_t>(), cap);
+    exp_n = list_claimed();                // before any merge: the local table
     return exp_n;
 }
 void DevicePipeline::Impl::do_export_entries(void* dst, uint64_t cap_records) {
     if (cap_records < exp_n) throw std::runtime_error("entry buffer too small");
-    ac_launch("export_scatter", &stream, ExportScatterBody{table_view(), exp_flag.as<uint32_t>(), (SlotRec*)dst}, cap);
+    ac_launch("export_scatter", &stream, ExportScatterBody{table_view(), occ_list.as<uint32_t>(), (SlotRec*)dst}, exp_n);
     ac_sync(&stream);
 }
 
 template <int W> void DevicePipeline::Impl::merge_w(const void* dev_ptr, uint64_t n) {
     if (stage < 1) throw std::runtime_error("build_local must precede merge_entries");
     const KParams p = make_kparams(k, W);
-    ac_launch("merge", &stream, MergeBody<W>{table_view(), p, (const SlotRec*)dev_ptr, pos_slot.as<uint32_t>(), counters.as<unsigned long long>()}, n);
+    ac_launch("merge", &stream, MergeBody<W>{table_view(), p, (const SlotRec*)dev_ptr, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), claimed.as<uint32_t>()}, n);
 }
 
 // ---- stage 2: adjacency over the (now global) table, unitig occurrences along this rank's sequences ----
@@ -1978,12 +2161,8 @@ template <int W> void DevicePipeline::Impl::runs_local_w() {
     any_dotted = n_dotted != 0;
 
     flags8.ensure(cap);
-    exp_flag.ensure(cap * 4);
-    ac_launch("occupied_flag", &stream, ExportFlagBody{slots.as<Slot>(), exp_flag.as<uint32_t>()}, cap);
-    n_slots_used = exclusive_scan(exp_flag.as<uint32_t>(), exp_flag.as<uint32_t>(), cap);       // distinct canonical k-mers = occupied slots
-    occ_list.ensure((n_slots_used + 1) * 4);
-    ac_launch("occupied_list", &stream, OccupiedListBody{slots.as<Slot>(), exp_flag.as<uint32_t>(), occ_list.as<uint32_t>()}, cap);
-    const uint64_t bloom_words = n_slots_used / 4 + 64;       // 16 bits per distinct k-mer
+    n_slots_used = list_claimed();          // distinct canonical k-mers (with the other ranks' after a merge)
+    const uint64_t bloom_words = n_slots_used / 2 + 64;       // 32 bits per distinct k-mer, 3 set per k-mer: one test in 1,500 passes by chance (26 MB for BASELINE config 2: L2 resident)
     bloom.ensure(bloom_words * 8);
     ac_memset(bloom.p, 0, bloom_words * 8, &stream);
     ac_launch("bloom_build", &stream, BloomBuildBody<W>{tv, p, occ_list.as<uint32_t>(), bloom.as<uint64_t>(), bloom_words}, n_slots_used);
@@ -2075,9 +2254,9 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
 
     // ---- seed order: stable LSD radix sort of the unitigs by their seed k-mer ----
     const uint32_t U = n_unitigs;
-    sort_a.ensure((size_t)U * 4); sort_b.ensure((size_t)U * 4);
+    sort_a.ensure((size_t)U * 4); sort_b.ensure((size_t)U * 4); sort_ra.ensure((size_t)U * sizeof(SortRec)); sort_rb.ensure((size_t)U * sizeof(SortRec));
     const SeedLess seed_less{unitigs.as<DeviceUnitig>(), W};
-    const uint32_t* perm = sort_indices(&stream, seed_less, U, sort_a.as<uint32_t>(), sort_b.as<uint32_t>());
+    const uint32_t* perm = sort_indices(&stream, seed_less, U, sort_a.as<uint32_t>(), sort_b.as<uint32_t>(), sort_ra.as<SortRec>(), sort_rb.as<SortRec>());
     mark(10);
 
     // ---- host-ready arrays in seed order ----
@@ -2120,7 +2299,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     num_prefix.ensure((size_t)U * 8);
     ac_launch("number_key", &stream, NumberKeyBody{d_rec.as<UnitigRec>(), d_arena.as<char>(), num_prefix.as<uint64_t>()}, U);
     const NumberLess number_less{d_rec.as<UnitigRec>(), d_depth.as<uint32_t>(), d_arena.as<char>(), num_prefix.as<uint64_t>(), nullptr};
-    uint32_t* ord_in = sort_indices(&stream, number_less, U, sort_a.as<uint32_t>(), sort_b.as<uint32_t>());
+    uint32_t* ord_in = sort_indices(&stream, number_less, U, sort_a.as<uint32_t>(), sort_b.as<uint32_t>(), sort_ra.as<SortRec>(), sort_rb.as<SortRec>());
     // the work list of expand_repeats, in the numbering order just found
     d_fixed.ensure((size_t)U * 4); ac_memset(d_fixed.p, 0, (size_t)U * 4, &stream);
     uint8_t* seed_start = d_fixed.as<uint8_t>(); uint8_t* seed_end = seed_start + U; uint8_t* fix_start = seed_end + U; uint8_t* fix_end = fix_start + U;
@@ -2200,7 +2379,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
             ac_launch("inverse_perm", &stream, InversePermBody{ord_in, d_pos.as<uint32_t>()}, U);
             ac_launch("number_key", &stream, NumberKeyBody{d_rec.as<UnitigRec>(), R.arena_src->as<char>(), num_prefix.as<uint64_t>()}, U);
             const NumberLess final_less{d_rec.as<UnitigRec>(), d_depth.as<uint32_t>(), R.arena_src->as<char>(), num_prefix.as<uint64_t>(), d_pos.as<uint32_t>()};
-            R.final_order = sort_indices(&stream, final_less, U, sort_c.as<uint32_t>(), sort_d.as<uint32_t>());
+            R.final_order = sort_indices(&stream, final_less, U, sort_c.as<uint32_t>(), sort_d.as<uint32_t>(), sort_ra.as<SortRec>(), sort_rb.as<SortRec>());
         } else R.final_order = ord_in;     // nothing moved: the stable sort would change nothing
         if (device_gfa && U < 100000000u) {          // save_gfa (unitig_graph.rs:317-360): H, S, L and P lines rendered here
             uint32_t* fin = R.final_order;

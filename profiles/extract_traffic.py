@@ -1,6 +1,6 @@
 """Reads an `ncu --set full` report and records the DRAM traffic of the captured kernel in profiles/kernel_traffic.json
-(the `roofline.traffic` field of bench.py).  usage: python profiles/extract_traffic.py <report.ncu-rep> <key>
-where key is e.g. "InsertBody<2>:cfg2:k51"."""
+(the `roofline.traffic` field of bench.py).  usage: python profiles/extract_traffic.py <report.ncu-rep> <key> [kernel-name substring]
+where key is e.g. "InsertBody<2>:cfg2:k51"; with a substring the first launch whose name contains it is taken (reports with several kernels)."""
 import csv
 import io
 import json
@@ -11,8 +11,10 @@ import sys
 rep, key = sys.argv[1], sys.argv[2]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}
+want = sys.argv[3] if len(sys.argv) > 3 else ""
+vals = next(r for r in rows[2:] if want in r[col["Kernel Name"]])
 
 
 def to_bytes(name):
