@@ -53,6 +53,7 @@ struct ac_handle {
     LoadedInput loaded;                    // only when filled by ac_load_sequences (keeps the YAML details)
     std::unique_ptr<DevicePipeline> pipe;                   // the pipeline that finishes the graph (devices[0])
     std::vector<std::unique_ptr<DevicePipeline>> peers;     // ac_config.n_devices > 1: the pipelines of devices[1..]
+    const char* path_lines = nullptr; uint64_t path_lines_len = 0;     // ac_path_lines_render: this rank's P lines (pinned, owned by the pipeline)
     std::vector<int32_t> devices;
     PipelineResult res;
     HostGraph graph;
@@ -195,7 +196,7 @@ int ac_add_sequence(ac_handle* h, uint16_t seq_id, const uint8_t* fwd, uint64_t 
     AC_GUARD_END(h)
 }
 
-int ac_upload(ac_handle* h) {
+static int upload_block(ac_handle* h, uint32_t seq_lo, uint32_t seq_hi) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     AC_GUARD_BEGIN
     if (h->seqs.empty()) return set_error(h, AC_EINPUT, "no sequences found in input assemblies");
@@ -211,9 +212,20 @@ int ac_upload(ac_handle* h) {
         }
         h->pipe->set_path_line_texts(blob.data(), pre.data(), suf.data(), (uint32_t)h->seqs.size());
     }
-    h->pipe->upload(h->ascii.p, h->ascii.size, h->infos.data(), (uint32_t)h->infos.size(), h->cfg.k);
+    if (!h->peers.empty() && !(seq_lo == 0 && seq_hi >= h->infos.size())) return set_error(h, AC_EINVAL, "ac_upload_shard is for one device per process");
+    h->pipe->upload(h->ascii.p, h->ascii.size, h->infos.data(), (uint32_t)h->infos.size(), h->cfg.k, seq_lo, seq_hi);
     for (auto& peer : h->peers) peer->upload(h->ascii.p, h->ascii.size, h->infos.data(), (uint32_t)h->infos.size(), h->cfg.k);      // every device holds every sequence (end k-mers of foreign occurrences are read from them)
     h->uploaded = true; h->built = h->gfa_ready = h->fused = h->graph_ready = false;
+    return ok(h);
+    AC_GUARD_END(h)
+}
+int ac_upload(ac_handle* h) { return upload_block(h, 0, 0xFFFFFFFFu); }
+int ac_upload_shard(ac_handle* h, uint32_t seq_lo, uint32_t seq_hi) { return upload_block(h, seq_lo, seq_hi); }
+int ac_strand_block(ac_handle* h, uint32_t seq_lo, uint32_t seq_hi, void** dev_ptr, uint64_t* n_bytes) {
+    if (!h || !dev_ptr || !n_bytes) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    if (!h->uploaded) return set_error(h, AC_EINVAL, "ac_upload_shard must precede ac_strand_block");
+    *dev_ptr = h->pipe->strand_block(seq_lo, seq_hi, n_bytes);
     return ok(h);
     AC_GUARD_END(h)
 }
@@ -408,11 +420,11 @@ int ac_runs_import_padded(ac_handle* h, const void* src, uint64_t stride_records
     AC_GUARD_END(h)
 }
 // ac_compress on the rank that imported every rank's occurrences: simplify_structure and the GFA text on the device as well
-int ac_compress_finish(ac_handle* h) {
+static int compress_finish(ac_handle* h, bool split_paths) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");
     AC_GUARD_BEGIN
     static const bool host_tail = getenv("AC_HOST_SIMPLIFY") != nullptr;
-    if (host_tail) {
+    if (host_tail && !split_paths) {
         int rc = ac_build_finish(h); if (rc != AC_OK) return rc;
         if ((rc = ac_simplify(h)) != AC_OK) return rc;
         uint64_t n = 0; return ac_gfa_size(h, &n);
@@ -421,7 +433,7 @@ int ac_compress_finish(ac_handle* h) {
     if (h->built && h->graph_ready) flusher.start(h->res);
     {
         CallbackScope scope(h->pipe.get(), [&flusher] { flusher.join(); });
-        h->pipe->finish(h->res, h->cfg.keep_positions != 0, true);
+        h->pipe->finish(h->res, h->cfg.keep_positions != 0, true, split_paths);
     }
     h->pipe->complete(h->res);
     h->fused = true; h->graph_ready = false; h->built = true;
@@ -430,6 +442,28 @@ int ac_compress_finish(ac_handle* h) {
     h->t.host_graph = h->t.host_simplify = h->t.host_gfa = 0;
     return ok(h);
     AC_GUARD_END(h)
+}
+int ac_compress_finish(ac_handle* h) { return compress_finish(h, false); }
+int ac_compress_finish_split(ac_handle* h) { return compress_finish(h, true); }
+int ac_path_tokens_export(ac_handle* h, void* dst, uint64_t stride_tokens, const uint64_t* counts, uint32_t n_ranks) {
+    if (!h || !dst || !counts) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    h->pipe->export_path_tokens(dst, stride_tokens, counts, n_ranks);
+    return ok(h);
+    AC_GUARD_END(h)
+}
+int ac_path_lines_render(ac_handle* h, const void* tokens, uint64_t n_tokens) {
+    if (!h || (!tokens && n_tokens)) return set_error(h, AC_EINVAL, "null argument");
+    AC_GUARD_BEGIN
+    h->path_lines = nullptr; h->path_lines_len = 0;
+    h->pipe->render_path_lines(tokens, n_tokens, &h->path_lines, &h->path_lines_len);
+    return ok(h);
+    AC_GUARD_END(h)
+}
+int ac_path_lines_data(ac_handle* h, const char** data, uint64_t* n_bytes) {
+    if (!h || !data || !n_bytes) return set_error(h, AC_EINVAL, "null argument");
+    *data = h->path_lines; *n_bytes = h->path_lines_len;
+    return ok(h);
 }
 int ac_build_finish(ac_handle* h) {
     if (!h) return set_error(nullptr, AC_EINVAL, "null handle");

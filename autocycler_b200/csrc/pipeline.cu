@@ -235,14 +235,15 @@ template <int W> struct InsertBody {
         const uint32_t empty_hi = 0xFFFFFFFFu << (32u - t.gb);
         uint64_t slot = table_home(t, h);
         bool done = !valid, failed = false;
+        bool fetched = home_group != nullptr;      // the home group is in registers already: good for the first look at it only
         uint32_t fresh = 0;                 // lanes of this warp whose window claimed a slot
         for (uint32_t probes = 0;;) {
             bool claimed = false; Slot q = 0;
             if (!done) {
-                for (bool fetched = home_group != nullptr;; fetched = false) {
+                for (;; fetched = false) {
                     Slot grp[4];
                     const uint64_t base = slot & ~3ull;
-                    if (fetched) { grp[0] = home_group[0]; grp[1] = home_group[1]; grp[2] = home_group[2]; grp[3] = home_group[3]; }      // loaded while the previous unit was probed; may lag the table, as any load may (see slot_add_occurrence)
+                    if (fetched) { fetched = false; grp[0] = home_group[0]; grp[1] = home_group[1]; grp[2] = home_group[2]; grp[3] = home_group[3]; }      // loaded while the previous unit was probed; may lag the table, as any load may (see slot_add_occurrence)
                     else ac_ld_group(t.slots + base, grp);
                     // the first slot of the group, from `slot` on, that is empty or carries the tag
                     uint32_t cand = 0;
@@ -313,6 +314,10 @@ template <int W> struct InsertBody {
     }
     AC_D void operator()(uint64_t i) const {
         Unit u; prepare(i, u);
+#ifdef AC_EMULATE
+        Slot grp[4] = {0, 0, 0, 0};          // the CPU suite takes the route of the pipelined kernel: the home group handed in
+        if (u.valid && !sizing) { ac_ld_group(t.slots + table_home(t, u.h), grp); upsert(u.valid, u.fwd, u.rc, u.h, u.flags, u.g, grp); return; }
+#endif
         upsert(u.valid, u.fwd, u.rc, u.h, u.flags, u.g);
     }
 };
@@ -852,7 +857,7 @@ template <class Less> struct MergeWaysBody {
 #define AC_SORT_TILE 16          // small tiles: the CPU suite's graphs then go through several merge passes
 #endif
 #ifndef AC_EMULATE
-template <class Less> __global__ void __launch_bounds__(512) ac_tile_sort_kernel(const Less less, uint32_t n, uint32_t* __restrict__ idx, SortRec* __restrict__ recs) {
+template <class Less> __global__ void __launch_bounds__(1024) ac_tile_sort_kernel(const Less less, uint32_t n, uint32_t* __restrict__ idx, SortRec* __restrict__ recs) {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     SortRec* keys = reinterpret_cast<SortRec*>(tile_smem);                                           // [AC_SORT_TILE] the records, staged once
     uint16_t* buf0 = reinterpret_cast<uint16_t*>(tile_smem + AC_SORT_TILE * sizeof(SortRec));         // local ids, ping
@@ -911,7 +916,7 @@ template <class Less> static uint32_t* sort_indices(AcStream* stream, const Less
 #ifndef AC_EMULATE
     const size_t smem = AC_SORT_TILE * (sizeof(SortRec) + 2 * sizeof(uint16_t));
     AC_CUDA_CHECK(cudaFuncSetAttribute(ac_tile_sort_kernel<Less>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      // per device: cheap enough to repeat
-    ac_tile_sort_kernel<Less><<<(unsigned)tiles, 512, smem, stream->s>>>(less, n, a, ra); ++g_ac_kernel_launches;
+    ac_tile_sort_kernel<Less><<<(unsigned)tiles, 1024, smem, stream->s>>>(less, n, a, ra); ++g_ac_kernel_launches;      // 32 warps on the SM: the searches are chains of dependent shared-memory loads
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("launch tile sort: ") + cudaGetErrorString(e));
 #else
@@ -1507,28 +1512,39 @@ struct GfaLinkBody {          // get_links_for_gfa (:333-350): forward_next then
     }
 };
 struct PathLastBody { const uint64_t* path_off; uint8_t* last; AC_D void operator()(uint64_t i) const { if (path_off[i + 1] > path_off[i]) last[path_off[i + 1] - 1] = 1; } };
+// `path` holds seed-order unitig strands and number_of maps them to final numbers; with number_of == nullptr the entries are tokens
+// already: (final number - 1) << 1 | strand (what a rank that owns the sequences, but not the graph, is sent: PathTokenBody).
+AC_D uint32_t path_number(const UStrand* path, const uint32_t* number_of, uint64_t x) { return (number_of ? number_of[path[x] >> 1] : path[x] >> 1) + 1; }
 struct PathSizeBody {
     const UStrand* path; const uint32_t* number_of; const uint8_t* last; uint64_t steps; uint32_t* p_size;
-    AC_D void operator()(uint64_t x) const { p_size[x] = x == steps ? 0u : ac_dec_len(number_of[path[x] >> 1] + 1) + 1 + (last[x] ? 0u : 1u); }   // num sign [,]
+    AC_D void operator()(uint64_t x) const { p_size[x] = x == steps ? 0u : ac_dec_len(path_number(path, number_of, x)) + 1 + (last[x] ? 0u : 1u); }   // num sign [,]
+};
+struct PathTokenBody {      // every occurrence's token, laid out per owning rank: rank q's occurrences [first[q], first[q+1]) go to dst + q * stride
+    const UStrand* path; const uint32_t* number_of; uint32_t* dst; uint64_t stride; uint32_t n_ranks; uint64_t first[AC_MAX_RANKS + 1];
+    AC_D void operator()(uint64_t x) const {
+        uint32_t q = 0; while (q + 1 < n_ranks && first[q + 1] <= x) ++q;
+        dst[(uint64_t)q * stride + (x - first[q])] = (number_of[path[x] >> 1] << 1) | (path[x] & 1u);
+    }
 };
 struct PathTextBody {
     const UStrand* path; const uint32_t* number_of; const uint8_t* last; const uint32_t* p_off; char* text;
     AC_D void operator()(uint64_t x) const {
         char* p = text + p_off[x];
-        p += ac_put_dec(p, number_of[path[x] >> 1] + 1); *p++ = (path[x] & 1u) ? '-' : '+';
+        p += ac_put_dec(p, path_number(path, number_of, x)); *p++ = (path[x] & 1u) ? '-' : '+';
         if (!last[x]) *p++ = ',';
     }
 };
 // The P line of sequence i starts at wrap_off[i] + p_off[path_off[i]] of the P section: what the earlier sequences print around their
 // lists, plus all earlier list text; its list follows the prefix, its suffix follows the list (get_gfa_path_line, unitig_graph.rs:352-360).
-struct PathLineView { const uint64_t* path_off; uint32_t n_seqs; const uint32_t* p_off; const uint64_t* wrap_off; const uint32_t* pre_len; const uint32_t* suf_len; const char* blob; const uint64_t* blob_off; };
+struct PathLineView { const uint64_t* path_off; uint32_t n_seqs; const uint32_t* p_off; const uint64_t* wrap_off; const uint32_t* pre_len; const uint32_t* suf_len; const char* blob; const uint64_t* blob_off;
+                      uint64_t wrap_base; };      // wrap_off counts from the first sequence of the input; a rank that prints its own sequences only starts at wrap_base
 struct PathTextFullBody {
     const UStrand* path; const uint32_t* number_of; const uint8_t* last; PathLineView v; char* text;
     AC_D void operator()(uint64_t x) const {
         uint32_t lo = 0, hi = v.n_seqs;                    // the sequence whose path holds step x
         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (v.path_off[mid] <= x) lo = mid; else hi = mid; }
-        char* p = text + v.wrap_off[lo] + v.pre_len[lo] + v.p_off[x];
-        p += ac_put_dec(p, number_of[path[x] >> 1] + 1); *p++ = (path[x] & 1u) ? '-' : '+';
+        char* p = text + (v.wrap_off[lo] - v.wrap_base) + v.pre_len[lo] + v.p_off[x];
+        p += ac_put_dec(p, path_number(path, number_of, x)); *p++ = (path[x] & 1u) ? '-' : '+';
         if (!last[x]) *p++ = ',';
     }
 };
@@ -1537,7 +1553,7 @@ struct PathWrapBody {       // one thread per (sequence, prefix or suffix)
     AC_D void operator()(uint64_t t) const {
         const uint32_t i = (uint32_t)(t >> 1); const bool suffix = t & 1;
         const char* src = v.blob + v.blob_off[i] + (suffix ? v.pre_len[i] : 0u);
-        char* dst = text + v.wrap_off[i] + (suffix ? v.pre_len[i] + v.p_off[v.path_off[i + 1]] : v.p_off[v.path_off[i]]);
+        char* dst = text + (v.wrap_off[i] - v.wrap_base) + (suffix ? v.pre_len[i] + v.p_off[v.path_off[i + 1]] : v.p_off[v.path_off[i]]);
         const uint32_t n = suffix ? v.suf_len[i] : v.pre_len[i];
         for (uint32_t b = 0; b < n; ++b) dst[b] = src[b];
     }
@@ -1779,7 +1795,7 @@ struct DevicePipeline::Impl {
     PinBuf h_dirty, h_exhausted, h_order2, h_text, h_ptext, h_pbound;
     PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
-    cudaEvent_t ev[20];
+    cudaEvent_t ev[24];
 #endif
 
     void mark(int i) {
@@ -1867,13 +1883,13 @@ struct DevicePipeline::Impl {
     template <int W> void local_w(uint32_t seq_lo, uint32_t seq_hi, bool multi);
     template <int W> void merge_w(const void* dev_ptr, uint64_t n);
     template <int W> void runs_local_w();
-    template <int W> void finish_w(PipelineResult& out, bool keep_positions, bool fused);
+    template <int W> void finish_w(PipelineResult& out, bool keep_positions, bool fused, bool split_paths);
     // what a finished build leaves in HBM for pull_graph() (at once in a plain build, on request after a fused one)
     struct Pending {
         uint32_t U = 0, n_strands = 0; uint64_t n_links = 0, n_cands = 0;
         uint32_t* order_built = nullptr; uint32_t* final_order = nullptr; uint8_t* fix_start = nullptr;
         DevBuf* arena_src = nullptr; uint64_t arena_final = 0;
-        bool first_pass_done = false, any_moved = false, gfa_on_device = false, hairpins_ready = false;
+        bool first_pass_done = false, any_moved = false, gfa_on_device = false, hairpins_ready = false, paths_split = false;
         uint64_t first_pass_total = 0, bases_removed = 0, gfa_bytes = 0;
     } R;
     bool pending_keep_positions = false;
@@ -1884,7 +1900,11 @@ struct DevicePipeline::Impl {
         exclusive_scan(x, x, n, 0, false);
         ac_copy_dd(total_dst, x + (n - 1), 4, &stream);
     }
-    uint64_t exp_n = 0;
+    uint64_t uploaded_bytes = 0;
+    uint64_t exp_n = 0, n_own_runs = 0; uint32_t own_seq_lo = 0, own_seq_hi = 0;
+    void do_export_path_tokens(void* dst, uint64_t stride, const uint64_t* counts, uint32_t n_ranks);
+    void do_render_path_lines(const void* tokens, uint64_t n_tokens, const char** text, uint64_t* bytes);
+    DevBuf d_own_off, d_own_last, d_own_size; uint64_t path_lines_d2h = 0;
     uint64_t list_claimed();
     uint64_t do_count_entries();
     void do_export_entries(void* dst, uint64_t cap_records);
@@ -1928,7 +1948,7 @@ DevicePipeline::~DevicePipeline() {
 
 unsigned long long DevicePipeline::kernel_launches() const { return g_ac_kernel_launches; }
 
-void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t k) {
+void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t k, uint32_t seq_lo, uint32_t seq_hi) {
     Impl& m = *impl;
 #ifndef AC_EMULATE
     AC_CUDA_CHECK(cudaSetDevice(m.device));
@@ -1942,7 +1962,13 @@ void DevicePipeline::upload(const uint8_t* ascii, uint64_t total, const SeqInfo*
     m.host_seqs.assign(seqs, seqs + n_seqs);
     m.mark(0);
     m.ascii.ensure(total);
-    ac_h2d(m.ascii.p, ascii, total, &m.stream);
+    if (seq_lo == 0 && seq_hi >= n_seqs) { ac_h2d(m.ascii.p, ascii, total, &m.stream); m.uploaded_bytes = total; }
+    else {              // a shard: only the strands of sequences [seq_lo, seq_hi); the caller's collective brings the other ranks' blocks (strand_block)
+        if (seq_lo > seq_hi || seq_hi > n_seqs) throw std::runtime_error("bad sequence shard");
+        const uint64_t b0 = seq_lo < n_seqs ? seqs[seq_lo].start : total, b1 = seq_hi < n_seqs ? seqs[seq_hi].start : total;
+        if (b1 > b0) ac_h2d(m.ascii.as<uint8_t>() + b0, ascii + b0, b1 - b0, &m.stream);
+        m.uploaded_bytes = b1 - b0;
+    }
     m.seqs.ensure(n_seqs * sizeof(SeqInfo));
     ac_h2d(m.seqs.p, seqs, n_seqs * sizeof(SeqInfo), &m.stream);
     if (m.path_pre.size() == n_seqs) {       // the P-line texts (set_path_line_texts): prefix and suffix of every sequence, and where each line's share starts
@@ -2049,7 +2075,7 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
     const SeqInfo* hs = host_seqs.data();
     if (seq_lo == seq_hi) { g_begin = g_end = 0; }       // a rank without sequences still merges, and computes the replicated stages
     else { g_begin = hs[seq_lo].start; g_end = hs[seq_hi - 1].start + hs[seq_hi - 1].len; }
-    is_multi = multi;
+    is_multi = multi; own_seq_lo = seq_lo; own_seq_hi = seq_hi;
     // windows = total - n_seqs*(k-1); a canonical table can hold at most that many entries (all ranks' windows: after
     // the exchange every rank's table holds the k-mers of every sequence)
     n_windows = total - (uint64_t)n_seqs * (k - 1);
@@ -2179,6 +2205,7 @@ template <int W> void DevicePipeline::Impl::runs_local_w() {
     ac_launch("run_scatter", &stream, RunScatterBody{bmask.as<uint32_t>(), boff.as<uint32_t>(), run_start.as<uint64_t>()}, n_bwords);
     ac_launch("run_ends", &stream, RunEndsLocalBody{seqs.as<SeqInfo>(), n_seqs, run_start.as<uint64_t>(), n_runs, pos_slot.as<uint32_t>(),
                                                     run_len.as<uint32_t>(), run_hs.as<uint32_t>(), run_ts.as<uint32_t>()}, n_runs);
+    n_own_runs = n_runs;
     stage = 2;
 }
 
@@ -2210,7 +2237,7 @@ void DevicePipeline::Impl::do_import_runs_from(const void* const* ptrs, const ui
 }
 
 // ---- stage 3: unitigs, seeds, links, seed order and the host-ready arrays (over every occurrence handed to it) ----
-template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool keep_positions, bool fused) {
+template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool keep_positions, bool fused, bool split_paths) {
     if (stage < 2) throw std::runtime_error("runs_local must precede finish");
     const KParams p = make_kparams(k, W);
     const TableView tv = table_view();
@@ -2387,25 +2414,27 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
             ac_launch("inverse_perm", &stream, InversePermBody{fin, d_pos2.as<uint32_t>()}, U);
             const GfaView gv{fin, d_pos2.as<uint32_t>(), d_rec.as<UnitigRec>(), R.arena_src->as<char>(), d_depth.as<uint32_t>(), d_next_off.as<uint32_t>(), d_next.as<UStrand>()};
             gfa_s_size.ensure(((size_t)U + 1) * 4); gfa_l_size.ensure(((size_t)U + 1) * 4); gfa_pieces.ensure(((size_t)U + 1) * 4);
-            const uint64_t steps = n_runs;
+            const uint64_t steps = split_paths ? 0 : n_runs;     // split_paths: the P lines are printed by the ranks that own the sequences (render_path_lines)
             d_last.ensure(steps + 8); gfa_p_size.ensure((steps + 1) * 4);
             ac_launch("gfa_size", &stream, GfaSizeBody{gv, U, gfa_s_size.as<uint32_t>(), gfa_l_size.as<uint32_t>()}, (uint64_t)U + 1);
             ac_launch("gfa_chunk_count", &stream, GfaChunkCountBody{gv, U, gfa_pieces.as<uint32_t>()}, (uint64_t)U + 1);
-            ac_memset(d_last.p, 0, steps + 8, &stream);
-            ac_launch("path_last", &stream, PathLastBody{d_path_off.as<uint64_t>(), d_last.as<uint8_t>()}, n_seqs);
-            ac_launch("path_size", &stream, PathSizeBody{d_path.as<UStrand>(), d_pos2.as<uint32_t>(), d_last.as<uint8_t>(), steps, gfa_p_size.as<uint32_t>()}, steps + 1);
-            // four scans, their totals read back together (one round trip instead of four)
-            d_totals.ensure(64);
+            // the scans, their totals read back together (one round trip)
+            d_totals.ensure(64); ac_memset(d_totals.p, 0, 64, &stream);
+            if (!split_paths) {
+                ac_memset(d_last.p, 0, steps + 8, &stream);
+                ac_launch("path_last", &stream, PathLastBody{d_path_off.as<uint64_t>(), d_last.as<uint8_t>()}, n_seqs);
+                ac_launch("path_size", &stream, PathSizeBody{d_path.as<UStrand>(), d_pos2.as<uint32_t>(), d_last.as<uint8_t>(), steps, gfa_p_size.as<uint32_t>()}, steps + 1);
+                scan_keep_total(gfa_p_size.as<uint32_t>(), steps + 1, d_totals.as<uint32_t>() + 3);
+            }
             scan_keep_total(gfa_s_size.as<uint32_t>(), (uint64_t)U + 1, d_totals.as<uint32_t>() + 0);
             scan_keep_total(gfa_l_size.as<uint32_t>(), (uint64_t)U + 1, d_totals.as<uint32_t>() + 1);
             scan_keep_total(gfa_pieces.as<uint32_t>(), (uint64_t)U + 1, d_totals.as<uint32_t>() + 2);
-            scan_keep_total(gfa_p_size.as<uint32_t>(), steps + 1, d_totals.as<uint32_t>() + 3);
             uint32_t tot[4];
             ac_d2h(tot, d_totals.p, 16, &stream); ac_sync(&stream);
             const uint64_t s_bytes = tot[0], l_bytes = tot[1], n_pieces = tot[2], p_list_bytes = tot[3];
             char head[64]; const uint64_t head_bytes = (uint64_t)snprintf(head, sizeof head, "H\tVN:Z:1.0\tKM:i:%u\n", k);
             if (path_wrap_total == 0 && n_seqs) throw std::runtime_error("set_path_line_texts() must precede a build that renders the GFA");
-            const uint64_t p_bytes = p_list_bytes + path_wrap_total;
+            const uint64_t p_bytes = split_paths ? 0 : p_list_bytes + path_wrap_total;
             R.gfa_bytes = head_bytes + s_bytes + l_bytes + p_bytes;
             d_text.ensure(R.gfa_bytes + 64);
             char* text = d_text.as<char>();
@@ -2414,10 +2443,13 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
             ac_launch("gfa_sequence", &stream, GfaSequenceBody{gv, U, gfa_pieces.as<uint32_t>(), gfa_s_size.as<uint32_t>(), text + head_bytes}, n_pieces);
             ac_launch("gfa_link", &stream, GfaLinkBody{gv, gfa_l_size.as<uint32_t>(), text + head_bytes + s_bytes}, U);
             const PathLineView pv{d_path_off.as<uint64_t>(), n_seqs, gfa_p_size.as<uint32_t>(), d_wrap_off.as<uint64_t>(), d_pre_len.as<uint32_t>(), d_suf_len.as<uint32_t>(),
-                                  d_blob.as<char>(), d_blob_off.as<uint64_t>()};
+                                  d_blob.as<char>(), d_blob_off.as<uint64_t>(), 0};
             char* p_text = text + head_bytes + s_bytes + l_bytes;
-            ac_launch("path_text", &stream, PathTextFullBody{d_path.as<UStrand>(), d_pos2.as<uint32_t>(), d_last.as<uint8_t>(), pv, p_text}, steps);
-            ac_launch("path_wrap", &stream, PathWrapBody{pv, p_text}, 2ull * n_seqs);
+            if (!split_paths) {
+                ac_launch("path_text", &stream, PathTextFullBody{d_path.as<UStrand>(), d_pos2.as<uint32_t>(), d_last.as<uint8_t>(), pv, p_text}, steps);
+                ac_launch("path_wrap", &stream, PathWrapBody{pv, p_text}, 2ull * n_seqs);
+            }
+            R.paths_split = split_paths;
             R.gfa_on_device = true;
         }
     }
@@ -2440,7 +2472,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     out.length_after = n_slots_used - R.bases_removed;
     out.gfa_text = R.gfa_on_device ? h_text.as<char>() : nullptr; out.gfa_bytes = R.gfa_on_device ? R.gfa_bytes : 0;
     out.n_unitigs = U; out.n_runs = n_runs; out.n_seqs = n_seqs; out.n_links = n_links;
-    out.h2d_bytes = total + (uint64_t)n_seqs * sizeof(SeqInfo);
+    out.h2d_bytes = uploaded_bytes + (uint64_t)n_seqs * sizeof(SeqInfo);
     out.d2h_bytes = d2h;
     pending_keep_positions = keep_positions;
     if (!fused) pull_graph(out, keep_positions);
@@ -2502,6 +2534,49 @@ void DevicePipeline::Impl::do_complete(PipelineResult& out) {
     out.t.boundaries = between(5, 6); out.t.runs = between(14, 7); out.t.unitigs = between(7, 8); out.t.links = between(8, 9);
     out.t.seed_sort = between(9, 10); out.t.emit = between(10, 11); out.t.simplify = between(11, 17); out.t.gfa = between(17, 18);
     out.t.d2h = between(18, 12); out.t.total = between(2, 4) + between(13, 6) + between(14, 12);
+}
+
+// ---- multi-GPU, path lines by owner: the rank that finished the graph hands every occurrence's final "<number><sign>" to
+// the rank that owns the sequence; every rank prints the P lines of its own sequences and copies them out through its own PCIe link ----
+void DevicePipeline::Impl::do_export_path_tokens(void* dst, uint64_t stride, const uint64_t* counts, uint32_t n_ranks) {
+    if (stage < 2 || !R.gfa_on_device || !R.paths_split) throw std::runtime_error("export_path_tokens follows a finish with split path lines");
+    if (n_ranks == 0 || n_ranks > AC_MAX_RANKS) throw std::runtime_error("export_path_tokens: bad rank count");
+    PathTokenBody body{d_path.as<UStrand>(), d_pos2.as<uint32_t>(), (uint32_t*)dst, stride, n_ranks, {0}};
+    for (uint32_t q = 0; q < n_ranks; ++q) { if (counts[q] > stride) throw std::runtime_error("export_path_tokens: a rank holds more occurrences than the stride"); body.first[q + 1] = body.first[q] + counts[q]; }
+    if (body.first[n_ranks] != n_runs) throw std::runtime_error("export_path_tokens: the counts do not add up to the occurrences imported");
+    ac_launch("path_tokens", &stream, body, n_runs);
+}
+void DevicePipeline::Impl::do_render_path_lines(const void* tokens, uint64_t n_tokens, const char** text, uint64_t* bytes) {
+    if (stage < 2) throw std::runtime_error("runs_local must precede render_path_lines");
+    if (n_tokens != n_own_runs) throw std::runtime_error("render_path_lines: one token per occurrence of this rank's sequences is expected");
+    if (path_pre.size() != n_seqs) throw std::runtime_error("set_path_line_texts() must precede render_path_lines");
+    const uint32_t n_own = own_seq_hi - own_seq_lo;
+    uint64_t wrap_lo = 0, wrap_hi = 0;
+    for (uint32_t i = 0; i < own_seq_hi; ++i) { if (i == own_seq_lo) wrap_lo = wrap_hi; wrap_hi += (uint64_t)path_pre[i] + path_suf[i]; }
+    if (own_seq_lo == own_seq_hi) wrap_lo = wrap_hi;
+    mark(19);
+    uint64_t total_bytes = 0;
+    if (n_own) {
+        const uint64_t steps = n_tokens;
+        d_own_off.ensure(((size_t)n_own + 1) * 8); d_own_last.ensure(steps + 8); d_own_size.ensure((steps + 1) * 4);
+        // this rank's occurrences are the first n_own_runs entries of run_start (the finishing rank imported its own block first)
+        ac_launch("path_off", &stream, PathOffBody{seqs.as<SeqInfo>() + own_seq_lo, n_own, run_start.as<uint64_t>(), steps, d_own_off.as<uint64_t>()}, (uint64_t)n_own + 1);
+        ac_memset(d_own_last.p, 0, steps + 8, &stream);
+        ac_launch("path_last", &stream, PathLastBody{d_own_off.as<uint64_t>(), d_own_last.as<uint8_t>()}, n_own);
+        ac_launch("path_size", &stream, PathSizeBody{(const UStrand*)tokens, nullptr, d_own_last.as<uint8_t>(), steps, d_own_size.as<uint32_t>()}, steps + 1);
+        const uint64_t list_bytes = exclusive_scan(d_own_size.as<uint32_t>(), d_own_size.as<uint32_t>(), steps + 1);
+        total_bytes = list_bytes + (wrap_hi - wrap_lo);
+        d_ptext.ensure(total_bytes + 64);
+        const PathLineView pv{d_own_off.as<uint64_t>(), n_own, d_own_size.as<uint32_t>(), d_wrap_off.as<uint64_t>() + own_seq_lo, d_pre_len.as<uint32_t>() + own_seq_lo,
+                              d_suf_len.as<uint32_t>() + own_seq_lo, d_blob.as<char>(), d_blob_off.as<uint64_t>() + own_seq_lo, wrap_lo};
+        ac_launch("path_text", &stream, PathTextFullBody{(const UStrand*)tokens, nullptr, d_own_last.as<uint8_t>(), pv, d_ptext.as<char>()}, steps);
+        ac_launch("path_wrap", &stream, PathWrapBody{pv, d_ptext.as<char>()}, 2ull * n_own);
+        h_ptext.ensure(total_bytes + 64);
+        ac_d2h(h_ptext.p, d_ptext.p, total_bytes, &stream);
+    }
+    ac_sync(&stream);
+    path_lines_d2h = total_bytes;
+    *text = total_bytes ? h_ptext.as<char>() : nullptr; *bytes = total_bytes;
 }
 
 // One instantiation of every k-mer kernel per key width: W = ceil(2k / 64) words, k up to 511.
@@ -2567,10 +2642,21 @@ void DevicePipeline::enable_peer_access(const int* devices, int n) {
     (void)devices; (void)n;
 #endif
 }
-void DevicePipeline::finish(PipelineResult& out, bool keep_positions, bool fused) {
+void DevicePipeline::finish(PipelineResult& out, bool keep_positions, bool fused, bool split_paths) {
     Impl& m = *impl; m.set_device(); const int W = m.W;
-    AC_DISPATCH_W(m.finish_w, out, keep_positions, fused)
+    if (split_paths && !fused) throw std::runtime_error("split path lines need the fused finish");
+    AC_DISPATCH_W(m.finish_w, out, keep_positions, fused, split_paths)
 }
+void* DevicePipeline::strand_block(uint32_t seq_lo, uint32_t seq_hi, uint64_t* n_bytes) {
+    Impl& m = *impl;
+    if (seq_lo > seq_hi || seq_hi > m.n_seqs || m.total == 0) throw std::runtime_error("strand_block: bad range, or nothing uploaded");
+    const SeqInfo* q = m.host_seqs.data();
+    const uint64_t b0 = seq_lo < m.n_seqs ? q[seq_lo].start : m.total, b1 = seq_hi < m.n_seqs ? q[seq_hi].start : m.total;
+    *n_bytes = b1 - b0;
+    return m.ascii.as<uint8_t>() + b0;
+}
+void DevicePipeline::export_path_tokens(void* dst, uint64_t stride, const uint64_t* counts, uint32_t n_ranks) { impl->set_device(); impl->do_export_path_tokens(dst, stride, counts, n_ranks); }
+void DevicePipeline::render_path_lines(const void* tokens, uint64_t n_tokens, const char** text, uint64_t* bytes) { impl->set_device(); impl->do_render_path_lines(tokens, n_tokens, text, bytes); }
 void DevicePipeline::fetch_graph(PipelineResult& out, bool keep_positions) {
     Impl& m = *impl; m.set_device();
     if (m.stage < 2 || !out.fused) throw std::runtime_error("fetch_graph follows a fused build");

@@ -105,7 +105,10 @@ public:
     DevicePipeline(int device, void* stream);
     ~DevicePipeline();
     // ascii: all padded, end-repaired forward strands concatenated (bytes in "ACGT."); seqs: their layout.
-    void upload(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t k);
+    // seq_lo / seq_hi: copy only the strands of that block of sequences to the device (multi-GPU: every rank uploads its own block and a
+    // collective over strand_block() ranges brings the others' over NVLink instead of over every rank's PCIe link).
+    void upload(const uint8_t* ascii, uint64_t total, const SeqInfo* seqs, uint32_t n_seqs, uint32_t k, uint32_t seq_lo = 0, uint32_t seq_hi = 0xFFFFFFFFu);
+    void* strand_block(uint32_t seq_lo, uint32_t seq_hi, uint64_t* n_bytes);   // device address and size of the strands of sequences [seq_lo, seq_hi) (contiguous)
     // What save_gfa prints around the unitig list of every path (unitig_graph.rs:352-360): "P\t<id>\t" before and
     // "\t*\tLN:i:..\tFN:Z:..\tHD:Z:..\n" behind it, concatenated per sequence (prefix then suffix), with their lengths.  Call before upload().
     void set_path_line_texts(const char* blob, const uint32_t* prefix_len, const uint32_t* suffix_len, uint32_t n_seqs);
@@ -136,7 +139,13 @@ public:
     const void* export_entries_own(uint64_t* n);                        // compacted 16-byte entry records of the local table; valid until the next build
     const void* export_runs_own(uint64_t* n);                           // this rank's 16-byte occurrence records
     void import_runs_from(const void* const* ptrs, const uint64_t* counts, uint32_t n_ranks);   // rank q's records at ptrs[q] (peer memory)
-    void finish(PipelineResult& out, bool keep_positions, bool fused = false);   // unitigs, seeds, links, seed order, host-ready arrays
+    // unitigs, seeds, links, seed order, host-ready arrays.  split_paths (fused only): the text ends after the L lines; the P lines are
+    // printed by the ranks that own the sequences — export_path_tokens() here lays out every occurrence's "(final number - 1) << 1 | strand"
+    // for its owner (rank q's tokens at dst + q * stride, counts[q] of them: the occurrence counts the import was given), and every rank
+    // turns the tokens of its own occurrences into the P lines of its own sequences (pinned host text) with render_path_lines().
+    void finish(PipelineResult& out, bool keep_positions, bool fused = false, bool split_paths = false);
+    void export_path_tokens(void* dst, uint64_t stride, const uint64_t* counts, uint32_t n_ranks);
+    void render_path_lines(const void* tokens_dev, uint64_t n_tokens, const char** text, uint64_t* bytes);
     // needles: n_needles keys of h bases each (2 words per key, kmer_key.h layout for k = h), pairwise distinct.
     // renumber_unitigs for a graph the host has edited: sorts n keys by (length descending, first 8 bases ascending, index
     // ascending) and writes the sorted indices; the host settles the rare ties beyond the prefix.  `keys` may be any host memory.

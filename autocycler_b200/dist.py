@@ -80,6 +80,7 @@ def _exchange(kmer_graph, seq_lo, seq_hi, device, group, stats):
     dist.gather(rsend, list(rrecv.view(world, -1).unbind(0)) if rank == 0 else None, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     settle()
     t5 = clock()
+    kmer_graph._run_counts = rsizes
     if stats is not None:
         stats.update(entries_sent=n.value, entries_received=sum(sizes) - n.value, exchange_bytes_sent=n.value * ENTRY_BYTES,
                      exchange_bytes_received=(sum(sizes) - n.value) * ENTRY_BYTES, runs_total=sum(rsizes), runs_gathered_bytes=sum(rsizes) * RUN_BYTES)
@@ -101,6 +102,10 @@ def finish_stats(stats):
         names = ["local_table", "exchange", "merge", "adjacency_runs", "gather_runs"]
         for i, name in enumerate(names):
             stats[name + "_ms"] = ev[i].elapsed_time(ev[i + 1])
+    ev2 = stats.pop("_events2", None)
+    if ev2 and all(e is not None for e in ev2):
+        stats["finish_and_tokens_ms"] = ev2[0].elapsed_time(ev2[1])     # rank 0: the union graph, H/S/L text, token scatter; other ranks: waiting for it
+        stats["path_lines_ms"] = ev2[1].elapsed_time(ev2[2])
     return stats
 
 
@@ -112,6 +117,107 @@ def from_kmer_graph_distributed(kmer_graph, seq_lo, seq_hi, device, group=None, 
     h = kmer_graph._h
     h.check(h.lib.ac_build_finish(h.ptr))
     return UnitigGraph(kmer_graph)
+
+
+TOKEN_BYTES = 4
+
+
+class _DeviceBytes:
+    """A range of the library's device memory as something torch.as_tensor() wraps without a copy."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def upload_sharded(kmer_graph, bounds, device, group=None):
+    """kmer_graph.upload() for the N-rank build: every rank copies only its own block of strands over its PCIe link (bounds[r] .. bounds[r+1]
+    are rank r's sequences) and one broadcast per block brings the others' over NVLink into place.  -> bytes this rank uploaded."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    h = kmer_graph._h
+    lib = h.lib
+    h.check(lib.ac_upload_shard(h.ptr, bounds[rank], bounds[rank + 1]))
+    on_cuda = torch.device(device).type == "cuda"
+    if on_cuda and h.stream != torch.cuda.current_stream(device).cuda_stream:
+        torch.cuda.synchronize(device)
+    work, mine = [], 0
+    for r in range(world):
+        ptr, n = C.c_void_p(), C.c_uint64()
+        h.check(lib.ac_strand_block(h.ptr, bounds[r], bounds[r + 1], C.byref(ptr), C.byref(n)))
+        if r == rank:
+            mine = n.value
+        if n.value == 0:
+            continue
+        if on_cuda:
+            block = torch.as_tensor(_DeviceBytes(ptr.value, n.value), device=device)
+        else:
+            block = torch.frombuffer((C.c_uint8 * n.value).from_address(ptr.value), dtype=torch.uint8)
+        work.append(dist.broadcast(block, src=dist.get_global_rank(group, r) if group is not None else r, group=group, async_op=True))
+    for w in work:
+        w.wait()
+    if on_cuda and h.stream != torch.cuda.current_stream(device).cuda_stream:
+        torch.cuda.synchronize(device)
+    return mine
+
+
+class PathLines:
+    """The P lines of this rank's sequences (compress_distributed(..., split_paths=True)): a view of the library's pinned buffer."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def view(self):
+        n = C.c_uint64(); ptr = C.c_void_p()
+        self._h.check(self._h.lib.ac_path_lines_data(self._h.ptr, C.byref(ptr), C.byref(n)))
+        return memoryview((C.c_char * n.value).from_address(ptr.value)) if n.value else memoryview(b"")
+
+
+def compress_distributed_split(kmer_graph, seq_lo, seq_hi, device, group=None, stats=None):
+    """UnitigGraph.compress over the ranks with the P lines printed where the sequences live: rank 0 finishes the graph and prints H, S and
+    L lines, hands every occurrence's final "<number><sign>" to the rank that owns the sequence (one scatter, 4 bytes per occurrence), and
+    every rank prints the P lines of its own sequences and copies them out over its own PCIe link.
+    -> (graph on rank 0 / None elsewhere, PathLines); input_assemblies.gfa = rank 0's gfa_view() + every rank's lines in rank order."""
+    import torch
+    import torch.distributed as dist
+    from .api import UnitigGraph
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    on_cuda = torch.device(device).type == "cuda"
+    is_root = _exchange(kmer_graph, seq_lo, seq_hi, device, group, stats)
+    h = kmer_graph._h
+    lib = h.lib
+    rsizes = kmer_graph._run_counts
+    max_r = max(1, max(rsizes))
+    e0 = torch.cuda.Event(enable_timing=True) if (stats is not None and on_cuda) else None
+    if e0 is not None:
+        e0.record()
+    graph = None
+    chunk = torch.empty(max_r, dtype=torch.int32, device=device)
+    if is_root:
+        h.check(lib.ac_compress_finish_split(h.ptr))
+        graph = UnitigGraph(kmer_graph)
+        tokens = torch.empty(world * max_r, dtype=torch.int32, device=device)
+        counts = (C.c_uint64 * world)(*rsizes)
+        h.check(lib.ac_path_tokens_export(h.ptr, tokens.data_ptr(), max_r, counts, world))
+        if on_cuda and kmer_graph._h.stream != torch.cuda.current_stream(device).cuda_stream:
+            torch.cuda.synchronize(device)
+        dist.scatter(chunk, list(tokens.view(world, max_r).unbind(0)), src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    else:
+        dist.scatter(chunk, None, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if on_cuda and kmer_graph._h.stream != torch.cuda.current_stream(device).cuda_stream:
+        torch.cuda.synchronize(device)
+    e1 = torch.cuda.Event(enable_timing=True) if e0 is not None else None
+    if e1 is not None:
+        e1.record()
+    h.check(lib.ac_path_lines_render(h.ptr, chunk.data_ptr(), rsizes[rank]))
+    if stats is not None:
+        e2 = torch.cuda.Event(enable_timing=True) if e0 is not None else None
+        if e2 is not None:
+            e2.record()
+        stats["_events2"] = (e0, e1, e2)
+        stats["path_tokens_bytes"] = sum(rsizes) * TOKEN_BYTES
+    kmer_graph._token_buffers = (chunk,)
+    return graph, PathLines(h)
 
 
 def compress_distributed(kmer_graph, seq_lo, seq_hi, device, group=None, stats=None):

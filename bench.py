@@ -207,18 +207,22 @@ def run_gpu(args):
     bounds = [first_of[f] for f in files] + [len(seqs)]
     seq_lo, seq_hi = bounds[per_rank * rank], bounds[per_rank * (rank + 1)]
 
+    rank_bounds = [bounds[per_rank * r] for r in range(world)] + [len(seqs)]
+
     def step(upload):
-        if upload:
+        if upload and world == 1:
             kg.upload()
+        elif upload:                 # every rank copies its own strands host -> device; the others' arrive over NVLink
+            acdist.upload_sharded(kg, rank_bounds, dev)
         if world == 1:
             g = api.UnitigGraph.compress(kg)                 # compress.rs:42-47 in one call: k-mer graph -> unitig graph -> simplify -> GFA text
         else:
             st = {}
-            g = acdist.compress_distributed(kg, seq_lo, seq_hi, dev, stats=st)      # the same, sharded: one all-gather of k-mer buckets, rank 0 finishes
+            # the same, sharded: one all-gather of k-mer buckets, rank 0 finishes the graph and prints H/S/L, every rank prints its own P lines
+            g, lines = acdist.compress_distributed_split(kg, seq_lo, seq_hi, dev, stats=st)
             exchange_stats.append(st)
-            if g is None:
-                return None, None
-        return g, g.gfa_view()
+            return g, (g.gfa_view() if g is not None else memoryview(b""), lines.view())
+        return g, (g.gfa_view(), memoryview(b""))
 
     exchange_stats = []
 
@@ -262,13 +266,38 @@ def run_gpu(args):
 
     g, gfa, t = last
     parity = None
+
+    def whole_file(parts):
+        """input_assemblies.gfa of a step: rank 0's text followed by every rank's P lines in rank order (gathered to rank 0 for the check only)."""
+        head, lines = parts
+        if world == 1:
+            return bytes(head)
+        mine = torch.frombuffer(bytearray(bytes(lines)) or bytearray(1), dtype=torch.uint8).to(dev)
+        n_mine = torch.tensor([len(lines)], dtype=torch.int64, device=dev)
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, n_mine)
+        sizes = [int(x) for x in sizes.tolist()]
+        pad = torch.zeros(max(1, max(sizes)), dtype=torch.uint8, device=dev); pad[:mine.numel()] = mine
+        got = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, got, dst=0)
+        if rank != 0:
+            return None
+        return bytes(head) + b"".join(bytes(got[r][:sizes[r]].cpu().numpy().tobytes()) for r in range(world))
+
+    file1, file2 = whole_file(gfa), whole_file(last2[1])
+    d2h_all = torch.tensor([float(last2[2].d2h_bytes) + len(last2[1][1])], device=dev)
+    own_strand_bytes = sum(sq.length + K - 1 for sq in seqs[seq_lo:seq_hi]) + 24 * len(seqs)      # this rank's padded strands + the sequence table
+    h2d_all = torch.tensor([float(last2[2].h2d_bytes) if world == 1 else float(own_strand_bytes)], device=dev)
+    if world > 1:
+        dist.all_reduce(d2h_all); dist.all_reduce(h2d_all)
     if rank == 0:      # every timed run is checked: SHA-256 of the last step's GFA against the oracle's committed hash
         import hashlib
-        sha = hashlib.sha256(bytes(gfa)).hexdigest()
-        sha2 = hashlib.sha256(bytes(last2[1])).hexdigest()
+        sha = hashlib.sha256(file1).hexdigest()
+        sha2 = hashlib.sha256(file2).hexdigest()
         golden = golden_for(golden_key)
         parity = {"sha256": sha, "golden": golden, "golden_key": golden_key, "ok": bool(golden) and sha == golden and sha2 == golden,
-                  "checked": "last step of the resident-input loop and of the host-buffer (e2e) loop"}
+                  "checked": "last step of the resident-input loop and of the host-buffer (e2e) loop" + ("" if world == 1 else "; the file is rank 0's H/S/L text followed by the ranks' P lines")}
+        gfa = file1
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -289,11 +318,12 @@ def run_gpu(args):
         "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic (splitmix64 genomes, SURVEY.md §8d)",
         "config": {"workload": WORKLOAD, "k": K, "input_bases": n_bases, "sequences": len(seqs),
-                   "exchange": None if world == 1 else "all-gather of deduplicated k-mer entries (16 B each) over NCCL, then gather of unitig occurrences (16 B each) to rank 0",
+                   "exchange": None if world == 1 else "all-gather of deduplicated k-mer entries (16 B each) over NCCL, gather of unitig occurrences (16 B each) to rank 0, scatter of path tokens (4 B per occurrence) back to the owners",
                    "l2": "working set per step (table %.0f MB + per-position arrays) exceeds the 126 MB L2 and is re-initialised every step" % (t.table_capacity * 16 / 1e6),
                    "gfa_bytes": len(gfa), "unitigs": int(g.counts().n_unitigs), "numa_node": numa_node},
         "e2e": {"value": round(e2e, 3), "unit": "Mbp/s", "ms_per_step": round(ms_e2e / args.steps, 3),
-                "h2d_bytes_per_step": int(last2[2].h2d_bytes), "d2h_bytes_per_step": int(last2[2].d2h_bytes)},
+                "h2d_bytes_per_step": int(h2d_all.item()), "d2h_bytes_per_step": int(d2h_all.item()),
+                "copies": "h2d = every rank's own strands over its own PCIe link (the others' blocks are broadcast over NVLink), summed over the ranks; d2h = rank 0's H/S/L text + every rank's own P lines, each over its own link" if world > 1 else "one GPU"},
         "gpu_launches": int(launches),
         "parity": parity,
         "clocks": clocks,
@@ -310,8 +340,8 @@ def run_gpu(args):
         keys = [k2 for k2 in xstats[0] if k2.endswith("_ms")]
         out["stage_ms"].update({k2: round(sum(st[k2] for st in xstats) / len(xstats), 3) for k2 in keys})
         out["exchange"] = {k2: int(xstats[-1][k2]) for k2 in xstats[-1] if not k2.endswith("_ms")}
-        tail = {k2: v for k2, v in out["stage_ms"].items() if k2 in ("unitigs", "links", "seed_sort", "emit", "device_simplify", "device_gfa", "d2h")}
-        out["limiting_stage"] = max(tail, key=tail.get) + " (rank 0 finishes the union graph alone)"
+        tail = {k2: v for k2, v in out["stage_ms"].items() if k2 in ("unitigs", "links", "seed_sort", "emit", "device_simplify", "device_gfa", "d2h", "adjacency", "merge_ms", "exchange_ms", "gather_runs_ms", "path_lines_ms")}
+        out["limiting_stage"] = max(tail, key=tail.get) + " (rank 0's view; unitigs to device_gfa are the union graph finished by rank 0 alone)"
     if rank == 0:
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sample_replicon=600_000)

@@ -99,6 +99,10 @@ int ac_add_sequence(ac_handle* h, uint16_t seq_id, const uint8_t* fwd_padded, ui
                     const char* filename, const char* contig_header);
 int ac_clear_sequences(ac_handle* h);
 int ac_upload(ac_handle* h);            /* host -> HBM copy of the added sequences */
+/* Multi-GPU: copy only the strands of sequences [seq_lo, seq_hi) over this process's PCIe link; the other ranks' blocks are brought
+ * over NVLink by the caller's collective, each into the device range ac_strand_block names for it (blocks tile the strand buffer). */
+int ac_upload_shard(ac_handle* h, uint32_t seq_lo, uint32_t seq_hi);
+int ac_strand_block(ac_handle* h, uint32_t seq_lo, uint32_t seq_hi, void** dev_ptr, uint64_t* n_bytes);
 int ac_build(ac_handle* h);             /* k-mer table, unitigs, links, renumber: the graph after from_kmer_graph */
 int ac_simplify(ac_handle* h);          /* simplify_structure */
 /* compress.rs:42-47 in one call — build_kmer_graph, build_unitig_graph, simplify_unitig_graph and the bytes save_gfa writes — as ONE
@@ -133,6 +137,17 @@ int ac_runs_import(ac_handle* h, const void* src, uint64_t n);
 int ac_runs_import_padded(ac_handle* h, const void* src, uint64_t stride_records, const uint64_t* counts, uint32_t n_ranks);
 int ac_build_finish(ac_handle* h);      /* on the rank that imported the runs: the graph after from_kmer_graph */
 int ac_compress_finish(ac_handle* h);
+/* The same with the P lines printed where the sequences live (the GFA of many assemblies is mostly P lines; one rank printing and
+ * copying out all of them is what bounds the scaling):
+ *   rank 0 (it must own the first block of sequences): ac_compress_finish_split — ac_gfa_data then ends after the L lines —
+ *   -> ac_path_tokens_export: one uint32 per occurrence, "(final unitig number - 1) << 1 | strand", rank r's counts[r] tokens at
+ *   dst + r * stride_tokens (the counts given to ac_runs_import_padded) -> [scatter] -> every rank: ac_path_lines_render with the tokens
+ *   of its own occurrences -> ac_path_lines_data: the P lines of its own sequences (unitig_graph.rs:352-360), pinned host memory.
+ * input_assemblies.gfa = rank 0's text followed by the ranks' path lines in rank order. */
+int ac_compress_finish_split(ac_handle* h);
+int ac_path_tokens_export(ac_handle* h, void* dst, uint64_t stride_tokens, const uint64_t* counts, uint32_t n_ranks);
+int ac_path_lines_render(ac_handle* h, const void* tokens, uint64_t n_tokens);
+int ac_path_lines_data(ac_handle* h, const char** data, uint64_t* n_bytes);   /* borrowed: valid until the next call on h */
 int ac_counts_get(const ac_handle* h, ac_counts* out);
 int ac_unitigs_copy(const ac_handle* h, ac_unitigs* out);
 int ac_path_copy(const ac_handle* h, uint64_t seq_index, int32_t* out, uint64_t cap, uint64_t* n);  /* get_unitig_path_for_sequence_i32 */

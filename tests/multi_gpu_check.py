@@ -55,6 +55,20 @@ for name, n_asm, lens, k in cases:
         print(name, k, "world", world, "same as the oracle" if good else f"DIFFERENT multi={multi[:12]} single={single[:12]} oracle={expected[:12]}", flush=True)
         ok = ok and good
     dist.barrier()
+    # the fused forms: rank 0 prints the whole file / every rank prints the P lines of its own sequences (what bench.py times at N > 1)
+    kg.upload()
+    gf = acdist.compress_distributed(kg, bounds[flo], bounds[fhi], torch.device("cuda", local))
+    fused = hashlib.sha256(bytes(gf.gfa_view())).hexdigest() if rank == 0 else None
+    kg.upload()
+    gs, lines = acdist.compress_distributed_split(kg, bounds[flo], bounds[fhi], torch.device("cuda", local))
+    parts = [None] * world
+    dist.all_gather_object(parts, bytes(lines.view()))
+    if rank == 0:
+        split = hashlib.sha256(bytes(gs.gfa_view()) + b"".join(parts)).hexdigest()
+        good = fused == split == expected
+        print(name, k, "world", world, "fused and split-path forms", "same as the oracle" if good else f"DIFFERENT fused={fused[:12]} split={split[:12]} oracle={expected[:12]}", flush=True)
+        ok = ok and good
+    dist.barrier()
 if rank == 0:
     print("MULTI_GPU_CHECK", "OK" if ok else "FAIL", flush=True)
 dist.destroy_process_group()

@@ -51,6 +51,19 @@ for ci, (files, k) in enumerate(todo):
     if rank == 0 and bytes(g.gfa_view()).decode() != want:
         ok = False
         print("MISMATCH (fused) case", ci, "k", k, flush=True)
+    cuts = [acdist.shard_bounds(len(seqs), r, world) for r in range(world)]
+    kg = api.KmerGraph(k, lib=lib)                                   # a fresh handle: its strand buffer holds nothing yet
+    kg.add_sequences(seqs, count, upload=False)
+    if any(b == a for a, b in cuts):
+        kg.upload()
+    else:                                                            # every rank uploads its own strands only; broadcasts bring the rest
+        acdist.upload_sharded(kg, [c[0] for c in cuts] + [len(seqs)], "cpu")
+    g2, lines = acdist.compress_distributed_split(kg, lo, hi, "cpu")   # the same with every rank printing the P lines of its own sequences
+    parts = [None] * world
+    dist.all_gather_object(parts, bytes(lines.view()))
+    if rank == 0 and (bytes(g2.gfa_view()) + b"".join(parts)).decode() != want:
+        ok = False
+        print("MISMATCH (split path lines) case", ci, "k", k, flush=True)
 dist.barrier()
 if rank == 0:
     print("RESULT", "OK" if ok else "FAIL", flush=True)
