@@ -322,7 +322,7 @@ template <int W> struct InsertBody {
     }
 };
 #ifndef AC_EMULATE
-// The insert kernel proper: the grid-stride loop of ac_body_kernel_occ, software-pipelined — while a unit is probed, the keys of the
+// The insert loop software-pipelined (AC_INSERT_PIPELINED=1; NOT the default, it measured slower): while a unit is probed, the keys of the
 // thread's NEXT unit are already built and the load of its home group is in flight, so the table's latency (most of the kernel's stall
 // samples, profiles/r2h) overlaps the probing of the unit before.  n is a multiple of 32: whole warps walk the loop together.
 template <int W, int CTAS> __global__ void __launch_bounds__(256, CTAS) ac_insert_kernel(const InsertBody<W> body, uint64_t n) {
@@ -643,11 +643,11 @@ struct RunAssignBody {
 
 // The distinct k-mers as a list of their slots: the windows that claimed a slot (InsertBody::claimed_bits), compacted.
 struct ClaimedCountBody { const uint32_t* bits; uint64_t n_words; uint32_t* cnt; AC_D void operator()(uint64_t w) const { cnt[w] = w < n_words ? ac_popc(bits[w]) : 0u; } };
-struct ClaimedListBody {
+struct ClaimedListBody {     // one thread per coordinate: slot ids read coalesced, a word's entries written side by side
     const uint32_t* bits; const uint32_t* off; const uint32_t* pos_slot; uint32_t* list;
-    AC_D void operator()(uint64_t w) const {
-        uint32_t m = bits[w], at = off[w];
-        while (m) { const int b = ac_ctz(m); list[at++] = pos_slot[w * 32 + (uint64_t)b]; m &= m - 1; }
+    AC_D void operator()(uint64_t g) const {
+        const uint32_t m = bits[g >> 5], b = (uint32_t)g & 31u;
+        if ((m >> b) & 1u) list[off[g >> 5] + ac_popc(m & ((1u << b) - 1u))] = pos_slot[g];
     }
 };
 // Multi-GPU exchange of the deduplicated local tables ("k-mer buckets"): the occupied slots, by the list the insert kernel made.
@@ -1785,7 +1785,7 @@ struct DevicePipeline::Impl {
     DevBuf ascii, packed, seqs, slots, pos_slot, flags8, bmask, bcount, boff, counters, uid_rep, slot_unitig;
     DevBuf run_start, run_len, run_uk, run_dir, is_rep, rep_idx, run_unitig, unitigs, nchunks, chunk_off, partial, link_count, links;
     DevBuf scan_tmp[4];
-    int insert_occupancy = getenv("AC_INSERT_OCC") ? atoi(getenv("AC_INSERT_OCC")) : 4;   // resident CTAs per SM the insert kernel is compiled for (3 to 6)
+    int insert_occupancy = getenv("AC_INSERT_OCC") ? atoi(getenv("AC_INSERT_OCC")) : 6;   // resident CTAs per SM the insert kernel is compiled for (5, 6 or 8; 3 to 6 for the pipelined loop)
     DevBuf d_fixed, cand_flag, cand_index, d_cands, d_cand_at, d_deps, d_spec;
     DevBuf sort_a, sort_b, sort_ra, sort_rb, num_prefix, rank, d_len, d_depth, need, d_seq_off, d_arena, d_min_fpos, d_min_rpos;
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
@@ -2128,11 +2128,11 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
         claimed.ensure((n_words + 8) * 4); ac_memset(claimed.p, 0, (n_words + 8) * 4, &stream);
         const InsertBody<W> ins{tv, p, interior8.as<uint8_t>(), (uint32_t)g_first, (uint32_t)g_begin, (uint32_t)g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), false, claimed.as<uint32_t>()};
 #ifndef AC_EMULATE
-        static const bool plain_loop = getenv("AC_INSERT_PLAIN") != nullptr;      // comparison: the loop without the prefetch of the next unit's home group
-        if (!plain_loop) ac_launch_insert<W>(&stream, ins, (g_end - g_first + 31) / 32 * 32, insert_occupancy);
+        static const bool pipelined = getenv("AC_INSERT_PIPELINED") != nullptr;   // the loop with the next unit's home group in flight: measured slower (r2k: 0.98 ms against 0.79 on cfg2, 75 registers or spills), kept for comparison
+        if (pipelined) ac_launch_insert<W>(&stream, ins, (g_end - g_first + 31) / 32 * 32, insert_occupancy == 6 ? 3 : insert_occupancy);
         else
 #endif
-        ac_launch_occ("insert", &stream, ins, (g_end - g_first + 31) / 32 * 32, insert_occupancy == 4 || insert_occupancy == 3 ? 5 : insert_occupancy);
+        ac_launch_occ("insert", &stream, ins, (g_end - g_first + 31) / 32 * 32, insert_occupancy);
         ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
         if (hc[2] && cap != safe_cap) { cap = safe_cap; continue; }         // the estimate was off (it is an estimate): start again with the safe size
         if (hc[2]) throw std::runtime_error("k-mer table overflow");
@@ -2151,7 +2151,7 @@ uint64_t DevicePipeline::Impl::list_claimed() {
     ac_launch("claimed_count", &stream, ClaimedCountBody{claimed.as<uint32_t>(), n_words, claimed_cnt.as<uint32_t>()}, n_words + 1);
     const uint64_t n = exclusive_scan(claimed_cnt.as<uint32_t>(), claimed_cnt.as<uint32_t>(), n_words + 1);
     occ_list.ensure((n + 1) * 4);
-    ac_launch("claimed_list", &stream, ClaimedListBody{claimed.as<uint32_t>(), claimed_cnt.as<uint32_t>(), pos_slot.as<uint32_t>(), occ_list.as<uint32_t>()}, n_words);
+    ac_launch("claimed_list", &stream, ClaimedListBody{claimed.as<uint32_t>(), claimed_cnt.as<uint32_t>(), pos_slot.as<uint32_t>(), occ_list.as<uint32_t>()}, n_words * 32);
     return n;
 }
 uint64_t DevicePipeline::Impl::do_count_entries() {
