@@ -140,10 +140,13 @@ class _Handle:
     def __init__(self, lib, k, device=0, stream=None, keep_positions=False, devices=None):
         self.lib = lib
         self.k = k
-        self.stream = stream or 0        # the cudaStream_t the library was told to run on (0: its own)
+        # stream: None -> the library creates a private (non-blocking) stream; a cudaStream_t -> it runs there.  0 names CUDA's legacy
+        # default stream (what torch.cuda.current_stream().cuda_stream is unless the caller switched streams): ac_config takes NULL as
+        # "private", so the default stream is handed over by its explicit handle cudaStreamLegacy (0x1).
+        self.stream = stream             # what the caller named (None: the library's own)
         self.ptr = C.c_void_p()
         devs = (C.c_int32 * len(devices))(*devices) if devices else None      # several GPUs driven by this one process (ac_config.n_devices)
-        cfg = AcConfig(k, device, stream, 1 if keep_positions else 0, len(devices) if devices else 0, devs)
+        cfg = AcConfig(k, device, None if stream is None else (stream or 1), 1 if keep_positions else 0, len(devices) if devices else 0, devs)
         rc = lib.ac_create(C.byref(self.ptr), C.byref(cfg))
         if rc != AC_OK:
             raise AutocyclerGpuError(rc, lib.ac_last_error(None).decode())
@@ -151,6 +154,11 @@ class _Handle:
     def check(self, rc):
         if rc != AC_OK:
             raise AutocyclerGpuError(rc, self.lib.ac_last_error(self.ptr).decode())
+
+    def runs_on(self, cuda_stream):
+        """True when the library was told to run on exactly this cudaStream_t (then work a caller enqueues there is ordered with the
+        library's by the stream itself); a handle with a private stream is ordered with nobody and needs the device to settle."""
+        return self.stream is not None and int(self.stream) == int(cuda_stream)
 
     def close(self):
         if self.ptr:
@@ -344,9 +352,9 @@ def merge_linear_paths(graph, seqs=()):   # graph_simplification.rs:315-371; seq
     graph._h.check(graph._h.lib.ac_merge_linear_paths(graph._h.ptr, 1 if seqs is not None and len(seqs) else 0))
 
 
-def load_sequences(assemblies_dir, k_size, max_contigs=25, threads=8, lib=None, device=0):
+def load_sequences(assemblies_dir, k_size, max_contigs=25, threads=8, lib=None, device=0, stream=None):
     """compress.rs:98-133 -> (KmerGraph holding the staged sequences, [Sequence], assembly_count)."""
-    kg = KmerGraph(k_size, device=device, lib=lib)
+    kg = KmerGraph(k_size, device=device, lib=lib, stream=stream)
     h = kg._h
     count = C.c_uint64()
     h.check(h.lib.ac_load_sequences(h.ptr, os.fsencode(assemblies_dir), max_contigs, threads, C.byref(count)))

@@ -129,6 +129,13 @@ inline void ac_l2_keep(AcStream* st, void* base, size_t bytes) {
     if (bytes == 0) cudaCtxResetPersistingL2Cache();
     cudaGetLastError();
 }
+// AC_SYNC_LAUNCHES=1 (debugging): wait for every kernel right after its launch and name the one that failed.
+inline void ac_debug_sync(const char* name, AcStream* st) {
+    static const bool on = getenv("AC_SYNC_LAUNCHES") != nullptr;
+    if (!on) return;
+    const cudaError_t e = cudaStreamSynchronize(st->s);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("kernel ") + name + " failed: " + cudaGetErrorString(e));
+}
 inline void* ac_host_alloc(size_t bytes) { void* p = nullptr; AC_CUDA_CHECK(cudaMallocHost(&p, bytes ? bytes : 1)); return p; }
 inline void ac_host_free(void* p) { if (p) cudaFreeHost(p); }
 
@@ -175,6 +182,7 @@ template <class Body> inline void ac_launch_occ(const char* name, AcStream* st, 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("launch ") + name + ": " + cudaGetErrorString(e));
     ++g_ac_kernel_launches;
+    ac_debug_sync(name, st);
 }
 
 // Cooperative launch (all CTAs co-resident): body(thread, n_threads, sync) walks its items with stride n_threads and may call
@@ -204,6 +212,7 @@ template <class Body> inline void ac_launch_coop(const char* name, AcStream* st,
     cudaError_t e = cudaLaunchCooperativeKernel((void*)ac_coop_kernel<Body>, dim3(blocks), dim3(256), args, 0, st->s);
     if (e != cudaSuccess) throw std::runtime_error(std::string("cooperative launch ") + name + ": " + cudaGetErrorString(e));
     ++g_ac_kernel_launches;
+    ac_debug_sync(name, st);
 }
 
 template <class Body> inline void ac_launch(const char* name, AcStream* st, const Body& body, uint64_t n) {
@@ -216,6 +225,7 @@ template <class Body> inline void ac_launch(const char* name, AcStream* st, cons
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("launch ") + name + ": " + cudaGetErrorString(e));
     ++g_ac_kernel_launches;
+    ac_debug_sync(name, st);
 }
 #endif   // __CUDACC__
 #endif

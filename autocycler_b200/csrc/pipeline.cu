@@ -361,6 +361,7 @@ template <int W> static void ac_launch_insert(AcStream* st, const InsertBody<W>&
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("launch insert: ") + cudaGetErrorString(e));
     ++g_ac_kernel_launches;
+    ac_debug_sync("insert", st);
 }
 #endif
 
@@ -919,6 +920,7 @@ template <class Less> static uint32_t* sort_indices(AcStream* stream, const Less
     ac_tile_sort_kernel<Less><<<(unsigned)tiles, 1024, smem, stream->s>>>(less, n, a, ra); ++g_ac_kernel_launches;      // 32 warps on the SM: the searches are chains of dependent shared-memory loads
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("launch tile sort: ") + cudaGetErrorString(e));
+    ac_debug_sync("tile_sort", stream);
 #else
     ac_launch("tile_sort", stream, TileSortBody<Less>{less, n, a, ra}, tiles);
 #endif
@@ -1765,7 +1767,15 @@ __global__ void __launch_bounds__(256) ac_scan_chained_kernel(const uint32_t* in
 // ------------------------------------------------------------------------------------------------
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
-    void ensure(size_t bytes) { if (bytes > cap) { ac_dev_free(p); p = nullptr; cap = 0; p = ac_dev_alloc(bytes); cap = bytes; } }
+    void ensure(size_t bytes) {
+        if (bytes > cap) {
+            ac_dev_free(p); p = nullptr; cap = 0; p = ac_dev_alloc(bytes); cap = bytes;
+#ifdef AC_EMULATE
+            static const bool poison = getenv("AC_EMU_POISON") != nullptr;
+            if (poison) memset(p, 0xA5, cap);
+#endif
+        }
+    }
     template <class T> T* as() { return (T*)p; }
     ~DevBuf() { ac_dev_free(p); }
 };
@@ -1841,6 +1851,7 @@ struct DevicePipeline::Impl {
         scan_tickets += nb;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw std::runtime_error(std::string("launch scan: ") + cudaGetErrorString(e));
+        ac_debug_sync("scan", &stream);
         uint32_t total_sum = 0;
         if (want_total) { ac_d2h(&total_sum, st + 1, sizeof(uint32_t), &stream); ac_sync(&stream); }
         return total_sum;
@@ -1912,6 +1923,24 @@ struct DevicePipeline::Impl {
     void do_import_runs(const void* dev_ptr, uint64_t n);
     void do_import_runs_from(const void* const* ptrs, const uint64_t* counts, uint32_t n_ranks);
     DevBuf own_entries, own_runs;
+#ifdef AC_EMULATE
+    // AC_EMU_POISON=1 (CPU suite): before every table build, every device buffer a kernel writes is filled with a pattern, so a kernel that
+    // reads what THIS build has not written (on the GPU: leftovers of the previous build, whose slot numbers differ from run to run, while
+    // the emulation reproduces them exactly) shows up on the CPU as well.
+    void poison() {
+        static const bool on = getenv("AC_EMU_POISON") != nullptr;
+        if (!on) return;
+        DevBuf* all[] = {&packed, &slots, &pos_slot, &flags8, &bmask, &bcount, &boff, &counters, &uid_rep, &slot_unitig, &run_start, &run_len, &run_uk, &run_dir, &is_rep, &rep_idx,
+                         &run_unitig, &unitigs, &nchunks, &chunk_off, &partial, &link_count, &links, &scan_tmp[0], &scan_tmp[1], &scan_tmp[2], &scan_tmp[3], &d_fixed, &cand_flag, &cand_index,
+                         &d_cands, &d_cand_at, &d_deps, &d_spec, &sort_a, &sort_b, &sort_ra, &sort_rb, &num_prefix, &rank, &d_len, &d_depth, &need, &d_seq_off, &d_arena, &d_min_fpos, &d_min_rpos,
+                         &strand_cnt, &d_next_off, &d_next, &prev_cnt, &d_prev_off, &d_prev, &d_path, &d_path_off, &d_rec, &d_pred, &d_level, &d_flagmax, &d_counters64, &d_dirty, &d_exhausted,
+                         &d_arena2, &d_arena3, &d_pos, &sort_c, &sort_d, &d_pos2, &gfa_s_size, &gfa_l_size, &gfa_p_size, &gfa_pieces, &d_text, &d_ptext, &d_last, &run_hs, &run_ts, &claimed,
+                         &claimed_cnt, &occ_list, &bloom, &count_big, &interior8, &d_small, &d_totals, &d_own_off, &d_own_last, &d_own_size, &own_entries, &own_runs};
+        for (DevBuf* b : all) if (b->p) memset(b->p, 0xA5, b->cap);
+    }
+#else
+    void poison() {}
+#endif
 };
 
 DevicePipeline::DevicePipeline(int device, void* stream) : impl(new Impl) {
@@ -2076,6 +2105,7 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
     if (seq_lo == seq_hi) { g_begin = g_end = 0; }       // a rank without sequences still merges, and computes the replicated stages
     else { g_begin = hs[seq_lo].start; g_end = hs[seq_hi - 1].start + hs[seq_hi - 1].len; }
     is_multi = multi; own_seq_lo = seq_lo; own_seq_hi = seq_hi;
+    poison();
     // windows = total - n_seqs*(k-1); a canonical table can hold at most that many entries (all ranks' windows: after
     // the exchange every rank's table holds the k-mers of every sequence)
     n_windows = total - (uint64_t)n_seqs * (k - 1);

@@ -31,7 +31,7 @@ def _exchange(kmer_graph, seq_lo, seq_hi, device, group, stats):
     on_cuda = torch.device(device).type == "cuda"
     # The collectives are ordered after the kernels on torch's current stream.  When the library runs on that same stream (bench.py
     # and the tests hand it over) stream order is all that is needed; a handle with a private stream needs the device to settle.
-    same_stream = on_cuda and kmer_graph._h.stream == torch.cuda.current_stream(device).cuda_stream
+    same_stream = on_cuda and kmer_graph._h.runs_on(torch.cuda.current_stream(device).cuda_stream)
 
     def settle():
         if on_cuda and not same_stream:
@@ -139,7 +139,7 @@ def upload_sharded(kmer_graph, bounds, device, group=None):
     lib = h.lib
     h.check(lib.ac_upload_shard(h.ptr, bounds[rank], bounds[rank + 1]))
     on_cuda = torch.device(device).type == "cuda"
-    if on_cuda and h.stream != torch.cuda.current_stream(device).cuda_stream:
+    if on_cuda and not h.runs_on(torch.cuda.current_stream(device).cuda_stream):
         torch.cuda.synchronize(device)
     work, mine = [], 0
     for r in range(world):
@@ -156,7 +156,7 @@ def upload_sharded(kmer_graph, bounds, device, group=None):
         work.append(dist.broadcast(block, src=dist.get_global_rank(group, r) if group is not None else r, group=group, async_op=True))
     for w in work:
         w.wait()
-    if on_cuda and h.stream != torch.cuda.current_stream(device).cuda_stream:
+    if on_cuda and not h.runs_on(torch.cuda.current_stream(device).cuda_stream):
         torch.cuda.synchronize(device)
     return mine
 
@@ -199,12 +199,12 @@ def compress_distributed_split(kmer_graph, seq_lo, seq_hi, device, group=None, s
         tokens = torch.empty(world * max_r, dtype=torch.int32, device=device)
         counts = (C.c_uint64 * world)(*rsizes)
         h.check(lib.ac_path_tokens_export(h.ptr, tokens.data_ptr(), max_r, counts, world))
-        if on_cuda and kmer_graph._h.stream != torch.cuda.current_stream(device).cuda_stream:
+        if on_cuda and not kmer_graph._h.runs_on(torch.cuda.current_stream(device).cuda_stream):
             torch.cuda.synchronize(device)
         dist.scatter(chunk, list(tokens.view(world, max_r).unbind(0)), src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     else:
         dist.scatter(chunk, None, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-    if on_cuda and kmer_graph._h.stream != torch.cuda.current_stream(device).cuda_stream:
+    if on_cuda and not kmer_graph._h.runs_on(torch.cuda.current_stream(device).cuda_stream):
         torch.cuda.synchronize(device)
     e1 = torch.cuda.Event(enable_timing=True) if e0 is not None else None
     if e1 is not None:

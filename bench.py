@@ -192,7 +192,11 @@ def run_gpu(args):
     args.workload = workload
     assemblies = synth.make_assemblies(workload, n_assemblies=n_assemblies)
     n_bases = synth.total_bases(assemblies)
-    stream = torch.cuda.current_stream()
+    # One stream for everything that is timed: the library's kernels and copies, NCCL's ordering (ProcessGroupNCCL orders each collective
+    # against the current stream) and the CUDA events.  A stream of its own rather than the default one: nothing else in the process can
+    # serialise against it.
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
     # stage A once, untimed: product loader + end repair, then a handle bound to torch's current stream
     _, seqs, count = prepare_sequences(assemblies, K)
     kg = api.KmerGraph(K, device=local, stream=stream.cuda_stream)

@@ -43,7 +43,7 @@ typedef struct ac_handle ac_handle;
 typedef struct {
     uint32_t k;             /* odd; 3..511 (compress.rs:56-58 restricts the CLI to 11..501) */
     int32_t device;         /* CUDA device ordinal */
-    void* stream;           /* cudaStream_t to run on, or NULL for a private stream */
+    void* stream;           /* cudaStream_t to run on, or NULL for a private (non-blocking) stream; the default stream is named by its handle (cudaStreamLegacy / cudaStreamPerThread) */
     uint32_t keep_positions;/* non-zero: ac_unitigs_copy can return full forward/reverse position lists */
     int32_t n_devices;      /* > 1: this ONE process drives several GPUs: the assemblies are sharded by file over */
     const int32_t* devices; /* devices[0..n_devices) (devices[0] finishes the graph; `device` and `stream` are ignored); 0/1: one GPU, `device` */
