@@ -22,6 +22,19 @@ def shard_bounds(n_items, rank, world):
     return n_items * rank // world, n_items * (rank + 1) // world
 
 
+def _buffer(kmer_graph, name, numel, dtype, device):
+    """A device buffer that lives as long as the handle and only ever grows: the exchange of a repeated build goes through the same
+    addresses every time (no allocator traffic between the collectives, nothing for NCCL to set up again), and what the library
+    reads asynchronously stays alive without further bookkeeping.  -> a view of exactly `numel` elements."""
+    import torch
+    cache = kmer_graph.__dict__.setdefault("_exchange_cache", {})
+    t = cache.get(name)
+    if t is None or t.numel() < numel or t.dtype != dtype or t.device != torch.device(device):
+        t = torch.empty(max(1, numel + numel // 8), dtype=dtype, device=device)
+        cache[name] = t
+    return t[:numel]
+
+
 def _exchange(kmer_graph, seq_lo, seq_hi, device, group, stats):
     """Steps 1-4 up to the imported occurrences on rank 0.  -> True on rank 0."""
     import torch
@@ -55,9 +68,9 @@ def _exchange(kmer_graph, seq_lo, seq_hi, device, group, stats):
     dist.all_gather_into_tensor(sizes, torch.tensor([n.value], dtype=torch.int64, device=device), group=group)
     sizes = [int(s) for s in sizes.tolist()]
     max_n = max(sizes)
-    send = torch.empty(max(1, max_n) * ENTRY_BYTES, dtype=torch.uint8, device=device)
+    send = _buffer(kmer_graph, "send", max(1, max_n) * ENTRY_BYTES, torch.uint8, device)
     h.check(lib.ac_entries_export(h.ptr, send.data_ptr(), max_n))
-    recv = torch.empty(world * send.numel(), dtype=torch.uint8, device=device)
+    recv = _buffer(kmer_graph, "recv", world * send.numel(), torch.uint8, device)
     dist.all_gather_into_tensor(recv, send, group=group)
     settle()
     t2 = clock()
@@ -74,9 +87,9 @@ def _exchange(kmer_graph, seq_lo, seq_hi, device, group, stats):
     dist.all_gather_into_tensor(rsizes, torch.tensor([n_runs.value], dtype=torch.int64, device=device), group=group)
     rsizes = [int(s) for s in rsizes.tolist()]
     max_r = max(1, max(rsizes))
-    rsend = torch.empty(max_r * RUN_BYTES, dtype=torch.uint8, device=device)
+    rsend = _buffer(kmer_graph, "rsend", max_r * RUN_BYTES, torch.uint8, device)
     h.check(lib.ac_runs_export(h.ptr, rsend.data_ptr(), max_r))
-    rrecv = torch.empty(world * rsend.numel(), dtype=torch.uint8, device=device) if rank == 0 else None
+    rrecv = _buffer(kmer_graph, "rrecv", world * rsend.numel(), torch.uint8, device) if rank == 0 else None
     dist.gather(rsend, list(rrecv.view(world, -1).unbind(0)) if rank == 0 else None, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     settle()
     t5 = clock()
@@ -192,11 +205,11 @@ def compress_distributed_split(kmer_graph, seq_lo, seq_hi, device, group=None, s
     if e0 is not None:
         e0.record()
     graph = None
-    chunk = torch.empty(max_r, dtype=torch.int32, device=device)
+    chunk = _buffer(kmer_graph, "chunk", max_r, torch.int32, device)
     if is_root:
         h.check(lib.ac_compress_finish_split(h.ptr))
         graph = UnitigGraph(kmer_graph)
-        tokens = torch.empty(world * max_r, dtype=torch.int32, device=device)
+        tokens = _buffer(kmer_graph, "tokens", world * max_r, torch.int32, device)
         counts = (C.c_uint64 * world)(*rsizes)
         h.check(lib.ac_path_tokens_export(h.ptr, tokens.data_ptr(), max_r, counts, world))
         if on_cuda and not kmer_graph._h.runs_on(torch.cuda.current_stream(device).cuda_stream):

@@ -229,6 +229,7 @@ def run_gpu(args):
         return g, (g.gfa_view(), memoryview(b""))
 
     exchange_stats = []
+    step_walls = []          # host clock of every timed step, per loop: where a rank waits shows up as a long step on the OTHER ranks' stages
 
     def barrier():
         torch.cuda.synchronize()
@@ -247,10 +248,14 @@ def run_gpu(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         last = None
+        walls = []
         for _ in range(args.steps):
+            w0 = time.perf_counter()
             g, gfa = step(upload)
             t = api.AcTimings(); lib.ac_timings_get(kg._h.ptr, t)
             ins.append(t.insert); dev.append(t.as_dict()); last = (g, gfa, t)
+            walls.append(round((time.perf_counter() - w0) * 1e3, 3))
+        step_walls.append(walls)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -264,9 +269,19 @@ def run_gpu(args):
         t = api.AcTimings(); lib.ac_timings_get(kg._h.ptr, t); return t.kernel_launches
 
     sampler = ClockSampler(local); sampler.start()
-    ms_res, ins_ms, dev_t, last, launches, xstats = timed(upload=False)      # inputs resident in HBM
-    ms_e2e, _, _, last2, _, _ = timed(upload=True)                           # host buffers -> GFA bytes on the host
+    if os.environ.get("AC_BENCH_E2E_FIRST"):                                   # comparison only: the two timed loops in the other order
+        ms_e2e, _, _, last2, _, _ = timed(upload=True)
+        ms_res, ins_ms, dev_t, last, launches, xstats = timed(upload=False)
+    else:
+        ms_res, ins_ms, dev_t, last, launches, xstats = timed(upload=False)      # inputs resident in HBM
+        ms_e2e, _, _, last2, _, _ = timed(upload=True)                           # host buffers -> GFA bytes on the host
     clocks = sampler.stop()
+    per_rank = None
+    if world > 1:          # every rank's view of the sharded stages (rank 0 prints them): a stage that is long on one rank only is that rank waiting for another
+        keys = [k2 for k2 in (xstats[0] if xstats else {}) if k2.endswith("_ms")]
+        mine = {"rank": rank, "step_wall_ms": step_walls, **{k2: round(sum(st[k2] for st in xstats) / len(xstats), 3) for k2 in keys}}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
 
     g, gfa, t = last
     parity = None
@@ -345,6 +360,7 @@ def run_gpu(args):
         out["stage_ms"].update({k2: round(sum(st[k2] for st in xstats) / len(xstats), 3) for k2 in keys})
         out["exchange"] = {k2: int(xstats[-1][k2]) for k2 in xstats[-1] if not k2.endswith("_ms")}
         tail = {k2: v for k2, v in out["stage_ms"].items() if k2 in ("unitigs", "links", "seed_sort", "emit", "device_simplify", "device_gfa", "d2h", "adjacency", "merge_ms", "exchange_ms", "gather_runs_ms", "path_lines_ms")}
+        out["per_rank"] = per_rank
         out["limiting_stage"] = max(tail, key=tail.get) + " (rank 0's view; unitigs to device_gfa are the union graph finished by rank 0 alone)"
     if rank == 0:
         if not args.no_cpu_baseline:
