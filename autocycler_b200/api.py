@@ -48,7 +48,7 @@ class AcUnitigs(C.Structure):
 
 class AcTimings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d", "pack", "insert", "adjacency", "boundaries", "runs", "unitigs", "links", "seed_sort", "emit", "d2h",
-                                        "device_total", "host_graph", "host_simplify", "host_gfa", "sample", "device_simplify", "device_gfa")] + \
+                                        "device_total", "host_graph", "host_simplify", "host_gfa", "sample", "device_simplify", "device_gfa", "insert_kernel", "reserved0")] + \
                [(n, C.c_uint64) for n in ("insert_occurrences", "table_capacity", "table_used", "kernel_launches", "h2d_bytes", "d2h_bytes")]
 
     def as_dict(self):

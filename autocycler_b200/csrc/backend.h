@@ -174,11 +174,7 @@ template <class Body> inline void ac_launch_occ(const char* name, AcStream* st, 
     const int threads = 256;
     const uint64_t want = (n + threads - 1) / threads, max_blocks = 148ull * (uint64_t)ctas_per_sm * 2;   // two waves of resident CTAs, grid-stride beyond
     const unsigned blocks = (unsigned)(want < max_blocks ? want : max_blocks);
-    switch (ctas_per_sm) {
-        case 8: ac_body_kernel_occ<Body, 8><<<blocks, threads, 0, st->s>>>(body, n); break;
-        case 6: ac_body_kernel_occ<Body, 6><<<blocks, threads, 0, st->s>>>(body, n); break;
-        default: ac_body_kernel_occ<Body, 5><<<blocks, threads, 0, st->s>>>(body, n); break;
-    }
+    ac_body_kernel_occ<Body, 6><<<blocks, threads, 0, st->s>>>(body, n);      // one register budget is compiled (6 resident CTAs per SM: 40 registers for the insert body)
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("launch ") + name + ": " + cudaGetErrorString(e));
     ++g_ac_kernel_launches;
@@ -206,7 +202,9 @@ template <class Body> inline void ac_launch_coop(const char* name, AcStream* st,
     }
     uint64_t want = (work + per_block - 1) / per_block;
     if (want < 1) want = 1;
-    const uint64_t cap = resident < 148 ? (uint64_t)resident : 148;     // one CTA per SM is plenty for these small steps, and keeps the barrier cheap
+    static const int env_cap = getenv("AC_COOP_CTAS") ? atoi(getenv("AC_COOP_CTAS")) : 0;       // comparison only: fewer CTAs make a cheaper barrier and a longer walk
+    const int limit = env_cap > 0 && env_cap < 148 ? env_cap : 148;
+    const uint64_t cap = resident < limit ? (uint64_t)resident : (uint64_t)limit;     // one CTA per SM is plenty for these small steps, and keeps the barrier cheap
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     void* args[] = {(void*)&body};
     cudaError_t e = cudaLaunchCooperativeKernel((void*)ac_coop_kernel<Body>, dim3(blocks), dim3(256), args, 0, st->s);

@@ -281,6 +281,7 @@ static void record_timings(ac_handle* h) {
     t.h2d = pt.h2d; t.pack = pt.pack; t.insert = pt.insert; t.adjacency = pt.adjacency; t.boundaries = pt.boundaries; t.runs = pt.runs;
     t.unitigs = pt.unitigs; t.links = pt.links; t.seed_sort = pt.seed_sort; t.emit = pt.emit; t.d2h = pt.d2h; t.device_total = pt.total;
     t.sample = pt.sample; t.device_simplify = pt.simplify; t.device_gfa = pt.gfa;
+    t.insert_kernel = pt.insert_kernel; t.reserved0 = 0;
     uint64_t windows = 0; for (auto& s : h->seqs) windows += s.length;
     t.insert_occurrences = windows; t.table_capacity = h->res.capacity; t.table_used = h->res.n_slots_used;
     t.kernel_launches = h->pipe->kernel_launches();

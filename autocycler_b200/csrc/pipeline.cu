@@ -315,55 +315,12 @@ template <int W> struct InsertBody {
     AC_D void operator()(uint64_t i) const {
         Unit u; prepare(i, u);
 #ifdef AC_EMULATE
-        Slot grp[4] = {0, 0, 0, 0};          // the CPU suite takes the route of the pipelined kernel: the home group handed in
+        Slot grp[4] = {0, 0, 0, 0};          // the CPU suite also takes the route with the home group handed in by the caller
         if (u.valid && !sizing) { ac_ld_group(t.slots + table_home(t, u.h), grp); upsert(u.valid, u.fwd, u.rc, u.h, u.flags, u.g, grp); return; }
 #endif
         upsert(u.valid, u.fwd, u.rc, u.h, u.flags, u.g);
     }
 };
-#ifndef AC_EMULATE
-// The insert loop software-pipelined (AC_INSERT_PIPELINED=1; NOT the default, it measured slower): while a unit is probed, the keys of the
-// thread's NEXT unit are already built and the load of its home group is in flight, so the table's latency (most of the kernel's stall
-// samples, profiles/r2h) overlaps the probing of the unit before.  n is a multiple of 32: whole warps walk the loop together.
-template <int W, int CTAS> __global__ void __launch_bounds__(256, CTAS) ac_insert_kernel(const InsertBody<W> body, uint64_t n) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    typename InsertBody<W>::Unit cur, nxt;
-    Slot grp[4], grp_next[4];
-    body.prepare(i, cur);
-    if (cur.valid) ac_ld_group(body.t.slots + table_home(body.t, cur.h), grp);
-    for (;;) {
-        const uint64_t j = i + stride;
-        const bool more = j < n;
-        if (more) {
-            body.prepare(j, nxt);
-            if (nxt.valid) ac_ld_group(body.t.slots + table_home(body.t, nxt.h), grp_next);
-        }
-        body.upsert(cur.valid, cur.fwd, cur.rc, cur.h, cur.flags, cur.g, grp);
-        if (!more) break;
-        cur = nxt; i = j;
-#pragma unroll
-        for (int x = 0; x < 4; ++x) grp[x] = grp_next[x];
-        __syncwarp();
-    }
-}
-template <int W> static void ac_launch_insert(AcStream* st, const InsertBody<W>& body, uint64_t n, int ctas_per_sm) {
-    if (n == 0) return;
-    const uint64_t want = (n + 255) / 256, max_blocks = 148ull * (uint64_t)ctas_per_sm * 2;
-    const unsigned blocks = (unsigned)(want < max_blocks ? want : max_blocks);
-    switch (ctas_per_sm) {
-        case 6: ac_insert_kernel<W, 6><<<blocks, 256, 0, st->s>>>(body, n); break;
-        case 5: ac_insert_kernel<W, 5><<<blocks, 256, 0, st->s>>>(body, n); break;
-        case 3: ac_insert_kernel<W, 3><<<blocks, 256, 0, st->s>>>(body, n); break;
-        default: ac_insert_kernel<W, 4><<<blocks, 256, 0, st->s>>>(body, n); break;
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) throw std::runtime_error(std::string("launch insert: ") + cudaGetErrorString(e));
-    ++g_ac_kernel_launches;
-    ac_debug_sync("insert", st);
-}
-#endif
 
 // The sizing pass: how many distinct canonical k-mers are there?  A k-mer is sampled when a hash of the seven bases around its centre,
 // read on its canonical strand, ends in six zero bits — a property of the k-mer, so it is kept or dropped with ALL its occurrences and
@@ -1302,6 +1259,15 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
     UnitigRec* rec; char* arena; unsigned long long* arena_used; unsigned long long* total_shifted; uint64_t* dirty; uint8_t* exhausted;
     bool all_due;            // the first pass visits every candidate; later passes only those on the work list
     unsigned long long* total_removed;   // bases the graph lost: every source gives up the piece, the destination gains it once
+    // Marks per level, so that a later pass can step over the levels nobody is due on (SimplifyCoopBody): [level] counts of the marks that
+    // THIS pass will still reach (the marked candidate sits on a later level) and of those left to the next pass.  Counts only ever say
+    // "somebody may be due"; the dirty bits stay the truth.
+    uint32_t* due_cur = nullptr; uint32_t* due_next = nullptr;
+    AC_D void count_mark(uint32_t cnd) const {
+        if (!due_cur) return;
+        const uint32_t lv = level[cnd];
+        ac_atomic_add(!all_due && lv > this_level ? &due_cur[lv] : &due_next[lv], 1u);
+    }
     // strand s read from the end that candidate side `side` compares: its last bases backwards (inputs, side 0) or its first bases (outputs)
     AC_D StrandCursor cursor(UStrand s, uint32_t side) const {
         const UnitigRec& r = rec[s >> 1]; const char* p = arena + r.seq_off;
@@ -1312,6 +1278,7 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
     AC_D void mark(int32_t cnd, bool hard, int32_t below) const {
         if (cnd < 0 || cnd >= below || (!hard && exhausted[cnd])) return;
         ac_atomic_or(&dirty[(size_t)cnd >> 6], (uint64_t)1 << (cnd & 63));
+        count_mark((uint32_t)cnd);
     }
     // Every lane of a warp calls this together (ci may lie beyond the list: such a lane only helps).
     AC_D void operator()(uint64_t ci, uint64_t n) const {
@@ -1393,7 +1360,7 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
             if (trimmed_end) { mark(ds.c[3], false, below); mark(ds.c[4], false, below); mark(ds.c[1], false, below); }
             else { mark(ds.c[2], false, below); mark(ds.c[5], false, below); mark(ds.c[0], false, below); }
         }
-        if (c != common_len) ac_atomic_or(&dirty[(size_t)ci >> 6], (uint64_t)1 << (ci & 63));          // capped: look again next pass
+        if (c != common_len) { ac_atomic_or(&dirty[(size_t)ci >> 6], (uint64_t)1 << (ci & 63)); count_mark((uint32_t)ci); }      // capped: look again next pass (its own level: counted for the next pass)
         ac_atomic_add(total_shifted, (unsigned long long)c);
         ac_atomic_add(total_removed, (unsigned long long)c * (gn - 1));
     }
@@ -1413,6 +1380,12 @@ struct ApplyLevelBody {      // graph_simplification.rs:64-84 for the candidates
 struct SimplifyCoopBody {
     ApplyLevelBody apply; RelocBoundBody next_bound; uint64_t n; const uint32_t* n_levels;
     unsigned long long* c64; unsigned long long* res; uint64_t arena_cap; uint32_t first_set; bool first_is_pass_one, single_pass;
+    // Levels nobody is due on are stepped over without a barrier (later passes touch few of them: BASELINE config 2 walks 47 of its
+    // 6 x 14 levels).  due: three sets of per-level mark counts (stride due_stride), used in rotation — the pass reads `cur`, marks for the
+    // pass after it go to `next`, and the set the pass before read is cleared for re-use once everybody is past this pass's first barrier.
+    // Every thread takes the same decision at a level: marks into cur[l] are only made while a level below l is worked on, and a barrier
+    // lies between that and the first look at cur[l].  The last level is never skipped, so that every pass has a barrier.
+    uint32_t* due = nullptr; uint32_t due_stride = 0, first_due = 0;
     template <class Sync> AC_D void operator()(uint64_t tid, uint64_t nt, Sync& sync) const {
         const uint32_t levels = *n_levels;
         ApplyLevelBody a = apply;
@@ -1421,11 +1394,27 @@ struct SimplifyCoopBody {
             const uint32_t q = (first_set + pass) & 1u;
             unsigned long long* mine = c64 + AC_PASS_SET(q); unsigned long long* other = c64 + AC_PASS_SET(q ^ 1u);
             a.all_due = first_is_pass_one && pass == 0; a.total_shifted = mine;
+            const uint32_t dq = (first_due + pass) % 3u;
+            uint32_t* due_old = nullptr;
+            if (due) { a.due_cur = due + (size_t)dq * due_stride; a.due_next = due + (size_t)((dq + 1u) % 3u) * due_stride; due_old = due + (size_t)((dq + 2u) % 3u) * due_stride; }
+            bool fenced = false;
             for (uint32_t l = 1; l <= levels; ++l) {
+                if (due && !a.all_due && l < levels && ac_ld_volatile(&a.due_cur[l]) == 0) continue;
                 a.this_level = l;
+#ifdef AC_EMULATE
+                if (getenv("AC_HOST_PROFILE")) {
+                    uint64_t due = 0;
+                    for (uint64_t ci = 0; ci < n; ++ci) if (a.level[ci] == l && (a.all_due || ((a.dirty[ci >> 6] >> (ci & 63)) & 1))) ++due;
+                    fprintf(stderr, "[device] pass %u level %u: %llu due at its start\n", pass, l, (unsigned long long)due);
+                }
+#endif
                 for (uint64_t base = 0; base < n; base += nt) a(base + tid, n);      // whole warps go in: a lane without a candidate still helps its warp
                 sync();
-                if (l == 1 && tid == 0) for (uint32_t x = 0; x < AC_PASS_SET_WORDS; ++x) other[x] = 0;
+                if (!fenced && tid == 0) {
+                    for (uint32_t x = 0; x < AC_PASS_SET_WORDS; ++x) other[x] = 0;
+                    if (due_old) for (uint32_t x = 0; x <= levels; ++x) due_old[x] = 0;
+                }
+                fenced = true;
                 if (l == levels && tid == 0) mine[2 + AC_BOUND_STRIPES] = ac_ld_volatile(c64);       // nothing is relocated after the last level: the same value for every thread's decision below
             }
             nb.bound = mine + 1;
@@ -1439,7 +1428,7 @@ struct SimplifyCoopBody {
             unsigned long long bound = 0;
             for (uint32_t x = 0; x < AC_BOUND_STRIPES; ++x) bound += ac_ld_volatile(mine + 1 + x);
             const bool go_on = moved != 0 && !single_pass && used + bound + 64 <= arena_cap && pass < 1000000u;
-            if (tid == 0) { res[0] = moved; res[1] += moved; res[2] = pass + 1; res[3] = bound; res[4] = ac_ld_volatile(mine + 1 + AC_BOUND_STRIPES); res[5] = q ^ 1u; res[6] = used; }
+            if (tid == 0) { res[0] = moved; res[1] += moved; res[2] = pass + 1; res[3] = bound; res[4] = ac_ld_volatile(mine + 1 + AC_BOUND_STRIPES); res[5] = q ^ 1u; res[6] = used; res[7] = (dq + 1u) % 3u; }
             if (!go_on) return;
         }
     }
@@ -1795,13 +1784,13 @@ struct DevicePipeline::Impl {
     DevBuf ascii, packed, seqs, slots, pos_slot, flags8, bmask, bcount, boff, counters, uid_rep, slot_unitig;
     DevBuf run_start, run_len, run_uk, run_dir, is_rep, rep_idx, run_unitig, unitigs, nchunks, chunk_off, partial, link_count, links;
     DevBuf scan_tmp[4];
-    int insert_occupancy = getenv("AC_INSERT_OCC") ? atoi(getenv("AC_INSERT_OCC")) : 6;   // resident CTAs per SM the insert kernel is compiled for (5, 6 or 8; 3 to 6 for the pipelined loop)
+    int insert_occupancy = 6;   // resident CTAs per SM the insert kernel is compiled for (5 measured the same, 8 slower for its spills: profiles/r2h_bench_cfg2_occ*.json)
     DevBuf d_fixed, cand_flag, cand_index, d_cands, d_cand_at, d_deps, d_spec;
     DevBuf sort_a, sort_b, sort_ra, sort_rb, num_prefix, rank, d_len, d_depth, need, d_seq_off, d_arena, d_min_fpos, d_min_rpos;
     DevBuf strand_cnt, d_next_off, d_next, prev_cnt, d_prev_off, d_prev, d_path, d_path_off;
     DevBuf d_rec;
     PinBuf h_cands, h_deps, h_spec, h_fixed, h_keys, h_sorted;
-    DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2, d_arena3, d_pos, sort_c, sort_d, d_pos2, gfa_s_size, gfa_l_size, gfa_p_size, gfa_pieces, d_text, d_ptext, d_last, d_pbound;
+    DevBuf d_keys, dist_member, dist_shared, d_pred, d_level, d_flagmax, d_counters64, d_dirty, d_exhausted, d_arena2, d_arena3, d_pos, sort_c, sort_d, d_pos2, gfa_s_size, gfa_l_size, gfa_p_size, gfa_pieces, d_text, d_ptext, d_last, d_pbound, d_due;
     PinBuf h_dirty, h_exhausted, h_order2, h_text, h_ptext, h_pbound;
     PinBuf h_rec, h_depth, h_order, h_arena, h_next_off, h_next, h_prev_off, h_prev, h_path, h_path_off, h_run_start, h_run_len;
 #ifndef AC_EMULATE
@@ -1935,7 +1924,7 @@ struct DevicePipeline::Impl {
                          &d_cands, &d_cand_at, &d_deps, &d_spec, &sort_a, &sort_b, &sort_ra, &sort_rb, &num_prefix, &rank, &d_len, &d_depth, &need, &d_seq_off, &d_arena, &d_min_fpos, &d_min_rpos,
                          &strand_cnt, &d_next_off, &d_next, &prev_cnt, &d_prev_off, &d_prev, &d_path, &d_path_off, &d_rec, &d_pred, &d_level, &d_flagmax, &d_counters64, &d_dirty, &d_exhausted,
                          &d_arena2, &d_arena3, &d_pos, &sort_c, &sort_d, &d_pos2, &gfa_s_size, &gfa_l_size, &gfa_p_size, &gfa_pieces, &d_text, &d_ptext, &d_last, &run_hs, &run_ts, &claimed,
-                         &claimed_cnt, &occ_list, &bloom, &count_big, &interior8, &d_small, &d_totals, &d_own_off, &d_own_last, &d_own_size, &own_entries, &own_runs};
+                         &claimed_cnt, &occ_list, &bloom, &count_big, &interior8, &d_small, &d_totals, &d_own_off, &d_own_last, &d_own_size, &own_entries, &own_runs, &d_due};
         for (DevBuf* b : all) if (b->p) memset(b->p, 0xA5, b->cap);
     }
 #else
@@ -2157,12 +2146,11 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
         const uint64_t g_first = g_begin & ~31ull;
         claimed.ensure((n_words + 8) * 4); ac_memset(claimed.p, 0, (n_words + 8) * 4, &stream);
         const InsertBody<W> ins{tv, p, interior8.as<uint8_t>(), (uint32_t)g_first, (uint32_t)g_begin, (uint32_t)g_end, multi, pos_slot.as<uint32_t>(), counters.as<unsigned long long>(), false, claimed.as<uint32_t>()};
-#ifndef AC_EMULATE
-        static const bool pipelined = getenv("AC_INSERT_PIPELINED") != nullptr;   // the loop with the next unit's home group in flight: measured slower (r2k: 0.98 ms against 0.79 on cfg2, 75 registers or spills), kept for comparison
-        if (pipelined) ac_launch_insert<W>(&stream, ins, (g_end - g_first + 31) / 32 * 32, insert_occupancy == 6 ? 3 : insert_occupancy);
-        else
-#endif
+        // (a software-pipelined form of this loop — the next unit's keys built and its home group in flight while the current one is probed —
+        // measured slower, 0.98 ms against 0.79 on BASELINE config 2 with 75 registers: profiles/r2k_*; it is not kept)
+        mark(20);
         ac_launch_occ("insert", &stream, ins, (g_end - g_first + 31) / 32 * 32, insert_occupancy);
+        mark(21);
         ac_d2h(hc, counters.p, sizeof hc, &stream); ac_sync(&stream);
         if (hc[2] && cap != safe_cap) { cap = safe_cap; continue; }         // the estimate was off (it is an estimate): start again with the safe size
         if (hc[2]) throw std::runtime_error("k-mer table overflow");
@@ -2407,17 +2395,23 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
         ac_memset(d_dirty.p, 0, ((n_cands + 63) / 64) * 8 + 8, &stream); ac_memset(d_exhausted.p, 0, n_cands + 8, &stream);
         // `while expand_repeats() > 0 {}` (only its first call without device_simplify): one launch for as many passes as the arena has room for
         static const bool always_grow = getenv("AC_DEVICE_TIGHT_ARENA") != nullptr;   // test hook: one pass per launch, the growth path before every pass
-        uint32_t next_set = 0; uint64_t passes = 0;
+        uint32_t next_set = 0, next_due = 0; uint64_t passes = 0;
+        static const bool walk_all_levels = getenv("AC_SIMPLIFY_ALL_LEVELS") != nullptr;      // comparison only: every pass walks every level
+        const uint32_t due_stride = fm[3] + 2;
+        if (!walk_all_levels) { d_due.ensure((size_t)3 * due_stride * 4); ac_memset(d_due.p, 0, (size_t)3 * due_stride * 4, &stream); }
         for (bool first = true;; first = false) {
             const ApplyLevelBody apply{d_cands.as<ExpandCandidate>(), d_deps.as<ExpandDeps>(), d_level.as<uint32_t>(), 0, d_spec.as<uint32_t>(),
                                        d_rec.as<UnitigRec>(), d_arena2.as<char>(), c64, c64, d_dirty.as<uint64_t>(), d_exhausted.as<uint8_t>(), first, c64 + AC_PASS_REMOVED};
             const uint64_t room = always_grow ? 0 : d_arena2.cap;
-            ac_launch_coop("simplify", &stream, SimplifyCoopBody{apply, bound_body, n_cands, d_flagmax.as<uint32_t>() + 3, c64, res, room, next_set, first, !device_simplify}, n_cands, 64);
+            ac_launch_coop("simplify", &stream, SimplifyCoopBody{apply, bound_body, n_cands, d_flagmax.as<uint32_t>() + 3, c64, res, room, next_set, first, !device_simplify,
+                                                                 walk_all_levels ? nullptr : d_due.as<uint32_t>(), due_stride, next_due}, n_cands, 64);
             ac_d2h(h64, c64, sizeof h64, &stream); ac_sync(&stream);
             const unsigned long long* r = h64 + AC_PASS_WORDS;
             R.arena_final = h64[0]; R.first_pass_total = r[0]; R.first_pass_done = true;      // what the last expand_repeats() call returned
             R.bases_removed = h64[AC_PASS_REMOVED]; R.any_moved = r[1] != 0;
-            passes += r[2]; next_set = (uint32_t)r[5];
+            passes += r[2]; next_set = (uint32_t)r[5]; next_due = (uint32_t)r[7];
+            if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[device] expand_repeats launch: %llu passes (%llu so far), %u levels, %llu candidates, %llu left on the work list, last pass moved %llu bases\n",
+                                                   r[2], (unsigned long long)passes, fm[3], (unsigned long long)n_cands, r[4], r[0]);
             if (!device_simplify || R.first_pass_total == 0) break;
             if (passes > 1000000) throw std::runtime_error("repeat expansion did not settle");
             bound = r[3];                                                                  // the launch stopped for want of room: make it
@@ -2560,7 +2554,7 @@ void DevicePipeline::Impl::do_complete(PipelineResult& out) {
     if (!arena_pending) return;
     ac_sync(&stream);
     arena_pending = false;
-    out.t.h2d = between(0, 1); out.t.pack = between(2, 3); out.t.insert = between(15, 4); out.t.sample = between(3, 15); out.t.adjacency = between(13, 5);
+    out.t.h2d = between(0, 1); out.t.pack = between(2, 3); out.t.insert = between(15, 4); out.t.insert_kernel = between(20, 21); out.t.sample = between(3, 15); out.t.adjacency = between(13, 5);
     out.t.boundaries = between(5, 6); out.t.runs = between(14, 7); out.t.unitigs = between(7, 8); out.t.links = between(8, 9);
     out.t.seed_sort = between(9, 10); out.t.emit = between(10, 11); out.t.simplify = between(11, 17); out.t.gfa = between(17, 18);
     out.t.d2h = between(18, 12); out.t.total = between(2, 4) + between(13, 6) + between(14, 12);

@@ -15,7 +15,7 @@
 #define AC_SEQ_SLACK 32       // spare bytes on both sides of every unitig in the sequence arena
 
 struct PipelineTimings {      // milliseconds, CUDA events on the pipeline's stream (0 under emulation)
-    float h2d = 0, pack = 0, sample = 0, insert = 0, adjacency = 0, boundaries = 0, runs = 0, unitigs = 0, links = 0, seed_sort = 0, emit = 0, simplify = 0, gfa = 0, d2h = 0, total = 0;
+    float h2d = 0, pack = 0, sample = 0, insert = 0, insert_kernel = 0, adjacency = 0, boundaries = 0, runs = 0, unitigs = 0, links = 0, seed_sort = 0, emit = 0, simplify = 0, gfa = 0, d2h = 0, total = 0;
 };
 
 struct DeviceUnitig {

@@ -81,6 +81,7 @@ typedef struct {            /* milliseconds */
     float h2d, pack, insert, adjacency, boundaries, runs, unitigs, links, seed_sort, emit, d2h, device_total;
     float host_graph, host_simplify, host_gfa;
     float sample, device_simplify, device_gfa;   /* sizing pass of the k-mer table; expand_repeats passes + renumbering and the GFA text when they run on the device */
+    float insert_kernel, reserved0;              /* the hash-insert kernel alone (CUDA events right around its launch; `insert` also holds the table initialisation and the counter read-back) */
     uint64_t insert_occurrences;   /* k-mer occurrences hashed by the insert kernel (forward windows; each feeds both strands) */
     uint64_t table_capacity, table_used;
     uint64_t kernel_launches;      /* cumulative launches of this library's kernels in the process */
