@@ -349,6 +349,7 @@ def run_gpu(args):
         "roofline": {"kernel": "%s<%d> (k-mer hash insert)" % (INSERT_BODY, W), "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "peak_kind": peak_kind,
                      "traffic": measured_traffic("%s<%d>:%s:k%d" % (INSERT_BODY, W, args.workload, K)) if world == 1 else None,
+                     "limiter": "integer ALU pipe (70 % busy, issue slots 64 %; DRAM 18 %, L2 43 %: profiles/kernels_r2.md) - the kernel moves about its algorithmic bytes and is bound by the instructions that hash, probe and compare",
                      "algorithmic_bytes_per_window": bytes_per_window, "windows_per_launch": int(own_windows), "kernel_ms": round(insert_ms, 3),
                      "timed": "CUDA events right around the kernel's launch on the library's stream, mean over the timed steps (stage_ms.insert also holds the table initialisation and the counter read-back)",
                      "accounting": "SURVEY 8(d): 8W+16 bytes per canonical window insert; by DESIGN.md's own count (8W+20.25) achieved %.1f GB/s = %.4f of peak; %.4f of the nominal 8 TB/s"
@@ -365,7 +366,7 @@ def run_gpu(args):
         out["limiting_stage"] = max(tail, key=tail.get) + " (rank 0's view; unitigs to device_gfa are the union graph finished by rank 0 alone)"
     if rank == 0:
         if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(sample_replicon=600_000)
+            out["cpu_baseline"] = cpu_baseline(sample_replicon=1_500_000)       # about 15 s of one core
         if world == 1 and not args.no_cli_wall:
             out["cli_wall"] = cli_wall(assemblies, K, n_bases, parity["golden"] if parity else None)
         print(json.dumps(out), flush=True)
