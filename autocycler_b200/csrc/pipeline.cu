@@ -2137,8 +2137,11 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
     for (int attempt = 0;; ++attempt) {
         if (attempt > 3) throw std::runtime_error("k-mer table build did not settle");
         slots.ensure(cap * sizeof(Slot));
-        static const bool l2_keep = getenv("AC_L2_PERSIST") != nullptr;
-        if (l2_keep) ac_l2_keep(&stream, slots.p, cap * sizeof(Slot));
+        // AC_L2_PERSIST=table | packed (comparison only): ask the L2 to keep the k-mer table, or the 2-bit sequence store every probe's
+        // comparison reads at random, resident while the table is probed (inputs whose table is several times the L2)
+        static const char* l2_keep = getenv("AC_L2_PERSIST");
+        if (l2_keep && !strcmp(l2_keep, "packed")) ac_l2_keep(&stream, packed.p, n_words * sizeof(uint64_t));
+        else if (l2_keep) ac_l2_keep(&stream, slots.p, cap * sizeof(Slot));
         ac_memset(slots.p, 0xFF, cap * sizeof(Slot), &stream);               // AC_EMPTY_SLOT
         if (big_counts) { count_big.ensure(cap * 4); ac_memset(count_big.p, 0, cap * 4, &stream); }
         ac_memset(counters.p, 0, sizeof hc, &stream);
