@@ -136,17 +136,21 @@ class Sequence:
         return Sequence(id, "." * half_k + seq + "." * half_k, filename, contig_header, length)
 
 
+def stream_handle(stream):
+    """The value of ac_config.stream for a caller's stream: None -> NULL (the library creates a private, non-blocking stream); a
+    cudaStream_t -> itself; 0 — CUDA's legacy default stream, what torch.cuda.current_stream().cuda_stream is unless the caller switched
+    streams — -> its explicit handle cudaStreamLegacy (0x1), because NULL already means "private"."""
+    return None if stream is None else (int(stream) or 1)
+
+
 class _Handle:
     def __init__(self, lib, k, device=0, stream=None, keep_positions=False, devices=None):
         self.lib = lib
         self.k = k
-        # stream: None -> the library creates a private (non-blocking) stream; a cudaStream_t -> it runs there.  0 names CUDA's legacy
-        # default stream (what torch.cuda.current_stream().cuda_stream is unless the caller switched streams): ac_config takes NULL as
-        # "private", so the default stream is handed over by its explicit handle cudaStreamLegacy (0x1).
-        self.stream = stream             # what the caller named (None: the library's own)
+        self.stream = stream             # what the caller named (None: the library's own); stream_handle() is what the library is given
         self.ptr = C.c_void_p()
         devs = (C.c_int32 * len(devices))(*devices) if devices else None      # several GPUs driven by this one process (ac_config.n_devices)
-        cfg = AcConfig(k, device, None if stream is None else (stream or 1), 1 if keep_positions else 0, len(devices) if devices else 0, devs)
+        cfg = AcConfig(k, device, stream_handle(stream), 1 if keep_positions else 0, len(devices) if devices else 0, devs)
         rc = lib.ac_create(C.byref(self.ptr), C.byref(cfg))
         if rc != AC_OK:
             raise AutocyclerGpuError(rc, lib.ac_last_error(None).decode())

@@ -350,3 +350,14 @@ def test_several_devices_in_one_process(emu, tmp_path, n_devices):
         api.compress(d, out, k_size=max(k, 11) if k >= 11 else k, lib=emu, devices=list(range(n_devices))) if k >= 11 else None
         if k >= 11:
             assert open(os.path.join(out, "input_assemblies.gfa")).read() == expected and open(os.path.join(out, "input_assemblies.yaml")).read() == yaml
+
+
+def test_stream_argument_semantics(emu):
+    """ac_config.stream (include/autocycler_gpu.h): NULL = a private stream, otherwise the cudaStream_t to run on.  torch's default stream
+    has the handle 0, which must not turn into "private" on the way (the N-rank build orders its collectives by the stream only when the
+    library really runs on it: autocycler_b200/dist.py): it is handed over as cudaStreamLegacy."""
+    assert api.stream_handle(None) is None and api.stream_handle(0) == 1 and api.stream_handle(0x7F00DEAD0000) == 0x7F00DEAD0000
+    private, default, side = (api.KmerGraph(51, lib=emu, stream=s) for s in (None, 0, 0x7F00DEAD0000))
+    assert not private._h.runs_on(0) and not private._h.runs_on(0x7F00DEAD0000)
+    assert default._h.runs_on(0) and not default._h.runs_on(0x7F00DEAD0000)
+    assert side._h.runs_on(0x7F00DEAD0000) and not side._h.runs_on(0)
