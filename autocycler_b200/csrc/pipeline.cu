@@ -2332,7 +2332,7 @@ template <int W> void DevicePipeline::Impl::finish_w(PipelineResult& out, bool k
     d_small.ensure(64); ac_memset(d_small.p, 0, 64, &stream);           // [0] hairpin links
     ac_launch("link_order", &stream, LinkOrderBody{link_count.as<uint32_t>(), links.as<uint32_t>(), rank.as<uint32_t>(), unitigs.as<DeviceUnitig>(),
                                                    d_next_off.as<uint32_t>(), d_next.as<UStrand>(), prev_cnt.as<uint32_t>(), d_small.as<uint32_t>()}, n_strands);
-    exclusive_scan(prev_cnt.as<uint32_t>(), d_prev_off.as<uint32_t>(), (uint64_t)n_strands + 1);
+    exclusive_scan(prev_cnt.as<uint32_t>(), d_prev_off.as<uint32_t>(), (uint64_t)n_strands + 1, 0, false);      // the total is n_links again: no read-back, the stream carries on
     ac_memset(prev_cnt.p, 0, ((size_t)n_strands + 1) * 4, &stream);    // reused as the fill cursor
     ac_launch("prev_fill", &stream, PrevFillBody{d_next_off.as<uint32_t>(), d_next.as<UStrand>(), d_prev_off.as<uint32_t>(), prev_cnt.as<uint32_t>(), d_prev.as<UStrand>()}, n_strands);
     ac_launch("prev_sort", &stream, PrevSortBody{d_prev_off.as<uint32_t>(), d_prev.as<UStrand>()}, n_strands);
