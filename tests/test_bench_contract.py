@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -47,3 +49,25 @@ def test_workload_selection_matches_the_committed_goldens():
 def test_reference_arm_other_ranks_do_nothing():
     r = run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2", "--steps", "1", "--warmup", "0")
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_b200_arm_line():
+    """The B200 arm on the smallest BASELINE config (a second or two on the GPU): one JSON line with the driver's keys, the timed output
+    equal to the oracle's committed hash, kernels of this library counted, the roofline entry for the insert kernel timed on its own."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "cfg1", "--steps", "3", "--warmup", "3", "--no-cpu-baseline"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "e2e", "gpu_launches", "parity", "clocks", "roofline", "stage_ms"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["unit"] == "Mbp/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["parity"]["ok"] is True and d["parity"]["golden_key"] == "cfg1_k51"
+    assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["gpu_launches"] >= 3 * 30
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and 0 < rf["frac"] < 1 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3
+    assert 0 < rf["kernel_ms"] <= d["stage_ms"]["insert"] + 1e-3 and d["stage_ms"]["host_simplify"] == 0 and d["stage_ms"]["host_gfa"] == 0
