@@ -1,15 +1,22 @@
 """Multi-GPU form of UnitigGraph.from_kmer_graph / UnitigGraph.compress: one process per GPU under torch.distributed.
 
-Every rank stages and uploads ALL sequences (they are small: 1 byte per base) and owns a contiguous block of them.
+Every rank stages ALL sequences on the host (1 byte per base) and owns a contiguous block of them (sorted file order).
+  0. upload_sharded: every rank copies only its own strands over its PCIe link, one broadcast per block brings the others' over NVLink
   1. local k-mer table over the owned sequences                       (parallel: the dominant insert work is split N ways)
-  2. ONE data-path collective: all-gather of the deduplicated local tables (16 B per distinct k-mer) over NVLink,
+  2. ONE data-path collective for the table: all-gather of the deduplicated local tables (16 B per distinct k-mer),
      merged into every rank's table (counts add, first/last flags OR, the slot keeps the smallest occurrence, which
      names the k-mer identically on every rank)
   3. adjacency on the now global table (replicated), unitig occurrences along the owned sequences (parallel)
   4. gather of the occurrences (16 B each) to rank 0, which builds unitigs / links / seed order over all of them and
      continues exactly like the single-GPU path: host graph (from_kmer_graph_distributed) or, fused, repeat expansion,
-     renumbering and the GFA text on its device (compress_distributed).
-PyTorch is plumbing here (device buffers + NCCL); the records are produced and consumed by the library's kernels.
+     renumbering and the GFA text on its device (compress_distributed)
+  5. compress_distributed_split: the P lines — most of a many-assembly GFA — are printed by the ranks that own the sequences, from
+     the final "<number><sign>" tokens rank 0 scatters (4 B per occurrence); the file is rank 0's text + the ranks' lines in rank order.
+Ordering: when the handle runs on torch's current stream (`KmerGraph(stream=torch.cuda.current_stream().cuda_stream)`; bench.py does
+this), NCCL's own ordering against that stream is all that is needed; a handle with a private stream (stream=None) is fenced by
+torch.cuda.synchronize around every collective.  PyTorch is plumbing here (device buffers + NCCL); the records are produced and
+consumed by the library's kernels.  The same stages with no collective library at all: ac_config.n_devices (one process, peers read
+over NVLink).
 """
 import ctypes as C
 
