@@ -1,16 +1,17 @@
 #!/usr/bin/env python
 """bench.py — input-assembly Mbp/s through compress -> unitig GFA (BASELINE.json's metric).
 
-A "step" is one pass of the hot path over one batch of synthetic input assemblies:
-padded, end-repaired strands (host memory)  ->  k-mer table, unitigs, links (B200 kernels)  ->
-repeat expansion + renumbering (host)  ->  the bytes of input_assemblies.gfa in host memory.
+A "step" is one pass of the hot path over one batch of synthetic input assemblies (compress.rs:42-47, `ac_compress`):
+padded, end-repaired strands  ->  k-mer table, unitigs, links, repeat expansion, renumbering, GFA text (ONE pipeline of B200 kernels)
+->  the bytes of input_assemblies.gfa in pinned host memory.  Every timed run is gated on the oracle's committed SHA-256 of that file.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          the CUDA path through the C ABI
-  python bench.py --impl reference [...]                        the reference's CPU algorithm (oracle port), 1 core
+  python bench.py [--gpus N] [--steps K] [--warmup W]          the CUDA path through the C ABI (N > 1: torchrun, BASELINE config 5's first 8N assemblies)
+  python bench.py --impl reference [...]                        the reference's CPU algorithm (oracle port, -O3 -march=native), 1 core, the SAME full-size input
 
 `value`  : Mbp/s with the strands already resident in HBM when the timed region starts.
 `e2e`    : the same, with the strands copied from pinned host memory inside the timed region (the call a user makes).
-`roofline`: the hash-insert kernel against the measured HBM copy peak (MEASURED_PEAKS.json).
+`roofline`: the hash-insert kernel alone (events right around its launch) against the measured HBM copy peak (MEASURED_PEAKS.json).
+`cli_wall`: `autocycler compress` from process start to both files closed (stage A, CUDA context and file I/O included).
 """
 import argparse
 import json
