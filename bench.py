@@ -339,7 +339,7 @@ def run_gpu(args):
         "dtype": "u64", "data": "synthetic (splitmix64 genomes, SURVEY.md §8d)",
         "config": {"workload": WORKLOAD, "k": K, "input_bases": n_bases, "sequences": len(seqs),
                    "exchange": None if world == 1 else "all-gather of deduplicated k-mer entries (16 B each) over NCCL, gather of unitig occurrences (16 B each) to rank 0, scatter of path tokens (4 B per occurrence) back to the owners",
-                   "l2": "working set per step (table %.0f MB + per-position arrays) exceeds the 126 MB L2 and is re-initialised every step" % (t.table_capacity * 16 / 1e6),
+                   "l2": "working set per step (table %.0f MB at 8 B per slot + %.0f MB of per-position arrays) exceeds the 126 MB L2; the table is re-initialised and every array rewritten every step" % (t.table_capacity * 8 / 1e6, n_bases * 4.6 / 1e6),
                    "gfa_bytes": len(gfa), "unitigs": int(g.counts().n_unitigs), "numa_node": numa_node},
         "e2e": {"value": round(e2e, 3), "unit": "Mbp/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": int(h2d_all.item()), "d2h_bytes_per_step": int(d2h_all.item()),
