@@ -408,6 +408,10 @@ template <int W> struct BloomBuildBody {   // 32 filter bits per distinct k-mer,
 template <int W> struct AdjacencyBody {
     TableView t; KParams p; bool any_dotted; const uint32_t* occupied; uint8_t* flags8;   // one thread per OCCUPIED slot (full warps)
     const uint64_t* bloom; uint64_t n_words;
+    // Multi-GPU: only the k-mers of this rank's own windows need the flags (the boundary kernel reads them along the owned sequences and
+    // nothing else does).  The list is in coordinate order, so they are the stretch between the scanned claim counts of the words that
+    // hold the first and the last owned coordinate (a few foreign neighbours in those two words come along): range[w0] .. range[w1].
+    const uint32_t* range = nullptr; uint64_t w0 = 0, w1 = 0;
     // Is k-mer `a` in the table?  Almost every candidate neighbour is absent; the L2-resident Bloom filter answers that
     // without touching the table in HBM.
     AC_D bool present(const Key<W>& a, const Key<W>& arc) const {
@@ -417,6 +421,7 @@ template <int W> struct AdjacencyBody {
         return table_find<W>(t, a, arc, p) != AC_NONE32;
     }
     AC_D void operator()(uint64_t x) const {
+        if (range) { x += range[w0]; if (x >= range[w1]) return; }
         const uint64_t i = occupied[x];
         const Slot e = t.slots[i];
         const uint32_t aux = slot_flags(e);
@@ -1901,7 +1906,7 @@ struct DevicePipeline::Impl {
         ac_copy_dd(total_dst, x + (n - 1), 4, &stream);
     }
     uint64_t uploaded_bytes = 0;
-    uint64_t exp_n = 0, n_own_runs = 0; uint32_t own_seq_lo = 0, own_seq_hi = 0;
+    uint64_t exp_n = 0, n_own_runs = 0; uint32_t own_seq_lo = 0, own_seq_hi = 0; bool exp_valid = false;      // exp_n: this rank's own distinct k-mers, counted before the merge
     void do_export_path_tokens(void* dst, uint64_t stride, const uint64_t* counts, uint32_t n_ranks);
     void do_render_path_lines(const void* tokens, uint64_t n_tokens, const char** text, uint64_t* bytes);
     DevBuf d_own_off, d_own_last, d_own_size; uint64_t path_lines_d2h = 0;
@@ -2093,7 +2098,7 @@ template <int W> void DevicePipeline::Impl::local_w(uint32_t seq_lo, uint32_t se
     const SeqInfo* hs = host_seqs.data();
     if (seq_lo == seq_hi) { g_begin = g_end = 0; }       // a rank without sequences still merges, and computes the replicated stages
     else { g_begin = hs[seq_lo].start; g_end = hs[seq_hi - 1].start + hs[seq_hi - 1].len; }
-    is_multi = multi; own_seq_lo = seq_lo; own_seq_hi = seq_hi;
+    is_multi = multi; own_seq_lo = seq_lo; own_seq_hi = seq_hi; exp_valid = false;
     poison();
     // windows = total - n_seqs*(k-1); a canonical table can hold at most that many entries (all ranks' windows: after
     // the exchange every rank's table holds the k-mers of every sequence)
@@ -2178,6 +2183,7 @@ uint64_t DevicePipeline::Impl::list_claimed() {
 uint64_t DevicePipeline::Impl::do_count_entries() {
     if (stage < 1) throw std::runtime_error("build_local must precede the entry export");
     exp_n = list_claimed();                // before any merge: the local table
+    exp_valid = true;
     return exp_n;
 }
 void DevicePipeline::Impl::do_export_entries(void* dst, uint64_t cap_records) {
@@ -2213,7 +2219,15 @@ template <int W> void DevicePipeline::Impl::runs_local_w() {
     bloom.ensure(bloom_words * 8);
     ac_memset(bloom.p, 0, bloom_words * 8, &stream);
     ac_launch("bloom_build", &stream, BloomBuildBody<W>{tv, p, occ_list.as<uint32_t>(), bloom.as<uint64_t>(), bloom_words}, n_slots_used);
-    ac_launch("adjacency", &stream, AdjacencyBody<W>{tv, p, any_dotted, occ_list.as<uint32_t>(), flags8.as<uint8_t>(), bloom.as<uint64_t>(), bloom_words}, n_slots_used);
+    AdjacencyBody<W> adj{tv, p, any_dotted, occ_list.as<uint32_t>(), flags8.as<uint8_t>(), bloom.as<uint64_t>(), bloom_words};
+    uint64_t n_adj = n_slots_used;
+    if (is_multi && exp_valid && exp_n + 64 < n_slots_used) {      // the merged table holds every rank's k-mers; this rank's own ones were listed (and counted) before the merge
+        const uint64_t n_cw = (total + 31) / 32;
+        adj.range = claimed_cnt.as<uint32_t>(); adj.w0 = g_begin >> 5; adj.w1 = std::min<uint64_t>((g_end + 31) >> 5, n_cw);
+        n_adj = exp_n + 64;
+        if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[device] adjacency flags for this rank's own k-mers: at most %llu of %llu\n", (unsigned long long)n_adj, (unsigned long long)n_slots_used);
+    }
+    ac_launch("adjacency", &stream, adj, n_adj);
     mark(5);
 
     const uint64_t n_bwords = (total + 31) / 32;

@@ -361,3 +361,51 @@ def test_stream_argument_semantics(emu):
     assert not private._h.runs_on(0) and not private._h.runs_on(0x7F00DEAD0000)
     assert default._h.runs_on(0) and not default._h.runs_on(0x7F00DEAD0000)
     assert side._h.runs_on(0x7F00DEAD0000) and not side._h.runs_on(0)
+
+
+DIFFERENT_KMERS_CODE = """
+import os, random, sys, tempfile
+sys.path.insert(0, %(tests)r); sys.path.insert(0, %(root)r)
+import cases, oracle_lib as o
+from autocycler_b200 import api
+emu = api.load_library(%(lib)r)
+n_devices = int(sys.argv[1])
+for seed, k in [(1, 21), (2, 31), (3, 51)]:
+    rng = random.Random(9000 + seed)
+    shared = cases.rand_seq(rng, 700)
+    files = []
+    for f in range(2 * n_devices):
+        own = cases.rand_seq(rng, rng.randint(900, 1600))
+        cut = rng.randrange(100, 600)
+        body = own[:400] + (shared[cut:] if f %% 3 == 0 else cases.rc(shared[:cut]) if f %% 3 == 1 else "") + own[400:]
+        recs = [("c1 len=%%d" %% len(body), body)]
+        if f %% 2:
+            extra = cases.rand_seq(rng, rng.randint(k + 5, 300))
+            recs.append(("c2 len=%%d" %% len(extra), extra))
+        files.append(("asm_%%02d.fasta" %% f, recs))
+    with tempfile.TemporaryDirectory() as d:
+        cases.write_case(files, d)
+        expected, yaml, st = o.compress_dir(d, k)
+        count, oseqs = o.load_sequences(d, k)
+    seqs = [api.Sequence(t[0], t[4], t[1], t[2], t[3]) for t in oseqs]
+    kg = api.KmerGraph(k, lib=emu, devices=list(range(n_devices)))
+    kg.add_sequences(seqs, count)
+    g = api.UnitigGraph.compress(kg)
+    assert bytes(g.gfa_view()).decode() == expected, (seed, k)
+print("SAME AS THE ORACLE")
+"""
+
+
+@pytest.mark.parametrize("n_devices", [2, 3, 4])
+def test_devices_holding_different_kmers(emu, n_devices):
+    """Ranks whose assemblies share little: the merged table then holds several times a rank's own k-mers, and the adjacency flags are
+    computed for the rank's own ones only (pipeline.cu runs_local_w) — the stretch of the coordinate-ordered k-mer list between the
+    words of its first and last coordinate.  Some files share a piece (so that k-mers claimed by one rank occur on another), contigs end
+    inside shared pieces.  Same bytes as the oracle, in a child process whose device buffers are poisoned before every build (a flag
+    nobody wrote would show) and which reports that the short route was taken."""
+    import subprocess
+    import sys
+    code = DIFFERENT_KMERS_CODE % {"tests": os.path.join(ROOT, "tests"), "root": ROOT, "lib": os.path.join(ROOT, "tests", "emu", "libautocycler_emu.so")}
+    r = subprocess.run([sys.executable, "-c", code, str(n_devices)], env={**os.environ, "AC_EMU_POISON": "1", "AC_HOST_PROFILE": "1"}, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SAME AS THE ORACLE" in r.stdout, r.stderr[-2000:]
+    assert "adjacency flags for this rank's own k-mers" in r.stderr
