@@ -656,8 +656,10 @@ bool HostGraph::adopt_candidates(const PipelineResult& r) {
     first_pass = true; cands_ready = true; spec_from_device = true;
     device_pass_total = (size_t)-1;
     if (r.first_pass_done) {                  // the device has applied pass 1 already: rec / arena hold its result, this is what it left for pass 2
-        memcpy(dirty.data(), r.dirty, dirty.size() * 8);
-        memcpy(exhausted.data(), r.exhausted, n);
+        if (n) {                              // (no candidates: nothing was listed and the vectors are empty)
+            memcpy(dirty.data(), r.dirty, dirty.size() * 8);
+            memcpy(exhausted.data(), r.exhausted, n);
+        }
         first_pass = false; spec_from_device = false;
         pass_id = 1;                          // the unitigs it changed carry flags == 1
         device_pass_total = (size_t)r.first_pass_total;
