@@ -35,3 +35,28 @@ def test_config2_golden_under_emulation(tmp_path, env):
     assert (int(line[3]), int(line[4])) == (g["unitigs_after"], g["links_after"])
     if "AC_DEVICE_SIMPLIFY" not in env:
         assert int(line[2]) == g["n_kmers"]
+
+
+MULTI_CODE = """
+import sys, hashlib, tempfile, os
+sys.path.insert(0, %(tests)r); sys.path.insert(0, %(root)r)
+from autocycler_b200 import api, synth
+lib = api.load_library(%(lib)r)
+with tempfile.TemporaryDirectory() as d:
+    synth.write_assemblies(synth.make_assemblies("cfg5", n_assemblies=16), d)
+    out = os.path.join(d, "out")
+    api.compress(d, out, k_size=51, lib=lib, devices=[0, 1])
+    print("SHA", hashlib.sha256(open(os.path.join(out, "input_assemblies.gfa"), "rb").read()).hexdigest())
+"""
+
+
+def test_config5_first_16_on_two_emulated_devices():
+    """The N = 2 workload of bench.py --gpus 2 (the first 16 assemblies of BASELINE config 5, 80 Mbp) through the sharded build at full
+    size — two emulated devices in one process, `autocycler compress --devices 0,1` — against the oracle's committed SHA-256; device
+    buffers poisoned before every table build.  About half a minute."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "autocycler_b200", "csrc"), "emu"], check=True)
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "config_goldens.json")))["cfg5_k51_n16"]
+    code = MULTI_CODE % {"tests": os.path.join(ROOT, "tests"), "root": ROOT, "lib": os.path.join(ROOT, "tests", "emu", "libautocycler_emu.so")}
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, "AC_EMU_POISON": "1"}, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert [l for l in r.stdout.splitlines() if l.startswith("SHA")][0].split()[1] == g["sha256"]
