@@ -79,7 +79,8 @@ def test_sharded_build_matches_oracle(tmp_path, world):
     port = str(29500 + (os.getpid() % 2000) + world)
     procs = []
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=port,
+                   AC_EMU_POISON="1")        # every device buffer a kernel writes is filled with a pattern before each table build: leftovers of the previous build on the handle cannot help
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
