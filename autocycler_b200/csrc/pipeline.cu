@@ -408,10 +408,6 @@ template <int W> struct BloomBuildBody {   // 32 filter bits per distinct k-mer,
 template <int W> struct AdjacencyBody {
     TableView t; KParams p; bool any_dotted; const uint32_t* occupied; uint8_t* flags8;   // one thread per OCCUPIED slot (full warps)
     const uint64_t* bloom; uint64_t n_words;
-    // Multi-GPU: only the k-mers of this rank's own windows need the flags (the boundary kernel reads them along the owned sequences and
-    // nothing else does).  The list is in coordinate order, so they are the stretch between the scanned claim counts of the words that
-    // hold the first and the last owned coordinate (a few foreign neighbours in those two words come along): range[w0] .. range[w1].
-    const uint32_t* range = nullptr; uint64_t w0 = 0, w1 = 0;
     // Is k-mer `a` in the table?  Almost every candidate neighbour is absent; the L2-resident Bloom filter answers that
     // without touching the table in HBM.
     AC_D bool present(const Key<W>& a, const Key<W>& arc) const {
@@ -421,7 +417,6 @@ template <int W> struct AdjacencyBody {
         return table_find<W>(t, a, arc, p) != AC_NONE32;
     }
     AC_D void operator()(uint64_t x) const {
-        if (range) { x += range[w0]; if (x >= range[w1]) return; }
         const uint64_t i = occupied[x];
         const Slot e = t.slots[i];
         const uint32_t aux = slot_flags(e);
@@ -452,6 +447,14 @@ template <int W> struct AdjacencyBody {
         if (in_c == 1 && !(aux & AC_AUX_FIRST_CANON)) bits |= AC_FLAG8_IN_OK;
         flags8[i] = (uint8_t)bits;                   // bit0 outOK, bit1 inOK (canonical orientation)
     }
+};
+// Multi-GPU: only the k-mers of this rank's own windows need the flags (the boundary kernel reads them along the owned sequences and
+// nothing else does).  The list is in coordinate order, so they are the stretch between the scanned claim counts of the words that
+// hold the first and the last owned coordinate (a few foreign neighbours in those two words come along): range[w0] .. range[w1].
+// A body of its own, so that the single-GPU kernel stays exactly what was measured.
+template <int W> struct AdjacencyOwnBody {
+    AdjacencyBody<W> all; const uint32_t* range; uint64_t w0, w1;
+    AC_D void operator()(uint64_t x) const { x += range[w0]; if (x < range[w1]) all(x); }
 };
 
 // Where the unitig occurrences start: bit j of word w set <=> an occurrence starts at coordinate 32w+j, i.e. it is window 0 of a
@@ -2219,15 +2222,12 @@ template <int W> void DevicePipeline::Impl::runs_local_w() {
     bloom.ensure(bloom_words * 8);
     ac_memset(bloom.p, 0, bloom_words * 8, &stream);
     ac_launch("bloom_build", &stream, BloomBuildBody<W>{tv, p, occ_list.as<uint32_t>(), bloom.as<uint64_t>(), bloom_words}, n_slots_used);
-    AdjacencyBody<W> adj{tv, p, any_dotted, occ_list.as<uint32_t>(), flags8.as<uint8_t>(), bloom.as<uint64_t>(), bloom_words};
-    uint64_t n_adj = n_slots_used;
+    const AdjacencyBody<W> adj{tv, p, any_dotted, occ_list.as<uint32_t>(), flags8.as<uint8_t>(), bloom.as<uint64_t>(), bloom_words};
     if (is_multi && exp_valid && exp_n + 64 < n_slots_used) {      // the merged table holds every rank's k-mers; this rank's own ones were listed (and counted) before the merge
-        const uint64_t n_cw = (total + 31) / 32;
-        adj.range = claimed_cnt.as<uint32_t>(); adj.w0 = g_begin >> 5; adj.w1 = std::min<uint64_t>((g_end + 31) >> 5, n_cw);
-        n_adj = exp_n + 64;
+        const uint64_t n_cw = (total + 31) / 32, n_adj = exp_n + 64;
         if (getenv("AC_HOST_PROFILE")) fprintf(stderr, "[device] adjacency flags for this rank's own k-mers: at most %llu of %llu\n", (unsigned long long)n_adj, (unsigned long long)n_slots_used);
-    }
-    ac_launch("adjacency", &stream, adj, n_adj);
+        ac_launch("adjacency", &stream, AdjacencyOwnBody<W>{adj, claimed_cnt.as<uint32_t>(), g_begin >> 5, std::min<uint64_t>((g_end + 31) >> 5, n_cw)}, n_adj);
+    } else ac_launch("adjacency", &stream, adj, n_slots_used);
     mark(5);
 
     const uint64_t n_bwords = (total + 31) / 32;
