@@ -350,7 +350,9 @@ def run_gpu(args):
         "roofline": {"kernel": "%s<%d> (k-mer hash insert)" % (INSERT_BODY, W), "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "peak_kind": peak_kind,
                      "traffic": measured_traffic("%s<%d>:%s:k%d" % (INSERT_BODY, W, args.workload, K)) if world == 1 else None,
-                     "limiter": "integer ALU pipe (70 % busy, issue slots 64 %; DRAM 18 %, L2 43 %: profiles/kernels_r2.md) - the kernel moves about its algorithmic bytes and is bound by the instructions that hash, probe and compare",
+                     "limiter": ("integer ALU pipe (70 % busy, issue slots 64 %; DRAM 18 %, L2 43 %: profiles/kernels_r2.md) - the kernel moves about its algorithmic bytes and is bound by the instructions that hash, probe and compare"
+                                 if t.table_capacity * 8 <= 126e6 else
+                                 "DRAM latency: the table (%.0f MB) exceeds the 126 MB L2, every probe and most comparisons are random 32-byte DRAM sectors (3.7 x the algorithmic bytes, DRAM busy 35 %, issue slots 37 %: profiles/kernels_r2.md, config 4)" % (t.table_capacity * 8 / 1e6)),
                      "algorithmic_bytes_per_window": bytes_per_window, "windows_per_launch": int(own_windows), "kernel_ms": round(insert_ms, 3),
                      "timed": "CUDA events right around the kernel's launch on the library's stream, mean over the timed steps (stage_ms.insert also holds the table initialisation and the counter read-back)",
                      "accounting": "SURVEY 8(d): 8W+16 bytes per canonical window insert; by DESIGN.md's own count (8W+20.25) achieved %.1f GB/s = %.4f of peak; %.4f of the nominal 8 TB/s"
